@@ -1,0 +1,100 @@
+"""ctypes binding of libhhfm_sm100.so (the C ABI declared in include/hhfm_sm100.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.  The product never
+routes through `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhhfm_sm100.so")
+
+i32, i64, f32, vp, cint = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_int
+
+# name -> argtypes; every function returns int except the three noted below
+SIGNATURES = {
+    "hhfm_pack_ids_i64": [vp, i64, i64, i64, vp, i64, i64, i64, cint],
+    "hhfm_pack_ids_i32": [vp, i64, i64, i64, vp, i64, i64, i64, cint],
+    "hhfm_pack_fill_i32": [vp, i64, i64, i64, i64, i32, cint],
+    "hhfm_pack_csr_i64": [vp, vp, i64, i64, i64, vp, vp, vp, i64, cint],
+    "hhfm_fm_fwd": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp],
+    "hhfm_fm_fwd_bwd_sqloss": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp,
+                               vp, i32, vp],
+    "hhfm_fm_bwd": [vp, vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, i32, vp],
+    "hhfm_pairrank_fwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
+    "hhfm_pairrank_fwd_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp,
+                              vp, i32, vp],
+    "hhfm_pairrank_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, i32, vp],
+    "hhfm_scatter_add_rows": [vp, vp, i64, i64, vp, i64, vp],
+    "hhfm_opt_adagrad_dense_l2": [vp, vp, vp, i64, f32, f32, i32, vp, vp],
+    "hhfm_opt_adam_dense_l2": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp],
+    "hhfm_opt_momentum_dense_l2": [vp, vp, vp, i64, f32, f32, f32, i32, vp, vp],
+    "hhfm_opt_sgd_dense_l2": [vp, vp, i64, f32, f32, i32, vp, vp],
+    "hhfm_opt_adagrad_rows": [vp, vp, vp, vp, vp, i64, i64, f32, i32, vp],
+    "hhfm_opt_momentum_rows": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp],
+    "hhfm_opt_sgd_rows": [vp, vp, vp, vp, i64, i64, f32, i32, vp],
+    "hhfm_loss_finalize": [vp, vp, f32, vp, vp],
+    "hhfm_topn_build_query": [i32, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
+    "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],
+    "hhfm_topn_select": [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp],
+    "hhfm_metrics_walk": [vp, vp, vp, i64, i32, i32, vp, vp],
+}
+OPTIONAL = {}   # symbols added by later kernels are appended by their modules via `declare`
+
+
+class HhfmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises HhfmError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HhfmError(
+            "libhhfm_sm100.so not found at %s -- build it with `python -m hhfm_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.hhfm_abi_version.restype = cint
+    lib.hhfm_abi_version.argtypes = []
+    lib.hhfm_last_error.restype = C.c_char_p
+    lib.hhfm_last_error.argtypes = []
+    lib.hhfm_partials_len.restype = i64
+    lib.hhfm_partials_len.argtypes = []
+    for name, args in list(SIGNATURES.items()) + list(OPTIONAL.items()):
+        fn = getattr(lib, name)
+        fn.restype = cint
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declare(name, argtypes):
+    """Register an additional entry point (used by modules that bind later-added kernels)."""
+    OPTIONAL[name] = argtypes
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype = cint
+        fn.argtypes = argtypes
+
+
+def call(name, *args):
+    """Invoke an entry point and raise HhfmError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise HhfmError("%s failed (%d): %s" % (name, rc, lib.hhfm_last_error().decode("utf-8", "replace")))
+
+
+def partials_len() -> int:
+    return int(load().hhfm_partials_len())
+
+
+def exported_symbols():
+    return ["hhfm_abi_version", "hhfm_last_error", "hhfm_partials_len"] + list(SIGNATURES) + list(OPTIONAL)

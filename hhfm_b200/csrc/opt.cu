@@ -1,0 +1,244 @@
+// K4 generic row scatter-add, K5 TF-1.x optimizers (dense-with-L2 and touched-rows variants), loss finalize.
+// Reference: tf.train.{Adagrad,Adam,Momentum,GradientDescent}Optimizer.minimize (FM.py:129-136, BPR.py:93,
+// MF.py:104).  TF kernels restated: ApplyAdagrad `accum += g*g; var -= lr*g*rsqrt(accum)` (no epsilon),
+// ApplyAdam with lr_t folded by the caller, ApplyMomentum `accum = accum*mu + g; var -= lr*accum`.
+// All kernels are pure streaming float4 passes (HBM-bound): read g,w,state -> write w,state,(g=0).
+#include "common.cuh"
+
+namespace hhfm {
+
+struct OptP {
+  float lr, lamda, p1, p2, p3;   // adam: p1=beta1 p2=beta2 p3=eps ; momentum: p1=mu
+};
+
+template <int KIND>
+__device__ __forceinline__ void opt_elem(float& w, float& s1, float& s2, float g, const OptP& p) {
+  if (KIND == HHFM_OPT_ADAGRAD) {
+    s1 = s1 + g * g;
+    w = w - p.lr * g / sqrtf(s1);
+  } else if (KIND == HHFM_OPT_ADAM) {
+    s1 = p.p1 * s1 + (1.f - p.p1) * g;
+    s2 = p.p2 * s2 + (1.f - p.p2) * (g * g);
+    w = w - p.lr * s1 / (sqrtf(s2) + p.p3);
+  } else if (KIND == HHFM_OPT_MOMENTUM) {
+    s1 = s1 * p.p1 + g;
+    w = w - p.lr * s1;
+  } else {
+    w = w - p.lr * g;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void opt_vec4(float4& w, float4& s1, float4& s2, float4 g, const OptP& p) {
+  opt_elem<KIND>(w.x, s1.x, s2.x, g.x, p);
+  opt_elem<KIND>(w.y, s1.y, s2.y, g.y, p);
+  opt_elem<KIND>(w.z, s1.z, s2.z, g.z, p);
+  opt_elem<KIND>(w.w, s1.w, s2.w, g.w, p);
+}
+
+// dense: n elements, g_eff = g + lamda*w.  Handles n % 4 != 0 with a scalar tail (bias vectors, scalars).
+template <int KIND>
+__global__ void __launch_bounds__(256) opt_dense_kernel(float* __restrict__ w, float* __restrict__ s1,
+                                                        float* __restrict__ s2, float* __restrict__ g, int64_t n,
+                                                        OptP p, int zero_grad, float* sq_partials) {
+  __shared__ float scratch[32];
+  const int64_t n4 = n >> 2;
+  float sq = 0.f;
+  float4* w4 = reinterpret_cast<float4*>(w);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* a4 = reinterpret_cast<float4*>(s1);
+  float4* b4 = reinterpret_cast<float4*>(s2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 wv = w4[i], gv = g4[i];
+    float4 av = (KIND != HHFM_OPT_SGD) ? a4[i] : f4_zero();
+    float4 bv = (KIND == HHFM_OPT_ADAM) ? b4[i] : f4_zero();
+    sq += f4_dot(wv, wv);
+    gv = f4_fma(wv, p.lamda, gv);
+    opt_vec4<KIND>(wv, av, bv, gv, p);
+    w4[i] = wv;
+    if (KIND != HHFM_OPT_SGD) a4[i] = av;
+    if (KIND == HHFM_OPT_ADAM) b4[i] = bv;
+    if (zero_grad) g4[i] = f4_zero();
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float wv = w[i], gv = g[i];
+    float av = (KIND != HHFM_OPT_SGD) ? s1[i] : 0.f;
+    float bv = (KIND == HHFM_OPT_ADAM) ? s2[i] : 0.f;
+    sq += wv * wv;
+    gv = fmaf(wv, p.lamda, gv);
+    opt_elem<KIND>(wv, av, bv, gv, p);
+    w[i] = wv;
+    if (KIND != HHFM_OPT_SGD) s1[i] = av;
+    if (KIND == HHFM_OPT_ADAM) s2[i] = bv;
+    if (zero_grad) g[i] = 0.f;
+  }
+  if (sq_partials != nullptr) {
+    const float b = block_sum(sq, scratch);
+    write_partial(sq_partials, b);
+  }
+}
+
+// rows: only rows[0 .. *n_rows) move (TF SparseApply*), K elements each; K % 4 == 0 or K == 1.
+template <int KIND>
+__global__ void __launch_bounds__(256) opt_rows_kernel(float* __restrict__ w, float* __restrict__ s1,
+                                                       float* __restrict__ g, const int32_t* __restrict__ rows,
+                                                       const int32_t* __restrict__ n_rows_dev, int K, OptP p,
+                                                       int zero_grad) {
+  const int n_rows = *n_rows_dev;
+  float dummy = 0.f;
+  if (K == 1) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = rows[i];
+      float wv = w[r], gv = g[r], av = (KIND != HHFM_OPT_SGD) ? s1[r] : 0.f;
+      opt_elem<KIND>(wv, av, dummy, gv, p);
+      w[r] = wv;
+      if (KIND != HHFM_OPT_SGD) s1[r] = av;
+      if (zero_grad) g[r] = 0.f;
+    }
+    return;
+  }
+  const int kv = K >> 2;
+  const int64_t total = (int64_t)n_rows * kv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = rows[i / kv];
+    const int64_t off = (int64_t)r * kv + (i % kv);
+    float4 wv = reinterpret_cast<float4*>(w)[off], gv = reinterpret_cast<float4*>(g)[off];
+    float4 av = (KIND != HHFM_OPT_SGD) ? reinterpret_cast<float4*>(s1)[off] : f4_zero();
+    float4 bv = f4_zero();
+    opt_vec4<KIND>(wv, av, bv, gv, p);
+    reinterpret_cast<float4*>(w)[off] = wv;
+    if (KIND != HHFM_OPT_SGD) reinterpret_cast<float4*>(s1)[off] = av;
+    if (zero_grad) reinterpret_cast<float4*>(g)[off] = f4_zero();
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t* __restrict__ rows, const float* __restrict__ src,
+                                                           int64_t n, int K, float* __restrict__ dst) {
+  const int kv = K >> 2;
+  const int64_t total = n * kv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kv;
+    const int c = (int)(i % kv);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    red_add_v4(dst + (size_t)__ldg(rows + r) * K + 4 * c, v);
+  }
+}
+
+__global__ void scatter_scalar_kernel(const int32_t* __restrict__ rows, const float* __restrict__ src, int64_t n,
+                                      float* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(dst + __ldg(rows + i), __ldg(src + i));
+}
+
+// loss = sum(loss_partials) + half_lamda * sum(sq_partials): one warp, fixed order -> deterministic.
+__global__ void loss_finalize_kernel(const float* __restrict__ lp, const float* __restrict__ sp, float half_lamda,
+                                     float* __restrict__ out) {
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < kPartials; i += 32) {
+    a += lp[i];
+    if (sp) b += sp[i];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (threadIdx.x == 0) out[0] = a + half_lamda * b;
+}
+
+static int dense_grid(int64_t n) {
+  int64_t need = ((n >> 2) + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kPartials) cap = kPartials;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+template <int KIND>
+static int launch_dense(float* w, float* s1, float* s2, float* g, int64_t n, OptP p, int zero_grad, float* sq_partials,
+                        cudaStream_t st) {
+  HHFM_REQUIRE(w && g && n > 0, "opt_dense: w, g required and n > 0");
+  HHFM_REQUIRE(KIND == HHFM_OPT_SGD || s1, "opt_dense: optimizer state is NULL");
+  HHFM_REQUIRE(KIND != HHFM_OPT_ADAM || s2, "opt_dense: adam needs two state buffers");
+  HHFM_REQUIRE((((uintptr_t)w | (uintptr_t)g | (uintptr_t)s1 | (uintptr_t)s2) & 15) == 0 || n < 4,
+               "opt_dense: buffers must be 16-byte aligned");
+  opt_dense_kernel<KIND><<<dense_grid(n), 256, 0, st>>>(w, s1, s2, g, n, p, zero_grad, sq_partials);
+  return check_launch("opt_dense_kernel");
+}
+
+template <int KIND>
+static int launch_rows(float* w, float* s1, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
+                       int64_t K, OptP p, int zero_grad, cudaStream_t st) {
+  HHFM_REQUIRE(w && g && rows && n_rows_dev, "opt_rows: w, g, rows, n_rows_dev required");
+  HHFM_REQUIRE(KIND == HHFM_OPT_SGD || s1, "opt_rows: optimizer state is NULL");
+  HHFM_REQUIRE(K == 1 || (K % 4 == 0 && K > 0), "opt_rows: K must be 1 or a multiple of 4");
+  HHFM_REQUIRE(max_rows > 0, "opt_rows: max_rows must be > 0");
+  int64_t work = K == 1 ? max_rows : max_rows * (K >> 2);
+  int64_t need = (work + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  int grid = (int)(need < cap ? need : cap);
+  if (grid < 1) grid = 1;
+  opt_rows_kernel<KIND><<<grid, 256, 0, st>>>(w, s1, g, rows, n_rows_dev, (int)K, p, zero_grad);
+  return check_launch("opt_rows_kernel");
+}
+
+}  // namespace hhfm
+
+using namespace hhfm;
+
+extern "C" int hhfm_opt_adagrad_dense_l2(float* w, float* acc, float* g, int64_t n, float lr, float lamda,
+                                         int32_t zero_grad, float* sq_partials, hhfm_stream_t stream) {
+  OptP p{lr, lamda, 0.f, 0.f, 0.f};
+  return launch_dense<HHFM_OPT_ADAGRAD>(w, acc, nullptr, g, n, p, zero_grad, sq_partials, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_adam_dense_l2(float* w, float* m, float* v, float* g, int64_t n, float lr_t, float beta1,
+                                      float beta2, float eps, float lamda, int32_t zero_grad, float* sq_partials,
+                                      hhfm_stream_t stream) {
+  OptP p{lr_t, lamda, beta1, beta2, eps};
+  return launch_dense<HHFM_OPT_ADAM>(w, m, v, g, n, p, zero_grad, sq_partials, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_momentum_dense_l2(float* w, float* acc, float* g, int64_t n, float lr, float momentum,
+                                          float lamda, int32_t zero_grad, float* sq_partials, hhfm_stream_t stream) {
+  OptP p{lr, lamda, momentum, 0.f, 0.f};
+  return launch_dense<HHFM_OPT_MOMENTUM>(w, acc, nullptr, g, n, p, zero_grad, sq_partials, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_sgd_dense_l2(float* w, float* g, int64_t n, float lr, float lamda, int32_t zero_grad,
+                                     float* sq_partials, hhfm_stream_t stream) {
+  OptP p{lr, lamda, 0.f, 0.f, 0.f};
+  return launch_dense<HHFM_OPT_SGD>(w, nullptr, nullptr, g, n, p, zero_grad, sq_partials, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_adagrad_rows(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev,
+                                     int64_t max_rows, int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream) {
+  OptP p{lr, 0.f, 0.f, 0.f, 0.f};
+  return launch_rows<HHFM_OPT_ADAGRAD>(w, acc, g, rows, n_rows_dev, max_rows, K, p, zero_grad, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_momentum_rows(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev,
+                                      int64_t max_rows, int64_t K, float lr, float momentum, int32_t zero_grad,
+                                      hhfm_stream_t stream) {
+  OptP p{lr, 0.f, momentum, 0.f, 0.f};
+  return launch_rows<HHFM_OPT_MOMENTUM>(w, acc, g, rows, n_rows_dev, max_rows, K, p, zero_grad, (cudaStream_t)stream);
+}
+extern "C" int hhfm_opt_sgd_rows(float* w, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
+                                 int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream) {
+  OptP p{lr, 0.f, 0.f, 0.f, 0.f};
+  return launch_rows<HHFM_OPT_SGD>(w, nullptr, g, rows, n_rows_dev, max_rows, K, p, zero_grad, (cudaStream_t)stream);
+}
+
+extern "C" int hhfm_scatter_add_rows(const int32_t* rows, const float* src, int64_t n, int64_t K, float* dst, int64_t M,
+                                     hhfm_stream_t stream) {
+  HHFM_REQUIRE(rows && src && dst && M > 0, "scatter_add_rows: NULL argument");
+  HHFM_REQUIRE(K == 1 || (K > 0 && K % 4 == 0), "scatter_add_rows: K must be 1 or a multiple of 4");
+  if (n == 0) return HHFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t work = K == 1 ? n : n * (K >> 2);
+  int64_t need = (work + 255) / 256, cap = (int64_t)sm_count() * 8;
+  int grid = (int)(need < cap ? need : cap);
+  if (K == 1) scatter_scalar_kernel<<<grid, 256, 0, st>>>(rows, src, n, dst);
+  else scatter_rows_kernel<<<grid, 256, 0, st>>>(rows, src, n, (int)K, dst);
+  return check_launch("scatter_rows_kernel");
+}
+
+extern "C" int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, float half_lamda, float* loss_out,
+                                  hhfm_stream_t stream) {
+  HHFM_REQUIRE(loss_partials && loss_out, "loss_finalize: NULL argument");
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, sq_partials, half_lamda, loss_out);
+  return check_launch("loss_finalize_kernel");
+}

@@ -1,0 +1,390 @@
+// K3: HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88) pairwise ranking with max-negative, fused:
+// group pooling -> hybrid feature -> positive / negative dots -> reduce_max -> -log(sigmoid) -> gradients ->
+// sort-free scatter (REDG.E.ADD.F32x4).  Same lane mapping as fm.cu: LPS = K/4 lanes own one sample.
+//
+// Record (int32, `stride` ints, 16-byte aligned): [user, item+, ctx.., time.., neg.., pad].
+#include "common.cuh"
+
+namespace hhfm {
+
+struct PrArgs {
+  const int32_t* idx;
+  int64_t B;
+  int stride;
+  int n_ctx, n_time, n_neg;
+  int pc, pt, pf;
+  const float* V;
+  int K;
+  float* pos_out;
+  float* neg_out;
+  const float* dpos;
+  const float* dneg;
+  float* gV;
+  float* loss_partials;
+  int32_t* touch_stamp;
+  int32_t stamp;
+  int32_t* touched_rows;
+  int32_t* touched_count;
+  int groups_active;
+};
+
+enum { PR_FWD = 0, PR_TRAIN = 1, PR_BWD = 2 };
+
+// Pool n rows V[ids[0..n)] element-wise (OurModel7.py:124/141 Pooling1C/Pooling1T over axis=1).
+// MAX keeps the per-element tie count for the reduce_max gradient.  Rows are combined in id order.
+template <int LPS, int VPL, bool ANYMAX>
+__device__ __forceinline__ void pool_rows(const float* __restrict__ V, const int32_t* __restrict__ ids, int n, int mode,
+                                          int K, int lg, Frag<LPS, VPL>& out, Frag<LPS, VPL>& cnt) {
+  using F4 = Frag<LPS, VPL>;
+  frag_zero(out);
+  if (ANYMAX) frag_zero(cnt);
+  for (int j = 0; j < n; j += 4) {
+    int id[4];
+    F4 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) id[u] = (j + u < n) ? __ldg(ids + j + u) : -1;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (id[u] >= 0) frag_load(e[u], V, id[u], K, lg);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (id[u] < 0) continue;
+      if (ANYMAX && mode == HHFM_POOL_MAX) {
+        const bool first = (j + u) == 0;
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+          float* o = reinterpret_cast<float*>(&out.v[i]);
+          float* c = reinterpret_cast<float*>(&cnt.v[i]);
+          const float* x = reinterpret_cast<const float*>(&e[u].v[i]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (first || x[q] > o[q]) { o[q] = x[q]; c[q] = 1.f; }
+            else if (x[q] == o[q]) c[q] += 1.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VPL; i++) out.v[i] = f4_add(out.v[i], e[u].v[i]);
+      }
+    }
+  }
+  if (mode == HHFM_POOL_MEAN) {
+    const float fn = (float)n;
+#pragma unroll
+    for (int i = 0; i < VPL; i++)
+      out.v[i] = make_float4(out.v[i].x / fn, out.v[i].y / fn, out.v[i].z / fn, out.v[i].w / fn);
+  }
+}
+
+// Scatter the gradient d of a pooled vector back to its n member rows.
+template <int LPS, int VPL, bool ANYMAX>
+__device__ __forceinline__ void pool_rows_bwd(const PrArgs& a, const int32_t* __restrict__ ids, int n, int mode, int lg,
+                                              const Frag<LPS, VPL>& pooled, const Frag<LPS, VPL>& cnt,
+                                              const Frag<LPS, VPL>& d) {
+  using F4 = Frag<LPS, VPL>;
+  const int K = a.K;
+  F4 dm = d;
+  if (mode == HHFM_POOL_MEAN) {
+    const float fn = (float)n;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) dm.v[i] = make_float4(d.v[i].x / fn, d.v[i].y / fn, d.v[i].z / fn, d.v[i].w / fn);
+  }
+  for (int j = 0; j < n; j++) {
+    const int id = __ldg(ids + j);
+    if (ANYMAX && mode == HHFM_POOL_MAX) {
+      F4 e, r;
+      frag_load(e, a.V, id, K, lg);
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const float* x = reinterpret_cast<const float*>(&e.v[i]);
+        const float* o = reinterpret_cast<const float*>(&pooled.v[i]);
+        const float* c = reinterpret_cast<const float*>(&cnt.v[i]);
+        const float* dd = reinterpret_cast<const float*>(&d.v[i]);
+        float* rr = reinterpret_cast<float*>(&r.v[i]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) rr[q] = (x[q] == o[q]) ? (1.f / c[q]) * dd[q] : 0.f;
+      }
+      frag_red<LPS, VPL>(a.gV, id, K, lg, r);
+    } else {
+      frag_red<LPS, VPL>(a.gV, id, K, lg, dm);
+    }
+    if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
+  }
+}
+
+template <int LPS, int VPL, int MODE, bool ANYMAX>
+__global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
+  __shared__ float scratch[32];
+  using F4 = Frag<LPS, VPL>;
+  const int lane = threadIdx.x & 31, lg = lane % LPS, grp = lane / LPS;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int ga = a.groups_active;
+  const int K = a.K;
+  const int num = 1 + (a.n_ctx > 0) + (a.n_time > 0);   // OurModel7.py:89,94 self.num
+  float loss_acc = 0.f;
+
+  for (int64_t s0 = warp_g * ga; s0 < a.B; s0 += n_warps * ga) {
+    const int64_t s = s0 + grp;
+    const bool valid = (grp < ga) && (s < a.B);
+    const int64_t sc = valid ? s : (a.B - 1);   // padding groups recompute the last sample, never write
+    const int32_t* rec = a.idx + sc * a.stride;
+    const int uid = __ldg(rec + 0), pid = __ldg(rec + 1);
+    const int32_t* ctx = rec + 2;
+    const int32_t* tim = ctx + a.n_ctx;
+    const int32_t* neg = tim + a.n_time;
+
+    // ---- forward: hybrid feature (OurModel7.py:105-168) ----
+    F4 eu, vp, C, cC, T, cT, hyb, cF;
+    frag_load(eu, a.V, uid, K, lg);
+    frag_load(vp, a.V, pid, K, lg);
+    frag_zero(C); frag_zero(T);
+    if (ANYMAX) { frag_zero(cC); frag_zero(cT); frag_zero(cF); }
+    if (a.n_ctx > 0) pool_rows<LPS, VPL, ANYMAX>(a.V, ctx, a.n_ctx, a.pc, K, lg, C, cC);
+    if (a.n_time > 0) pool_rows<LPS, VPL, ANYMAX>(a.V, tim, a.n_time, a.pt, K, lg, T, cT);
+    if (num == 1) {
+      hyb = eu;
+    } else if (ANYMAX && a.pf == HHFM_POOL_MAX) {
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const float* xu = reinterpret_cast<const float*>(&eu.v[i]);
+        const float* xc = reinterpret_cast<const float*>(&C.v[i]);
+        const float* xt = reinterpret_cast<const float*>(&T.v[i]);
+        float* o = reinterpret_cast<float*>(&hyb.v[i]);
+        float* c = reinterpret_cast<float*>(&cF.v[i]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          float m = xu[q], n_ = 1.f;
+          if (a.n_ctx > 0) { if (xc[q] > m) { m = xc[q]; n_ = 1.f; } else if (xc[q] == m) n_ += 1.f; }
+          if (a.n_time > 0) { if (xt[q] > m) { m = xt[q]; n_ = 1.f; } else if (xt[q] == m) n_ += 1.f; }
+          o[q] = m; c[q] = n_;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        float4 h = eu.v[i];
+        if (a.n_ctx > 0) h = f4_add(h, C.v[i]);
+        if (a.n_time > 0) h = f4_add(h, T.v[i]);
+        if (a.pf == HHFM_POOL_MEAN) { const float fn = (float)num; h = make_float4(h.x / fn, h.y / fn, h.z / fn, h.w / fn); }
+        hyb.v[i] = h;
+      }
+    }
+
+    // ---- scores: OurModel7.py:171-174 / BPR.py:79-81 ----
+    const float pos = group_sum<LPS>(frag_dot(hyb, vp));
+    float m = -INFINITY;
+    unsigned long long tie = 0ull;    // bit j set <=> neg_j equals the running max
+    for (int j = 0; j < a.n_neg; j += 4) {
+      int id[4];
+      F4 e[4];
+      float p[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) id[u] = (j + u < a.n_neg) ? __ldg(neg + j + u) : -1;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (id[u] >= 0) frag_load(e[u], a.V, id[u], K, lg);
+#pragma unroll
+      for (int u = 0; u < 4; u++) p[u] = (id[u] >= 0) ? frag_dot(hyb, e[u]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; u++) p[u] = group_sum<LPS>(p[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (id[u] < 0) continue;
+        if (p[u] > m) { m = p[u]; tie = 1ull << (j + u); }
+        else if (p[u] == m) tie |= 1ull << (j + u);
+        if (a.neg_out && valid && lg == 0) a.neg_out[s * a.n_neg + j + u] = p[u];
+      }
+    }
+    if (a.pos_out && valid && lg == 0) a.pos_out[s] = pos;
+
+    if (MODE != PR_FWD && valid) {
+      // ---- loss and d loss / d scores ----
+      float gp = 0.f, gn = 0.f;   // d/dpos, d/d(each tied max negative)
+      if (MODE == PR_TRAIN) {
+        const float x = pos - m;
+        const float sg = 1.f / (1.f + expf(-x));            // tf.sigmoid
+        if (lg == 0) loss_acc += -logf(sg);                  // OurModel7.py:178
+        gp = sg - 1.f;                                       // d(-log sigmoid(x))/dx
+        gn = -gp / (float)__popcll(tie);                     // reduce_max grad split among ties
+      } else {
+        gp = __ldg(a.dpos + s);
+      }
+      // d hyb = gp*v+ + sum_j gn_j*v_j ;  gV[item+] += gp*hyb ; gV[neg_j] += gn_j*hyb
+      F4 dh, t;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) { dh.v[i] = f4_scale(vp.v[i], gp); t.v[i] = f4_scale(hyb.v[i], gp); }
+      frag_red<LPS, VPL>(a.gV, pid, K, lg, t);
+      if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, pid);
+      if (MODE == PR_TRAIN) {
+        unsigned long long w = tie;
+        while (w) {
+          const int j = __ffsll((long long)w) - 1;
+          w &= w - 1;
+          const int id = __ldg(neg + j);
+          F4 e;
+          frag_load(e, a.V, id, K, lg);
+#pragma unroll
+          for (int i = 0; i < VPL; i++) { dh.v[i] = f4_fma(e.v[i], gn, dh.v[i]); t.v[i] = f4_scale(hyb.v[i], gn); }
+          frag_red<LPS, VPL>(a.gV, id, K, lg, t);
+          if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
+        }
+      } else if (a.dneg != nullptr) {
+        for (int j = 0; j < a.n_neg; j++) {
+          const float c = __ldg(a.dneg + s * a.n_neg + j);
+          const int id = __ldg(neg + j);
+          F4 e;
+          frag_load(e, a.V, id, K, lg);
+#pragma unroll
+          for (int i = 0; i < VPL; i++) { dh.v[i] = f4_fma(e.v[i], c, dh.v[i]); t.v[i] = f4_scale(hyb.v[i], c); }
+          frag_red<LPS, VPL>(a.gV, id, K, lg, t);
+          if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
+        }
+      }
+      // ---- back through Pooling1F over stack[user, C, T] ----
+      F4 du = dh, dC = dh, dT = dh;
+      if (num > 1) {
+        if (ANYMAX && a.pf == HHFM_POOL_MAX) {
+#pragma unroll
+          for (int i = 0; i < VPL; i++) {
+            const float* h = reinterpret_cast<const float*>(&hyb.v[i]);
+            const float* c = reinterpret_cast<const float*>(&cF.v[i]);
+            const float* d = reinterpret_cast<const float*>(&dh.v[i]);
+            const float* xu = reinterpret_cast<const float*>(&eu.v[i]);
+            const float* xc = reinterpret_cast<const float*>(&C.v[i]);
+            const float* xt = reinterpret_cast<const float*>(&T.v[i]);
+            float* ou = reinterpret_cast<float*>(&du.v[i]);
+            float* oc = reinterpret_cast<float*>(&dC.v[i]);
+            float* ot = reinterpret_cast<float*>(&dT.v[i]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float share = (1.f / c[q]) * d[q];
+              ou[q] = (xu[q] == h[q]) ? share : 0.f;
+              oc[q] = (xc[q] == h[q]) ? share : 0.f;
+              ot[q] = (xt[q] == h[q]) ? share : 0.f;
+            }
+          }
+        } else if (a.pf == HHFM_POOL_MEAN) {
+          const float fn = (float)num;
+#pragma unroll
+          for (int i = 0; i < VPL; i++) {
+            du.v[i] = make_float4(dh.v[i].x / fn, dh.v[i].y / fn, dh.v[i].z / fn, dh.v[i].w / fn);
+            dC.v[i] = du.v[i];
+            dT.v[i] = du.v[i];
+          }
+        }
+      }
+      frag_red<LPS, VPL>(a.gV, uid, K, lg, du);
+      if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, uid);
+      if (a.n_ctx > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, ctx, a.n_ctx, a.pc, lg, C, cC, dC);
+      if (a.n_time > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, tim, a.n_time, a.pt, lg, T, cT, dT);
+    }
+  }
+
+  if (MODE == PR_TRAIN) {
+    const float bl = block_sum(loss_acc, scratch);
+    write_partial(a.loss_partials, bl);
+  }
+}
+
+template <int LPS, int VPL, int MODE, bool ANYMAX>
+static int launch_pr(const PrArgs& a, int deterministic, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairrank_kernel<LPS, VPL, MODE, ANYMAX>, kBlock, 0);
+    if (occ < 1) occ = 1;
+  }
+  PrArgs b = a;
+  constexpr int G = 32 / LPS;
+  if (deterministic) {
+    b.groups_active = 1;
+    pairrank_kernel<LPS, VPL, MODE, ANYMAX><<<1, 32, 0, st>>>(b);
+  } else {
+    b.groups_active = G;
+    const int grid = grid_for(a.B, (kBlock / 32) * G, occ);
+    pairrank_kernel<LPS, VPL, MODE, ANYMAX><<<grid, kBlock, 0, st>>>(b);
+  }
+  return check_launch("pairrank_kernel");
+}
+
+template <int MODE>
+static int dispatch_pr(const PrArgs& a, int deterministic, cudaStream_t st) {
+  const bool anymax = (a.n_ctx > 0 && a.pc == HHFM_POOL_MAX) || (a.n_time > 0 && a.pt == HHFM_POOL_MAX) ||
+                      ((a.n_ctx > 0 || a.n_time > 0) && a.pf == HHFM_POOL_MAX);
+  if (anymax) {
+#define CALL(L, V) return launch_pr<L, V, MODE, true>(a, deterministic, st)
+    HHFM_DISPATCH_K(a.K, CALL);
+#undef CALL
+  } else {
+#define CALL(L, V) return launch_pr<L, V, MODE, false>(a, deterministic, st)
+    HHFM_DISPATCH_K(a.K, CALL);
+#undef CALL
+  }
+  return HHFM_ERR_UNSUPPORTED;
+}
+
+static int check_pr(const int32_t* idx, int64_t B, int64_t stride, int n_ctx, int n_time, int n_neg, int pc, int pt,
+                    int pf, const float* V, int64_t M, int64_t K) {
+  HHFM_REQUIRE(idx && V, "pairrank: idx and V must not be NULL");
+  HHFM_REQUIRE(B >= 0 && M > 0, "pairrank: bad sizes");
+  HHFM_REQUIRE(K > 0 && K % 4 == 0 && K <= 512, "pairrank: K=%lld unsupported (need K %% 4 == 0, K <= 512)", (long long)K);
+  HHFM_REQUIRE(n_ctx >= 0 && n_time >= 0 && n_neg >= 0 && n_neg <= 64, "pairrank: need 0 <= n_neg <= 64, n_ctx,n_time >= 0");
+  HHFM_REQUIRE(stride >= 2 + n_ctx + n_time + n_neg && stride % 4 == 0, "pairrank: stride %lld too small or not a multiple of 4", (long long)stride);
+  HHFM_REQUIRE(pc >= 0 && pc <= 2 && pt >= 0 && pt <= 2 && pf >= 0 && pf <= 2, "pairrank: bad pool mode");
+  HHFM_REQUIRE(((uintptr_t)V & 15) == 0 && ((uintptr_t)idx & 15) == 0, "pairrank: V and idx must be 16-byte aligned");
+  return HHFM_OK;
+}
+
+static PrArgs make_args(const int32_t* idx, int64_t B, int64_t stride, int n_ctx, int n_time, int n_neg, int pc, int pt,
+                        int pf, const float* V, int64_t K) {
+  PrArgs a{};
+  a.idx = idx; a.B = B; a.stride = (int)stride; a.n_ctx = n_ctx; a.n_time = n_time; a.n_neg = n_neg;
+  a.pc = pc; a.pt = pt; a.pf = pf; a.V = V; a.K = (int)K;
+  return a;
+}
+
+}  // namespace hhfm
+
+using namespace hhfm;
+
+extern "C" int hhfm_pairrank_fwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time,
+                                 int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V,
+                                 int64_t M, int64_t K, float* pos_out, float* neg_out, hhfm_stream_t stream) {
+  int rc = check_pr(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, M, K);
+  if (rc) return rc;
+  HHFM_REQUIRE(pos_out != nullptr, "pairrank_fwd: pos_out is NULL");
+  if (B == 0) return HHFM_OK;
+  PrArgs a = make_args(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, K);
+  a.pos_out = pos_out; a.neg_out = neg_out;
+  return dispatch_pr<PR_FWD>(a, 0, (cudaStream_t)stream);
+}
+
+extern "C" int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time,
+                                     int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack,
+                                     const float* V, int64_t M, int64_t K, float* pos_out, float* neg_out, float* gV,
+                                     float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
+                                     int32_t* touched_count, int32_t deterministic, hhfm_stream_t stream) {
+  int rc = check_pr(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, M, K);
+  if (rc) return rc;
+  HHFM_REQUIRE(B > 0 && n_neg >= 1, "pairrank_fwd_bwd: needs B > 0 and at least one negative");
+  HHFM_REQUIRE(gV && loss_partials, "pairrank_fwd_bwd: gV and loss_partials are required");
+  HHFM_REQUIRE(!touch_stamp || (touched_rows && touched_count), "pairrank_fwd_bwd: touch_stamp needs touched_rows/count");
+  HHFM_REQUIRE(((uintptr_t)gV & 15) == 0, "pairrank: gV must be 16-byte aligned");
+  PrArgs a = make_args(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, K);
+  a.pos_out = pos_out; a.neg_out = neg_out; a.gV = gV; a.loss_partials = loss_partials;
+  a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows; a.touched_count = touched_count;
+  return dispatch_pr<PR_TRAIN>(a, deterministic, (cudaStream_t)stream);
+}
+
+extern "C" int hhfm_pairrank_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time,
+                                 int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V,
+                                 int64_t M, int64_t K, const float* dpos, const float* dneg, float* gV,
+                                 int32_t deterministic, hhfm_stream_t stream) {
+  int rc = check_pr(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, M, K);
+  if (rc) return rc;
+  HHFM_REQUIRE(dpos && gV, "pairrank_bwd: dpos and gV are required");
+  if (B == 0) return HHFM_OK;
+  PrArgs a = make_args(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, K);
+  a.dpos = dpos; a.dneg = dneg; a.gV = gV;
+  return dispatch_pr<PR_BWD>(a, deterministic, (cudaStream_t)stream);
+}

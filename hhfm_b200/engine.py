@@ -1,0 +1,281 @@
+"""Host-side plumbing between the reference-shaped Python API and the C ABI (libhhfm_sm100.so).
+
+PyTorch is used for device memory, streams and torch.distributed only; every arithmetic step of the hot path
+is a hand-written sm_100a kernel behind `include/hhfm_sm100.h`.  Nothing here falls back to CPU math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+POOL_SUM, POOL_MAX, POOL_MEAN = 0, 1, 2
+QUERY_USER, QUERY_FM, QUERY_HHFM = 0, 1, 2
+_NTHREADS = int(os.environ.get("HHFM_PACK_THREADS", "0"))   # 0 = hardware concurrency
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.HhfmError("hhfm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _lib.load()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (or numpy array) as c_void_p; None -> NULL."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------------
+# K0: batch packing into pinned staging buffers
+# --------------------------------------------------------------------------------------------------
+class Staging:
+    """Growable pinned-host + device buffer pair for one kind of batch record (int32 or float32)."""
+
+    def __init__(self, dtype, device=None):
+        self.dtype = dtype
+        self.device = device
+        self.host = None
+        self.dev = None
+
+    def ensure(self, numel):
+        if self.host is None or self.host.numel() < numel:
+            cap = max(numel, 1024)
+            pin = torch.cuda.is_available()
+            self.host = torch.empty(cap, dtype=self.dtype, pin_memory=pin)
+            if self.device is not None:
+                self.dev = torch.empty(cap, dtype=self.dtype, device=self.device)
+        return self.host[:numel]
+
+    def upload(self, numel):
+        """Asynchronous H2D of the first `numel` elements on the current stream."""
+        self.dev[:numel].copy_(self.host[:numel], non_blocking=True)
+        return self.dev[:numel]
+
+
+def _as_2d_ids(a):
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.dtype not in (np.int64, np.int32):
+        if not np.issubdtype(a.dtype, np.integer):
+            # the reference feeds float ndarrays holding integral ids in places (DataFrame.values)
+            a = a.astype(np.int64)
+        else:
+            a = a.astype(np.int64)
+    if a.strides[1] != a.itemsize:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def pack_ids_into(dst_host, dst_stride, dst_col0, src, id_limit):
+    """Narrow an [rows, cols] id array into columns [dst_col0, dst_col0+cols) of int32 records."""
+    src = _as_2d_ids(src)
+    rows, cols = src.shape
+    if cols == 0:
+        return 0
+    fn = "hhfm_pack_ids_i64" if src.dtype == np.int64 else "hhfm_pack_ids_i32"
+    _lib.call(fn, ptr(src), rows, cols, src.strides[0] // src.itemsize, ptr(dst_host), dst_stride, dst_col0,
+              id_limit, _NTHREADS)
+    return cols
+
+
+def pack_records(parts, id_limit, staging: Staging, align=4):
+    """Concatenate id blocks column-wise into one [B, stride] int32 record buffer (stride % align == 0, padding
+    = -1).  Returns (host_view [B,stride], stride)."""
+    parts = [_as_2d_ids(p) for p in parts if p is not None]
+    B = parts[0].shape[0]
+    for p in parts:
+        if p.shape[0] != B:
+            raise ValueError("pack_records: blocks disagree on the number of rows")
+    width = sum(p.shape[1] for p in parts)
+    stride = _round_up(max(width, 1), align)
+    host = staging.ensure(B * stride)
+    col = 0
+    for p in parts:
+        col += pack_ids_into(host, stride, col, p, id_limit)
+    if stride > width:
+        _lib.call("hhfm_pack_fill_i32", ptr(host), B, stride - width, stride, width, -1, _NTHREADS)
+    return host.view(B, stride), stride
+
+
+# --------------------------------------------------------------------------------------------------
+# K5: optimizers with TF-1.x semantics
+# --------------------------------------------------------------------------------------------------
+class Optimizer:
+    """tf.train.{Adagrad,Adam,Momentum,GradientDescent}Optimizer (FM.py:129-136) over device tensors."""
+
+    KINDS = {"AdagradOptimizer": "adagrad", "AdamOptimizer": "adam", "MomentumOptimizer": "momentum",
+             "GradientDescentOptimizer": "sgd"}
+
+    def __init__(self, optimizer_type, learning_rate, initial_accumulator_value=0.1, momentum=0.95, beta1=0.9,
+                 beta2=0.999, epsilon=1e-8):
+        if optimizer_type not in self.KINDS:
+            raise ValueError("unknown optimizer_type %r" % (optimizer_type,))
+        self.kind = self.KINDS[optimizer_type]
+        self.lr = float(learning_rate)
+        self.acc0 = float(initial_accumulator_value)
+        self.momentum = float(momentum)
+        self.beta1, self.beta2, self.eps = float(beta1), float(beta2), float(epsilon)
+        self.t = 0
+        self.state = {}
+
+    def slots(self, name, w):
+        if name not in self.state:
+            if self.kind == "adagrad":
+                self.state[name] = (torch.full_like(w, self.acc0), None)
+            elif self.kind == "adam":
+                self.state[name] = (torch.zeros_like(w), torch.zeros_like(w))
+            elif self.kind == "momentum":
+                self.state[name] = (torch.zeros_like(w), None)
+            else:
+                self.state[name] = (None, None)
+        return self.state[name]
+
+    def begin_step(self):
+        self.t += 1
+
+    def _lr_t(self):
+        return self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+    def apply_dense(self, name, w, g, lamda=0.0, sq_partials=None, zero_grad=True):
+        """Dense update of every element with g_eff = g + lamda*w (aggregated dense gradient)."""
+        s1, s2 = self.slots(name, w)
+        n = w.numel()
+        z = 1 if zero_grad else 0
+        st = cur_stream()
+        if self.kind == "adagrad":
+            _lib.call("hhfm_opt_adagrad_dense_l2", ptr(w), ptr(s1), ptr(g), n, self.lr, lamda, z, ptr(sq_partials), st)
+        elif self.kind == "adam":
+            _lib.call("hhfm_opt_adam_dense_l2", ptr(w), ptr(s1), ptr(s2), ptr(g), n, self._lr_t(), self.beta1,
+                      self.beta2, self.eps, lamda, z, ptr(sq_partials), st)
+        elif self.kind == "momentum":
+            _lib.call("hhfm_opt_momentum_dense_l2", ptr(w), ptr(s1), ptr(g), n, self.lr, self.momentum, lamda, z,
+                      ptr(sq_partials), st)
+        else:
+            _lib.call("hhfm_opt_sgd_dense_l2", ptr(w), ptr(g), n, self.lr, lamda, z, ptr(sq_partials), st)
+
+    def apply_rows(self, name, w, g, rows, n_rows_dev, K, zero_grad=True):
+        """Sparse (IndexedSlices) update: only the touched rows move.  TF1's sparse Adam moves every row, so it
+        maps to the dense kernel."""
+        if self.kind == "adam":
+            return self.apply_dense(name, w, g, 0.0, None, zero_grad)
+        s1, _ = self.slots(name, w)
+        z = 1 if zero_grad else 0
+        st = cur_stream()
+        max_rows = rows.numel()
+        if self.kind == "adagrad":
+            _lib.call("hhfm_opt_adagrad_rows", ptr(w), ptr(s1), ptr(g), ptr(rows), ptr(n_rows_dev), max_rows, K, self.lr, z, st)
+        elif self.kind == "momentum":
+            _lib.call("hhfm_opt_momentum_rows", ptr(w), ptr(s1), ptr(g), ptr(rows), ptr(n_rows_dev), max_rows, K, self.lr,
+                      self.momentum, z, st)
+        else:
+            _lib.call("hhfm_opt_sgd_rows", ptr(w), ptr(g), ptr(rows), ptr(n_rows_dev), max_rows, K, self.lr, z, st)
+
+
+class TouchTracker:
+    """Per-step list of touched embedding rows, produced on the device by the scatter kernels."""
+
+    def __init__(self, M, device):
+        self.stamp_arr = torch.zeros(M, dtype=torch.int32, device=device)
+        self.rows = torch.empty(M, dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.stamp = 0
+
+    def begin_step(self):
+        self.stamp += 1
+        if self.stamp >= 2 ** 31 - 1:
+            self.stamp_arr.zero_()
+            self.stamp = 1
+        self.count.zero_()
+
+
+# --------------------------------------------------------------------------------------------------
+# K6/K7: full-catalog top-N, exact path
+# --------------------------------------------------------------------------------------------------
+class TopN:
+    """Exact full-catalog scorer + selector over an item shard [item_lo, item_hi) of the catalog."""
+
+    def __init__(self, device, max_workspace_bytes=1 << 30):
+        self.device = device
+        self.stage = Staging(torch.int32, device)
+        self.max_ws = max_workspace_bytes
+        self._ws = None
+
+    def _workspace(self, numel):
+        if self._ws is None or self._ws.numel() < numel:
+            self._ws = torch.empty(numel, dtype=torch.float32, device=self.device)
+        return self._ws[:numel]
+
+    def upload_rows(self, A, id_limit):
+        host, stride = pack_records([A], id_limit, self.stage)
+        dev = self.stage.upload(host.numel()).view(host.shape[0], stride)
+        return dev, stride
+
+    def topk(self, kind, A_dev, stride, n_ctx, n_time, pools, V, bias, n_user, n_item, tp, item_lo=0, item_hi=None,
+             return_scores=False):
+        """A_dev int32 [C,stride] on device.  Returns ids int32 [C,tp] relative to the item range (+ scores)."""
+        item_hi = n_item if item_hi is None else item_hi
+        N = item_hi - item_lo
+        C_rows = A_dev.shape[0]
+        M, K = V.shape
+        st = cur_stream()
+        Q = torch.empty(C_rows, K, dtype=torch.float32, device=self.device)
+        Fc = torch.empty(C_rows, K, dtype=torch.float32, device=self.device) if kind == QUERY_FM else None
+        _lib.call("hhfm_topn_build_query", kind, ptr(A_dev), C_rows, stride, n_ctx, n_time, pools[0], pools[1], pools[2],
+                  ptr(V), M, K, ptr(Q), ptr(Fc), st)
+        items = V[n_user + item_lo:n_user + item_hi]
+        ibias = bias.reshape(-1)[n_user + item_lo:n_user + item_hi] if (bias is not None and kind == QUERY_FM) else None
+        out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        out_sc = torch.empty(C_rows, tp, dtype=torch.float32, device=self.device)
+        chunk = max(1, min(C_rows, self.max_ws // max(1, 4 * N), 65535 * 32))
+        for c0 in range(0, C_rows, chunk):
+            c1 = min(C_rows, c0 + chunk)
+            ws = self._workspace((c1 - c0) * N).view(c1 - c0, N)
+            _lib.call("hhfm_topn_score_exact", kind, ptr(Q[c0:c1]), ptr(Fc[c0:c1]) if Fc is not None else None, c1 - c0,
+                      ptr(items), ptr(ibias), N, K, ptr(ws), N, st)
+            _lib.call("hhfm_topn_select", ptr(ws), None, None, c1 - c0, N, N, tp, item_lo, ptr(out_sc[c0:c1]),
+                      ptr(out_ids[c0:c1]), st)
+        return (out_ids, out_sc) if return_scores else out_ids
+
+
+def metrics_walk(pred_global, target, target_in_pf, TopK):
+    """Device evaluate_TopK walk (FM.py:336-357).  Tensors on device; returns rank codes int32 [C]."""
+    C_rows, tp = pred_global.shape
+    code = torch.empty(C_rows, dtype=torch.int32, device=pred_global.device)
+    _lib.call("hhfm_metrics_walk", ptr(pred_global), ptr(target), ptr(target_in_pf), C_rows, tp, TopK, ptr(code),
+              cur_stream())
+    return code
+
+
+def metrics_from_codes(codes):
+    """[mean HR, mean NDCG, mean reciprocal rank] exactly as FM.py:340-359 builds them from the walk: the
+    per-row values are appended in row order and averaged with np.average; rows with code -2 append nothing."""
+    res_map, res_ndcg, res_pre = [], [], []
+    for n in np.asarray(codes).tolist():
+        if n == -2:
+            continue
+        if n == -1:
+            res_map.append(0); res_ndcg.append(0); res_pre.append(0)
+        else:
+            res_map.append(1)
+            res_ndcg.append(np.log(2) / np.log(n + 2))
+            res_pre.append(1 / (n + 1))
+    return [np.average(res_map), np.average(res_ndcg), np.average(res_pre)]

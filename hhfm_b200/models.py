@@ -1,0 +1,471 @@
+"""Model classes with the reference's `Newcode` API, running on libhhfm_sm100.so.
+
+Each class keeps the reference constructor signature, `partial_fit(data) -> loss`, `topk(A, tp) -> int32[C,tp]`,
+the `weights` dict and a minimal `sess.run(handle, feed_dict)` shim for what the reference `Train` classes
+reach into (FM.py:313-319, OurModel7.py:441-455, BPR.py:247-252).  The TensorFlow graph + session of the
+reference (`_init_graph`) is replaced by device tensors and C-ABI kernel launches; there is no CPU path.
+
+  FM    Newcode/FM.py:59-198          MF   Newcode/MF.py:43-149
+  OUR   Newcode/OurModel7.py:50-307   BPR  Newcode/BPR.py:45-136
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import (POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_USER, Optimizer, Staging, TopN, TouchTracker, cur_stream,
+                     pack_records, ptr, require_cuda)
+
+
+class Handle:
+    """Stand-in for a tf.placeholder / graph tensor: only its identity matters (feed_dict key, fetch)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return "<hhfm handle %s>" % self.name
+
+
+class Session:
+    """`model.sess` shim: `run(fetches, feed_dict)` dispatches to the owning model."""
+
+    def __init__(self, model):
+        self._model = model
+
+    def run(self, fetches, feed_dict=None):
+        return self._model._run(fetches, feed_dict or {})
+
+    def close(self):
+        pass
+
+
+class _Base:
+    """Shared device state: embedding table, gradient arena, loss partial buffers, staging, optimizer."""
+
+    def _setup(self, features_M, K, seed, with_bias, optimizer_type, learning_rate, acc0, lamda):
+        self.device = require_cuda()
+        if K % 4 != 0 or K > 512:
+            raise _lib.HhfmError("hidden_factor=%d unsupported: the sm_100a kernels need K %% 4 == 0 and K <= 512" % K)
+        self._M, self._K = int(features_M), int(K)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(seed))
+        V = torch.empty(self._M, self._K, dtype=torch.float32).normal_(0.0, 0.01, generator=gen)
+        self.weights = {"feature_embeddings": V.to(self.device)}          # FM.py:152-154
+        if with_bias:
+            self.weights["feature_bias"] = torch.zeros(self._M, 1, dtype=torch.float32, device=self.device)  # :155-156
+        P = _lib.partials_len()
+        self._P = P
+        # one flat gradient arena so a data-parallel step needs a single all-reduce
+        n_v = self._M * self._K
+        n_b = self._M if with_bias else 0
+        self._arena = torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device)
+        self._gV = self._arena[:n_v].view(self._M, self._K)
+        self._gb = self._arena[n_v:n_v + n_b] if with_bias else None
+        self._gb0 = self._arena[n_v + n_b:n_v + n_b + 1]
+        self._loss_partials = self._arena[n_v + n_b + 4:]
+        self._sq_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._loss_host = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        self._opt = Optimizer(optimizer_type, learning_rate, initial_accumulator_value=acc0)
+        self._lamda = float(lamda)
+        self._touch = TouchTracker(self._M, self.device)
+        self._idx_stage = Staging(torch.int32, self.device)
+        self._f32_stage = Staging(torch.float32, self.device)
+        self._topn = TopN(self.device)
+        self._dp_group = None
+        self.deterministic = False
+        self.sess = Session(self)
+
+    # ---- data parallel: batch rows sharded across ranks, one all-reduce of the arena ----
+    def enable_data_parallel(self, group=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
+        self._dp_group = group if group is not None else dist.group.WORLD
+        for w in self.weights.values():
+            dist.broadcast(w, src=0, group=self._dp_group)
+
+    def _allreduce_grads(self):
+        if self._dp_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._arena, group=self._dp_group)
+
+    def _touch_args(self, extra=False):
+        """Touched-row tracking is only paid for when a *_rows optimizer will consume the list."""
+        need = self._dp_group is None and (self._lamda <= 0 or extra)
+        if not need:
+            return (None, 0, None, None)
+        self._touch.begin_step()
+        return (ptr(self._touch.stamp_arr), self._touch.stamp, ptr(self._touch.rows), ptr(self._touch.count))
+
+    # ---- optimizer step on the embedding table (+ optional bias rows) ----
+    def _apply_table(self, sparse_ok):
+        """lamda > 0: aggregated dense gradient g + lamda*V over all rows (FM.py:124 regulariser).
+        lamda == 0: IndexedSlices semantics; Adagrad/SGD/Adam dense kernels are exactly equivalent on untouched
+        rows (g = 0), Momentum needs the touched-row list."""
+        V = self.weights["feature_embeddings"]
+        use_rows = sparse_ok and self._lamda <= 0 and self._dp_group is None
+        if use_rows:
+            self._opt.apply_rows("feature_embeddings", V, self._gV, self._touch.rows, self._touch.count, self._K)
+            return False
+        if self._lamda <= 0 and self._opt.kind == "momentum":
+            raise NotImplementedError("sparse Momentum under data parallelism is not implemented")
+        sq = self._sq_partials if self._lamda > 0 else None
+        self._opt.apply_dense("feature_embeddings", V, self._gV, self._lamda if self._lamda > 0 else 0.0, sq)
+        return self._lamda > 0
+
+    def _finish_loss(self, with_reg):
+        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if with_reg else None,
+                  0.5 * self._lamda if with_reg else 0.0, ptr(self._loss_dev), cur_stream())
+        self._loss_host.copy_(self._loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def _upload_ids(self, parts):
+        host, stride = pack_records(parts, self._M, self._idx_stage)
+        dev = self._idx_stage.upload(host.numel()).view(host.shape[0], stride)
+        return dev, stride
+
+    def _upload_f32(self, arr):
+        arr = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(-1))
+        host = self._f32_stage.ensure(arr.size)
+        host.copy_(torch.from_numpy(arr))
+        return self._f32_stage.upload(arr.size)
+
+    def load_weights(self, weights):
+        """Inject weights (numpy arrays or tensors keyed like `self.weights`) -- parity tests use this because
+        the reference initialises unseeded (FM.py:153)."""
+        for k, v in weights.items():
+            if k not in self.weights:
+                raise KeyError(k)
+            t = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(self.weights[k].shape)
+            self.weights[k].copy_(t.to(self.device))
+
+    def get_weights(self):
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.weights.items()}
+
+
+# ====================================================================================================
+class FM(_Base):
+    """Factorization machine, Newcode/FM.py:59-198."""
+
+    interaction = 0
+
+    def __init__(self, valid_dimension, features_M, n_user, n_item, hidden_factor, learning_rate, lamda_bilinear, keep,
+                 optimizer_type, batch_norm, verbose, random_seed=2016):
+        self.valid_dimension = valid_dimension
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.hidden_factor = hidden_factor
+        self.features_M = features_M
+        self.lamda_bilinear = lamda_bilinear
+        self.keep = keep
+        self.random_seed = random_seed
+        self.optimizer_type = optimizer_type
+        self.batch_norm = batch_norm
+        self.verbose = verbose
+        self.train_rmse, self.valid_rmse, self.test_rmse = [], [], []
+        self._init_graph()
+
+    def _init_graph(self):
+        if self.batch_norm:
+            raise NotImplementedError("batch_norm=1 (FM.py:111-112) is not on the accelerated path; default is 0")
+        if float(self.keep) != 1.0:
+            raise NotImplementedError("dropout keep<1 (FM.py:114) is not on the accelerated path; default is 1")
+        self.train_features = Handle("train_features_fm")    # FM.py:89-92
+        self.train_labels = Handle("train_labels_fm")
+        self.dropout_keep = Handle("dropout_keep_fm")
+        self.train_phase = Handle("train_phase_fm")
+        self.out = Handle("out")
+        self.loss = Handle("loss")
+        self.optimizer = Handle("optimizer")
+        self._setup(self.features_M, self.hidden_factor, self.random_seed, True, self.optimizer_type,
+                    self.learning_rate, 0.1, self.lamda_bilinear)
+        self._b0 = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.weights["bias"] = self._b0.view(())                                   # FM.py:157
+
+    # -- forward only: `sess.run(model.out, ...)` of evaluate_AUC (FM.py:313-319) --
+    def predict(self, X):
+        X = np.asarray(X)
+        F = X.shape[1]
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        B = idx.shape[0]
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, F, ptr(self.weights["feature_embeddings"]),
+                  ptr(self.weights.get("feature_bias")), ptr(self._b0), self._M, self._K, self.interaction, ptr(out),
+                  cur_stream())
+        return out.cpu().numpy().reshape(-1, 1)
+
+    def partial_fit(self, data):
+        """One minibatch step (FM.py:168-171): forward, squared loss, backward, optimizer.  Returns the loss."""
+        X = np.asarray(data["X"])
+        F = X.shape[1]
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        y = self._upload_f32(data["Y"])
+        B = idx.shape[0]
+        self._opt.begin_step()
+        V = self.weights["feature_embeddings"]
+        bias = self.weights.get("feature_bias")
+        ts, stamp, tr, tc = self._touch_args(extra=self._opt.kind == "momentum")
+        _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, F, ptr(V), ptr(bias), ptr(self._b0), self._M,
+                  self._K, self.interaction, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0),
+                  ptr(self._loss_partials), ts, stamp, tr, tc, 1 if self.deterministic else 0, cur_stream())
+        self._allreduce_grads()
+        with_reg = self._apply_table(sparse_ok=True)
+        if bias is not None:
+            self._apply_bias()
+        return self._finish_loss(with_reg)
+
+    def _apply_bias(self):
+        # feature_bias receives IndexedSlices (only touched rows move); the scalar bias is dense.
+        bias = self.weights["feature_bias"]
+        if self._opt.kind == "momentum" and self._dp_group is None:
+            self._opt.apply_rows("feature_bias", bias, self._gb, self._touch.rows, self._touch.count, 1)
+        else:
+            self._opt.apply_dense("feature_bias", bias, self._gb, 0.0, None)
+        self._opt.apply_dense("bias", self._b0, self._gb0, 0.0, None)
+
+    def topk(self, A, tp):
+        """Full-catalog top-N (FM.py:172-185): indices relative to the item id range."""
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        ids = self._topn.topk(QUERY_FM, A_dev, stride, A.shape[1] - 2, 0, (0, 0, 0), self.weights["feature_embeddings"],
+                              self.weights["feature_bias"], self.n_user, self.n_item, tp)
+        return ids.cpu().numpy()
+
+    def _run(self, fetches, feed):
+        if fetches is self.out:
+            return self.predict(feed[self.train_features])
+        if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
+            loss = self.partial_fit({"X": feed[self.train_features], "Y": feed[self.train_labels]})
+            return loss, None
+        raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))
+
+
+# ====================================================================================================
+class MF(FM):
+    """Pointwise matrix factorisation, Newcode/MF.py:43-149: out = sum_k V[u]*V[i] (the bias term is computed but
+    not added, MF.py:91-92); Adagrad accumulator starts at 1e-8 (MF.py:104); topk retrieves 100 (MF.py:147)."""
+
+    interaction = 1
+
+    def __init__(self, features_M, n_user, n_item, hidden_factor, learning_rate, lamda_bilinear, keep, optimizer_type,
+                 batch_norm, verbose, random_seed=2016):
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.hidden_factor = hidden_factor
+        self.features_M = features_M
+        self.lamda_bilinear = lamda_bilinear
+        self.keep = keep
+        self.random_seed = random_seed
+        self.optimizer_type = optimizer_type
+        self.batch_norm = batch_norm
+        self.verbose = verbose
+        self.train_rmse, self.valid_rmse, self.test_rmse = [], [], []
+        self._init_graph()
+
+    def _init_graph(self):
+        if self.batch_norm:
+            raise NotImplementedError("batch_norm=1 is not on the accelerated path")
+        if float(self.keep) != 1.0:
+            raise NotImplementedError("MF dropout keep<1 (MF.py:87, default 0.7) needs TF's RNG stream and is not on "
+                                      "the accelerated path; pass keep=1")
+        self.train_features = Handle("train_features_fm")
+        self.train_labels = Handle("train_labels_fm")
+        self.dropout_keep = Handle("dropout_keep_fm")
+        self.train_phase = Handle("train_phase_fm")
+        self.out = Handle("out")
+        self.loss = Handle("loss")
+        self.optimizer = Handle("optimizer")
+        self._setup(self.features_M, self.hidden_factor, self.random_seed, True, self.optimizer_type,
+                    self.learning_rate, 1e-8, self.lamda_bilinear)
+        self._b0 = None
+
+    def predict(self, X):
+        host, stride = pack_records([np.asarray(X)[:, :2]], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        B = idx.shape[0]
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, 2, ptr(self.weights["feature_embeddings"]), None, None,
+                  self._M, self._K, 1, ptr(out), cur_stream())
+        return out.cpu().numpy().reshape(-1, 1)
+
+    def partial_fit(self, data):
+        X = np.asarray(data["X"])[:, :2]
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        y = self._upload_f32(data["Y"])
+        B = idx.shape[0]
+        self._opt.begin_step()
+        V = self.weights["feature_embeddings"]
+        ts, stamp, tr, tc = self._touch_args()
+        _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, 2, ptr(V), None, None, self._M, self._K, 1, ptr(y),
+                  None, ptr(self._gV), None, None, ptr(self._loss_partials), ts, stamp, tr, tc,
+                  1 if self.deterministic else 0, cur_stream())
+        self._allreduce_grads()
+        with_reg = self._apply_table(sparse_ok=True)
+        return self._finish_loss(with_reg)
+
+    def topk(self, A, tp=100):
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        ids = self._topn.topk(QUERY_USER, A_dev, stride, 0, 0, (0, 0, 0), self.weights["feature_embeddings"], None,
+                              self.n_user, self.n_item, tp)
+        return ids.cpu().numpy()
+
+
+# ====================================================================================================
+class _PairRank(_Base):
+    """Shared HHFM / BPR machinery: record packing, fused forward+backward kernel, scoring, top-N."""
+
+    def _groups(self):
+        raise NotImplementedError
+
+    def _fit_records(self, parts, n_ctx, n_time, n_neg):
+        idx, stride = self._upload_ids(parts)
+        B = idx.shape[0]
+        self._opt.begin_step()
+        V = self.weights["feature_embeddings"]
+        pc, pt, pf = self.pools
+        ts, stamp, tr, tc = self._touch_args()
+        _lib.call("hhfm_pairrank_fwd_bwd", ptr(idx), B, stride, n_ctx, n_time, n_neg, pc, pt, pf, ptr(V), self._M,
+                  self._K, None, None, ptr(self._gV), ptr(self._loss_partials), ts, stamp, tr, tc,
+                  1 if self.deterministic else 0, cur_stream())
+        self._allreduce_grads()
+        with_reg = self._apply_table(sparse_ok=True)
+        return self._finish_loss(with_reg)
+
+    def _positive_feedback(self, parts, n_ctx, n_time):
+        idx, stride = self._upload_ids(parts)
+        B = idx.shape[0]
+        pos = torch.empty(B, dtype=torch.float32, device=self.device)
+        pc, pt, pf = self.pools
+        _lib.call("hhfm_pairrank_fwd", ptr(idx), B, stride, n_ctx, n_time, 0, pc, pt, pf,
+                  ptr(self.weights["feature_embeddings"]), self._M, self._K, ptr(pos), None, cur_stream())
+        return pos.cpu().numpy().reshape(-1, 1)
+
+
+class OUR(_PairRank):
+    """HHFM ("OurModel7"), Newcode/OurModel7.py:50-307."""
+
+    def __init__(self, feature_dimension, time_dimension, features_M, n_user, n_item, hidden_factor, learning_rate,
+                 lamda_bilinear, optimizer_type, context, time, pooling=(POOL_SUM, POOL_SUM, POOL_SUM), random_seed=2016):
+        self.feature_dimension = feature_dimension
+        self.time_dimension = time_dimension
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.hidden_factor = hidden_factor
+        self.features_M = features_M
+        self.lamda_bilinear = lamda_bilinear
+        self.optimizer_type = optimizer_type
+        self.context = context
+        self.time = time
+        # Pooling1C / Pooling1T / Pooling1F: module-level globals in the reference (OurModel7.py:14-19)
+        self.pools = tuple(int(p) for p in pooling)
+        self.random_seed = random_seed
+        self._init_graph()
+
+    def _init_graph(self):
+        self.Pos, self.Fea, self.Tim, self.Neg = Handle("Pos"), Handle("Fea"), Handle("Tim"), Handle("Neg")
+        self.PositiveFeadback = Handle("PositiveFeadback")
+        self.loss, self.optimizer = Handle("loss"), Handle("optimizer")
+        self.num = 1 + (1 if self.context else 0) + (1 if self.time else 0)      # OurModel7.py:89,94
+        self._n_ctx = int(self.feature_dimension) if self.context else 0
+        self._n_time = int(self.time_dimension) if self.time else 0
+        self._setup(self.features_M, self.hidden_factor, self.random_seed, True, self.optimizer_type,
+                    self.learning_rate, 0.1, self.lamda_bilinear)
+        # feature_bias exists in the reference graph (OurModel7.py:213-214) but receives no gradient
+        self._gb = None
+
+    def _parts(self, X, F1, F2, Y=None):
+        parts = [np.asarray(X)[:, :2]]
+        if self.context:
+            parts.append(np.asarray(F1))
+        if self.time:
+            parts.append(np.asarray(F2))
+        if Y is not None:
+            parts.append(np.asarray(Y))
+        return parts
+
+    def partial_fit(self, data):
+        """OurModel7.py:219-228: data = {'X':[B,2], 'F1':[B,fc], 'F2':[B,ft], 'Y':[B,NG]}."""
+        Y = np.asarray(data["Y"])
+        parts = self._parts(data["X"], data.get("F1"), data.get("F2"), Y)
+        return self._fit_records(parts, self._n_ctx, self._n_time, Y.shape[1])
+
+    def positive_feedback(self, X, F1=None, F2=None):
+        return self._positive_feedback(self._parts(X, F1, F2), self._n_ctx, self._n_time)
+
+    def topk(self, A, tp):
+        """OurModel7.py:229-295: A = [user, item, ctx.., time..]."""
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        ids = self._topn.topk(QUERY_HHFM, A_dev, stride, self._n_ctx, self._n_time, self.pools,
+                              self.weights["feature_embeddings"], None, self.n_user, self.n_item, tp)
+        return ids.cpu().numpy()
+
+    def _run(self, fetches, feed):
+        if fetches is self.PositiveFeadback:
+            return self.positive_feedback(feed[self.Pos], feed.get(self.Fea), feed.get(self.Tim))
+        if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
+            d = {"X": feed[self.Pos], "Y": feed[self.Neg]}
+            if self.Fea in feed:
+                d["F1"] = feed[self.Fea]
+            if self.Tim in feed:
+                d["F2"] = feed[self.Tim]
+            return self.partial_fit(d), None
+        raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))
+
+
+class BPR(_PairRank):
+    """BPR-MF with max-negative, Newcode/BPR.py:45-136 (Adagrad accumulator starts at 1e-8, BPR.py:93)."""
+
+    pools = (POOL_SUM, POOL_SUM, POOL_SUM)
+
+    def __init__(self, features_M, n_user, n_item, hidden_factor, learning_rate, lamda_bilinear, optimizer_type,
+                 random_seed=2016):
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.hidden_factor = hidden_factor
+        self.features_M = features_M
+        self.lamda_bilinear = lamda_bilinear
+        self.optimizer_type = optimizer_type
+        self.random_seed = random_seed
+        self.train_rmse, self.valid_rmse, self.test_rmse = [], [], []
+        self._init_graph()
+
+    def _init_graph(self):
+        self.Pos, self.Neg = Handle("Pos"), Handle("Neg")
+        self.PositiveFeadback = Handle("PositiveFeadback")
+        self.loss, self.optimizer = Handle("loss"), Handle("optimizer")
+        self._setup(self.features_M, self.hidden_factor, self.random_seed, False, self.optimizer_type,
+                    self.learning_rate, 1e-8, self.lamda_bilinear)
+
+    def partial_fit(self, data):
+        Y = np.asarray(data["Y"])
+        return self._fit_records([np.asarray(data["X"])[:, :2], Y], 0, 0, Y.shape[1])
+
+    def positive_feedback(self, X):
+        return self._positive_feedback([np.asarray(X)[:, :2]], 0, 0)
+
+    def topk(self, A, Topk):
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        ids = self._topn.topk(QUERY_USER, A_dev, stride, 0, 0, (0, 0, 0), self.weights["feature_embeddings"], None,
+                              self.n_user, self.n_item, Topk)
+        return ids.cpu().numpy()
+
+    def _run(self, fetches, feed):
+        if fetches is self.PositiveFeadback:
+            return self.positive_feedback(feed[self.Pos])
+        if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
+            return self.partial_fit({"X": feed[self.Pos], "Y": feed[self.Neg]}), None
+        raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))

@@ -1,0 +1,205 @@
+/*
+ * hhfm_sm100.h -- C ABI of libhhfm_sm100.so: the B200 (sm_100a) replacement for the factorization-machine
+ * hot path of data-man-34/HHFM (Newcode/*.py).
+ *
+ * The reference has no native layer: its "kernels" are the TensorFlow-1.x ops instantiated by the graphs in
+ * Newcode/{FM,MF,AFM,DFM,OurModel7,BPR}.py and executed by `sess.run` (FM.py:168-171).  Each entry point
+ * below names the reference graph lines (file:line under /root/reference) whose TF ops it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All device pointers are CALLER-OWNED (torch tensors on the
+ *     host side); the library never allocates or frees device memory.  Scratch is passed in; sizes come from
+ *     the hhfm_*_len / hhfm_workspace_bytes_* queries.
+ *   - Every device entry point takes a CUDA stream and is stream-ordered / asynchronous, re-entrant across
+ *     streams, and keeps no global mutable state (the last-error string is thread-local).
+ *   - Return value: HHFM_OK (0) or a negative hhfm_status.  `hhfm_last_error()` describes the last failure
+ *     on the calling thread.  No exception crosses the ABI.  There is NO CPU fallback: without a CUDA device
+ *     the device entry points return HHFM_ERR_LAUNCH.
+ *   - dtype: float32 values, int32 ids (FM.py:89), shapes as int64_t.  Embedding tables are row-major
+ *     [M, K] with K % 4 == 0, K <= 512, 16-byte aligned.
+ *   - Gradient buffers are accumulated into (+=) with red.global.add.v4.f32; the caller (or the optimizer
+ *     entry points with zero_grad=1) keeps them zero between steps.
+ */
+#ifndef HHFM_SM100_H
+#define HHFM_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hhfm_stream_t; /* cudaStream_t */
+
+typedef enum {
+  HHFM_OK = 0,
+  HHFM_ERR_BAD_ARG = -1,
+  HHFM_ERR_UNSUPPORTED = -2,
+  HHFM_ERR_LAUNCH = -3
+} hhfm_status;
+
+/* Pooling1C / Pooling1T / Pooling1F of OurModel7.py:14-19 (tf.reduce_sum | reduce_max | reduce_mean) */
+typedef enum { HHFM_POOL_SUM = 0, HHFM_POOL_MAX = 1, HHFM_POOL_MEAN = 2 } hhfm_pool;
+
+/* optimizer kinds: FM.py:129-136 (tf.train.{Adagrad,Adam,Momentum,GradientDescent}Optimizer) */
+typedef enum { HHFM_OPT_ADAGRAD = 0, HHFM_OPT_ADAM = 1, HHFM_OPT_MOMENTUM = 2, HHFM_OPT_SGD = 3 } hhfm_opt;
+
+/* top-N query kinds */
+typedef enum {
+  HHFM_QUERY_USER = 0, /* q = V[user]                      BPR.py:132, MF.py:145          */
+  HHFM_QUERY_FM = 1,   /* q = V[user]+Fc, Fc = sum ctx     FM.py:174-177                  */
+  HHFM_QUERY_HHFM = 2  /* q = hybrid feature               OurModel7.py:232-292           */
+} hhfm_query;
+
+int hhfm_abi_version(void);
+const char* hhfm_last_error(void);
+/* number of float slots every `loss_partials` / `sq_partials` argument must provide */
+int64_t hhfm_partials_len(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K0  host-side batch packing (CPU threads; dst may be pinned host memory).
+ * Replaces the numpy slicing that feeds `feed_dict` (FM.py:251-256, OurModel7.py:373-385): int64 (or int32)
+ * id columns are narrowed to int32 and written into a row-major record buffer with a caller-chosen row
+ * stride, so one sample's ids are contiguous and 16-byte aligned for the device kernels.
+ * Ids outside [0, id_limit) make the call fail with HHFM_ERR_BAD_ARG (TF's gather would raise).
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_pack_ids_i64(const int64_t* src, int64_t rows, int64_t cols, int64_t src_row_stride,
+                      int32_t* dst, int64_t dst_row_stride, int64_t dst_col0, int64_t id_limit, int nthreads);
+int hhfm_pack_ids_i32(const int32_t* src, int64_t rows, int64_t cols, int64_t src_row_stride,
+                      int32_t* dst, int64_t dst_row_stride, int64_t dst_col0, int64_t id_limit, int nthreads);
+/* fill columns [dst_col0, dst_col0+cols) of every record with `value` (padding = -1) */
+int hhfm_pack_fill_i32(int32_t* dst, int64_t rows, int64_t cols, int64_t dst_row_stride, int64_t dst_col0,
+                       int32_t value, int nthreads);
+/* general CSR: ids [rows, cols] (+ optional values) -> row_ptr int32[rows+1], col int32[rows*cols],
+ * val f32[rows*cols] (val/src_val may both be NULL => implicit 1.0, the reference's one-hot fields). */
+int hhfm_pack_csr_i64(const int64_t* src, const float* src_val, int64_t rows, int64_t cols, int64_t src_row_stride,
+                      int32_t* row_ptr, int32_t* col, float* val, int64_t id_limit, int nthreads);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  FM / MF: gather + second-order interaction (+ squared loss + backward scatter)
+ *   out[s] = sum_k 0.5((sum_f e_f)^2 - sum_f e_f^2) + sum_f val_f*bias[x_f] + b0,  e_f = val_f * V[x_f]
+ *   FM.py:99-120 (embedding_lookup, reduce_sum, square, subtract, add_n); DFM.py:104-122 second order.
+ *   interaction = 1 selects MF.py:81-92: out = sum_k V[x_0]*V[x_1] (first two ids, no bias).
+ * Batch layout: CSR.  row_ptr == NULL means fixed width F (row s owns col[s*F .. s*F+F)); val == NULL
+ * means all values 1.0.  bias / b0 may be NULL (treated as 0).  b0 is a device scalar.
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_fm_fwd(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
+                const float* V, const float* bias, const float* b0, int64_t M, int64_t K, int32_t interaction,
+                float* out, hhfm_stream_t stream);
+
+/* Fused training pass: forward, loss = 0.5*sum(y-out)^2 (FM.py:123-126), and TF-autodiff-equivalent
+ * backward: gV[x_f] += g*val_f*(S - e_f), gbias[x_f] += g*val_f, gb0 += g, g = out - y.
+ * Duplicate ids (inside a row or across rows) are summed like UnsortedSegmentSum.
+ *   out            [B] nullable
+ *   gV             [M,K], accumulated into
+ *   gbias          [M] nullable;  gb0 [1] nullable
+ *   loss_partials  [hhfm_partials_len()]: per-CTA partial sums, reduce with hhfm_loss_finalize
+ *   touch_stamp    [M] nullable: if given, every row whose stamp != `stamp` is stamped and appended to
+ *                  touched_rows (capacity M) with touched_count[0] incremented -> feeds the *_rows optimizers
+ *   deterministic  1 = one warp, program-order accumulation (bit-reproducible; test mode)              */
+int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
+                           const float* V, const float* bias, const float* b0, int64_t M, int64_t K,
+                           int32_t interaction, const float* labels, float* out, float* gV, float* gbias, float* gb0,
+                           float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
+                           int32_t* touched_count, int32_t deterministic, hhfm_stream_t stream);
+
+/* Backward only, for torch.autograd: g = gout[s] given by the caller. */
+int hhfm_fm_bwd(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
+                const float* V, int64_t M, int64_t K, int32_t interaction, const float* gout,
+                float* gV, float* gbias, float* gb0, int32_t deterministic, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88) pairwise ranking
+ * Record layout (int32, row stride `stride` >= 2+n_ctx+n_time+n_neg, stride % 4 == 0, 16-byte aligned):
+ *   [user, item+, ctx_0..ctx_{n_ctx-1}, time_0..time_{n_time-1}, neg_0..neg_{n_neg-1}, pad...]
+ *   hyb = Pool_stack(stack[V[user], Pool_ctx(V[ctx]), Pool_time(V[time])]);  BPR: n_ctx = n_time = 0
+ *   pos = hyb.V[item+]; neg_j = hyb.V[neg_j]; loss = -sum log(sigmoid(pos - max_j neg_j))
+ *   reduce_max backward splits equally among tied maxima (TF semantics).
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_pairrank_fwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time, int32_t n_neg,
+                      int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V, int64_t M, int64_t K,
+                      float* pos_out, float* neg_out, hhfm_stream_t stream);
+
+int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time,
+                          int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V,
+                          int64_t M, int64_t K, float* pos_out, float* neg_out, float* gV, float* loss_partials,
+                          int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
+                          int32_t deterministic, hhfm_stream_t stream);
+
+/* Backward only, for torch.autograd: dpos [B], dneg [B,n_neg] (nullable) given by the caller. */
+int hhfm_pairrank_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_ctx, int32_t n_time, int32_t n_neg,
+                      int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V, int64_t M, int64_t K,
+                      const float* dpos, const float* dneg, float* gV, int32_t deterministic, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  generic segmented scatter-add of rows: dst[rows[i], :] += src[i, :]   (TF UnsortedSegmentSum /
+ * IndexedSlices aggregation implicit in every `.minimize`, FM.py:132).  Sort-free: vector reductions.
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_scatter_add_rows(const int32_t* rows, const float* src, int64_t n, int64_t K, float* dst, int64_t M,
+                          hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  optimizers with TF-1.x semantics (FM.py:129-136; BPR.py:93 / MF.py:104 use acc0 = 1e-8)
+ *   adagrad : acc += g^2; w -= lr*g/sqrt(acc)                (no epsilon)
+ *   adam    : lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the CALLER and passed as `lr`;
+ *             m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g^2; w -= lr*m/(sqrt(v)+eps)
+ *   momentum: acc = acc*mu + g; w -= lr*acc
+ *   sgd     : w -= lr*g
+ * _dense_l2: g_eff = g + lamda*w over all n elements (the reference's l2_regularizer on the embedding table
+ *   makes the gradient dense, FM.py:124).  sq_partials (nullable, [hhfm_partials_len()]) receives per-CTA
+ *   partial sums of w^2 BEFORE the update, for the regulariser term of the reported loss.
+ * _rows: only the listed rows move (TF SparseApply*): rows int32[*n_rows_dev], each row has K elements.
+ *   zero_grad = 1 clears the consumed gradient entries so the buffer is ready for the next step.
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_opt_adagrad_dense_l2(float* w, float* acc, float* g, int64_t n, float lr, float lamda, int32_t zero_grad,
+                              float* sq_partials, hhfm_stream_t stream);
+int hhfm_opt_adam_dense_l2(float* w, float* m, float* v, float* g, int64_t n, float lr_t, float beta1, float beta2,
+                           float eps, float lamda, int32_t zero_grad, float* sq_partials, hhfm_stream_t stream);
+int hhfm_opt_momentum_dense_l2(float* w, float* acc, float* g, int64_t n, float lr, float momentum, float lamda,
+                               int32_t zero_grad, float* sq_partials, hhfm_stream_t stream);
+int hhfm_opt_sgd_dense_l2(float* w, float* g, int64_t n, float lr, float lamda, int32_t zero_grad,
+                          float* sq_partials, hhfm_stream_t stream);
+int hhfm_opt_adagrad_rows(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev,
+                          int64_t max_rows, int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream);
+int hhfm_opt_momentum_rows(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev,
+                           int64_t max_rows, int64_t K, float lr, float momentum, int32_t zero_grad,
+                           hhfm_stream_t stream);
+int hhfm_opt_sgd_rows(float* w, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
+                      int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream);
+
+/* loss_out[0] = sum(loss_partials) + half_lamda * sum(sq_partials)   (fixed summation order; sq may be NULL) */
+int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, float half_lamda, float* loss_out,
+                       hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  full-catalog top-N (FM.py:172-185, BPR.py:131-136, MF.py:144-149, OurModel7.py:229-295)
+ * Exact path (bit-identical to the oracle's canonical fp32 order: k ascending, separately rounded mul/add):
+ *   build_query -> score_exact -> select.
+ *   A: int32 [C, stride] rows [user, item, ctx..., time...] (the reference's `feed_dict` rows, FM.py:333).
+ *   items = V + n_user*K (the item id range is contiguous, FM.py:175); item_bias = bias + n_user or NULL.
+ *   FM: score = fl(bias_n + sum_k fl(q_k * fl(v_nk + Fc_k)));  others: score = sum_k fl(q_k*v_nk).
+ * select: per row the tp best of `n` (score, id) pairs under (score desc, id asc) == tf.nn.top_k order.
+ *   ids == NULL means id = column index; counts == NULL means every row has n entries.  Output ids get
+ *   id_offset added (item-shard offset for the multi-GPU merge).  tp <= 1024.
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_topn_build_query(int32_t kind, const int32_t* A, int64_t C, int64_t stride, int32_t n_ctx, int32_t n_time,
+                          int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V, int64_t M,
+                          int64_t K, float* Q, float* Fc, hhfm_stream_t stream);
+int hhfm_topn_score_exact(int32_t kind, const float* Q, const float* Fc, int64_t C, const float* items,
+                          const float* item_bias, int64_t N, int64_t K, float* scores, int64_t score_stride,
+                          hhfm_stream_t stream);
+int hhfm_topn_select(const float* scores, const int32_t* ids, const int32_t* counts, int64_t C, int64_t row_stride,
+                     int64_t n, int32_t tp, int32_t id_offset, float* out_scores, int32_t* out_ids,
+                     hhfm_stream_t stream);
+
+/* K7  evaluate_TopK walk (FM.py:336-357) including its positive_feedback quirk.
+ *   pred [C,tp] GLOBAL item ids; target [C]; target_in_pf [C] = (item in positive_feedback[key]) computed
+ *   by the host.  rank_code[c] = n >= 0: hit at counter n;  -1: miss (appends 0);  -2: row appends nothing. */
+int hhfm_metrics_walk(const int32_t* pred, const int32_t* target, const uint8_t* target_in_pf, int64_t C,
+                      int32_t tp, int32_t TopK, int32_t* rank_code, hhfm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HHFM_SM100_H */

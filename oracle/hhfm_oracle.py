@@ -1,0 +1,575 @@
+"""CPU oracle for the HHFM factorization-machine hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy fp32 restatement of the TensorFlow-1.x graphs the reference builds in
+`Newcode/{FM,MF,AFM,DFM,OurModel7,BPR}.py` plus the host logic of `Newcode/NewLoadData.py` and the
+`Train.evaluate_TopK / sample_negative` loops.  Every function cites the reference file:line it follows.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import
+this module.  The product (`hhfm_b200/`) never does: it must fail loudly when the CUDA library is missing.
+
+PARITY STATUS
+  * loader, negative sampler, batch assembly, evaluate_TopK walk: PINNED against the reference's own code
+    executed in the build container (tests/golden/make_reference_goldens.py imports /root/reference/Newcode
+    with stub `tensorflow`/`toolz` modules and numpy/pandas compat shims; fixtures in tests/golden/).
+  * model arithmetic (forward / loss / gradients / optimizers / top-k): **parity unpinned** -- the arithmetic
+    lives in TensorFlow 1.x (unpinned, ~1.5-1.8, not vendored, not installable here: no TF-1 wheel for
+    Python 3.12).  The restatement encodes TF's documented op semantics:
+      l2_loss(t)=sum(t^2)/2; l2_regularizer(s)(w)=s*sum(w^2)/2; Adagrad acc0=0.1, acc+=g^2, w-=lr*g/sqrt(acc)
+      (no epsilon); sparse (IndexedSlices) grads are summed per unique row and only touched rows move; a
+      sparse + dense gradient on one variable aggregates to dense; TF1 Adam's sparse path equals the dense
+      update with zero rows; reduce_max splits its gradient equally among ties; top_k sorts descending with
+      the lower index first among equals; softmax subtracts the row max.
+    Analytic gradients here are cross-checked against torch.autograd (tests/test_oracle.py).
+
+All arithmetic is float32 (np.float32 arrays; each NumPy ufunc rounds to fp32 like a non-fused GPU op).
+Canonical score order for the top-N evaluators: products and sums are taken for k = 0..K-1 in ascending
+order with a separately rounded multiply and add (no FMA) -- the CUDA exact rescoring kernel uses
+`__fmul_rn/__fadd_rn` in the same order, so scores are bit-identical and index lists compare exactly.
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+
+import numpy as np
+
+F32 = np.float32
+
+POOL_SUM, POOL_MAX, POOL_MEAN = 0, 1, 2
+
+
+# ----------------------------------------------------------------------------------------------------
+# data: Newcode/NewLoadData.py:16-62
+# ----------------------------------------------------------------------------------------------------
+class LoadDataOracle:
+    """Restatement of `LoadData.__init__` (NewLoadData.py:16-62) on an in-memory token table.
+
+    tokens: object/str array [rows, 1+F]; column 0 is the label, 1 the user, 2 the item.
+    The shuffle (NewLoadData.py:39) draws from the legacy global NumPy RNG exactly like the reference, so
+    `np.random.seed(s)` before construction reproduces the reference split.
+    """
+
+    def __init__(self, tokens, ratio=0.9):
+        tokens = np.asarray(tokens, dtype=object)
+        self.n_user = len(set(tokens[:, 1].tolist()))        # NewLoadData.py:22
+        self.n_item = len(set(tokens[:, 2].tolist()))        # NewLoadData.py:23
+        ids = {}
+        for tok in tokens[:, 1:].T.reshape(-1):              # column-major first-seen ids, :29-33
+            if tok not in ids:
+                ids[tok] = len(ids)
+        self.features_M = len(ids)                           # :35
+        data = np.empty(tokens.shape, dtype=np.int64)
+        data[:, 0] = tokens[:, 0].astype(np.int64)
+        for c in range(1, tokens.shape[1]):
+            data[:, c] = [ids[t] for t in tokens[:, c]]      # :34
+        self.Total_data = data
+        np.random.shuffle(data)                              # :39 (in place, global RNG)
+        test_size = int(len(data) * (1 - ratio))             # :40
+        train, test = [], []
+        self.positive_feedback = defaultdict(set)
+        self.train_set = defaultdict(set)
+        seen = set()
+        i = 0
+        cols = [c for c in range(1, data.shape[1]) if c != 2]
+        for line in data:                                    # :48-58
+            key = tuple(line[cols])
+            if key not in seen and i < test_size:
+                seen.add(key)
+                test.append(line)
+                i += 1
+            else:
+                self.positive_feedback[key].add(line[2])
+                train.append(line)
+                self.train_set[line[1]].add(line[2])
+        self.Train_data = np.array(train)
+        self.Test_data = np.array(test)
+
+
+def sample_negative(rows, n_user, n_item, positive_feedback, num, randint=None):
+    """`Train.sample_negative` (FM.py:284-294): uniform item draw with rejection against the positives of
+    the row's key (all columns but the item).  `rows` = [n, F] ids without the label column."""
+    randint = randint or np.random.randint
+    samples = randint(n_user, n_user + n_item, size=(len(rows), num))
+    cols = [c for c in range(rows.shape[1]) if c != 1]
+    for i, row in enumerate(rows):
+        key = tuple(row[cols])
+        for j in range(num):
+            neg = samples[i, j]
+            while neg in positive_feedback[key]:
+                samples[i, j] = neg = randint(n_user, n_user + n_item)
+    return samples
+
+
+def assemble_pointwise_epoch(train, neg_samples, NG, neg_label):
+    """FM.py:240-249 / AFM.py:309-318: positives followed by NG item-replaced copies labelled `neg_label`
+    (FM: -0 == 0, AFM/DFM/MF: -1).  The shuffle (FM.py:250) is left to the caller."""
+    copy_ = np.tile(train[:, None, :], [1, NG, 1]).reshape(-1, train.shape[1])
+    copy_[:, 2] = neg_samples.reshape(-1)
+    copy_[:, 0] = neg_label
+    return np.append(train, copy_, axis=0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# metrics: FM.py:325-359 (same text in AFM/DFM/BPR/OurModel7/CARS2)
+# ----------------------------------------------------------------------------------------------------
+def evaluate_topk_walk(prediction, rows, positive_feedback, TopK):
+    """The per-row walk of `Train.evaluate_TopK` (FM.py:336-357), verbatim including its quirk: the
+    `elif item in positive_feedback[key]` branch tests the *target* item, so such rows never advance `n`.
+
+    prediction: int [C, tp] GLOBAL item ids (topk output + n_user, FM.py:335); rows: int [C, F].
+    Returns the three result lists (hit, ndcg, reciprocal rank); rows that fall through append nothing.
+    """
+    res_map, res_ndcg, res_pre = [], [], []
+    cols = [c for c in range(rows.shape[1]) if c != 1]
+    for i, line in enumerate(rows):
+        item = line[1]
+        key = tuple(line[cols])
+        n = 0
+        for it in prediction[i]:
+            if n > TopK - 1:
+                res_map.append(0); res_ndcg.append(0); res_pre.append(0)
+                break
+            elif it == item:
+                res_map.append(1)
+                res_ndcg.append(np.log(2) / np.log(n + 2))
+                res_pre.append(1 / (n + 1))
+                break
+            elif item in positive_feedback[key]:
+                continue
+            else:
+                n = n + 1
+    return res_map, res_ndcg, res_pre
+
+
+def evaluate_topk_simple(prediction, items):
+    """MF.py:265-274 / WDMF.py:247-256: hit iff the target is anywhere in the retrieved list."""
+    return [1 if items[i] in prediction[i] else 0 for i in range(len(items))]
+
+
+def topk_lowest_index(score, tp):
+    """`tf.nn.top_k(score, tp)` indices: descending score, lower index first among equals."""
+    score = np.asarray(score)
+    order = np.lexsort((np.arange(score.shape[1])[None, :].repeat(score.shape[0], 0), -score), axis=1)
+    return order[:, :tp].astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------------
+# small fp32 helpers
+# ----------------------------------------------------------------------------------------------------
+def _f32(x):
+    return np.asarray(x, dtype=F32)
+
+
+def _sigmoid(x):
+    x = _f32(x)
+    return (F32(1.0) / (F32(1.0) + np.exp(-x))).astype(F32)
+
+
+def seq_sum(a, axis):
+    """Sequential fp32 sum along `axis` (index 0,1,2,... order) -- the canonical order of the CUDA kernels
+    where the count is small (fields of one sample)."""
+    a = np.moveaxis(_f32(a), axis, 0)
+    acc = a[0].copy()
+    for t in range(1, a.shape[0]):
+        acc = (acc + a[t]).astype(F32)
+    return acc
+
+
+def seq_dot(a, b):
+    """sum_k fl(a_k*b_k) for k ascending, fp32, multiply and add rounded separately (no FMA).
+    a: [..., K], b: [..., K] broadcastable."""
+    a = _f32(a); b = _f32(b)
+    K = a.shape[-1]
+    acc = (a[..., 0] * b[..., 0]).astype(F32)
+    for k in range(1, K):
+        acc = (acc + (a[..., k] * b[..., k]).astype(F32)).astype(F32)
+    return acc
+
+
+# ----------------------------------------------------------------------------------------------------
+# FM: FM.py:99-126
+# ----------------------------------------------------------------------------------------------------
+def fm_forward(X, V, b, b0, val=None):
+    """out[B] = sum_k 0.5((sum_f e_f)^2 - sum_f e_f^2) + sum_f b[x_f] + b0   (FM.py:99-120).
+    e_f = val_f * V[x_f]; the reference's values are implicitly 1.0."""
+    E = _f32(V)[X]                                       # :99  [B,F,K]
+    if val is not None:
+        E = (E * _f32(val)[:, :, None]).astype(F32)
+    S = E.sum(axis=1, dtype=F32)                         # :100
+    Q = (E * E).astype(F32).sum(axis=1, dtype=F32)       # :105-106
+    fm = (F32(0.5) * (S * S - Q)).astype(F32)            # :109
+    bil = fm.sum(axis=1, dtype=F32)                      # :113,117
+    fb = _f32(b).reshape(-1)[X]
+    if val is not None:
+        fb = (fb * _f32(val)).astype(F32)
+    fb = fb.sum(axis=1, dtype=F32)                       # :118
+    out = (bil + fb + F32(b0)).astype(F32)               # :119-120
+    return out, E, S
+
+
+def fm_loss_grads(X, Y, V, b, b0, lamda=0.0, val=None):
+    """Squared loss (FM.py:123-126) and its gradients (TF autodiff of the graph above).
+    Returns loss, out, dV (dense [M,K]; includes +lamda*V when lamda>0), db [M], db0, and the list of
+    touched rows.  Duplicate ids inside a row and across rows are summed (UnsortedSegmentSum)."""
+    V = _f32(V); Y = _f32(Y).reshape(-1)
+    out, E, S = fm_forward(X, V, b, b0, val)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)                              # d loss / d out
+    if val is None:
+        dE = (g[:, None, None] * (S[:, None, :] - E)).astype(F32)
+        dbe = np.broadcast_to(g[:, None], X.shape).astype(F32)
+    else:
+        vv = _f32(val)[:, :, None]
+        dE = (g[:, None, None] * vv * (S[:, None, :] - E)).astype(F32)
+        dbe = (g[:, None] * _f32(val)).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, X.reshape(-1), dE.reshape(-1, V.shape[1]))
+    db = np.zeros(V.shape[0], F32)
+    np.add.at(db, X.reshape(-1), dbe.reshape(-1))
+    db0 = g.sum(dtype=F32)
+    if lamda > 0:
+        loss = F32(loss + F32(lamda) * F32(0.5) * (V * V).astype(F32).sum(dtype=F32))   # :124
+        dV = (dV + F32(lamda) * V).astype(F32)
+    return F32(loss), out, dV, db, F32(db0), np.unique(X)
+
+
+# ----------------------------------------------------------------------------------------------------
+# MF: MF.py:81-98  (dropout keep=1 => identity; the bias term is computed but not added, :91-92)
+# ----------------------------------------------------------------------------------------------------
+def mf_forward(X, V):
+    u = _f32(V)[X[:, 0]]; it = _f32(V)[X[:, 1]]
+    return (u * it).astype(F32).sum(axis=1, dtype=F32), u, it
+
+
+def mf_loss_grads(X, Y, V, lamda=0.0):
+    V = _f32(V); Y = _f32(Y).reshape(-1)
+    out, u, it = mf_forward(X, V)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, X[:, 0], (g[:, None] * it).astype(F32))
+    np.add.at(dV, X[:, 1], (g[:, None] * u).astype(F32))
+    if lamda > 0:
+        loss = F32(loss + F32(lamda) * F32(0.5) * (V * V).astype(F32).sum(dtype=F32))
+        dV = (dV + F32(lamda) * V).astype(F32)
+    return F32(loss), out, dV
+
+
+# ----------------------------------------------------------------------------------------------------
+# HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88): pairwise ranking with max-negative
+# ----------------------------------------------------------------------------------------------------
+def _pool(E, mode):
+    """Pooling1*/(tf.reduce_sum|reduce_max|reduce_mean)(E, axis=1) (OurModel7.py:14-19)."""
+    if mode == POOL_SUM:
+        return E.sum(axis=1, dtype=F32)
+    if mode == POOL_MEAN:
+        return E.mean(axis=1, dtype=F32)
+    return E.max(axis=1)
+
+
+def _pool_bwd(E, out, d_out, mode):
+    """Gradient of _pool w.r.t. E [B,n,K].  reduce_max splits equally among ties (TF _MinOrMaxGrad)."""
+    n = E.shape[1]
+    if mode == POOL_SUM:
+        return np.broadcast_to(d_out[:, None, :], E.shape).astype(F32)
+    if mode == POOL_MEAN:
+        return np.broadcast_to((d_out / F32(n))[:, None, :], E.shape).astype(F32)
+    ind = (E == out[:, None, :]).astype(F32)
+    cnt = ind.sum(axis=1, keepdims=True, dtype=F32)
+    return (ind / cnt * d_out[:, None, :]).astype(F32)
+
+
+def hybrid_feature(V, Pos, Fea=None, Tim=None, pools=(POOL_SUM, POOL_SUM, POOL_SUM)):
+    """hyb = Pool1F(stack[users, Pool1C(V[Fea]), Pool1T(V[Tim])]) (OurModel7.py:105-168).  The pooled pair
+    products (Pool2*) are built but commented out of the sums in the reference (:124,141,168) -> omitted.
+    BPR (BPR.py:76) is the special case Fea=Tim=None: hyb = V[user]."""
+    V = _f32(V)
+    parts = {"u": V[Pos[:, 0]]}
+    stack = [parts["u"]]
+    if Fea is not None and Fea.shape[1] > 0:
+        parts["EC"] = V[Fea]; parts["C"] = _pool(parts["EC"], pools[0]); stack.append(parts["C"])
+    if Tim is not None and Tim.shape[1] > 0:
+        parts["ET"] = V[Tim]; parts["T"] = _pool(parts["ET"], pools[1]); stack.append(parts["T"])
+    parts["stack"] = np.stack(stack, axis=1)             # [B,num,K]
+    if len(stack) == 1:
+        hyb = stack[0]
+        parts["single"] = True
+    else:
+        hyb = _pool(parts["stack"], pools[2])
+    return hyb.astype(F32), parts
+
+
+def pairrank_scores(V, Pos, Neg, Fea=None, Tim=None, pools=(0, 0, 0)):
+    """PositiveFeadback [B] and NegativeFeadback [B,NG] (OurModel7.py:171-172, BPR.py:79-80)."""
+    V = _f32(V)
+    hyb, parts = hybrid_feature(V, Pos, Fea, Tim, pools)
+    vp = V[Pos[:, 1]]
+    pos = (hyb * vp).astype(F32).sum(axis=1, dtype=F32)
+    if Neg is None:
+        return pos, None, hyb, parts
+    vn = V[Neg]
+    neg = (hyb[:, None, :] * vn).astype(F32).sum(axis=2, dtype=F32)
+    return pos, neg, hyb, parts
+
+
+def pairrank_loss_grads(V, Pos, Neg, Fea=None, Tim=None, pools=(0, 0, 0), lamda=0.0):
+    """loss = -sum log(sigmoid(pos - max_j neg_j)) (+ lamda*0.5*||V||^2)  (OurModel7.py:174-182, BPR.py:81-86)
+    and the dense gradient dV.  Also returns pos, neg."""
+    V = _f32(V)
+    pos, neg, hyb, parts = pairrank_scores(V, Pos, Neg, Fea, Tim, pools)
+    m = neg.max(axis=1)
+    x = (pos - m).astype(F32)
+    sg = _sigmoid(x)
+    loss = -np.log(sg).astype(F32).sum(dtype=F32)
+    g = (sg - F32(1.0)).astype(F32)                      # d loss / d x  = -(1 - sigmoid(x))
+    tie = (neg == m[:, None]).astype(F32)
+    dneg = (-g[:, None] * tie / tie.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+    vp = V[Pos[:, 1]]; vn = V[Neg]
+    dhyb = (g[:, None] * vp + (dneg[:, :, None] * vn).astype(F32).sum(axis=1, dtype=F32)).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, Pos[:, 1], (g[:, None] * hyb).astype(F32))
+    np.add.at(dV, Neg.reshape(-1), (dneg[:, :, None] * hyb[:, None, :]).astype(F32).reshape(-1, V.shape[1]))
+    if parts.get("single"):
+        np.add.at(dV, Pos[:, 0], dhyb)
+    else:
+        dstack = _pool_bwd(parts["stack"], hyb, dhyb, pools[2])
+        s = 0
+        np.add.at(dV, Pos[:, 0], dstack[:, s]); s += 1
+        if "C" in parts:
+            dEC = _pool_bwd(parts["EC"], parts["C"], dstack[:, s], pools[0]); s += 1
+            np.add.at(dV, Fea.reshape(-1), dEC.reshape(-1, V.shape[1]))
+        if "T" in parts:
+            dET = _pool_bwd(parts["ET"], parts["T"], dstack[:, s], pools[1]); s += 1
+            np.add.at(dV, Tim.reshape(-1), dET.reshape(-1, V.shape[1]))
+    if lamda > 0:
+        loss = F32(loss + F32(lamda) * F32(0.5) * (V * V).astype(F32).sum(dtype=F32))
+        dV = (dV + F32(lamda) * V).astype(F32)
+    return F32(loss), pos, neg, dV
+
+
+# ----------------------------------------------------------------------------------------------------
+# AFM: AFM.py:103-148
+# ----------------------------------------------------------------------------------------------------
+def pair_index(F):
+    """(i,j), i<j in the lexicographic order of AFM.py:107-110."""
+    return [(i, j) for i in range(F) for j in range(i + 1, F)]
+
+
+def afm_forward(X, w):
+    """w: dict feature_embeddings [M,K], feature_bias [M,1], bias, attention_W [K,A], attention_b [1,A],
+    attention_p [A], prediction [K,1].  Returns out [B] and a cache for the backward."""
+    V = _f32(w["feature_embeddings"])
+    E = V[X]                                                             # :103
+    pi = pair_index(X.shape[1])
+    I = np.array([p[0] for p in pi]); J = np.array([p[1] for p in pi])
+    P = (E[:, I, :] * E[:, J, :]).astype(F32)                            # :105-112  [B,P,K]
+    W = _f32(w["attention_W"]); ab = _f32(w["attention_b"]).reshape(-1); ap = _f32(w["attention_p"]).reshape(-1)
+    Z = (P.reshape(-1, P.shape[2]) @ W).astype(F32).reshape(P.shape[0], P.shape[1], -1) + ab   # :117-118,123
+    H = np.maximum(Z, F32(0)).astype(F32)
+    s = (H * ap).astype(F32).sum(axis=2, dtype=F32)                      # :123-124  [B,P]
+    smax = s.max(axis=1, keepdims=True)
+    ex = np.exp((s - smax).astype(F32)).astype(F32)
+    a = (ex / ex.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)      # :125 softmax over pairs
+    afm = (a[:, :, None] * P).astype(F32).sum(axis=1, dtype=F32)         # :130  [B,K]
+    wp = _f32(w["prediction"]).reshape(-1)
+    bil = (afm * wp).astype(F32).sum(axis=1, dtype=F32)                  # :138-139
+    fb = _f32(w["feature_bias"]).reshape(-1)[X].sum(axis=1, dtype=F32)   # :140
+    out = (bil + fb + F32(np.asarray(w["bias"]).reshape(()))).astype(F32)  # :141-142
+    return out, dict(E=E, P=P, Z=Z, H=H, a=a, afm=afm, I=I, J=J)
+
+
+def afm_loss_grads(X, Y, w, lamda_attention=0.0):
+    """0.5*sum(y-out)^2 + lamda_attention*0.5*||attention_W||^2 (AFM.py:146) and all gradients."""
+    Y = _f32(Y).reshape(-1)
+    out, c = afm_forward(X, w)
+    V = _f32(w["feature_embeddings"]); W = _f32(w["attention_W"])
+    ap = _f32(w["attention_p"]).reshape(-1); wp = _f32(w["prediction"]).reshape(-1)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)
+    B, Pn, K = c["P"].shape
+    d_afm = (g[:, None] * wp[None, :]).astype(F32)                       # [B,K]
+    d_wp = (g[:, None] * c["afm"]).astype(F32).sum(axis=0, dtype=F32)
+    d_a = (c["P"] * d_afm[:, None, :]).astype(F32).sum(axis=2, dtype=F32)      # [B,P]
+    dP = (c["a"][:, :, None] * d_afm[:, None, :]).astype(F32)
+    d_s = (c["a"] * (d_a - (c["a"] * d_a).astype(F32).sum(axis=1, keepdims=True, dtype=F32))).astype(F32)
+    d_ap = (d_s[:, :, None] * c["H"]).astype(F32).sum(axis=(0, 1), dtype=F32)
+    d_Z = (d_s[:, :, None] * ap[None, None, :] * (c["Z"] > 0)).astype(F32)       # [B,P,A]
+    d_ab = d_Z.sum(axis=(0, 1), dtype=F32)
+    d_W = (c["P"].reshape(-1, K).T @ d_Z.reshape(B * Pn, -1)).astype(F32)
+    dP = (dP + (d_Z.reshape(B * Pn, -1) @ W.T).astype(F32).reshape(B, Pn, K)).astype(F32)
+    dE = np.zeros_like(c["E"])
+    np.add.at(dE, (slice(None), c["I"]), (dP * c["E"][:, c["J"], :]).astype(F32))
+    np.add.at(dE, (slice(None), c["J"]), (dP * c["E"][:, c["I"], :]).astype(F32))
+    dV = np.zeros_like(V)
+    np.add.at(dV, X.reshape(-1), dE.reshape(-1, K))
+    db = np.zeros(V.shape[0], F32)
+    np.add.at(db, X.reshape(-1), np.broadcast_to(g[:, None], X.shape).reshape(-1))
+    if lamda_attention > 0:
+        loss = F32(loss + F32(lamda_attention) * F32(0.5) * (W * W).astype(F32).sum(dtype=F32))
+        d_W = (d_W + F32(lamda_attention) * W).astype(F32)
+    grads = dict(feature_embeddings=dV, feature_bias=db.reshape(-1, 1), bias=g.sum(dtype=F32),
+                 attention_W=d_W, attention_b=d_ab.reshape(1, -1), attention_p=d_ap, prediction=d_wp.reshape(-1, 1))
+    return F32(loss), out, grads
+
+
+# ----------------------------------------------------------------------------------------------------
+# DeepFM: DFM.py:104-152
+# ----------------------------------------------------------------------------------------------------
+def dfm_forward(X, w, n_layers=3):
+    V = _f32(w["feature_embeddings"])
+    E = V[X]                                                             # :104-105
+    y1 = _f32(w["feature_bias"]).reshape(-1)[X]                          # :109-110  [B,F]
+    S = E.sum(axis=1, dtype=F32)
+    y2 = (F32(0.5) * (S * S - (E * E).astype(F32).sum(axis=1, dtype=F32))).astype(F32)   # :114-122
+    h = E.reshape(E.shape[0], -1)                                        # :125
+    acts = [h]
+    for i in range(n_layers):                                            # :126-128
+        h = np.maximum((h @ _f32(w["layer_%d" % i])).astype(F32) + _f32(w["bias_%d" % i]).reshape(1, -1), F32(0)).astype(F32)
+        acts.append(h)
+    cat = np.concatenate([y1, y2, h], axis=1)                            # :131-132
+    out = ((cat @ _f32(w["concat_projection"])).astype(F32).reshape(-1) + F32(np.asarray(w["concat_bias"]).reshape(()))).astype(F32)  # :137
+    return out, dict(E=E, S=S, acts=acts, cat=cat)
+
+
+# ----------------------------------------------------------------------------------------------------
+# optimizers: TF1 semantics (FM.py:129-136, BPR.py:93, MF.py:104)
+# ----------------------------------------------------------------------------------------------------
+def adagrad_dense(w, acc, g, lr):
+    """ApplyAdagrad: acc += g^2; w -= lr * g / sqrt(acc)   (no epsilon; acc0 = 0.1 or 1e-8)."""
+    acc = (_f32(acc) + (_f32(g) * _f32(g)).astype(F32)).astype(F32)
+    w = (_f32(w) - (F32(lr) * _f32(g) / np.sqrt(acc)).astype(F32)).astype(F32)
+    return w, acc
+
+
+def adagrad_rows(w, acc, g, rows, lr):
+    """SparseApplyAdagrad on the de-duplicated rows: untouched rows keep w and acc."""
+    w = _f32(w).copy(); acc = _f32(acc).copy()
+    w[rows], acc[rows] = adagrad_dense(w[rows], acc[rows], _f32(g)[rows], lr)
+    return w, acc
+
+
+def adam_dense(w, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
+    """TF1 AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); var -= lr_t*m/(sqrt(v)+eps).  The sparse path
+    (`_apply_sparse_shared`) decays m,v of every row and moves every row, i.e. equals this with zero rows."""
+    lr_t = F32(lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
+    g = _f32(g)
+    m = (F32(beta1) * _f32(m) + F32(1 - beta1) * g).astype(F32)
+    v = (F32(beta2) * _f32(v) + F32(1 - beta2) * (g * g).astype(F32)).astype(F32)
+    w = (_f32(w) - (lr_t * m / (np.sqrt(v) + F32(eps))).astype(F32)).astype(F32)
+    return w, m, v
+
+
+def momentum_dense(w, acc, g, lr, momentum=0.95):
+    """ApplyMomentum: acc = acc*momentum + g; w -= lr*acc."""
+    acc = (_f32(acc) * F32(momentum) + _f32(g)).astype(F32)
+    return (_f32(w) - F32(lr) * acc).astype(F32), acc
+
+
+def momentum_rows(w, acc, g, rows, lr, momentum=0.95):
+    w = _f32(w).copy(); acc = _f32(acc).copy()
+    w[rows], acc[rows] = momentum_dense(w[rows], acc[rows], _f32(g)[rows], lr, momentum)
+    return w, acc
+
+
+def sgd_dense(w, g, lr):
+    return (_f32(w) - F32(lr) * _f32(g)).astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------------
+# full-catalog top-N: canonical fp32 scores + lowest-index top_k
+# ----------------------------------------------------------------------------------------------------
+def fm_topk_scores(A, V, b, n_user, n_item):
+    """FM.topk (FM.py:174-185): score[c,n] = b[n] + sum_k (u+Fc)_k * (v_n+Fc)_k, Fc = sum of ctx rows.
+    Canonical order: Fc sequential over columns 2..; A_k = fl(u_k+Fc_k); B_nk = fl(v_nk+Fc_k); seq_dot;
+    then fl(bias + score)."""
+    V = _f32(V)
+    u = V[A[:, 0]]
+    if A.shape[1] > 2:
+        Fc = seq_sum(V[A[:, 2:]], axis=1)
+    else:
+        Fc = np.zeros_like(u)
+    UF = (u + Fc).astype(F32)                                   # :177
+    items = V[n_user:n_user + n_item]
+    IF = (items[None, :, :] + Fc[:, None, :]).astype(F32)       # :178
+    score = seq_dot(UF[:, None, :], IF)                         # :180-183
+    bias = _f32(b).reshape(-1)[n_user:n_user + n_item]
+    return (bias[None, :] + score).astype(F32)                  # :185
+
+
+def dot_topk_scores(Q, V, n_user, n_item):
+    """BPR.topk / MF.topk / OUR.topk (BPR.py:132-135, MF.py:145-148, OurModel7.py:294): score = q_c . v_n."""
+    items = _f32(V)[n_user:n_user + n_item]
+    return seq_dot(_f32(Q)[:, None, :], items[None, :, :])
+
+
+def afm_topk_scores(A, w, n_user, n_item):
+    """AFM.topk (AFM.py:209-246): un-normalised exp attention over user/context pairs and item x field
+    pairs; score = (sum a*P / sum a) . w_pred + b[n]."""
+    V = _f32(w["feature_embeddings"]); W = _f32(w["attention_W"])
+    ab = _f32(w["attention_b"]).reshape(-1); ap = _f32(w["attention_p"]).reshape(-1)
+    wp = _f32(w["prediction"]).reshape(-1)
+    UF = np.concatenate([V[A[:, 0]][:, None, :], V[A[:, 2:]]], axis=1)          # :210-212 [C,uf,K]
+    uf_n = UF.shape[1]
+    pi = pair_index(uf_n)
+    if pi:
+        I = np.array([p[0] for p in pi]); J = np.array([p[1] for p in pi])
+        uf = (UF[:, I] * UF[:, J]).astype(F32)                                  # :214-220
+        z = np.maximum((uf @ W).astype(F32) + ab, F32(0))
+        a_uf = np.exp((z * ap).astype(F32).sum(axis=2, dtype=F32)).astype(F32)  # :223-224 [C,P]
+        UFwise = (uf * a_uf[:, :, None]).astype(F32).sum(axis=1, dtype=F32)     # :232
+        a_sum = a_uf.sum(axis=1, dtype=F32)
+    else:
+        UFwise = np.zeros((A.shape[0], V.shape[1]), F32); a_sum = np.zeros(A.shape[0], F32)
+    items = V[n_user:n_user + n_item]
+    out = np.empty((A.shape[0], n_item), F32)
+    bias = _f32(w["feature_bias"]).reshape(-1)[n_user:n_user + n_item]
+    for c in range(A.shape[0]):                                                 # row loop bounds memory
+        ufi = (UF[c][None, :, :] * items[:, None, :]).astype(F32)              # :227  [N,uf,K]
+        zi = np.maximum((ufi @ W).astype(F32) + ab, F32(0))
+        a_i = np.exp((zi * ap).astype(F32).sum(axis=2, dtype=F32)).astype(F32)  # :230  [N,uf]
+        Iw = (ufi * a_i[:, :, None]).astype(F32).sum(axis=1, dtype=F32)         # :233
+        s1 = (UFwise[c][None, :] + Iw).astype(F32)                              # :234
+        wgt = (a_sum[c] + a_i.sum(axis=1, dtype=F32)).astype(F32)               # :235
+        s2 = (s1 / wgt[:, None]).astype(F32)                                    # :236
+        out[c] = ((s2 * wp).astype(F32).sum(axis=1, dtype=F32) + bias).astype(F32)   # :239-243
+    return out
+
+
+def hhfm_topk_scores(A, V, n_user, n_item, n_ctx, n_time, pools=(0, 0, 0)):
+    """OUR.topk (OurModel7.py:229-295): A = [user, item, ctx..., time...]; hyb as in training."""
+    Fea = A[:, 2:2 + n_ctx] if n_ctx > 0 else None
+    Tim = A[:, 2 + n_ctx:2 + n_ctx + n_time] if n_time > 0 else None
+    hyb, _ = hybrid_feature_seq(V, A[:, :2], Fea, Tim, pools)
+    return dot_topk_scores(hyb, V, n_user, n_item)
+
+
+def hybrid_feature_seq(V, Pos, Fea, Tim, pools):
+    """hybrid_feature with the canonical sequential pooling order used by the top-N query builder."""
+    V = _f32(V)
+
+    def pool(E, mode):
+        if mode == POOL_MAX:
+            return E.max(axis=1)
+        s = seq_sum(E, axis=1)
+        return s if mode == POOL_SUM else (s / F32(E.shape[1])).astype(F32)
+
+    stack = [V[Pos[:, 0]]]
+    if Fea is not None and Fea.shape[1] > 0:
+        stack.append(pool(V[Fea], pools[0]))
+    if Tim is not None and Tim.shape[1] > 0:
+        stack.append(pool(V[Tim], pools[1]))
+    if len(stack) == 1:
+        return stack[0], None
+    return pool(np.stack(stack, axis=1), pools[2]).astype(F32), None
+
+
+# ----------------------------------------------------------------------------------------------------
+# AUC: FM.py:296-324
+# ----------------------------------------------------------------------------------------------------
+def auc_from_scores(pos_score, neg_score):
+    """fraction of (positive, sampled negative) pairs with pos > neg (FM.py:320-324).
+    pos_score [n], neg_score [n, 50]."""
+    return float(np.mean((np.asarray(pos_score)[:, None] > np.asarray(neg_score)).reshape(-1)))

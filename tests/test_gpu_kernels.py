@@ -1,0 +1,423 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): scores / losses / gradients within 1e-5 relative in fp32 (assert_close: element
+tolerance 1e-5 * max(|ref|, rms(ref))); top-K index lists, exact scores and HR/NDCG codes bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import hhfm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, cuda, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(cuda)
+
+
+def _lib_ptr():
+    from hhfm_b200 import _lib
+    from hhfm_b200.engine import cur_stream, ptr
+    return _lib, ptr, cur_stream
+
+
+def make_table(rng, M, K, scale=0.1):
+    return rng.normal(0, scale, (M, K)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K1 FM
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (5000, 10, 64), (333, 6, 128), (257, 13, 8), (100, 3, 16),
+                                   (65, 10, 32), (40, 5, 256), (31, 7, 100), (1, 1, 4), (70, 10, 512)])
+def test_fm_forward_matches_oracle(cuda, B, F, K):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(B * 1000 + K)
+    M = 500
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32); b0 = np.float32(0.25)
+    X = rng.integers(0, M, (B, F))
+    if F > 3:
+        X[:, 3] = X[:, 2]                                   # the same token in two columns shares one row
+    ref, _, _ = O.fm_forward(X, V, b, b0)
+    out = torch.empty(B, device=cuda)
+    tV, tb, tb0, tX = dev(V, cuda), dev(b, cuda), dev(np.array([b0]), cuda), dev(X, cuda, torch.int32)
+    lib.call("hhfm_fm_fwd", None, ptr(tX), None, B, F, ptr(tV), ptr(tb), ptr(tb0), M, K, 0, ptr(out), st())
+    assert_close(out.cpu().numpy(), ref, what="fm out")
+
+
+def test_fm_forward_csr_ragged_with_values(cuda):
+    """General CSR (variable row length incl. empty rows, explicit feature values)."""
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(7)
+    M, K, B = 300, 64, 200
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32)
+    lens = rng.integers(0, 12, B); lens[0] = 0; lens[-1] = 0
+    row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    col = rng.integers(0, M, row_ptr[-1]).astype(np.int32)
+    val = rng.uniform(0.5, 2.0, row_ptr[-1]).astype(np.float32)
+    ref = np.zeros(B, np.float32)
+    for s in range(B):
+        if lens[s] == 0:
+            ref[s] = 0.0
+            continue
+        sl = slice(row_ptr[s], row_ptr[s + 1])
+        ref[s] = O.fm_forward(col[sl][None, :], V, b, 0.0, val[sl][None, :])[0][0]
+    out = torch.empty(B, device=cuda)
+    lib.call("hhfm_fm_fwd", ptr(dev(row_ptr, cuda)), ptr(dev(col, cuda)), ptr(dev(val, cuda)), B, 0, ptr(dev(V, cuda)),
+             ptr(dev(b, cuda)), None, M, K, 0, ptr(out), st())
+    assert_close(out.cpu().numpy(), ref, what="fm csr out")
+
+
+def _fm_train_call(cuda, X, Y, V, b, b0, interaction=0, deterministic=0, track=True, val=None):
+    lib, ptr, st = _lib_ptr()
+    B, F = X.shape
+    M, K = V.shape
+    P = lib.partials_len()
+    tV = dev(V, cuda); tb = dev(b, cuda) if b is not None else None
+    tb0 = dev(np.array([b0], np.float32), cuda) if b0 is not None else None
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    lp = torch.full((P,), 123.0, device=cuda); out = torch.empty(B, device=cuda); loss = torch.zeros(1, device=cuda)
+    stamp = torch.zeros(M, dtype=torch.int32, device=cuda); rows = torch.full((M,), -1, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    tval = dev(val, cuda) if val is not None else None
+    lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(dev(X, cuda, torch.int32)), ptr(tval), B, F, ptr(tV), ptr(tb), ptr(tb0), M, K,
+             interaction, ptr(dev(Y.reshape(-1), cuda)), ptr(out), ptr(gV), ptr(gb) if b is not None else None,
+             ptr(gb0) if b0 is not None else None, ptr(lp), ptr(stamp) if track else None, 1, ptr(rows) if track else None,
+             ptr(cnt) if track else None, deterministic, st())
+    lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(loss), st())
+    n = int(cnt.item())
+    return dict(loss=float(loss.item()), out=out.cpu().numpy(), gV=gV.cpu().numpy(), gb=gb.cpu().numpy(),
+                gb0=float(gb0.item()), touched=np.sort(rows.cpu().numpy()[:n]))
+
+
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (5000, 10, 64), (999, 6, 128), (130, 12, 16), (77, 10, 256)])
+def test_fm_fused_train_pass_matches_oracle(cuda, B, F, K):
+    rng = np.random.default_rng(B + K)
+    M = 400
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32); b0 = np.float32(-0.1)
+    X = rng.integers(0, M, (B, F)); X[:, 1] = rng.integers(0, 3, B)      # heavy duplicates across rows
+    if F > 4:
+        X[:, 4] = X[:, 0]                                                # duplicate inside a row
+    Y = rng.choice([1.0, 0.0], (B, 1)).astype(np.float32)
+    loss, out, dV, db, db0, touched = O.fm_loss_grads(X, Y, V, b, b0, lamda=0.0)
+    got = _fm_train_call(cuda, X, Y, V, b, b0)
+    assert_close(got["out"], out, what="out")
+    assert_close(got["loss"], loss, what="loss")
+    assert_close(got["gV"], dV, what="gV")
+    assert_close(got["gb"], db, what="gbias")
+    assert_close(got["gb0"], db0, what="gb0")
+    assert (got["touched"] == touched).all()
+
+
+def test_fm_train_pass_with_feature_values(cuda):
+    rng = np.random.default_rng(3)
+    M, K, B, F = 200, 32, 300, 7
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32)
+    X = rng.integers(0, M, (B, F)); Y = rng.normal(0, 1, (B, 1)).astype(np.float32)
+    val = rng.uniform(0.5, 1.5, (B, F)).astype(np.float32)
+    loss, out, dV, db, db0, _ = O.fm_loss_grads(X, Y, V, b, 0.0, 0.0, val=val)
+    got = _fm_train_call(cuda, X, Y, V, b, 0.0, val=val)
+    assert_close(got["loss"], loss, what="loss"); assert_close(got["gV"], dV, what="gV"); assert_close(got["gb"], db, what="gb")
+
+
+def test_fm_deterministic_mode_is_bit_reproducible(cuda):
+    rng = np.random.default_rng(11)
+    M, K, B, F = 50, 64, 2000, 10
+    V = make_table(rng, M, K); b = np.zeros((M, 1), np.float32)
+    X = rng.integers(0, M, (B, F)); Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    a = _fm_train_call(cuda, X, Y, V, b, 0.0, deterministic=1)
+    c = _fm_train_call(cuda, X, Y, V, b, 0.0, deterministic=1)
+    assert (a["gV"].view(np.int32) == c["gV"].view(np.int32)).all() and a["loss"] == c["loss"]
+    ref = O.fm_loss_grads(X, Y, V, b, 0.0, 0.0)
+    assert_close(a["gV"], ref[2], what="det gV")
+
+
+def test_mf_interaction_matches_oracle(cuda):
+    rng = np.random.default_rng(5)
+    M, K, B = 300, 64, 1000
+    V = make_table(rng, M, K)
+    X = rng.integers(0, M, (B, 2)); Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    loss, out, dV = O.mf_loss_grads(X, Y, V, 0.0)
+    got = _fm_train_call(cuda, X, Y, V, None, None, interaction=1)
+    assert_close(got["out"], out, what="mf out"); assert_close(got["loss"], loss, what="mf loss")
+    assert_close(got["gV"], dV, what="mf gV")
+
+
+def test_fm_backward_entry_point(cuda):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(9)
+    M, K, B, F = 120, 64, 500, 10
+    V = make_table(rng, M, K); X = rng.integers(0, M, (B, F)); gout = rng.normal(0, 1, B).astype(np.float32)
+    E = V[X]; S = E.sum(1)
+    dV = np.zeros_like(V); np.add.at(dV, X.reshape(-1), (gout[:, None, None] * (S[:, None, :] - E)).reshape(-1, K))
+    db = np.zeros(M, np.float32); np.add.at(db, X.reshape(-1), np.repeat(gout, F))
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    lib.call("hhfm_fm_bwd", None, ptr(dev(X, cuda, torch.int32)), None, B, F, ptr(dev(V, cuda)), M, K, 0, ptr(dev(gout, cuda)),
+             ptr(gV), ptr(gb), ptr(gb0), 0, st())
+    assert_close(gV.cpu().numpy(), dV, what="bwd gV"); assert_close(gb.cpu().numpy(), db, what="bwd gb")
+    assert_close(gb0.item(), gout.sum(), what="bwd gb0")
+
+
+# ----------------------------------------------------------------------------------------------------
+# K3 HHFM / BPR
+# ----------------------------------------------------------------------------------------------------
+def _records(Pos, Fea, Tim, Neg):
+    parts = [Pos] + [p for p in (Fea, Tim, Neg) if p is not None and p.shape[1] > 0]
+    w = sum(p.shape[1] for p in parts)
+    stride = (w + 3) // 4 * 4
+    rec = np.full((Pos.shape[0], stride), -1, np.int32)
+    rec[:, :w] = np.concatenate(parts, axis=1)
+    return rec, stride
+
+
+def _pairrank_train(cuda, V, Pos, Fea, Tim, Neg, pools, deterministic=0):
+    lib, ptr, st = _lib_ptr()
+    M, K = V.shape
+    rec, stride = _records(Pos, Fea, Tim, Neg)
+    B = rec.shape[0]
+    nc = 0 if Fea is None else Fea.shape[1]; nt = 0 if Tim is None else Tim.shape[1]; ng = Neg.shape[1]
+    P = lib.partials_len()
+    gV = torch.zeros(M, K, device=cuda); lp = torch.full((P,), -5.0, device=cuda); loss = torch.zeros(1, device=cuda)
+    pos = torch.empty(B, device=cuda); neg = torch.empty(B, ng, device=cuda)
+    stamp = torch.zeros(M, dtype=torch.int32, device=cuda); rows = torch.zeros(M, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    lib.call("hhfm_pairrank_fwd_bwd", ptr(dev(rec, cuda)), B, stride, nc, nt, ng, pools[0], pools[1], pools[2],
+             ptr(dev(V, cuda)), M, K, ptr(pos), ptr(neg), ptr(gV), ptr(lp), ptr(stamp), 3, ptr(rows), ptr(cnt), deterministic, st())
+    lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(loss), st())
+    return dict(loss=float(loss.item()), pos=pos.cpu().numpy(), neg=neg.cpu().numpy(), gV=gV.cpu().numpy(),
+                touched=np.sort(rows.cpu().numpy()[:int(cnt.item())]))
+
+
+@pytest.mark.parametrize("pools", [(0, 0, 0), (1, 1, 1), (2, 2, 2), (1, 0, 2), (0, 2, 1)])
+@pytest.mark.parametrize("B,K,fc,ft", [(64, 64, 8, 0), (5000, 64, 8, 0), (700, 128, 5, 5), (300, 16, 3, 3), (200, 32, 0, 3)])
+def test_hhfm_fused_pass_matches_oracle(cuda, pools, B, K, fc, ft):
+    rng = np.random.default_rng(B + K + fc)
+    M, NG = 600, 10
+    V = make_table(rng, M, K)
+    Pos = rng.integers(0, M, (B, 2))
+    Fea = rng.integers(0, M, (B, fc)) if fc else None
+    Tim = rng.integers(0, M, (B, ft)) if ft else None
+    if fc > 1:
+        Fea[:, 1] = Fea[:, 0]                       # same token twice in the group -> exact max-pool ties
+    if ft > 2:
+        Tim[:, 2] = Tim[:, 0]
+    Neg = rng.integers(0, M, (B, NG)); Neg[:, 3] = Neg[:, 2]; Neg[::7] = Neg[::7, :1]   # duplicate / all-same negatives
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, Tim, pools, 0.0)
+    got = _pairrank_train(cuda, V, Pos, Fea, Tim, Neg, pools)
+    assert_close(got["pos"], pos, what="pos"); assert_close(got["neg"], neg, what="neg")
+    assert_close(got["loss"], loss, what="loss")
+    assert_close(got["gV"], dV, what="gV")
+    assert set(got["touched"].tolist()) <= set(np.unique(np.concatenate([a.reshape(-1) for a in (Pos, Fea, Tim, Neg) if a is not None])).tolist())
+    assert set(np.unique(Pos).tolist()) <= set(got["touched"].tolist())
+
+
+def test_bpr_is_the_no_context_special_case(cuda):
+    rng = np.random.default_rng(21)
+    M, K, B = 400, 128, 3000
+    V = make_table(rng, M, K); Pos = rng.integers(0, M, (B, 2)); Neg = rng.integers(0, M, (B, 10))
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, None, None, (0, 0, 0), 0.0)
+    got = _pairrank_train(cuda, V, Pos, None, None, Neg, (0, 0, 0))
+    assert_close(got["loss"], loss, what="bpr loss"); assert_close(got["gV"], dV, what="bpr gV")
+
+
+def test_pairrank_forward_and_backward_entry_points(cuda):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(22)
+    M, K, B, NG = 300, 64, 400, 6
+    V = make_table(rng, M, K); Pos = rng.integers(0, M, (B, 2)); Fea = rng.integers(0, M, (B, 4)); Neg = rng.integers(0, M, (B, NG))
+    rec, stride = _records(Pos, Fea, None, Neg)
+    pos = torch.empty(B, device=cuda); neg = torch.empty(B, NG, device=cuda)
+    tV, trec = dev(V, cuda), dev(rec, cuda)
+    lib.call("hhfm_pairrank_fwd", ptr(trec), B, stride, 4, 0, NG, 0, 0, 0, ptr(tV), M, K, ptr(pos), ptr(neg), st())
+    rp, rn, hyb, _ = O.pairrank_scores(V, Pos, Neg, Fea, None, (0, 0, 0))
+    assert_close(pos.cpu().numpy(), rp, what="pos"); assert_close(neg.cpu().numpy(), rn, what="neg")
+    dpos = rng.normal(0, 1, B).astype(np.float32); dneg = rng.normal(0, 1, (B, NG)).astype(np.float32)
+    tVg = torch.tensor(V, requires_grad=True)
+    h = tVg[Pos[:, 0]] + tVg[Fea].sum(1)
+    ((h * tVg[Pos[:, 1]]).sum(1) * torch.tensor(dpos)).sum().add(((h[:, None, :] * tVg[Neg]).sum(2) * torch.tensor(dneg)).sum()).backward()
+    gV = torch.zeros(M, K, device=cuda)
+    lib.call("hhfm_pairrank_bwd", ptr(trec), B, stride, 4, 0, NG, 0, 0, 0, ptr(tV), M, K, ptr(dev(dpos, cuda)), ptr(dev(dneg, cuda)),
+             ptr(gV), 0, st())
+    assert_close(gV.cpu().numpy(), tVg.grad.numpy(), what="pairrank bwd gV")
+
+
+# ----------------------------------------------------------------------------------------------------
+# K4/K5 scatter + optimizers
+# ----------------------------------------------------------------------------------------------------
+def test_scatter_add_rows_sums_duplicates(cuda):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(1)
+    M, K, n = 100, 64, 5000
+    rows = rng.integers(0, 5, n).astype(np.int32); src = rng.normal(0, 1, (n, K)).astype(np.float32)
+    ref = np.zeros((M, K), np.float32); np.add.at(ref, rows, src)
+    dst = torch.zeros(M, K, device=cuda)
+    lib.call("hhfm_scatter_add_rows", ptr(dev(rows, cuda)), ptr(dev(src, cuda)), n, K, ptr(dst), M, st())
+    assert_close(dst.cpu().numpy(), ref, rtol=2e-5, what="scatter")
+
+
+@pytest.mark.parametrize("n", [4096, 4099, 3, 1])
+def test_dense_optimizers_match_tf1_semantics(cuda, n):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(n)
+    w0 = rng.normal(0, 0.1, n).astype(np.float32); g0 = rng.normal(0, 1, n).astype(np.float32)
+    lam, lr = 0.1, 0.05
+    P = lib.partials_len()
+    # adagrad
+    w, acc, g = dev(w0, cuda), torch.full((n,), 0.1, device=cuda), dev(g0, cuda)
+    sq = torch.zeros(P, device=cuda)
+    lib.call("hhfm_opt_adagrad_dense_l2", ptr(w), ptr(acc), ptr(g), n, lr, lam, 1, ptr(sq), st())
+    rw, racc = O.adagrad_dense(w0, np.full(n, 0.1, np.float32), g0 + np.float32(lam) * w0, lr)
+    assert_close(w.cpu().numpy(), rw, what="adagrad w"); assert_close(acc.cpu().numpy(), racc, what="adagrad acc")
+    assert (g.cpu().numpy() == 0).all()
+    assert_close(sq.sum().item(), (w0.astype(np.float64) ** 2).sum(), what="sum w^2")
+    # adam (t = 3)
+    w, m, v, g = dev(w0, cuda), dev(g0 * 0.1, cuda), dev(g0 * g0 * 0.01, cuda), dev(g0, cuda)
+    import math
+    lr_t = lr * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)
+    lib.call("hhfm_opt_adam_dense_l2", ptr(w), ptr(m), ptr(v), ptr(g), n, lr_t, 0.9, 0.999, 1e-8, 0.0, 0, None, st())
+    rw, rm, rv = O.adam_dense(w0, g0 * 0.1, g0 * g0 * 0.01, g0, lr, 3)
+    assert_close(w.cpu().numpy(), rw, what="adam w"); assert_close(m.cpu().numpy(), rm, what="adam m"); assert_close(v.cpu().numpy(), rv, what="adam v")
+    assert (g.cpu().numpy() == g0).all()
+    # momentum
+    w, a, g = dev(w0, cuda), dev(g0 * 0.5, cuda), dev(g0, cuda)
+    lib.call("hhfm_opt_momentum_dense_l2", ptr(w), ptr(a), ptr(g), n, lr, 0.95, 0.0, 1, None, st())
+    rw, ra = O.momentum_dense(w0, g0 * 0.5, g0, lr)
+    assert_close(w.cpu().numpy(), rw, what="momentum w"); assert_close(a.cpu().numpy(), ra, what="momentum acc")
+    # sgd
+    w, g = dev(w0, cuda), dev(g0, cuda)
+    lib.call("hhfm_opt_sgd_dense_l2", ptr(w), ptr(g), n, lr, 0.0, 1, None, st())
+    assert_close(w.cpu().numpy(), O.sgd_dense(w0, g0, lr), what="sgd w")
+
+
+def test_row_optimizers_move_only_touched_rows(cuda):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(2)
+    M, K = 300, 64
+    w0 = make_table(rng, M, K); g0 = np.zeros((M, K), np.float32)
+    touched = np.sort(rng.choice(M, 40, replace=False)).astype(np.int32)
+    g0[touched] = rng.normal(0, 1, (40, K)).astype(np.float32)
+    rows = np.full(M, -1, np.int32); rows[:40] = rng.permutation(touched)
+    cnt = dev(np.array([40], np.int32), cuda)
+    w, acc, g = dev(w0, cuda), torch.full((M, K), 1e-8, device=cuda), dev(g0, cuda)
+    lib.call("hhfm_opt_adagrad_rows", ptr(w), ptr(acc), ptr(g), ptr(dev(rows, cuda)), ptr(cnt), M, K, 0.01, 1, st())
+    rw, racc = O.adagrad_rows(w0, np.full((M, K), 1e-8, np.float32), g0, touched, 0.01)
+    assert_close(w.cpu().numpy(), rw, what="rows w"); assert_close(acc.cpu().numpy(), racc, what="rows acc")
+    assert (g.cpu().numpy() == 0).all()
+    untouched = np.setdiff1d(np.arange(M), touched)
+    assert (w.cpu().numpy()[untouched] == w0[untouched]).all()
+    w, a, g = dev(w0, cuda), dev(g0 * 0 + 0.5, cuda), dev(g0, cuda)
+    lib.call("hhfm_opt_momentum_rows", ptr(w), ptr(a), ptr(g), ptr(dev(rows, cuda)), ptr(cnt), M, K, 0.1, 0.95, 0, st())
+    rw, ra = O.momentum_rows(w0, np.full((M, K), 0.5, np.float32), g0, touched, 0.1)
+    assert_close(w.cpu().numpy(), rw, what="mom rows w"); assert (a.cpu().numpy()[untouched] == 0.5).all()
+    # K == 1 (feature_bias vector)
+    b0 = rng.normal(0, 0.1, M).astype(np.float32); gb = np.zeros(M, np.float32); gb[touched] = 1.5
+    b, accb, g = dev(b0, cuda), torch.full((M,), 0.1, device=cuda), dev(gb, cuda)
+    lib.call("hhfm_opt_adagrad_rows", ptr(b), ptr(accb), ptr(g), ptr(dev(rows, cuda)), ptr(cnt), M, 1, 0.1, 1, st())
+    rb, _ = O.adagrad_rows(b0, np.full(M, 0.1, np.float32), gb, touched, 0.1)
+    assert_close(b.cpu().numpy(), rb, what="bias rows")
+
+
+# ----------------------------------------------------------------------------------------------------
+# K6 / K7 exact top-N and the metric walk
+# ----------------------------------------------------------------------------------------------------
+def _topn(cuda, kind, A, V, bias, n_user, n_item, tp, n_ctx, n_time, pools=(0, 0, 0), lo=0, hi=None):
+    from hhfm_b200.engine import TopN
+    t = TopN(cuda)
+    A_dev, stride = t.upload_rows(A, V.shape[0])
+    tb = dev(bias, cuda) if bias is not None else None
+    ids, sc = t.topk(kind, A_dev, stride, n_ctx, n_time, pools, dev(V, cuda), tb, n_user, n_item, tp, lo, hi, return_scores=True)
+    return ids.cpu().numpy(), sc.cpu().numpy()
+
+
+@pytest.mark.parametrize("C,N,K,tp,F", [(300, 4082, 64, 20, 10), (37, 580, 128, 20, 12), (5, 24, 16, 20, 10), (64, 1000, 256, 100, 4),
+                                        (3, 10, 8, 20, 2)])
+def test_fm_topk_lists_are_bit_exact(cuda, C, N, K, tp, F):
+    rng = np.random.default_rng(C + N)
+    n_user = 50; M = n_user + N + 40
+    V = make_table(rng, M, K); b = rng.normal(0, 0.01, (M, 1)).astype(np.float32)
+    A = np.concatenate([rng.integers(0, n_user, (C, 1)), rng.integers(n_user, n_user + N, (C, 1)),
+                        rng.integers(n_user + N, M, (C, F - 2))], axis=1)
+    ref = O.fm_topk_scores(A, V, b, n_user, N)
+    ids, sc = _topn(cuda, 1, A, V, b, n_user, N, tp, F - 2, 0)
+    want = O.topk_lowest_index(ref, tp)
+    k = min(tp, N)
+    assert (ids[:, :k] == want[:, :k]).all()
+    assert (ids[:, k:] == -1).all()
+    got_sc = np.take_along_axis(ref, want[:, :k], axis=1)
+    assert (sc[:, :k].view(np.int32) == got_sc.view(np.int32)).all(), "exact scores must be bit-identical to the oracle"
+
+
+def test_topk_tie_break_is_lowest_index(cuda):
+    """Quantised weights make many exactly equal scores; tf.nn.top_k keeps the lower index first."""
+    rng = np.random.default_rng(4)
+    n_user, N, K, C = 10, 500, 16, 40
+    M = n_user + N
+    V = rng.integers(-2, 3, (M, K)).astype(np.float32) * 0.25
+    V[n_user + 100:n_user + 200] = V[n_user:n_user + 100]          # duplicated items -> guaranteed ties
+    A = np.stack([rng.integers(0, n_user, C), rng.integers(n_user, M, C)], axis=1)
+    ref = O.dot_topk_scores(V[A[:, 0]], V, n_user, N)
+    ids, sc = _topn(cuda, 0, A, V, None, n_user, N, 50, 0, 0)
+    assert (ids == O.topk_lowest_index(ref, 50)).all()
+    # +0.0 and -0.0 compare equal
+    V2 = V.copy(); V2[0] = 0.0; V2[n_user:n_user + N:2] *= -1.0
+    A2 = np.stack([np.zeros(C, int), rng.integers(n_user, M, C)], axis=1)
+    ids2, _ = _topn(cuda, 0, A2, V2, None, n_user, N, 30, 0, 0)
+    assert (ids2 == np.arange(30)[None, :]).all()
+
+
+@pytest.mark.parametrize("pools", [(0, 0, 0), (1, 1, 1), (2, 2, 2)])
+def test_hhfm_topk_bit_exact(cuda, pools):
+    rng = np.random.default_rng(6)
+    n_user, N, K, C, fc, ft = 30, 777, 64, 100, 5, 5
+    M = n_user + N + 60
+    V = make_table(rng, M, K)
+    A = np.concatenate([rng.integers(0, n_user, (C, 1)), rng.integers(n_user, n_user + N, (C, 1)),
+                        rng.integers(n_user + N, M, (C, fc + ft))], axis=1)
+    ref = O.hhfm_topk_scores(A, V, n_user, N, fc, ft, pools)
+    ids, sc = _topn(cuda, 2, A, V, None, n_user, N, 20, fc, ft, pools)
+    want = O.topk_lowest_index(ref, 20)
+    assert (ids == want).all()
+    assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
+
+
+def test_item_sharded_topk_merges_to_the_single_shard_answer(cuda):
+    """shard items, local top-tp with global offsets, concatenate, re-select: identical lists."""
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(8)
+    n_user, N, K, C, tp = 20, 1003, 32, 50, 20
+    M = n_user + N
+    V = rng.integers(-3, 4, (M, K)).astype(np.float32) * 0.125          # tie-heavy
+    A = np.stack([rng.integers(0, n_user, C), rng.integers(n_user, M, C)], axis=1)
+    full, _ = _topn(cuda, 0, A, V, None, n_user, N, tp, 0, 0)
+    G = 4
+    bounds = [N * g // G for g in range(G + 1)]
+    parts = [_topn(cuda, 0, A, V, None, n_user, N, tp, 0, 0, lo=bounds[g], hi=bounds[g + 1]) for g in range(G)]
+    cat_ids = dev(np.concatenate([p[0] for p in parts], axis=1), cuda)
+    cat_sc = dev(np.concatenate([p[1] for p in parts], axis=1), cuda)
+    out_ids = torch.empty(C, tp, dtype=torch.int32, device=cuda); out_sc = torch.empty(C, tp, device=cuda)
+    lib.call("hhfm_topn_select", ptr(cat_sc), ptr(cat_ids), None, C, G * tp, G * tp, tp, 0, ptr(out_sc), ptr(out_ids), st())
+    assert (out_ids.cpu().numpy() == full).all()
+
+
+def test_metrics_walk_matches_the_reference_walk(cuda):
+    from hhfm_b200 import engine
+    from collections import defaultdict
+    rng = np.random.default_rng(12)
+    C, tp, n_user, N = 500, 20, 40, 60
+    rows = np.concatenate([rng.integers(0, n_user, (C, 1)), rng.integers(n_user, n_user + N, (C, 1)), rng.integers(100, 104, (C, 2))], axis=1)
+    pred = np.stack([rng.permutation(N)[:tp] + n_user for _ in range(C)])
+    pf = defaultdict(set)
+    for r in rows[::3]:
+        pf[(r[0], r[2], r[3])].add(r[1])                 # rows whose target item is in positive_feedback[key]
+    in_pf = np.array([r[1] in pf[(r[0], r[2], r[3])] for r in rows], np.uint8)
+    for TopK in (1, 5, 10, 20, 25):
+        m, n, p = O.evaluate_topk_walk(pred, rows, pf, TopK)
+        codes = engine.metrics_walk(dev(pred, cuda, torch.int32), dev(rows[:, 1], cuda, torch.int32), dev(in_pf, cuda), TopK).cpu().numpy()
+        got = engine.metrics_from_codes(codes)
+        assert got[0] == np.average(m) and got[1] == np.average(n) and got[2] == np.average(p)
+        assert (codes != -2).sum() == len(m)
