@@ -214,6 +214,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     V = model.weights["feature_embeddings"]
     n_ctx = len(CTX_CARD)
+    from hhfm_b200.engine import NO_HOT, HotRows
+    hot = None if args.no_hot else HotRows.from_batch(dev_batches[0], FEATURES_M, K_FACTOR, dev)
+    hot_args = hot.args() if hot is not None else NO_HOT
+    if args.no_hot:
+        model.hot_rows = None
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + 1))]
 
@@ -223,9 +228,11 @@ def run_ours(args):
         if timed_idx is not None:
             ev[2 * timed_idx].record()
         _lib.call("hhfm_pairrank_fwd_bwd", ptr(rec), B, stride, n_ctx, 0, NG, 0, 0, 0, ptr(V), FEATURES_M, K_FACTOR,
-                  None, None, ptr(model._gV), ptr(model._loss_partials), None, 0, None, None, 0, cur_stream())
+                  None, None, ptr(model._gV), ptr(model._loss_partials), None, 0, None, None, *hot_args, 0, cur_stream())
         if timed_idx is not None:
             ev[2 * timed_idx + 1].record()
+        if hot is not None:
+            hot.fold(model._gV, None)
         model._allreduce_grads()
         model._opt.apply_dense("feature_embeddings", V, model._gV, LAMDA, model._sq_partials)
         _lib.call("hhfm_loss_finalize", ptr(model._loss_partials), ptr(model._sq_partials), 0.5 * LAMDA,
@@ -255,15 +262,15 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # e2e arm: the user-facing call with host numpy batches (int64 ids as the reference feeds them)
-    e2e_steps = max(3, min(args.steps, 10))
-    for i in range(2):
+    e2e_steps = 0 if args.quick else max(3, min(args.steps, 10))
+    for i in range(0 if args.quick else 2):
         model.partial_fit(host_batches[i % n_batches])
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         model.partial_fit(host_batches[i % n_batches])
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
 
     if world > 1:
         t = torch.tensor([total_ms, kern_ms, e2e_s], device=dev, dtype=torch.float64)
@@ -275,7 +282,7 @@ def run_ours(args):
         ms_per_step = total_ms / args.steps
         value = world * B * args.steps / (total_ms * 1e-3)
         achieved = B * ALGO_BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
-        cb = cpu_baseline() if world == 1 else None
+        cb = cpu_baseline() if (world == 1 and not args.quick) else None
         line = {
             "metric": "hhfm_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -283,7 +290,8 @@ def run_ours(args):
             "config": workload_config(B, world),
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": B * stride * 4,
                     "d2h_bytes_per_step": 4, "steps": e2e_steps, "api": "OUR.partial_fit(host int64 numpy batch)"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": (4 if hot is not None else 3) * args.steps,
+            "hot_rows": {"n_hot": hot.n_hot, "n_rep": hot.n_rep} if hot is not None else None,
             "roofline": {"bound": "hbm", "kernel": "pairrank_kernel<16,1,TRAIN>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "kernel_ms": kern_ms,
@@ -305,6 +313,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="positives per GPU per step")
+    ap.add_argument("--no-hot", dest="no_hot", action="store_true", help="disable the two-level hot-row scatter")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

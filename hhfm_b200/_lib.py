@@ -21,11 +21,11 @@ SIGNATURES = {
     "hhfm_pack_csr_i64": [vp, vp, i64, i64, i64, vp, vp, vp, i64, cint],
     "hhfm_fm_fwd": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp],
     "hhfm_fm_fwd_bwd_sqloss": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp,
-                               vp, i32, vp],
+                               vp, vp, vp, vp, i32, i32, i32, vp],
     "hhfm_fm_bwd": [vp, vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, i32, vp],
     "hhfm_pairrank_fwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_pairrank_fwd_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp,
-                              vp, i32, vp],
+                              vp, vp, vp, i32, i32, i32, vp],
     "hhfm_pairrank_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, i32, vp],
     "hhfm_scatter_add_rows": [vp, vp, i64, i64, vp, i64, vp],
     "hhfm_opt_adagrad_dense_l2": [vp, vp, vp, i64, f32, f32, i32, vp, vp],
@@ -36,6 +36,7 @@ SIGNATURES = {
     "hhfm_opt_momentum_rows": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp],
     "hhfm_opt_sgd_rows": [vp, vp, vp, vp, i64, i64, f32, i32, vp],
     "hhfm_loss_finalize": [vp, vp, f32, vp, vp],
+    "hhfm_hot_fold": [vp, vp, i32, i32, i64, vp, vp, vp, vp],
     "hhfm_topn_build_query": [i32, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],
     "hhfm_topn_select": [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp],

@@ -97,9 +97,11 @@ struct Frag {
   float4 v[VPL];
 };
 
+// A row of K floats viewed by the LPS lanes of a group.  K may be smaller than 4*LPS*VPL (e.g. K = 100): the
+// surplus lanes read zeros and write nothing.  When K == 4*LPS*VPL the bound test folds away (kExact below).
 template <int LPS, int VPL>
 __device__ __forceinline__ void frag_load(Frag<LPS, VPL>& r, const float* __restrict__ V, int row, int K, int lg) {
-  const float4* p = reinterpret_cast<const float4*>(V + (size_t)row * K);
+  const float4* p = reinterpret_cast<const float4*>(V) + (size_t)row * (K >> 2);
   const int kv = K >> 2;
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
@@ -109,14 +111,49 @@ __device__ __forceinline__ void frag_load(Frag<LPS, VPL>& r, const float* __rest
 }
 
 template <int LPS, int VPL>
-__device__ __forceinline__ void frag_red(float* __restrict__ G, int row, int K, int lg, const Frag<LPS, VPL>& r) {
-  float* p = G + (size_t)row * K;
+__device__ __forceinline__ void frag_red_ptr(float* __restrict__ p, int K, int lg, const Frag<LPS, VPL>& r) {
   const int kv = K >> 2;
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
     const int c = lg + i * LPS;
     if (c < kv) red_add_v4(p + 4 * c, r.v[i]);
   }
+}
+
+template <int LPS, int VPL>
+__device__ __forceinline__ void frag_red(float* __restrict__ G, int row, int K, int lg, const Frag<LPS, VPL>& r) {
+  frag_red_ptr<LPS, VPL>(G + (size_t)row * K, K, lg, r);
+}
+
+// Two-level sort-free scatter target.  Rows flagged hot (hot_slot[row] >= 0) accumulate into one of n_rep
+// replicas of a small [n_rep, n_hot, K] buffer chosen per lane-group, so the reductions of a row that thousands
+// of samples share spread over n_rep addresses / L2 slices instead of serialising on one; hhfm_hot_fold sums the
+// replicas back into the [M, K] gradient before the optimizer.  Cold rows go straight to the gradient table.
+struct HotPlan {
+  const int32_t* slot;   // [M] slot id or -1, NULL = no hot rows
+  float* ghot;           // [n_rep, n_hot, K]
+  float* ghot_bias;      // [n_rep, n_hot] (FM feature_bias gradient) or NULL
+  int n_rep, n_hot;
+};
+
+template <int LPS, int VPL>
+__device__ __forceinline__ void scatter_row(float* __restrict__ G, const HotPlan& hp, int rep, int row, int K, int lg,
+                                            const Frag<LPS, VPL>& r) {
+  float* p = G + (size_t)row * K;
+  if (hp.slot != nullptr) {
+    const int s = __ldg(hp.slot + row);
+    if (s >= 0) p = hp.ghot + ((size_t)rep * hp.n_hot + s) * K;
+  }
+  frag_red_ptr<LPS, VPL>(p, K, lg, r);
+}
+
+__device__ __forceinline__ void scatter_bias(float* __restrict__ gb, const HotPlan& hp, int rep, int row, float v) {
+  float* p = gb + row;
+  if (hp.slot != nullptr && hp.ghot_bias != nullptr) {
+    const int s = __ldg(hp.slot + row);
+    if (s >= 0) p = hp.ghot_bias + (size_t)rep * hp.n_hot + s;
+  }
+  atomicAdd(p, v);
 }
 
 template <int LPS, int VPL>

@@ -32,6 +32,7 @@ struct FmArgs {
   int32_t* touched_rows;
   int32_t* touched_count;
   int groups_active;
+  HotPlan hot;
 };
 
 enum { FM_FWD = 0, FM_TRAIN = 1, FM_BWD = 2 };
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
   const int K = a.K;
   const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
   float loss_acc = 0.f, g0_acc = 0.f;
+  const int rep = a.hot.slot ? (int)((warp_g * (32 / LPS) + grp) % a.hot.n_rep) : 0;
 
   for (int64_t s0 = warp_g * ga; s0 < a.B; s0 += n_warps * ga) {
     const int64_t s = s0 + grp;
@@ -159,9 +161,9 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
               float4 x = a.val ? f4_scale(e[u].v[i], vv[u]) : e[u].v[i];
               d.v[i] = f4_scale(f4_sub(S.v[i], x), gv);
             }
-            frag_red<LPS, VPL>(a.gV, id[u], K, lg, d);
+            scatter_row<LPS, VPL>(a.gV, a.hot, rep, id[u], K, lg, d);
             if (lg == 0) {
-              if (a.gbias) atomicAdd(a.gbias + id[u], gv);
+              if (a.gbias) scatter_bias(a.gbias, a.hot, rep, id[u], gv);
               touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id[u]);
             }
           }
@@ -175,8 +177,8 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
         d0.v[i] = f4_scale(e1.v[i], g);
         d1.v[i] = f4_scale(e0.v[i], g);
       }
-      frag_red<LPS, VPL>(a.gV, x0, K, lg, d0);
-      frag_red<LPS, VPL>(a.gV, x1, K, lg, d1);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, x0, K, lg, d0);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, x1, K, lg, d1);
       if (lg == 0) {
         touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, x0);
         touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, x1);
@@ -257,9 +259,11 @@ extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col
                                       int64_t K, int32_t interaction, const float* labels, float* out, float* gV,
                                       float* gbias, float* gb0, float* loss_partials, int32_t* touch_stamp,
                                       int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
-                                      int32_t deterministic, hhfm_stream_t stream) {
+                                      const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep,
+                                      int32_t n_hot, int32_t deterministic, hhfm_stream_t stream) {
   int rc = check_common(B, F, col, V, M, K, interaction, row_ptr);
   if (rc) return rc;
+  HHFM_REQUIRE(!hot_slot || (ghot && n_rep >= 1 && n_hot >= 1), "fm_fwd_bwd_sqloss: hot_slot needs ghot, n_rep, n_hot");
   HHFM_REQUIRE(labels && gV && loss_partials, "fm_fwd_bwd_sqloss: labels, gV and loss_partials are required");
   HHFM_REQUIRE(B > 0, "fm_fwd_bwd_sqloss: empty batch");
   HHFM_REQUIRE(!touch_stamp || (touched_rows && touched_count), "fm_fwd_bwd_sqloss: touch_stamp needs touched_rows/count");
@@ -269,6 +273,7 @@ extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col
   a.K = (int)K; a.interaction = interaction; a.labels = labels; a.out = out; a.gV = gV; a.gbias = gbias; a.gb0 = gb0;
   a.loss_partials = loss_partials; a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows;
   a.touched_count = touched_count;
+  a.hot = HotPlan{hot_slot, ghot, ghot_bias, n_rep, n_hot};
   return dispatch_fm<FM_TRAIN>(a, deterministic, (cudaStream_t)stream);
 }
 

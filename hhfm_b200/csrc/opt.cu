@@ -131,6 +131,36 @@ __global__ void scatter_scalar_kernel(const int32_t* __restrict__ rows, const fl
     atomicAdd(dst + __ldg(rows + i), __ldg(src + i));
 }
 
+// Fold the n_rep replicas of the hot-row accumulators into the gradient table (fixed order: deterministic) and
+// clear them for the next step.  One thread per float4 of a hot row (+ one per bias slot).
+__global__ void __launch_bounds__(256) hot_fold_kernel(float* __restrict__ ghot, float* __restrict__ ghot_bias, int n_rep,
+                                                       int n_hot, int K, const int32_t* __restrict__ hot_rows,
+                                                       float* __restrict__ gV, float* __restrict__ gbias) {
+  const int kv = K >> 2;
+  const int64_t total = (int64_t)n_hot * kv;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const int s = (int)(i / kv), c = (int)(i % kv);
+    float4 acc = f4_zero();
+    for (int r = 0; r < n_rep; r++) {
+      float4* p = reinterpret_cast<float4*>(ghot + ((size_t)r * n_hot + s) * K) + c;
+      acc = f4_add(acc, *p);
+      *p = f4_zero();
+    }
+    float4* d = reinterpret_cast<float4*>(gV + (size_t)hot_rows[s] * K) + c;
+    *d = f4_add(*d, acc);
+  } else if (ghot_bias != nullptr && gbias != nullptr && i < total + n_hot) {
+    const int s = (int)(i - total);
+    float acc = 0.f;
+    for (int r = 0; r < n_rep; r++) {
+      float* p = ghot_bias + (size_t)r * n_hot + s;
+      acc += *p;
+      *p = 0.f;
+    }
+    gbias[hot_rows[s]] += acc;
+  }
+}
+
 // loss = sum(loss_partials) + half_lamda * sum(sq_partials): one warp, fixed order -> deterministic.
 __global__ void loss_finalize_kernel(const float* __restrict__ lp, const float* __restrict__ sp, float half_lamda,
                                      float* __restrict__ out) {
@@ -234,6 +264,16 @@ extern "C" int hhfm_scatter_add_rows(const int32_t* rows, const float* src, int6
   if (K == 1) scatter_scalar_kernel<<<grid, 256, 0, st>>>(rows, src, n, dst);
   else scatter_rows_kernel<<<grid, 256, 0, st>>>(rows, src, n, (int)K, dst);
   return check_launch("scatter_rows_kernel");
+}
+
+extern "C" int hhfm_hot_fold(float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K,
+                             const int32_t* hot_rows, float* gV, float* gbias, hhfm_stream_t stream) {
+  HHFM_REQUIRE(ghot && hot_rows && gV, "hot_fold: NULL argument");
+  HHFM_REQUIRE(n_rep >= 1 && n_hot >= 1 && K > 0 && K % 4 == 0, "hot_fold: bad sizes");
+  const int64_t total = (int64_t)n_hot * (K >> 2) + n_hot;
+  hot_fold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ghot, ghot_bias, n_rep, n_hot, (int)K,
+                                                                                    hot_rows, gV, gbias);
+  return check_launch("hot_fold_kernel");
 }
 
 extern "C" int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, float half_lamda, float* loss_out,

@@ -26,6 +26,7 @@ struct PrArgs {
   int32_t* touched_rows;
   int32_t* touched_count;
   int groups_active;
+  HotPlan hot;
 };
 
 enum { PR_FWD = 0, PR_TRAIN = 1, PR_BWD = 2 };
@@ -78,7 +79,7 @@ __device__ __forceinline__ void pool_rows(const float* __restrict__ V, const int
 
 // Scatter the gradient d of a pooled vector back to its n member rows.
 template <int LPS, int VPL, bool ANYMAX>
-__device__ __forceinline__ void pool_rows_bwd(const PrArgs& a, const int32_t* __restrict__ ids, int n, int mode, int lg,
+__device__ __forceinline__ void pool_rows_bwd(const PrArgs& a, int rep, const int32_t* __restrict__ ids, int n, int mode, int lg,
                                               const Frag<LPS, VPL>& pooled, const Frag<LPS, VPL>& cnt,
                                               const Frag<LPS, VPL>& d) {
   using F4 = Frag<LPS, VPL>;
@@ -104,9 +105,9 @@ __device__ __forceinline__ void pool_rows_bwd(const PrArgs& a, const int32_t* __
 #pragma unroll
         for (int q = 0; q < 4; q++) rr[q] = (x[q] == o[q]) ? (1.f / c[q]) * dd[q] : 0.f;
       }
-      frag_red<LPS, VPL>(a.gV, id, K, lg, r);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, id, K, lg, r);
     } else {
-      frag_red<LPS, VPL>(a.gV, id, K, lg, dm);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, id, K, lg, dm);
     }
     if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
   }
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
   const int K = a.K;
   const int num = 1 + (a.n_ctx > 0) + (a.n_time > 0);   // OurModel7.py:89,94 self.num
   float loss_acc = 0.f;
+  const int rep = a.hot.slot ? (int)((warp_g * (32 / LPS) + grp) % a.hot.n_rep) : 0;
 
   for (int64_t s0 = warp_g * ga; s0 < a.B; s0 += n_warps * ga) {
     const int64_t s = s0 + grp;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
       F4 dh, t;
 #pragma unroll
       for (int i = 0; i < VPL; i++) { dh.v[i] = f4_scale(vp.v[i], gp); t.v[i] = f4_scale(hyb.v[i], gp); }
-      frag_red<LPS, VPL>(a.gV, pid, K, lg, t);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, pid, K, lg, t);
       if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, pid);
       if (MODE == PR_TRAIN) {
         unsigned long long w = tie;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
           frag_load(e, a.V, id, K, lg);
 #pragma unroll
           for (int i = 0; i < VPL; i++) { dh.v[i] = f4_fma(e.v[i], gn, dh.v[i]); t.v[i] = f4_scale(hyb.v[i], gn); }
-          frag_red<LPS, VPL>(a.gV, id, K, lg, t);
+          scatter_row<LPS, VPL>(a.gV, a.hot, rep, id, K, lg, t);
           if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
         }
       } else if (a.dneg != nullptr) {
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
           frag_load(e, a.V, id, K, lg);
 #pragma unroll
           for (int i = 0; i < VPL; i++) { dh.v[i] = f4_fma(e.v[i], c, dh.v[i]); t.v[i] = f4_scale(hyb.v[i], c); }
-          frag_red<LPS, VPL>(a.gV, id, K, lg, t);
+          scatter_row<LPS, VPL>(a.gV, a.hot, rep, id, K, lg, t);
           if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
         }
       }
@@ -274,10 +276,10 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
           }
         }
       }
-      frag_red<LPS, VPL>(a.gV, uid, K, lg, du);
+      scatter_row<LPS, VPL>(a.gV, a.hot, rep, uid, K, lg, du);
       if (lg == 0) touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, uid);
-      if (a.n_ctx > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, ctx, a.n_ctx, a.pc, lg, C, cC, dC);
-      if (a.n_time > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, tim, a.n_time, a.pt, lg, T, cT, dT);
+      if (a.n_ctx > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, rep, ctx, a.n_ctx, a.pc, lg, C, cC, dC);
+      if (a.n_time > 0) pool_rows_bwd<LPS, VPL, ANYMAX>(a, rep, tim, a.n_time, a.pt, lg, T, cT, dT);
     }
   }
 
@@ -363,9 +365,11 @@ extern "C" int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stri
                                      int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack,
                                      const float* V, int64_t M, int64_t K, float* pos_out, float* neg_out, float* gV,
                                      float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
-                                     int32_t* touched_count, int32_t deterministic, hhfm_stream_t stream) {
+                                     int32_t* touched_count, const int32_t* hot_slot, float* ghot, int32_t n_rep,
+                                     int32_t n_hot, int32_t deterministic, hhfm_stream_t stream) {
   int rc = check_pr(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, M, K);
   if (rc) return rc;
+  HHFM_REQUIRE(!hot_slot || (ghot && n_rep >= 1 && n_hot >= 1), "pairrank_fwd_bwd: hot_slot needs ghot, n_rep, n_hot");
   HHFM_REQUIRE(B > 0 && n_neg >= 1, "pairrank_fwd_bwd: needs B > 0 and at least one negative");
   HHFM_REQUIRE(gV && loss_partials, "pairrank_fwd_bwd: gV and loss_partials are required");
   HHFM_REQUIRE(!touch_stamp || (touched_rows && touched_count), "pairrank_fwd_bwd: touch_stamp needs touched_rows/count");
@@ -373,6 +377,7 @@ extern "C" int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stri
   PrArgs a = make_args(idx, B, stride, n_ctx, n_time, n_neg, pool_ctx, pool_time, pool_stack, V, K);
   a.pos_out = pos_out; a.neg_out = neg_out; a.gV = gV; a.loss_partials = loss_partials;
   a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows; a.touched_count = touched_count;
+  a.hot = HotPlan{hot_slot, ghot, nullptr, n_rep, n_hot};
   return dispatch_pr<PR_TRAIN>(a, deterministic, (cudaStream_t)stream);
 }
 

@@ -207,6 +207,53 @@ class TouchTracker:
         self.count.zero_()
 
 
+class HotRows:
+    """Two-level scatter plan (see hhfm_sm100.h `hot_slot`): rows that many samples of a batch share get
+    `n_rep` replicated accumulators so their vector reductions do not serialise on one L2 slice."""
+
+    N_REP = int(os.environ.get("HHFM_HOT_REP", "64"))
+    MAX_HOT = int(os.environ.get("HHFM_HOT_MAX", "1024"))
+    MIN_COUNT = int(os.environ.get("HHFM_HOT_MIN_COUNT", "2048"))
+
+    def __init__(self, hot_rows, M, K, device, with_bias=False, n_rep=None):
+        hot_rows = torch.as_tensor(hot_rows, dtype=torch.int32, device=device).reshape(-1)
+        self.n_hot = int(hot_rows.numel())
+        self.n_rep = int(n_rep or self.N_REP)
+        self.K = K
+        self.rows = hot_rows.contiguous()
+        self.slot = torch.full((M,), -1, dtype=torch.int32, device=device)
+        self.slot[self.rows.long()] = torch.arange(self.n_hot, dtype=torch.int32, device=device)
+        self.ghot = torch.zeros(self.n_rep, self.n_hot, K, dtype=torch.float32, device=device)
+        self.ghot_bias = torch.zeros(self.n_rep, self.n_hot, dtype=torch.float32, device=device) if with_bias else None
+
+    @classmethod
+    def from_batch(cls, idx_dev, M, K, device, with_bias=False):
+        """Pick the hot rows from the id histogram of one packed batch (one-time plumbing, not on the hot path):
+        rows hit at least MIN_COUNT times, the MAX_HOT most frequent of them.  Returns None if there are none."""
+        flat = idx_dev.reshape(-1)
+        flat = flat[flat >= 0].long()
+        counts = torch.bincount(flat, minlength=M)
+        hot = torch.nonzero(counts >= cls.MIN_COUNT).reshape(-1)
+        if hot.numel() == 0:
+            return None
+        if hot.numel() > cls.MAX_HOT:
+            hot = torch.topk(counts, cls.MAX_HOT).indices
+        return cls(torch.sort(hot).values, M, K, device, with_bias)
+
+    def args(self, with_bias=False):
+        if with_bias:
+            return (ptr(self.slot), ptr(self.ghot), ptr(self.ghot_bias), self.n_rep, self.n_hot)
+        return (ptr(self.slot), ptr(self.ghot), self.n_rep, self.n_hot)
+
+    def fold(self, gV, gbias=None):
+        _lib.call("hhfm_hot_fold", ptr(self.ghot), ptr(self.ghot_bias) if gbias is not None else None, self.n_rep,
+                  self.n_hot, self.K, ptr(self.rows), ptr(gV), ptr(gbias), cur_stream())
+
+
+NO_HOT = (None, None, 0, 0)
+NO_HOT_BIAS = (None, None, None, 0, 0)
+
+
 # --------------------------------------------------------------------------------------------------
 # K6/K7: full-catalog top-N, exact path
 # --------------------------------------------------------------------------------------------------

@@ -45,15 +45,12 @@ class _FMInteraction(torch.autograd.Function):
         gb0 = torch.zeros(1, dtype=torch.float32, device=V.device) if ctx.has_b0 else None
         _lib.call("hhfm_fm_bwd", None, ptr(idx), None, B, F, ptr(V), V.shape[0], V.shape[1], ctx.interaction, ptr(gout),
                   ptr(gV), ptr(gb), ptr(gb0), 0, cur_stream())
-        return (None, gV, gb.view(ctx.bias_shape) if gb is not None else None,
-                gb0.view(()) if gb0 is not None else None, None)
+        return (None, gV, gb.view(ctx.bias_shape) if gb is not None else None, gb0, None)
 
 
 def fm_interaction(idx, V, bias=None, b0=None, interaction=0):
-    if b0 is not None and b0.dim() == 0:
-        b0 = b0.view(1)
-        out = _FMInteraction.apply(idx, V, bias, b0, interaction)
-        return out
+    if b0 is not None:
+        b0 = b0.reshape(1)          # differentiable view: the [1] gradient flows back to a 0-dim scalar
     return _FMInteraction.apply(idx, V, bias, b0, interaction)
 
 

@@ -14,8 +14,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import (POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_USER, Optimizer, Staging, TopN, TouchTracker, cur_stream,
-                     pack_records, ptr, require_cuda)
+from .engine import (NO_HOT, NO_HOT_BIAS, POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_USER, HotRows, Optimizer, Staging, TopN,
+                     TouchTracker, cur_stream, pack_records, ptr, require_cuda)
 
 
 class Handle:
@@ -76,7 +76,23 @@ class _Base:
         self._topn = TopN(self.device)
         self._dp_group = None
         self.deterministic = False
+        self.hot_rows = "auto"      # "auto": plan from the first batch; None: off; or an explicit id list
+        self._hot = None
+        self._hot_planned = False
+        self._with_bias_grad = with_bias
         self.sess = Session(self)
+
+    def _hot_plan(self, idx_dev, with_bias):
+        """Hot-row plan for the two-level scatter (engine.HotRows), built once from the first batch."""
+        if not self._hot_planned:
+            self._hot_planned = True
+            if self.hot_rows is None or self.deterministic:
+                self._hot = None
+            elif isinstance(self.hot_rows, str):
+                self._hot = HotRows.from_batch(idx_dev, self._M, self._K, self.device, with_bias)
+            else:
+                self._hot = HotRows(self.hot_rows, self._M, self._K, self.device, with_bias)
+        return self._hot
 
     # ---- data parallel (SURVEY.md 8e): batch rows sharded across ranks, one all-reduce of the arena ----
     def enable_data_parallel(self, group=None):
@@ -212,9 +228,13 @@ class FM(_Base):
         V = self.weights["feature_embeddings"]
         bias = self.weights.get("feature_bias")
         ts, stamp, tr, tc = self._touch_args(extra=self._opt.kind == "momentum")
+        hot = self._hot_plan(idx, True)
         _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, F, ptr(V), ptr(bias), ptr(self._b0), self._M,
                   self._K, self.interaction, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0),
-                  ptr(self._loss_partials), ts, stamp, tr, tc, 1 if self.deterministic else 0, cur_stream())
+                  ptr(self._loss_partials), ts, stamp, tr, tc, *(hot.args(True) if hot else NO_HOT_BIAS),
+                  1 if self.deterministic else 0, cur_stream())
+        if hot:
+            hot.fold(self._gV, self._gb)
         self._allreduce_grads()
         with_reg = self._apply_table(sparse_ok=True)
         if bias is not None:
@@ -305,9 +325,12 @@ class MF(FM):
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
         ts, stamp, tr, tc = self._touch_args()
+        hot = self._hot_plan(idx, False)
         _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, 2, ptr(V), None, None, self._M, self._K, 1, ptr(y),
                   None, ptr(self._gV), None, None, ptr(self._loss_partials), ts, stamp, tr, tc,
-                  1 if self.deterministic else 0, cur_stream())
+                  *(hot.args(True) if hot else NO_HOT_BIAS), 1 if self.deterministic else 0, cur_stream())
+        if hot:
+            hot.fold(self._gV, None)
         self._allreduce_grads()
         with_reg = self._apply_table(sparse_ok=True)
         return self._finish_loss(with_reg)
@@ -334,9 +357,12 @@ class _PairRank(_Base):
         V = self.weights["feature_embeddings"]
         pc, pt, pf = self.pools
         ts, stamp, tr, tc = self._touch_args()
+        hot = self._hot_plan(idx, False)
         _lib.call("hhfm_pairrank_fwd_bwd", ptr(idx), B, stride, n_ctx, n_time, n_neg, pc, pt, pf, ptr(V), self._M,
                   self._K, None, None, ptr(self._gV), ptr(self._loss_partials), ts, stamp, tr, tc,
-                  1 if self.deterministic else 0, cur_stream())
+                  *(hot.args() if hot else NO_HOT), 1 if self.deterministic else 0, cur_stream())
+        if hot:
+            hot.fold(self._gV, None)
         self._allreduce_grads()
         with_reg = self._apply_table(sparse_ok=True)
         return self._finish_loss(with_reg)

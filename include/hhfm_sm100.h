@@ -97,12 +97,17 @@ int hhfm_fm_fwd(const int32_t* row_ptr, const int32_t* col, const float* val, in
  *   loss_partials  [hhfm_partials_len()]: per-CTA partial sums, reduce with hhfm_loss_finalize
  *   touch_stamp    [M] nullable: if given, every row whose stamp != `stamp` is stamped and appended to
  *                  touched_rows (capacity M) with touched_count[0] incremented -> feeds the *_rows optimizers
+ *   hot_slot       [M] nullable: two-level scatter for rows that many samples share (low-cardinality columns,
+ *                  Zipf heads).  hot_slot[row] = s >= 0 sends that row's reductions to replica (group % n_rep) of
+ *                  ghot [n_rep, n_hot, K] (ghot_bias [n_rep, n_hot]) instead of gV / gbias, so they do not
+ *                  serialise on one L2 slice; call hhfm_hot_fold before the optimizer.  -1 = cold row.
  *   deterministic  1 = one warp, program-order accumulation (bit-reproducible; test mode)              */
 int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
                            const float* V, const float* bias, const float* b0, int64_t M, int64_t K,
                            int32_t interaction, const float* labels, float* out, float* gV, float* gbias, float* gb0,
                            float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
-                           int32_t* touched_count, int32_t deterministic, hhfm_stream_t stream);
+                           int32_t* touched_count, const int32_t* hot_slot, float* ghot, float* ghot_bias,
+                           int32_t n_rep, int32_t n_hot, int32_t deterministic, hhfm_stream_t stream);
 
 /* Backward only, for torch.autograd: g = gout[s] given by the caller. */
 int hhfm_fm_bwd(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
@@ -125,6 +130,7 @@ int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t
                           int32_t n_neg, int32_t pool_ctx, int32_t pool_time, int32_t pool_stack, const float* V,
                           int64_t M, int64_t K, float* pos_out, float* neg_out, float* gV, float* loss_partials,
                           int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
+                          const int32_t* hot_slot, float* ghot, int32_t n_rep, int32_t n_hot,
                           int32_t deterministic, hhfm_stream_t stream);
 
 /* Backward only, for torch.autograd: dpos [B], dneg [B,n_neg] (nullable) given by the caller. */
@@ -167,6 +173,10 @@ int hhfm_opt_momentum_rows(float* w, float* acc, float* g, const int32_t* rows, 
                            hhfm_stream_t stream);
 int hhfm_opt_sgd_rows(float* w, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
                       int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream);
+
+/* gV[hot_rows[s], :] += sum_r ghot[r, s, :] (and gbias likewise), replicas cleared; fixed summation order. */
+int hhfm_hot_fold(float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K, const int32_t* hot_rows,
+                  float* gV, float* gbias, hhfm_stream_t stream);
 
 /* loss_out[0] = sum(loss_partials) + half_lamda * sum(sq_partials)   (fixed summation order; sq may be NULL) */
 int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, float half_lamda, float* loss_out,

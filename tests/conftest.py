@@ -34,6 +34,25 @@ def assert_close(a, b, rtol=1e-5, what=""):
         what, int(bad.sum()), b.size, float(err.max()), float(tol.reshape(-1)[np.argmax(err)]), np.unravel_index(np.argmax(err), b.shape))
 
 
+def assert_update_close(w_got, w_ref, w_prev, g, acc_prev, lr, rtol=1e-5, what=""):
+    """Post-step weights of one TF1-Adagrad step, compared as UPDATES (delta = w_new - w_prev) with a first-order
+    propagation of the 1e-5 relative gradient tolerance through update(g) = lr*g/sqrt(acc+g^2):
+        tol = rtol * ( max(|delta|, rms(delta)) + |d update/d g| * max(|g|, rms(g)) ),  d update/d g = lr*acc/(acc+g^2)^1.5.
+    The second term only matters for the reference's acc0 = 1e-8 configs (BPR.py:93, MF.py:104), where the update
+    of an element with |g| << 1e-4 is 100*g: a gradient that differs in the last fp32 bit moves the weight by more
+    than 1e-5 of the typical update.  TF itself has the same conditioning."""
+    w_got = np.asarray(w_got, np.float64); w_ref = np.asarray(w_ref, np.float64); w_prev = np.asarray(w_prev, np.float64)
+    g = np.asarray(g, np.float64); acc_prev = np.asarray(acc_prev, np.float64)
+    delta = w_ref - w_prev
+    rms_d = float(np.sqrt(np.mean(delta * delta))); rms_g = float(np.sqrt(np.mean(g * g)))
+    sens = lr * acc_prev / np.power(acc_prev + g * g, 1.5)
+    tol = rtol * (np.maximum(np.abs(delta), rms_d) + sens * np.maximum(np.abs(g), rms_g))
+    err = np.abs(w_got - w_ref)
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d elements off, worst err %.3e vs tol %.3e" % (
+        what, int(bad.sum()), err.size, float(err.max()), float(tol.reshape(-1)[np.argmax(err)]))
+
+
 @pytest.fixture(scope="session")
 def cuda():
     import torch

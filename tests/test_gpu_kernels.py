@@ -13,11 +13,26 @@ from oracle import hhfm_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+_KEEP = []
+
+
 def dev(a, cuda, dtype=None):
+    """Host array -> device tensor.  The tensor is kept alive until the end of the test: the C ABI takes raw
+    pointers, so a temporary freed right after `ptr(...)` could be recycled by the caching allocator."""
     t = torch.as_tensor(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.to(cuda)
+    t = t.to(cuda)
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def _lib_ptr():
@@ -88,7 +103,7 @@ def _fm_train_call(cuda, X, Y, V, b, b0, interaction=0, deterministic=0, track=T
     lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(dev(X, cuda, torch.int32)), ptr(tval), B, F, ptr(tV), ptr(tb), ptr(tb0), M, K,
              interaction, ptr(dev(Y.reshape(-1), cuda)), ptr(out), ptr(gV), ptr(gb) if b is not None else None,
              ptr(gb0) if b0 is not None else None, ptr(lp), ptr(stamp) if track else None, 1, ptr(rows) if track else None,
-             ptr(cnt) if track else None, deterministic, st())
+             ptr(cnt) if track else None, None, None, None, 0, 0, deterministic, st())
     lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(loss), st())
     n = int(cnt.item())
     return dict(loss=float(loss.item()), out=out.cpu().numpy(), gV=gV.cpu().numpy(), gb=gb.cpu().numpy(),
@@ -175,9 +190,12 @@ def _records(Pos, Fea, Tim, Neg):
     return rec, stride
 
 
-def _pairrank_train(cuda, V, Pos, Fea, Tim, Neg, pools, deterministic=0):
+def _pairrank_train(cuda, V, Pos, Fea, Tim, Neg, pools, deterministic=0, hot_rows=None):
     lib, ptr, st = _lib_ptr()
+    from hhfm_b200.engine import NO_HOT, HotRows
     M, K = V.shape
+    hot = HotRows(hot_rows, M, K, cuda, n_rep=8) if hot_rows is not None else None
+    hot_args = hot.args() if hot is not None else NO_HOT
     rec, stride = _records(Pos, Fea, Tim, Neg)
     B = rec.shape[0]
     nc = 0 if Fea is None else Fea.shape[1]; nt = 0 if Tim is None else Tim.shape[1]; ng = Neg.shape[1]
@@ -187,7 +205,10 @@ def _pairrank_train(cuda, V, Pos, Fea, Tim, Neg, pools, deterministic=0):
     stamp = torch.zeros(M, dtype=torch.int32, device=cuda); rows = torch.zeros(M, dtype=torch.int32, device=cuda)
     cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
     lib.call("hhfm_pairrank_fwd_bwd", ptr(dev(rec, cuda)), B, stride, nc, nt, ng, pools[0], pools[1], pools[2],
-             ptr(dev(V, cuda)), M, K, ptr(pos), ptr(neg), ptr(gV), ptr(lp), ptr(stamp), 3, ptr(rows), ptr(cnt), deterministic, st())
+             ptr(dev(V, cuda)), M, K, ptr(pos), ptr(neg), ptr(gV), ptr(lp), ptr(stamp), 3, ptr(rows), ptr(cnt),
+             *hot_args, deterministic, st())
+    if hot is not None:
+        hot.fold(gV, None)
     lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(loss), st())
     return dict(loss=float(loss.item()), pos=pos.cpu().numpy(), neg=neg.cpu().numpy(), gV=gV.cpu().numpy(),
                 touched=np.sort(rows.cpu().numpy()[:int(cnt.item())]))
@@ -214,6 +235,43 @@ def test_hhfm_fused_pass_matches_oracle(cuda, pools, B, K, fc, ft):
     assert_close(got["gV"], dV, what="gV")
     assert set(got["touched"].tolist()) <= set(np.unique(np.concatenate([a.reshape(-1) for a in (Pos, Fea, Tim, Neg) if a is not None])).tolist())
     assert set(np.unique(Pos).tolist()) <= set(got["touched"].tolist())
+
+
+def test_hot_row_replicas_fold_to_the_same_gradient(cuda):
+    """Two-level scatter: rows flagged hot accumulate in replicated buffers; after hhfm_hot_fold the gradient equals
+    the single-level result (and the oracle)."""
+    rng = np.random.default_rng(77)
+    M, K, B = 300, 64, 4000
+    V = make_table(rng, M, K)
+    Pos = np.stack([rng.integers(0, 5, B), rng.integers(100, 200, B)], axis=1)       # 5 very hot users
+    Fea = np.stack([250 + rng.integers(0, 2, B), 260 + rng.integers(0, 3, B), 270 + rng.integers(0, 7, B)], axis=1)
+    Neg = rng.integers(100, 200, (B, 10))
+    hot_rows = np.concatenate([np.arange(5), 250 + np.arange(2), 260 + np.arange(3), 270 + np.arange(7), [150]])
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, None, (0, 0, 0), 0.0)
+    got = _pairrank_train(cuda, V, Pos, Fea, None, Neg, (0, 0, 0), hot_rows=hot_rows)
+    assert_close(got["loss"], loss, what="loss"); assert_close(got["gV"], dV, what="gV with hot replicas")
+
+
+def test_fm_hot_row_replicas_with_bias(cuda):
+    lib, ptr, st = _lib_ptr()
+    from hhfm_b200.engine import HotRows
+    rng = np.random.default_rng(78)
+    M, K, B, F = 200, 32, 3000, 6
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32)
+    X = np.stack([rng.integers(0, 100, B), rng.integers(100, 180, B), 190 + rng.integers(0, 2, B), 192 + rng.integers(0, 3, B),
+                  195 + rng.integers(0, 5, B), rng.integers(0, 3, B)], axis=1)
+    Y = rng.choice([1.0, 0.0], (B, 1)).astype(np.float32)
+    loss, out, dV, db, db0, _ = O.fm_loss_grads(X, Y, V, b, 0.0, 0.0)
+    hot = HotRows(np.concatenate([np.arange(3), np.arange(190, 200)]), M, K, cuda, with_bias=True, n_rep=4)
+    P = lib.partials_len()
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    lp = torch.zeros(P, device=cuda)
+    lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(dev(X, cuda, torch.int32)), None, B, F, ptr(dev(V, cuda)), ptr(dev(b, cuda)), None,
+             M, K, 0, ptr(dev(Y.reshape(-1), cuda)), None, ptr(gV), ptr(gb), ptr(gb0), ptr(lp), None, 0, None, None,
+             *hot.args(True), 0, st())
+    hot.fold(gV, gb)
+    assert_close(gV.cpu().numpy(), dV, what="fm gV hot"); assert_close(gb.cpu().numpy(), db, what="fm gb hot")
+    assert float(hot.ghot.abs().max()) == 0.0 and float(hot.ghot_bias.abs().max()) == 0.0, "fold must clear the replicas"
 
 
 def test_bpr_is_the_no_context_special_case(cuda):
