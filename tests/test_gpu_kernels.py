@@ -479,3 +479,53 @@ def test_metrics_walk_matches_the_reference_walk(cuda):
         got = engine.metrics_from_codes(codes)
         assert got[0] == np.average(m) and got[1] == np.average(n) and got[2] == np.average(p)
         assert (codes != -2).sum() == len(m)
+
+
+# ----------------------------------------------------------------------------------------------------
+# committed golden fixtures (tests/golden/): the oracle's vectors and the reference's own metric walk
+# ----------------------------------------------------------------------------------------------------
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def test_device_matches_committed_oracle_vectors(cuda):
+    g = np.load(_os.path.join(_GOLD, "oracle_vectors.npz"))
+    n_user, n_item, M, K, B, F, NG = [int(x) for x in g["dims"]]
+    V, b, X, Y, Neg = g["V"], g["b"], g["X"], g["Y"], g["Neg"]
+    got = _fm_train_call(cuda, X, Y, V, b, np.float32(0.05))
+    assert_close(got["out"], g["fm_out"], what="golden fm out")
+    assert_close(got["gV"] + np.float32(0.1) * V, g["fm_dV"], what="golden fm dV (+lamda*V)")
+    assert_close(got["gb"], g["fm_db"], what="golden fm db"); assert_close(got["gb0"], g["fm_db0"], what="golden fm db0")
+    ids, _ = _topn(cuda, 1, X[:16], V, b, n_user, n_item, 20, F - 2, 0)
+    assert (ids == g["fm_top20"]).all()
+    for tag, pools in (("sum", (0, 0, 0)), ("max", (1, 1, 1)), ("mean", (2, 2, 2))):
+        r = _pairrank_train(cuda, V, X[:, :2], X[:, 2:4], X[:, 4:6], Neg, pools)
+        assert_close(r["pos"], g["hhfm_%s_pos" % tag], what="golden pos " + tag)
+        assert_close(r["neg"], g["hhfm_%s_neg" % tag], what="golden neg " + tag)
+        assert_close(r["gV"] + np.float32(0.01) * V, g["hhfm_%s_dV" % tag], what="golden hhfm dV " + tag)
+        ids, _ = _topn(cuda, 2, X[:16], V, None, n_user, n_item, 20, 2, 2, pools)
+        assert (ids == g["hhfm_%s_top20" % tag]).all()
+    r = _pairrank_train(cuda, V, X[:, :2], None, None, Neg, (0, 0, 0))
+    assert_close(r["gV"] + np.float32(0.1) * V, g["bpr_dV"], what="golden bpr dV")
+    r = _fm_train_call(cuda, X[:, :2], Y * 2 - 1, V, None, None, interaction=1)
+    assert_close(r["out"], g["mf_out"], what="golden mf out"); assert_close(r["gV"] + np.float32(0.01) * V, g["mf_dV"], what="golden mf dV")
+
+
+@pytest.mark.parametrize("name", ["frappe", "resturant"])
+def test_device_metric_walk_reproduces_the_reference_run(cuda, name, tmp_path):
+    """Rows + predictions recorded while the reference's own Train.evaluate_TopK (FM.py:325-359) ran; the device walk
+    must return exactly its [HR, NDCG, reciprocal-rank] triple."""
+    from hhfm_b200 import engine
+    from hhfm_b200.Newcode.NewLoadData import LoadData
+    g = np.load(_os.path.join(_GOLD, "reference_host_logic.npz"))
+    d = tmp_path / name
+    d.mkdir()
+    (d / (name + ".libfm")).write_text(str(g["libfm_" + name]))
+    np.random.seed(11)
+    ld = LoadData(str(tmp_path) + "/", name)
+    for TopK in (1, 5, 10, 20):
+        rows = g["%s_walk%d_rows" % (name, TopK)]; pred = g["%s_walk%d_pred" % (name, TopK)] + ld.n_user
+        codes = engine.metrics_walk(dev(pred, cuda, torch.int32), dev(rows[:, 1], cuda, torch.int32),
+                                    dev(ld.in_positive_feedback(rows).astype(np.uint8), cuda), TopK).cpu().numpy()
+        assert engine.metrics_from_codes(codes) == g["%s_walk%d_result" % (name, TopK)].tolist()

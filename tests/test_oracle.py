@@ -1,0 +1,102 @@
+"""CPU: the oracle against (a) torch.autograd on the op-for-op torch mirror of the TF graphs, (b) its own committed
+golden vectors.  The reference cannot run here (no TensorFlow 1.x), so this is what pins the restatement's algebra."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import hhfm_oracle as O
+from oracle import torch_cpu as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_oracle_reproduces_its_golden_vectors():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(HERE, "golden", "make_oracle_goldens.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    gold = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+    now = mk.cases()
+    assert sorted(now) == sorted(gold.files)
+    for k in gold.files:
+        a, b = np.asarray(now[k]), gold[k]
+        if a.dtype.kind == "f":
+            assert_close(a, b, rtol=2e-6, what=k)      # BLAS/libm differences between hosts only
+        else:
+            assert (a == b).all(), k
+
+
+@pytest.fixture
+def prob():
+    rng = np.random.default_rng(0)
+    M, K, B, F, NG = 200, 16, 64, 6, 5
+    V = rng.normal(0, 0.1, (M, K)).astype(np.float32); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32)
+    X = rng.integers(0, M, (B, F)); X[:, 3] = X[:, 2]
+    Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    return rng, M, K, B, F, NG, V, b, X, Y
+
+
+def test_fm_gradients_agree_with_autograd(prob):
+    rng, M, K, B, F, NG, V, b, X, Y = prob
+    loss, out, dV, db, db0, _ = O.fm_loss_grads(X, Y, V, b, np.float32(0.3), lamda=0.1)
+    tV = torch.tensor(V, requires_grad=True); tb = torch.tensor(b, requires_grad=True); tb0 = torch.tensor(0.3, requires_grad=True)
+    l, o = T.fm_loss(torch.tensor(X), torch.tensor(Y), tV, tb, tb0, 0.1); l.backward()
+    assert_close(loss, l.item(), what="loss"); assert_close(out, o.detach().numpy()[:, 0], what="out")
+    assert_close(dV, tV.grad.numpy(), what="dV"); assert_close(db, tb.grad.numpy()[:, 0], what="db")
+    assert_close(db0, tb0.grad.item(), what="db0")
+
+
+@pytest.mark.parametrize("pools", [(0, 0, 0), (1, 1, 1), (2, 2, 2), (1, 0, 2), (0, 2, 1)])
+def test_pairrank_gradients_agree_with_autograd(prob, pools):
+    rng, M, K, B, F, NG, V, b, X, Y = prob
+    Pos = rng.integers(0, M, (B, 2)); Fea = rng.integers(0, M, (B, 3)); Fea[:, 1] = Fea[:, 0]
+    Tim = rng.integers(0, M, (B, 2)); Neg = rng.integers(0, M, (B, NG)); Neg[:, 1] = Neg[:, 0]
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, Tim, pools, 0.01)
+    tV = torch.tensor(V, requires_grad=True)
+    l, p, n = T.pairrank_loss(tV, torch.tensor(Pos), torch.tensor(Neg), torch.tensor(Fea), torch.tensor(Tim), pools, 0.01)
+    l.backward()
+    assert_close(loss, l.item(), what="loss"); assert_close(dV, tV.grad.numpy(), what="dV")
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, None, None, (0, 0, 0), 0.1)       # BPR
+    tV = torch.tensor(V, requires_grad=True)
+    l, _, _ = T.pairrank_loss(tV, torch.tensor(Pos), torch.tensor(Neg), None, None, (0, 0, 0), 0.1); l.backward()
+    assert_close(dV, tV.grad.numpy(), what="bpr dV")
+
+
+def test_afm_gradients_agree_with_autograd(prob):
+    rng, M, K, B, F, NG, V, b, X, Y = prob
+    w = dict(feature_embeddings=V, feature_bias=b, bias=np.float32(0.1), attention_W=rng.normal(0, 0.2, (K, K)).astype(np.float32),
+             attention_b=rng.normal(0, 0.2, (1, K)).astype(np.float32), attention_p=rng.normal(0, 1, (K,)).astype(np.float32),
+             prediction=rng.normal(1, 0.1, (K, 1)).astype(np.float32))
+    loss, out, g = O.afm_loss_grads(X, Y, w, 100.0)
+    tw = {k: torch.tensor(v, requires_grad=True) for k, v in w.items()}
+    l, o = T.afm_loss(torch.tensor(X), torch.tensor(Y), tw, 100.0); l.backward()
+    assert_close(loss, l.item(), what="afm loss"); assert_close(out, o.detach().numpy()[:, 0], what="afm out")
+    for k in g:
+        assert_close(np.asarray(g[k]).reshape(-1), tw[k].grad.numpy().reshape(-1), rtol=2e-5, what="afm grad " + k)
+
+
+def test_topk_order_is_descending_with_lowest_index_ties():
+    s = np.array([[1.0, 3.0, 3.0, -0.0, 0.0, 2.0]], np.float32)
+    assert O.topk_lowest_index(s, 6).tolist() == [[1, 2, 5, 0, 3, 4]]
+    rng = np.random.default_rng(1)
+    s = rng.integers(-3, 4, (50, 200)).astype(np.float32)
+    ts, ti = torch.topk(torch.tensor(s), 200, dim=1, sorted=True)
+    got = O.topk_lowest_index(s, 200)
+    assert (np.take_along_axis(s, got, 1) == ts.numpy()).all()
+    for r in range(50):                                     # equal scores appear in ascending index order
+        v = s[r, got[r]]
+        for a, c in zip(range(199), range(1, 200)):
+            if v[a] == v[c]:
+                assert got[r, a] < got[r, c]
+
+
+def test_tf1_optimizer_restatements():
+    w = np.array([1.0, -2.0], np.float32); g = np.array([0.5, 0.0], np.float32)
+    w1, a1 = O.adagrad_dense(w, np.full(2, 0.1, np.float32), g, 0.1)
+    assert_close(a1, [0.35, 0.1]); assert_close(w1, [1.0 - 0.1 * 0.5 / np.sqrt(0.35), -2.0])
+    w1, m1, v1 = O.adam_dense(w, np.zeros(2, np.float32), np.zeros(2, np.float32), g, 0.01, 1)
+    assert_close(w1, [1.0 - 0.01 * np.sqrt(1 - 0.999) / (1 - 0.9) * 0.05 / (np.sqrt(0.00025) + 1e-8), -2.0])
+    w1, a1 = O.momentum_dense(w, np.array([1.0, 1.0], np.float32), g, 0.1)
+    assert_close(a1, [1.45, 0.95]); assert_close(w1, [1.0 - 0.145, -2.0 - 0.095])
