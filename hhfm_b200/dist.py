@@ -1,0 +1,85 @@
+"""torch.distributed plumbing for the two places the path exchanges data:
+
+  training   batch rows sharded across ranks; ONE all-reduce of the flat gradient arena per step
+             ([gV | gbias | gb0 | loss partials], 1.4 MB at frappe shape), then every rank applies the identical update.
+  evaluation item catalog sharded in contiguous id ranges; every rank scores all contexts against its items, keeps its
+             local top-tp with GLOBAL ids, all-gather of [C, tp] (score, id), and a merge under the comparator
+             (score desc, id asc) -- the lists are bit-identical to a single-GPU run.
+
+Works on whatever device the tensors live on (NCCL for CUDA tensors, gloo in the CPU tests); the collectives are
+torch.distributed's -- there is no hand-rolled exchange on this path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous, balanced [lo, hi) of n units for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_arena(arena, group=None):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=group)
+    return arena
+
+
+def merge_topk(local_scores, local_ids, tp, group=None):
+    """All-gather the per-shard candidate lists and keep the tp best per row under (score desc, id asc).
+    local_scores f32 [C, tp_local], local_ids int [C, tp_local] (global ids; -1 = padding)."""
+    rank, ws = world(group)
+    if ws > 1:
+        sc = [torch.empty_like(local_scores) for _ in range(ws)]
+        ids = [torch.empty_like(local_ids) for _ in range(ws)]
+        dist.all_gather(sc, local_scores.contiguous(), group=group)
+        dist.all_gather(ids, local_ids.contiguous(), group=group)
+        scores, idx = torch.cat(sc, dim=1), torch.cat(ids, dim=1)
+    else:
+        scores, idx = local_scores, local_ids
+    if scores.is_cuda:
+        from . import _lib
+        from .engine import cur_stream, ptr
+        C, n = scores.shape
+        out_ids = torch.empty(C, tp, dtype=torch.int32, device=scores.device)
+        out_sc = torch.empty(C, tp, dtype=torch.float32, device=scores.device)
+        scores = scores.contiguous().float(); idx = idx.contiguous().to(torch.int32)
+        # padding entries carry id -1: give them the lowest possible score so they sort last
+        scores = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
+        idx = torch.where(idx < 0, torch.full_like(idx, 2 ** 31 - 1), idx)
+        _lib.call("hhfm_topn_select", ptr(scores), ptr(idx), None, C, n, n, tp, 0, ptr(out_sc), ptr(out_ids), cur_stream())
+        out_ids = torch.where(out_ids == 2 ** 31 - 1, torch.full_like(out_ids, -1), out_ids)
+        return out_ids, out_sc
+    # host tensors (gloo tests / tiny merges): stable sort by id, then stable sort by descending score
+    scores = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
+    o1 = torch.argsort(idx, dim=1, stable=True)
+    s1, i1 = torch.gather(scores, 1, o1), torch.gather(idx, 1, o1)
+    s1 = s1 + 0.0                                                 # -0.0 -> +0.0 (top_k compares values)
+    o2 = torch.argsort(s1, dim=1, descending=True, stable=True)
+    return torch.gather(i1, 1, o2)[:, :tp], torch.gather(s1, 1, o2)[:, :tp]
+
+
+def gather_rows(t, group=None):
+    """Concatenate per-rank row blocks of possibly different length (rank order)."""
+    rank, ws = world(group)
+    if ws == 1:
+        return t
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)

@@ -108,6 +108,30 @@ class _Base:
             import torch.distributed as dist
             dist.all_reduce(self._arena, group=self._dp_group)
 
+    def enable_item_sharding(self, group=None):
+        """Full-catalog top-N with the item catalog sharded across the ranks of `group`: every rank
+        scores all contexts against its contiguous item range, then the candidates are all-gathered and merged."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("enable_item_sharding: torch.distributed is not initialised")
+        self._eval_group = group if group is not None else dist.group.WORLD
+
+    def _topk(self, kind, A, n_ctx, n_time, pools, bias, tp):
+        from . import dist as hd
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        V = self.weights["feature_embeddings"]
+        grp = getattr(self, "_eval_group", None)
+        if grp is None:
+            ids = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp)
+            return ids.cpu().numpy()
+        rank, ws = hd.world(grp)
+        lo, hi = hd.shard_range(self.n_item, rank, ws)
+        ids, sc = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp,
+                                  item_lo=lo, item_hi=hi, return_scores=True)
+        ids, _ = hd.merge_topk(sc, ids, tp, grp)
+        return ids.cpu().numpy()
+
     def _touch_args(self, extra=False):
         """Touched-row tracking is only paid for when a *_rows optimizer will consume the list."""
         need = self._dp_group is None and (self._lamda <= 0 or extra)
@@ -253,10 +277,7 @@ class FM(_Base):
     def topk(self, A, tp):
         """Full-catalog top-N (FM.py:172-185): indices relative to the item id range."""
         A = np.asarray(A)
-        A_dev, stride = self._topn.upload_rows(A, self._M)
-        ids = self._topn.topk(QUERY_FM, A_dev, stride, A.shape[1] - 2, 0, (0, 0, 0), self.weights["feature_embeddings"],
-                              self.weights["feature_bias"], self.n_user, self.n_item, tp)
-        return ids.cpu().numpy()
+        return self._topk(QUERY_FM, A, A.shape[1] - 2, 0, (0, 0, 0), self.weights["feature_bias"], tp)
 
     def _run(self, fetches, feed):
         if fetches is self.out:
@@ -336,11 +357,7 @@ class MF(FM):
         return self._finish_loss(with_reg)
 
     def topk(self, A, tp=100):
-        A = np.asarray(A)
-        A_dev, stride = self._topn.upload_rows(A, self._M)
-        ids = self._topn.topk(QUERY_USER, A_dev, stride, 0, 0, (0, 0, 0), self.weights["feature_embeddings"], None,
-                              self.n_user, self.n_item, tp)
-        return ids.cpu().numpy()
+        return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, tp)
 
 
 # ====================================================================================================
@@ -431,11 +448,7 @@ class OUR(_PairRank):
 
     def topk(self, A, tp):
         """OurModel7.py:229-295: A = [user, item, ctx.., time..]."""
-        A = np.asarray(A)
-        A_dev, stride = self._topn.upload_rows(A, self._M)
-        ids = self._topn.topk(QUERY_HHFM, A_dev, stride, self._n_ctx, self._n_time, self.pools,
-                              self.weights["feature_embeddings"], None, self.n_user, self.n_item, tp)
-        return ids.cpu().numpy()
+        return self._topk(QUERY_HHFM, A, self._n_ctx, self._n_time, self.pools, None, tp)
 
     def _run(self, fetches, feed):
         if fetches is self.PositiveFeadback:
@@ -483,11 +496,7 @@ class BPR(_PairRank):
         return self._positive_feedback([np.asarray(X)[:, :2]], 0, 0)
 
     def topk(self, A, Topk):
-        A = np.asarray(A)
-        A_dev, stride = self._topn.upload_rows(A, self._M)
-        ids = self._topn.topk(QUERY_USER, A_dev, stride, 0, 0, (0, 0, 0), self.weights["feature_embeddings"], None,
-                              self.n_user, self.n_item, Topk)
-        return ids.cpu().numpy()
+        return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, Topk)
 
     def _run(self, fetches, feed):
         if fetches is self.PositiveFeadback:

@@ -133,7 +133,7 @@ def hhfm_train_step(V, acc, Pos, Neg, Fea, Tim, pools, lamda, lr):
     (g,) = torch.autograd.grad(loss, V)
     V.requires_grad_(False)
     adagrad_(V, acc, g, lr)
-    return float(loss)
+    return float(loss.detach())
 
 
 def fm_train_step(V, b, b0, accV, accb, accb0, X, Y, lamda, lr):
@@ -146,4 +146,4 @@ def fm_train_step(V, b, b0, accV, accb, accb0, X, Y, lamda, lr):
     adagrad_(V, accV, gV, lr)
     adagrad_(b, accb, gb, lr)
     adagrad_(b0, accb0, gb0, lr)
-    return float(loss)
+    return float(loss.detach())

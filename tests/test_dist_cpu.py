@@ -1,0 +1,89 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU paths without a GPU --
+row sharding + one all-reduce of the flat gradient arena for training, item sharding + all-gather + merge with the
+(score desc, id asc) comparator for evaluation, rank-code gather for the metrics."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def run2(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _train_shards(rank, world):
+    """Each rank computes the oracle gradient of its row shard; all-reduce of the arena == gradient of the full batch."""
+    from hhfm_b200 import dist as hd
+    from oracle import hhfm_oracle as O
+    rng = np.random.default_rng(0)
+    M, K, B = 60, 8, 64
+    V = rng.normal(0, 0.1, (M, K)).astype(np.float32)
+    Pos = rng.integers(0, M, (B, 2)); Neg = rng.integers(0, M, (B, 4)); Fea = rng.integers(0, M, (B, 3))
+    lo, hi = hd.shard_range(B, rank, world)
+    loss, _, _, dV = O.pairrank_loss_grads(V, Pos[lo:hi], Neg[lo:hi], Fea[lo:hi], None, (0, 0, 0), 0.0)
+    arena = torch.cat([torch.from_numpy(dV.reshape(-1)), torch.tensor([float(loss)])])
+    hd.allreduce_arena(arena)
+    full_loss, _, _, full_dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, None, (0, 0, 0), 0.0)
+    return (np.abs(arena[:-1].numpy() - full_dV.reshape(-1)).max() < 1e-6, abs(arena[-1].item() - full_loss) < 1e-3 * abs(full_loss), (lo, hi))
+
+
+def test_data_parallel_gradient_allreduce_equals_full_batch():
+    res = run2(_train_shards)
+    assert all(r[0] and r[1] for r in res)
+    assert res[0][2] == (0, 32) and res[1][2] == (32, 64)
+
+
+def _eval_shards(rank, world):
+    from hhfm_b200 import dist as hd
+    from oracle import hhfm_oracle as O
+    rng = np.random.default_rng(1)
+    C, N, tp = 9, 101, 7
+    score = rng.integers(-3, 4, (C, N)).astype(np.float32)        # tie-heavy
+    lo, hi = hd.shard_range(N, rank, world)
+    local = O.topk_lowest_index(score[:, lo:hi], tp)
+    ls = torch.from_numpy(np.take_along_axis(score[:, lo:hi], local, axis=1))
+    li = torch.from_numpy(local + lo)
+    ids, sc = hd.merge_topk(ls, li, tp)
+    want = O.topk_lowest_index(score, tp)
+    codes = torch.arange(lo, hi, dtype=torch.int32)
+    allc = hd.gather_rows(codes)
+    return ((ids.numpy() == want).all(), (sc.numpy() == np.take_along_axis(score, want, axis=1)).all(), allc.tolist() == list(range(N)))
+
+
+def test_item_sharded_topk_merge_is_bit_identical():
+    assert all(all(r) for r in run2(_eval_shards))
+
+
+def test_shard_range_covers_everything():
+    from hhfm_b200 import dist as hd
+    for n in (0, 1, 7, 64, 1000003):
+        for w in (1, 2, 3, 8):
+            spans = [hd.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1

@@ -1,0 +1,55 @@
+"""GPU, multi-process: data-parallel training and item-sharded evaluation over NCCL.  Runs with however many GPUs the
+box has (skips the multi-GPU part on a 1-GPU box but still checks the world-size-1 path)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hhfm_b200 import dist as hd
+        from hhfm_b200.models import OUR
+        from oracle import hhfm_oracle as O
+        rng = np.random.default_rng(0)
+        n_user, n_item, M, K, fc, B = 100, 301, 500, 64, 4, 4096
+        model = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, 'AdagradOptimizer', True, False)
+        model.enable_data_parallel(); model.enable_item_sharding()
+        V = model.get_weights()["feature_embeddings"].copy()
+        X = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B)], axis=1)
+        F1 = rng.integers(n_user + n_item, M, (B, fc)); Y = n_user + rng.integers(0, n_item, (B, 10))
+        lo, hi = hd.shard_range(B, rank, world)
+        loss = model.partial_fit({"X": X[lo:hi], "F1": F1[lo:hi], "Y": Y[lo:hi]})
+        loss_ref, _, _, dV = O.pairrank_loss_grads(V, X, Y, F1, None, (0, 0, 0), 0.01)
+        V1, _ = O.adagrad_dense(V, np.full_like(V, 0.1), dV, 0.1)
+        got = model.get_weights()["feature_embeddings"]
+        ok_loss = abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
+        ok_w = bool(np.all(np.abs(got - V1) <= 2e-5 * np.maximum(np.abs(V1 - V), np.sqrt(np.mean((V1 - V) ** 2)))))
+        A = np.concatenate([X[:200], F1[:200]], axis=1)
+        ids = model.topk(A, 20)
+        want = O.topk_lowest_index(O.hhfm_topk_scores(A, got, n_user, n_item, fc, 0), 20)
+        ret[rank] = (ok_loss, ok_w, bool((ids == want).all()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_step_and_sharded_topk(cuda):
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 2)
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] == (True, True, True), (r, ret[r])
