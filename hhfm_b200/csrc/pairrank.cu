@@ -3,6 +3,8 @@
 // sort-free scatter (REDG.E.ADD.F32x4).  Same lane mapping as fm.cu: LPS = K/4 lanes own one sample.
 //
 // Record (int32, `stride` ints, 16-byte aligned): [user, item+, ctx.., time.., neg.., pad].
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hhfm {
@@ -289,6 +291,137 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path of the fused training pass for the reference's default configuration: every Pooling1* is
+// tf.reduce_sum (OurModel7.py:14-19), so context and time rows are interchangeable (all are summed into the
+// hybrid feature and all receive d_hyb), K == 4*LPS, and the group widths are compile-time constants:
+// NP = n_ctx + n_time pooled rows, NNEG negatives.  Everything is unrolled: the record is read with int4 loads,
+// all NP + NNEG + 2 row gathers are independent LDG.128s, no bound or mode tests remain in the loop.
+// Same arithmetic order as the generic kernel.  (~3x fewer instructions per sample; see profiles/.)
+// ---------------------------------------------------------------------------------------------------
+template <int LPS, int NP, int NNEG>
+__global__ void __launch_bounds__(kBlock, 2) pairrank_sum_train_kernel(const PrArgs a) {
+  __shared__ float scratch[32];
+  constexpr int W = 2 + NP + NNEG;
+  constexpr int W4 = (W + 3) / 4;
+  const int lane = threadIdx.x & 31, lg = lane % LPS, grp = lane / LPS;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr int G = 32 / LPS;
+  const float4* __restrict__ Vp = reinterpret_cast<const float4*>(a.V) + lg;
+  float* __restrict__ Gp = a.gV + 4 * lg;
+  const int rep = a.hot.slot ? (int)((warp_g * G + grp) % a.hot.n_rep) : 0;
+  float* __restrict__ Hp = a.hot.slot ? a.hot.ghot + (size_t)rep * a.hot.n_hot * (4 * LPS) + 4 * lg : nullptr;
+  float loss_acc = 0.f;
+
+  auto scatter = [&](int row, float4 v) {
+    float* p = Gp + (size_t)row * (4 * LPS);
+    if (Hp != nullptr) {
+      const int s = __ldg(a.hot.slot + row);
+      if (s >= 0) p = Hp + (size_t)s * (4 * LPS);
+    }
+    red_add_v4(p, v);
+  };
+
+  for (int64_t s0 = warp_g * G; s0 < a.B; s0 += n_warps * G) {
+    const int64_t s = s0 + grp;
+    const bool valid = s < a.B;
+    const int64_t sc = valid ? s : (a.B - 1);
+    int idx[W4 * 4];
+    const int4* r4 = reinterpret_cast<const int4*>(a.idx + sc * a.stride);
+#pragma unroll
+    for (int i = 0; i < W4; i++) {
+      const int4 t = __ldg(r4 + i);
+      idx[4 * i] = t.x; idx[4 * i + 1] = t.y; idx[4 * i + 2] = t.z; idx[4 * i + 3] = t.w;
+    }
+    float4 e[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) e[i] = __ldg(Vp + (size_t)idx[i] * LPS);
+
+    float4 hyb = e[0];                                   // user, then ctx.., time.. in record order
+#pragma unroll
+    for (int i = 0; i < NP; i++) hyb = f4_add(hyb, e[2 + i]);
+    float p[1 + NNEG];
+    p[0] = f4_dot(hyb, e[1]);
+#pragma unroll
+    for (int j = 0; j < NNEG; j++) p[1 + j] = f4_dot(hyb, e[2 + NP + j]);
+#pragma unroll
+    for (int j = 0; j <= NNEG; j++) p[j] = group_sum<LPS>(p[j]);
+
+    float m = p[1];
+    unsigned tie = 1u;
+#pragma unroll
+    for (int j = 1; j < NNEG; j++) {
+      if (p[1 + j] > m) { m = p[1 + j]; tie = 1u << j; }
+      else if (p[1 + j] == m) tie |= 1u << j;
+    }
+    if (valid) {
+      const float x = p[0] - m;
+      const float sg = 1.f / (1.f + expf(-x));
+      if (lg == 0) loss_acc += -logf(sg);
+      const float gp = sg - 1.f;
+      const float gn = -gp / (float)__popc(tie);
+      float4 dh = f4_scale(e[1], gp);
+      scatter(idx[1], f4_scale(hyb, gp));
+      const float4 tn = f4_scale(hyb, gn);
+      unsigned w = tie;
+      while (w) {
+        const int j = __ffs((int)w) - 1;
+        w &= w - 1;
+        const int id = __ldg(a.idx + sc * a.stride + 2 + NP + j);
+        const float4 v = __ldg(Vp + (size_t)id * LPS);
+        dh = f4_fma(v, gn, dh);
+        scatter(id, tn);
+      }
+      scatter(idx[0], dh);
+#pragma unroll
+      for (int i = 0; i < NP; i++) scatter(idx[2 + i], dh);
+    }
+  }
+  const float bl = block_sum(loss_acc, scratch);
+  write_partial(a.loss_partials, bl);
+}
+
+template <int LPS, int NP, int NNEG>
+static int launch_pr_fast(const PrArgs& a, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pairrank_sum_train_kernel<LPS, NP, NNEG>, kBlock, 0);
+    if (occ < 1) occ = 1;
+  }
+  constexpr int G = 32 / LPS;
+  const int grid = grid_for(a.B, (kBlock / 32) * G, occ);
+  pairrank_sum_train_kernel<LPS, NP, NNEG><<<grid, kBlock, 0, st>>>(a);
+  return check_launch("pairrank_sum_train_kernel");
+}
+
+// returns 1 if the fast path does not cover this configuration
+template <int LPS>
+static int dispatch_pr_fast_np(const PrArgs& a, cudaStream_t st, int* rc) {
+  const int np = a.n_ctx + a.n_time;
+  if (a.n_neg != 10) return 1;
+  switch (np) {
+    case 0: *rc = launch_pr_fast<LPS, 0, 10>(a, st); return 0;
+    case 3: *rc = launch_pr_fast<LPS, 3, 10>(a, st); return 0;
+    case 8: *rc = launch_pr_fast<LPS, 8, 10>(a, st); return 0;
+    case 10: *rc = launch_pr_fast<LPS, 10, 10>(a, st); return 0;
+    default: return 1;
+  }
+}
+
+static int dispatch_pr_fast(const PrArgs& a, cudaStream_t st, int* rc) {
+  const bool all_sum = (a.n_ctx == 0 || a.pc == HHFM_POOL_SUM) && (a.n_time == 0 || a.pt == HHFM_POOL_SUM) &&
+                       ((a.n_ctx == 0 && a.n_time == 0) || a.pf == HHFM_POOL_SUM);
+  if (!all_sum || a.touch_stamp || a.pos_out || a.neg_out) return 1;
+  if ((int64_t)a.n_ctx + a.n_time + 2 + a.n_neg > a.stride) return 1;
+  switch (a.K) {
+    case 32: return dispatch_pr_fast_np<8>(a, st, rc);
+    case 64: return dispatch_pr_fast_np<16>(a, st, rc);
+    case 128: return dispatch_pr_fast_np<32>(a, st, rc);
+    default: return 1;
+  }
+}
+
 template <int LPS, int VPL, int MODE, bool ANYMAX>
 static int launch_pr(const PrArgs& a, int deterministic, cudaStream_t st) {
   static int occ = 0;
@@ -323,6 +456,12 @@ static int dispatch_pr(const PrArgs& a, int deterministic, cudaStream_t st) {
 #undef CALL
   }
   return HHFM_ERR_UNSUPPORTED;
+}
+
+// HHFM_NO_FAST=1 forces the generic kernel (A/B measurements, tests of both paths).
+static bool hhfm_fast_path_enabled() {
+  const char* e = getenv("HHFM_NO_FAST");
+  return !(e && e[0] == '1');
 }
 
 static int check_pr(const int32_t* idx, int64_t B, int64_t stride, int n_ctx, int n_time, int n_neg, int pc, int pt,
@@ -378,6 +517,10 @@ extern "C" int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stri
   a.pos_out = pos_out; a.neg_out = neg_out; a.gV = gV; a.loss_partials = loss_partials;
   a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows; a.touched_count = touched_count;
   a.hot = HotPlan{hot_slot, ghot, nullptr, n_rep, n_hot};
+  if (!deterministic && hhfm_fast_path_enabled()) {
+    int frc = 0;
+    if (dispatch_pr_fast(a, (cudaStream_t)stream, &frc) == 0) return frc;
+  }
   return dispatch_pr<PR_TRAIN>(a, deterministic, (cudaStream_t)stream);
 }
 

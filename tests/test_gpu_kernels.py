@@ -274,6 +274,39 @@ def test_fm_hot_row_replicas_with_bias(cuda):
     assert float(hot.ghot.abs().max()) == 0.0 and float(hot.ghot_bias.abs().max()) == 0.0, "fold must clear the replicas"
 
 
+@pytest.mark.parametrize("K,fc,ft", [(64, 8, 0), (128, 5, 5), (32, 0, 0), (64, 3, 0), (128, 5, 3), (64, 0, 0)])
+@pytest.mark.parametrize("use_hot", [False, True])
+def test_specialised_sum_pooling_kernel_matches_oracle_and_generic(cuda, K, fc, ft, use_hot):
+    """The unrolled fast path (all pools = sum, NG = 10, K in {32,64,128}) against the oracle and the generic kernel."""
+    import os
+    lib, ptr, st = _lib_ptr()
+    from hhfm_b200.engine import NO_HOT, HotRows
+    rng = np.random.default_rng(K + fc + ft)
+    M, B, NG = 700, 3001, 10
+    V = make_table(rng, M, K)
+    Pos = np.stack([rng.integers(0, 6, B), rng.integers(100, 400, B)], axis=1)
+    Fea = np.stack([600 + 3 * c + rng.integers(0, 3, B) for c in range(fc)], axis=1) if fc else None
+    Tim = rng.integers(100, 400, (B, ft)) if ft else None
+    Neg = rng.integers(100, 400, (B, NG)); Neg[::9] = Neg[::9, :1]; Neg[:, 5] = Neg[:, 4]
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, Tim, (0, 0, 0), 0.0)
+    rec, stride = _records(Pos, Fea, Tim, Neg)
+    P = lib.partials_len()
+    results = {}
+    for mode in ("fast", "generic"):
+        os.environ["HHFM_NO_FAST"] = "1" if mode == "generic" else "0"
+        hot = HotRows(np.concatenate([np.arange(6), np.arange(600, 600 + 3 * fc)]), M, K, cuda, n_rep=8) if use_hot else None
+        gV = torch.zeros(M, K, device=cuda); lp = torch.zeros(P, device=cuda); out = torch.zeros(1, device=cuda)
+        lib.call("hhfm_pairrank_fwd_bwd", ptr(dev(rec, cuda)), B, stride, fc, ft, NG, 0, 0, 0, ptr(dev(V, cuda)), M, K, None, None,
+                 ptr(gV), ptr(lp), None, 0, None, None, *(hot.args() if hot else NO_HOT), 0, st())
+        if hot:
+            hot.fold(gV, None)
+        lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(out), st())
+        results[mode] = (gV.cpu().numpy(), float(out.item()))
+    os.environ.pop("HHFM_NO_FAST", None)
+    for mode, (gV, l) in results.items():
+        assert_close(l, loss, what=mode + " loss"); assert_close(gV, dV, what=mode + " gV")
+
+
 def test_bpr_is_the_no_context_special_case(cuda):
     rng = np.random.default_rng(21)
     M, K, B = 400, 128, 3000
