@@ -41,6 +41,14 @@ SIGNATURES = {
     "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],
     "hhfm_topn_select": [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp],
     "hhfm_metrics_walk": [vp, vp, vp, i64, i32, i32, vp, vp],
+    "hhfm_topn_tc_supported": [i32, i64, i64, i32],
+    "hhfm_topn_tc_prepare_items": [i32, vp, vp, i64, i64, vp, vp, vp],
+    "hhfm_topn_score": [i32, vp, vp, i64, vp, i64, i64, i32, vp, i64, vp],
+    "hhfm_topn_rescore_merge": [i32, vp, vp, i64, vp, vp, vp, i64, i64, i32, i32, vp, i64, vp, vp, vp, vp],
+}
+INT64_FUNCS = {
+    "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],
+    "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
 }
 OPTIONAL = {}   # symbols added by later kernels are appended by their modules via `declare`
 
@@ -72,6 +80,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = cint
         fn.argtypes = args
+    for name, args in INT64_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.restype = i64
+        fn.argtypes = args
     _lib = lib
     return lib
 
@@ -98,4 +110,5 @@ def partials_len() -> int:
 
 
 def exported_symbols():
-    return ["hhfm_abi_version", "hhfm_last_error", "hhfm_partials_len"] + list(SIGNATURES) + list(OPTIONAL)
+    return (["hhfm_abi_version", "hhfm_last_error", "hhfm_partials_len"] + list(SIGNATURES) + list(OPTIONAL) +
+            list(INT64_FUNCS))

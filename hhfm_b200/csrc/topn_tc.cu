@@ -1,0 +1,642 @@
+// K6 tensor-core path: full-catalog scoring as a bf16 GEMM on tcgen05 (accumulators in TMEM, operands staged by TMA)
+// used as a FILTER, followed by exact fp32 rescoring of the few survivors -- index lists stay bit-identical to the
+// exact path / the oracle (FM.py:172-185, BPR.py:131-136, MF.py:144-149, OurModel7.py:229-295).
+//
+//   1. prep      Q [C,K] fp32 -> bf16 A [C,Kp], per-row ||q||, (FM) R_c = q.Fc and ||Fc||;  items -> bf16 B [N,Kp]
+//                (FM: the item bias rides in an extra k-chunk as hi+lo bf16 against two 1.0 columns of A), max ||v||.
+//   2. GEMM      tc_score_kernel: persistent, warp-specialised (TMA producer / single-thread tcgen05.mma issuer /
+//                4 epilogue warps).  CTA tile 128 contexts x BN items, all of Kp per stage.  The epilogue reads the
+//                fp32 accumulator with tcgen05.ld (thread t owns context row t) and keeps ONE number per 32 items:
+//                the group maximum -> gmax [C, ceil(N/32)].  No atomics, no data-dependent control flow.
+//   3. threshold tau_c = tp-th largest group maximum of row c (select_kernel).  The tp group maxima are tp distinct
+//                items with approximate score >= tau_c, so the exact tp-th best score s* >= tau_c - E_c.
+//   4. rescore   every group with gmax >= tau_c - 2 E_c is rescored exactly (canonical fp32 order) and items with
+//                s >= tau_c (+R_c) - E_c become candidates; the final select_kernel sorts them (score desc, id asc).
+// E_c bounds |approx - exact| for row c: bf16 rounding of both operands gives 2^-8 ||q|| ||v|| (Cauchy-Schwarz);
+// we use 2^-7 ||q_c|| max_n||v_n|| plus the bias split and fp32 rounding terms.  Every true top-tp item n has
+// approx_n >= s* - E >= tau - 2E, so its group is rescored: the candidate set contains the exact answer.
+// A row whose candidates overflow the buffer is flagged and redone by the exact path (host side).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace hhfm {
+
+constexpr int kGroup = 32;          // items per group maximum (= one tcgen05.ld.32x32b.x32)
+constexpr int kBM = 128;            // contexts per CTA tile (UMMA M)
+constexpr int kKC = 64;             // bf16 elements per 128-byte swizzle row
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s
+      if (err) atomicExch(err, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B = 1024)
+// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) {   // v >= 0
+  atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// items fp32 [N,K] (+bias [N]) -> bf16 [N,Kp]; stats[0] = max ||v_n||, stats[1] = max |b_n|.  One warp per item.
+__global__ void __launch_bounds__(256) tc_prep_items_kernel(const float* __restrict__ items, const float* __restrict__ bias,
+                                                            int64_t N, int K, int Kp, __nv_bfloat16* __restrict__ out,
+                                                            float* __restrict__ stats) {
+  const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float sq = 0.f;
+  for (int k = lane; k < Kp; k += 32) {
+    float v = 0.f;
+    if (k < K) {
+      v = __ldg(items + n * K + k);
+      sq += v * v;
+    } else if (bias != nullptr && k == K) {
+      v = __bfloat162float(__float2bfloat16_rn(__ldg(bias + n)));
+    } else if (bias != nullptr && k == K + 1) {
+      const float b = __ldg(bias + n);
+      v = b - __bfloat162float(__float2bfloat16_rn(b));
+    }
+    out[n * Kp + k] = __float2bfloat16_rn(v);
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) {
+    atomic_max_pos(stats + 0, sqrtf(sq) * 1.0000005f);
+    if (bias != nullptr) atomic_max_pos(stats + 1, fabsf(__ldg(bias + n)));
+  }
+}
+
+// Q fp32 [C,K] (+Fc for FM) -> bf16 [C,Kp]; qinfo[c] = {||q||, R = q.Fc, ||Fc||, 0}.  One warp per context.
+__global__ void __launch_bounds__(256) tc_prep_queries_kernel(const float* __restrict__ Q, const float* __restrict__ Fc,
+                                                              int64_t C, int K, int Kp, int fm, __nv_bfloat16* __restrict__ out,
+                                                              float4* __restrict__ qinfo) {
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float sq = 0.f, r = 0.f, sf = 0.f;
+  for (int k = lane; k < Kp; k += 32) {
+    float v = 0.f;
+    if (k < K) {
+      v = __ldg(Q + c * K + k);
+      sq += v * v;
+      if (fm) {
+        const float f = __ldg(Fc + c * K + k);
+        r = fmaf(v, f, r);
+        sf += f * f;
+      }
+    } else if (fm && (k == K || k == K + 1)) {
+      v = 1.f;
+    }
+    out[c * Kp + k] = __float2bfloat16_rn(v);
+  }
+  sq = warp_sum(sq); r = warp_sum(r); sf = warp_sum(sf);
+  if (lane == 0) qinfo[c] = make_float4(sqrtf(sq) * 1.0000005f, r, sqrtf(sf) * 1.0000005f, 0.f);
+}
+
+// E_c: bound on |approximate - exact| for row c (see header).
+__device__ __forceinline__ float row_error_bound(float4 qi, float vmax, float bmax, int fm, int K) {
+  float e = 0.0078125f * qi.x * vmax;                                // 2^-7 ||q|| max||v||
+  e += 1.1920929e-07f * (float)(K + 8) * qi.x * (vmax + qi.z);       // fp32 accumulation / canonical-order rounding
+  if (fm) e += 1.5258789e-05f * bmax + 4.7683716e-07f * (fabsf(qi.y) + bmax);   // bias hi+lo split, R_c rounding
+  return e * 1.01f + 1e-30f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the GEMM: gmax[c, g] = max over items n in group g of (A[c,:] . B[n,:])
+// ---------------------------------------------------------------------------------------------------
+struct TcArgs {
+  int n_row_blocks, n_tiles, tiles_per_unit, splits, n_units;
+  int64_t C, N;
+  int64_t gmax_stride;    // floats per gmax row
+  float* gmax;
+  int* err;
+};
+
+template <int NKC, int BN, int STAGES>
+struct TcSmem {
+  static constexpr int kABytes = NKC * kBM * 128;
+  static constexpr int kBStage = NKC * BN * 128;
+  static constexpr int kBytes = kABytes + STAGES * kBStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int NKC, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TcSmem<NKC, BN, STAGES>::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * TcSmem<NKC, BN, STAGES>::kBStage);
+  uint64_t* full = bars;                    // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;          // [STAGES] MMA -> TMA
+  uint64_t* a_full = bars + 2 * STAGES;     // A tile landed
+  uint64_t* a_empty = a_full + 1;           // MMA finished with the A tile
+  uint64_t* t_full = a_empty + 1;           // [2] accumulator ready
+  uint64_t* t_empty = t_full + 2;           // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BN;    // 512 (BN=256) or 256 (BN=128): power of two >= 32
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================= TMA producer (one lane) =================
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0, aph = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const int rb = u / a.splits, sp = u % a.splits;
+        const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
+        mbar_wait(a_empty, aph ^ 1, a.err);
+        mbar_expect_tx(a_full, TcSmem<NKC, BN, STAGES>::kABytes);
+#pragma unroll
+        for (int kc = 0; kc < NKC; kc++) tma_load_2d(sA + kc * kBM * 128, &tmA, kc * kKC, rb * kBM, a_full);
+        aph ^= 1;
+        for (int t = t0; t < t1; t++) {
+          mbar_wait(empty + st, ph ^ 1, a.err);
+          mbar_expect_tx(full + st, TcSmem<NKC, BN, STAGES>::kBStage);
+#pragma unroll
+          for (int kc = 0; kc < NKC; kc++)
+            tma_load_2d(sB + st * TcSmem<NKC, BN, STAGES>::kBStage + kc * BN * 128, &tmB, kc * kKC, t * BN, full + st);
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer (one lane) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      int st = 0, acc = 0; uint32_t ph = 0, aph = 0, tph = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const int sp = u % a.splits;
+        const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
+        mbar_wait(a_full, aph, a.err);
+        aph ^= 1;
+        for (int t = t0; t < t1; t++) {
+          mbar_wait(t_empty + acc, tph ^ 1, a.err);
+          mbar_wait(full + st, ph, a.err);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + st * TcSmem<NKC, BN, STAGES>::kBStage);
+#pragma unroll
+          for (int kc = 0; kc < NKC; kc++) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {       // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+              const uint64_t ad = make_sdesc(a0 + kc * kBM * 128 + k4 * 32);
+              const uint64_t bd = make_sdesc(b0 + kc * BN * 128 + k4 * 32);
+              umma_bf16(tmem_base + acc * BN, ad, bd, idesc, (kc | k4) != 0);
+            }
+          }
+          umma_commit(empty + st);        // smem stage reusable once these MMAs retire
+          umma_commit(t_full + acc);      // accumulator complete
+          if (++st == STAGES) { st = 0; ph ^= 1; }
+          if (++acc == 2) { acc = 0; tph ^= 1; }
+        }
+        umma_commit(a_empty);             // A tile reusable
+      }
+    }
+  } else {
+    // ================= epilogue: 4 warps, thread t owns context row t =================
+    int acc = 0; uint32_t tph = 0;
+    const int row_in_tile = warp * 32 + lane;
+    constexpr int kChunks = BN / kGroup;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const int rb = u / a.splits, sp = u % a.splits;
+      const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
+      const int64_t row = (int64_t)rb * kBM + row_in_tile;
+      for (int t = t0; t < t1; t++) {
+        mbar_wait(t_full + acc, tph, a.err);
+        tc_fence_after();
+        float gm[kChunks];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+        const int64_t n_base = (int64_t)t * BN;
+#pragma unroll
+        for (int c = 0; c < kChunks; c++) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * kGroup, r);
+          tmem_ld_wait();
+          float m = -INFINITY;
+          if (n_base + (c + 1) * kGroup <= a.N) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(r[i]));
+          } else {                              // last tile: items beyond N are TMA zero fill, not scores
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (n_base + c * kGroup + i < a.N) m = fmaxf(m, __uint_as_float(r[i]));
+          }
+          gm[c] = m;
+        }
+        tc_fence_before();
+        mbar_arrive(t_empty + acc);
+        if (row < a.C) {
+          float4* dst = reinterpret_cast<float4*>(a.gmax + row * a.gmax_stride + (int64_t)t * kChunks);
+#pragma unroll
+          for (int c = 0; c < kChunks; c += 4) dst[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+        }
+        if (++acc == 2) { acc = 0; tph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact rescoring of the surviving groups.  One CTA per context row; warps scan 32 group maxima at a time, a warp
+// rescores one surviving group (lane = item) in the canonical fp32 order and appends items with s >= tau + R - E.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_rescore_kernel(int kind, const float* __restrict__ Q, const float* __restrict__ Fc,
+                                                         const float* __restrict__ items, const float* __restrict__ item_bias,
+                                                         int64_t N, int K, const float* __restrict__ gmax, int64_t gmax_stride,
+                                                         int n_groups, const float* __restrict__ tau, int tau_stride,
+                                                         const float4* __restrict__ qinfo, const float* __restrict__ stats,
+                                                         int cap, float* __restrict__ cand_scores, int32_t* __restrict__ cand_ids,
+                                                         int32_t* __restrict__ cand_cnt, int32_t* __restrict__ overflow) {
+  __shared__ int s_cnt;
+  extern __shared__ float s_q[];            // q[K] (+ Fc[K] for FM)
+  const int64_t c = blockIdx.x;
+  const int fm = kind == HHFM_QUERY_FM;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    s_q[k] = Q[c * K + k];
+    if (fm) s_q[K + k] = Fc[c * K + k];
+  }
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const float4 qi = qinfo[c];
+  const float E = row_error_bound(qi, stats[0], stats[1], fm, K);
+  const float t = tau[c * tau_stride];
+  const float thr_group = t - 2.f * E;
+  const float thr_exact = t + (fm ? qi.y : 0.f) - E;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* grow = gmax + c * gmax_stride;
+  for (int g0 = warp * 32; g0 < n_groups; g0 += nw * 32) {
+    const int g = g0 + lane;
+    const bool hit = (g < n_groups) && (grow[g] >= thr_group);
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    while (mask) {
+      const int b = __ffs((int)mask) - 1;
+      mask &= mask - 1;
+      const int64_t n = (int64_t)(g0 + b) * kGroup + lane;
+      float s = -INFINITY;
+      if (n < N) {
+        const float* v = items + n * K;
+        float acc = 0.f;
+        for (int k = 0; k < K; k++) {
+          const float x = fm ? __fadd_rn(__ldg(v + k), s_q[K + k]) : __ldg(v + k);
+          const float p = __fmul_rn(s_q[k], x);
+          acc = (k == 0) ? p : __fadd_rn(acc, p);
+        }
+        s = (fm && item_bias) ? __fadd_rn(__ldg(item_bias + n), acc) : acc;
+      }
+      const bool keep = (n < N) && (s >= thr_exact);
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (km) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_cnt, __popc(km));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+          const int slot = base + __popc(km & ((1u << lane) - 1));
+          if (slot < cap) {
+            cand_scores[c * cap + slot] = s;
+            cand_ids[c * cap + slot] = (int32_t)n;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n = s_cnt;
+    cand_cnt[c] = n < cap ? n : cap;
+    overflow[c] = n > cap ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int round_up(int64_t x, int64_t m) { return (int)((x + m - 1) / m * m); }
+
+struct TcPlan {
+  int Kp, nkc, bn, stages;
+  bool ok;
+};
+
+static TcPlan tc_plan(int kind, int64_t K) {
+  TcPlan p{};
+  const int64_t kk = K + (kind == HHFM_QUERY_FM ? 2 : 0);
+  p.Kp = round_up(kk, kKC);
+  p.nkc = p.Kp / kKC;
+  p.ok = true;
+  if (p.nkc == 1) { p.bn = 256; p.stages = 4; }
+  else if (p.nkc == 2) { p.bn = 256; p.stages = 2; }
+  else if (p.nkc == 3) { p.bn = 128; p.stages = 3; }
+  else if (p.nkc == 4) { p.bn = 128; p.stages = 2; }
+  else p.ok = false;
+  return p;
+}
+
+// The driver entry point is resolved at run time so the library does not link against libcuda (it must load on a
+// box without a GPU driver: the CPU test tier imports it to check the exported symbols).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int Kp, int box_rows) {
+  EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
+  if (cuTensorMapEncodeTiled == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return HHFM_ERR_LAUNCH;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HHFM_ERR_LAUNCH;
+  }
+  return HHFM_OK;
+}
+
+template <int NKC, int BN, int STAGES>
+static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const TcArgs& a, cudaStream_t st) {
+  constexpr int smem = TcSmem<NKC, BN, STAGES>::kBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_score_kernel<NKC, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("tc_score_kernel: cannot reserve %d bytes of shared memory", smem);
+      return HHFM_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
+  tc_score_kernel<NKC, BN, STAGES><<<grid, 192, smem, st>>>(tA, tB, a);
+  return check_launch("tc_score_kernel");
+}
+
+struct TcLayout {   // carve-up of the caller's workspace
+  size_t off_A, off_qinfo, off_gmax, off_tau, off_cs, off_ci, off_cc, off_err, total;
+  int64_t gmax_stride;
+  int n_groups, cap;
+};
+
+static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
+  TcLayout L{};
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const int64_t n_pad = (N + bn - 1) / bn * bn;
+  L.n_groups = (int)((N + kGroup - 1) / kGroup);
+  L.gmax_stride = n_pad / kGroup;
+  L.cap = 2 * tp + 96;
+  size_t o = 0;
+  L.off_A = o; o = align(o + (size_t)C * Kp * 2);
+  L.off_qinfo = o; o = align(o + (size_t)C * 16);
+  L.off_gmax = o; o = align(o + (size_t)C * L.gmax_stride * 4);
+  L.off_tau = o; o = align(o + (size_t)C * tp * 4 * 2);      // select writes [C,tp] scores + ids
+  L.off_cs = o; o = align(o + (size_t)C * L.cap * 4);
+  L.off_ci = o; o = align(o + (size_t)C * L.cap * 4);
+  L.off_cc = o; o = align(o + (size_t)C * 4);
+  L.off_err = o; o = align(o + 256);
+  L.total = o;
+  return L;
+}
+
+}  // namespace hhfm
+
+using namespace hhfm;
+
+extern "C" int hhfm_topn_select(const float* scores, const int32_t* ids, const int32_t* counts, int64_t C,
+                                int64_t row_stride, int64_t n, int32_t tp, int32_t id_offset, float* out_scores,
+                                int32_t* out_ids, hhfm_stream_t stream);
+
+extern "C" int hhfm_topn_tc_supported(int32_t kind, int64_t N, int64_t K, int32_t tp) {
+  if (kind < 0 || kind > 2 || K <= 0 || tp < 1 || tp > 1024) return 0;
+  if (!tc_plan(kind, K).ok) return 0;
+  return ((N + kGroup - 1) / kGroup) >= tp ? 1 : 0;     // need at least tp group maxima for the threshold
+}
+
+extern "C" int64_t hhfm_topn_tc_item_operand_bytes(int32_t kind, int64_t N, int64_t K) {
+  TcPlan p = tc_plan(kind, K);
+  return p.ok ? (int64_t)N * p.Kp * 2 : 0;
+}
+
+extern "C" int64_t hhfm_workspace_bytes_topn(int32_t kind, int64_t C, int64_t N, int64_t K, int32_t tp) {
+  TcPlan p = tc_plan(kind, K);
+  if (!p.ok) return 0;
+  return (int64_t)tc_layout(C, N, p.Kp, tp, p.bn).total;
+}
+
+extern "C" int hhfm_topn_tc_prepare_items(int32_t kind, const float* items, const float* item_bias, int64_t N, int64_t K,
+                                          void* item_operand, float* stats, hhfm_stream_t stream) {
+  HHFM_REQUIRE(items && item_operand && stats && N > 0, "topn_tc_prepare_items: NULL argument");
+  TcPlan p = tc_plan(kind, K);
+  HHFM_REQUIRE(p.ok, "topn_tc_prepare_items: K=%lld unsupported by the tensor-core path", (long long)K);
+  HHFM_REQUIRE(((uintptr_t)item_operand & 127) == 0, "topn_tc_prepare_items: item_operand must be 128-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(stats, 0, 2 * sizeof(float), st);
+  tc_prep_items_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(items, kind == HHFM_QUERY_FM ? item_bias : nullptr, N, (int)K,
+                                                              p.Kp, reinterpret_cast<__nv_bfloat16*>(item_operand), stats);
+  return check_launch("tc_prep_items_kernel");
+}
+
+// Stage 1-3: filter.  Leaves gmax / tau / qinfo in the workspace for hhfm_topn_rescore_merge.
+extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, int64_t C, const void* item_operand,
+                               int64_t N, int64_t K, int32_t tp, void* workspace, int64_t workspace_bytes,
+                               hhfm_stream_t stream) {
+  HHFM_REQUIRE(Q && item_operand && workspace, "topn_score: NULL argument");
+  HHFM_REQUIRE(kind != HHFM_QUERY_FM || Fc, "topn_score: FM needs Fc");
+  HHFM_REQUIRE(hhfm_topn_tc_supported(kind, N, K, tp), "topn_score: configuration not supported by the tensor-core path");
+  HHFM_REQUIRE(C > 0, "topn_score: C must be > 0");
+  TcPlan p = tc_plan(kind, K);
+  TcLayout L = tc_layout(C, N, p.Kp, tp, p.bn);
+  HHFM_REQUIRE(workspace_bytes >= (int64_t)L.total, "topn_score: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+               (long long)L.total);
+  HHFM_REQUIRE(((uintptr_t)workspace & 255) == 0, "topn_score: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws + L.off_A);
+  float4* qinfo = reinterpret_cast<float4*>(ws + L.off_qinfo);
+  float* gmax = reinterpret_cast<float*>(ws + L.off_gmax);
+  float* tau_sc = reinterpret_cast<float*>(ws + L.off_tau);
+  int32_t* tau_id = reinterpret_cast<int32_t*>(ws + L.off_tau + (size_t)C * tp * 4);
+  int* err = reinterpret_cast<int*>(ws + L.off_err);
+  cudaMemsetAsync(err, 0, sizeof(int), st);
+  tc_prep_queries_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(Q, Fc, C, (int)K, p.Kp, kind == HHFM_QUERY_FM, A, qinfo);
+  int rc = check_launch("tc_prep_queries_kernel");
+  if (rc) return rc;
+
+  CUtensorMap tA, tB;
+  if ((rc = make_tmap(&tA, A, C, p.Kp, kBM))) return rc;
+  if ((rc = make_tmap(&tB, item_operand, N, p.Kp, p.bn))) return rc;
+  TcArgs a{};
+  a.C = C; a.N = N;
+  a.n_row_blocks = (int)((C + kBM - 1) / kBM);
+  a.n_tiles = (int)((N + p.bn - 1) / p.bn);
+  int splits = (2 * sm_count() + a.n_row_blocks - 1) / a.n_row_blocks;     // aim at >= 2 units per SM
+  if (splits > a.n_tiles) splits = a.n_tiles;
+  if (splits < 1) splits = 1;
+  a.tiles_per_unit = (a.n_tiles + splits - 1) / splits;
+  a.splits = (a.n_tiles + a.tiles_per_unit - 1) / a.tiles_per_unit;
+  a.n_units = a.n_row_blocks * a.splits;
+  a.gmax = gmax; a.gmax_stride = L.gmax_stride; a.err = err;
+  if (p.nkc == 1) rc = launch_tc<1, 256, 4>(tA, tB, a, st);
+  else if (p.nkc == 2) rc = launch_tc<2, 256, 2>(tA, tB, a, st);
+  else if (p.nkc == 3) rc = launch_tc<3, 128, 3>(tA, tB, a, st);
+  else rc = launch_tc<4, 128, 2>(tA, tB, a, st);
+  if (rc) return rc;
+  // tau_c = tp-th largest group maximum
+  return hhfm_topn_select(gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, tp, 0, tau_sc, tau_id, stream);
+}
+
+// Stage 4: exact rescoring of surviving groups + final (score desc, id asc) selection.
+extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float* Fc, int64_t C, const float* items,
+                                       const float* item_bias, const float* stats, int64_t N, int64_t K, int32_t tp,
+                                       int32_t id_offset, void* workspace, int64_t workspace_bytes, float* out_scores,
+                                       int32_t* out_ids, int32_t* overflow, hhfm_stream_t stream) {
+  HHFM_REQUIRE(Q && items && stats && workspace && out_ids && overflow, "topn_rescore_merge: NULL argument");
+  TcPlan p = tc_plan(kind, K);
+  HHFM_REQUIRE(p.ok, "topn_rescore_merge: unsupported K");
+  TcLayout L = tc_layout(C, N, p.Kp, tp, p.bn);
+  HHFM_REQUIRE(workspace_bytes >= (int64_t)L.total, "topn_rescore_merge: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const float4* qinfo = reinterpret_cast<const float4*>(ws + L.off_qinfo);
+  const float* gmax = reinterpret_cast<const float*>(ws + L.off_gmax);
+  const float* tau_sc = reinterpret_cast<const float*>(ws + L.off_tau);
+  float* cs = reinterpret_cast<float*>(ws + L.off_cs);
+  int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
+  int32_t* cc = reinterpret_cast<int32_t*>(ws + L.off_cc);
+  const int fm = kind == HHFM_QUERY_FM;
+  const size_t smem = (size_t)K * (fm ? 2 : 1) * sizeof(float);
+  tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, gmax, L.gmax_stride,
+                                                    L.n_groups, tau_sc + (tp - 1), tp, qinfo, stats, L.cap, cs, ci, cc, overflow);
+  int rc = check_launch("tc_rescore_kernel");
+  if (rc) return rc;
+  return hhfm_topn_select(cs, ci, cc, C, L.cap, L.cap, tp, id_offset, out_scores, out_ids, stream);
+}

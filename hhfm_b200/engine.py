@@ -258,38 +258,74 @@ NO_HOT_BIAS = (None, None, None, 0, 0)
 # K6/K7: full-catalog top-N, exact path
 # --------------------------------------------------------------------------------------------------
 class TopN:
-    """Exact full-catalog scorer + selector over an item shard [item_lo, item_hi) of the catalog."""
+    """Full-catalog scorer + selector over an item shard [item_lo, item_hi) of the catalog.
+
+    method="exact": fp32 SIMT scorer (canonical order) + radix select.
+    method="tc":    tcgen05 bf16 GEMM filter with a fused group-max epilogue, exact rescoring of the survivors, select;
+                    same lists bit for bit (see csrc/topn_tc.cu).
+    method="auto":  "tc" when the configuration is supported and the problem is big enough to leave launch latency
+                    behind (C*N >= 2^22 pairs), otherwise "exact".
+    """
 
     def __init__(self, device, max_workspace_bytes=1 << 30):
         self.device = device
         self.stage = Staging(torch.int32, device)
         self.max_ws = max_workspace_bytes
         self._ws = None
+        self._ws_bytes = None
+        self._items = {}            # (kind, lo, hi) -> (version, operand, stats)
+        self.last_method = None
+        self.last_overflow_rows = 0
 
     def _workspace(self, numel):
         if self._ws is None or self._ws.numel() < numel:
             self._ws = torch.empty(numel, dtype=torch.float32, device=self.device)
         return self._ws[:numel]
 
+    def _byte_workspace(self, nbytes):
+        if self._ws_bytes is None or self._ws_bytes.numel() < nbytes:
+            self._ws_bytes = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws_bytes
+
     def upload_rows(self, A, id_limit):
         host, stride = pack_records([A], id_limit, self.stage)
         dev = self.stage.upload(host.numel()).view(host.shape[0], stride)
         return dev, stride
 
+    def build_query(self, kind, A_dev, stride, n_ctx, n_time, pools, V):
+        C_rows = A_dev.shape[0]
+        M, K = V.shape
+        Q = torch.empty(C_rows, K, dtype=torch.float32, device=self.device)
+        Fc = torch.empty(C_rows, K, dtype=torch.float32, device=self.device) if kind == QUERY_FM else None
+        _lib.call("hhfm_topn_build_query", kind, ptr(A_dev), C_rows, stride, n_ctx, n_time, pools[0], pools[1], pools[2],
+                  ptr(V), M, K, ptr(Q), ptr(Fc), cur_stream())
+        return Q, Fc
+
     def topk(self, kind, A_dev, stride, n_ctx, n_time, pools, V, bias, n_user, n_item, tp, item_lo=0, item_hi=None,
-             return_scores=False):
+             return_scores=False, method="auto", version=None):
         """A_dev int32 [C,stride] on device.  Returns ids int32 [C,tp] relative to the item range (+ scores)."""
         item_hi = n_item if item_hi is None else item_hi
         N = item_hi - item_lo
         C_rows = A_dev.shape[0]
-        M, K = V.shape
-        st = cur_stream()
-        Q = torch.empty(C_rows, K, dtype=torch.float32, device=self.device)
-        Fc = torch.empty(C_rows, K, dtype=torch.float32, device=self.device) if kind == QUERY_FM else None
-        _lib.call("hhfm_topn_build_query", kind, ptr(A_dev), C_rows, stride, n_ctx, n_time, pools[0], pools[1], pools[2],
-                  ptr(V), M, K, ptr(Q), ptr(Fc), st)
+        K = V.shape[1]
+        Q, Fc = self.build_query(kind, A_dev, stride, n_ctx, n_time, pools, V)
         items = V[n_user + item_lo:n_user + item_hi]
         ibias = bias.reshape(-1)[n_user + item_lo:n_user + item_hi] if (bias is not None and kind == QUERY_FM) else None
+        lib = _lib.load()
+        supported = bool(lib.hhfm_topn_tc_supported(kind, N, K, tp)) and N > 0
+        if method == "tc" and not supported:
+            raise _lib.HhfmError("tensor-core top-N does not cover kind=%d N=%d K=%d tp=%d" % (kind, N, K, tp))
+        use_tc = supported and (method == "tc" or (method == "auto" and C_rows * N >= (1 << 22)))
+        self.last_method = "tc" if use_tc else "exact"
+        if use_tc:
+            out_ids, out_sc = self._topk_tc(kind, Q, Fc, items, ibias, N, K, tp, item_lo, version)
+        else:
+            out_ids, out_sc = self._topk_exact(kind, Q, Fc, items, ibias, N, K, tp, item_lo)
+        return (out_ids, out_sc) if return_scores else out_ids
+
+    def _topk_exact(self, kind, Q, Fc, items, ibias, N, K, tp, item_lo):
+        C_rows = Q.shape[0]
+        st = cur_stream()
         out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
         out_sc = torch.empty(C_rows, tp, dtype=torch.float32, device=self.device)
         chunk = max(1, min(C_rows, self.max_ws // max(1, 4 * N), 65535 * 32))
@@ -300,7 +336,47 @@ class TopN:
                       ptr(items), ptr(ibias), N, K, ptr(ws), N, st)
             _lib.call("hhfm_topn_select", ptr(ws), None, None, c1 - c0, N, N, tp, item_lo, ptr(out_sc[c0:c1]),
                       ptr(out_ids[c0:c1]), st)
-        return (out_ids, out_sc) if return_scores else out_ids
+        return out_ids, out_sc
+
+    def _item_operand(self, kind, items, ibias, N, K, key, version):
+        hit = self._items.get(key)
+        if hit is not None and version is not None and hit[0] == version:
+            return hit[1], hit[2]
+        lib = _lib.load()
+        nbytes = int(lib.hhfm_topn_tc_item_operand_bytes(kind, N, K))
+        op = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_topn_tc_prepare_items", kind, ptr(items), ptr(ibias), N, K, ptr(op), ptr(stats), cur_stream())
+        self._items[key] = (version, op, stats)
+        return op, stats
+
+    def _topk_tc(self, kind, Q, Fc, items, ibias, N, K, tp, item_lo, version):
+        lib = _lib.load()
+        C_rows = Q.shape[0]
+        st = cur_stream()
+        op, stats = self._item_operand(kind, items, ibias, N, K, (kind, item_lo, item_lo + N), version)
+        out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        out_sc = torch.empty(C_rows, tp, dtype=torch.float32, device=self.device)
+        overflow = torch.zeros(C_rows, dtype=torch.int32, device=self.device)
+        per_row = max(1, int(lib.hhfm_workspace_bytes_topn(kind, 1024, N, K, tp)) // 1024)
+        chunk = max(128, min(C_rows, (self.max_ws // per_row) // 128 * 128))
+        for c0 in range(0, C_rows, chunk):
+            c1 = min(C_rows, c0 + chunk)
+            nbytes = int(lib.hhfm_workspace_bytes_topn(kind, c1 - c0, N, K, tp))
+            ws = self._byte_workspace(nbytes)
+            fcp = ptr(Fc[c0:c1]) if Fc is not None else None
+            _lib.call("hhfm_topn_score", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(op), N, K, tp, ptr(ws), nbytes, st)
+            _lib.call("hhfm_topn_rescore_merge", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(items), ptr(ibias), ptr(stats), N, K,
+                      tp, item_lo, ptr(ws), nbytes, ptr(out_sc[c0:c1]), ptr(out_ids[c0:c1]), ptr(overflow[c0:c1]), st)
+        bad = torch.nonzero(overflow).reshape(-1)
+        self.last_overflow_rows = int(bad.numel())
+        if bad.numel() > 0:          # candidate buffer overflowed (tie-degenerate rows): redo those rows exactly
+            Qb = Q[bad].contiguous()
+            Fb = Fc[bad].contiguous() if Fc is not None else None
+            ids_b, sc_b = self._topk_exact(kind, Qb, Fb, items, ibias, N, K, tp, item_lo)
+            out_ids[bad] = ids_b
+            out_sc[bad] = sc_b
+        return out_ids, out_sc
 
 
 def metrics_walk(pred_global, target, target_in_pf, TopK):

@@ -75,6 +75,8 @@ class _Base:
         self._f32_stage = Staging(torch.float32, self.device)
         self._topn = TopN(self.device)
         self._dp_group = None
+        self._version = 0           # bumped whenever the weights change (invalidates cached top-N item operands)
+        self.topn_method = "auto"   # "auto" | "exact" | "tc"
         self.deterministic = False
         self.hot_rows = "auto"      # "auto": plan from the first batch; None: off; or an explicit id list
         self._hot = None
@@ -123,12 +125,14 @@ class _Base:
         V = self.weights["feature_embeddings"]
         grp = getattr(self, "_eval_group", None)
         if grp is None:
-            ids = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp)
+            ids = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp,
+                                  method=self.topn_method, version=self._version)
             return ids.cpu().numpy()
         rank, ws = hd.world(grp)
         lo, hi = hd.shard_range(self.n_item, rank, ws)
         ids, sc = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp,
-                                  item_lo=lo, item_hi=hi, return_scores=True)
+                                  item_lo=lo, item_hi=hi, return_scores=True, method=self.topn_method,
+                                  version=self._version)
         ids, _ = hd.merge_topk(sc, ids, tp, grp)
         return ids.cpu().numpy()
 
@@ -157,6 +161,7 @@ class _Base:
         return self._lamda > 0
 
     def _finish_loss(self, with_reg):
+        self._version += 1
         _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if with_reg else None,
                   0.5 * self._lamda if with_reg else 0.0, ptr(self._loss_dev), cur_stream())
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
@@ -182,6 +187,7 @@ class _Base:
                 raise KeyError(k)
             t = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(self.weights[k].shape)
             self.weights[k].copy_(t.to(self.device))
+        self._version += 1
 
     def get_weights(self):
         return {k: v.detach().cpu().numpy().copy() for k, v in self.weights.items()}

@@ -203,6 +203,30 @@ int hhfm_topn_select(const float* scores, const int32_t* ids, const int32_t* cou
                      int64_t n, int32_t tp, int32_t id_offset, float* out_scores, int32_t* out_ids,
                      hhfm_stream_t stream);
 
+/* Tensor-core path (topn_tc.cu): the same top-N lists, bit-identical, with the catalog scoring done as a bf16 GEMM
+ * on tcgen05 (TMA-staged operands, fp32 accumulators in TMEM) used as a FILTER, then exact fp32 rescoring:
+ *   hhfm_topn_tc_prepare_items  items fp32 [N,K] (+bias) -> bf16 operand [N,Kp] and stats = {max ||v||, max |b|}
+ *                               (cache it while the weights do not change; size from hhfm_topn_tc_item_operand_bytes)
+ *   hhfm_topn_score             queries -> bf16, GEMM with a fused group-max epilogue (one fp32 per 32 items),
+ *                               tau_c = tp-th largest group maximum; results stay in `workspace`
+ *   hhfm_topn_rescore_merge     groups with max >= tau_c - 2E_c are rescored exactly (canonical order), candidates
+ *                               selected under (score desc, id asc); id_offset = item-shard offset (multi-GPU merge).
+ *                               overflow[c] = 1 marks a row whose candidate buffer overflowed (tie-degenerate data):
+ *                               the caller must redo that row with the exact path.
+ * hhfm_topn_tc_supported says whether (kind, N, K, tp) is covered (K + bias chunk <= 256, ceil(N/32) >= tp).
+ * workspace: 256-byte aligned, hhfm_workspace_bytes_topn bytes; item_operand: 128-byte aligned. */
+int hhfm_topn_tc_supported(int32_t kind, int64_t N, int64_t K, int32_t tp);
+int64_t hhfm_topn_tc_item_operand_bytes(int32_t kind, int64_t N, int64_t K);
+int64_t hhfm_workspace_bytes_topn(int32_t kind, int64_t C, int64_t N, int64_t K, int32_t tp);
+int hhfm_topn_tc_prepare_items(int32_t kind, const float* items, const float* item_bias, int64_t N, int64_t K,
+                               void* item_operand, float* stats, hhfm_stream_t stream);
+int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, int64_t C, const void* item_operand, int64_t N,
+                    int64_t K, int32_t tp, void* workspace, int64_t workspace_bytes, hhfm_stream_t stream);
+int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float* Fc, int64_t C, const float* items,
+                            const float* item_bias, const float* stats, int64_t N, int64_t K, int32_t tp,
+                            int32_t id_offset, void* workspace, int64_t workspace_bytes, float* out_scores,
+                            int32_t* out_ids, int32_t* overflow, hhfm_stream_t stream);
+
 /* K7  evaluate_TopK walk (FM.py:336-357) including its positive_feedback quirk.
  *   pred [C,tp] GLOBAL item ids; target [C]; target_in_pf [C] = (item in positive_feedback[key]) computed
  *   by the host.  rank_code[c] = n >= 0: hit at counter n;  -1: miss (appends 0);  -2: row appends nothing. */

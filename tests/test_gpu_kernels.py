@@ -416,12 +416,15 @@ def test_row_optimizers_move_only_touched_rows(cuda):
 # ----------------------------------------------------------------------------------------------------
 # K6 / K7 exact top-N and the metric walk
 # ----------------------------------------------------------------------------------------------------
-def _topn(cuda, kind, A, V, bias, n_user, n_item, tp, n_ctx, n_time, pools=(0, 0, 0), lo=0, hi=None):
+def _topn(cuda, kind, A, V, bias, n_user, n_item, tp, n_ctx, n_time, pools=(0, 0, 0), lo=0, hi=None, method="exact", info=None):
     from hhfm_b200.engine import TopN
     t = TopN(cuda)
     A_dev, stride = t.upload_rows(A, V.shape[0])
     tb = dev(bias, cuda) if bias is not None else None
-    ids, sc = t.topk(kind, A_dev, stride, n_ctx, n_time, pools, dev(V, cuda), tb, n_user, n_item, tp, lo, hi, return_scores=True)
+    ids, sc = t.topk(kind, A_dev, stride, n_ctx, n_time, pools, dev(V, cuda), tb, n_user, n_item, tp, lo, hi, return_scores=True,
+                     method=method)
+    if info is not None:
+        info["method"] = t.last_method; info["overflow_rows"] = t.last_overflow_rows
     return ids.cpu().numpy(), sc.cpu().numpy()
 
 
@@ -474,6 +477,49 @@ def test_hhfm_topk_bit_exact(cuda, pools):
     want = O.topk_lowest_index(ref, 20)
     assert (ids == want).all()
     assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
+
+
+@pytest.mark.parametrize("kind,C,N,K,tp,F", [(1, 300, 4082, 64, 20, 10), (0, 200, 5000, 128, 100, 2), (2, 130, 3001, 64, 20, 10),
+                                              (1, 257, 2500, 128, 20, 6), (0, 64, 1111, 32, 20, 2), (0, 50, 9000, 200, 100, 2),
+                                              (1, 17, 700, 16, 20, 4), (0, 1000, 20000, 64, 100, 2)])
+def test_tensor_core_topk_is_bit_identical_to_the_exact_path(cuda, kind, C, N, K, tp, F):
+    """tcgen05 GEMM filter + exact rescoring must return the oracle's lists and score bits."""
+    rng = np.random.default_rng(kind * 100 + C + K)
+    n_user = 40; M = n_user + N + 50
+    V = make_table(rng, M, K, scale=0.05); b = rng.normal(0, 0.02, (M, 1)).astype(np.float32)
+    V[n_user + 7] *= 8.0                                     # one large-norm item stresses the max-norm error bound
+    A = np.concatenate([rng.integers(0, n_user, (C, 1)), rng.integers(n_user, n_user + N, (C, 1)),
+                        rng.integers(n_user + N, M, (C, F - 2))], axis=1)
+    n_ctx = F - 2 if kind != 0 else 0
+    info = {}
+    ids, sc = _topn(cuda, kind, A, V, b if kind == 1 else None, n_user, N, tp, n_ctx, 0, method="tc", info=info)
+    assert info["method"] == "tc"
+    if kind == 1:
+        ref = O.fm_topk_scores(A, V, b, n_user, N)
+    elif kind == 2:
+        ref = O.hhfm_topk_scores(A, V, n_user, N, n_ctx, 0)
+    else:
+        ref = O.dot_topk_scores(V[A[:, 0]], V, n_user, N)
+    want = O.topk_lowest_index(ref, tp)
+    assert (ids == want).all(), "tensor-core path changed a top-%d list (%d rows differ)" % (tp, int((ids != want).any(axis=1).sum()))
+    assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
+
+
+def test_tensor_core_topk_survives_degenerate_ties_and_shards(cuda):
+    """Quantised weights: thousands of exactly tied scores overflow the candidate buffer of some rows -> those rows are
+    redone by the exact path; sharded calls carry the shard offset.  Lists must still equal the exact path."""
+    rng = np.random.default_rng(41)
+    n_user, N, K, C, tp = 16, 6000, 64, 96, 20
+    M = n_user + N
+    V = (rng.integers(-1, 2, (M, K)) * 0.25).astype(np.float32)
+    A = np.stack([rng.integers(0, n_user, C), rng.integers(n_user, M, C)], axis=1)
+    info = {}
+    ids, sc = _topn(cuda, 0, A, V, None, n_user, N, tp, 0, 0, method="tc", info=info)
+    ref = O.dot_topk_scores(V[A[:, 0]], V, n_user, N)
+    assert (ids == O.topk_lowest_index(ref, tp)).all()
+    lo, hi = 1500, 5200
+    ids2, _ = _topn(cuda, 0, A, V, None, n_user, N, tp, 0, 0, lo=lo, hi=hi, method="tc")
+    assert (ids2 == O.topk_lowest_index(ref[:, lo:hi], tp) + lo).all()
 
 
 def test_item_sharded_topk_merges_to_the_single_shard_answer(cuda):
