@@ -43,8 +43,8 @@ SIGNATURES = {
     "hhfm_metrics_walk": [vp, vp, vp, i64, i32, i32, vp, vp],
     "hhfm_topn_tc_supported": [i32, i64, i64, i32],
     "hhfm_topn_tc_prepare_items": [i32, vp, vp, i64, i64, vp, vp, vp],
-    "hhfm_topn_score": [i32, vp, vp, i64, vp, i64, i64, i32, vp, i64, vp],
-    "hhfm_topn_rescore_merge": [i32, vp, vp, i64, vp, vp, vp, i64, i64, i32, i32, vp, i64, vp, vp, vp, vp],
+    "hhfm_topn_score": [i32, vp, vp, i64, vp, i64, i64, i32, vp, vp, i64, vp],
+    "hhfm_topn_rescore_merge": [i32, vp, vp, i64, vp, vp, i64, i64, i32, i32, vp, i64, vp, vp, vp, vp],
 }
 INT64_FUNCS = {
     "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],

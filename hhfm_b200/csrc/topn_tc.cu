@@ -4,17 +4,19 @@
 //
 //   1. prep      Q [C,K] fp32 -> bf16 A [C,Kp], per-row ||q||, (FM) R_c = q.Fc and ||Fc||;  items -> bf16 B [N,Kp]
 //                (FM: the item bias rides in an extra k-chunk as hi+lo bf16 against two 1.0 columns of A), max ||v||.
-//   2. GEMM      tc_score_kernel: persistent, warp-specialised (TMA producer / single-thread tcgen05.mma issuer /
-//                4 epilogue warps).  CTA tile 128 contexts x BN items, all of Kp per stage.  The epilogue reads the
-//                fp32 accumulator with tcgen05.ld (thread t owns context row t) and keeps ONE number per 32 items:
-//                the group maximum -> gmax [C, ceil(N/32)].  No atomics, no data-dependent control flow.
+//   2. GEMM #1   tc_score_kernel<.., EMIT=false>: persistent, warp-specialised (TMA producer / single-thread tcgen05.mma
+//                issuer / 4 epilogue warps).  CTA tile 128 contexts x BN items, all of Kp per stage.  The epilogue reads
+//                the fp32 accumulator with tcgen05.ld (thread t owns context row t) and keeps only group maxima:
+//                one per 32 items (small catalogs) or one per BN-item tile -> gmax [C, n_groups].
 //   3. threshold tau_c = tp-th largest group maximum of row c (select_kernel).  The tp group maxima are tp distinct
 //                items with approximate score >= tau_c, so the exact tp-th best score s* >= tau_c - E_c.
-//   4. rescore   every group with gmax >= tau_c - 2 E_c is rescored exactly (canonical fp32 order) and items with
-//                s >= tau_c (+R_c) - E_c become candidates; the final select_kernel sorts them (score desc, id asc).
-// E_c bounds |approx - exact| for row c: bf16 rounding of both operands gives 2^-8 ||q|| ||v|| (Cauchy-Schwarz);
+//   4. GEMM #2   tc_score_kernel<.., EMIT=true>: the same GEMM again (it is the cheapest stage), the epilogue now
+//                compares against tau_c - 2 E_c and appends the ids of the few survivors (~2 tp per row).
+//   5. rescore   survivors are rescored exactly in the canonical fp32 order (512 B per candidate instead of whole
+//                groups), then select_kernel sorts them (score desc, id asc).
+// E_c bounds |approx - exact| for row c: bf16 rounding (rel. 2^-8 per operand) gives 2^-7 ||q|| ||v|| by Cauchy-Schwarz;
 // we use 2^-7 ||q_c|| max_n||v_n|| plus the bias split and fp32 rounding terms.  Every true top-tp item n has
-// approx_n >= s* - E >= tau - 2E, so its group is rescored: the candidate set contains the exact answer.
+// approx_n >= s* - E >= tau - 2E, so it is emitted: the candidate set contains the exact answer, ties included.
 // A row whose candidates overflow the buffer is flagged and redone by the exact path (host side).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -208,6 +210,11 @@ struct TcArgs {
   int64_t C, N;
   int64_t gmax_stride;    // floats per gmax row
   float* gmax;
+  int fine;               // 1: one maximum per 32 items, 0: one per BN-item tile
+  const float* thr_emit;  // EMIT: per-row threshold in approximate-score space
+  int32_t* seg_ids;       // EMIT: [C, splits, cap_u] survivor ids; segment (row, split) is private to ONE thread
+  int32_t* seg_cnt;       // EMIT: [C, splits] survivors found (may exceed cap_u -> overflow)
+  int cap_u;
   int* err;
 };
 
@@ -218,7 +225,7 @@ struct TcSmem {
   static constexpr int kBytes = kABytes + STAGES * kBStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int NKC, int BN, int STAGES>
+template <int NKC, int BN, int STAGES, bool EMIT>
 __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -314,37 +321,77 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
       const int rb = u / a.splits, sp = u % a.splits;
       const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
       const int64_t row = (int64_t)rb * kBM + row_in_tile;
+      const float thr = (EMIT && row < a.C) ? __ldg(a.thr_emit + row) : INFINITY;
+      int32_t* seg = EMIT ? a.seg_ids + ((int64_t)row * a.splits + sp) * a.cap_u : nullptr;
+      int n_emit = 0;
       for (int t = t0; t < t1; t++) {
         mbar_wait(t_full + acc, tph, a.err);
         tc_fence_after();
         float gm[kChunks];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
         const int64_t n_base = (int64_t)t * BN;
+        if (!EMIT) {
 #pragma unroll
-        for (int c = 0; c < kChunks; c++) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * kGroup, r);
-          tmem_ld_wait();
-          float m = -INFINITY;
-          if (n_base + (c + 1) * kGroup <= a.N) {
+          for (int c = 0; c < kChunks; c++) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * kGroup, r);
+            tmem_ld_wait();
+            float m = -INFINITY;
+            if (n_base + (c + 1) * kGroup <= a.N) {
+#pragma unroll
+              for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(r[i]));
+            } else {                            // last tile: items beyond N are TMA zero fill, not scores
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (n_base + c * kGroup + i < a.N) m = fmaxf(m, __uint_as_float(r[i]));
+            }
+            gm[c] = m;
+          }
+        } else {
+          // Survivor emission.  The chunk loop is NOT unrolled and the per-element work is a branch-free bit mask plus
+          // a short rare loop: the whole epilogue stays inside the instruction cache (an unrolled 8 x 32 emission
+          // body is ~100 KB of SASS and made this pass 10x slower than the max pass).
+#pragma unroll 1
+          for (int c = 0; c < kChunks; c++) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * kGroup, r);
+            tmem_ld_wait();
+            float m = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(r[i]));
-          } else {                              // last tile: items beyond N are TMA zero fill, not scores
+            if (m >= thr) {                     // rare: ~2 tp survivors per row over the whole catalog
+              unsigned mask = 0u;
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-              if (n_base + c * kGroup + i < a.N) m = fmaxf(m, __uint_as_float(r[i]));
+              for (int i = 0; i < 32; i++) mask |= (__uint_as_float(r[i]) >= thr ? 1u : 0u) << i;
+              const int nb = (int)n_base + c * kGroup;
+              while (mask) {                    // no atomics: the segment belongs to this thread
+                const int i = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                if (nb + i < a.N) {
+                  if (n_emit < a.cap_u) seg[n_emit] = nb + i;
+                  n_emit++;
+                }
+              }
+            }
           }
-          gm[c] = m;
         }
         tc_fence_before();
         mbar_arrive(t_empty + acc);
-        if (row < a.C) {
-          float4* dst = reinterpret_cast<float4*>(a.gmax + row * a.gmax_stride + (int64_t)t * kChunks);
+        if (!EMIT && row < a.C) {
+          if (a.fine) {
+            float4* dst = reinterpret_cast<float4*>(a.gmax + row * a.gmax_stride + (int64_t)t * kChunks);
 #pragma unroll
-          for (int c = 0; c < kChunks; c += 4) dst[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+            for (int c = 0; c < kChunks; c += 4) dst[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+          } else {
+            float m = gm[0];
+#pragma unroll
+            for (int c = 1; c < kChunks; c++) m = fmaxf(m, gm[c]);
+            a.gmax[row * a.gmax_stride + t] = m;
+          }
         }
         if (++acc == 2) { acc = 0; tph ^= 1; }
       }
+      if (EMIT && row < a.C) a.seg_cnt[row * a.splits + sp] = n_emit;
     }
   }
   tc_fence_before();
@@ -353,17 +400,30 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exact rescoring of the surviving groups.  One CTA per context row; warps scan 32 group maxima at a time, a warp
-// rescores one surviving group (lane = item) in the canonical fp32 order and appends items with s >= tau + R - E.
+// thresholds: thr_emit[c] = tau_c - 2 E_c (approximate-score space)
+// ---------------------------------------------------------------------------------------------------
+__global__ void tc_threshold_kernel(int64_t C, int fm, int K, const float* __restrict__ tau, int tau_stride,
+                                    const float4* __restrict__ qinfo, const float* __restrict__ stats,
+                                    float* __restrict__ thr_emit) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float E = row_error_bound(qinfo[c], stats[0], stats[1], fm, K);
+  thr_emit[c] = tau[c * tau_stride] - 2.f * E;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact rescoring of the survivors.  One CTA per context row; a warp takes 32 candidates at a time, stages their item
+// rows 32 k at a time with coalesced 128-byte reads, and lane r walks row r in ascending k (canonical order).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_rescore_kernel(int kind, const float* __restrict__ Q, const float* __restrict__ Fc,
                                                          const float* __restrict__ items, const float* __restrict__ item_bias,
-                                                         int64_t N, int K, const float* __restrict__ gmax, int64_t gmax_stride,
-                                                         int n_groups, const float* __restrict__ tau, int tau_stride,
-                                                         const float4* __restrict__ qinfo, const float* __restrict__ stats,
-                                                         int cap, float* __restrict__ cand_scores, int32_t* __restrict__ cand_ids,
-                                                         int32_t* __restrict__ cand_cnt, int32_t* __restrict__ overflow) {
-  __shared__ int s_cnt;
+                                                         int64_t N, int K, int splits, int cap_u, const int32_t* __restrict__ seg_ids,
+                                                         const int32_t* __restrict__ seg_cnt, int cap, float* __restrict__ cand_scores,
+                                                         int32_t* __restrict__ cand_ids, int32_t* __restrict__ cand_cnt,
+                                                         int32_t* __restrict__ overflow) {
+  __shared__ float s_tile[8][32][33];
+  __shared__ int s_off[512];                // prefix of per-split survivor counts (splits <= 2*SMs+1 <= 511)
+  __shared__ int s_over;
   extern __shared__ float s_q[];            // q[K] (+ Fc[K] for FM)
   const int64_t c = blockIdx.x;
   const int fm = kind == HHFM_QUERY_FM;
@@ -371,55 +431,59 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(int kind, const float* 
     s_q[k] = Q[c * K + k];
     if (fm) s_q[K + k] = Fc[c * K + k];
   }
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  const float4 qi = qinfo[c];
-  const float E = row_error_bound(qi, stats[0], stats[1], fm, K);
-  const float t = tau[c * tau_stride];
-  const float thr_group = t - 2.f * E;
-  const float thr_exact = t + (fm ? qi.y : 0.f) - E;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* grow = gmax + c * gmax_stride;
-  for (int g0 = warp * 32; g0 < n_groups; g0 += nw * 32) {
-    const int g = g0 + lane;
-    const bool hit = (g < n_groups) && (grow[g] >= thr_group);
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    while (mask) {
-      const int b = __ffs((int)mask) - 1;
-      mask &= mask - 1;
-      const int64_t n = (int64_t)(g0 + b) * kGroup + lane;
-      float s = -INFINITY;
-      if (n < N) {
-        const float* v = items + n * K;
-        float acc = 0.f;
-        for (int k = 0; k < K; k++) {
-          const float x = fm ? __fadd_rn(__ldg(v + k), s_q[K + k]) : __ldg(v + k);
-          const float p = __fmul_rn(s_q[k], x);
-          acc = (k == 0) ? p : __fadd_rn(acc, p);
-        }
-        s = (fm && item_bias) ? __fadd_rn(__ldg(item_bias + n), acc) : acc;
-      }
-      const bool keep = (n < N) && (s >= thr_exact);
-      const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (km) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_cnt, __popc(km));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) {
-          const int slot = base + __popc(km & ((1u << lane) - 1));
-          if (slot < cap) {
-            cand_scores[c * cap + slot] = s;
-            cand_ids[c * cap + slot] = (int32_t)n;
-          }
-        }
-      }
+  if (threadIdx.x == 0) {
+    int tot = 0, over = 0;
+    for (int sp = 0; sp < splits; sp++) {
+      int n = seg_cnt[c * splits + sp];
+      if (n > cap_u) { over = 1; n = cap_u; }
+      s_off[sp] = tot;
+      tot += n;
     }
+    s_off[splits] = tot;
+    s_over = over | (tot > cap ? 1 : 0);
   }
   __syncthreads();
+  const int total = s_off[splits];
+  const int cnt = total < cap ? total : cap;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float (*tile)[33] = s_tile[warp];
+  for (int i0 = warp * 32; i0 < cnt; i0 += nw * 32) {
+    const int i = i0 + lane;
+    int my_id = -1;
+    if (i < cnt) {
+      int lo = 0, hi = splits;              // largest sp with s_off[sp] <= i
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= i) lo = mid; else hi = mid;
+      }
+      my_id = seg_ids[(c * splits + lo) * cap_u + (i - s_off[lo])];
+    }
+    float acc = 0.f;
+    for (int kc = 0; kc < K; kc += 32) {
+      const int kk = kc + lane;
+#pragma unroll 8
+      for (int r = 0; r < 32; r++) {
+        const int id = __shfl_sync(0xffffffffu, my_id, r);
+        tile[r][lane] = (id >= 0 && kk < K) ? __ldg(items + (int64_t)id * K + kk) : 0.f;
+      }
+      __syncwarp();
+      const int kn = min(32, K - kc);
+      for (int j = 0; j < kn; j++) {
+        const float v = tile[lane][j];
+        const float x = fm ? __fadd_rn(v, s_q[K + kc + j]) : v;
+        const float p = __fmul_rn(s_q[kc + j], x);
+        acc = (kc + j == 0) ? p : __fadd_rn(acc, p);
+      }
+      __syncwarp();
+    }
+    if (i < cnt) {
+      cand_scores[c * cap + i] = (fm && item_bias) ? __fadd_rn(__ldg(item_bias + my_id), acc) : acc;
+      cand_ids[c * cap + i] = my_id;
+    }
+  }
   if (threadIdx.x == 0) {
-    const int n = s_cnt;
-    cand_cnt[c] = n < cap ? n : cap;
-    overflow[c] = n > cap ? 1 : 0;
+    overflow[c] = s_over;
+    cand_cnt[c] = cnt;
   }
 }
 
@@ -485,46 +549,91 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int Kp, i
   return HHFM_OK;
 }
 
-template <int NKC, int BN, int STAGES>
+template <int NKC, int BN, int STAGES, bool EMIT>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const TcArgs& a, cudaStream_t st) {
   constexpr int smem = TcSmem<NKC, BN, STAGES>::kBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_score_kernel<NKC, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_score_kernel<NKC, BN, STAGES, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("tc_score_kernel: cannot reserve %d bytes of shared memory", smem);
       return HHFM_ERR_LAUNCH;
     }
     attr_set = true;
   }
   const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
-  tc_score_kernel<NKC, BN, STAGES><<<grid, 192, smem, st>>>(tA, tB, a);
+  tc_score_kernel<NKC, BN, STAGES, EMIT><<<grid, 192, smem, st>>>(tA, tB, a);
   return check_launch("tc_score_kernel");
 }
 
 struct TcLayout {   // carve-up of the caller's workspace
-  size_t off_A, off_qinfo, off_gmax, off_tau, off_cs, off_ci, off_cc, off_err, total;
+  size_t off_A, off_qinfo, off_gmax, off_tau, off_thr, off_seg, off_segcnt, off_cs, off_ci, off_cc, off_err, total;
   int64_t gmax_stride;
-  int n_groups, cap;
+  int n_groups, cap, cap_u, fine;
+  int n_row_blocks, n_tiles, tiles_per_unit, splits, n_units;
 };
 
 static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
   TcLayout L{};
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const int64_t n_pad = (N + bn - 1) / bn * bn;
-  L.n_groups = (int)((N + kGroup - 1) / kGroup);
-  L.gmax_stride = n_pad / kGroup;
-  L.cap = 2 * tp + 96;
+  const int64_t n_tiles = (N + bn - 1) / bn;
+  L.fine = n_tiles < 4 * (int64_t)tp;                 // small catalogs: one maximum per 32 items for a tight tau
+  if (L.fine) {
+    L.n_groups = (int)((N + kGroup - 1) / kGroup);
+    L.gmax_stride = n_tiles * (bn / kGroup);
+  } else {
+    L.n_groups = (int)n_tiles;
+    L.gmax_stride = (n_tiles + 3) / 4 * 4;
+  }
+  // work decomposition: unit = (row block of 128 contexts, contiguous range of item tiles); >= 2 units per SM if possible
+  L.n_row_blocks = (int)((C + kBM - 1) / kBM);
+  L.n_tiles = (int)n_tiles;
+  int splits = (2 * sm_count() + L.n_row_blocks - 1) / L.n_row_blocks;
+  if (splits > L.n_tiles) splits = L.n_tiles;
+  if (splits < 1) splits = 1;
+  L.tiles_per_unit = (L.n_tiles + splits - 1) / splits;
+  L.splits = (L.n_tiles + L.tiles_per_unit - 1) / L.tiles_per_unit;
+  L.n_units = L.n_row_blocks * L.splits;
+  L.cap = 4 * tp + 256;                               // survivors per row (expected ~2 tp)
+  L.cap_u = (4 * L.cap) / L.splits + 32;              // per (row, split) segment: 4x the even share + slack
+  if (L.cap_u > L.cap) L.cap_u = L.cap;
   size_t o = 0;
   L.off_A = o; o = align(o + (size_t)C * Kp * 2);
   L.off_qinfo = o; o = align(o + (size_t)C * 16);
   L.off_gmax = o; o = align(o + (size_t)C * L.gmax_stride * 4);
   L.off_tau = o; o = align(o + (size_t)C * tp * 4 * 2);      // select writes [C,tp] scores + ids
+  L.off_thr = o; o = align(o + (size_t)C * 4);
+  L.off_seg = o; o = align(o + (size_t)C * L.splits * L.cap_u * 4);
+  L.off_segcnt = o; o = align(o + (size_t)C * L.splits * 4);
   L.off_cs = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_ci = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_cc = o; o = align(o + (size_t)C * 4);
   L.off_err = o; o = align(o + 256);
   L.total = o;
   return L;
+}
+
+template <bool EMIT>
+static int run_gemm(const TcPlan& p, const CUtensorMap& tA, const CUtensorMap& tB, const TcArgs& a, cudaStream_t st) {
+  if (p.nkc == 1) return launch_tc<1, 256, 4, EMIT>(tA, tB, a, st);
+  if (p.nkc == 2) return launch_tc<2, 256, 2, EMIT>(tA, tB, a, st);
+  if (p.nkc == 3) return launch_tc<3, 128, 3, EMIT>(tA, tB, a, st);
+  return launch_tc<4, 128, 2, EMIT>(tA, tB, a, st);
+}
+
+static TcArgs make_tc_args(const TcPlan& p, const TcLayout& L, int64_t C, int64_t N, uint8_t* ws) {
+  TcArgs a{};
+  a.C = C; a.N = N;
+  a.n_row_blocks = L.n_row_blocks; a.n_tiles = L.n_tiles; a.tiles_per_unit = L.tiles_per_unit;
+  a.splits = L.splits; a.n_units = L.n_units;
+  a.gmax = reinterpret_cast<float*>(ws + L.off_gmax);
+  a.gmax_stride = L.gmax_stride;
+  a.fine = L.fine;
+  a.thr_emit = reinterpret_cast<const float*>(ws + L.off_thr);
+  a.seg_ids = reinterpret_cast<int32_t*>(ws + L.off_seg);
+  a.seg_cnt = reinterpret_cast<int32_t*>(ws + L.off_segcnt);
+  a.cap_u = L.cap_u;
+  a.err = reinterpret_cast<int*>(ws + L.off_err);
+  return a;
 }
 
 }  // namespace hhfm
@@ -538,7 +647,7 @@ extern "C" int hhfm_topn_select(const float* scores, const int32_t* ids, const i
 extern "C" int hhfm_topn_tc_supported(int32_t kind, int64_t N, int64_t K, int32_t tp) {
   if (kind < 0 || kind > 2 || K <= 0 || tp < 1 || tp > 1024) return 0;
   if (!tc_plan(kind, K).ok) return 0;
-  return ((N + kGroup - 1) / kGroup) >= tp ? 1 : 0;     // need at least tp group maxima for the threshold
+  return ((N + kGroup - 1) / kGroup) >= tp ? 1 : 0;     // need at least tp group maxima for the threshold (fine mode)
 }
 
 extern "C" int64_t hhfm_topn_tc_item_operand_bytes(int32_t kind, int64_t N, int64_t K) {
@@ -567,9 +676,9 @@ extern "C" int hhfm_topn_tc_prepare_items(int32_t kind, const float* items, cons
 
 // Stage 1-3: filter.  Leaves gmax / tau / qinfo in the workspace for hhfm_topn_rescore_merge.
 extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, int64_t C, const void* item_operand,
-                               int64_t N, int64_t K, int32_t tp, void* workspace, int64_t workspace_bytes,
-                               hhfm_stream_t stream) {
-  HHFM_REQUIRE(Q && item_operand && workspace, "topn_score: NULL argument");
+                               int64_t N, int64_t K, int32_t tp, const float* stats, void* workspace,
+                               int64_t workspace_bytes, hhfm_stream_t stream) {
+  HHFM_REQUIRE(Q && item_operand && workspace && stats, "topn_score: NULL argument");
   HHFM_REQUIRE(kind != HHFM_QUERY_FM || Fc, "topn_score: FM needs Fc");
   HHFM_REQUIRE(hhfm_topn_tc_supported(kind, N, K, tp), "topn_score: configuration not supported by the tensor-core path");
   HHFM_REQUIRE(C > 0, "topn_score: C must be > 0");
@@ -582,60 +691,48 @@ extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, in
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws + L.off_A);
   float4* qinfo = reinterpret_cast<float4*>(ws + L.off_qinfo);
-  float* gmax = reinterpret_cast<float*>(ws + L.off_gmax);
   float* tau_sc = reinterpret_cast<float*>(ws + L.off_tau);
   int32_t* tau_id = reinterpret_cast<int32_t*>(ws + L.off_tau + (size_t)C * tp * 4);
-  int* err = reinterpret_cast<int*>(ws + L.off_err);
-  cudaMemsetAsync(err, 0, sizeof(int), st);
-  tc_prep_queries_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(Q, Fc, C, (int)K, p.Kp, kind == HHFM_QUERY_FM, A, qinfo);
+  const int fm = kind == HHFM_QUERY_FM;
+  cudaMemsetAsync(ws + L.off_err, 0, sizeof(int), st);
+  tc_prep_queries_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(Q, Fc, C, (int)K, p.Kp, fm, A, qinfo);
   int rc = check_launch("tc_prep_queries_kernel");
   if (rc) return rc;
-
   CUtensorMap tA, tB;
   if ((rc = make_tmap(&tA, A, C, p.Kp, kBM))) return rc;
   if ((rc = make_tmap(&tB, item_operand, N, p.Kp, p.bn))) return rc;
-  TcArgs a{};
-  a.C = C; a.N = N;
-  a.n_row_blocks = (int)((C + kBM - 1) / kBM);
-  a.n_tiles = (int)((N + p.bn - 1) / p.bn);
-  int splits = (2 * sm_count() + a.n_row_blocks - 1) / a.n_row_blocks;     // aim at >= 2 units per SM
-  if (splits > a.n_tiles) splits = a.n_tiles;
-  if (splits < 1) splits = 1;
-  a.tiles_per_unit = (a.n_tiles + splits - 1) / splits;
-  a.splits = (a.n_tiles + a.tiles_per_unit - 1) / a.tiles_per_unit;
-  a.n_units = a.n_row_blocks * a.splits;
-  a.gmax = gmax; a.gmax_stride = L.gmax_stride; a.err = err;
-  if (p.nkc == 1) rc = launch_tc<1, 256, 4>(tA, tB, a, st);
-  else if (p.nkc == 2) rc = launch_tc<2, 256, 2>(tA, tB, a, st);
-  else if (p.nkc == 3) rc = launch_tc<3, 128, 3>(tA, tB, a, st);
-  else rc = launch_tc<4, 128, 2>(tA, tB, a, st);
-  if (rc) return rc;
-  // tau_c = tp-th largest group maximum
-  return hhfm_topn_select(gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, tp, 0, tau_sc, tau_id, stream);
+  TcArgs a = make_tc_args(p, L, C, N, ws);
+  // GEMM #1: group maxima;  tau_c = tp-th largest;  thresholds;  GEMM #2: emit survivors
+  if ((rc = run_gemm<false>(p, tA, tB, a, st))) return rc;
+  if ((rc = hhfm_topn_select(a.gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, tp, 0, tau_sc, tau_id, stream))) return rc;
+  tc_threshold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, fm, (int)K, tau_sc + (tp - 1), tp, qinfo, stats,
+                                                                  reinterpret_cast<float*>(ws + L.off_thr));
+  if ((rc = check_launch("tc_threshold_kernel"))) return rc;
+  return run_gemm<true>(p, tA, tB, a, st);
 }
 
-// Stage 4: exact rescoring of surviving groups + final (score desc, id asc) selection.
+// Stage 5: exact rescoring of the survivors + final (score desc, id asc) selection.
 extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float* Fc, int64_t C, const float* items,
-                                       const float* item_bias, const float* stats, int64_t N, int64_t K, int32_t tp,
-                                       int32_t id_offset, void* workspace, int64_t workspace_bytes, float* out_scores,
-                                       int32_t* out_ids, int32_t* overflow, hhfm_stream_t stream) {
-  HHFM_REQUIRE(Q && items && stats && workspace && out_ids && overflow, "topn_rescore_merge: NULL argument");
+                                       const float* item_bias, int64_t N, int64_t K, int32_t tp, int32_t id_offset,
+                                       void* workspace, int64_t workspace_bytes, float* out_scores, int32_t* out_ids,
+                                       int32_t* overflow, hhfm_stream_t stream) {
+  HHFM_REQUIRE(Q && items && workspace && out_ids && overflow, "topn_rescore_merge: NULL argument");
   TcPlan p = tc_plan(kind, K);
   HHFM_REQUIRE(p.ok, "topn_rescore_merge: unsupported K");
   TcLayout L = tc_layout(C, N, p.Kp, tp, p.bn);
   HHFM_REQUIRE(workspace_bytes >= (int64_t)L.total, "topn_rescore_merge: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  const float4* qinfo = reinterpret_cast<const float4*>(ws + L.off_qinfo);
-  const float* gmax = reinterpret_cast<const float*>(ws + L.off_gmax);
-  const float* tau_sc = reinterpret_cast<const float*>(ws + L.off_tau);
   float* cs = reinterpret_cast<float*>(ws + L.off_cs);
   int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
   int32_t* cc = reinterpret_cast<int32_t*>(ws + L.off_cc);
   const int fm = kind == HHFM_QUERY_FM;
   const size_t smem = (size_t)K * (fm ? 2 : 1) * sizeof(float);
-  tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, gmax, L.gmax_stride,
-                                                    L.n_groups, tau_sc + (tp - 1), tp, qinfo, stats, L.cap, cs, ci, cc, overflow);
+  HHFM_REQUIRE(L.splits <= 511, "topn_rescore_merge: too many item splits");
+  tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, L.splits, L.cap_u,
+                                                    reinterpret_cast<const int32_t*>(ws + L.off_seg),
+                                                    reinterpret_cast<const int32_t*>(ws + L.off_segcnt), L.cap, cs, ci, cc,
+                                                    overflow);
   int rc = check_launch("tc_rescore_kernel");
   if (rc) return rc;
   return hhfm_topn_select(cs, ci, cc, C, L.cap, L.cap, tp, id_offset, out_scores, out_ids, stream);

@@ -358,15 +358,16 @@ class TopN:
         out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
         out_sc = torch.empty(C_rows, tp, dtype=torch.float32, device=self.device)
         overflow = torch.zeros(C_rows, dtype=torch.int32, device=self.device)
-        per_row = max(1, int(lib.hhfm_workspace_bytes_topn(kind, 1024, N, K, tp)) // 1024)
-        chunk = max(128, min(C_rows, (self.max_ws // per_row) // 128 * 128))
+        chunk = C_rows                 # largest context chunk whose workspace fits the budget
+        while chunk > 128 and int(lib.hhfm_workspace_bytes_topn(kind, chunk, N, K, tp)) > self.max_ws:
+            chunk = max(128, (chunk // 2 + 127) // 128 * 128)
         for c0 in range(0, C_rows, chunk):
             c1 = min(C_rows, c0 + chunk)
             nbytes = int(lib.hhfm_workspace_bytes_topn(kind, c1 - c0, N, K, tp))
             ws = self._byte_workspace(nbytes)
             fcp = ptr(Fc[c0:c1]) if Fc is not None else None
-            _lib.call("hhfm_topn_score", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(op), N, K, tp, ptr(ws), nbytes, st)
-            _lib.call("hhfm_topn_rescore_merge", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(items), ptr(ibias), ptr(stats), N, K,
+            _lib.call("hhfm_topn_score", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(op), N, K, tp, ptr(stats), ptr(ws), nbytes, st)
+            _lib.call("hhfm_topn_rescore_merge", kind, ptr(Q[c0:c1]), fcp, c1 - c0, ptr(items), ptr(ibias), N, K,
                       tp, item_lo, ptr(ws), nbytes, ptr(out_sc[c0:c1]), ptr(out_ids[c0:c1]), ptr(overflow[c0:c1]), st)
         bad = torch.nonzero(overflow).reshape(-1)
         self.last_overflow_rows = int(bad.numel())

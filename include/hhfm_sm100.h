@@ -207,10 +207,11 @@ int hhfm_topn_select(const float* scores, const int32_t* ids, const int32_t* cou
  * on tcgen05 (TMA-staged operands, fp32 accumulators in TMEM) used as a FILTER, then exact fp32 rescoring:
  *   hhfm_topn_tc_prepare_items  items fp32 [N,K] (+bias) -> bf16 operand [N,Kp] and stats = {max ||v||, max |b|}
  *                               (cache it while the weights do not change; size from hhfm_topn_tc_item_operand_bytes)
- *   hhfm_topn_score             queries -> bf16, GEMM with a fused group-max epilogue (one fp32 per 32 items),
- *                               tau_c = tp-th largest group maximum; results stay in `workspace`
- *   hhfm_topn_rescore_merge     groups with max >= tau_c - 2E_c are rescored exactly (canonical order), candidates
- *                               selected under (score desc, id asc); id_offset = item-shard offset (multi-GPU merge).
+ *   hhfm_topn_score             queries -> bf16; GEMM #1 with a fused group-max epilogue; tau_c = tp-th largest group
+ *                               maximum; GEMM #2 whose epilogue emits the ids with approx score >= tau_c - 2E_c;
+ *                               survivors stay in `workspace`
+ *   hhfm_topn_rescore_merge     survivors are rescored exactly (canonical order) and selected under
+ *                               (score desc, id asc); id_offset = item-shard offset (multi-GPU merge).
  *                               overflow[c] = 1 marks a row whose candidate buffer overflowed (tie-degenerate data):
  *                               the caller must redo that row with the exact path.
  * hhfm_topn_tc_supported says whether (kind, N, K, tp) is covered (K + bias chunk <= 256, ceil(N/32) >= tp).
@@ -221,11 +222,12 @@ int64_t hhfm_workspace_bytes_topn(int32_t kind, int64_t C, int64_t N, int64_t K,
 int hhfm_topn_tc_prepare_items(int32_t kind, const float* items, const float* item_bias, int64_t N, int64_t K,
                                void* item_operand, float* stats, hhfm_stream_t stream);
 int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, int64_t C, const void* item_operand, int64_t N,
-                    int64_t K, int32_t tp, void* workspace, int64_t workspace_bytes, hhfm_stream_t stream);
+                    int64_t K, int32_t tp, const float* stats, void* workspace, int64_t workspace_bytes,
+                    hhfm_stream_t stream);
 int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float* Fc, int64_t C, const float* items,
-                            const float* item_bias, const float* stats, int64_t N, int64_t K, int32_t tp,
-                            int32_t id_offset, void* workspace, int64_t workspace_bytes, float* out_scores,
-                            int32_t* out_ids, int32_t* overflow, hhfm_stream_t stream);
+                            const float* item_bias, int64_t N, int64_t K, int32_t tp, int32_t id_offset,
+                            void* workspace, int64_t workspace_bytes, float* out_scores, int32_t* out_ids,
+                            int32_t* overflow, hhfm_stream_t stream);
 
 /* K7  evaluate_TopK walk (FM.py:336-357) including its positive_feedback quirk.
  *   pred [C,tp] GLOBAL item ids; target [C]; target_in_pf [C] = (item in positive_feedback[key]) computed
