@@ -58,18 +58,49 @@ def make_batch(rng, B):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread every ~2 ms (the nvidia-smi CLI needs longer to start than a short timed region lasts); the CLI loop of the
+    recipe is the fallback when pynvml is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.gpu = gpu_index
+        self.uuid = uuid
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.sm, self.reason_bits, self.power = [], 0, []
+        self.max_sm = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.max_sm = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -79,11 +110,37 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def sample(self):
+        """One synchronous NVML sample (called by the timing loop itself while the GPU is busy)."""
+        if self.nvml is None:
+            return
+        try:
+            self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+            try:
+                self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.power.append(self.nvml.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+            reasons = sorted(k for k, b in self.BITS.items() if self.reason_bits & b)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                    "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -105,7 +162,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -308,15 +365,21 @@ def run_ours(args):
     for i in range(args.warmup):
         device_step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.start()
     t_start.record()
     for i in range(args.steps):
         device_step(args.warmup + i, timed_idx=i)
     t_end.record()
+    if rank == 0:
+        sampler.sample()                 # the queue is still draining here: at least one sample under load
     barrier()
     total_ms = t_start.elapsed_time(t_end)
     kern_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
@@ -380,7 +443,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="positives per GPU per step")

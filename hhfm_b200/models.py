@@ -7,6 +7,7 @@ reference (`_init_graph`) is replaced by device tensors and C-ABI kernel launche
 
   FM    Newcode/FM.py:59-198          MF   Newcode/MF.py:43-149
   OUR   Newcode/OurModel7.py:50-307   BPR  Newcode/BPR.py:45-136
+  AFM   Newcode/AFM.py:63-246
 """
 from __future__ import annotations
 
@@ -510,3 +511,133 @@ class BPR(_PairRank):
         if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
             return self.partial_fit({"X": feed[self.Pos], "Y": feed[self.Neg]}), None
         raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))
+
+
+# ====================================================================================================
+class AFM(FM):
+    """Attentional FM, Newcode/AFM.py:63-246.  hidden_factor = [attention size A, embedding size K] (AFM.py:39)."""
+
+    def __init__(self, n_user, n_item, features_M, attention, hidden_factor, activation_function, learning_rate,
+                 lamda_attention, keep, optimizer_type, decay, valid_dimension, random_seed=2016):
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.attention = attention
+        self.hidden_factor = hidden_factor
+        self.activation_function = activation_function      # unused by the reference graph too (relu is hard-coded, AFM.py:123)
+        self.features_M = features_M
+        self.valid_dimension = valid_dimension
+        self.lamda_attention = lamda_attention
+        self.keep = keep
+        self.random_seed = random_seed
+        self.optimizer_type = optimizer_type
+        self.decay = decay
+        self.u_f = valid_dimension - 1
+        self._init_graph()
+
+    def _init_graph(self):
+        if not self.attention:
+            raise NotImplementedError("attention=0 (AFM.py:132) is not on the accelerated path; the reference default is 1")
+        if any(float(k) != 1.0 for k in self.keep):
+            raise NotImplementedError("dropout keep<1 (AFM.py:126,134) is not on the accelerated path; default is [1,1]")
+        self.train_features = Handle("train_features_afm")
+        self.train_labels = Handle("train_labels_afm")
+        self.dropout_keep = Handle("dropout_keep_afm")
+        self.train_phase = Handle("train_phase_afm")
+        self.out = Handle("out_afm")
+        self.loss = Handle("loss")
+        self.optimizer = Handle("optimizer")
+        A, K = int(self.hidden_factor[0]), int(self.hidden_factor[1])
+        self._A = A
+        self._setup(self.features_M, K, self.random_seed, True, self.optimizer_type, self.learning_rate, 0.1, 0.0)
+        if K > 128 or A > 128 or (K + 31) // 32 != (A + 31) // 32:
+            raise _lib.HhfmError("AFM kernels need K, A <= 128 in the same 32-tier (reference: A == K)")
+        dev = self.device
+        self._b0 = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.weights["bias"] = self._b0.view(())                                            # AFM.py:186
+        rs = np.random.RandomState(self.random_seed)
+        glorot = np.sqrt(2.0 / (A + K))                                                     # AFM.py:190
+        self.weights["attention_W"] = torch.tensor(rs.normal(0, glorot, (K, A)), dtype=torch.float32, device=dev)
+        self.weights["attention_b"] = torch.tensor(rs.normal(0, glorot, (1, A)), dtype=torch.float32, device=dev)
+        self.weights["attention_p"] = torch.tensor(rs.normal(0, 1, (A,)), dtype=torch.float32, device=dev)
+        self.weights["prediction"] = torch.ones(K, 1, dtype=torch.float32, device=dev)      # AFM.py:199
+        self._gW = torch.zeros(K, A, dtype=torch.float32, device=dev)
+        self._gbatt = torch.zeros(A, dtype=torch.float32, device=dev)
+        self._gp = torch.zeros(A, dtype=torch.float32, device=dev)
+        self._gwp = torch.zeros(K, dtype=torch.float32, device=dev)
+
+    def _small(self):
+        w = self.weights
+        return ptr(w["attention_W"]), ptr(w["attention_b"]), ptr(w["attention_p"]), ptr(w["prediction"])
+
+    def predict(self, X):
+        X = np.asarray(X)
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        return self._predict_dev(idx).cpu().numpy().reshape(-1, 1)
+
+    def _predict_dev(self, idx):
+        B, F = idx.shape
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        W, batt, pv, wp = self._small()
+        _lib.call("hhfm_afm_fwd", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
+                  ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(out), cur_stream())
+        return out
+
+    def partial_fit(self, data):
+        """AFM.py:205-208.  V and feature_bias receive IndexedSlices (only touched rows move); attention_W carries the
+        lamda_attention L2 term (AFM.py:146); attention_b/p, prediction and bias are small dense variables."""
+        X = np.asarray(data["X"])
+        F = X.shape[1]
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        y = self._upload_f32(data["Y"])
+        B = idx.shape[0]
+        self._opt.begin_step()
+        ts, stamp, tr, tc = self._touch_args(extra=True)
+        hot = self._hot_plan(idx, True)
+        W, batt, pv, wp = self._small()
+        _lib.call("hhfm_afm_fwd_bwd_sqloss", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]),
+                  ptr(self.weights["feature_bias"]), ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(y), None,
+                  ptr(self._gV), ptr(self._gb), ptr(self._gb0), ptr(self._gW), ptr(self._gbatt), ptr(self._gp), ptr(self._gwp),
+                  ptr(self._loss_partials), ts, stamp, tr, tc, *(hot.args(True) if hot else NO_HOT_BIAS), cur_stream())
+        if hot:
+            hot.fold(self._gV, self._gb)
+        if self._dp_group is not None:
+            import torch.distributed as dist
+            self._allreduce_grads()
+            for g in (self._gW, self._gbatt, self._gp, self._gwp):
+                dist.all_reduce(g, group=self._dp_group)
+        self._apply_table(sparse_ok=True)                       # lamda on V is 0: rows (or the dense equivalent under DP)
+        self._apply_bias()
+        lam = float(self.lamda_attention)
+        o = self._opt
+        o.apply_dense("attention_W", self.weights["attention_W"], self._gW, lam, self._sq_partials if lam > 0 else None)
+        o.apply_dense("attention_b", self.weights["attention_b"], self._gbatt, 0.0, None)
+        o.apply_dense("attention_p", self.weights["attention_p"], self._gp, 0.0, None)
+        o.apply_dense("prediction", self.weights["prediction"], self._gwp, 0.0, None)
+        self._version += 1
+        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if lam > 0 else None, 0.5 * lam,
+                  ptr(self._loss_dev), cur_stream())
+        self._loss_host.copy_(self._loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def topk(self, A, tp):
+        """AFM.topk (AFM.py:209-246) scores every item for each context row.  The reference restates `out` with an
+        un-normalised exp attention and drops the per-row constants, which is rank-equivalent to scoring the full model:
+        here every (row, item) pair goes through the forward kernel and the exact selector (lowest-index ties)."""
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        C_rows, F = A.shape
+        N = self.n_item
+        out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
+        chunk = max(1, (1 << 22) // max(N, 1))
+        for c0 in range(0, C_rows, chunk):
+            c1 = min(C_rows, c0 + chunk)
+            rows = A_dev[c0:c1, :F].unsqueeze(1).repeat(1, N, 1)              # [c, N, F]
+            rows[:, :, 1] = items.unsqueeze(0)
+            sc = self._predict_dev(rows.reshape(-1, F).contiguous()).view(c1 - c0, N)
+            _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
+        return out_ids.cpu().numpy()

@@ -115,6 +115,26 @@ int hhfm_fm_bwd(const int32_t* row_ptr, const int32_t* col, const float* val, in
                 float* gV, float* gbias, float* gb0, int32_t deterministic, hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2  Attentional FM (AFM.py:103-148): pairwise products P_p = E_i*E_j (i<j, lexicographic), attention MLP
+ *     Z_p = P_p W + b, s_p = relu(Z_p).p, a = softmax over pairs, afm = sum_p a_p P_p,
+ *     out = afm.w_pred + sum_f bias[x_f] + b0;  loss = 0.5*sum(y-out)^2.
+ *   idx [B,F] int32 (2 <= F <= 16);  W [K,A] row-major, batt [A], pvec [A], wpred [K];  K, A multiples of 4, <= 128,
+ *   in the same 32-tier (reference: A == K).  Gradients accumulate into gV / gbias / gb0 (sort-free scatter, optional
+ *   hot-row replicas) and gW [K,A], gbatt [A], gp [A], gwpred [K].  The lamda_attention*||W||^2/2 term (AFM.py:146) is
+ *   applied by the caller through hhfm_opt_*_dense_l2 on W.
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_afm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias, const float* b0,
+                 const float* W, const float* batt, const float* pvec, const float* wpred, int64_t M, int64_t K,
+                 int64_t A, float* out, hhfm_stream_t stream);
+int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias,
+                            const float* b0, const float* W, const float* batt, const float* pvec, const float* wpred,
+                            int64_t M, int64_t K, int64_t A, const float* labels, float* out, float* gV, float* gbias,
+                            float* gb0, float* gW, float* gbatt, float* gp, float* gwpred, float* loss_partials,
+                            int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
+                            const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
+                            hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K3  HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88) pairwise ranking
  * Record layout (int32, row stride `stride` >= 2+n_ctx+n_time+n_neg, stride % 4 == 0, 16-byte aligned):
  *   [user, item+, ctx_0..ctx_{n_ctx-1}, time_0..time_{n_time-1}, neg_0..neg_{n_neg-1}, pad...]

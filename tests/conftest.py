@@ -34,7 +34,7 @@ def assert_close(a, b, rtol=1e-5, what=""):
         what, int(bad.sum()), b.size, float(err.max()), float(tol.reshape(-1)[np.argmax(err)]), np.unravel_index(np.argmax(err), b.shape))
 
 
-def assert_update_close(w_got, w_ref, w_prev, g, acc_prev, lr, rtol=1e-5, what=""):
+def assert_update_close(w_got, w_ref, w_prev, g, acc_prev, lr, rtol=1e-5, what="", atol=0.0):
     """Post-step weights of one TF1-Adagrad step, compared as UPDATES (delta = w_new - w_prev) with a first-order
     propagation of the 1e-5 relative gradient tolerance through update(g) = lr*g/sqrt(acc+g^2):
         tol = rtol * ( max(|delta|, rms(delta)) + |d update/d g| * max(|g|, rms(g)) ),  d update/d g = lr*acc/(acc+g^2)^1.5.
@@ -46,7 +46,7 @@ def assert_update_close(w_got, w_ref, w_prev, g, acc_prev, lr, rtol=1e-5, what="
     delta = w_ref - w_prev
     rms_d = float(np.sqrt(np.mean(delta * delta))); rms_g = float(np.sqrt(np.mean(g * g)))
     sens = lr * acc_prev / np.power(acc_prev + g * g, 1.5)
-    tol = rtol * (np.maximum(np.abs(delta), rms_d) + sens * np.maximum(np.abs(g), rms_g))
+    tol = rtol * (np.maximum(np.abs(delta), rms_d) + sens * np.maximum(np.abs(g), rms_g)) + atol
     err = np.abs(w_got - w_ref)
     bad = err > tol
     assert not bad.any(), "%s: %d/%d elements off, worst err %.3e vs tol %.3e" % (

@@ -608,3 +608,48 @@ def test_device_metric_walk_reproduces_the_reference_run(cuda, name, tmp_path):
         codes = engine.metrics_walk(dev(pred, cuda, torch.int32), dev(rows[:, 1], cuda, torch.int32),
                                     dev(ld.in_positive_feedback(rows).astype(np.uint8), cuda), TopK).cpu().numpy()
         assert engine.metrics_from_codes(codes) == g["%s_walk%d_result" % (name, TopK)].tolist()
+
+
+# ----------------------------------------------------------------------------------------------------
+# K2 AFM
+# ----------------------------------------------------------------------------------------------------
+def _afm_weights(rng, M, K, A):
+    return dict(feature_embeddings=rng.normal(0, 0.1, (M, K)).astype(np.float32), feature_bias=rng.normal(0, 0.1, (M, 1)).astype(np.float32),
+                bias=np.float32(0.05), attention_W=rng.normal(0, 0.2, (K, A)).astype(np.float32),
+                attention_b=rng.normal(0, 0.2, (1, A)).astype(np.float32), attention_p=rng.normal(0, 1, (A,)).astype(np.float32),
+                prediction=rng.normal(1, 0.1, (K, 1)).astype(np.float32))
+
+
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64)])
+def test_afm_fused_pass_matches_oracle(cuda, B, F, K):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(B + F + K)
+    M, A = 300, K
+    w = _afm_weights(rng, M, K, A)
+    X = rng.integers(0, M, (B, F)); X[:, 1] = rng.integers(0, 4, B)
+    if F > 3:
+        X[:, 3] = X[:, 2]
+    Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    loss, out, g = O.afm_loss_grads(X, Y, w, 0.0)
+    tw = {k: dev(np.asarray(v, np.float32).reshape(-1) if k == "bias" else v, cuda) for k, v in w.items()}
+    P = lib.partials_len()
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    gW = torch.zeros(K, A, device=cuda); gba = torch.zeros(A, device=cuda); gp = torch.zeros(A, device=cuda); gwp = torch.zeros(K, device=cuda)
+    lp = torch.zeros(P, device=cuda); o = torch.empty(B, device=cuda); lo = torch.zeros(1, device=cuda)
+    tX = dev(X, cuda, torch.int32)
+    args = (ptr(tX), B, F, ptr(tw["feature_embeddings"]), ptr(tw["feature_bias"]), ptr(tw["bias"]), ptr(tw["attention_W"]),
+            ptr(tw["attention_b"]), ptr(tw["attention_p"]), ptr(tw["prediction"]), M, K, A)
+    o2 = torch.empty(B, device=cuda)
+    lib.call("hhfm_afm_fwd", *args, ptr(o2), st())
+    assert_close(o2.cpu().numpy(), out, what="afm fwd out")
+    lib.call("hhfm_afm_fwd_bwd_sqloss", *args, ptr(dev(Y.reshape(-1), cuda)), ptr(o), ptr(gV), ptr(gb), ptr(gb0), ptr(gW), ptr(gba),
+             ptr(gp), ptr(gwp), ptr(lp), None, 0, None, None, None, None, None, 0, 0, st())
+    lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(lo), st())
+    assert_close(o.cpu().numpy(), out, what="afm out"); assert_close(lo.item(), loss, what="afm loss")
+    assert_close(gV.cpu().numpy(), g["feature_embeddings"], rtol=2e-5, what="afm gV")
+    assert_close(gb.cpu().numpy(), g["feature_bias"].reshape(-1), what="afm gbias")
+    assert_close(gb0.item(), g["bias"], what="afm gb0")
+    assert_close(gW.cpu().numpy(), g["attention_W"], rtol=2e-5, what="afm gW")
+    assert_close(gba.cpu().numpy(), g["attention_b"].reshape(-1), rtol=2e-5, what="afm gb_att")
+    assert_close(gp.cpu().numpy(), g["attention_p"], rtol=2e-5, what="afm gp")
+    assert_close(gwp.cpu().numpy(), g["prediction"].reshape(-1), rtol=2e-5, what="afm gw_pred")

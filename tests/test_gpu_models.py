@@ -229,3 +229,57 @@ def test_autograd_functions_match_torch_reference(cuda):
     assert_close(V.grad.cpu().numpy(), Vr.grad.numpy(), what="autograd gV")
     assert_close(b.grad.cpu().numpy(), br.grad.numpy(), what="autograd gb")
     assert_close(c.grad.item(), cr.grad.item(), what="autograd gb0")
+
+
+def test_afm_steps_and_topk_match_oracle(cuda):
+    """AFM.partial_fit (AFM.py:205-208) teacher-forced against the oracle + TF1 Adagrad; AFM.topk rank-equivalence."""
+    from conftest import assert_update_close
+    from hhfm_b200.models import AFM
+    rng = np.random.default_rng(7)
+    n_user, n_item = 60, 200
+    X0, M = frappe_like(rng, 10, n_user=n_user, n_item=n_item, ctx=(7, 2, 3, 9))
+    K, lr, lam = 64, 0.1, 100.0
+    F = X0.shape[1]
+    model = AFM(n_user, n_item, M, 1, [K, K], 'relu', lr, lam, [1, 1], 'AdagradOptimizer', 0.999, F)
+    names = ["feature_embeddings", "feature_bias", "bias", "attention_W", "attention_b", "attention_p", "prediction"]
+    for step in range(4):
+        w = model.get_weights()
+        acc = {k: (model._opt.state[k][0].detach().cpu().numpy().reshape(np.asarray(w[k]).shape).copy() if k in model._opt.state
+                   else np.full(np.asarray(w[k]).shape, 0.1, np.float32)) for k in names}
+        X, _ = frappe_like(rng, 3000 if step < 3 else 517, n_user=n_user, n_item=n_item, ctx=(7, 2, 3, 9))
+        Y = rng.choice([1.0, -1.0], (len(X), 1)).astype(np.float32)
+        loss_ref, _, g = O.afm_loss_grads(X, Y, w, lam)
+        loss = model.partial_fit({"X": X, "Y": Y})
+        assert_close(loss, loss_ref, what="afm loss step %d" % step)
+        got = model.get_weights()
+        for k in names:
+            gk = np.asarray(g[k], np.float32).reshape(np.asarray(w[k]).shape)
+            w1, _ = O.adagrad_dense(np.asarray(w[k], np.float32), acc[k], gk, lr)
+            if k in ("feature_embeddings", "feature_bias"):
+                assert_update_close(got[k], w1, w[k], gk, acc[k], lr, rtol=3e-5, what="afm %s step %d" % (k, step))
+            else:
+                # Small dense variables: their gradients are sums over B*P terms that largely cancel (softmax gradients
+                # sum to zero over the pairs), so single elements are fp32 rounding noise in the oracle and on the device
+                # alike; the update is compared norm-wise (1e-4 of the largest update of the tensor, plus a 1e-8 floor: at
+                # the reference init Z ~ b for every pair, so d attention_b is an exactly cancelling sum).
+                d_ref = np.asarray(w1, np.float64) - np.asarray(w[k], np.float64)
+                d_got = np.asarray(got[k], np.float64).reshape(d_ref.shape) - np.asarray(w[k], np.float64)
+                ulp = 4 * 1.2e-7 * float(np.abs(np.asarray(w[k], np.float64)).max())     # 4 ulp of the tensor's largest weight
+                assert np.abs(d_got - d_ref).max() <= 1e-4 * np.abs(d_ref).max() + 1e-8 + ulp, (k, step, np.abs(d_got - d_ref).max(), np.abs(d_ref).max())
+    # predict through the sess shim and top-N (rank-equivalent to the reference formula)
+    w = model.get_weights()
+    out = model.sess.run(model.out, feed_dict={model.train_features: X[:300], model.train_labels: [[1]] * 300,
+                                               model.dropout_keep: [1.0, 1.0], model.train_phase: False})
+    assert_close(out[:, 0], O.afm_forward(X[:300], w)[0], what="afm predict")
+    A = X[:40]
+    ids = model.topk(A, 20)
+    ref = O.afm_topk_scores(A, w, n_user, n_item)
+    want = O.topk_lowest_index(ref, 20)
+    for r in range(len(A)):
+        if (ids[r] == want[r]).all():
+            continue
+        # lists may differ only between items whose reference scores are numerically indistinguishable
+        kth = ref[r, want[r, -1]]
+        tol = 2e-5 * max(abs(kth), float(np.sqrt(np.mean(ref[r] ** 2))))
+        for a_, b_ in zip(ids[r], want[r]):
+            assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
