@@ -26,6 +26,8 @@ SIGNATURES = {
     "hhfm_afm_fwd": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp],
     "hhfm_afm_fwd_bwd_sqloss": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                 vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp],
+    "hhfm_dfm_fwd": [vp, i64, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp],
+    "hhfm_dfm_fwd_bwd_sqloss": [vp, i64, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "hhfm_pairrank_fwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_pairrank_fwd_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp,
                               vp, vp, vp, i32, i32, i32, vp],
@@ -52,6 +54,9 @@ SIGNATURES = {
 INT64_FUNCS = {
     "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
+    "hhfm_dfm_param_count": [i64, i64, i32, vp],
+    "hhfm_dfm_reg_count": [i64, i64, i32, vp],
+    "hhfm_workspace_bytes_dfm": [i64, i64, i64, i32, vp],
 }
 OPTIONAL = {}   # symbols added by later kernels are appended by their modules via `declare`
 

@@ -1,0 +1,556 @@
+// K8: DeepFM (Newcode/DFM.py:104-152), fp32.
+//
+//   E = V[x] [F,K];  y1_f = feature_bias[x_f];  y2 = 0.5((sum_f e_f)^2 - sum_f e_f^2)            (DFM.py:104-122)
+//   H_0 = reshape(E) [F*K];  H_i = relu(H_{i-1} W_{i-1} + b_{i-1}),  i = 1..L                     (DFM.py:125-128)
+//   out = [y1 | y2 | H_L] . proj + cbias;  loss = 0.5 sum (y - out)^2  (+ l2 through the optimizer)   (DFM.py:131-152)
+//
+// Two kernels:
+//  * `sgemm_kernel<AMODE,BMODE,EPI>`: a 128x64x16 register-blocked fp32 SIMT GEMM (8x4 outputs per thread, double-
+//    buffered shared tiles) whose A operand can be GATHERED from the embedding table (layer 0 never materialises
+//    the [B, F*K] activation in HBM), whose epilogue fuses bias+relu, the relu mask of the backward (+ the bias
+//    gradient column sums), split-K atomics for weight gradients, or the SCATTER of d(H_0) straight into the
+//    embedding-gradient rows (sort-free vector reductions).  fp32 on CUDA cores because the parity bar is 1e-5
+//    relative: tcgen05 has no fp32-input MMA kind (a 3xTF32 split is the planned faster variant).
+//  * `dfm_head_kernel<VPL,TRAIN>`: one warp per sample: FM part, projection, loss, d(out), dZ_L, FM-part scatter and
+//    the projection / last-bias gradients.
+//
+// Parameter block (one flat caller-owned buffer, gradients use the same layout):
+//   [ layer_0 (d0 x d1) | ... | layer_{L-1} (d_{L-1} x d_L) | concat_projection (F+K+d_L) |   <- l2-regularised part
+//     bias_0 (d1) | ... | bias_{L-1} (d_L) | concat_bias (1) ]
+#include "common.cuh"
+
+namespace hhfm {
+
+enum { A_ROW = 0, A_COL = 1, A_GATHER = 2, A_GATHER_T = 3 };
+enum { B_ROW = 0, B_COL = 1 };
+enum { EPI_STORE = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2, EPI_ATOMIC = 3, EPI_SCATTER = 4 };
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int LDAS = BM + 4, LDBS = BN + 4;
+constexpr int kDfmMaxLayers = 8;
+
+struct GemmArgs {
+  const float* A;        // dense operand, or the embedding table V in the gather modes
+  const float* B;
+  float* C;
+  int M, N, Kd;
+  int64_t lda, ldb, ldc;
+  const int32_t* idx;    // [rows, F] (gather modes, EPI_SCATTER)
+  int F, K;
+  const float* bias;     // EPI_BIAS_RELU: [N]
+  const float* mask;     // EPI_MASK: C = acc * (mask > 0); may alias C
+  int64_t ldmask;
+  float* colsum;         // EPI_MASK, optional: colsum[n] += sum_m C[m,n]
+  int k_chunk;           // split-K: blockIdx.z covers [z*k_chunk, (z+1)*k_chunk)
+};
+
+// A-operand element (m, k).  In the gather modes (f, c) = (field, offset inside the embedding row) of the gathered
+// coordinate are precomputed by the caller so the inner loads carry no integer division.
+template <int AMODE>
+__device__ __forceinline__ float load_a(const GemmArgs& g, int m, int k, int f, int c) {
+  if (m >= g.M || k >= g.Kd) return 0.f;
+  if (AMODE == A_ROW) return __ldg(g.A + (int64_t)m * g.lda + k);
+  if (AMODE == A_COL) return __ldg(g.A + (int64_t)k * g.lda + m);
+  const int sample = (AMODE == A_GATHER) ? m : k;
+  const int row = __ldg(g.idx + (int64_t)sample * g.F + f);
+  return __ldg(g.A + (int64_t)row * g.K + c);
+}
+
+template <int BMODE>
+__device__ __forceinline__ float load_b(const GemmArgs& g, int k, int n) {
+  if (n >= g.N || k >= g.Kd) return 0.f;
+  if (BMODE == B_ROW) return __ldg(g.B + (int64_t)k * g.ldb + n);
+  return __ldg(g.B + (int64_t)n * g.ldb + k);
+}
+
+template <int AMODE, int BMODE, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][LDAS];
+  __shared__ __align__(16) float Bs[2][BK][LDBS];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  int k_beg = 0, k_end = g.Kd;
+  if (EPI == EPI_ATOMIC) {
+    k_beg = blockIdx.z * g.k_chunk;
+    k_end = min(g.Kd, k_beg + g.k_chunk);
+    if (k_beg >= k_end) return;
+  }
+  constexpr bool A_KC = (AMODE == A_ROW || AMODE == A_GATHER);   // k is the contiguous index of the A operand
+  constexpr bool B_KC = (BMODE == B_COL);
+
+  float ra[8], rb[4];
+  int gf = 0, gc = 0;        // A_GATHER_T: (field, offset) of this thread's fixed m
+  if (AMODE == A_GATHER_T) {
+    const int m = m0 + (tid & 127);
+    gf = m / g.K;
+    gc = m - gf * g.K;
+  }
+  auto fetch = [&](int k0) {
+    if (AMODE == A_GATHER) {   // (field, offset) of this thread's k = k0 + (tid & 15)
+      gf = k0 / g.K;
+      gc = k0 - gf * g.K + (tid & 15);
+      while (gc >= g.K) { gc -= g.K; gf++; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int mm = A_KC ? ((tid >> 4) + 16 * i) : (tid & 127);
+      const int kk = A_KC ? (tid & 15) : ((tid >> 7) + 2 * i);
+      const int k = k0 + kk;
+      ra[i] = (k < k_end) ? load_a<AMODE>(g, m0 + mm, k, gf, gc) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int nn = B_KC ? ((tid >> 4) + 16 * i) : (tid & 63);
+      const int kk = B_KC ? (tid & 15) : ((tid >> 6) + 4 * i);
+      const int k = k0 + kk;
+      rb[i] = (k < k_end) ? load_b<BMODE>(g, k, n0 + nn) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int mm = A_KC ? ((tid >> 4) + 16 * i) : (tid & 127);
+      const int kk = A_KC ? (tid & 15) : ((tid >> 7) + 2 * i);
+      As[buf][kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int nn = B_KC ? ((tid >> 4) + 16 * i) : (tid & 63);
+      const int kk = B_KC ? (tid & 15) : ((tid >> 6) + 4 * i);
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+
+  fetch(k_beg);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = k_beg; k0 < k_end; k0 += BK) {
+    const bool more = (k0 + BK) < k_end;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // ---- epilogue ----
+  const int nb = n0 + tx * 4;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  const int sf = (EPI == EPI_SCATTER) ? nb / g.K : 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int m = m0 + ty * 8 + r;
+    if (m >= g.M) continue;
+    if (EPI == EPI_SCATTER) {
+      // d(H_0)[m, n] belongs to embedding row idx[m, n / K], element n % K; 4 consecutive n share a row (K % 4 == 0)
+      if (nb < g.N) {
+        const int row = __ldg(g.idx + (int64_t)m * g.F + sf);
+        red_add_v4(g.C + (int64_t)row * g.K + (nb - sf * g.K), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+      }
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int n = nb + c;
+      if (n >= g.N) continue;
+      float v = acc[r][c];
+      float* dst = g.C + (int64_t)m * g.ldc + n;
+      if (EPI == EPI_BIAS_RELU) v = fmaxf(v + __ldg(g.bias + n), 0.f);
+      if (EPI == EPI_MASK) {
+        v = (g.mask[(int64_t)m * g.ldmask + n] > 0.f) ? v : 0.f;
+        cs[c] += v;
+      }
+      if (EPI == EPI_ATOMIC) atomicAdd(dst, v);
+      else *dst = v;
+    }
+  }
+  if (EPI == EPI_MASK && g.colsum != nullptr) {
+    // bias gradient: column sums of this tile (16 row-groups -> shared -> one atomic per column)
+    __syncthreads();
+    float* red = &As[0][0][0];     // 16 x 64 floats
+#pragma unroll
+    for (int c = 0; c < 4; c++) red[ty * BN + tx * 4 + c] = cs[c];
+    __syncthreads();
+    if (tid < BN && n0 + tid < g.N) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; r++) s += red[r * BN + tid];
+      atomicAdd(g.colsum + n0 + tid, s);
+    }
+  }
+}
+
+template <int AMODE, int BMODE, int EPI>
+static int launch_gemm(GemmArgs g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.Kd <= 0) return HHFM_OK;
+  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, 1);
+  if (EPI == EPI_ATOMIC) {
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    int64_t splits = (4 * (int64_t)sm_count() + tiles - 1) / tiles;
+    const int64_t max_splits = (g.Kd + 8 * BK - 1) / (8 * BK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int64_t chunk = (g.Kd + splits - 1) / splits;
+    chunk = (chunk + BK - 1) / BK * BK;
+    g.k_chunk = (int)chunk;
+    grid.z = (unsigned)((g.Kd + chunk - 1) / chunk);
+  }
+  sgemm_kernel<AMODE, BMODE, EPI><<<grid, 256, 0, st>>>(g);
+  return check_launch("sgemm_kernel");
+}
+
+// --------------------------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const int32_t* idx;
+  int64_t B;
+  int F, K, D;             // D = width of the last hidden layer
+  const float* V;
+  const float* fbias;      // feature_bias [M]
+  const float* proj;       // [F + K + D]
+  const float* cbias;      // [1]
+  float* H;                // [B, ldh]: H_L on entry; dZ_L on exit (TRAIN)
+  int64_t ldh;
+  const float* labels;
+  float* out;
+  float* gV;
+  float* gfbias;
+  float* gproj;            // [F + K + D]
+  float* gcbias;           // [1]
+  float* gblast;           // [D]  bias gradient of the last hidden layer = column sums of dZ_L
+  float* loss_partials;
+};
+
+constexpr int kHeadT = 8;    // D <= 32 * kHeadT
+
+template <int VPL, bool TRAIN>
+__global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
+  extern __shared__ float sred[];         // TRAIN: [F + K + 2*D + 1]
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31;
+  const int F = a.F, K = a.K, D = a.D, kv = K >> 2;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nred = F + K + 2 * D + 1;
+  if (TRAIN) {
+    for (int i = threadIdx.x; i < nred; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+  }
+  const float cb = __ldg(a.cbias);
+  const float p1 = (lane < F) ? __ldg(a.proj + lane) : 0.f;
+  float4 p2[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int c = lane + 32 * i;
+    const float* q = a.proj + F + 4 * c;            // the projection block has no 16-byte alignment guarantee
+    p2[i] = (c < kv) ? make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3)) : f4_zero();
+  }
+  float p3[kHeadT];
+#pragma unroll
+  for (int t = 0; t < kHeadT; t++) p3[t] = (lane + 32 * t < D) ? __ldg(a.proj + F + K + lane + 32 * t) : 0.f;
+
+  float g1 = 0.f, gcb = 0.f, loss_acc = 0.f;
+  float4 g2[VPL];
+  float g3[kHeadT], gbl[kHeadT];
+#pragma unroll
+  for (int i = 0; i < VPL; i++) g2[i] = f4_zero();
+#pragma unroll
+  for (int t = 0; t < kHeadT; t++) { g3[t] = 0.f; gbl[t] = 0.f; }
+
+  for (int64_t s = warp_g; s < a.B; s += n_warps) {
+    const int my_id = (lane < F) ? __ldg(a.idx + s * F + lane) : 0;
+    const float y1 = (lane < F) ? __ldg(a.fbias + my_id) : 0.f;
+    float4 S[VPL], Q[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; i++) { S[i] = f4_zero(); Q[i] = f4_zero(); }
+    for (int f = 0; f < F; f++) {
+      const int id = __shfl_sync(0xffffffffu, my_id, f);
+      const float4* row = reinterpret_cast<const float4*>(a.V) + (size_t)id * kv;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const int c = lane + 32 * i;
+        if (c < kv) {
+          const float4 e = ldg4(row + c);
+          S[i] = f4_add(S[i], e);
+          Q[i] = f4_add(Q[i], f4_mul(e, e));
+        }
+      }
+    }
+    float4 y2[VPL];
+    float part = y1 * p1;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      y2[i] = f4_scale(f4_sub(f4_mul(S[i], S[i]), Q[i]), 0.5f);
+      part += f4_dot(y2[i], p2[i]);
+    }
+    float h[kHeadT];
+    float* hrow = a.H + s * a.ldh;
+#pragma unroll
+    for (int t = 0; t < kHeadT; t++) {
+      const int j = lane + 32 * t;
+      h[t] = (j < D) ? hrow[j] : 0.f;
+      part = fmaf(h[t], p3[t], part);
+    }
+    const float out = warp_sum(part) + cb;
+    if (lane == 0 && a.out) a.out[s] = out;
+    if (!TRAIN) continue;
+
+    const float g = out - __ldg(a.labels + s);        // d loss / d out, loss = 0.5 (y - out)^2
+    loss_acc += (lane == 0) ? 0.5f * g * g : 0.f;
+    gcb += (lane == 0) ? g : 0.f;
+    g1 = fmaf(g, y1, g1);
+#pragma unroll
+    for (int i = 0; i < VPL; i++) g2[i] = f4_fma(y2[i], g, g2[i]);
+#pragma unroll
+    for (int t = 0; t < kHeadT; t++) {
+      const int j = lane + 32 * t;
+      g3[t] = fmaf(g, h[t], g3[t]);
+      const float dz = (h[t] > 0.f) ? g * p3[t] : 0.f;
+      gbl[t] += dz;
+      if (j < D) hrow[j] = dz;
+    }
+    // FM part of the embedding gradient: dV[x_f] += g * proj2 * (S - e_f);  d feature_bias[x_f] += g * proj1[f]
+    if (lane < F) atomicAdd(a.gfbias + my_id, g * p1);
+    for (int f = 0; f < F; f++) {
+      const int id = __shfl_sync(0xffffffffu, my_id, f);
+      const float4* row = reinterpret_cast<const float4*>(a.V) + (size_t)id * kv;
+      float* dst = a.gV + (size_t)id * K;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const int c = lane + 32 * i;
+        if (c < kv) {
+          const float4 e = ldg4(row + c);
+          red_add_v4(dst + 4 * c, f4_scale(f4_mul(p2[i], f4_sub(S[i], e)), g));
+        }
+      }
+    }
+  }
+  if (!TRAIN) return;
+  // ---- CTA reduction of the small dense gradients, then one global atomic per element ----
+  if (lane < F) atomicAdd(&sred[lane], g1);
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int c = lane + 32 * i;
+    if (c < kv) {
+      atomicAdd(&sred[F + 4 * c + 0], g2[i].x);
+      atomicAdd(&sred[F + 4 * c + 1], g2[i].y);
+      atomicAdd(&sred[F + 4 * c + 2], g2[i].z);
+      atomicAdd(&sred[F + 4 * c + 3], g2[i].w);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kHeadT; t++) {
+    const int j = lane + 32 * t;
+    if (j < D) {
+      atomicAdd(&sred[F + K + j], g3[t]);
+      atomicAdd(&sred[F + K + D + j], gbl[t]);
+    }
+  }
+  if (lane == 0) atomicAdd(&sred[F + K + 2 * D], gcb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nred; i += blockDim.x) {
+    const float v = sred[i];
+    if (i < F + K + D) atomicAdd(a.gproj + i, v);
+    else if (i < F + K + 2 * D) atomicAdd(a.gblast + (i - F - K - D), v);
+    else atomicAdd(a.gcbias, v);
+  }
+  const float bl = block_sum(loss_acc, scratch);
+  write_partial(a.loss_partials, bl);
+}
+
+template <bool TRAIN>
+static int launch_head(const HeadArgs& a, cudaStream_t st) {
+  const int grid = grid_for(a.B, 8, 4);
+  const size_t smem = TRAIN ? (size_t)(a.F + a.K + 2 * a.D + 1) * sizeof(float) : 0;
+  const int kv = a.K >> 2;
+  if (kv <= 32) dfm_head_kernel<1, TRAIN><<<grid, 256, smem, st>>>(a);
+  else if (kv <= 64) dfm_head_kernel<2, TRAIN><<<grid, 256, smem, st>>>(a);
+  else dfm_head_kernel<4, TRAIN><<<grid, 256, smem, st>>>(a);
+  return check_launch("dfm_head_kernel");
+}
+
+// --------------------------------------------------------------------------------------------------------------
+struct DfmLayout {
+  int L;
+  int d[kDfmMaxLayers + 1];          // d[0] = F*K, d[i] = layer_sizes[i-1]
+  int64_t ld[kDfmMaxLayers + 1];     // leading dimension of the H_i workspace block (d[i] rounded up to 4)
+  int64_t w_off[kDfmMaxLayers];      // offsets into the parameter block
+  int64_t b_off[kDfmMaxLayers];
+  int64_t proj_off, cbias_off, total, reg_len;
+  int64_t h_off[kDfmMaxLayers + 1];  // offsets into the workspace (floats); h_off[0] unused
+  int64_t ws_floats;
+};
+
+static int dfm_layout(int64_t B, int64_t F, int64_t K, int32_t L, const int32_t* sizes, DfmLayout& lo) {
+  HHFM_REQUIRE(L >= 1 && L <= kDfmMaxLayers && sizes, "dfm: 1 <= n_layers <= %d", kDfmMaxLayers);
+  HHFM_REQUIRE(F >= 1 && F <= 32, "dfm: 1 <= field_size <= 32");
+  HHFM_REQUIRE(K % 4 == 0 && K > 0 && K <= 512, "dfm: embedding_size must be a multiple of 4, <= 512");
+  lo.L = L;
+  lo.d[0] = (int)(F * K);
+  int64_t off = 0, ws = 0;
+  for (int i = 0; i < L; i++) {
+    HHFM_REQUIRE(sizes[i] >= 1 && sizes[i] <= 4096, "dfm: layer size out of range");
+    lo.d[i + 1] = sizes[i];
+    lo.w_off[i] = off;
+    off += (int64_t)lo.d[i] * lo.d[i + 1];
+  }
+  HHFM_REQUIRE(lo.d[L] <= 32 * kHeadT, "dfm: last hidden layer must be <= %d wide", 32 * kHeadT);
+  lo.proj_off = off;
+  off += F + K + lo.d[L];
+  off = (off + 3) / 4 * 4;          // zero padding keeps the un-regularised tail 16-byte aligned for the optimizer
+  lo.reg_len = off;
+  for (int i = 0; i < L; i++) {
+    lo.b_off[i] = off;
+    off += lo.d[i + 1];
+  }
+  lo.cbias_off = off;
+  lo.total = off + 1;
+  for (int i = 1; i <= L; i++) {
+    lo.ld[i] = (lo.d[i] + 3) / 4 * 4;
+    lo.h_off[i] = ws;
+    ws += B * lo.ld[i];
+  }
+  lo.ws_floats = ws;
+  return HHFM_OK;
+}
+
+static int dfm_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
+                       const DfmLayout& lo, float* ws, cudaStream_t st) {
+  for (int i = 0; i < lo.L; i++) {
+    GemmArgs g{};
+    g.M = (int)B; g.N = lo.d[i + 1]; g.Kd = lo.d[i];
+    g.B = params + lo.w_off[i]; g.ldb = lo.d[i + 1];
+    g.C = ws + lo.h_off[i + 1]; g.ldc = lo.ld[i + 1];
+    g.bias = params + lo.b_off[i];
+    int rc;
+    if (i == 0) {
+      g.A = V; g.idx = idx; g.F = (int)F; g.K = (int)K;
+      rc = launch_gemm<A_GATHER, B_ROW, EPI_BIAS_RELU>(g, st);
+    } else {
+      g.A = ws + lo.h_off[i]; g.lda = lo.ld[i];
+      rc = launch_gemm<A_ROW, B_ROW, EPI_BIAS_RELU>(g, st);
+    }
+    if (rc != HHFM_OK) return rc;
+  }
+  return HHFM_OK;
+}
+
+}  // namespace hhfm
+
+using namespace hhfm;
+
+extern "C" int64_t hhfm_dfm_param_count(int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes) {
+  DfmLayout lo;
+  if (dfm_layout(1, F, K, n_layers, layer_sizes, lo) != HHFM_OK) return -1;
+  return lo.total;
+}
+
+extern "C" int64_t hhfm_dfm_reg_count(int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes) {
+  DfmLayout lo;
+  if (dfm_layout(1, F, K, n_layers, layer_sizes, lo) != HHFM_OK) return -1;
+  return lo.reg_len;
+}
+
+extern "C" int64_t hhfm_workspace_bytes_dfm(int64_t B, int64_t F, int64_t K, int32_t n_layers,
+                                            const int32_t* layer_sizes) {
+  DfmLayout lo;
+  if (dfm_layout(B, F, K, n_layers, layer_sizes, lo) != HHFM_OK) return -1;
+  return lo.ws_floats * (int64_t)sizeof(float);
+}
+
+extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
+                            int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
+                            float* workspace, float* out, hhfm_stream_t stream) {
+  HHFM_REQUIRE(idx && V && feature_bias && params && workspace && out, "dfm_fwd: NULL argument");
+  HHFM_REQUIRE(B >= 0 && B < (1ll << 31) && M > 0, "dfm_fwd: bad sizes");
+  if (B == 0) return HHFM_OK;
+  DfmLayout lo;
+  int rc = dfm_layout(B, F, K, n_layers, layer_sizes, lo);
+  if (rc != HHFM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
+  if (rc != HHFM_OK) return rc;
+  HeadArgs h{};
+  h.idx = idx; h.B = B; h.F = (int)F; h.K = (int)K; h.D = lo.d[lo.L];
+  h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off;
+  h.H = workspace + lo.h_off[lo.L]; h.ldh = lo.ld[lo.L]; h.out = out;
+  return launch_head<false>(h, st);
+}
+
+extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V,
+                                       const float* feature_bias, int64_t M, int64_t K, const float* params,
+                                       int32_t n_layers, const int32_t* layer_sizes, const float* labels,
+                                       float* workspace, float* out, float* gV, float* gbias, float* gparams,
+                                       float* loss_partials, hhfm_stream_t stream) {
+  HHFM_REQUIRE(idx && V && feature_bias && params && workspace && labels && gV && gbias && gparams && loss_partials,
+               "dfm_fwd_bwd_sqloss: NULL argument");
+  HHFM_REQUIRE(B > 0 && B < (1ll << 31) && M > 0, "dfm_fwd_bwd_sqloss: bad sizes");
+  DfmLayout lo;
+  int rc = dfm_layout(B, F, K, n_layers, layer_sizes, lo);
+  if (rc != HHFM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = lo.L;
+  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
+  if (rc != HHFM_OK) return rc;
+  HeadArgs h{};
+  h.idx = idx; h.B = B; h.F = (int)F; h.K = (int)K; h.D = lo.d[L];
+  h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off;
+  h.H = workspace + lo.h_off[L]; h.ldh = lo.ld[L]; h.labels = labels; h.out = out;
+  h.gV = gV; h.gfbias = gbias; h.gproj = gparams + lo.proj_off; h.gcbias = gparams + lo.cbias_off;
+  h.gblast = gparams + lo.b_off[L - 1]; h.loss_partials = loss_partials;
+  rc = launch_head<true>(h, st);
+  if (rc != HHFM_OK) return rc;
+  // backward through the tower: layer i maps H_i -> H_{i+1}; dZ_{i+1} lives in the H_{i+1} block
+  for (int i = L - 1; i >= 0; i--) {
+    const float* dZ = workspace + lo.h_off[i + 1];
+    // d layer_i = H_i^T dZ_{i+1}   (split-K over the samples)
+    GemmArgs w{};
+    w.M = lo.d[i]; w.N = lo.d[i + 1]; w.Kd = (int)B;
+    w.B = dZ; w.ldb = lo.ld[i + 1];
+    w.C = gparams + lo.w_off[i]; w.ldc = lo.d[i + 1];
+    if (i == 0) {
+      w.A = V; w.idx = idx; w.F = (int)F; w.K = (int)K;
+      rc = launch_gemm<A_GATHER_T, B_ROW, EPI_ATOMIC>(w, st);
+    } else {
+      w.A = workspace + lo.h_off[i]; w.lda = lo.ld[i];
+      rc = launch_gemm<A_COL, B_ROW, EPI_ATOMIC>(w, st);
+    }
+    if (rc != HHFM_OK) return rc;
+    // d H_i = dZ_{i+1} layer_i^T, masked by relu'(H_i) (in place), or scattered into the embedding gradient (i == 0)
+    GemmArgs x{};
+    x.M = (int)B; x.N = lo.d[i]; x.Kd = lo.d[i + 1];
+    x.A = dZ; x.lda = lo.ld[i + 1];
+    x.B = params + lo.w_off[i]; x.ldb = lo.d[i + 1];
+    if (i == 0) {
+      x.C = gV; x.idx = idx; x.F = (int)F; x.K = (int)K;
+      rc = launch_gemm<A_ROW, B_COL, EPI_SCATTER>(x, st);
+    } else {
+      x.C = workspace + lo.h_off[i]; x.ldc = lo.ld[i];
+      x.mask = x.C; x.ldmask = lo.ld[i];
+      x.colsum = gparams + lo.b_off[i - 1];
+      rc = launch_gemm<A_ROW, B_COL, EPI_MASK>(x, st);
+    }
+    if (rc != HHFM_OK) return rc;
+  }
+  return HHFM_OK;
+}

@@ -7,7 +7,7 @@ reference (`_init_graph`) is replaced by device tensors and C-ABI kernel launche
 
   FM    Newcode/FM.py:59-198          MF   Newcode/MF.py:43-149
   OUR   Newcode/OurModel7.py:50-307   BPR  Newcode/BPR.py:45-136
-  AFM   Newcode/AFM.py:63-246
+  AFM   Newcode/AFM.py:63-246          DeepFM  Newcode/DFM.py:50-232
 """
 from __future__ import annotations
 
@@ -641,3 +641,159 @@ class AFM(FM):
             sc = self._predict_dev(rows.reshape(-1, F).contiguous()).view(c1 - c0, N)
             _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
         return out_ids.cpu().numpy()
+
+
+# ====================================================================================================
+class DeepFM(_Base):
+    """DeepFM, Newcode/DFM.py:50-232.  FM first/second-order parts + a relu MLP tower over the flattened embeddings,
+    joined by `concat_projection`; Adagrad only (DFM.py:153); l2 on the projection and the layer matrices (:145-150).
+
+    All dense variables live in ONE flat device buffer (layout: include/hhfm_sm100.h, K8); `weights[...]` are views."""
+
+    def __init__(self, n_user, n_item, feature_size, field_size, embedding_size, deep_layers, deep_layers_activation,
+                 learning_rate, verbose=True, l2_reg=0.0, random_seed=2016, use_fm=True, use_deep=True, loss_type="mse"):
+        assert (use_fm or use_deep)
+        assert loss_type in ["logloss", "mse"], \
+            "loss_type can be either 'logloss' for classification task or 'mse' for regression task"
+        self.n_user = n_user
+        self.n_item = n_item
+        self.feature_size = feature_size
+        self.field_size = field_size
+        self.embedding_size = embedding_size
+        self.deep_layers = [int(d) for d in deep_layers]
+        self.deep_layers_activation = deep_layers_activation
+        self.use_fm = use_fm
+        self.use_deep = use_deep
+        self.l2_reg = l2_reg
+        self.learning_rate = learning_rate
+        self.verbose = verbose
+        self.random_seed = random_seed
+        self.loss_type = loss_type
+        self._init_graph()
+
+    def _init_graph(self):
+        if not (self.use_fm and self.use_deep) or self.loss_type != "mse":
+            raise NotImplementedError("only use_fm=use_deep=True, loss_type='mse' (what DFM.py:257-259 builds) is on the "
+                                      "accelerated path")
+        act = self.deep_layers_activation
+        if not (act == "relu" or getattr(act, "__name__", "") == "relu"):
+            raise NotImplementedError("deep_layers_activation must be relu (DFM.py:258 passes tf.nn.relu)")
+        self.feat_index, self.label = Handle("feat_index"), Handle("label")
+        self.dropout_keep_fm, self.dropout_keep_deep = Handle("dropout_keep_fm"), Handle("dropout_keep_deep")
+        self.train_phase = Handle("train_phase")
+        self.out, self.loss, self.optimizer = Handle("out"), Handle("loss"), Handle("optimizer")
+        F, K, L = int(self.field_size), int(self.embedding_size), len(self.deep_layers)
+        self._setup(self.feature_size, K, self.random_seed, True, "AdagradOptimizer", self.learning_rate, 0.1, 0.0)
+        dev = self.device
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(self.random_seed) + 1)
+        self.weights["feature_bias"].copy_(torch.empty(self._M, 1).uniform_(0.0, 1.0, generator=gen))   # DFM.py:180-181
+        self._sizes = np.asarray(self.deep_layers, dtype=np.int32)
+        lib = _lib.load()
+        sp = self._sizes.ctypes.data
+        n_par = int(lib.hhfm_dfm_param_count(F, K, L, sp))
+        self._n_reg = int(lib.hhfm_dfm_reg_count(F, K, L, sp))
+        if n_par < 0:
+            raise _lib.HhfmError("DeepFM: %s" % lib.hhfm_last_error().decode())
+        self._params = torch.zeros(n_par, dtype=torch.float32, device=dev)
+        self._gparams = torch.zeros(n_par, dtype=torch.float32, device=dev)
+        rs = np.random.RandomState(self.random_seed)
+        dims = [F * K] + self.deep_layers
+        off = 0
+        for i in range(L):                                                                    # DFM.py:184-198
+            glorot = np.sqrt(2.0 / (dims[i] + dims[i + 1]))
+            n = dims[i] * dims[i + 1]
+            self.weights["layer_%d" % i] = self._params[off:off + n].view(dims[i], dims[i + 1])
+            self.weights["layer_%d" % i].copy_(torch.tensor(rs.normal(0, glorot, (dims[i], dims[i + 1])), dtype=torch.float32))
+            off += n
+        n_in = F + K + dims[-1]
+        self.weights["concat_projection"] = self._params[off:off + n_in].view(n_in, 1)        # DFM.py:201-210
+        self.weights["concat_projection"].copy_(torch.tensor(rs.normal(0, np.sqrt(2.0 / (n_in + 1)), (n_in, 1)), dtype=torch.float32))
+        off = self._n_reg                      # the regularised block is zero-padded to a multiple of 4 elements
+        for i in range(L):
+            glorot = np.sqrt(2.0 / (dims[i] + dims[i + 1]))
+            self.weights["bias_%d" % i] = self._params[off:off + dims[i + 1]].view(1, dims[i + 1])
+            self.weights["bias_%d" % i].copy_(torch.tensor(rs.normal(0, glorot, (1, dims[i + 1])), dtype=torch.float32))
+            off += dims[i + 1]
+        self.weights["concat_bias"] = self._params[off:off + 1].view(())
+        self.weights["concat_bias"].fill_(0.01)                                               # DFM.py:211
+        self._ws = None
+
+    def _workspace(self, B):
+        need = int(_lib.load().hhfm_workspace_bytes_dfm(B, int(self.field_size), self._K, len(self.deep_layers),
+                                                        self._sizes.ctypes.data)) // 4
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1), dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def _forward_dev(self, idx):
+        B, F = idx.shape
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_dfm_fwd", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
+                  self._M, self._K, ptr(self._params), len(self.deep_layers), self._sizes.ctypes.data,
+                  ptr(self._workspace(B)), ptr(out), cur_stream())
+        return out
+
+    def predict(self, X):
+        X = np.asarray(X)
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        return self._forward_dev(idx).cpu().numpy().reshape(-1, 1)
+
+    def partial_fit(self, data):
+        """DFM.py:216-219: one Adagrad step on {'X': [B,F] ids, 'Y': [B,1] labels}; returns the loss."""
+        X = np.asarray(data["X"])
+        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
+        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        y = self._upload_f32(data["Y"])
+        B, F = idx.shape
+        if F != int(self.field_size):
+            raise _lib.HhfmError("DeepFM.partial_fit: X has %d columns, field_size is %d" % (F, self.field_size))
+        self._opt.begin_step()
+        V, fb = self.weights["feature_embeddings"], self.weights["feature_bias"]
+        _lib.call("hhfm_dfm_fwd_bwd_sqloss", ptr(idx), B, F, ptr(V), ptr(fb), self._M, self._K, ptr(self._params),
+                  len(self.deep_layers), self._sizes.ctypes.data, ptr(y), ptr(self._workspace(B)), None, ptr(self._gV),
+                  ptr(self._gb), ptr(self._gparams), ptr(self._loss_partials), cur_stream())
+        if self._dp_group is not None:
+            import torch.distributed as dist
+            self._allreduce_grads()
+            dist.all_reduce(self._gparams, group=self._dp_group)
+        # V / feature_bias get IndexedSlices: Adagrad leaves rows with g = 0 untouched, so the dense kernel is exact
+        o = self._opt
+        o.apply_dense("feature_embeddings", V, self._gV, 0.0, None)
+        o.apply_dense("feature_bias", fb, self._gb, 0.0, None)
+        lam = float(self.l2_reg)
+        nr = self._n_reg
+        o.apply_dense("dense_reg", self._params[:nr], self._gparams[:nr], lam if lam > 0 else 0.0,
+                      self._sq_partials if lam > 0 else None)
+        o.apply_dense("dense_bias", self._params[nr:], self._gparams[nr:], 0.0, None)
+        self._version += 1
+        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if lam > 0 else None, 0.5 * lam,
+                  ptr(self._loss_dev), cur_stream())
+        self._loss_host.copy_(self._loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
+
+    def topk(self, A, tp):
+        """DFM.py:220-231: every (row, item) pair through the forward graph, then top_k (lowest index first on ties)."""
+        A = np.asarray(A)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        C_rows, F = A.shape
+        N = self.n_item
+        out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
+        chunk = max(1, (1 << 21) // max(N, 1))
+        for c0 in range(0, C_rows, chunk):
+            c1 = min(C_rows, c0 + chunk)
+            rows = A_dev[c0:c1, :F].unsqueeze(1).repeat(1, N, 1)
+            rows[:, :, 1] = items.unsqueeze(0)
+            sc = self._forward_dev(rows.reshape(-1, F).contiguous()).view(c1 - c0, N)
+            _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
+        return out_ids.cpu().numpy()
+
+    def _run(self, fetches, feed):
+        if fetches is self.out:
+            return self.predict(feed[self.feat_index])
+        if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
+            return self.partial_fit({"X": feed[self.feat_index], "Y": feed[self.label]}), None
+        raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))

@@ -135,6 +135,28 @@ int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
                             hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K8  DeepFM (DFM.py:104-152): y1_f = feature_bias[x_f], y2 = 0.5((sum e)^2 - sum e^2), a relu MLP tower over the
+ *     flattened embeddings, out = [y1 | y2 | H_L] . concat_projection + concat_bias;  loss = 0.5*sum(y-out)^2.
+ *   idx [B,F] int32 (F <= 32);  K % 4 == 0;  layer_sizes: HOST array of n_layers (<= 8) widths, last <= 256.
+ *   params / gparams: ONE flat buffer, layout
+ *     [ layer_0 (F*K x d1) | ... | layer_{L-1} | concat_projection (F+K+d_L) | 0-3 zero pad | bias_0 (d1) | ... | bias_{L-1} | concat_bias ]
+ *   (row-major matrices; hhfm_dfm_param_count() elements; the first hhfm_dfm_reg_count() carry DFM.py:145-150's l2).
+ *   workspace: hhfm_workspace_bytes_dfm(B, ...) bytes, caller-owned (hidden activations, reused for their gradients).
+ *   Layer 0 gathers its A operand straight from V; d(H_0) is scattered into gV by the GEMM epilogue.
+ *   Gradients ACCUMULATE into gV [M,K], gbias [M], gparams (zero them first).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t hhfm_dfm_param_count(int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes);
+int64_t hhfm_dfm_reg_count(int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes);
+int64_t hhfm_workspace_bytes_dfm(int64_t B, int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes);
+int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias, int64_t M,
+                 int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes, float* workspace,
+                 float* out, hhfm_stream_t stream);
+int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
+                            int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
+                            const float* labels, float* workspace, float* out, float* gV, float* gbias,
+                            float* gparams, float* loss_partials, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K3  HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88) pairwise ranking
  * Record layout (int32, row stride `stride` >= 2+n_ctx+n_time+n_neg, stride % 4 == 0, 16-byte aligned):
  *   [user, item+, ctx_0..ctx_{n_ctx-1}, time_0..time_{n_time-1}, neg_0..neg_{n_neg-1}, pad...]

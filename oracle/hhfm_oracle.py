@@ -434,6 +434,43 @@ def dfm_forward(X, w, n_layers=3):
     return out, dict(E=E, S=S, acts=acts, cat=cat)
 
 
+def dfm_loss_grads(X, Y, w, l2_reg=0.0, n_layers=3):
+    """DFM.py:139-152: loss = 0.5*sum(y-out)^2 + l2_reg/2*(||concat_projection||^2 + sum_i ||layer_i||^2) and the
+    gradient of every variable (TF autodiff restated; relu'(0) = 0)."""
+    Y = _f32(Y).reshape(-1)
+    out, c = dfm_forward(X, w, n_layers)
+    V = _f32(w["feature_embeddings"])
+    B, F, K = c["E"].shape
+    proj = _f32(w["concat_projection"]).reshape(-1)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)                                               # d loss / d out
+    grads = {}
+    grads["concat_projection"] = (c["cat"].T @ g).astype(F32).reshape(-1, 1)
+    grads["concat_bias"] = g.sum(dtype=F32)
+    d_cat = (g[:, None] * proj[None, :]).astype(F32)
+    d_y1, d_y2, d_h = d_cat[:, :F], d_cat[:, F:F + K], d_cat[:, F + K:]
+    for i in reversed(range(n_layers)):
+        h_out, h_in = c["acts"][i + 1], c["acts"][i]
+        dZ = (d_h * (h_out > 0)).astype(F32)
+        grads["layer_%d" % i] = (h_in.T @ dZ).astype(F32)
+        grads["bias_%d" % i] = dZ.sum(axis=0, dtype=F32).reshape(1, -1)
+        d_h = (dZ @ _f32(w["layer_%d" % i]).T).astype(F32)
+    dE = (d_h.reshape(B, F, K) + (d_y2[:, None, :] * (c["S"][:, None, :] - c["E"])).astype(F32)).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, X.reshape(-1), dE.reshape(-1, K))
+    db = np.zeros(V.shape[0], F32)
+    np.add.at(db, X.reshape(-1), d_y1.reshape(-1))
+    grads["feature_embeddings"] = dV
+    grads["feature_bias"] = db.reshape(-1, 1)
+    if l2_reg > 0:
+        for k in ["concat_projection"] + ["layer_%d" % i for i in range(n_layers)]:
+            wk = _f32(w[k])
+            loss = F32(loss + F32(l2_reg) * F32(0.5) * (wk * wk).astype(F32).sum(dtype=F32))
+            grads[k] = (grads[k] + F32(l2_reg) * wk.reshape(grads[k].shape)).astype(F32)
+    return F32(loss), out, grads
+
+
 # ----------------------------------------------------------------------------------------------------
 # optimizers: TF1 semantics (FM.py:129-136, BPR.py:93, MF.py:104)
 # ----------------------------------------------------------------------------------------------------

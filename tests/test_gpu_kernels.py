@@ -653,3 +653,71 @@ def test_afm_fused_pass_matches_oracle(cuda, B, F, K):
     assert_close(gba.cpu().numpy(), g["attention_b"].reshape(-1), rtol=2e-5, what="afm gb_att")
     assert_close(gp.cpu().numpy(), g["attention_p"], rtol=2e-5, what="afm gp")
     assert_close(gwp.cpu().numpy(), g["prediction"].reshape(-1), rtol=2e-5, what="afm gw_pred")
+
+
+# ----------------------------------------------------------------------------------------------------
+# K8 DeepFM
+# ----------------------------------------------------------------------------------------------------
+def _dfm_weights(rng, M, F, K, layers):
+    dims = [F * K] + list(layers)
+    w = dict(feature_embeddings=rng.normal(0, 0.1, (M, K)).astype(np.float32),
+             feature_bias=rng.uniform(0, 1, (M, 1)).astype(np.float32),
+             concat_projection=rng.normal(0, np.sqrt(2.0 / (F + K + dims[-1] + 1)), (F + K + dims[-1], 1)).astype(np.float32),
+             concat_bias=np.float32(0.01))
+    for i in range(len(layers)):
+        gl = np.sqrt(2.0 / (dims[i] + dims[i + 1]))
+        w["layer_%d" % i] = rng.normal(0, gl, (dims[i], dims[i + 1])).astype(np.float32)
+        w["bias_%d" % i] = rng.normal(0, gl, (1, dims[i + 1])).astype(np.float32)
+    return w
+
+
+def _dfm_flat(w, F, K, layers, lib):
+    sizes = np.asarray(layers, np.int32)
+    n = int(lib.load().hhfm_dfm_param_count(F, K, len(layers), sizes.ctypes.data))
+    nr = int(lib.load().hhfm_dfm_reg_count(F, K, len(layers), sizes.ctypes.data))
+    flat = np.zeros(n, np.float32)
+    off = 0
+    slots = {}
+    for i in range(len(layers)):
+        a = w["layer_%d" % i].reshape(-1); flat[off:off + a.size] = a; slots["layer_%d" % i] = (off, w["layer_%d" % i].shape); off += a.size
+    a = w["concat_projection"].reshape(-1); flat[off:off + a.size] = a; slots["concat_projection"] = (off, w["concat_projection"].shape)
+    off = nr
+    for i in range(len(layers)):
+        a = w["bias_%d" % i].reshape(-1); flat[off:off + a.size] = a; slots["bias_%d" % i] = (off, w["bias_%d" % i].shape); off += a.size
+    flat[off] = w["concat_bias"]; slots["concat_bias"] = (off, ())
+    assert off + 1 == n
+    return flat, slots, sizes
+
+
+@pytest.mark.parametrize("B,F,K,layers", [(64, 10, 64, (150, 200, 150)), (1001, 10, 64, (150, 200, 150)), (300, 6, 32, (40, 24)),
+                                          (77, 12, 128, (150, 200, 150)), (50, 3, 16, (7,)), (129, 2, 8, (33, 65, 17, 5))])
+def test_dfm_fused_pass_matches_oracle(cuda, B, F, K, layers):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(B + F + K)
+    M = 300
+    w = _dfm_weights(rng, M, F, K, layers)
+    X = rng.integers(0, M, (B, F)); X[:, 1] = rng.integers(0, 4, B)
+    if F > 3:
+        X[:, 3] = X[:, 2]
+    Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    loss, out, g = O.dfm_loss_grads(X, Y, w, 0.0, n_layers=len(layers))
+    flat, slots, sizes = _dfm_flat(w, F, K, layers, lib)
+    L = len(layers)
+    tV = dev(w["feature_embeddings"], cuda); tb = dev(w["feature_bias"], cuda); tp = dev(flat, cuda)
+    tX = dev(X, cuda, torch.int32)
+    ws = torch.empty(int(lib.load().hhfm_workspace_bytes_dfm(B, F, K, L, sizes.ctypes.data)) // 4 + 1, device=cuda)
+    o = torch.empty(B, device=cuda)
+    lib.call("hhfm_dfm_fwd", ptr(tX), B, F, ptr(tV), ptr(tb), M, K, ptr(tp), L, sizes.ctypes.data, ptr(ws), ptr(o), st())
+    assert_close(o.cpu().numpy(), out, what="dfm fwd out")
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gp = torch.zeros(flat.size, device=cuda)
+    lp = torch.zeros(lib.partials_len(), device=cuda); lo = torch.zeros(1, device=cuda); o2 = torch.empty(B, device=cuda)
+    lib.call("hhfm_dfm_fwd_bwd_sqloss", ptr(tX), B, F, ptr(tV), ptr(tb), M, K, ptr(tp), L, sizes.ctypes.data,
+             ptr(dev(Y.reshape(-1), cuda)), ptr(ws), ptr(o2), ptr(gV), ptr(gb), ptr(gp), ptr(lp), st())
+    lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(lo), st())
+    assert_close(o2.cpu().numpy(), out, what="dfm out"); assert_close(lo.item(), loss, what="dfm loss")
+    assert_close(gV.cpu().numpy(), g["feature_embeddings"], rtol=2e-5, what="dfm gV")
+    assert_close(gb.cpu().numpy(), g["feature_bias"].reshape(-1), rtol=2e-5, what="dfm gbias")
+    gp = gp.cpu().numpy()
+    for k, (off, shape) in slots.items():
+        ref = np.asarray(g[k], np.float32).reshape(-1)
+        assert_close(gp[off:off + ref.size], ref, rtol=2e-5, what="dfm g %s" % k)

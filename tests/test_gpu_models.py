@@ -283,3 +283,65 @@ def test_afm_steps_and_topk_match_oracle(cuda):
         tol = 2e-5 * max(abs(kth), float(np.sqrt(np.mean(ref[r] ** 2))))
         for a_, b_ in zip(ids[r], want[r]):
             assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
+
+
+def test_dfm_steps_and_topk_match_oracle(cuda):
+    """DeepFM.partial_fit (DFM.py:216-219) teacher-forced against the oracle + TF1 Adagrad; DeepFM.topk (DFM.py:220-231)."""
+    from conftest import assert_update_close
+    from hhfm_b200.models import DeepFM
+    rng = np.random.default_rng(11)
+    n_user, n_item = 60, 200
+    X0, M = frappe_like(rng, 10, n_user=n_user, n_item=n_item, ctx=(7, 2, 3, 9))
+    K, lr, lam = 64, 0.01, 0.01
+    F = X0.shape[1]
+    layers = [150, 200, 150]
+    model = DeepFM(n_user, n_item, M, F, K, layers, 'relu', lr, 0, lam)
+    names = list(model.weights.keys())
+    acc_name = {"feature_embeddings": "feature_embeddings", "feature_bias": "feature_bias"}
+    for step in range(4):
+        w = model.get_weights()
+        acc_reg = model._opt.state["dense_reg"][0].cpu().numpy().copy() if "dense_reg" in model._opt.state else None
+        acc_bias = model._opt.state["dense_bias"][0].cpu().numpy().copy() if "dense_bias" in model._opt.state else None
+        flat_off = {}
+        off = 0
+        for i in range(3):
+            flat_off["layer_%d" % i] = ("r", off); off += w["layer_%d" % i].size
+        flat_off["concat_projection"] = ("r", off)
+        off = 0
+        for i in range(3):
+            flat_off["bias_%d" % i] = ("b", off); off += w["bias_%d" % i].size
+        flat_off["concat_bias"] = ("b", off)
+        X, _ = frappe_like(rng, 3000 if step < 3 else 517, n_user=n_user, n_item=n_item, ctx=(7, 2, 3, 9))
+        Y = rng.choice([1.0, -1.0], (len(X), 1)).astype(np.float32)
+        loss_ref, _, g = O.dfm_loss_grads(X, Y, w, lam)
+        acc_tab = {k: (model._opt.state[k][0].cpu().numpy().copy() if k in model._opt.state else np.full(w[k].shape, 0.1, np.float32))
+                   for k in ("feature_embeddings", "feature_bias")}
+        loss = model.partial_fit({"X": X, "Y": Y})
+        assert_close(loss, loss_ref, what="dfm loss step %d" % step)
+        got = model.get_weights()
+        for k in names:
+            wk = np.asarray(w[k], np.float32)
+            gk = np.asarray(g[k], np.float32).reshape(wk.shape)
+            if k in acc_tab:
+                acc = acc_tab[k]
+            else:
+                kind, o_ = flat_off[k]
+                src = acc_reg if kind == "r" else acc_bias
+                acc = np.full(wk.shape, 0.1, np.float32) if src is None else src[o_:o_ + wk.size].reshape(wk.shape)
+            w1, _ = O.adagrad_dense(wk, acc, gk, lr)
+            assert_update_close(np.asarray(got[k]).reshape(wk.shape), w1, wk, gk, acc, lr, rtol=3e-5,
+                                atol=4 * 1.2e-7 * float(np.abs(wk).max()), what="dfm %s step %d" % (k, step))
+    w = model.get_weights()
+    out = model.sess.run(model.out, feed_dict={model.feat_index: X[:300], model.label: [[1]] * 300})
+    assert_close(out[:, 0], O.dfm_forward(X[:300], w)[0], what="dfm predict")
+    A = X[:40]
+    ids = model.topk(A, 20)
+    rows = np.repeat(A[:, None, :], n_item, axis=1); rows[:, :, 1] = n_user + np.arange(n_item)[None, :]
+    ref = O.dfm_forward(rows.reshape(-1, F), w)[0].reshape(len(A), n_item)
+    want = O.topk_lowest_index(ref, 20)
+    for r in range(len(A)):
+        if (ids[r] == want[r]).all():
+            continue
+        tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
+        for a_, b_ in zip(ids[r], want[r]):
+            assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
