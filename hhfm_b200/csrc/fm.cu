@@ -5,6 +5,8 @@
 // float4 of every embedding row -> every gathered row is one fully coalesced K*4-byte read, the reduction
 // over fields is per-lane register work, and only the final sum over k needs log2(LPS) shuffles.
 // The backward re-reads the rows (L1/L2 hits) and issues one REDG.E.ADD.F32x4 per 16 bytes.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hhfm {
@@ -197,6 +199,367 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Specialised training kernel for the common case (fixed-width rows, implicit values 1.0, FM interaction, K = 4*LPS,
+// F <= NF <= LPS).  What it changes over fm_kernel, measured on the scaled config (M = 10^7, K = 128: every row comes
+// from HBM): the generic kernel keeps 4 gathers in flight per warp and re-reads the rows for the backward, which left
+// DRAM at 12 % with every warp in long-scoreboard stalls.  Here all F row gathers (and the hot-slot / bias lookups) of
+// a sample are issued back to back, the rows stay in registers for the backward (no re-read), and the touched-row list
+// is appended with one warp-aggregated atomic instead of one per row.
+template <int LPS, int NF>
+__global__ void __launch_bounds__(kBlock, 2) fm_train_fixed_kernel(const FmArgs a) {
+  __shared__ float scratch[32];
+  constexpr int G = 32 / LPS;
+  const int lane = threadIdx.x & 31, lg = lane % LPS, grp = lane / LPS;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int F = a.F;
+  constexpr int K = 4 * LPS;
+  const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
+  float loss_acc = 0.f, g0_acc = 0.f;
+  const int rep = a.hot.slot ? (int)((warp_g * G + grp) % a.hot.n_rep) : 0;
+  const float4* V4 = reinterpret_cast<const float4*>(a.V);
+
+  for (int64_t s0 = warp_g * G; s0 < a.B; s0 += n_warps * G) {
+    const int64_t s = s0 + grp;
+    const bool valid = s < a.B;
+    const bool mine = valid && lg < F;                 // lane lg of the group looks after field lg
+    const int my_id = mine ? __ldg(a.col + s * F + lg) : 0;
+    int id[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) id[f] = __shfl_sync(0xffffffffu, my_id, grp * LPS + (f < LPS ? f : 0));
+    float4 e[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) e[f] = (valid && f < F) ? ldg4(V4 + (size_t)id[f] * LPS + lg) : f4_zero();
+    const int my_slot = (mine && a.hot.slot) ? __ldg(a.hot.slot + my_id) : -1;
+    const float my_bias = (mine && a.bias) ? __ldg(a.bias + my_id) : 0.f;
+    const float y = valid ? __ldg(a.labels + s) : 0.f;
+
+    float4 S = f4_zero(), Q = f4_zero();
+#pragma unroll
+    for (int f = 0; f < NF; f++) {                      // fields in order (FM.py:100,105-106)
+      S = f4_add(S, e[f]);
+      Q = f4_add(Q, f4_mul(e[f], e[f]));
+    }
+    const float part = 0.5f * f4_hsum(f4_sub(f4_mul(S, S), Q));
+    // bias terms are summed in field order by the group leader to match the generic kernel / oracle order
+    float bsum = 0.f;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const float bf = __shfl_sync(0xffffffffu, my_bias, grp * LPS + (f < LPS ? f : 0));
+      if (f < F) bsum += bf;
+    }
+    const float bil = group_sum<LPS>(part);
+    const float out = (bil + bsum) + b0;
+    const float diff = y - out;
+    const float g = valid ? -diff : 0.f;
+    if (valid && lg == 0) {
+      loss_acc += 0.5f * diff * diff;
+      g0_acc += g;
+      if (a.out) a.out[s] = out;
+    }
+    // ---- backward: gV[x_f] += g*(S - e_f) (one REDG.128 per lane and field); gbias[x_f] += g ----
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      const int slot = __shfl_sync(0xffffffffu, my_slot, grp * LPS + (f < LPS ? f : 0));
+      if (valid && f < F) {
+        float* dst = (slot >= 0) ? a.hot.ghot + ((size_t)rep * a.hot.n_hot + slot) * K : a.gV + (size_t)id[f] * K;
+        red_add_v4(dst + 4 * lg, f4_scale(f4_sub(S, e[f]), g));
+      }
+    }
+    if (mine && a.gbias) {
+      float* p = a.gbias + my_id;
+      if (my_slot >= 0 && a.hot.ghot_bias != nullptr) p = a.hot.ghot_bias + (size_t)rep * a.hot.n_hot + my_slot;
+      atomicAdd(p, g);
+    }
+    if (a.touch_stamp != nullptr) {
+      // first toucher of a row in this step claims it; the claims of a warp share one counter atomic
+      bool claimed = false;
+      if (mine && __ldcv(a.touch_stamp + my_id) != a.stamp) claimed = atomicExch(a.touch_stamp + my_id, a.stamp) != a.stamp;
+      const unsigned m = __ballot_sync(0xffffffffu, claimed);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(a.touched_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (claimed) a.touched_rows[base + __popc(m & ((1u << lane) - 1))] = my_id;
+      }
+    }
+  }
+  const float bl = block_sum(loss_acc, scratch);
+  write_partial(a.loss_partials, bl);
+  if (a.gb0 != nullptr) {
+    const float bg = block_sum(g0_acc, scratch);
+    if (threadIdx.x == 0 && bg != 0.f) atomicAdd(a.gb0, bg);
+  }
+}
+
+template <int LPS, int NF>
+static int launch_fm_fixed(const FmArgs& a, cudaStream_t st) {
+  static int occ = 0;
+  if (occ == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm_train_fixed_kernel<LPS, NF>, kBlock, 0);
+    if (occ < 1) occ = 1;
+  }
+  const int grid = grid_for(a.B, (kBlock / 32) * (32 / LPS), occ);
+  fm_train_fixed_kernel<LPS, NF><<<grid, kBlock, 0, st>>>(a);
+  return check_launch("fm_train_fixed_kernel");
+}
+
+// Returns HHFM_ERR_UNSUPPORTED when the shape is not covered (the caller then uses the generic kernel).
+static int dispatch_fm_fixed(const FmArgs& a, cudaStream_t st) {
+  if (a.row_ptr != nullptr || a.val != nullptr || a.interaction != 0) return HHFM_ERR_UNSUPPORTED;
+  const int lps = a.K / 4;
+  if (a.K != 32 && a.K != 64 && a.K != 128) return HHFM_ERR_UNSUPPORTED;
+  if (a.F > 16 || a.F > lps) return HHFM_ERR_UNSUPPORTED;
+#define FIXED(L)                                              \
+  do {                                                        \
+    if (a.F <= 8) return launch_fm_fixed<L, 8>(a, st);        \
+    if (a.F <= 12) return launch_fm_fixed<L, 12>(a, st);      \
+    return launch_fm_fixed<L, (L >= 16 ? 16 : 8)>(a, st);     \
+  } while (0)
+  if (lps == 8) FIXED(8);
+  if (lps == 16) FIXED(16);
+  FIXED(32);
+#undef FIXED
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged training kernel for tables that do not fit in L2 (scaled config: M = 10^7, K = 128, 5 GB of rows).
+// The register kernel above is bounded by memory latency there (ncu: DRAM 29 %, every warp in long-scoreboard stalls,
+// 16 warps/SM x 10 gathers in flight).  Here every warp runs its own NS-deep pipeline in shared memory:
+//   iteration t:  (A) LDGSTS the ids of sample t                                     -> id ring
+//                 (B) sample t-PD: one bulk copy (cp.async.bulk, UBLKCP) per field row -> row stage, completion on the
+//                     stage's mbarrier; LDGSTS of bias[id] / hot_slot[id]              -> per-stage side buffers
+//                 (C) sample t-PD-NS+1: wait on its mbarrier, FM forward + loss + backward from shared memory
+// so NS*F rows (NS*F*K*4 bytes, 20 KB at F=10, K=128) are in flight per warp with no register cost, and no load of
+// the consumer step (C) goes to global memory.  Touched rows are marked with a plain store into the stamp array and
+// compacted into the list afterwards (touched_compact_kernel) instead of one returning atomic per row.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldgsts4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ldgsts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_row(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+
+constexpr int kStagedWarps = 10;
+constexpr int kStagedMaxF = 16;
+
+// shared memory per warp: NS row stages [F][K] floats, then (NS+PD) id slots, NS bias slots, NS hot-slot slots of
+// kStagedMaxF words each, then NS mbarriers.
+__host__ __device__ inline size_t staged_warp_bytes(int NS, int F, int K) {
+  const int PD = NS - 1;
+  const size_t b = (size_t)NS * F * K * 4 + (size_t)((NS + PD) + 2 * NS) * kStagedMaxF * 4 + (size_t)NS * 8;
+  return (b + 127) / 128 * 128;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kStagedWarps * 32, 1) fm_train_staged_kernel(const FmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[32];
+  constexpr int PD = NS - 1;          // id prefetch distance (iterations)
+  constexpr int RI = NS + PD;         // id ring slots
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = a.F, K = a.K, kv = K >> 2;
+  const uint32_t row_bytes = (uint32_t)K * 4u;
+  unsigned char* base = smem_raw + (size_t)warp * staged_warp_bytes(NS, F, K);
+  float* rows = reinterpret_cast<float*>(base);                                   // [NS][F][K]
+  int* idring = reinterpret_cast<int*>(base + (size_t)NS * F * K * 4);             // [RI][16]
+  float* biasbuf = reinterpret_cast<float*>(idring + RI * kStagedMaxF);            // [NS][16]
+  int* slotbuf = reinterpret_cast<int*>(biasbuf + NS * kStagedMaxF);               // [NS][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slotbuf + NS * kStagedMaxF);        // [NS]
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) mbar_init1(bars + i);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // contiguous range of samples per warp: consecutive iterations read consecutive id records
+  const int64_t n_warps = (int64_t)gridDim.x * kStagedWarps;
+  const int64_t warp_g = (int64_t)blockIdx.x * kStagedWarps + warp;
+  const int64_t per = (a.B + n_warps - 1) / n_warps;
+  const int64_t s_beg = warp_g * per;
+  const int64_t s_end = (s_beg + per < a.B) ? s_beg + per : a.B;
+  const int64_t n = s_end > s_beg ? s_end - s_beg : 0;
+  const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
+  const int rep = a.hot.slot ? (int)(warp_g % a.hot.n_rep) : 0;
+  float loss_acc = 0.f, g0_acc = 0.f;
+
+  for (int64_t t = 0; t < n + PD + NS - 1; t++) {
+    // (A) ids of sample t
+    if (t < n && lane < F) ldgsts4(idring + (t % RI) * kStagedMaxF + lane, a.col + (s_beg + t) * F + lane);
+    // Group t (committed below) = {ids of sample t, bias / hot-slot words of sample t-PD}.  Groups <= t-PD are complete
+    // after this wait (the PD-1 most recent committed ones may be pending): the ids of sample t-PD and, since
+    // PD == NS-1, the bias / hot-slot words of the sample consumed in this iteration.
+    ldgsts_wait<(PD > 0 ? PD - 1 : 0)>();
+    __syncwarp();
+    // (B) issue the row copies of sample j
+    const int64_t j = t - PD;
+    if (j >= 0 && j < n) {
+      const int st = (int)(j % NS);
+      if (lane == 0) mbar_expect(bars + st, row_bytes * (uint32_t)F);
+      __syncwarp();
+      if (lane < F) {
+        const int id = idring[(j % RI) * kStagedMaxF + lane];
+        bulk_row(rows + ((size_t)st * F + lane) * K, a.V + (size_t)id * K, row_bytes, bars + st);
+        if (a.bias) ldgsts4(biasbuf + st * kStagedMaxF + lane, a.bias + id);
+        if (a.hot.slot) ldgsts4(slotbuf + st * kStagedMaxF + lane, a.hot.slot + id);
+      }
+    }
+    ldgsts_commit();
+    // (C) consume sample c
+    const int64_t c = t - PD - NS + 1;
+    if (c >= 0 && c < n) {
+      const int st = (int)(c % NS);
+      const int64_t s = s_beg + c;
+      mbar_wait_parity(bars + st, (uint32_t)((c / NS) & 1));
+      const float4* r4 = reinterpret_cast<const float4*>(rows + (size_t)st * F * K);
+      const int* ids = idring + (c % RI) * kStagedMaxF;
+      float4 S[4], Q[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { S[i] = f4_zero(); Q[i] = f4_zero(); }
+      for (int f = 0; f < F; f++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) {
+            const float4 e = r4[f * kv + cc];
+            S[i] = f4_add(S[i], e);
+            Q[i] = f4_add(Q[i], f4_mul(e, e));
+          }
+        }
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; i++) part += 0.5f * f4_hsum(f4_sub(f4_mul(S[i], S[i]), Q[i]));
+      float bsum = 0.f;
+      if (a.bias)
+        for (int f = 0; f < F; f++) bsum += biasbuf[st * kStagedMaxF + f];
+      const float out = (warp_sum(part) + bsum) + b0;
+      const float diff = __ldg(a.labels + s) - out;
+      const float g = -diff;
+      if (lane == 0) {
+        loss_acc += 0.5f * diff * diff;
+        g0_acc += g;
+        if (a.out) a.out[s] = out;
+      }
+      for (int f = 0; f < F; f++) {
+        const int id = ids[f];
+        const int slot = a.hot.slot ? slotbuf[st * kStagedMaxF + f] : -1;
+        float* dst = (slot >= 0) ? a.hot.ghot + ((size_t)rep * a.hot.n_hot + slot) * K : a.gV + (size_t)id * K;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) red_add_v4(dst + 4 * cc, f4_scale(f4_sub(S[i], r4[f * kv + cc]), g));
+        }
+      }
+      if (lane < F) {
+        const int id = ids[lane];
+        if (a.gbias) {
+          const int slot = a.hot.slot ? slotbuf[st * kStagedMaxF + lane] : -1;
+          float* p = (slot >= 0 && a.hot.ghot_bias != nullptr) ? a.hot.ghot_bias + (size_t)rep * a.hot.n_hot + slot : a.gbias + id;
+          atomicAdd(p, g);
+        }
+        if (a.touch_stamp) a.touch_stamp[id] = a.stamp;       // compacted into the list by touched_compact_kernel
+      }
+      __syncwarp();     // every lane is done with this stage before the next iteration re-arms it
+    }
+  }
+  ldgsts_wait<0>();
+  const float bl = block_sum(loss_acc, scratch);
+  write_partial(a.loss_partials, bl);
+  if (a.gb0 != nullptr) {
+    const float bg = block_sum(g0_acc, scratch);
+    if (threadIdx.x == 0 && bg != 0.f) atomicAdd(a.gb0, bg);
+  }
+}
+
+// rows whose stamp equals `stamp` -> appended to list[*count ...] (one counter atomic per warp)
+__global__ void __launch_bounds__(256) touched_compact_kernel(const int32_t* __restrict__ stamp_arr, int32_t stamp, int64_t M,
+                                                              int32_t* __restrict__ list, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (M + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; r++) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = (i < M) && (__ldg(stamp_arr + i) == stamp);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int basep = 0;
+      if (lane == leader) basep = atomicAdd(count, __popc(m));
+      basep = __shfl_sync(0xffffffffu, basep, leader);
+      if (hit) list[basep + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
+    }
+  }
+}
+
+// HHFM_ERR_UNSUPPORTED when the shape is not covered or the table is small enough to live in L2 (the register kernel wins
+// there); `M` is needed for the stamp compaction.
+static int dispatch_fm_staged(const FmArgs& a, int64_t M, cudaStream_t st) {
+  if (a.row_ptr != nullptr || a.val != nullptr || a.interaction != 0) return HHFM_ERR_UNSUPPORTED;
+  if (a.F > kStagedMaxF || a.K < 64 || a.K > 512) return HHFM_ERR_UNSUPPORTED;
+  const char* env = getenv("HHFM_FM_STAGED");       // 0 = never, 1 = always, unset = by table size
+  const int force = env ? (env[0] == '1' ? 1 : 0) : 2;
+  if (force == 0) return HHFM_ERR_UNSUPPORTED;
+  if (force == 2 && (size_t)M * a.K * 4 < ((size_t)96 << 20)) return HHFM_ERR_UNSUPPORTED;
+  int ns = 4;
+  while (ns > 2 && staged_warp_bytes(ns, a.F, a.K) * kStagedWarps > (size_t)200 * 1024) ns--;
+  const size_t smem = staged_warp_bytes(ns, a.F, a.K) * kStagedWarps;
+  if (smem > (size_t)200 * 1024) return HHFM_ERR_UNSUPPORTED;
+  const int grid = sm_count();
+  if (grid > kPartials) return HHFM_ERR_UNSUPPORTED;
+  cudaError_t e = cudaSuccess;
+  if (ns == 4) {
+    e = cudaFuncSetAttribute(fm_train_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) fm_train_staged_kernel<4><<<grid, kStagedWarps * 32, smem, st>>>(a);
+  } else if (ns == 3) {
+    e = cudaFuncSetAttribute(fm_train_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) fm_train_staged_kernel<3><<<grid, kStagedWarps * 32, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(fm_train_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) fm_train_staged_kernel<2><<<grid, kStagedWarps * 32, smem, st>>>(a);
+  }
+  if (e != cudaSuccess) {
+    set_error("fm_train_staged_kernel: %s", cudaGetErrorString(e));
+    return HHFM_ERR_LAUNCH;
+  }
+  int rc = check_launch("fm_train_staged_kernel");
+  if (rc != HHFM_OK) return rc;
+  if (a.touch_stamp != nullptr) {
+    int64_t blocks = (M + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    touched_compact_kernel<<<(int)blocks, 256, 0, st>>>(a.touch_stamp, a.stamp, M, a.touched_rows, a.touched_count);
+    rc = check_launch("touched_compact_kernel");
+  }
+  return rc;
+}
+
 template <int LPS, int VPL, int MODE>
 static int launch_fm(const FmArgs& a, int deterministic, cudaStream_t st) {
   static int occ = 0;
@@ -274,6 +637,12 @@ extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col
   a.loss_partials = loss_partials; a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows;
   a.touched_count = touched_count;
   a.hot = HotPlan{hot_slot, ghot, ghot_bias, n_rep, n_hot};
+  if (!deterministic) {
+    rc = dispatch_fm_staged(a, M, (cudaStream_t)stream);
+    if (rc != HHFM_ERR_UNSUPPORTED) return rc;
+    rc = dispatch_fm_fixed(a, (cudaStream_t)stream);
+    if (rc != HHFM_ERR_UNSUPPORTED) return rc;
+  }
   return dispatch_fm<FM_TRAIN>(a, deterministic, (cudaStream_t)stream);
 }
 

@@ -161,13 +161,21 @@ class _Base:
         self._opt.apply_dense("feature_embeddings", V, self._gV, self._lamda if self._lamda > 0 else 0.0, sq)
         return self._lamda > 0
 
-    def _finish_loss(self, with_reg):
+    def _enqueue_loss(self, with_reg, half_lamda=None):
+        """Deterministic reduction of the per-CTA loss partials (+ regulariser) into `_loss_dev`; no host sync."""
         self._version += 1
+        hl = (0.5 * self._lamda) if half_lamda is None else half_lamda
         _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if with_reg else None,
-                  0.5 * self._lamda if with_reg else 0.0, ptr(self._loss_dev), cur_stream())
+                  hl if with_reg else 0.0, ptr(self._loss_dev), cur_stream())
+
+    def _read_loss(self):
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self._loss_host[0])
+
+    def _upload_rows(self, X):
+        host, stride = pack_records([np.asarray(X)], self._M, self._idx_stage, align=1)
+        return self._idx_stage.upload(host.numel()).view(-1, stride)
 
     def _upload_ids(self, parts):
         host, stride = pack_records(parts, self._M, self._idx_stage)
@@ -249,12 +257,15 @@ class FM(_Base):
 
     def partial_fit(self, data):
         """One minibatch step (FM.py:168-171): forward, squared loss, backward, optimizer.  Returns the loss."""
-        X = np.asarray(data["X"])
-        F = X.shape[1]
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(data["X"])
         y = self._upload_f32(data["Y"])
-        B = idx.shape[0]
+        self.fit_device(idx, y)
+        return self._read_loss()
+
+    def fit_device(self, idx, y):
+        """The step on device-resident inputs (idx int32 [B,F], y fp32 [B]); everything is enqueued on the current
+        stream and nothing synchronises -- `partial_fit` = upload + fit_device + loss read-back."""
+        B, F = idx.shape
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
         bias = self.weights.get("feature_bias")
@@ -270,7 +281,7 @@ class FM(_Base):
         with_reg = self._apply_table(sparse_ok=True)
         if bias is not None:
             self._apply_bias()
-        return self._finish_loss(with_reg)
+        self._enqueue_loss(with_reg)
 
     def _apply_bias(self):
         # feature_bias receives IndexedSlices (only touched rows move); the scalar bias is dense.
@@ -345,10 +356,12 @@ class MF(FM):
         return out.cpu().numpy().reshape(-1, 1)
 
     def partial_fit(self, data):
-        X = np.asarray(data["X"])[:, :2]
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(np.asarray(data["X"])[:, :2])
         y = self._upload_f32(data["Y"])
+        self.fit_device(idx, y)
+        return self._read_loss()
+
+    def fit_device(self, idx, y):
         B = idx.shape[0]
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
@@ -361,7 +374,7 @@ class MF(FM):
             hot.fold(self._gV, None)
         self._allreduce_grads()
         with_reg = self._apply_table(sparse_ok=True)
-        return self._finish_loss(with_reg)
+        self._enqueue_loss(with_reg)
 
     def topk(self, A, tp=100):
         return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, tp)
@@ -376,7 +389,12 @@ class _PairRank(_Base):
 
     def _fit_records(self, parts, n_ctx, n_time, n_neg):
         idx, stride = self._upload_ids(parts)
-        B = idx.shape[0]
+        self.fit_device(idx, n_ctx, n_time, n_neg)
+        return self._read_loss()
+
+    def fit_device(self, idx, n_ctx, n_time, n_neg):
+        """The step on device-resident records (int32 [B,stride], layout: include/hhfm_sm100.h K3); no host sync."""
+        B, stride = idx.shape
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
         pc, pt, pf = self.pools
@@ -389,7 +407,7 @@ class _PairRank(_Base):
             hot.fold(self._gV, None)
         self._allreduce_grads()
         with_reg = self._apply_table(sparse_ok=True)
-        return self._finish_loss(with_reg)
+        self._enqueue_loss(with_reg)
 
     def _positive_feedback(self, parts, n_ctx, n_time):
         idx, stride = self._upload_ids(parts)
@@ -587,12 +605,13 @@ class AFM(FM):
     def partial_fit(self, data):
         """AFM.py:205-208.  V and feature_bias receive IndexedSlices (only touched rows move); attention_W carries the
         lamda_attention L2 term (AFM.py:146); attention_b/p, prediction and bias are small dense variables."""
-        X = np.asarray(data["X"])
-        F = X.shape[1]
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(data["X"])
         y = self._upload_f32(data["Y"])
-        B = idx.shape[0]
+        self.fit_device(idx, y)
+        return self._read_loss()
+
+    def fit_device(self, idx, y):
+        B, F = idx.shape
         self._opt.begin_step()
         ts, stamp, tr, tc = self._touch_args(extra=True)
         hot = self._hot_plan(idx, True)
@@ -616,12 +635,7 @@ class AFM(FM):
         o.apply_dense("attention_b", self.weights["attention_b"], self._gbatt, 0.0, None)
         o.apply_dense("attention_p", self.weights["attention_p"], self._gp, 0.0, None)
         o.apply_dense("prediction", self.weights["prediction"], self._gwp, 0.0, None)
-        self._version += 1
-        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if lam > 0 else None, 0.5 * lam,
-                  ptr(self._loss_dev), cur_stream())
-        self._loss_host.copy_(self._loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self._loss_host[0])
+        self._enqueue_loss(lam > 0, 0.5 * lam)
 
     def topk(self, A, tp):
         """AFM.topk (AFM.py:209-246) scores every item for each context row.  The reference restates `out` with an
@@ -742,13 +756,15 @@ class DeepFM(_Base):
 
     def partial_fit(self, data):
         """DFM.py:216-219: one Adagrad step on {'X': [B,F] ids, 'Y': [B,1] labels}; returns the loss."""
-        X = np.asarray(data["X"])
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(data["X"])
         y = self._upload_f32(data["Y"])
+        self.fit_device(idx, y)
+        return self._read_loss()
+
+    def fit_device(self, idx, y):
         B, F = idx.shape
         if F != int(self.field_size):
-            raise _lib.HhfmError("DeepFM.partial_fit: X has %d columns, field_size is %d" % (F, self.field_size))
+            raise _lib.HhfmError("DeepFM: X has %d columns, field_size is %d" % (F, self.field_size))
         self._opt.begin_step()
         V, fb = self.weights["feature_embeddings"], self.weights["feature_bias"]
         _lib.call("hhfm_dfm_fwd_bwd_sqloss", ptr(idx), B, F, ptr(V), ptr(fb), self._M, self._K, ptr(self._params),
@@ -767,12 +783,7 @@ class DeepFM(_Base):
         o.apply_dense("dense_reg", self._params[:nr], self._gparams[:nr], lam if lam > 0 else 0.0,
                       self._sq_partials if lam > 0 else None)
         o.apply_dense("dense_bias", self._params[nr:], self._gparams[nr:], 0.0, None)
-        self._version += 1
-        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if lam > 0 else None, 0.5 * lam,
-                  ptr(self._loss_dev), cur_stream())
-        self._loss_host.copy_(self._loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(self._loss_host[0])
+        self._enqueue_loss(lam > 0, 0.5 * lam)
 
     def topk(self, A, tp):
         """DFM.py:220-231: every (row, item) pair through the forward graph, then top_k (lowest index first on ties)."""

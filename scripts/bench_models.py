@@ -1,0 +1,201 @@
+#!/usr/bin/env python
+"""Per-model training-step throughput on one B200 with device-resident batches (the BASELINE.json configs that are
+not bench.py's headline line): FM c1 (frappe), FM c5 (scaled, HBM-bound), BPR c4, AFM c3, DeepFM.
+
+    python scripts/bench_models.py [--only fm_c1,fm_c5,bpr_c4,afm_c3,dfm] [--steps 20] [--json out.json]
+
+Each line: samples/s from CUDA events over `steps` whole steps (kernel + scatter fold + optimizer + loss reduction), and
+the roofline fraction from SURVEY.md 8(d)'s algorithmic bytes (HBM-bound models) or flops (AFM / DeepFM, fp32 SIMT).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x max SM clock = 74.4 TF
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"])
+    return 6650.0
+
+
+def zipf_ids(rng, n, size, a=1.1):
+    # inverse-CDF sampling of a truncated Zipf without materialising n probabilities for huge n
+    if n <= 1 << 16:
+        p = 1.0 / np.arange(1, n + 1) ** a
+        p /= p.sum()
+        return rng.choice(n, size=size, p=p)
+    u = rng.random(size)
+    # continuous approximation: P(X <= x) ~ (1 - x^(1-a)) / (1 - n^(1-a))
+    x = (1.0 - u * (1.0 - float(n) ** (1.0 - a))) ** (1.0 / (1.0 - a))
+    return np.minimum(n - 1, np.floor(x - 1.0 + 1e-9).astype(np.int64).clip(0))
+
+
+def frappe_rows(rng, B):
+    n_user, n_item, ctx = 957, 4082, (7, 2, 3, 2, 9, 80, 233, 7)
+    cols = [zipf_ids(rng, n_user, B), n_user + zipf_ids(rng, n_item, B)]
+    base = n_user + n_item
+    for c in ctx:
+        cols.append(base + rng.integers(0, c, B))
+        base += c
+    return np.stack(cols, 1).astype(np.int32), base, n_user, n_item
+
+
+def timed(fn, steps, warmup):
+    import torch
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_fm_c1(args, dev):
+    import torch
+    from hhfm_b200.models import FM
+    rng = np.random.default_rng(1)
+    B = 1 << 20
+    batches = []
+    for _ in range(4):
+        X, M, n_user, n_item = frappe_rows(rng, B)
+        batches.append((torch.from_numpy(X).to(dev), torch.from_numpy(rng.choice([1.0, 0.0], B).astype(np.float32)).to(dev)))
+    m = FM(10, M, n_user, n_item, 64, 0.1, 0.1, 1, "AdagradOptimizer", 0, 0)
+    ms = timed(lambda i: m.fit_device(*batches[i % 4]), args.steps, 5)
+    algo = 2648 + 2600
+    return {"config": "c1 FM frappe-10 (F=10, M=%d, K=64, dense-L2 Adagrad), B=2^20" % M, "ms_per_step": ms,
+            "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
+            "roofline": {"bound": "hbm", "achieved_gbs": B * algo / ms / 1e6, "peak_gbs": peaks(),
+                         "frac": B * algo / ms / 1e6 / peaks(), "note": "table L2-resident at this shape"}}
+
+
+def run_fm_c5(args, dev):
+    import torch
+    from hhfm_b200.models import FM
+    rng = np.random.default_rng(5)
+    B, K = 1 << 20, 128
+    n_user, n_item, n_ctx_ids = 4_000_000, 1_000_000, 5_000_000
+    M = n_user + n_item + n_ctx_ids
+    per_ctx = n_ctx_ids // 8
+    batches = []
+    for _ in range(3):
+        cols = [zipf_ids(rng, n_user, B), n_user + zipf_ids(rng, n_item, B)]
+        base = n_user + n_item
+        for c in range(8):
+            cols.append(base + rng.integers(0, per_ctx, B))
+            base += per_ctx
+        X = np.stack(cols, 1).astype(np.int32)
+        batches.append((torch.from_numpy(X).to(dev), torch.from_numpy(rng.choice([1.0, 0.0], B).astype(np.float32)).to(dev)))
+    uniq = int(np.unique(batches[0][0].cpu().numpy()).size)
+    m = FM(10, M, n_user, n_item, K, 0.1, 0.0, 1, "AdagradOptimizer", 0, 0)      # lamda = 0: sparse (IndexedSlices) update
+    ms = timed(lambda i: m.fit_device(*batches[i % 3]), args.steps, 3)
+    F = 10
+    algo = (4 * F + 4 * F * K + 4 * F + 4 + 4) + (4 * F * K + 4 * F) + 20 * (K + 1) * uniq / B
+    return {"config": "c5 scaled FM (F=10, M=10^7, K=128, sparse Adagrad rows), B=2^20, %d unique rows/step" % uniq,
+            "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
+            "roofline": {"bound": "hbm", "achieved_gbs": B * algo / ms / 1e6, "peak_gbs": peaks(),
+                         "frac": B * algo / ms / 1e6 / peaks()}}
+
+
+def run_bpr_c4(args, dev):
+    import torch
+    from hhfm_b200.models import BPR
+    from hhfm_b200.engine import Staging, pack_records
+    rng = np.random.default_rng(4)
+    B, K, NG = 1 << 20, 128, 10
+    n_user, n_item = 6522, 580
+    M = 7730
+    recs = []
+    for _ in range(4):
+        X = np.stack([zipf_ids(rng, n_user, B), n_user + zipf_ids(rng, n_item, B)], 1).astype(np.int64)
+        Y = (n_user + rng.integers(0, n_item, (B, NG))).astype(np.int64)
+        stg = Staging(torch.int32, dev)
+        host, stride = pack_records([X, Y], M, stg)
+        recs.append(stg.upload(host.numel()).view(B, stride).clone())
+    m = BPR(M, n_user, n_item, K, 0.05, 0.01, "AdagradOptimizer")
+    ms = timed(lambda i: m.fit_device(recs[i % 4], 0, 0, NG), args.steps, 5)
+    algo = 12 * 4 * K + 48 + 3 * 4 * K
+    return {"config": "c4 BPR restaurant shape (M=7730, N=580, K=128, NG=10, dense-L2 Adagrad), B=2^20",
+            "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
+            "roofline": {"bound": "hbm", "achieved_gbs": B * algo / ms / 1e6, "peak_gbs": peaks(),
+                         "frac": B * algo / ms / 1e6 / peaks(), "note": "table L2-resident at this shape"}}
+
+
+def run_afm_c3(args, dev):
+    import torch
+    from hhfm_b200.models import AFM
+    rng = np.random.default_rng(3)
+    B, K = 1 << 17, 64
+    batches = []
+    for _ in range(2):
+        X, M, n_user, n_item = frappe_rows(rng, B)
+        batches.append((torch.from_numpy(X).to(dev), torch.from_numpy(rng.choice([1.0, -1.0], B).astype(np.float32)).to(dev)))
+    m = AFM(n_user, n_item, M, 1, [K, K], "relu", 0.1, 100.0, [1, 1], "AdagradOptimizer", 0.999, 10)
+    ms = timed(lambda i: m.fit_device(*batches[i % 2]), max(3, args.steps // 4), 2)
+    P = 45
+    flops = 3 * 2 * P * K * K + 10 * P * K
+    return {"config": "c3 AFM frappe-10 (P=45 pairs, K=A=64), B=2^17", "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+            "algorithmic_flops_per_sample": flops,
+            "roofline": {"bound": "fp32-simt", "achieved_tflops": B * flops / ms / 1e9, "peak_tflops": FP32_SIMT_TFLOPS,
+                         "frac": B * flops / ms / 1e9 / FP32_SIMT_TFLOPS}}
+
+
+def run_dfm(args, dev):
+    import torch
+    from hhfm_b200.models import DeepFM
+    rng = np.random.default_rng(6)
+    B, K = 1 << 17, 64
+    layers = [150, 200, 150]
+    batches = []
+    for _ in range(2):
+        X, M, n_user, n_item = frappe_rows(rng, B)
+        batches.append((torch.from_numpy(X).to(dev), torch.from_numpy(rng.choice([1.0, -1.0], B).astype(np.float32)).to(dev)))
+    m = DeepFM(n_user, n_item, M, 10, K, layers, "relu", 0.01, 0, 0.01)
+    ms = timed(lambda i: m.fit_device(*batches[i % 2]), max(3, args.steps // 2), 2)
+    dims = [10 * K] + layers
+    mm = sum(dims[i] * dims[i + 1] for i in range(3))
+    flops = 3 * 2 * mm
+    return {"config": "DeepFM frappe-10 (640-150-200-150, K=64), B=2^17", "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+            "algorithmic_flops_per_sample": flops,
+            "roofline": {"bound": "fp32-simt", "achieved_tflops": B * flops / ms / 1e9, "peak_tflops": FP32_SIMT_TFLOPS,
+                         "frac": B * flops / ms / 1e9 / FP32_SIMT_TFLOPS}}
+
+
+RUNNERS = {"fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=",".join(RUNNERS))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    import torch
+    dev = torch.device("cuda", 0)
+    out = {}
+    for name in args.only.split(","):
+        r = RUNNERS[name](args, dev)
+        out[name] = r
+        print(json.dumps({name: r}), flush=True)
+        torch.cuda.empty_cache()
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -721,3 +721,56 @@ def test_dfm_fused_pass_matches_oracle(cuda, B, F, K, layers):
     for k, (off, shape) in slots.items():
         ref = np.asarray(g[k], np.float32).reshape(-1)
         assert_close(gp[off:off + ref.size], ref, rtol=2e-5, what="dfm g %s" % k)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K1 variants: the TMA-staged pipeline (large tables) against the oracle and the register kernels
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (5000, 10, 128), (999, 6, 128), (3, 16, 64), (777, 10, 256), (2049, 1, 512),
+                                   (1500, 12, 100)])
+def test_fm_staged_pipeline_matches_oracle(cuda, B, F, K, monkeypatch):
+    """fm_train_staged_kernel (cp.async.bulk row staging + mbarriers; chosen automatically when the table exceeds L2)
+    forced on small inputs: out / loss / gradients / touched-row set against the oracle."""
+    monkeypatch.setenv("HHFM_FM_STAGED", "1")
+    rng = np.random.default_rng(B + K + F)
+    M = 400
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32); b0 = np.float32(-0.1)
+    X = rng.integers(0, M, (B, F))
+    if F > 1:
+        X[:, 1] = rng.integers(0, 3, B)
+    if F > 4:
+        X[:, 4] = X[:, 0]
+    Y = rng.choice([1.0, 0.0], (B, 1)).astype(np.float32)
+    loss, out, dV, db, db0, touched = O.fm_loss_grads(X, Y, V, b, b0, lamda=0.0)
+    got = _fm_train_call(cuda, X, Y, V, b, b0)
+    assert_close(got["out"], out, what="out")
+    assert_close(got["loss"], loss, what="loss")
+    assert_close(got["gV"], dV, what="gV")
+    assert_close(got["gb"], db, what="gbias")
+    assert_close(got["gb0"], db0, what="gb0")
+    assert (got["touched"] == touched).all()
+    got2 = _fm_train_call(cuda, X, Y, V, None, None, track=False)          # no bias, no tracking
+    monkeypatch.setenv("HHFM_FM_STAGED", "0")
+    ref2 = _fm_train_call(cuda, X, Y, V, None, None, track=False)
+    assert_close(got2["out"], ref2["out"], what="staged vs register out"); assert_close(got2["gV"], ref2["gV"], what="staged vs register gV")
+
+
+def test_fm_staged_pipeline_with_hot_rows(cuda, monkeypatch):
+    lib, ptr, st = _lib_ptr()
+    from hhfm_b200.engine import HotRows
+    monkeypatch.setenv("HHFM_FM_STAGED", "1")
+    rng = np.random.default_rng(79)
+    M, K, B, F = 200, 128, 3000, 6
+    V = make_table(rng, M, K); b = rng.normal(0, 0.1, (M, 1)).astype(np.float32)
+    X = np.stack([rng.integers(0, 100, B), rng.integers(100, 180, B), 190 + rng.integers(0, 2, B), 192 + rng.integers(0, 3, B),
+                  195 + rng.integers(0, 5, B), rng.integers(0, 3, B)], axis=1)
+    Y = rng.choice([1.0, 0.0], (B, 1)).astype(np.float32)
+    loss, out, dV, db, db0, _ = O.fm_loss_grads(X, Y, V, b, 0.0, 0.0)
+    hot = HotRows(np.concatenate([np.arange(3), np.arange(190, 200)]), M, K, cuda, with_bias=True, n_rep=4)
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    lp = torch.zeros(lib.partials_len(), device=cuda)
+    lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(dev(X, cuda, torch.int32)), None, B, F, ptr(dev(V, cuda)), ptr(dev(b, cuda)), None,
+             M, K, 0, ptr(dev(Y.reshape(-1), cuda)), None, ptr(gV), ptr(gb), ptr(gb0), ptr(lp), None, 0, None, None,
+             *hot.args(True), 0, st())
+    hot.fold(gV, gb)
+    assert_close(gV.cpu().numpy(), dV, what="fm gV hot staged"); assert_close(gb.cpu().numpy(), db, what="fm gb hot staged")
