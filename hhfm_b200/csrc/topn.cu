@@ -133,11 +133,13 @@ __device__ __forceinline__ float key_score(unsigned long long k) {
 }
 __device__ __forceinline__ int key_id(unsigned long long k) { return (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)); }
 
+constexpr int kSelectStage = 4096;     // rows with at most this many entries keep their keys in shared memory
+
 __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
                                                      const int32_t* __restrict__ counts, int64_t row_stride, int64_t n_max,
-                                                     int tp, int tp_pow2, int id_offset, float* __restrict__ out_scores,
-                                                     int32_t* __restrict__ out_ids) {
-  extern __shared__ unsigned long long s_keys[];     // tp_pow2 winners
+                                                     int tp, int tp_pow2, int staged, int id_offset,
+                                                     float* __restrict__ out_scores, int32_t* __restrict__ out_ids) {
+  extern __shared__ unsigned long long s_keys[];     // tp_pow2 winners (+ the row's keys when staged)
   __shared__ unsigned s_hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_krem, s_cnt;
@@ -148,6 +150,10 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   if (n > n_max) n = n_max;
   const int want = (int)(n < tp ? n : tp);
   const int t = threadIdx.x;
+  unsigned long long* s_all = s_keys + tp_pow2;
+  if (staged)
+    for (int64_t i = t; i < n; i += 256) s_all[i] = make_key(sc[i], idp ? idp[i] : (int)i);
+  auto key_at = [&](int64_t i) { return staged ? s_all[i] : make_key(sc[i], idp ? idp[i] : (int)i); };
 
   unsigned long long thresh = 0ull;
   if (n > tp) {
@@ -158,19 +164,38 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
       __syncthreads();
       const unsigned long long prefix = s_prefix;
       for (int64_t i = t; i < n; i += 256) {
-        const unsigned long long k = make_key(sc[i], idp ? idp[i] : (int)i);
+        const unsigned long long k = key_at(i);
         if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
       }
       __syncthreads();
-      if (t == 0) {
-        int krem = s_krem, b = 255;
-        unsigned cum = 0;
-        for (; b > 0; b--) {
-          if (cum + s_hist[b] >= (unsigned)krem) break;
-          cum += s_hist[b];
+      if (t < 32) {
+        // bin holding the krem-th largest key: lane t owns bins 8t..8t+7, suffix sums across lanes by shuffles
+        unsigned h[8], T = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { h[q] = s_hist[t * 8 + q]; T += h[q]; }
+        unsigned S = T;                               // becomes the sum over lanes >= t
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_down_sync(0xffffffffu, S, o);
+          if (t + o < 32) S += v;
         }
-        s_krem = krem - (int)cum;
-        s_prefix = (prefix << 8) | (unsigned long long)b;
+        const unsigned krem = (unsigned)s_krem;
+        const unsigned bal = __ballot_sync(0xffffffffu, S >= krem);   // true for lanes 0..target
+        const int target = 31 - __clz((int)bal);
+        if (t == target) {
+          unsigned cum = S - T;
+          int bsel = 0;
+          bool done = false;
+#pragma unroll
+          for (int q = 7; q >= 0; q--) {
+            if (!done) {
+              if (q == 0 || cum + h[q] >= krem) { bsel = q; done = true; }
+              else cum += h[q];
+            }
+          }
+          s_krem = (int)(krem - cum);
+          s_prefix = (prefix << 8) | (unsigned long long)(t * 8 + bsel);
+        }
       }
       __syncthreads();
     }
@@ -180,7 +205,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   for (int i = t; i < tp_pow2; i += 256) s_keys[i] = 0ull;   // 0 sorts last
   __syncthreads();
   for (int64_t i = t; i < n; i += 256) {
-    const unsigned long long k = make_key(sc[i], idp ? idp[i] : (int)i);
+    const unsigned long long k = key_at(i);
     if (k >= thresh) {
       const int slot = atomicAdd(&s_cnt, 1);
       if (slot < tp_pow2) s_keys[slot] = k;
@@ -275,8 +300,10 @@ extern "C" int hhfm_topn_select(const float* scores, const int32_t* ids, const i
   if (C == 0) return HHFM_OK;
   int p2 = 1;
   while (p2 < tp) p2 <<= 1;
-  select_kernel<<<(unsigned)C, 256, p2 * sizeof(unsigned long long), (cudaStream_t)stream>>>(
-      scores, ids, counts, row_stride, n, tp, p2, id_offset, out_scores, out_ids);
+  const int staged = n <= kSelectStage ? 1 : 0;
+  const size_t smem = ((size_t)p2 + (staged ? (size_t)n : 0)) * sizeof(unsigned long long);
+  select_kernel<<<(unsigned)C, 256, smem, (cudaStream_t)stream>>>(scores, ids, counts, row_stride, n, tp, p2, staged,
+                                                                  id_offset, out_scores, out_ids);
   return check_launch("select_kernel");
 }
 

@@ -20,6 +20,7 @@
 // A row whose candidates overflow the buffer is flagged and redone by the exact path (host side).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -113,6 +114,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, with the destination registers of an earlier tcgen05.ld threaded through it ("+r"): every later use of
+// r[] then depends on the wait, so the compiler cannot schedule it into the window where the load is still in flight.
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows x 128 B = 1024)
@@ -211,6 +223,7 @@ struct TcArgs {
   int64_t gmax_stride;    // floats per gmax row
   float* gmax;
   int fine;               // 1: one maximum per 32 items, 0: one per BN-item tile
+  int tile_stride;        // max pass on a SAMPLE of the catalog: unit tile t covers item tile t * tile_stride
   const float* thr_emit;  // EMIT: per-row threshold in approximate-score space
   int32_t* seg_ids;       // EMIT: [C, splits, cap_u] survivor ids; segment (row, split) is private to ONE thread
   int32_t* seg_cnt;       // EMIT: [C, splits] survivors found (may exceed cap_u -> overflow)
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
           mbar_expect_tx(full + st, TcSmem<NKC, BN, STAGES>::kBStage);
 #pragma unroll
           for (int kc = 0; kc < NKC; kc++)
-            tma_load_2d(sB + st * TcSmem<NKC, BN, STAGES>::kBStage + kc * BN * 128, &tmB, kc * kKC, t * BN, full + st);
+            tma_load_2d(sB + st * TcSmem<NKC, BN, STAGES>::kBStage + kc * BN * 128, &tmB, kc * kKC, t * a.tile_stride * BN, full + st);
           if (++st == STAGES) { st = 0; ph ^= 1; }
         }
       }
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
         tc_fence_after();
         float gm[kChunks];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-        const int64_t n_base = (int64_t)t * BN;
+        const int64_t n_base = (int64_t)t * a.tile_stride * BN;
         if (!EMIT) {
 #pragma unroll
           for (int c = 0; c < kChunks; c++) {
@@ -348,31 +361,50 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
             gm[c] = m;
           }
         } else {
-          // Survivor emission.  The chunk loop is NOT unrolled and the per-element work is a branch-free bit mask plus
-          // a short rare loop: the whole epilogue stays inside the instruction cache (an unrolled 8 x 32 emission
-          // body is ~100 KB of SASS and made this pass 10x slower than the max pass).
-#pragma unroll 1
-          for (int c = 0; c < kChunks; c++) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c * kGroup, r);
-            tmem_ld_wait();
-            float m = -INFINITY;
+          // Survivor emission.  Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+          // scanned (with one buffer every chunk paid the full TMEM load latency: 1.7 ms against 1.0 ms for the max
+          // pass).  The scan is a max tree over four 8-item sub-groups; only a sub-group holding a survivor builds a
+          // bit mask.  The loop is unrolled by 2 only, so the epilogue stays inside the instruction cache (an unrolled
+          // 8 x 32 emission body is ~100 KB of SASS and ran 10x slower).
+          auto scan = [&](const uint32_t (&r)[32], int c) {
+            float mq[4];
 #pragma unroll
-            for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(r[i]));
-            if (m >= thr) {                     // rare: ~2 tp survivors per row over the whole catalog
-              unsigned mask = 0u;
+            for (int q = 0; q < 4; q++) {
+              float m = __uint_as_float(r[8 * q]);
 #pragma unroll
-              for (int i = 0; i < 32; i++) mask |= (__uint_as_float(r[i]) >= thr ? 1u : 0u) << i;
-              const int nb = (int)n_base + c * kGroup;
-              while (mask) {                    // no atomics: the segment belongs to this thread
-                const int i = __ffs((int)mask) - 1;
-                mask &= mask - 1;
-                if (nb + i < a.N) {
-                  if (n_emit < a.cap_u) seg[n_emit] = nb + i;
-                  n_emit++;
+              for (int i = 1; i < 8; i++) m = fmaxf(m, __uint_as_float(r[8 * q + i]));
+              mq[q] = m;
+            }
+            if (fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) >= thr) {   // rare: a few hundred survivors per row
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                if (mq[q] >= thr) {
+                  unsigned mask = 0u;
+#pragma unroll
+                  for (int i = 0; i < 8; i++) mask |= (__uint_as_float(r[8 * q + i]) >= thr ? 1u : 0u) << i;
+                  const int nb = (int)n_base + c * kGroup + 8 * q;
+                  while (mask) {                // no atomics: the segment belongs to this thread
+                    const int i = __ffs((int)mask) - 1;
+                    mask &= mask - 1;
+                    if (nb + i < a.N) {
+                      if (n_emit < a.cap_u) seg[n_emit] = nb + i;
+                      n_emit++;
+                    }
+                  }
                 }
               }
             }
+          };
+          uint32_t ra[32], rb[32];
+          tmem_ld32(taddr, ra);
+#pragma unroll 1
+          for (int c = 0; c < kChunks; c += 2) {
+            tmem_ld_wait_for(ra);
+            tmem_ld32(taddr + (c + 1) * kGroup, rb);
+            scan(ra, c);
+            tmem_ld_wait_for(rb);
+            if (c + 2 < kChunks) tmem_ld32(taddr + (c + 2) * kGroup, ra);
+            scan(rb, c + 1);
           }
         }
         tc_fence_before();
@@ -403,12 +435,32 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
 // thresholds: thr_emit[c] = tau_c - 2 E_c (approximate-score space)
 // ---------------------------------------------------------------------------------------------------
 __global__ void tc_threshold_kernel(int64_t C, int fm, int K, const float* __restrict__ tau, int tau_stride,
-                                    const float4* __restrict__ qinfo, const float* __restrict__ stats,
-                                    float* __restrict__ thr_emit) {
+                                    const float4* __restrict__ qinfo, const float* __restrict__ stats, int sampled,
+                                    float* __restrict__ thr_emit, float* __restrict__ thr_verify) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float E = row_error_bound(qinfo[c], stats[0], stats[1], fm, K);
-  thr_emit[c] = tau[c * tau_stride] - 2.f * E;
+  if (sampled) {
+    // tau is a rank statistic of a SAMPLE of the catalog: a heuristic cut, proven per row after rescoring:
+    // an item that was not emitted has approx < thr_emit, hence exact < thr_emit + E = thr_verify
+    thr_emit[c] = tau[c * tau_stride];
+    thr_verify[c] = tau[c * tau_stride] + E;
+  } else {
+    thr_emit[c] = tau[c * tau_stride] - 2.f * E;      // guaranteed: tp distinct items have approx >= tau
+    thr_verify[c] = -INFINITY;
+  }
+}
+
+// Sampled mode: the candidate set of row c is proven complete iff it holds >= tp items and the tp-th best exact score
+// is >= thr_verify[c] (every item that was filtered out scores strictly below that).  Otherwise the row is flagged and
+// redone by the exact path, like a candidate-buffer overflow.
+__global__ void tc_verify_kernel(int64_t C, int tp, const float* __restrict__ out_scores, const int32_t* __restrict__ cand_cnt,
+                                 const float* __restrict__ thr_verify, int32_t* __restrict__ overflow) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float tv = thr_verify[c];
+  if (tv == -INFINITY) return;
+  if (cand_cnt[c] < tp || !(out_scores[c * tp + (tp - 1)] >= tv)) overflow[c] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -461,7 +513,7 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(int kind, const float* 
     float acc = 0.f;
     for (int kc = 0; kc < K; kc += 32) {
       const int kk = kc + lane;
-#pragma unroll 8
+#pragma unroll
       for (int r = 0; r < 32; r++) {
         const int id = __shfl_sync(0xffffffffu, my_id, r);
         tile[r][lane] = (id >= 0 && kk < K) ? __ldg(items + (int64_t)id * K + kk) : 0.f;
@@ -566,42 +618,81 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const TcArgs&
 }
 
 struct TcLayout {   // carve-up of the caller's workspace
-  size_t off_A, off_qinfo, off_gmax, off_tau, off_thr, off_seg, off_segcnt, off_cs, off_ci, off_cc, off_err, total;
+  size_t off_A, off_qinfo, off_gmax, off_tau, off_thr, off_thrv, off_seg, off_segcnt, off_cs, off_ci, off_cc, off_err, total;
   int64_t gmax_stride;
   int n_groups, cap, cap_u, fine;
-  int n_row_blocks, n_tiles, tiles_per_unit, splits, n_units;
+  int n_row_blocks, n_tiles, tiles_per_unit, splits, n_units;      // emission pass (and the max pass when not sampled)
+  int sample_stride, rank_j, s_tiles, s_tiles_per_unit, s_splits, s_units;   // max pass
 };
+
+static void tc_decompose(int n_row_blocks, int n_tiles, int* splits_out, int* tiles_per_unit_out, int* units_out) {
+  // unit = (row block of 128 contexts, contiguous range of item tiles), units are dealt round-robin to one persistent CTA
+  // per SM.  ncu showed the first version (2 units per SM) idle 31 % of the time in a ragged last wave (320 units on
+  // 148 SMs), so the split count is now searched between ~4 and ~12 units per SM for the smallest makespan
+  // ceil(units / SMs) * tiles_per_unit.
+  const int sms = sm_count();
+  int lo = (4 * sms + n_row_blocks - 1) / n_row_blocks, hi = (12 * sms + n_row_blocks - 1) / n_row_blocks;
+  if (lo < 1) lo = 1;
+  if (hi > n_tiles) hi = n_tiles;
+  if (hi > 448) hi = 448;                 // tc_rescore_kernel keeps a prefix of the per-split counts in shared memory
+  if (lo > hi) lo = hi;
+  int64_t best = -1;
+  int best_splits = lo, best_tpu = (n_tiles + lo - 1) / lo;
+  for (int sp = lo; sp <= hi; sp++) {
+    const int tpu = (n_tiles + sp - 1) / sp;
+    const int real = (n_tiles + tpu - 1) / tpu;
+    const int64_t units = (int64_t)n_row_blocks * real;
+    const int64_t span = (units + sms - 1) / sms * tpu;
+    if (best < 0 || span < best) { best = span; best_splits = real; best_tpu = tpu; }
+  }
+  *tiles_per_unit_out = best_tpu;
+  *splits_out = best_splits;
+  *units_out = n_row_blocks * best_splits;
+}
+
+static int tc_sample_stride_env() {
+  const char* e = getenv("HHFM_TOPN_SAMPLE");       // 1 = never sample (two full passes), unset = 8 for large catalogs
+  if (e == nullptr) return 8;
+  const int v = atoi(e);
+  return v < 1 ? 1 : (v > 64 ? 64 : v);
+}
 
 static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
   TcLayout L{};
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const int64_t n_tiles = (N + bn - 1) / bn;
-  L.fine = n_tiles < 4 * (int64_t)tp;                 // small catalogs: one maximum per 32 items for a tight tau
+  L.n_row_blocks = (int)((C + kBM - 1) / kBM);
+  L.n_tiles = (int)n_tiles;
+  tc_decompose(L.n_row_blocks, L.n_tiles, &L.splits, &L.tiles_per_unit, &L.n_units);
+  // Max pass.  Large catalogs: only every `sample_stride`-th item tile is scored and the cut is the rank_j-th largest
+  // 32-item group maximum of that sample, chosen so that ~3.5 tp items of the full catalog pass it (proven per row
+  // afterwards, tc_verify_kernel).  Small catalogs: every tile, tau = tp-th largest group maximum (guaranteed cut).
+  int s = tc_sample_stride_env();
+  int j = (int)((7 * (int64_t)tp + 2 * s - 1) / (2 * s)) + 4;
+  if (s > 1 && (n_tiles / s) * (bn / kGroup) < 8 * (int64_t)j) s = 1;
+  if (j > 1024) s = 1;
+  L.sample_stride = s;
+  L.rank_j = s > 1 ? j : tp;
+  L.s_tiles = (int)((n_tiles + s - 1) / s);
+  L.fine = (s > 1) || n_tiles < 4 * (int64_t)tp;      // one maximum per 32 items for a tight tau
   if (L.fine) {
-    L.n_groups = (int)((N + kGroup - 1) / kGroup);
-    L.gmax_stride = n_tiles * (bn / kGroup);
+    L.n_groups = s > 1 ? L.s_tiles * (bn / kGroup) : (int)((N + kGroup - 1) / kGroup);
+    L.gmax_stride = (int64_t)L.s_tiles * (bn / kGroup);
   } else {
     L.n_groups = (int)n_tiles;
     L.gmax_stride = (n_tiles + 3) / 4 * 4;
   }
-  // work decomposition: unit = (row block of 128 contexts, contiguous range of item tiles); >= 2 units per SM if possible
-  L.n_row_blocks = (int)((C + kBM - 1) / kBM);
-  L.n_tiles = (int)n_tiles;
-  int splits = (2 * sm_count() + L.n_row_blocks - 1) / L.n_row_blocks;
-  if (splits > L.n_tiles) splits = L.n_tiles;
-  if (splits < 1) splits = 1;
-  L.tiles_per_unit = (L.n_tiles + splits - 1) / splits;
-  L.splits = (L.n_tiles + L.tiles_per_unit - 1) / L.tiles_per_unit;
-  L.n_units = L.n_row_blocks * L.splits;
-  L.cap = 4 * tp + 256;                               // survivors per row (expected ~2 tp)
+  tc_decompose(L.n_row_blocks, L.s_tiles, &L.s_splits, &L.s_tiles_per_unit, &L.s_units);
+  L.cap = (s > 1 ? 8 : 4) * tp + 256;                 // survivors per row (expected ~2 tp, ~3.5 tp when sampled)
   L.cap_u = (4 * L.cap) / L.splits + 32;              // per (row, split) segment: 4x the even share + slack
   if (L.cap_u > L.cap) L.cap_u = L.cap;
   size_t o = 0;
   L.off_A = o; o = align(o + (size_t)C * Kp * 2);
   L.off_qinfo = o; o = align(o + (size_t)C * 16);
   L.off_gmax = o; o = align(o + (size_t)C * L.gmax_stride * 4);
-  L.off_tau = o; o = align(o + (size_t)C * tp * 4 * 2);      // select writes [C,tp] scores + ids
+  L.off_tau = o; o = align(o + (size_t)C * L.rank_j * 4 * 2);      // select writes [C,rank_j] scores + ids
   L.off_thr = o; o = align(o + (size_t)C * 4);
+  L.off_thrv = o; o = align(o + (size_t)C * 4);
   L.off_seg = o; o = align(o + (size_t)C * L.splits * L.cap_u * 4);
   L.off_segcnt = o; o = align(o + (size_t)C * L.splits * 4);
   L.off_cs = o; o = align(o + (size_t)C * L.cap * 4);
@@ -620,11 +711,17 @@ static int run_gemm(const TcPlan& p, const CUtensorMap& tA, const CUtensorMap& t
   return launch_tc<4, 128, 2, EMIT>(tA, tB, a, st);
 }
 
-static TcArgs make_tc_args(const TcPlan& p, const TcLayout& L, int64_t C, int64_t N, uint8_t* ws) {
+static TcArgs make_tc_args(const TcPlan& p, const TcLayout& L, int64_t C, int64_t N, uint8_t* ws, bool max_pass) {
   TcArgs a{};
   a.C = C; a.N = N;
-  a.n_row_blocks = L.n_row_blocks; a.n_tiles = L.n_tiles; a.tiles_per_unit = L.tiles_per_unit;
-  a.splits = L.splits; a.n_units = L.n_units;
+  a.n_row_blocks = L.n_row_blocks;
+  if (max_pass) {
+    a.n_tiles = L.s_tiles; a.tiles_per_unit = L.s_tiles_per_unit; a.splits = L.s_splits; a.n_units = L.s_units;
+    a.tile_stride = L.sample_stride;
+  } else {
+    a.n_tiles = L.n_tiles; a.tiles_per_unit = L.tiles_per_unit; a.splits = L.splits; a.n_units = L.n_units;
+    a.tile_stride = 1;
+  }
   a.gmax = reinterpret_cast<float*>(ws + L.off_gmax);
   a.gmax_stride = L.gmax_stride;
   a.fine = L.fine;
@@ -692,7 +789,6 @@ extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, in
   __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws + L.off_A);
   float4* qinfo = reinterpret_cast<float4*>(ws + L.off_qinfo);
   float* tau_sc = reinterpret_cast<float*>(ws + L.off_tau);
-  int32_t* tau_id = reinterpret_cast<int32_t*>(ws + L.off_tau + (size_t)C * tp * 4);
   const int fm = kind == HHFM_QUERY_FM;
   cudaMemsetAsync(ws + L.off_err, 0, sizeof(int), st);
   tc_prep_queries_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(Q, Fc, C, (int)K, p.Kp, fm, A, qinfo);
@@ -701,14 +797,19 @@ extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, in
   CUtensorMap tA, tB;
   if ((rc = make_tmap(&tA, A, C, p.Kp, kBM))) return rc;
   if ((rc = make_tmap(&tB, item_operand, N, p.Kp, p.bn))) return rc;
-  TcArgs a = make_tc_args(p, L, C, N, ws);
-  // GEMM #1: group maxima;  tau_c = tp-th largest;  thresholds;  GEMM #2: emit survivors
-  if ((rc = run_gemm<false>(p, tA, tB, a, st))) return rc;
-  if ((rc = hhfm_topn_select(a.gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, tp, 0, tau_sc, tau_id, stream))) return rc;
-  tc_threshold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, fm, (int)K, tau_sc + (tp - 1), tp, qinfo, stats,
-                                                                  reinterpret_cast<float*>(ws + L.off_thr));
+  // max pass (sampled for large catalogs) -> cut -> emission pass over the whole catalog
+  const int32_t rj = L.rank_j;
+  int32_t* tau_idj = reinterpret_cast<int32_t*>(ws + L.off_tau + (size_t)C * rj * 4);
+  TcArgs a1 = make_tc_args(p, L, C, N, ws, true);
+  if ((rc = run_gemm<false>(p, tA, tB, a1, st))) return rc;
+  if ((rc = hhfm_topn_select(a1.gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, rj, 0, tau_sc, tau_idj, stream))) return rc;
+  tc_threshold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, fm, (int)K, tau_sc + (rj - 1), rj, qinfo, stats,
+                                                                  L.sample_stride > 1 ? 1 : 0,
+                                                                  reinterpret_cast<float*>(ws + L.off_thr),
+                                                                  reinterpret_cast<float*>(ws + L.off_thrv));
   if ((rc = check_launch("tc_threshold_kernel"))) return rc;
-  return run_gemm<true>(p, tA, tB, a, st);
+  TcArgs a2 = make_tc_args(p, L, C, N, ws, false);
+  return run_gemm<true>(p, tA, tB, a2, st);
 }
 
 // Stage 5: exact rescoring of the survivors + final (score desc, id asc) selection.
@@ -735,5 +836,10 @@ extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float
                                                     overflow);
   int rc = check_launch("tc_rescore_kernel");
   if (rc) return rc;
-  return hhfm_topn_select(cs, ci, cc, C, L.cap, L.cap, tp, id_offset, out_scores, out_ids, stream);
+  if (L.sample_stride > 1) HHFM_REQUIRE(out_scores != nullptr, "topn_rescore_merge: out_scores is required (sampled cut verification)");
+  rc = hhfm_topn_select(cs, ci, cc, C, L.cap, L.cap, tp, id_offset, out_scores, out_ids, stream);
+  if (rc || L.sample_stride == 1) return rc;
+  tc_verify_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, tp, out_scores, cc,
+                                                               reinterpret_cast<const float*>(ws + L.off_thrv), overflow);
+  return check_launch("tc_verify_kernel");
 }

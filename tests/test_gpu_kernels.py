@@ -774,3 +774,48 @@ def test_fm_staged_pipeline_with_hot_rows(cuda, monkeypatch):
              *hot.args(True), 0, st())
     hot.fold(gV, gb)
     assert_close(gV.cpu().numpy(), dV, what="fm gV hot staged"); assert_close(gb.cpu().numpy(), db, what="fm gb hot staged")
+
+
+# ----------------------------------------------------------------------------------------------------
+# K6 tensor-core path, sampled cut (large catalogs): the cut is a rank statistic of every 8th item tile, proven per row
+# after rescoring; rows that cannot be proven are redone exactly.  Lists must stay bit-identical.
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,C,N,K,tp", [(0, 130, 120000, 64, 100), (1, 70, 100003, 64, 20), (0, 40, 150000, 128, 100)])
+def test_tensor_core_sampled_cut_is_bit_identical(cuda, kind, C, N, K, tp, monkeypatch):
+    rng = np.random.default_rng(kind + C + K)
+    n_user = 40; M = n_user + N + 50
+    V = make_table(rng, M, K, scale=0.05); b = rng.normal(0, 0.02, (M, 1)).astype(np.float32)
+    F = 4 if kind == 1 else 2
+    A = np.concatenate([rng.integers(0, n_user, (C, 1)), rng.integers(n_user, n_user + N, (C, 1)),
+                        rng.integers(n_user + N, M, (C, F - 2))], axis=1)
+    info = {}
+    ids, sc = _topn(cuda, kind, A, V, b if kind == 1 else None, n_user, N, tp, F - 2 if kind == 1 else 0, 0, method="tc", info=info)
+    assert info["method"] == "tc"
+    ref = O.fm_topk_scores(A, V, b, n_user, N) if kind == 1 else O.dot_topk_scores(V[A[:, 0]], V, n_user, N)
+    want = O.topk_lowest_index(ref, tp)
+    assert (ids == want).all(), "sampled cut changed a top-%d list (%d rows differ)" % (tp, int((ids != want).any(axis=1).sum()))
+    assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
+    assert info["overflow_rows"] <= max(2, C // 20), "the sampled cut should be provable for almost every row"
+    monkeypatch.setenv("HHFM_TOPN_SAMPLE", "1")                      # two full passes, guaranteed cut
+    ids1, sc1 = _topn(cuda, kind, A, V, b if kind == 1 else None, n_user, N, tp, F - 2 if kind == 1 else 0, 0, method="tc")
+    assert (ids1 == ids).all() and (sc1.view(np.int32) == sc.view(np.int32)).all()
+
+
+@pytest.mark.parametrize("where", ["sampled_tiles", "unsampled_tiles"])
+def test_tensor_core_sampled_cut_unrepresentative_sample(cuda, where):
+    """Adversarial catalog order: every high-scoring item sits in the sampled tiles (cut too high: too few survivors, the
+    rows are flagged and redone exactly) or in none of them (cut too low: more survivors / overflow).  Same lists."""
+    rng = np.random.default_rng(5)
+    n_user, N, K, C, tp = 16, 131072, 64, 48, 50
+    M = n_user + N
+    V = make_table(rng, M, K, scale=0.02)
+    tile = (np.arange(N) // 256)
+    boost = (tile % 8 == 0) if where == "sampled_tiles" else (tile % 8 == 3)
+    V[n_user:][boost] *= 6.0
+    A = np.stack([rng.integers(0, n_user, C), rng.integers(n_user, M, C)], axis=1)
+    info = {}
+    ids, sc = _topn(cuda, 0, A, V, None, n_user, N, tp, 0, 0, method="tc", info=info)
+    ref = O.dot_topk_scores(V[A[:, 0]], V, n_user, N)
+    want = O.topk_lowest_index(ref, tp)
+    assert (ids == want).all()
+    assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
