@@ -29,6 +29,7 @@ namespace hhfm {
 constexpr int kGroup = 32;          // items per group maximum (= one tcgen05.ld.32x32b.x32)
 constexpr int kBM = 128;            // contexts per CTA tile (UMMA M)
 constexpr int kKC = 64;             // bf16 elements per 128-byte swizzle row
+constexpr int kTcThreads = 320;     // warps 0-3 and 6-9: epilogue (two per TMEM lane quarter), warp 4: TMA, warp 5: MMA
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -63,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
       __trap();
     }
   }
+}
+__device__ __forceinline__ void bulk_copy_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -239,7 +245,7 @@ struct TcSmem {
 };
 
 template <int NKC, int BN, int STAGES, bool EMIT>
-__global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 128); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
@@ -326,23 +332,28 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue: 4 warps, thread t owns context row t =================
+    // ================= epilogue: 8 warps.  A warp may only touch the TMEM lane quarter (warp % 4), so warps w and w+4
+    // (mod 4) share the 32 context rows of a quarter and split the BN accumulator columns in halves: thread
+    // (quarter, lane, half) owns context row quarter*32+lane for the item columns of its half.  With 4 epilogue warps the
+    // tensor pipe was 42 % (emission) / 69 % (max pass) busy, waiting for the epilogue to drain TMEM. =================
     int acc = 0; uint32_t tph = 0;
-    const int row_in_tile = warp * 32 + lane;
-    constexpr int kChunks = BN / kGroup;
+    const int quarter = warp & 3, half = warp >= 6 ? 1 : 0;
+    const int row_in_tile = quarter * 32 + lane;
+    constexpr int kChunksTile = BN / kGroup;
+    constexpr int kChunks = kChunksTile / 2;        // chunks per thread and tile
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       const int rb = u / a.splits, sp = u % a.splits;
       const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
       const int64_t row = (int64_t)rb * kBM + row_in_tile;
       const float thr = (EMIT && row < a.C) ? __ldg(a.thr_emit + row) : INFINITY;
-      int32_t* seg = EMIT ? a.seg_ids + ((int64_t)row * a.splits + sp) * a.cap_u : nullptr;
+      int32_t* seg = EMIT ? a.seg_ids + (((int64_t)row * a.splits + sp) * 2 + half) * a.cap_u : nullptr;
       int n_emit = 0;
       for (int t = t0; t < t1; t++) {
         mbar_wait(t_full + acc, tph, a.err);
         tc_fence_after();
         float gm[kChunks];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-        const int64_t n_base = (int64_t)t * a.tile_stride * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+        const int64_t n_base = (int64_t)t * a.tile_stride * BN + half * (BN / 2);
         if (!EMIT) {
 #pragma unroll
           for (int c = 0; c < kChunks; c++) {
@@ -411,19 +422,25 @@ __global__ void __launch_bounds__(192, 1) tc_score_kernel(const __grid_constant_
         mbar_arrive(t_empty + acc);
         if (!EMIT && row < a.C) {
           if (a.fine) {
-            float4* dst = reinterpret_cast<float4*>(a.gmax + row * a.gmax_stride + (int64_t)t * kChunks);
+            float* dst = a.gmax + row * a.gmax_stride + (int64_t)t * kChunksTile + half * kChunks;
+            if (kChunks % 4 == 0) {
 #pragma unroll
-            for (int c = 0; c < kChunks; c += 4) dst[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
-          } else {
+              for (int c = 0; c + 3 < kChunks; c += 4)
+                reinterpret_cast<float4*>(dst)[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c + 1 < kChunks; c += 2) reinterpret_cast<float2*>(dst)[c / 2] = make_float2(gm[c], gm[c + 1]);
+            }
+          } else {                                   // one maximum per half tile
             float m = gm[0];
 #pragma unroll
             for (int c = 1; c < kChunks; c++) m = fmaxf(m, gm[c]);
-            a.gmax[row * a.gmax_stride + t] = m;
+            a.gmax[row * a.gmax_stride + 2 * t + half] = m;
           }
         }
         if (++acc == 2) { acc = 0; tph ^= 1; }
       }
-      if (EMIT && row < a.C) a.seg_cnt[row * a.splits + sp] = n_emit;
+      if (EMIT && row < a.C) a.seg_cnt[(row * a.splits + sp) * 2 + half] = n_emit;
     }
   }
   tc_fence_before();
@@ -448,6 +465,104 @@ __global__ void tc_threshold_kernel(int64_t C, int fm, int K, const float* __res
   } else {
     thr_emit[c] = tau[c * tau_stride] - 2.f * E;      // guaranteed: tp distinct items have approx >= tau
     thr_verify[c] = -INFINITY;
+  }
+}
+
+// Sampled mode cut: any value whose rank among the n sampled group maxima is close to j works (the cut is a heuristic
+// that is proven per row afterwards), so instead of an exact radix select this finds the lower edge of the bucket that
+// holds the j-th largest value in a 256-bucket histogram over [min, max], refined (at most twice more) while that
+// bucket holds more than max(4, j/8) values.  The result has rank >= j and < j + max(4, j/8) (or the refinement depth
+// ran out on heavily tied data, which only lowers the cut).  One CTA per row, the row staged in shared memory.
+constexpr int kCutThreads = 128;
+__global__ void __launch_bounds__(kCutThreads) tc_cut_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int n, int j,
+                                                             int fm, int K, const float4* __restrict__ qinfo,
+                                                             const float* __restrict__ stats, float* __restrict__ thr_emit,
+                                                             float* __restrict__ thr_verify) {
+  extern __shared__ float s_val[];                 // n values
+  __shared__ unsigned s_hist[256];
+  __shared__ float s_red[2][kCutThreads / 32];
+  __shared__ float s_lo, s_width;
+  __shared__ int s_need, s_done;
+  const int64_t c = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const float* row = gmax + c * gmax_stride;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int i = t; i < n; i += kCutThreads) {
+    const float v = row[i];
+    s_val[i] = v;
+    if (v > -INFINITY) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if (lane == 0) { s_red[0][w] = mx; s_red[1][w] = mn; }
+  __syncthreads();
+  if (t == 0) {
+    float a = s_red[0][0], b = s_red[1][0];
+    for (int i = 1; i < kCutThreads / 32; i++) { a = fmaxf(a, s_red[0][i]); b = fminf(b, s_red[1][i]); }
+    s_lo = b;
+    s_width = (a - b) * (1.0f / 256.0f);
+    s_need = j;
+    s_done = !(a > b);                               // all equal (or empty): the cut is that value
+  }
+  __syncthreads();
+  for (int level = 0; level < 3 && !s_done; level++) {
+    for (int i = t; i < 256; i += kCutThreads) s_hist[i] = 0u;
+    __syncthreads();
+    const float lo = s_lo, width = s_width, inv = 1.0f / width;
+    for (int i = t; i < n; i += kCutThreads) {
+      const float v = s_val[i];
+      if (v >= lo) {
+        const float f = (v - lo) * inv;
+        // values above the current range were counted by the level before (s_need already excludes them)
+        if (level == 0 || f < 256.0f) atomicAdd(&s_hist[min(255, (int)f)], 1u);
+      }
+    }
+    __syncthreads();
+    if (t < 32) {
+      unsigned h[8], T = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { h[q] = s_hist[t * 8 + q]; T += h[q]; }
+      unsigned S = T;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, S, o);
+        if (t + o < 32) S += v;
+      }
+      const unsigned need = (unsigned)s_need;
+      const unsigned bal = __ballot_sync(0xffffffffu, S >= need);
+      const int target = bal ? 31 - __clz((int)bal) : 0;      // fewer than `need` values in range: take the lowest bucket
+      if (t == target) {
+        unsigned cum = S - T;
+        int bsel = 0;
+        bool done = false;
+#pragma unroll
+        for (int q = 7; q >= 0; q--) {
+          if (!done) {
+            if (q == 0 || cum + h[q] >= need) { bsel = q; done = true; }
+            else cum += h[q];
+          }
+        }
+        const int b = t * 8 + bsel;
+        const unsigned in_bucket = h[0] * (bsel == 0) + h[1] * (bsel == 1) + h[2] * (bsel == 2) + h[3] * (bsel == 3) +
+                                   h[4] * (bsel == 4) + h[5] * (bsel == 5) + h[6] * (bsel == 6) + h[7] * (bsel == 7);
+        const float new_lo = lo + (float)b * width;
+        s_lo = new_lo;
+        s_width = width * (1.0f / 256.0f);
+        s_need = (int)(need > cum ? need - cum : 1);
+        const unsigned limit = (unsigned)max(4, j / 8);
+        if (in_bucket <= limit || !(new_lo + width * (1.0f / 256.0f) > new_lo)) s_done = 1;
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    const float tau = s_lo;
+    const float E = row_error_bound(qinfo[c], stats[0], stats[1], fm, K);
+    thr_emit[c] = tau;
+    thr_verify[c] = tau + E;
   }
 }
 
@@ -540,6 +655,165 @@ __global__ void __launch_bounds__(256) tc_rescore_kernel(int kind, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// exact rescoring, second version: dense candidate lists + a flat work list, then a persistent kernel in which every
+// warp is an independent pipeline over work items (row, batch of 32 candidates): the 32 item rows and the query row(s)
+// of the NEXT item are in flight as bulk copies (cp.async.bulk, one mbarrier per stage) while the current item is
+// scored from shared memory, lane r walking candidate r in ascending k (canonical order, bit-identical to the oracle).
+// The first version took 32 coalesced loads per 32-k chunk with the warp stalled on each group (ncu: long scoreboard
+// 29 stall cycles per issue, 8.5 % of DRAM peak).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_compact_kernel(int nseg, int cap_u, int cap, const int32_t* __restrict__ seg_ids,
+                                                         const int32_t* __restrict__ seg_cnt, int32_t* __restrict__ cand_ids,
+                                                         int32_t* __restrict__ cand_cnt, int32_t* __restrict__ overflow,
+                                                         int32_t* __restrict__ work, int32_t* __restrict__ n_work) {
+  __shared__ int s_off[512];
+  __shared__ int s_warp_tot[4];
+  __shared__ int s_over;
+  const int64_t c = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) s_over = 0;
+  __syncthreads();
+  // exclusive prefix of the clamped segment counts: 4 entries per thread, warp scan, then the 4 warp totals
+  int v[4], sum = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int sgi = t * 4 + q;
+    int n = sgi < nseg ? seg_cnt[c * nseg + sgi] : 0;
+    if (n > cap_u) { n = cap_u; s_over = 1; }
+    v[q] = n;
+    sum += n;
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += x;
+  }
+  if (lane == 31) s_warp_tot[w] = incl;
+  __syncthreads();
+  int base = incl - sum;
+  for (int i = 0; i < w; i++) base += s_warp_tot[i];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int sgi = t * 4 + q;
+    if (sgi < nseg) {
+      const int32_t* src = seg_ids + (c * nseg + sgi) * cap_u;
+      for (int k = 0; k < v[q]; k++)
+        if (base + k < cap) cand_ids[c * cap + base + k] = src[k];
+    }
+    base += v[q];
+  }
+  if (t == 127) {
+    const int total = base;
+    const int cnt = total < cap ? total : cap;
+    cand_cnt[c] = cnt;
+    overflow[c] = (s_over || total > cap) ? 1 : 0;
+    const int nb = (cnt + 31) / 32;
+    const int w0 = atomicAdd(n_work, nb);
+    for (int b = 0; b < nb; b++) work[w0 + b] = (int32_t)((c << 6) | b);
+  }
+}
+
+struct RescoreArgs {
+  int kind;
+  const float* Q;
+  const float* Fc;
+  const float* items;
+  const float* item_bias;
+  int K, cap;
+  const int32_t* cand_ids;
+  const int32_t* cand_cnt;
+  const int32_t* work;
+  const int32_t* n_work;
+  float* cand_scores;
+};
+
+__host__ __device__ inline size_t rescore_stage_bytes(int K, int fm) { return (size_t)(32 + 1 + (fm ? 1 : 0)) * (K + 4) * 4; }
+
+__global__ void __launch_bounds__(256, 1) tc_rescore_staged_kernel(const RescoreArgs a, int warps) {
+  extern __shared__ __align__(128) unsigned char rs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps) return;
+  const int K = a.K, kv = K >> 2, fm = a.kind == HHFM_QUERY_FM, ld = K + 4;
+  const size_t stage_b = rescore_stage_bytes(K, fm);
+  unsigned char* base = rs_smem + (size_t)warp * (2 * stage_b + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * stage_b);
+  if (lane == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncwarp();
+  const int n_work = __ldg(a.n_work);
+  const int tw = gridDim.x * warps;
+  const int gw = blockIdx.x * warps + warp;
+  const uint32_t row_bytes = (uint32_t)K * 4u;
+
+  // software pipeline (registers): the work word two items ahead, the candidate id one item ahead
+  auto load_work = [&](int i) { return i < n_work ? __ldg(a.work + i) : -1; };
+  auto load_id = [&](int wk) {
+    if (wk < 0) return -1;
+    const int64_t row = wk >> 6;
+    const int i = (wk & 63) * 32 + lane;
+    return i < __ldg(a.cand_cnt + row) ? __ldg(a.cand_ids + row * a.cap + i) : -1;
+  };
+  auto issue = [&](int wk, int id, int st) {          // bulk copies of item `wk` into stage st
+    float* sb = reinterpret_cast<float*>(base + (size_t)st * stage_b);
+    const int64_t row = wk >> 6;
+    const unsigned valid = __ballot_sync(0xffffffffu, id >= 0);
+    if (lane == 0) mbar_expect_tx(bars + st, row_bytes * (uint32_t)(__popc(valid) + 1 + fm));
+    __syncwarp();
+    if (id >= 0) bulk_copy_1d(sb + (size_t)(1 + fm + lane) * ld, a.items + (int64_t)id * K, row_bytes, bars + st);
+    if (lane == 0) bulk_copy_1d(sb, a.Q + row * K, row_bytes, bars + st);
+    if (fm && lane == 1) bulk_copy_1d(sb + ld, a.Fc + row * K, row_bytes, bars + st);
+  };
+
+  int wk_cur = load_work(gw);
+  int id_cur = load_id(wk_cur);
+  int wk_next = load_work(gw + tw);
+  if (wk_cur >= 0) issue(wk_cur, id_cur, 0);
+  int id_next = load_id(wk_next);
+  uint32_t phbits = 0u;      // bit st = parity of the next completion of stage st
+  int st = 0;
+  for (int i = gw; i < n_work; i += tw) {
+    const int wk_next2 = load_work(i + 2 * tw);
+    if (wk_next >= 0) issue(wk_next, id_next, st ^ 1);
+    const int id_next2 = load_id(wk_next2);
+    // ---- score item wk_cur from stage st ----
+    mbar_wait(bars + st, (phbits >> st) & 1u, nullptr);
+    phbits ^= 1u << st;
+    const float* sb = reinterpret_cast<const float*>(base + (size_t)st * stage_b);
+    const float4* q4 = reinterpret_cast<const float4*>(sb);
+    const float4* f4 = reinterpret_cast<const float4*>(sb + ld);
+    const float4* r4 = reinterpret_cast<const float4*>(sb + (size_t)(1 + fm + lane) * ld);
+    if (id_cur >= 0) {
+      float acc = 0.f;
+      for (int k4 = 0; k4 < kv; k4++) {
+        const float4 v = r4[k4], q = q4[k4];
+        float4 x = v;
+        if (fm) {
+          const float4 f = f4[k4];
+          x = make_float4(__fadd_rn(v.x, f.x), __fadd_rn(v.y, f.y), __fadd_rn(v.z, f.z), __fadd_rn(v.w, f.w));
+        }
+        const float p0 = __fmul_rn(q.x, x.x);
+        acc = (k4 == 0) ? p0 : __fadd_rn(acc, p0);
+        acc = __fadd_rn(acc, __fmul_rn(q.y, x.y));
+        acc = __fadd_rn(acc, __fmul_rn(q.z, x.z));
+        acc = __fadd_rn(acc, __fmul_rn(q.w, x.w));
+      }
+      const int64_t row = wk_cur >> 6;
+      const int ci = (wk_cur & 63) * 32 + lane;
+      a.cand_scores[row * a.cap + ci] = (fm && a.item_bias) ? __fadd_rn(__ldg(a.item_bias + id_cur), acc) : acc;
+    }
+    __syncwarp();                                   // the stage is re-armed two iterations from now
+    wk_cur = wk_next; id_cur = id_next;
+    wk_next = wk_next2; id_next = id_next2;
+    st ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int round_up(int64_t x, int64_t m) { return (int)((x + m - 1) / m * m); }
@@ -613,12 +887,12 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const TcArgs&
     attr_set = true;
   }
   const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
-  tc_score_kernel<NKC, BN, STAGES, EMIT><<<grid, 192, smem, st>>>(tA, tB, a);
+  tc_score_kernel<NKC, BN, STAGES, EMIT><<<grid, kTcThreads, smem, st>>>(tA, tB, a);
   return check_launch("tc_score_kernel");
 }
 
 struct TcLayout {   // carve-up of the caller's workspace
-  size_t off_A, off_qinfo, off_gmax, off_tau, off_thr, off_thrv, off_seg, off_segcnt, off_cs, off_ci, off_cc, off_err, total;
+  size_t off_A, off_qinfo, off_gmax, off_tau, off_thr, off_thrv, off_seg, off_segcnt, off_cs, off_ci, off_cc, off_work, off_nwork, off_err, total;
   int64_t gmax_stride;
   int n_groups, cap, cap_u, fine;
   int n_row_blocks, n_tiles, tiles_per_unit, splits, n_units;      // emission pass (and the max pass when not sampled)
@@ -634,7 +908,7 @@ static void tc_decompose(int n_row_blocks, int n_tiles, int* splits_out, int* ti
   int lo = (4 * sms + n_row_blocks - 1) / n_row_blocks, hi = (12 * sms + n_row_blocks - 1) / n_row_blocks;
   if (lo < 1) lo = 1;
   if (hi > n_tiles) hi = n_tiles;
-  if (hi > 448) hi = 448;                 // tc_rescore_kernel keeps a prefix of the per-split counts in shared memory
+  if (hi > 224) hi = 224;                 // tc_rescore_kernel keeps a prefix of the 2*splits segment counts in shared memory
   if (lo > hi) lo = hi;
   int64_t best = -1;
   int best_splits = lo, best_tpu = (n_tiles + lo - 1) / lo;
@@ -679,12 +953,12 @@ static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
     L.n_groups = s > 1 ? L.s_tiles * (bn / kGroup) : (int)((N + kGroup - 1) / kGroup);
     L.gmax_stride = (int64_t)L.s_tiles * (bn / kGroup);
   } else {
-    L.n_groups = (int)n_tiles;
-    L.gmax_stride = (n_tiles + 3) / 4 * 4;
+    L.n_groups = 2 * (int)n_tiles;                    // one maximum per half tile
+    L.gmax_stride = (2 * n_tiles + 3) / 4 * 4;
   }
   tc_decompose(L.n_row_blocks, L.s_tiles, &L.s_splits, &L.s_tiles_per_unit, &L.s_units);
   L.cap = (s > 1 ? 8 : 4) * tp + 256;                 // survivors per row (expected ~2 tp, ~3.5 tp when sampled)
-  L.cap_u = (4 * L.cap) / L.splits + 32;              // per (row, split) segment: 4x the even share + slack
+  L.cap_u = (4 * L.cap) / (2 * L.splits) + 32;        // per (row, split, column half) segment: 4x the even share + slack
   if (L.cap_u > L.cap) L.cap_u = L.cap;
   size_t o = 0;
   L.off_A = o; o = align(o + (size_t)C * Kp * 2);
@@ -693,11 +967,13 @@ static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
   L.off_tau = o; o = align(o + (size_t)C * L.rank_j * 4 * 2);      // select writes [C,rank_j] scores + ids
   L.off_thr = o; o = align(o + (size_t)C * 4);
   L.off_thrv = o; o = align(o + (size_t)C * 4);
-  L.off_seg = o; o = align(o + (size_t)C * L.splits * L.cap_u * 4);
-  L.off_segcnt = o; o = align(o + (size_t)C * L.splits * 4);
+  L.off_seg = o; o = align(o + (size_t)C * 2 * L.splits * L.cap_u * 4);
+  L.off_segcnt = o; o = align(o + (size_t)C * 2 * L.splits * 4);
   L.off_cs = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_ci = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_cc = o; o = align(o + (size_t)C * 4);
+  L.off_work = o; o = align(o + (size_t)C * ((L.cap + 31) / 32) * 4);
+  L.off_nwork = o; o = align(o + 256);
   L.off_err = o; o = align(o + 256);
   L.total = o;
   return L;
@@ -802,12 +1078,21 @@ extern "C" int hhfm_topn_score(int32_t kind, const float* Q, const float* Fc, in
   int32_t* tau_idj = reinterpret_cast<int32_t*>(ws + L.off_tau + (size_t)C * rj * 4);
   TcArgs a1 = make_tc_args(p, L, C, N, ws, true);
   if ((rc = run_gemm<false>(p, tA, tB, a1, st))) return rc;
-  if ((rc = hhfm_topn_select(a1.gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, rj, 0, tau_sc, tau_idj, stream))) return rc;
-  tc_threshold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, fm, (int)K, tau_sc + (rj - 1), rj, qinfo, stats,
-                                                                  L.sample_stride > 1 ? 1 : 0,
-                                                                  reinterpret_cast<float*>(ws + L.off_thr),
-                                                                  reinterpret_cast<float*>(ws + L.off_thrv));
-  if ((rc = check_launch("tc_threshold_kernel"))) return rc;
+  if (L.sample_stride > 1 && (size_t)L.n_groups * 4 <= 96 * 1024) {
+    const size_t smem = (size_t)L.n_groups * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(tc_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_cut_kernel<<<(unsigned)C, kCutThreads, smem, st>>>(a1.gmax, L.gmax_stride, L.n_groups, rj, fm, (int)K, qinfo, stats,
+                                                         reinterpret_cast<float*>(ws + L.off_thr),
+                                                         reinterpret_cast<float*>(ws + L.off_thrv));
+    if ((rc = check_launch("tc_cut_kernel"))) return rc;
+  } else {
+    if ((rc = hhfm_topn_select(a1.gmax, nullptr, nullptr, C, L.gmax_stride, L.n_groups, rj, 0, tau_sc, tau_idj, stream))) return rc;
+    tc_threshold_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(C, fm, (int)K, tau_sc + (rj - 1), rj, qinfo, stats,
+                                                                    L.sample_stride > 1 ? 1 : 0,
+                                                                    reinterpret_cast<float*>(ws + L.off_thr),
+                                                                    reinterpret_cast<float*>(ws + L.off_thrv));
+    if ((rc = check_launch("tc_threshold_kernel"))) return rc;
+  }
   TcArgs a2 = make_tc_args(p, L, C, N, ws, false);
   return run_gemm<true>(p, tA, tB, a2, st);
 }
@@ -828,13 +1113,36 @@ extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float
   int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
   int32_t* cc = reinterpret_cast<int32_t*>(ws + L.off_cc);
   const int fm = kind == HHFM_QUERY_FM;
-  const size_t smem = (size_t)K * (fm ? 2 : 1) * sizeof(float);
-  HHFM_REQUIRE(L.splits <= 511, "topn_rescore_merge: too many item splits");
-  tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, L.splits, L.cap_u,
-                                                    reinterpret_cast<const int32_t*>(ws + L.off_seg),
-                                                    reinterpret_cast<const int32_t*>(ws + L.off_segcnt), L.cap, cs, ci, cc,
-                                                    overflow);
-  int rc = check_launch("tc_rescore_kernel");
+  HHFM_REQUIRE(2 * L.splits <= 511, "topn_rescore_merge: too many item splits");
+  int rc;
+  const size_t stage_b = rescore_stage_bytes((int)K, fm);
+  if (K % 4 == 0 && (((uintptr_t)items | (uintptr_t)Q | (uintptr_t)Fc) & 15) == 0 && 2 * stage_b + 128 <= (size_t)200 * 1024 &&
+      L.cap <= 2048) {
+    int32_t* n_work = reinterpret_cast<int32_t*>(ws + L.off_nwork);
+    cudaMemsetAsync(n_work, 0, sizeof(int32_t), st);
+    tc_compact_kernel<<<(unsigned)C, 128, 0, st>>>(2 * L.splits, L.cap_u, L.cap, reinterpret_cast<const int32_t*>(ws + L.off_seg),
+                                                  reinterpret_cast<const int32_t*>(ws + L.off_segcnt), ci, cc, overflow,
+                                                  reinterpret_cast<int32_t*>(ws + L.off_work), n_work);
+    if ((rc = check_launch("tc_compact_kernel"))) return rc;
+    int warps = (int)(((size_t)200 * 1024) / (2 * stage_b + 128));
+    if (warps > 8) warps = 8;
+    const size_t smem = (size_t)warps * (2 * stage_b + 128);
+    if (cudaFuncSetAttribute(tc_rescore_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("tc_rescore_staged_kernel: cannot reserve %d bytes of shared memory", (int)smem);
+      return HHFM_ERR_LAUNCH;
+    }
+    RescoreArgs ra{kind, Q, Fc, items, fm ? item_bias : nullptr, (int)K, L.cap, ci, cc,
+                   reinterpret_cast<const int32_t*>(ws + L.off_work), n_work, cs};
+    tc_rescore_staged_kernel<<<sm_count(), warps * 32, smem, st>>>(ra, warps);
+    rc = check_launch("tc_rescore_staged_kernel");
+  } else {
+    const size_t smem = (size_t)K * (fm ? 2 : 1) * sizeof(float);
+    tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, 2 * L.splits, L.cap_u,
+                                                      reinterpret_cast<const int32_t*>(ws + L.off_seg),
+                                                      reinterpret_cast<const int32_t*>(ws + L.off_segcnt), L.cap, cs, ci, cc,
+                                                      overflow);
+    rc = check_launch("tc_rescore_kernel");
+  }
   if (rc) return rc;
   if (L.sample_stride > 1) HHFM_REQUIRE(out_scores != nullptr, "topn_rescore_merge: out_scores is required (sampled cut verification)");
   rc = hhfm_topn_select(cs, ci, cc, C, L.cap, L.cap, tp, id_offset, out_scores, out_ids, stream);
