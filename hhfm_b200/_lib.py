@@ -19,6 +19,7 @@ SIGNATURES = {
     "hhfm_pack_ids_i32": [vp, i64, i64, i64, vp, i64, i64, i64, cint],
     "hhfm_pack_fill_i32": [vp, i64, i64, i64, i64, i32, cint],
     "hhfm_pack_csr_i64": [vp, vp, i64, i64, i64, vp, vp, vp, i64, cint],
+    "hhfm_pack_upload_records": [vp, i32, i64, i64, i64, vp, vp, vp, i32, vp],
     "hhfm_fm_fwd": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp],
     "hhfm_fm_fwd_bwd_sqloss": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp,
                                vp, vp, vp, vp, i32, i32, i32, vp],
@@ -54,6 +55,7 @@ SIGNATURES = {
 INT64_FUNCS = {
     "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
+    "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
     "hhfm_dfm_param_count": [i64, i64, i32, vp],
     "hhfm_dfm_reg_count": [i64, i64, i32, vp],
     "hhfm_workspace_bytes_dfm": [i64, i64, i64, i32, vp],

@@ -2,9 +2,14 @@
 // Packers replace the numpy slicing that builds `feed_dict` batches (FM.py:251-256, OurModel7.py:373-385):
 // id columns are narrowed to int32 and laid out as 16-byte aligned per-sample records in (pinned) host
 // memory, ready for one cudaMemcpyAsync.  Plain std::thread fan-out; no device work here.
+#include <pthread.h>
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -88,6 +93,115 @@ static int pack_ids(const T* src, int64_t rows, int64_t cols, int64_t src_row_st
   return HHFM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent worker pool for the pipelined packer (thread creation per call costs more than packing a chunk).
+// Not fork-safe by itself: the child of a fork() gets a fresh pool (pthread_atfork).
+// ---------------------------------------------------------------------------------------------------------------
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n) {
+    for (int i = 0; i < n_; i++) th_.emplace_back([this, i] { loop(i); });
+  }
+  int size() const { return n_; }
+  // run fn(worker) on every worker and wait
+  void run(const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> serial(run_mu_);      // one parallel region at a time
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn;
+    pending_ = n_;
+    gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* f;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        f = fn_;
+      }
+      (*f)(id);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+};
+
+static Pool* g_pool = nullptr;
+static std::mutex g_pool_mu;
+static void pool_forget() { g_pool = nullptr; new (&g_pool_mu) std::mutex(); }   // child after fork(): threads are gone
+
+static Pool* get_pool(int nthreads) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool == nullptr) {
+    static bool hooked = false;
+    if (!hooked) { pthread_atfork(nullptr, nullptr, pool_forget); hooked = true; }
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    g_pool = new Pool(nthreads);      // lives for the process (workers block on a condition variable when idle)
+  }
+  return g_pool;
+}
+
+// uint16 wire records -> int32 device records (0xFFFF = padding -> -1)
+__global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const uint2 v = *reinterpret_cast<const uint2*>(src + i);
+    int4 o;
+    o.x = (int)(v.x & 0xFFFFu); o.y = (int)(v.x >> 16); o.z = (int)(v.y & 0xFFFFu); o.w = (int)(v.y >> 16);
+    o.x = o.x == 0xFFFF ? -1 : o.x; o.y = o.y == 0xFFFF ? -1 : o.y; o.z = o.z == 0xFFFF ? -1 : o.z; o.w = o.w == 0xFFFF ? -1 : o.w;
+    *reinterpret_cast<int4*>(dst + i) = o;
+  } else {
+    for (int64_t k = i; k < n; k++) { const int v = src[k]; dst[k] = v == 0xFFFF ? -1 : v; }
+  }
+}
+
+template <typename D>
+static inline void pack_row_block(const hhfm_pack_part* parts, int n_parts, int64_t r0, int64_t r1, D* dst, int64_t stride,
+                                  int64_t width, int64_t id_limit, std::atomic<int64_t>& bad) {
+  const D pad = (D)-1;          // int32: -1, uint16: 0xFFFF
+  for (int64_t r = r0; r < r1; r++) {
+    D* d = dst + r * stride;
+    for (int p = 0; p < n_parts; p++) {
+      const hhfm_pack_part& pt = parts[p];
+      if (pt.elem_bytes == 8) {
+        const int64_t* s = reinterpret_cast<const int64_t*>(pt.data) + r * pt.row_stride;
+        for (int64_t c = 0; c < pt.cols; c++) {
+          const int64_t v = s[c];
+          if (v < 0 || v >= id_limit) bad.store(r);
+          d[c] = (D)v;
+        }
+      } else {
+        const int32_t* s = reinterpret_cast<const int32_t*>(pt.data) + r * pt.row_stride;
+        for (int64_t c = 0; c < pt.cols; c++) {
+          const int64_t v = s[c];
+          if (v < 0 || v >= id_limit) bad.store(r);
+          d[c] = (D)v;
+        }
+      }
+      d += pt.cols;
+    }
+    for (int64_t c = width; c < stride; c++) dst[r * stride + c] = pad;
+  }
+}
+
 }  // namespace hhfm
 
 using namespace hhfm;
@@ -131,5 +245,65 @@ extern "C" int hhfm_pack_csr_i64(const int64_t* src, const float* src_val, int64
     parallel_rows(rows, nthreads, [&](int64_t a, int64_t b) {
       for (int64_t r = a; r < b; r++) std::memcpy(val + r * cols, src_val + r * src_row_stride, sizeof(float) * cols);
     });
+  return HHFM_OK;
+}
+
+extern "C" int64_t hhfm_pack_upload_staging_bytes(int64_t rows, int64_t stride, int64_t id_limit) {
+  return rows * stride * (id_limit <= 65535 ? 2 : 4);
+}
+
+extern "C" int hhfm_pack_upload_records(const hhfm_pack_part* parts, int32_t n_parts, int64_t rows, int64_t stride,
+                                        int64_t id_limit, void* host_staging, void* dev_staging, int32_t* dev_records,
+                                        int32_t nthreads, hhfm_stream_t stream) {
+  HHFM_REQUIRE(parts && n_parts >= 1 && host_staging && dev_records, "pack_upload_records: NULL argument");
+  HHFM_REQUIRE(rows >= 0 && stride >= 1 && id_limit >= 1, "pack_upload_records: bad sizes");
+  int64_t width = 0;
+  for (int p = 0; p < n_parts; p++) {
+    HHFM_REQUIRE(parts[p].data && parts[p].cols >= 0 && parts[p].row_stride >= parts[p].cols &&
+                     (parts[p].elem_bytes == 8 || parts[p].elem_bytes == 4),
+                 "pack_upload_records: bad part %d", p);
+    width += parts[p].cols;
+  }
+  HHFM_REQUIRE(width <= stride, "pack_upload_records: stride %lld < total width %lld", (long long)stride, (long long)width);
+  if (rows == 0) return HHFM_OK;
+  const bool narrow = id_limit <= 65535;           // 0xFFFF is the padding code
+  HHFM_REQUIRE(!narrow || dev_staging, "pack_upload_records: the 16-bit wire format needs dev_staging");
+  cudaStream_t st = (cudaStream_t)stream;
+  Pool* pool = get_pool(nthreads);
+  const int nt = pool->size();
+  // chunk so that the H2D copy of chunk i overlaps the packing of chunk i+1 (>= 64K rows per chunk, <= 16 chunks)
+  int64_t n_chunks = rows / (64 * 1024);
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 16) n_chunks = 16;
+  const int64_t chunk = (rows + n_chunks - 1) / n_chunks;
+  std::atomic<int64_t> bad{-1};
+  const size_t esz = narrow ? 2 : 4;
+  for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
+    const int64_t c1 = std::min(rows, c0 + chunk);
+    const int64_t per = (c1 - c0 + nt - 1) / nt;
+    const std::function<void(int)> job = [&](int w) {
+      const int64_t a = c0 + (int64_t)w * per, b = std::min(c1, a + per);
+      if (a >= b) return;
+      if (narrow) pack_row_block<uint16_t>(parts, n_parts, a, b, reinterpret_cast<uint16_t*>(host_staging), stride, width, id_limit, bad);
+      else pack_row_block<int32_t>(parts, n_parts, a, b, reinterpret_cast<int32_t*>(host_staging), stride, width, id_limit, bad);
+    };
+    pool->run(job);
+    if (bad.load() >= 0) break;
+    const size_t off = (size_t)c0 * stride * esz, bytes = (size_t)(c1 - c0) * stride * esz;
+    void* dst = narrow ? (void*)((char*)dev_staging + off) : (void*)((char*)dev_records + off);
+    if (cudaMemcpyAsync(dst, (const char*)host_staging + off, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      set_error("pack_upload_records: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return HHFM_ERR_LAUNCH;
+    }
+  }
+  if (bad.load() >= 0) {
+    set_error("pack_ids: id out of range [0,%lld) in row %lld", (long long)id_limit, (long long)bad.load());
+    return HHFM_ERR_BAD_ARG;
+  }
+  if (narrow) {
+    const int64_t n = rows * stride;
+    widen_u16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dev_staging), dev_records, n);
+    return check_launch("widen_u16_kernel");
+  }
   return HHFM_OK;
 }

@@ -116,6 +116,56 @@ def pack_records(parts, id_limit, staging: Staging, align=4):
     return host.view(B, stride), stride
 
 
+class PackPart(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("cols", C.c_int64), ("row_stride", C.c_int64), ("elem_bytes", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class RecordUploader:
+    """Host id blocks -> int32 device records through `hhfm_pack_upload_records`: a persistent host thread pool packs
+    chunk i+1 while chunk i crosses PCIe; uint16 wire format when every id fits (id_limit <= 65535)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.host = None
+        self.dev_stage = None
+        self.dev = None
+        self._busy = None          # event recorded after the last upload: the pinned staging is free once it has passed
+
+    def upload(self, parts, id_limit, align=4):
+        parts = [_as_2d_ids(p) for p in parts if p is not None]
+        B = parts[0].shape[0]
+        for p in parts:
+            if p.shape[0] != B:
+                raise ValueError("upload: blocks disagree on the number of rows")
+        width = sum(p.shape[1] for p in parts)
+        stride = _round_up(max(width, 1), align)
+        lib = _lib.load()
+        nbytes = int(lib.hhfm_pack_upload_staging_bytes(B, stride, id_limit))
+        if self.host is None or self.host.numel() < nbytes:
+            cap = max(nbytes, 4096)
+            self.host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            self.dev_stage = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        if self.dev is None or self.dev.numel() < B * stride:
+            self.dev = torch.empty(max(B * stride, 1024), dtype=torch.int32, device=self.device)
+        if B == 0:
+            return self.dev[:0].view(0, stride), stride
+        if self._busy is not None:
+            self._busy.synchronize()
+        arr = (PackPart * len(parts))()
+        for i, p in enumerate(parts):
+            arr[i].data = p.ctypes.data
+            arr[i].cols = p.shape[1]
+            arr[i].row_stride = p.strides[0] // p.itemsize
+            arr[i].elem_bytes = p.itemsize
+        _lib.call("hhfm_pack_upload_records", C.cast(arr, C.c_void_p), len(parts), B, stride, id_limit, ptr(self.host),
+                  ptr(self.dev_stage), ptr(self.dev), _NTHREADS, cur_stream())
+        if self._busy is None:
+            self._busy = torch.cuda.Event()
+        self._busy.record()
+        return self.dev[:B * stride].view(B, stride), stride
+
+
 # --------------------------------------------------------------------------------------------------
 # K5: optimizers with TF-1.x semantics
 # --------------------------------------------------------------------------------------------------

@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import (NO_HOT, NO_HOT_BIAS, POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_USER, HotRows, Optimizer, Staging, TopN,
-                     TouchTracker, cur_stream, pack_records, ptr, require_cuda)
+from .engine import (NO_HOT, NO_HOT_BIAS, POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_USER, HotRows, Optimizer, RecordUploader, Staging,
+                     TopN, TouchTracker, cur_stream, pack_records, ptr, require_cuda)
 
 
 class Handle:
@@ -73,6 +73,7 @@ class _Base:
         self._lamda = float(lamda)
         self._touch = TouchTracker(self._M, self.device)
         self._idx_stage = Staging(torch.int32, self.device)
+        self._uploader = RecordUploader(self.device)
         self._f32_stage = Staging(torch.float32, self.device)
         self._topn = TopN(self.device)
         self._dp_group = None
@@ -174,13 +175,10 @@ class _Base:
         return float(self._loss_host[0])
 
     def _upload_rows(self, X):
-        host, stride = pack_records([np.asarray(X)], self._M, self._idx_stage, align=1)
-        return self._idx_stage.upload(host.numel()).view(-1, stride)
+        return self._uploader.upload([np.asarray(X)], self._M, align=1)[0]
 
     def _upload_ids(self, parts):
-        host, stride = pack_records(parts, self._M, self._idx_stage)
-        dev = self._idx_stage.upload(host.numel()).view(host.shape[0], stride)
-        return dev, stride
+        return self._uploader.upload(parts, self._M)
 
     def _upload_f32(self, arr):
         arr = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(-1))
@@ -246,8 +244,7 @@ class FM(_Base):
     def predict(self, X):
         X = np.asarray(X)
         F = X.shape[1]
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(X)
         B = idx.shape[0]
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, F, ptr(self.weights["feature_embeddings"]),
@@ -347,8 +344,7 @@ class MF(FM):
         self._b0 = None
 
     def predict(self, X):
-        host, stride = pack_records([np.asarray(X)[:, :2]], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(np.asarray(X)[:, :2])
         B = idx.shape[0]
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, 2, ptr(self.weights["feature_embeddings"]), None, None,
@@ -590,8 +586,7 @@ class AFM(FM):
 
     def predict(self, X):
         X = np.asarray(X)
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(X)
         return self._predict_dev(idx).cpu().numpy().reshape(-1, 1)
 
     def _predict_dev(self, idx):
@@ -750,8 +745,7 @@ class DeepFM(_Base):
 
     def predict(self, X):
         X = np.asarray(X)
-        host, stride = pack_records([X], self._M, self._idx_stage, align=1)
-        idx = self._idx_stage.upload(host.numel()).view(-1, stride)
+        idx = self._upload_rows(X)
         return self._forward_dev(idx).cpu().numpy().reshape(-1, 1)
 
     def partial_fit(self, data):

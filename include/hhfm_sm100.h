@@ -76,6 +76,26 @@ int hhfm_pack_fill_i32(int32_t* dst, int64_t rows, int64_t cols, int64_t dst_row
 int hhfm_pack_csr_i64(const int64_t* src, const float* src_val, int64_t rows, int64_t cols, int64_t src_row_stride,
                       int32_t* row_ptr, int32_t* col, float* val, int64_t id_limit, int nthreads);
 
+/* Fused, pipelined packer + upload (the path Model.partial_fit uses): the id blocks `parts` (column groups of one batch,
+ * int64 or int32, e.g. X | F1 | Y of OurModel7.py:374-385) are narrowed and interleaved into [rows, stride] records
+ * (padding = -1) by a persistent host thread pool, chunk by chunk, and every finished chunk is sent with
+ * cudaMemcpyAsync on `stream` while the next one is being packed.  When id_limit <= 65535 the wire format is uint16
+ * (half the PCIe bytes) and a device kernel widens it into the int32 records the kernels read.
+ *   host_staging: pinned host memory, hhfm_pack_upload_staging_bytes() bytes; dev_staging: device scratch of the same
+ *   size (only used by the 16-bit format, may be NULL otherwise); dev_records: int32 [rows, stride] on the device.
+ * Stream-ordered: returns after the last copy is enqueued; host_staging may be reused after the stream passes it. */
+typedef struct hhfm_pack_part {
+  const void* data;      /* [rows, cols] ids, row-major */
+  int64_t cols;
+  int64_t row_stride;    /* elements between consecutive rows */
+  int32_t elem_bytes;    /* 8 = int64, 4 = int32 */
+  int32_t reserved;
+} hhfm_pack_part;
+int64_t hhfm_pack_upload_staging_bytes(int64_t rows, int64_t stride, int64_t id_limit);
+int hhfm_pack_upload_records(const hhfm_pack_part* parts, int32_t n_parts, int64_t rows, int64_t stride, int64_t id_limit,
+                             void* host_staging, void* dev_staging, int32_t* dev_records, int32_t nthreads,
+                             hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  FM / MF: gather + second-order interaction (+ squared loss + backward scatter)
  *   out[s] = sum_k 0.5((sum_f e_f)^2 - sum_f e_f^2) + sum_f val_f*bias[x_f] + b0,  e_f = val_f * V[x_f]

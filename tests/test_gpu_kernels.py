@@ -819,3 +819,33 @@ def test_tensor_core_sampled_cut_unrepresentative_sample(cuda, where):
     want = O.topk_lowest_index(ref, tp)
     assert (ids == want).all()
     assert (sc.view(np.int32) == np.take_along_axis(ref, want, axis=1).view(np.int32)).all()
+
+
+# ----------------------------------------------------------------------------------------------------
+# K0 pipelined pack + upload (uint16 wire format when every id fits, int32 otherwise)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("id_limit,rows", [(5382, 200001), (65535, 70000), (65536, 70000), (10_000_000, 150000), (300, 5), (300, 0)])
+def test_pack_upload_records_matches_the_host_packer(cuda, id_limit, rows):
+    from hhfm_b200.engine import RecordUploader, Staging, pack_records
+    from hhfm_b200 import _lib
+    rng = np.random.default_rng(rows + id_limit)
+    X = rng.integers(0, id_limit, (rows, 2)).astype(np.int64)
+    F1 = rng.integers(0, id_limit, (rows, 8)).astype(np.int32)                 # int32 block
+    Y = np.ascontiguousarray(rng.integers(0, id_limit, (rows, 13)).astype(np.int64))[:, :10]   # strided view
+    if rows:
+        X[-1, 1] = id_limit - 1
+    up = RecordUploader(cuda)
+    recs, stride = up.upload([X, F1, Y], id_limit)
+    if rows == 0:
+        assert stride == 20 and recs.shape == (0, 20)
+        return
+    host, stride2 = pack_records([X, F1, Y], id_limit, Staging(torch.int32))
+    assert stride == stride2 == 20 and recs.shape == (rows, 20)
+    assert (recs.cpu().numpy() == host.numpy().reshape(rows, 20)).all()
+    recs3, stride3 = up.upload([X[:, :1], F1[:, :2]], id_limit)               # width 3 -> stride 4, one padding column
+    if rows:
+        got = recs3.cpu().numpy()
+        assert stride3 == 4 and (got[:, 3] == -1).all() and (got[:, 0] == X[:, 0]).all() and (got[:, 1:3] == F1[:, :2]).all()
+        Xbad = X.copy(); Xbad[rows // 2, 0] = id_limit
+        with pytest.raises(_lib.HhfmError, match="out of range"):
+            up.upload([Xbad, F1, Y], id_limit)
