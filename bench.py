@@ -241,7 +241,7 @@ def run_topn(world, rank, dev, quick):
     import torch.distributed as dist
     from hhfm_b200 import dist as hd
     from hhfm_b200.engine import TopN
-    C, N, K, tp, n_user = (2048, 200000, 128, 100, 1024) if quick else (8192, 1000000, 128, 100, 1024)
+    C, N, K, tp, n_user = (2048, 200000, 128, 100, 1024) if quick else (16384, 1000000, 128, 100, 1024)
     g = torch.Generator(device="cpu").manual_seed(4321 + rank)
     M = n_user + N
     V = torch.empty(M, K).normal_(0, 0.01, generator=g).to(dev)
@@ -288,8 +288,9 @@ def run_topn(world, rank, dev, quick):
                        "contexts": C, "items_per_gpu": N, "K": K, "tp": tp, "item_sharding": "N per GPU, all-gather merge"},
             "overflow_rows": t.last_overflow_rows,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "note": "algorithmic 2*K flop per pair over the WHOLE pipeline (query prep, 2 GEMM passes, threshold "
-                                 "select, exact rescoring, final select); the GEMM kernel alone: see profiles/"}}
+                         "note": "algorithmic 2*K flop per pair over the WHOLE pipeline (query prep, sampled max pass, cut, "
+                                 "emission GEMM, candidate compaction, exact rescoring, final select, proof of the cut); "
+                                 "peak = sustained cuBLAS bf16 (MEASURED_PEAKS.json); the GEMM kernel alone: see profiles/"}}
 
 
 def workload_config(batch, n_gpus):
@@ -377,6 +378,8 @@ def run_ours(args):
     t_start.record()
     for i in range(args.steps):
         device_step(args.warmup + i, timed_idx=i)
+        if rank == 0 and i % 5 == 4:
+            sampler.sample()             # the launch loop runs ahead of the GPU, so these samples are taken under load
     t_end.record()
     if rank == 0:
         sampler.sample()                 # the queue is still draining here: at least one sample under load
@@ -406,6 +409,19 @@ def run_ours(args):
     del dev_batches, host_batches
     torch.cuda.empty_cache()
     topn = None if args.no_topn else run_topn(world, rank, dev, args.quick)
+    models = None
+    if world == 1 and not args.quick and not args.no_models:
+        # the other BASELINE.json configs (device-resident batches, whole step): scaled FM c5 is the HBM-bound one
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_models as bm
+        margs = argparse.Namespace(steps=10)
+        models = {}
+        for name in ("fm_c1", "fm_c5", "bpr_c4", "afm_c3", "dfm"):
+            try:
+                models[name] = bm.RUNNERS[name](margs, dev)
+            except Exception as e:                      # a secondary line must not take the headline line down
+                models[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -433,6 +449,8 @@ def run_ours(args):
         }
         if topn is not None:
             line["topn"] = topn
+        if models is not None:
+            line["models"] = models
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))
@@ -449,6 +467,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="positives per GPU per step")
     ap.add_argument("--no-hot", dest="no_hot", action="store_true", help="disable the two-level hot-row scatter")
     ap.add_argument("--no-topn", dest="no_topn", action="store_true", help="skip the top-N half of the metric")
+    ap.add_argument("--no-models", dest="no_models", action="store_true", help="skip the per-model secondary lines")
     ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
