@@ -120,7 +120,8 @@ class ClockSampler:
                 self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 self.reason_bits |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            self.power.append(self.nvml.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            if len(self.sm) % 4 == 1:                    # NVML queries take milliseconds: keep the sample cheap
+                self.power.append(self.nvml.nvmlDeviceGetPowerUsage(self.h) / 1e3)
         except Exception:
             pass
 
@@ -353,10 +354,9 @@ def run_ours(args):
             ev[2 * timed_idx + 1].record()
         if hot is not None:
             hot.fold(model._gV, None)
-        model._allreduce_grads()
-        model._opt.apply_dense("feature_embeddings", V, model._gV, LAMDA, model._sq_partials)
-        _lib.call("hhfm_loss_finalize", ptr(model._loss_partials), ptr(model._sq_partials), 0.5 * LAMDA,
-                  ptr(model._loss_dev), cur_stream())
+        model._allreduce_grads()             # NVLink peer-arena barrier (the optimizer sums the peers' arenas) or NCCL
+        with_reg = model._apply_table(sparse_ok=True)
+        model._enqueue_loss(with_reg)
 
     def barrier():
         if world > 1:
@@ -378,8 +378,6 @@ def run_ours(args):
     t_start.record()
     for i in range(args.steps):
         device_step(args.warmup + i, timed_idx=i)
-        if rank == 0 and i % 5 == 4:
-            sampler.sample()             # the launch loop runs ahead of the GPU, so these samples are taken under load
     t_end.record()
     if rank == 0:
         sampler.sample()                 # the queue is still draining here: at least one sample under load

@@ -42,6 +42,13 @@ SIGNATURES = {
     "hhfm_opt_momentum_rows": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp],
     "hhfm_opt_sgd_rows": [vp, vp, vp, vp, i64, i64, f32, i32, vp],
     "hhfm_loss_finalize": [vp, vp, f32, vp, vp],
+    "hhfm_p2p_alloc": [i64, vp, vp],
+    "hhfm_p2p_open": [vp, vp],
+    "hhfm_p2p_close": [vp],
+    "hhfm_p2p_free": [vp],
+    "hhfm_p2p_barrier": [vp, i32, i32, i32, vp],
+    "hhfm_opt_dense_l2_p2p": [i32, vp, vp, vp, vp, i32, vp, i64, f32, f32, f32, f32, f32, vp, vp],
+    "hhfm_loss_finalize_p2p": [vp, i32, vp, f32, vp, vp],
     "hhfm_hot_fold": [vp, vp, i32, i32, i64, vp, vp, vp, vp],
     "hhfm_topn_build_query": [i32, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],

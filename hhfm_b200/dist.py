@@ -6,8 +6,9 @@
              local top-tp with GLOBAL ids, all-gather of [C, tp] (score, id), and a merge under the comparator
              (score desc, id asc) -- the lists are bit-identical to a single-GPU run.
 
-Works on whatever device the tensors live on (NCCL for CUDA tensors, gloo in the CPU tests); the collectives are
-torch.distributed's -- there is no hand-rolled exchange on this path.
+`PeerArena` is the training exchange on one NVLink box: the gradient arenas are cudaMalloc'd, mapped into every peer
+through CUDA IPC, and the optimizer kernel reads all ranks' arenas directly (csrc/p2p.cu) after a flag barrier -- no
+all-reduce pass.  `allreduce_arena` (NCCL / gloo) remains the fallback and what the CPU tests exercise.
 """
 from __future__ import annotations
 
@@ -83,3 +84,90 @@ def gather_rows(t, group=None):
     outs = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+
+
+class _RawDeviceBuffer:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """Double-buffered gradient arena shared with the other ranks of the box over CUDA IPC + NVLink (csrc/p2p.cu).
+
+    bufs[b]      this rank's arena b as a float32 tensor (kernels scatter into bufs[cur])
+    table(b, o)  host array with the address of float `o` of arena b on every rank (rank order)
+    barrier()    stream-ordered cross-GPU barrier: every rank's scatter kernels of this step are complete and visible
+    """
+
+    FLAG_INTS = 64
+
+    def __init__(self, n_floats, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.ws = world(group)
+        if self.ws > 16:
+            raise _lib.HhfmError("PeerArena: at most 16 ranks")
+        self.device = device
+        self.n = int(n_floats)
+        nbytes = (self.n * 4 + 255) // 256 * 256
+        self._own = []
+        handles = []
+        for _ in range(2):
+            p = C.c_void_p()
+            h = (C.c_ubyte * 64)()
+            _lib.call("hhfm_p2p_alloc", nbytes, C.byref(p), C.cast(h, C.c_void_p))
+            self._own.append(int(p.value))
+            handles.append(bytes(h))
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        _lib.call("hhfm_p2p_alloc", self.FLAG_INTS * 4, C.byref(p), C.cast(h, C.c_void_p))
+        self._own_flags = int(p.value)
+        handles.append(bytes(h))
+        torch.cuda.synchronize(device)
+        everyone = [None] * self.ws
+        dist.all_gather_object(everyone, handles, group=group)
+        self._opened = []
+        self.base = [[0] * self.ws for _ in range(2)]
+        self.flag_base = [0] * self.ws
+        for r in range(self.ws):
+            for k in range(3):
+                if r == self.rank:
+                    addr = (self._own + [self._own_flags])[k]
+                else:
+                    q = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(everyone[r][k])
+                    _lib.call("hhfm_p2p_open", C.cast(hb, C.c_void_p), C.byref(q))
+                    addr = int(q.value)
+                    self._opened.append(addr)
+                if k < 2:
+                    self.base[k][r] = addr
+                else:
+                    self.flag_base[r] = addr
+        self.bufs = [torch.as_tensor(_RawDeviceBuffer(self._own[b], (self.n,), "<f4"), device=device) for b in range(2)]
+        self._flag_table = (C.c_int64 * self.ws)(*self.flag_base)
+        self._tables = {}
+        self.epoch = 0
+        self.cur = 0
+        dist.barrier(group=group)
+
+    def table(self, b, offset_floats):
+        import ctypes as C
+        key = (b, int(offset_floats))
+        t = self._tables.get(key)
+        if t is None:
+            t = (C.c_int64 * self.ws)(*[self.base[b][r] + 4 * int(offset_floats) for r in range(self.ws)])
+            self._tables[key] = t
+        return t
+
+    def barrier(self):
+        from .engine import cur_stream
+        self.epoch += 1
+        self._lib.call("hhfm_p2p_barrier", self._flag_table, self.rank, self.ws, self.epoch, cur_stream())
+
+    def close(self):
+        for a in self._opened:
+            self._lib.call("hhfm_p2p_close", a)
+        self._opened = []

@@ -58,14 +58,13 @@ class _Base:
             self.weights["feature_bias"] = torch.zeros(self._M, 1, dtype=torch.float32, device=self.device)  # :155-156
         P = _lib.partials_len()
         self._P = P
-        # one flat gradient arena so a data-parallel step needs a single all-reduce
+        # one flat gradient arena so a data-parallel step needs a single exchange
         n_v = self._M * self._K
         n_b = self._M if with_bias else 0
-        self._arena = torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device)
-        self._gV = self._arena[:n_v].view(self._M, self._K)
-        self._gb = self._arena[n_v:n_v + n_b] if with_bias else None
-        self._gb0 = self._arena[n_v + n_b:n_v + n_b + 1]
-        self._loss_partials = self._arena[n_v + n_b + 4:]
+        self._arena_layout = (n_v, n_b, P)
+        self._with_bias_grad = with_bias
+        self._peer = None
+        self._bind_arena(torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device))
         self._sq_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
         self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._loss_host = torch.zeros(1, dtype=torch.float32, pin_memory=True)
@@ -83,8 +82,16 @@ class _Base:
         self.hot_rows = "auto"      # "auto": plan from the first batch; None: off; or an explicit id list
         self._hot = None
         self._hot_planned = False
-        self._with_bias_grad = with_bias
         self.sess = Session(self)
+
+    def _bind_arena(self, arena):
+        """Point the gradient views at `arena` ([gV | gbias | gb0 (4) | loss partials])."""
+        n_v, n_b, P = self._arena_layout
+        self._arena = arena
+        self._gV = arena[:n_v].view(self._M, self._K)
+        self._gb = arena[n_v:n_v + n_b] if (n_b and self._with_bias_grad) else None
+        self._gb0 = arena[n_v + n_b:n_v + n_b + 1]
+        self._loss_partials = arena[n_v + n_b + 4:n_v + n_b + 4 + P]
 
     def _hot_plan(self, idx_dev, with_bias):
         """Hot-row plan for the two-level scatter (engine.HotRows), built once from the first batch."""
@@ -99,18 +106,55 @@ class _Base:
         return self._hot
 
     # ---- data parallel: batch rows sharded across ranks, one all-reduce of the arena ----
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, p2p="auto"):
+        """Batch rows sharded across the ranks of `group`, weights replicated.  On CUDA the gradient
+        exchange is fused into the optimizer over NVLink peer memory (dist.PeerArena, csrc/p2p.cu); `p2p=False`, or a box
+        where CUDA IPC is unavailable, falls back to one NCCL all-reduce of the arena per step."""
         import torch.distributed as dist
+        from . import dist as hd
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
         self._dp_group = group if group is not None else dist.group.WORLD
         for w in self.weights.values():
             dist.broadcast(w, src=0, group=self._dp_group)
+        self._peer = None
+        ws = dist.get_world_size(self._dp_group)
+        if p2p and ws > 1 and self.device.type == "cuda":
+            peer, ok = None, 1
+            try:
+                peer = hd.PeerArena(self._arena.numel(), self.device, self._dp_group)
+            except _lib.HhfmError:
+                if p2p is True:
+                    raise
+                ok = 0
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._dp_group)
+            if int(flag.item()) == 1:
+                self._peer = peer
+                self._bind_arena(peer.bufs[peer.cur])
+            elif p2p is True:
+                raise _lib.HhfmError("enable_data_parallel: a rank could not map its peers' arenas")
 
     def _allreduce_grads(self):
-        if self._dp_group is not None:
+        """Make every rank's gradients of this step available: a cross-GPU barrier when the optimizer sums the peers'
+        arenas itself, otherwise an all-reduce of the arena."""
+        if self._dp_group is None:
+            return
+        if self._peer is not None:
+            self._peer.barrier()
+        else:
             import torch.distributed as dist
             dist.all_reduce(self._arena, group=self._dp_group)
+
+    def _apply_arena_dense(self, name, w, g, lamda, sq):
+        """Dense optimizer step for a tensor whose gradient `g` is a slice of the arena."""
+        if self._peer is None:
+            self._opt.apply_dense(name, w, g, lamda, sq)
+            return
+        pr = self._peer
+        off = (g.data_ptr() - self._arena.data_ptr()) // 4
+        other = pr.bufs[pr.cur ^ 1]
+        self._opt.apply_dense_p2p(name, w, pr.table(pr.cur, off), pr.ws, other[off:off + g.numel()], lamda, sq)
 
     def enable_item_sharding(self, group=None):
         """Full-catalog top-N with the item catalog sharded across the ranks of `group`: every rank
@@ -159,15 +203,26 @@ class _Base:
         if self._lamda <= 0 and self._opt.kind == "momentum":
             raise NotImplementedError("sparse Momentum under data parallelism is not implemented")
         sq = self._sq_partials if self._lamda > 0 else None
-        self._opt.apply_dense("feature_embeddings", V, self._gV, self._lamda if self._lamda > 0 else 0.0, sq)
+        self._apply_arena_dense("feature_embeddings", V, self._gV, self._lamda if self._lamda > 0 else 0.0, sq)
         return self._lamda > 0
 
     def _enqueue_loss(self, with_reg, half_lamda=None):
-        """Deterministic reduction of the per-CTA loss partials (+ regulariser) into `_loss_dev`; no host sync."""
+        """Deterministic reduction of the per-CTA loss partials (+ regulariser) into `_loss_dev`; no host sync.  Under data
+        parallelism the loss is the sum over all ranks (the reference loss is a sum over the batch, FM.py:124).  This is
+        the last call of a step: the peer arena flips to its other buffer here."""
         self._version += 1
         hl = (0.5 * self._lamda) if half_lamda is None else half_lamda
-        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if with_reg else None,
-                  hl if with_reg else 0.0, ptr(self._loss_dev), cur_stream())
+        sq = ptr(self._sq_partials) if with_reg else None
+        if self._peer is None:
+            _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), sq, hl if with_reg else 0.0, ptr(self._loss_dev),
+                      cur_stream())
+            return
+        pr = self._peer
+        off = (self._loss_partials.data_ptr() - self._arena.data_ptr()) // 4
+        _lib.call("hhfm_loss_finalize_p2p", pr.table(pr.cur, off), pr.ws, sq, hl if with_reg else 0.0, ptr(self._loss_dev),
+                  cur_stream())
+        pr.cur ^= 1
+        self._bind_arena(pr.bufs[pr.cur])
 
     def _read_loss(self):
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
@@ -286,8 +341,8 @@ class FM(_Base):
         if self._opt.kind == "momentum" and self._dp_group is None:
             self._opt.apply_rows("feature_bias", bias, self._gb, self._touch.rows, self._touch.count, 1)
         else:
-            self._opt.apply_dense("feature_bias", bias, self._gb, 0.0, None)
-        self._opt.apply_dense("bias", self._b0, self._gb0, 0.0, None)
+            self._apply_arena_dense("feature_bias", bias, self._gb, 0.0, None)
+        self._apply_arena_dense("bias", self._b0, self._gb0, 0.0, None)
 
     def topk(self, A, tp):
         """Full-catalog top-N (FM.py:172-185): indices relative to the item id range."""
@@ -446,6 +501,7 @@ class OUR(_PairRank):
         self._setup(self.features_M, self.hidden_factor, self.random_seed, True, self.optimizer_type,
                     self.learning_rate, 0.1, self.lamda_bilinear)
         # feature_bias exists in the reference graph (OurModel7.py:213-214) but receives no gradient
+        self._with_bias_grad = False
         self._gb = None
 
     def _parts(self, X, F1, F2, Y=None):
@@ -770,8 +826,8 @@ class DeepFM(_Base):
             dist.all_reduce(self._gparams, group=self._dp_group)
         # V / feature_bias get IndexedSlices: Adagrad leaves rows with g = 0 untouched, so the dense kernel is exact
         o = self._opt
-        o.apply_dense("feature_embeddings", V, self._gV, 0.0, None)
-        o.apply_dense("feature_bias", fb, self._gb, 0.0, None)
+        self._apply_arena_dense("feature_embeddings", V, self._gV, 0.0, None)
+        self._apply_arena_dense("feature_bias", fb, self._gb, 0.0, None)
         lam = float(self.l2_reg)
         nr = self._n_reg
         o.apply_dense("dense_reg", self._params[:nr], self._gparams[:nr], lam if lam > 0 else 0.0,

@@ -245,6 +245,29 @@ int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, flo
                        hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Data-parallel exchange over NVLink peer memory, fused into the optimizer (p2p.cu).
+ * hhfm_p2p_alloc: cudaMalloc'd, zeroed buffer + its 64-byte CUDA IPC handle; hhfm_p2p_open maps a peer's handle
+ * (one process per GPU on one box).  *_ptrs_host arguments are HOST arrays of n_ranks device addresses (rank order),
+ * this rank's own buffer included.
+ * hhfm_p2p_barrier: stream-ordered cross-GPU barrier (system-scope release/acquire flags; flags buffers hold >= n_ranks
+ *   int32 per rank, zero-initialised; `epoch` must increase by one per call).
+ * hhfm_opt_dense_l2_p2p: w/state update with g = sum over ranks (fixed rank order => bit-identical replicas) of
+ *   grad_r[i] + lamda*w; g_zero (may be NULL) is a LOCAL buffer cleared on the way (the other half of a double-buffered
+ *   gradient arena).  beta1 carries the momentum for HHFM_OPT_MOMENTUM, lr is lr_t for Adam.
+ * hhfm_loss_finalize_p2p: loss = sum over ranks of the loss partials + half_lamda * sum(sq_partials).
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_p2p_alloc(int64_t bytes, void** dev_ptr, void* handle64);
+int hhfm_p2p_open(const void* handle64, void** dev_ptr);
+int hhfm_p2p_close(void* dev_ptr);
+int hhfm_p2p_free(void* dev_ptr);
+int hhfm_p2p_barrier(const int64_t* flag_ptrs_host, int32_t rank, int32_t n_ranks, int32_t epoch, hhfm_stream_t stream);
+int hhfm_opt_dense_l2_p2p(int32_t kind, float* w, float* s1, float* s2, const int64_t* grad_ptrs_host, int32_t n_ranks,
+                          float* g_zero, int64_t n, float lr, float lamda, float beta1, float beta2, float eps,
+                          float* sq_partials, hhfm_stream_t stream);
+int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, const float* sq_partials, float half_lamda,
+                           float* loss_out, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K6  full-catalog top-N (FM.py:172-185, BPR.py:131-136, MF.py:144-149, OurModel7.py:229-295)
  * Exact path (bit-identical to the oracle's canonical fp32 order: k ascending, separately rounded mul/add):
  *   build_query -> score_exact -> select.

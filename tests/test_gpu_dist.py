@@ -26,22 +26,41 @@ def _worker(rank, world, port, ret):
         from oracle import hhfm_oracle as O
         rng = np.random.default_rng(0)
         n_user, n_item, M, K, fc, B = 100, 301, 500, 64, 4, 4096
-        model = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, 'AdagradOptimizer', True, False)
-        model.enable_data_parallel(); model.enable_item_sharding()
-        V = model.get_weights()["feature_embeddings"].copy()
         X = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B)], axis=1)
         F1 = rng.integers(n_user + n_item, M, (B, fc)); Y = n_user + rng.integers(0, n_item, (B, 10))
         lo, hi = hd.shard_range(B, rank, world)
-        loss = model.partial_fit({"X": X[lo:hi], "F1": F1[lo:hi], "Y": Y[lo:hi]})
-        loss_ref, _, _, dV = O.pairrank_loss_grads(V, X, Y, F1, None, (0, 0, 0), 0.01)
-        V1, _ = O.adagrad_dense(V, np.full_like(V, 0.1), dV, 0.1)
-        got = model.get_weights()["feature_embeddings"]
-        ok_loss = abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
-        ok_w = bool(np.all(np.abs(got - V1) <= 2e-5 * np.maximum(np.abs(V1 - V), np.sqrt(np.mean((V1 - V) ** 2)))))
-        A = np.concatenate([X[:200], F1[:200]], axis=1)
-        ids = model.topk(A, 20)
-        want = O.topk_lowest_index(O.hhfm_topk_scores(A, got, n_user, n_item, fc, 0), 20)
-        ret[rank] = (ok_loss, ok_w, bool((ids == want).all()))
+        finals = {}
+        results = []
+        for mode in ("auto", False):           # NVLink peer-arena exchange fused into the optimizer / NCCL all-reduce
+            model = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, 'AdagradOptimizer', True, False)
+            model.enable_data_parallel(p2p=mode); model.enable_item_sharding()
+            if world > 1 and mode == "auto":
+                assert model._peer is not None, "CUDA IPC peer mapping should be available on one box"
+            V = model.get_weights()["feature_embeddings"].copy()
+            loss = model.partial_fit({"X": X[lo:hi], "F1": F1[lo:hi], "Y": Y[lo:hi]})
+            loss_ref, _, _, dV = O.pairrank_loss_grads(V, X, Y, F1, None, (0, 0, 0), 0.01)
+            V1, _ = O.adagrad_dense(V, np.full_like(V, 0.1), dV, 0.1)
+            got = model.get_weights()["feature_embeddings"]
+            ok_loss = abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
+            ok_w = bool(np.all(np.abs(got - V1) <= 2e-5 * np.maximum(np.abs(V1 - V), np.sqrt(np.mean((V1 - V) ** 2)))))
+            A = np.concatenate([X[:200], F1[:200]], axis=1)
+            ids = model.topk(A, 20)
+            want = O.topk_lowest_index(O.hhfm_topk_scores(A, got, n_user, n_item, fc, 0), 20)
+            # three more steps (both arena buffers get reused), then the replicas must still be identical on every rank
+            for step in range(3):
+                r2 = np.random.default_rng(100 + step)
+                Xs = np.stack([r2.integers(0, n_user, B), n_user + r2.integers(0, n_item, B)], axis=1)
+                Fs = r2.integers(n_user + n_item, M, (B, fc)); Ys = n_user + r2.integers(0, n_item, (B, 10))
+                model.partial_fit({"X": Xs[lo:hi], "F1": Fs[lo:hi], "Y": Ys[lo:hi]})
+            w = model.weights["feature_embeddings"]
+            gathered = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(gathered, w)
+            same = all(bool(torch.equal(gathered[0], g)) for g in gathered)
+            finals[mode] = w.cpu().numpy().copy()
+            results.append((ok_loss, ok_w, bool((ids == want).all()), same))
+        d = np.abs(finals["auto"] - finals[False])
+        close = bool(np.all(d <= 1e-4 * np.maximum(np.abs(finals[False]), np.sqrt(np.mean(finals[False] ** 2)))))
+        ret[rank] = tuple(results) + (close,)
     finally:
         dist.destroy_process_group()
 
@@ -52,4 +71,4 @@ def test_data_parallel_step_and_sharded_topk(cuda):
     mgr = mp.Manager(); ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
-        assert ret[r] == (True, True, True), (r, ret[r])
+        assert ret[r] == ((True, True, True, True), (True, True, True, True), True), (r, ret[r])
