@@ -42,6 +42,9 @@ SIGNATURES = {
     "hhfm_opt_momentum_rows": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp],
     "hhfm_opt_sgd_rows": [vp, vp, vp, vp, i64, i64, f32, i32, vp],
     "hhfm_loss_finalize": [vp, vp, f32, vp, vp],
+    "hhfm_sample_negatives": [vp, i64, i32, i32, i32, vp, i64, i64, C.c_uint64, vp, i64, i64, vp],
+    "hhfm_expand_rows": [vp, i64, i32, i64, vp, i32, vp, i32, vp],
+    "hhfm_auc_count": [vp, vp, i64, i32, vp, vp],
     "hhfm_p2p_alloc": [i64, vp, vp],
     "hhfm_p2p_open": [vp, vp],
     "hhfm_p2p_close": [vp],

@@ -132,14 +132,16 @@ class RecordUploader:
         self.dev = None
         self._busy = None          # event recorded after the last upload: the pinned staging is free once it has passed
 
-    def upload(self, parts, id_limit, align=4):
+    def upload(self, parts, id_limit, align=4, extra_cols=0):
+        """`extra_cols` reserves columns after the packed ones (filled with the padding code -1 here, e.g. negatives that
+        the device sampler writes afterwards)."""
         parts = [_as_2d_ids(p) for p in parts if p is not None]
         B = parts[0].shape[0]
         for p in parts:
             if p.shape[0] != B:
                 raise ValueError("upload: blocks disagree on the number of rows")
         width = sum(p.shape[1] for p in parts)
-        stride = _round_up(max(width, 1), align)
+        stride = _round_up(max(width + int(extra_cols), 1), align)
         lib = _lib.load()
         nbytes = int(lib.hhfm_pack_upload_staging_bytes(B, stride, id_limit))
         if self.host is None or self.host.numel() < nbytes:
@@ -164,6 +166,57 @@ class RecordUploader:
             self._busy = torch.cuda.Event()
         self._busy.record()
         return self.dev[:B * stride].view(B, stride), stride
+
+
+class DeviceSampler:
+    """`Train.sample_negative` (FM.py:284-294) on the device: uniform item draws with rejection against
+    positive_feedback[key(row)], the membership test being a binary search in the loader's sorted (key_id, item) codes.
+    Counter-based generator (csrc/sampler.cu): reproducible from `seed`, statistically the reference's sampler, not its
+    numpy stream."""
+
+    def __init__(self, loader, n_user, n_item, device, seed=2016):
+        self.loader = loader
+        self.n_user, self.n_item = int(n_user), int(n_item)
+        self.device = device
+        self.codes = torch.as_tensor(np.ascontiguousarray(loader._pf_codes, dtype=np.int64)).to(device)
+        self.span = int(loader._span)
+        self.seed = int(seed)
+        self.calls = 0
+
+    def key_ids(self, rows):
+        """rows [n, F] host ids (label column removed) -> int32 device tensor of key ids (-1: key never trained)."""
+        return torch.as_tensor(self.loader.key_ids(rows).astype(np.int32)).to(self.device)
+
+    def next_seed(self):
+        self.calls += 1
+        return (self.seed * 0x9E3779B97F4A7C15 + self.calls) & 0xFFFFFFFFFFFFFFFF
+
+    def sample(self, key_id_dev, num, out=None, out_stride=None, out_col0=0, seed=None):
+        """Writes `num` negatives per row into out[:, out_col0:out_col0+num] (int32, row stride out_stride); allocates a
+        dense [n, num] tensor when `out` is None."""
+        n = int(key_id_dev.numel())
+        if out is None:
+            out = torch.empty(n, num, dtype=torch.int32, device=self.device)
+            out_stride, out_col0 = num, 0
+        _lib.call("hhfm_sample_negatives", ptr(key_id_dev), n, num, self.n_user, self.n_item, ptr(self.codes),
+                  int(self.codes.numel()), self.span, self.next_seed() if seed is None else seed, ptr(out), out_stride,
+                  out_col0, cur_stream())
+        return out
+
+
+def expand_rows(rows_dev, F, items_dev, out_stride=None):
+    """[n, stride] records + [n, num] items -> [n*num, out_stride] rows with column 1 replaced (FM.py:303-305) and -1
+    padding after column F, on the device."""
+    n, stride = rows_dev.shape
+    num = items_dev.shape[1]
+    out_stride = F if out_stride is None else out_stride
+    out = torch.empty(n * num, out_stride, dtype=torch.int32, device=rows_dev.device)
+    _lib.call("hhfm_expand_rows", ptr(rows_dev), n, F, stride, ptr(items_dev), num, ptr(out), out_stride, cur_stream())
+    return out
+
+
+def auc_wins(pos_dev, neg_dev, num, wins_dev):
+    _lib.call("hhfm_auc_count", ptr(pos_dev), ptr(neg_dev), int(pos_dev.numel()), num, ptr(wins_dev), cur_stream())
 
 
 # --------------------------------------------------------------------------------------------------

@@ -296,16 +296,17 @@ class FM(_Base):
         self.weights["bias"] = self._b0.view(())                                   # FM.py:157
 
     # -- forward only: `sess.run(model.out, ...)` of evaluate_AUC (FM.py:313-319) --
-    def predict(self, X):
-        X = np.asarray(X)
-        F = X.shape[1]
-        idx = self._upload_rows(X)
-        B = idx.shape[0]
+    def score_device(self, idx):
+        """Scores [n] (device) for device-resident id rows idx int32 [n, F]."""
+        B, F = idx.shape
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, F, ptr(self.weights["feature_embeddings"]),
                   ptr(self.weights.get("feature_bias")), ptr(self._b0), self._M, self._K, self.interaction, ptr(out),
                   cur_stream())
-        return out.cpu().numpy().reshape(-1, 1)
+        return out
+
+    def predict(self, X):
+        return self.score_device(self._upload_rows(np.asarray(X))).cpu().numpy().reshape(-1, 1)
 
     def partial_fit(self, data):
         """One minibatch step (FM.py:168-171): forward, squared loss, backward, optimizer.  Returns the loss."""
@@ -398,13 +399,16 @@ class MF(FM):
                     self.learning_rate, 1e-8, self.lamda_bilinear)
         self._b0 = None
 
-    def predict(self, X):
-        idx = self._upload_rows(np.asarray(X)[:, :2])
+    def score_device(self, idx):
         B = idx.shape[0]
+        idx2 = idx[:, :2].contiguous() if idx.shape[1] != 2 else idx
         out = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, 2, ptr(self.weights["feature_embeddings"]), None, None,
+        _lib.call("hhfm_fm_fwd", None, ptr(idx2), None, B, 2, ptr(self.weights["feature_embeddings"]), None, None,
                   self._M, self._K, 1, ptr(out), cur_stream())
-        return out.cpu().numpy().reshape(-1, 1)
+        return out
+
+    def predict(self, X):
+        return self.score_device(self._upload_rows(np.asarray(X)[:, :2])).cpu().numpy().reshape(-1, 1)
 
     def partial_fit(self, data):
         idx = self._upload_rows(np.asarray(data["X"])[:, :2])
@@ -462,12 +466,15 @@ class _PairRank(_Base):
 
     def _positive_feedback(self, parts, n_ctx, n_time):
         idx, stride = self._upload_ids(parts)
-        B = idx.shape[0]
+        return self._positive_feedback_dev(idx, n_ctx, n_time).cpu().numpy().reshape(-1, 1)
+
+    def _positive_feedback_dev(self, idx, n_ctx, n_time):
+        B, stride = idx.shape
         pos = torch.empty(B, dtype=torch.float32, device=self.device)
         pc, pt, pf = self.pools
         _lib.call("hhfm_pairrank_fwd", ptr(idx), B, stride, n_ctx, n_time, 0, pc, pt, pf,
                   ptr(self.weights["feature_embeddings"]), self._M, self._K, ptr(pos), None, cur_stream())
-        return pos.cpu().numpy().reshape(-1, 1)
+        return pos
 
 
 class OUR(_PairRank):
@@ -523,6 +530,10 @@ class OUR(_PairRank):
     def positive_feedback(self, X, F1=None, F2=None):
         return self._positive_feedback(self._parts(X, F1, F2), self._n_ctx, self._n_time)
 
+    def score_device(self, idx):
+        """PositiveFeadback (OurModel7.py:171) for device-resident rows [n, >= 2+n_ctx+n_time] = [user, item, ctx.., time..]."""
+        return self._positive_feedback_dev(idx, self._n_ctx, self._n_time)
+
     def topk(self, A, tp):
         """OurModel7.py:229-295: A = [user, item, ctx.., time..]."""
         return self._topk(QUERY_HHFM, A, self._n_ctx, self._n_time, self.pools, None, tp)
@@ -571,6 +582,9 @@ class BPR(_PairRank):
 
     def positive_feedback(self, X):
         return self._positive_feedback([np.asarray(X)[:, :2]], 0, 0)
+
+    def score_device(self, idx):
+        return self._positive_feedback_dev(idx, 0, 0)
 
     def topk(self, A, Topk):
         return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, Topk)
@@ -644,6 +658,9 @@ class AFM(FM):
         X = np.asarray(X)
         idx = self._upload_rows(X)
         return self._predict_dev(idx).cpu().numpy().reshape(-1, 1)
+
+    def score_device(self, idx):
+        return self._predict_dev(idx)
 
     def _predict_dev(self, idx):
         B, F = idx.shape
@@ -790,6 +807,9 @@ class DeepFM(_Base):
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 1), dtype=torch.float32, device=self.device)
         return self._ws
+
+    def score_device(self, idx):
+        return self._forward_dev(idx)
 
     def _forward_dev(self, idx):
         B, F = idx.shape

@@ -47,6 +47,10 @@ class BaseTrain(object):
     early_stop_tol = -0.0075  # FM.py:261 (AFM.py:330 uses -0.01)
     early_stop_cap = 100     # FM.py:262 `or epoch>100` (DFM has no cap)
     result_file = "../result.txt"
+    # negatives drawn and evaluate_AUC computed on the device (counter-based generator: statistically
+    # the reference's sampler, not numpy's stream).  Off by default so that a seeded run consumes the reference's stream.
+    device_sampler = bool(int(os.environ.get("HHFM_DEVICE_SAMPLER", "0")))
+    record_align = 1         # stride alignment of expanded rows (pair-ranking records need 4)
 
     # ---- to be provided by subclasses ----
     def score_rows(self, rows):
@@ -61,11 +65,39 @@ class BaseTrain(object):
     def sample_negative(self, data, num=10):
         return sample_negative(self.data, self.n_user, self.n_item, data, num)
 
+    def _sampler(self):
+        s = getattr(self, "_dev_sampler", None)
+        if s is None:
+            s = self._dev_sampler = engine.DeviceSampler(self.data, self.n_user, self.n_item, self.model.device)
+        return s
+
+    def evaluate_AUC_device(self, X):
+        """evaluate_AUC with everything after the id upload on the device: 50 negatives per row (device sampler), the
+        negative rows built by replacing the item column, both sides scored by the forward kernel, wins counted."""
+        if self.auc_first_chunk_only:
+            X = X[:600]                                   # OurModel7.py:461 / BPR.py:258: `return` inside the chunk loop
+        if len(X) == 0:
+            return float("nan")
+        smp, model = self._sampler(), self.model
+        F = X.shape[1]
+        ostride = (F + self.record_align - 1) // self.record_align * self.record_align
+        wins = torch.zeros(1, dtype=torch.int64, device=model.device)
+        step = max(600, (1 << 21) // 50)
+        for c0 in range(0, len(X), step):
+            rows = X[c0:c0 + step]
+            idx, _ = model._uploader.upload([rows], model._M, align=self.record_align)
+            negs = smp.sample(smp.key_ids(rows), 50)
+            neg_rows = engine.expand_rows(idx, F, negs, ostride)
+            engine.auc_wins(model.score_device(idx), model.score_device(neg_rows), 50, wins)
+        return float(wins.item()) / (50.0 * len(X))
+
     def evaluate_AUC(self, data1):
         """FM.py:296-324: 50 sampled negatives per positive, fraction with pos > neg, chunks of 600 rows."""
         dat = np.asarray(data1.values if hasattr(data1, "values") else data1)
         dat = dat[dat[:, 0] > 0]
         X = np.array(dat[:, 1:], dtype=np.int64)
+        if self.device_sampler:
+            return self.evaluate_AUC_device(X)
         score = []
         for c0 in range(0, len(X), 600):
             pos = X[c0:c0 + 600]
@@ -146,7 +178,28 @@ class PointwiseTrain(BaseTrain):
     NG = 2
     neg_label = 0            # FM.py:248 `-0`; AFM.py:317 / DFM.py:286 use -1
 
+    def run_epoch_device(self):
+        """The same epoch with the negatives drawn on the device and the shuffled batches cut from device-resident rows:
+        one id upload per epoch instead of one per batch."""
+        model, smp = self.model, self._sampler()
+        pos = np.array(self.data.Train_data.values)
+        n, F = pos.shape[0], pos.shape[1] - 1
+        idx, _ = model._uploader.upload([pos[:, 1:]], model._M, align=1)
+        negs = smp.sample(smp.key_ids(pos[:, 1:]), self.NG)
+        rows = torch.cat([idx, engine.expand_rows(idx, F, negs)], dim=0)
+        y = torch.cat([torch.as_tensor(pos[:, 0].astype(np.float32), device=model.device),
+                       torch.full((n * self.NG,), float(self.neg_label), device=model.device)])
+        perm = torch.as_tensor(np.random.permutation(len(rows)), device=model.device)      # FM.py:250 np.random.shuffle
+        rows, y = rows[perm].contiguous(), y[perm].contiguous()
+        loss = 0
+        for c0 in range(0, len(rows), self.batch_size):
+            model.fit_device(rows[c0:c0 + self.batch_size], y[c0:c0 + self.batch_size])
+            loss = loss + model._read_loss()
+        return loss
+
     def run_epoch(self):
+        if self.device_sampler:
+            return self.run_epoch_device()
         pos = np.array(self.data.Train_data.values)
         neg = np.tile(np.expand_dims(copy.deepcopy(pos), axis=1), [1, self.NG, 1]).reshape(-1, pos.shape[1])
         neg[:, 2] = self.sample_negative(pos[:, 1:], self.NG).reshape(-1)
@@ -185,7 +238,30 @@ class PairwiseTrain(BaseTrain):
             d['F2'] = np.array(rows[:, 2:], dtype=np.int64)
         return d
 
+    record_align = 4
+
+    def run_epoch_device(self):
+        """Shuffled positives are uploaded once per epoch as records with NG empty negative slots, the device sampler
+        fills the slots, and the batches are row ranges of that buffer."""
+        model, smp = self.model, self._sampler()
+        pos = np.array(self.data.Train_data.values[:, 1:])
+        np.random.shuffle(pos)                               # OurModel7.py:370
+        d = self.split(pos)
+        parts = [d['X']] + ([d['F1']] if 'F1' in d else []) + ([d['F2']] if 'F2' in d else [])
+        width = sum(p.shape[1] for p in parts)
+        rec, stride = model._uploader.upload(parts, model._M, align=4, extra_cols=self.NG)
+        smp.sample(smp.key_ids(pos), self.NG, out=rec, out_stride=stride, out_col0=width)
+        n_ctx = d['F1'].shape[1] if 'F1' in d else 0
+        n_time = d['F2'].shape[1] if 'F2' in d else 0
+        loss = 0
+        for c0 in range(0, len(pos), self.batch_size):
+            model.fit_device(rec[c0:c0 + self.batch_size], n_ctx, n_time, self.NG)
+            loss = loss + model._read_loss()
+        return loss
+
     def run_epoch(self):
+        if self.device_sampler:
+            return self.run_epoch_device()
         pos = np.array(self.data.Train_data.values[:, 1:])   # pandas-3 `.values` is a read-only view: copy
         np.random.shuffle(pos)                               # OurModel7.py:370
         neg = self.sample_negative(pos, self.NG)

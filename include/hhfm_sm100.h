@@ -268,6 +268,23 @@ int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, co
                            float* loss_out, hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K9  device negative sampler and evaluate_AUC (sampler.cu)
+ * hhfm_sample_negatives: out[r, out_col0 + j] (row stride out_stride) = a uniform item id in [n_user, n_user+n_item),
+ *   re-drawn while key_id[r]*span + item is in the sorted int64 list pf_codes (= `item in positive_feedback[key(row)]`,
+ *   FM.py:284-294); key_id[r] < 0 (key never trained) or key_id == NULL rejects nothing.  Every draw is
+ *   splitmix64(seed, cell = r*num + j, attempt): reproducible and order independent (oracle: sample_negative_hashed).
+ * hhfm_expand_rows: out[(r*num + j), :F] = rows[r, :F] with column 1 replaced by items[r*num + j], columns [F, out_stride)
+ *   = -1 (FM.py:303-305).
+ * hhfm_auc_count: *wins += #{(r, j): pos[r] > neg[r*num + j]}                                        (FM.py:321-323).
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_sample_negatives(const int32_t* key_id, int64_t n, int32_t num, int32_t n_user, int32_t n_item,
+                          const int64_t* pf_codes, int64_t n_codes, int64_t span, uint64_t seed, int32_t* out,
+                          int64_t out_stride, int64_t out_col0, hhfm_stream_t stream);
+int hhfm_expand_rows(const int32_t* rows, int64_t n, int32_t F, int64_t stride, const int32_t* items, int32_t num,
+                     int32_t* out, int32_t out_stride, hhfm_stream_t stream);
+int hhfm_auc_count(const float* pos, const float* neg, int64_t n, int32_t num, uint64_t* wins, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K6  full-catalog top-N (FM.py:172-185, BPR.py:131-136, MF.py:144-149, OurModel7.py:229-295)
  * Exact path (bit-identical to the oracle's canonical fp32 order: k ascending, separately rounded mul/add):
  *   build_query -> score_exact -> select.

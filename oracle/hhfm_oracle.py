@@ -100,6 +100,42 @@ def sample_negative(rows, n_user, n_item, positive_feedback, num, randint=None):
     return samples
 
 
+def _splitmix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def sample_negative_hashed(key_id, num, n_user, n_item, pf_codes, span, seed):
+    """Restatement of the DEVICE sampler (csrc/sampler.cu): the reference's uniform draw + rejection
+    (FM.py:284-294) with a counter-based generator: draw(cell, attempt) = n_user + ((h >> 32) * n_item >> 32),
+    h = splitmix64(seed ^ splitmix64(cell * 0x100000001B3 + attempt)), cell = row*num + column; a draw is rejected
+    while key_id[row]*span + item is in pf_codes.  Bit-exact against the kernel (integer work)."""
+    key_id = np.asarray(key_id, dtype=np.int64)
+    n = len(key_id)
+    codes = set(np.asarray(pf_codes, dtype=np.int64).tolist())
+    out = np.zeros((n, num), dtype=np.int32)
+    with np.errstate(over="ignore"):
+        cell = np.arange(n * num, dtype=np.uint64)
+        pending = np.ones(n * num, dtype=bool)
+        attempt = 0
+        flat = out.reshape(-1)
+        kid = np.repeat(key_id, num)
+        while pending.any() and attempt <= 4096:
+            idx = np.flatnonzero(pending)
+            h = _splitmix64(np.uint64(seed) ^ _splitmix64(cell[idx] * np.uint64(0x100000001B3) + np.uint64(attempt)))
+            item = n_user + (((h >> np.uint64(32)) * np.uint64(n_item)) >> np.uint64(32)).astype(np.int64)
+            flat[idx] = item
+            if attempt >= 4096:
+                break
+            rej = np.array([(k >= 0) and ((k * span + it) in codes) for k, it in zip(kid[idx].tolist(), item.tolist())], dtype=bool)
+            pending[idx[~rej]] = False
+            attempt += 1
+    return out
+
+
 def assemble_pointwise_epoch(train, neg_samples, NG, neg_label):
     """FM.py:240-249 / AFM.py:309-318: positives followed by NG item-replaced copies labelled `neg_label`
     (FM: -0 == 0, AFM/DFM/MF: -1).  The shuffle (FM.py:250) is left to the caller."""

@@ -849,3 +849,53 @@ def test_pack_upload_records_matches_the_host_packer(cuda, id_limit, rows):
         Xbad = X.copy(); Xbad[rows // 2, 0] = id_limit
         with pytest.raises(_lib.HhfmError, match="out of range"):
             up.upload([Xbad, F1, Y], id_limit)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K9 device negative sampler / AUC plumbing (integer work: bit-exact against the oracle restatement)
+# ----------------------------------------------------------------------------------------------------
+def test_device_negative_sampler_matches_oracle_and_rejects_positives(cuda):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(21)
+    n_user, n_item, n_keys, n, num = 50, 40, 30, 3000, 10
+    span = n_user + n_item
+    # every key owns 0..35 of the 40 items: heavy rejection for some rows
+    pf = []
+    for k in range(n_keys):
+        own = rng.choice(n_item, size=int(rng.integers(0, 36)), replace=False)
+        pf += [k * span + n_user + int(i) for i in own]
+    codes = np.unique(np.asarray(pf, dtype=np.int64))
+    key_id = rng.integers(-1, n_keys, n).astype(np.int32)               # -1: key never trained
+    seed = 0x1234ABCD5678
+    out = torch.full((n, 16), -7, dtype=torch.int32, device=cuda)
+    lib.call("hhfm_sample_negatives", ptr(dev(key_id, cuda)), n, num, n_user, n_item, ptr(dev(codes, cuda)), len(codes), span, seed,
+             ptr(out), 16, 3, st())
+    got = out.cpu().numpy()
+    want = O.sample_negative_hashed(key_id, num, n_user, n_item, codes, span, seed)
+    assert (got[:, 3:13] == want).all(), "device sampler differs from the oracle restatement"
+    assert (got[:, :3] == -7).all() and (got[:, 13:] == -7).all()
+    assert got[:, 3:13].min() >= n_user and got[:, 3:13].max() < n_user + n_item
+    cset = set(codes.tolist())
+    bad = sum((int(k) * span + int(it)) in cset for k, row in zip(key_id, got[:, 3:13]) if k >= 0 for it in row)
+    assert bad == 0, "a sampled negative is in positive_feedback[key]"
+    # rows without constraints are uniform over the catalog (chi-square, 39 dof: 99.9 % quantile ~ 72)
+    free = got[key_id < 0][:, 3:13].reshape(-1) - n_user
+    cnt = np.bincount(free, minlength=n_item); e = free.size / n_item
+    assert ((cnt - e) ** 2 / e).sum() < 80.0
+
+
+def test_expand_rows_and_auc_count(cuda):
+    lib, ptr, st = _lib_ptr()
+    from hhfm_b200 import engine
+    rng = np.random.default_rng(22)
+    n, F, num = 700, 6, 50
+    rows = rng.integers(0, 1000, (n, 8)).astype(np.int32)
+    items = rng.integers(1000, 2000, (n, num)).astype(np.int32)
+    out = engine.expand_rows(dev(rows, cuda), F, dev(items, cuda), 8).cpu().numpy()
+    ref = np.repeat(rows[:, None, :], num, axis=1); ref[:, :, 1] = items; ref[:, :, F:] = -1
+    assert (out == ref.reshape(-1, 8)).all()
+    pos = rng.normal(size=n).astype(np.float32); neg = rng.normal(size=n * num).astype(np.float32)
+    neg[::7] = np.repeat(pos, num)[::7]                                   # ties count as losses (strict >, FM.py:321)
+    wins = torch.zeros(1, dtype=torch.int64, device=cuda)
+    engine.auc_wins(dev(pos, cuda), dev(neg, cuda), num, wins)
+    assert int(wins.item()) == int((np.repeat(pos, num) > neg).sum())

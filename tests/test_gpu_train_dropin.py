@@ -64,3 +64,33 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     ids = session.model.topk(rows, 20)
     assert ids.shape == (50, 20) and ids.min() >= 0 and ids.max() < session.n_item
     assert all(len(set(r.tolist())) == 20 for r in ids)
+
+
+@pytest.mark.parametrize("which", ["FM", "M7", "DFM"])
+def test_device_sampler_epoch_and_auc(cuda, which, tmp_path, monkeypatch):
+    """negatives drawn on the device, batches cut from device-resident rows, evaluate_AUC on the device.
+    Statistically the reference's sampler: the model must train, and the device AUC must agree with the host-sampled AUC
+    of the same weights."""
+    path = _write_dataset(str(tmp_path))
+    monkeypatch.setenv("HHFM_RESULT_FILE", os.path.join(str(tmp_path), "result.txt"))
+    from hhfm_b200 import trainer
+    monkeypatch.setattr(trainer.BaseTrain, "device_sampler", True)
+    np.random.seed(9)
+    argv = ["--path", path, "--epoch", "11", "--batch_size", "2000"]
+    if which == "FM":
+        from hhfm_b200.Newcode.FM import FM_main as main
+        argv += ["--verbose", "10"]
+    elif which == "DFM":
+        from hhfm_b200.Newcode.DFM import DFM_main as main
+        argv += ["--verbose", "10", "--lr", "0.05"]
+    else:
+        from hhfm_b200.Newcode.OurModel7 import M7_main as main
+    session = main("frappe", 32, 5, argv=argv)
+    losses = [float(x) for x in session.loss_epoch]
+    assert len(losses) == 10 and losses[-1] < losses[0], losses
+    auc_dev = session.evaluate_AUC(session.data.Train_data)
+    session.device_sampler = False
+    auc_host = session.evaluate_AUC(session.data.Train_data)
+    assert abs(auc_dev - auc_host) < 0.03, (auc_dev, auc_host)
+    if which != "DFM":
+        assert auc_dev > 0.6
