@@ -1,0 +1,459 @@
+// DeepFM tower on the 5th-generation tensor cores with fp32-grade accuracy: 3xTF32 split GEMM on tcgen05.
+//
+// tcgen05 has no fp32-input MMA kind and the parity bar is 1e-5 relative, so every fp32 operand x is used as
+//   hi = the tf32 the hardware sees (kind::tf32 ignores the low 13 mantissa bits of the fp32 word in shared memory),
+//   lo = x - hi  (exact in fp32, materialised once per tensor by split_transpose_kernel),
+// and  A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  with fp32 accumulation in TMEM (the dropped lo.lo term and the tf32
+// rounding of lo are ~2^-21 relative).  Three MMAs per k-step at tf32 rate (~1.1 PFLOP/s dense) is still ~5x the fp32
+// CUDA-core peak (74 TFLOP/s).
+//
+// One kernel covers all nine GEMMs of a training step in "TN" form, C[M,N] = A[M,K] . B[N,K]^T, both operands K-major,
+// staged by TMA with 128-byte swizzle (32 fp32 per row):
+//   forward   H_{i+1} = relu(H_i . W_i + b_i)      A = H_i [B, d_i],            B = W_i^T [d_{i+1}, d_i]   EPI_BIAS_RELU
+//   d input   dZ_i = (dZ_{i+1} . W_i^T) * relu'(H_i) A = dZ_{i+1} [B, d_{i+1}],  B = W_i [d_i, d_{i+1}]     EPI_MASK / EPI_SCATTER
+//   d weight  dW_i = H_i^T . dZ_{i+1}               A = H_i^T [d_i, B],          B = dZ_{i+1}^T [d_{i+1}, B] EPI_ATOMIC (split-K)
+// Transposed and lo copies of the activations come from split_transpose_kernel (one pass per activation tensor).
+// Roles per CTA (320 threads): warp 4 = TMA producer, warp 5 = single-thread MMA issuer, warps 0-3 and 6-9 = epilogue
+// (two per TMEM lane quarter, alternating 32-column chunks); 2 smem stages of {A_hi, A_lo, B_hi, B_lo}, 2 TMEM accumulators.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "dfm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace hhfm {
+
+constexpr int kTfM = 128;           // rows per CTA tile (UMMA M)
+constexpr int kTfKC = 32;           // fp32 per 128-byte swizzle row
+constexpr int kTfThreads = 320;
+constexpr int kTfStages = 2;
+constexpr int kTfABytes = kTfM * 128;            // one A tile (hi or lo)
+constexpr int kTfBBytesMax = 256 * 128;          // one B tile at bn = 256
+constexpr int kTfStageBytes = 2 * kTfABytes + 2 * kTfBBytesMax;
+constexpr int kTfSmemBytes = kTfStages * kTfStageBytes + 1024 + 256;
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// lo part: x - hi is exact in fp32 but has up to 13 significant bits; it is stored already ROUNDED to the nearest tf32 so
+// that the hardware's truncation of the operand loses nothing more (unbiased, half the error of letting it truncate)
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float lo = x - tf32_hi(x);
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+
+struct TfKernelArgs {
+  int M, N, K;
+  int n_mtiles, n_ntiles, bn, splits, chunks_total, chunks_per_split, n_units;
+  int drain_every;       // k-chunks accumulated in TMEM before the partial sum is added into fp32 registers
+  int epi;
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  const float* mask;
+  int64_t ldmask;
+  const int32_t* idx;
+  int F, Kemb;
+  HotPlan hot;
+  int* err;
+};
+
+__global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmAlo,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmBlo,
+                                                                    const TfKernelArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTfStages * kTfStageBytes);
+  uint64_t* full = bars;                      // [stages] TMA -> MMA
+  uint64_t* empty = bars + kTfStages;         // [stages] MMA -> TMA
+  uint64_t* t_full = empty + kTfStages;       // [2] accumulator ready
+  uint64_t* t_empty = t_full + 2;             // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBlo);
+    for (int i = 0; i < kTfStages; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t b_bytes = (uint32_t)a.bn * 128u;
+  const uint32_t stage_tx = 2u * kTfABytes + 2u * b_bytes;
+
+  // unit u -> (m tile, n tile, k split); consecutive units share the n tile and split (B operand stays hot in L2)
+  auto decode = [&](int u, int& mt, int& nt, int& sp) {
+    mt = u % a.n_mtiles;
+    const int r = u / a.n_mtiles;
+    nt = r % a.n_ntiles;
+    sp = r / a.n_ntiles;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        int mt, nt, sp; decode(u, mt, nt, sp);
+        const int c0 = sp * a.chunks_per_split, c1 = min(a.chunks_total, c0 + a.chunks_per_split);
+        for (int c = c0; c < c1; c++) {
+          mbar_wait(empty + st, ph ^ 1, a.err);
+          mbar_expect_tx(full + st, stage_tx);
+          uint8_t* sb = smem + st * kTfStageBytes;
+          tma_load_2d(sb, &tmA, c * kTfKC, mt * kTfM, full + st);
+          tma_load_2d(sb + kTfABytes, &tmAlo, c * kTfKC, mt * kTfM, full + st);
+          tma_load_2d(sb + 2 * kTfABytes, &tmB, c * kTfKC, nt * a.bn, full + st);
+          tma_load_2d(sb + 2 * kTfABytes + kTfBBytesMax, &tmBlo, c * kTfKC, nt * a.bn, full + st);
+          if (++st == kTfStages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(kTfM, a.bn);
+      int st = 0, acc = 0; uint32_t ph = 0, tph = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        int mt, nt, sp; decode(u, mt, nt, sp);
+        const int c0 = sp * a.chunks_per_split, c1 = min(a.chunks_total, c0 + a.chunks_per_split);
+        for (int c = c0; c < c1; c++) {
+          const bool first = ((c - c0) % a.drain_every) == 0;       // first k-chunk of a TMEM partial sum
+          if (first) {
+            mbar_wait(t_empty + acc, tph ^ 1, a.err);
+            tc_fence_after();
+          }
+          const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+          mbar_wait(full + st, ph, a.err);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(smem + st * kTfStageBytes);
+          const uint32_t ah = sb, al = sb + kTfABytes, bh = sb + 2 * kTfABytes, bl = bh + kTfBBytesMax;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {          // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            const uint32_t o = k4 * 32;
+            umma_tf32(d, make_sdesc(al + o), make_sdesc(bh + o), idesc, (!first || k4 != 0) ? 1u : 0u);
+            umma_tf32(d, make_sdesc(ah + o), make_sdesc(bl + o), idesc, 1u);
+            umma_tf32(d, make_sdesc(ah + o), make_sdesc(bh + o), idesc, 1u);
+          }
+          umma_commit(empty + st);
+          if (++st == kTfStages) { st = 0; ph ^= 1; }
+          if (((c - c0) % a.drain_every) == a.drain_every - 1 || c == c1 - 1) {
+            umma_commit(t_full + acc);              // partial sum complete: hand it to the epilogue warps
+            if (++acc == 2) { acc = 0; tph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: thread = (TMEM lane quarter, lane) owns output row m = mt*128 + quarter*32 + lane; the two warps of
+    // a quarter take alternating 32-column chunks ----
+    const int quarter = warp & 3, half = warp >= 6 ? 1 : 0;
+    int acc = 0; uint32_t tph = 0;
+    const int n_chunks = (a.bn + 31) / 32;
+    const int rep = a.hot.slot ? (int)(blockIdx.x % a.hot.n_rep) : 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      int mt, nt, sp; decode(u, mt, nt, sp);
+      const int c0k = sp * a.chunks_per_split;
+      const bool has_work = c0k < a.chunks_total;
+      const int m = mt * kTfM + quarter * 32 + lane;
+      // Two-level accumulation.  The tensor core adds into its fp32 accumulator with truncation, a bias that grows with
+      // the number of accumulation steps (measured: 8e-3 absolute after K = 4096 on N(0,1) data).  So TMEM only holds the
+      // partial sum of `drain_every` k-chunks; the partial sums are added here in registers with round-to-nearest.
+      const int c1k = min(a.chunks_total, c0k + a.chunks_per_split);
+      const int n_drains = has_work ? (c1k - c0k + a.drain_every - 1) / a.drain_every : 0;
+      float accr[4][32];
+      for (int dr = 0; dr < n_drains; dr++) {
+        mbar_wait(t_full + acc, tph, a.err);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = half + 2 * j;
+          if (c < n_chunks) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait_for(r);
+#pragma unroll
+            for (int i = 0; i < 32; i++) accr[j][i] = (dr == 0) ? __uint_as_float(r[i]) : accr[j][i] + __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(t_empty + acc);
+        if (++acc == 2) { acc = 0; tph ^= 1; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = half + 2 * j;
+        if (c >= n_chunks) continue;
+        const float (&r)[32] = accr[j];
+        const int nb = nt * a.bn + c * 32;
+        if (m >= a.M || !has_work) continue;
+        if (a.epi == TF_EPI_SCATTER) {
+          // d(H_0)[m, n] belongs to embedding row idx[m, n / Kemb], element n % Kemb (4 consecutive n share a row)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int n = nb + i;
+            if (n < a.N && n < (nt + 1) * a.bn) {
+              const int f = n / a.Kemb;
+              const int row = __ldg(a.idx + (int64_t)m * a.F + f);
+              float* dst = a.C + (int64_t)row * a.Kemb;
+              if (a.hot.slot) {
+                const int s = __ldg(a.hot.slot + row);
+                if (s >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + s) * a.Kemb;
+              }
+              red_add_v4(dst + (n - f * a.Kemb), make_float4(r[i], r[i + 1],
+                                                            r[i + 2], r[i + 3]));
+            }
+          }
+          continue;
+        }
+        float* crow = a.C + (int64_t)m * a.ldc;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int n = nb + i;
+          if (n >= a.N || n >= (nt + 1) * a.bn) continue;
+          float v[4] = {r[i], r[i + 1], r[i + 2], r[i + 3]};
+          const int nv = min(4, a.N - n);
+          if (a.epi == TF_EPI_BIAS_RELU) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (q < nv) ? fmaxf(v[q] + __ldg(a.bias + n + q), 0.f) : 0.f;
+          } else if (a.epi == TF_EPI_MASK) {
+            const float* mrow = a.mask + (int64_t)m * a.ldmask + n;
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (q < nv && mrow[q] > 0.f) ? v[q] : 0.f;
+          }
+          if (a.epi == TF_EPI_ATOMIC) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (q < nv) atomicAdd(crow + n + q, v[q]);
+          } else if (nv == 4) {
+            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (q < nv) crow[n + q] = v[q];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// X [rows, ld] (cols valid) -> X_lo [rows, ld], XT [cols, ldt], XT_lo [cols, ldt]   (ldt >= rows).  32x32 tiles through
+// shared memory so both the row-major reads and the transposed writes are coalesced.  XT / XT_lo may be NULL.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld,
+                                                              float* __restrict__ Xlo, float* __restrict__ XT,
+                                                              float* __restrict__ XTlo, int64_t ldt) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int64_t r = r0 + ty + 8 * i;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = X[r * ld + c];
+      if (Xlo) Xlo[r * ld + c] = tf32_lo(v);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  if (XT == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = c0 + ty + 8 * i;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) {
+      const float v = tile[tx][ty + 8 * i];
+      XT[(int64_t)c * ldt + r] = v;
+      if (XTlo) XTlo[(int64_t)c * ldt + r] = tf32_lo(v);
+    }
+  }
+}
+
+// X0[b, f*K + k] = V[idx[b, f], k]: the flattened embeddings as a dense [B, F*K] matrix (the TMA operand of layer 0)
+__global__ void __launch_bounds__(256) gather_x0_kernel(const int32_t* __restrict__ idx, int64_t B, int F, int K,
+                                                        const float* __restrict__ V, float* __restrict__ X0, int64_t ld) {
+  const int kv = K >> 2;
+  const int64_t total = B * F * kv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kv);
+    const int64_t bf = i / kv;
+    const int f = (int)(bf % F);
+    const int64_t b = bf / F;
+    const int row = __ldg(idx + b * F + f);
+    reinterpret_cast<float4*>(X0 + b * ld + (int64_t)f * K)[c] = __ldg(reinterpret_cast<const float4*>(V + (int64_t)row * K) + c);
+  }
+}
+
+// column sums of X [rows, ld] (cols valid) accumulated into out[cols] (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld,
+                                                     float* __restrict__ out) {
+  __shared__ float s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + tx;
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = (int64_t)blockIdx.x * 8 + ty; r < rows; r += (int64_t)gridDim.x * 8) acc += X[r * ld + c];
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += s[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+// W [rows, cols] row-major (ld = cols) -> Wp [rows, ldp] (+lo) and WT [cols, ldtp] (+lo), zero padded
+__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp,
+                                                          float* __restrict__ Wplo, int ldp, float* __restrict__ WT,
+                                                          float* __restrict__ WTlo, int ldtp) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = W[i], lo = tf32_lo(v);
+    Wp[(int64_t)r * ldp + c] = v; Wplo[(int64_t)r * ldp + c] = lo;
+    WT[(int64_t)c * ldtp + r] = v; WTlo[(int64_t)c * ldtp + r] = lo;
+  }
+}
+
+static int make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return HHFM_ERR_LAUNCH;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTfKC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32 %lld x %lld, ld %lld) failed (%d)", (long long)rows, (long long)cols, (long long)ld, (int)r);
+    return HHFM_ERR_LAUNCH;
+  }
+  return HHFM_OK;
+}
+
+int tf_pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  int best = 256, best_cost = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 16) {
+    const int cost = (N + bn - 1) / bn * bn;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int tf_gemm(const TfGemm& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return HHFM_OK;
+  HHFM_REQUIRE((g.lda % 4) == 0 && (g.ldb % 4) == 0, "tf_gemm: operand leading dimensions must be multiples of 4 floats");
+  HHFM_REQUIRE((((uintptr_t)g.A | (uintptr_t)g.A_lo | (uintptr_t)g.B | (uintptr_t)g.B_lo) & 15) == 0, "tf_gemm: operands must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTfSmemBytes) != cudaSuccess) {
+      set_error("tf32x3_gemm_kernel: cannot reserve %d bytes of shared memory", kTfSmemBytes);
+      return HHFM_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  TfKernelArgs a{};
+  a.M = g.M; a.N = g.N; a.K = g.K;
+  a.bn = tf_pick_bn(g.N);
+  a.n_mtiles = (g.M + kTfM - 1) / kTfM;
+  a.n_ntiles = (g.N + a.bn - 1) / a.bn;
+  a.chunks_total = (g.K + kTfKC - 1) / kTfKC;
+  a.splits = 1;
+  if (g.epi == TF_EPI_ATOMIC) {
+    const int tiles = a.n_mtiles * a.n_ntiles;
+    int splits = (3 * sm_count() + tiles - 1) / tiles;
+    const int max_splits = (a.chunks_total + 15) / 16;     // at least 16 k-chunks (512 samples) per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    a.splits = splits;
+  }
+  a.chunks_per_split = (a.chunks_total + a.splits - 1) / a.splits;
+  a.splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
+  a.n_units = a.n_mtiles * a.n_ntiles * a.splits;
+  a.drain_every = 1;            // 32 k-elements (12 MMAs) per TMEM partial sum
+  a.epi = g.epi; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
+  a.idx = g.idx; a.F = g.F; a.Kemb = g.Kemb; a.hot = g.hot; a.err = nullptr;
+  HHFM_REQUIRE(g.epi == TF_EPI_SCATTER || g.epi == TF_EPI_ATOMIC || ((g.ldc % 4) == 0 && ((uintptr_t)g.C & 15) == 0),
+               "tf_gemm: C must be 16-byte aligned with ldc %% 4 == 0");
+  CUtensorMap tA, tAl, tB, tBl;
+  int rc;
+  if ((rc = make_tmap_f32(&tA, g.A, g.M, g.K, g.lda, kTfM))) return rc;
+  if ((rc = make_tmap_f32(&tAl, g.A_lo, g.M, g.K, g.lda, kTfM))) return rc;
+  if ((rc = make_tmap_f32(&tB, g.B, g.N, g.K, g.ldb, a.bn))) return rc;
+  if ((rc = make_tmap_f32(&tBl, g.B_lo, g.N, g.K, g.ldb, a.bn))) return rc;
+  const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
+  tf32x3_gemm_kernel<<<grid, kTfThreads, kTfSmemBytes, st>>>(tA, tAl, tB, tBl, a);
+  return check_launch("tf32x3_gemm_kernel");
+}
+
+int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, int64_t ldt,
+                       cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HHFM_OK;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  split_transpose_kernel<<<grid, 256, 0, st>>>(X, rows, cols, ld, Xlo, XT, XTlo, ldt);
+  return check_launch("split_transpose_kernel");
+}
+
+int tf_gather_x0(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, cudaStream_t st) {
+  int64_t blocks = (B * F * (K >> 2) + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gather_x0_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, B, F, K, V, X0, ld);
+  return check_launch("gather_x0_kernel");
+}
+
+int tf_colsum(const float* X, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st) {
+  int64_t bx = (rows + 8 * 64 - 1) / (8 * 64);
+  if (bx > 2 * sm_count()) bx = 2 * sm_count();
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)((cols + 31) / 32));
+  colsum_kernel<<<grid, 256, 0, st>>>(X, rows, cols, ld, out);
+  return check_launch("colsum_kernel");
+}
+
+int tf_prep_weight(const float* W, int rows, int cols, float* Wp, float* Wplo, int ldp, float* WT, float* WTlo, int ldtp,
+                   cudaStream_t st) {
+  const int64_t n = (int64_t)rows * cols;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  prep_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, rows, cols, Wp, Wplo, ldp, WT, WTlo, ldtp);
+  return check_launch("prep_weight_kernel");
+}
+
+}  // namespace hhfm
+
+using namespace hhfm;
+
+// C[M,N] = A[M,K] . B[N,K]^T with fp32-grade accuracy on the tensor cores (3xTF32 split, see the file header).
+// workspace: (M*lda + N*ldb) floats for the lo parts.  lda, ldb, ldc multiples of 4; all pointers 16-byte aligned.
+extern "C" int hhfm_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                   float* C, int64_t ldc, float* workspace, hhfm_stream_t stream) {
+  HHFM_REQUIRE(A && B && C && workspace, "gemm_tn_tf32x3: NULL argument");
+  HHFM_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm_tn_tf32x3: bad sizes");
+  HHFM_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm_tn_tf32x3: leading dimensions too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Alo = workspace;
+  float* Blo = workspace + M * lda;
+  int rc;
+  if ((rc = tf_split_transpose(A, M, (int)K, lda, Alo, nullptr, nullptr, 0, st))) return rc;
+  if ((rc = tf_split_transpose(B, N, (int)K, ldb, Blo, nullptr, nullptr, 0, st))) return rc;
+  TfGemm g{};
+  g.A = A; g.A_lo = Alo; g.B = B; g.B_lo = Blo; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = lda; g.ldb = ldb;
+  g.epi = TF_EPI_STORE; g.C = C; g.ldc = ldc;
+  return tf_gemm(g, st);
+}

@@ -1,0 +1,36 @@
+// Internal interface of the 3xTF32 tensor-core GEMM used by the DeepFM tower (dfm_tc.cu); see that file for the scheme.
+#pragma once
+#include "common.cuh"
+
+namespace hhfm {
+
+enum { TF_EPI_STORE = 0, TF_EPI_BIAS_RELU = 1, TF_EPI_MASK = 2, TF_EPI_ATOMIC = 3, TF_EPI_SCATTER = 4 };
+
+// C[M,N] (epilogue) = A[M,K] . B[N,K]^T, all row-major with the K index contiguous; *_lo = x - tf32(x) of the same shape.
+struct TfGemm {
+  const float* A;
+  const float* A_lo;
+  const float* B;
+  const float* B_lo;
+  int M, N, K;
+  int64_t lda, ldb;
+  int epi;
+  float* C;              // EPI_SCATTER: the embedding gradient table
+  int64_t ldc;
+  const float* bias;     // EPI_BIAS_RELU
+  const float* mask;     // EPI_MASK (may alias C)
+  int64_t ldmask;
+  const int32_t* idx;    // EPI_SCATTER: [M, F] ids; output column n belongs to row idx[m, n / Kemb], element n % Kemb
+  int F, Kemb;
+  HotPlan hot;           // EPI_SCATTER: optional hot-row replicas
+};
+
+int tf_gemm(const TfGemm& g, cudaStream_t st);
+int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, int64_t ldt,
+                       cudaStream_t st);
+int tf_gather_x0(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, cudaStream_t st);
+int tf_colsum(const float* X, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st);
+int tf_prep_weight(const float* W, int rows, int cols, float* Wp, float* Wplo, int ldp, float* WT, float* WTlo, int ldtp,
+                   cudaStream_t st);
+
+}  // namespace hhfm

@@ -176,6 +176,12 @@ int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
                             const float* labels, float* workspace, float* out, float* gV, float* gbias,
                             float* gparams, float* loss_partials, hhfm_stream_t stream);
 
+/* fp32-accurate GEMM on the tensor cores (the building block of the DeepFM tower, dfm_tc.cu): C[M,N] = A[M,K] . B[N,K]^T,
+ * row-major operands with K contiguous, 3xTF32 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi) with fp32 accumulation in TMEM.
+ * lda / ldb / ldc are multiples of 4 floats, pointers 16-byte aligned; workspace: (M*lda + N*ldb) floats. */
+int hhfm_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K, float* C,
+                        int64_t ldc, float* workspace, hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K3  HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88) pairwise ranking
  * Record layout (int32, row stride `stride` >= 2+n_ctx+n_time+n_neg, stride % 4 == 0, 16-byte aligned):

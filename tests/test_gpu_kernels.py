@@ -899,3 +899,27 @@ def test_expand_rows_and_auc_count(cuda):
     wins = torch.zeros(1, dtype=torch.int64, device=cuda)
     engine.auc_wins(dev(pos, cuda), dev(neg, cuda), num, wins)
     assert int(wins.item()) == int((np.repeat(pos, num) > neg).sum())
+
+
+# ----------------------------------------------------------------------------------------------------
+# 3xTF32 tensor-core GEMM (building block of the DeepFM tower): fp32-grade accuracy against float64
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (300, 150, 640), (5000, 200, 150), (1000, 640, 150), (640, 150, 4096),
+                                   (129, 16, 8), (4096, 256, 256), (77, 300, 100)])
+def test_tf32x3_gemm_is_fp32_accurate(cuda, M, N, K):
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(M + N + K)
+    lda = (K + 3) // 4 * 4 + 4; ldb = (K + 3) // 4 * 4; ldc = (N + 3) // 4 * 4
+    A = np.zeros((M, lda), np.float32); B = np.zeros((N, ldb), np.float32)
+    A[:, :K] = rng.normal(0, 1, (M, K)); B[:, :K] = rng.normal(0, 1, (N, K))
+    A[:, K:] = 7.0; B[:, K:] = -3.0                                  # padding must never be read
+    tA = dev(A, cuda); tB = dev(B, cuda)
+    C = torch.full((M, ldc), 99.0, device=cuda)
+    ws = torch.empty(M * lda + N * ldb, device=cuda)
+    lib.call("hhfm_gemm_tn_tf32x3", ptr(tA), lda, ptr(tB), ldb, M, N, K, ptr(C), ldc, ptr(ws), st())
+    got = C.cpu().numpy()
+    ref = A[:, :K].astype(np.float64) @ B[:, :K].astype(np.float64).T
+    scale = np.sqrt(K)                                                # typical magnitude of a dot product of K N(0,1) terms
+    err = np.abs(got[:, :N] - ref).max() / scale
+    assert err < 4e-6, "3xTF32 GEMM error %.3e (relative to sqrt(K)); plain tf32 would be ~5e-4" % err
+    assert (got[:, N:] == 99.0).all()
