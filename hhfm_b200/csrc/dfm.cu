@@ -17,7 +17,10 @@
 // Parameter block (one flat caller-owned buffer, gradients use the same layout):
 //   [ layer_0 (d0 x d1) | ... | layer_{L-1} (d_{L-1} x d_L) | concat_projection (F+K+d_L) |   <- l2-regularised part
 //     bias_0 (d1) | ... | bias_{L-1} (d_L) | concat_bias (1) ]
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "dfm_tc.cuh"
 
 namespace hhfm {
 
@@ -42,6 +45,7 @@ struct GemmArgs {
   int64_t ldmask;
   float* colsum;         // EPI_MASK, optional: colsum[n] += sum_m C[m,n]
   int k_chunk;           // split-K: blockIdx.z covers [z*k_chunk, (z+1)*k_chunk)
+  HotPlan hot;           // EPI_SCATTER: optional hot-row replicas
 };
 
 // A-operand element (m, k).  In the gather modes (f, c) = (field, offset inside the embedding row) of the gathered
@@ -166,7 +170,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       // d(H_0)[m, n] belongs to embedding row idx[m, n / K], element n % K; 4 consecutive n share a row (K % 4 == 0)
       if (nb < g.N) {
         const int row = __ldg(g.idx + (int64_t)m * g.F + sf);
-        red_add_v4(g.C + (int64_t)row * g.K + (nb - sf * g.K), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+        float* dstrow = g.C + (int64_t)row * g.K;
+        if (g.hot.slot) {
+          const int hs = __ldg(g.hot.slot + row);
+          if (hs >= 0) dstrow = g.hot.ghot + ((size_t)(blockIdx.x % g.hot.n_rep) * g.hot.n_hot + hs) * g.K;
+        }
+        red_add_v4(dstrow + (nb - sf * g.K), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
       }
       continue;
     }
@@ -239,6 +248,7 @@ struct HeadArgs {
   float* gcbias;           // [1]
   float* gblast;           // [D]  bias gradient of the last hidden layer = column sums of dZ_L
   float* loss_partials;
+  HotPlan hot;             // optional hot-row replicas for the FM-part scatter
 };
 
 constexpr int kHeadT = 8;    // D <= 32 * kHeadT
@@ -269,6 +279,7 @@ __global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
 #pragma unroll
   for (int t = 0; t < kHeadT; t++) p3[t] = (lane + 32 * t < D) ? __ldg(a.proj + F + K + lane + 32 * t) : 0.f;
 
+  const int rep = a.hot.slot ? (int)(warp_g % a.hot.n_rep) : 0;
   float g1 = 0.f, gcb = 0.f, loss_acc = 0.f;
   float4 g2[VPL];
   float g3[kHeadT], gbl[kHeadT];
@@ -330,11 +341,17 @@ __global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
       if (j < D) hrow[j] = dz;
     }
     // FM part of the embedding gradient: dV[x_f] += g * proj2 * (S - e_f);  d feature_bias[x_f] += g * proj1[f]
-    if (lane < F) atomicAdd(a.gfbias + my_id, g * p1);
+    const int my_slot = (a.hot.slot && lane < F) ? __ldg(a.hot.slot + my_id) : -1;
+    if (lane < F) {
+      float* pb = a.gfbias + my_id;
+      if (my_slot >= 0 && a.hot.ghot_bias != nullptr) pb = a.hot.ghot_bias + (size_t)rep * a.hot.n_hot + my_slot;
+      atomicAdd(pb, g * p1);
+    }
     for (int f = 0; f < F; f++) {
       const int id = __shfl_sync(0xffffffffu, my_id, f);
       const float4* row = reinterpret_cast<const float4*>(a.V) + (size_t)id * kv;
-      float* dst = a.gV + (size_t)id * K;
+      const int slot = __shfl_sync(0xffffffffu, my_slot, f);
+      float* dst = (slot >= 0) ? a.hot.ghot + ((size_t)rep * a.hot.n_hot + slot) * K : a.gV + (size_t)id * K;
 #pragma unroll
       for (int i = 0; i < VPL; i++) {
         const int c = lane + 32 * i;
@@ -455,6 +472,77 @@ static int dfm_forward(const int32_t* idx, int64_t B, int64_t F, const float* V,
   return HHFM_OK;
 }
 
+// ---- tensor-core path (dfm_tc.cu): every activation tensor X_l (l = 0: flattened embeddings, l >= 1: H_l, later dZ_l)
+// lives in four forms: X [B, ld_l], X_lo, and the k-blocked transposes X^T / X^T_lo ([B/32 panels][d_l][32]); every layer matrix in padded forms W [d_i, ldp_i] (+lo)
+// and W^T [d_{i+1}, ldt_i] (+lo).
+struct DfmTcLayout {
+  int64_t ldB;
+  int64_t x[kDfmMaxLayers + 1], xlo[kDfmMaxLayers + 1], xt[kDfmMaxLayers + 1], xtlo[kDfmMaxLayers + 1];
+  int64_t ldx[kDfmMaxLayers + 1];
+  int64_t w[kDfmMaxLayers], wlo[kDfmMaxLayers], wt[kDfmMaxLayers], wtlo[kDfmMaxLayers];
+  int ldp[kDfmMaxLayers], ldt[kDfmMaxLayers];
+  int64_t scratch, scratch_floats;      // split-K partial tiles of the weight-gradient GEMMs
+  int64_t total;
+};
+
+static bool dfm_use_tc(int64_t K) {
+  const char* e = getenv("HHFM_DFM_TC");       // 0 = fp32 CUDA-core GEMMs, unset/1 = 3xTF32 tensor-core GEMMs
+  if (e && e[0] == '0') return false;
+  return K % 16 == 0;                          // the scatter epilogue maps 16-column chunks to one embedding row
+}
+
+static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t) {
+  auto r4 = [](int64_t x) { return (x + 3) / 4 * 4; };
+  t.ldB = (B + 31) / 32 * 32;          // the transposed forms are k-blocked panels of 32 samples
+  int64_t o = 0;
+  for (int l = 0; l <= lo.L; l++) {
+    t.ldx[l] = r4(lo.d[l]);
+    t.x[l] = o; o += B * t.ldx[l];
+    t.xlo[l] = o; o += B * t.ldx[l];
+    t.xt[l] = o; o += (int64_t)lo.d[l] * t.ldB;
+    t.xtlo[l] = o; o += (int64_t)lo.d[l] * t.ldB;
+  }
+  for (int i = 0; i < lo.L; i++) {
+    t.ldp[i] = (int)r4(lo.d[i + 1]);
+    t.ldt[i] = (int)r4(lo.d[i]);
+    t.w[i] = o; o += (int64_t)lo.d[i] * t.ldp[i];
+    t.wlo[i] = o; o += (int64_t)lo.d[i] * t.ldp[i];
+    t.wt[i] = o; o += (int64_t)lo.d[i + 1] * t.ldt[i];
+    t.wtlo[i] = o; o += (int64_t)lo.d[i + 1] * t.ldt[i];
+  }
+  t.scratch = r4(o);
+  t.scratch_floats = tf_splitk_scratch_floats();
+  t.total = t.scratch + t.scratch_floats;
+}
+
+static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
+                          const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st) {
+  int rc;
+  for (int i = 0; i < lo.L; i++)
+    if ((rc = tf_prep_weight(params + lo.w_off[i], lo.d[i], lo.d[i + 1], ws + t.w[i], ws + t.wlo[i], t.ldp[i], ws + t.wt[i],
+                             ws + t.wtlo[i], t.ldt[i], st)))
+      return rc;
+  if ((rc = tf_gather_x0(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], st))) return rc;
+  if ((rc = tf_split_transpose(ws + t.x[0], B, lo.d[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
+                               train ? ws + t.xtlo[0] : nullptr, st)))
+    return rc;
+  for (int i = 0; i < lo.L; i++) {
+    TfGemm g{};
+    g.A = ws + t.x[i]; g.A_lo = ws + t.xlo[i]; g.lda = t.ldx[i];
+    g.B = ws + t.wt[i]; g.B_lo = ws + t.wtlo[i]; g.ldb = t.ldt[i];
+    g.M = (int)B; g.N = lo.d[i + 1]; g.K = lo.d[i];
+    g.epi = TF_EPI_BIAS_RELU; g.C = ws + t.x[i + 1]; g.ldc = t.ldx[i + 1]; g.bias = params + lo.b_off[i];
+    if ((rc = tf_gemm(g, st))) return rc;
+    if (i + 1 < lo.L) {   // H_L is consumed by the head kernel as is (and replaced by dZ_L, split afterwards)
+      const bool need_t = train;
+      if ((rc = tf_split_transpose(ws + t.x[i + 1], B, lo.d[i + 1], t.ldx[i + 1], ws + t.xlo[i + 1],
+                                   need_t ? ws + t.xt[i + 1] : nullptr, need_t ? ws + t.xtlo[i + 1] : nullptr, st)))
+        return rc;
+    }
+  }
+  return HHFM_OK;
+}
+
 }  // namespace hhfm
 
 using namespace hhfm;
@@ -475,6 +563,11 @@ extern "C" int64_t hhfm_workspace_bytes_dfm(int64_t B, int64_t F, int64_t K, int
                                             const int32_t* layer_sizes) {
   DfmLayout lo;
   if (dfm_layout(B, F, K, n_layers, layer_sizes, lo) != HHFM_OK) return -1;
+  if (dfm_use_tc(K)) {
+    DfmTcLayout t;
+    dfm_tc_layout(B, lo, t);
+    return t.total * (int64_t)sizeof(float);
+  }
   return lo.ws_floats * (int64_t)sizeof(float);
 }
 
@@ -488,12 +581,21 @@ extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const floa
   int rc = dfm_layout(B, F, K, n_layers, layer_sizes, lo);
   if (rc != HHFM_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
-  if (rc != HHFM_OK) return rc;
   HeadArgs h{};
   h.idx = idx; h.B = B; h.F = (int)F; h.K = (int)K; h.D = lo.d[lo.L];
-  h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off;
-  h.H = workspace + lo.h_off[lo.L]; h.ldh = lo.ld[lo.L]; h.out = out;
+  h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off; h.out = out;
+  if (dfm_use_tc(K)) {
+    DfmTcLayout t;
+    dfm_tc_layout(B, lo, t);
+    HHFM_REQUIRE(((uintptr_t)workspace & 15) == 0, "dfm_fwd: workspace must be 16-byte aligned");
+    rc = dfm_tc_forward(idx, B, F, V, K, params, lo, t, workspace, false, st);
+    if (rc != HHFM_OK) return rc;
+    h.H = workspace + t.x[lo.L]; h.ldh = t.ldx[lo.L];
+    return launch_head<false>(h, st);
+  }
+  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
+  if (rc != HHFM_OK) return rc;
+  h.H = workspace + lo.h_off[lo.L]; h.ldh = lo.ld[lo.L];
   return launch_head<false>(h, st);
 }
 
@@ -501,23 +603,67 @@ extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
                                        const float* feature_bias, int64_t M, int64_t K, const float* params,
                                        int32_t n_layers, const int32_t* layer_sizes, const float* labels,
                                        float* workspace, float* out, float* gV, float* gbias, float* gparams,
-                                       float* loss_partials, hhfm_stream_t stream) {
+                                       float* loss_partials, const int32_t* hot_slot, float* ghot, float* ghot_bias,
+                                       int32_t n_rep, int32_t n_hot, hhfm_stream_t stream) {
   HHFM_REQUIRE(idx && V && feature_bias && params && workspace && labels && gV && gbias && gparams && loss_partials,
                "dfm_fwd_bwd_sqloss: NULL argument");
   HHFM_REQUIRE(B > 0 && B < (1ll << 31) && M > 0, "dfm_fwd_bwd_sqloss: bad sizes");
   DfmLayout lo;
   int rc = dfm_layout(B, F, K, n_layers, layer_sizes, lo);
   if (rc != HHFM_OK) return rc;
+  HHFM_REQUIRE(!hot_slot || (ghot && n_rep >= 1 && n_hot >= 1), "dfm_fwd_bwd_sqloss: hot_slot needs ghot, n_rep, n_hot");
   cudaStream_t st = (cudaStream_t)stream;
   const int L = lo.L;
-  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
-  if (rc != HHFM_OK) return rc;
+  const HotPlan hot{hot_slot, ghot, ghot_bias, n_rep, n_hot};
   HeadArgs h{};
   h.idx = idx; h.B = B; h.F = (int)F; h.K = (int)K; h.D = lo.d[L];
   h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off;
-  h.H = workspace + lo.h_off[L]; h.ldh = lo.ld[L]; h.labels = labels; h.out = out;
+  h.labels = labels; h.out = out;
   h.gV = gV; h.gfbias = gbias; h.gproj = gparams + lo.proj_off; h.gcbias = gparams + lo.cbias_off;
-  h.gblast = gparams + lo.b_off[L - 1]; h.loss_partials = loss_partials;
+  h.gblast = gparams + lo.b_off[L - 1]; h.loss_partials = loss_partials; h.hot = hot;
+  if (dfm_use_tc(K)) {
+    DfmTcLayout t;
+    dfm_tc_layout(B, lo, t);
+    HHFM_REQUIRE(((uintptr_t)workspace & 15) == 0, "dfm_fwd_bwd_sqloss: workspace must be 16-byte aligned");
+    float* ws = workspace;
+    if ((rc = dfm_tc_forward(idx, B, F, V, K, params, lo, t, ws, true, st))) return rc;
+    h.H = ws + t.x[L]; h.ldh = t.ldx[L];
+    if ((rc = launch_head<true>(h, st))) return rc;
+    // dZ_L (in the X_L block) -> lo / transposed forms
+    if ((rc = tf_split_transpose(ws + t.x[L], B, lo.d[L], t.ldx[L], ws + t.xlo[L], ws + t.xt[L], ws + t.xtlo[L], st))) return rc;
+    for (int i = L - 1; i >= 0; i--) {
+      // bias gradient of layer i (the head kernel already produced the last one)
+      if (i < L - 1 && (rc = tf_colsum(ws + t.x[i + 1], B, lo.d[i + 1], t.ldx[i + 1], gparams + lo.b_off[i], st))) return rc;
+      // d layer_i = H_i^T . dZ_{i+1}: A = X_i^T [d_i, B], B = dZ_{i+1}^T [d_{i+1}, B], split over the samples
+      TfGemm w{};
+      w.A = ws + t.xt[i]; w.A_lo = ws + t.xtlo[i]; w.B = ws + t.xt[i + 1]; w.B_lo = ws + t.xtlo[i + 1]; w.k_blocked = 1;
+      w.M = lo.d[i]; w.N = lo.d[i + 1]; w.K = (int)B;
+      w.epi = TF_EPI_ATOMIC; w.C = gparams + lo.w_off[i]; w.ldc = lo.d[i + 1];
+      w.scratch = ws + t.scratch; w.scratch_floats = t.scratch_floats;
+      if ((rc = tf_gemm(w, st))) return rc;
+      // d H_i = dZ_{i+1} . layer_i^T: A = dZ_{i+1} [B, d_{i+1}], B = layer_i [d_i, d_{i+1}]
+      TfGemm x{};
+      x.A = ws + t.x[i + 1]; x.A_lo = ws + t.xlo[i + 1]; x.lda = t.ldx[i + 1];
+      x.B = ws + t.w[i]; x.B_lo = ws + t.wlo[i]; x.ldb = t.ldp[i];
+      x.M = (int)B; x.N = lo.d[i]; x.K = lo.d[i + 1];
+      if (i == 0) {
+        x.epi = TF_EPI_SCATTER; x.C = gV; x.idx = idx; x.F = (int)F; x.Kemb = (int)K; x.hot = hot;
+        if ((rc = tf_gemm(x, st))) return rc;
+      } else {
+        // unmasked product into the (no longer needed) lo block of H_i; the split pass applies relu'(H_i) and leaves dZ_i in
+        // the H_i block, its lo part in the lo block and the k-blocked transposes
+        x.epi = TF_EPI_STORE; x.C = ws + t.xlo[i]; x.ldc = t.ldx[i];
+        if ((rc = tf_gemm(x, st))) return rc;
+        if ((rc = tf_split_transpose(ws + t.xlo[i], B, lo.d[i], t.ldx[i], ws + t.xlo[i], ws + t.xt[i], ws + t.xtlo[i], st,
+                                     ws + t.x[i], ws + t.x[i])))
+          return rc;
+      }
+    }
+    return HHFM_OK;
+  }
+  rc = dfm_forward(idx, B, F, V, K, params, lo, workspace, st);
+  if (rc != HHFM_OK) return rc;
+  h.H = workspace + lo.h_off[L]; h.ldh = lo.ld[L];
   rc = launch_head<true>(h, st);
   if (rc != HHFM_OK) return rc;
   // backward through the tower: layer i maps H_i -> H_{i+1}; dZ_{i+1} lives in the H_{i+1} block
@@ -542,7 +688,7 @@ extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
     x.A = dZ; x.lda = lo.ld[i + 1];
     x.B = params + lo.w_off[i]; x.ldb = lo.d[i + 1];
     if (i == 0) {
-      x.C = gV; x.idx = idx; x.F = (int)F; x.K = (int)K;
+      x.C = gV; x.idx = idx; x.F = (int)F; x.K = (int)K; x.hot = hot;
       rc = launch_gemm<A_ROW, B_COL, EPI_SCATTER>(x, st);
     } else {
       x.C = workspace + lo.h_off[i]; x.ldc = lo.ld[i];

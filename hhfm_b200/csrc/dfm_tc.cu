@@ -16,6 +16,7 @@
 // Roles per CTA (320 threads): warp 4 = TMA producer, warp 5 = single-thread MMA issuer, warps 0-3 and 6-9 = epilogue
 // (two per TMEM lane quarter, alternating 32-column chunks); 2 smem stages of {A_hi, A_lo, B_hi, B_lo}, 2 TMEM accumulators.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dfm_tc.cuh"
@@ -25,12 +26,12 @@ namespace hhfm {
 
 constexpr int kTfM = 128;           // rows per CTA tile (UMMA M)
 constexpr int kTfKC = 32;           // fp32 per 128-byte swizzle row
-constexpr int kTfThreads = 320;
-constexpr int kTfStages = 2;
+constexpr int kTfEpiWarps = 16;     // 4 per TMEM lane quarter
+constexpr int kTfThreads = (2 + kTfEpiWarps) * 32;   // warps 0-3, 6-17: epilogue; warp 4: TMA; warp 5: MMA
+constexpr int kTfMaxStages = 4;
 constexpr int kTfABytes = kTfM * 128;            // one A tile (hi or lo)
-constexpr int kTfBBytesMax = 256 * 128;          // one B tile at bn = 256
-constexpr int kTfStageBytes = 2 * kTfABytes + 2 * kTfBBytesMax;
-constexpr int kTfSmemBytes = kTfStages * kTfStageBytes + 1024 + 256;
+constexpr int kTfSmemBudget = 216 * 1024;        // operand stages (the rest of the 227 KB: barriers + alignment slack)
+constexpr int kTfSmemBytes = kTfSmemBudget + 1024 + 256;
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // lo part: x - hi is exact in fp32 but has up to 13 significant bits; it is stored already ROUNDED to the nearest tf32 so
@@ -44,6 +45,8 @@ struct TfKernelArgs {
   int M, N, K;
   int n_mtiles, n_ntiles, bn, splits, chunks_total, chunks_per_split, n_units;
   int drain_every;       // k-chunks accumulated in TMEM before the partial sum is added into fp32 registers
+  int n_stages, stage_bytes;   // smem pipeline depth / bytes per stage for this bn
+  int a_rpc, b_rpc;            // > 0: operands are k-blocked panels [k-chunk][rows][32]; rows per chunk panel of A / B
   int epi;
   float* C;
   int64_t ldc;
@@ -63,10 +66,10 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
                                                                     const TfKernelArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTfStages * kTfStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTfSmemBudget);
   uint64_t* full = bars;                      // [stages] TMA -> MMA
-  uint64_t* empty = bars + kTfStages;         // [stages] MMA -> TMA
-  uint64_t* t_full = empty + kTfStages;       // [2] accumulator ready
+  uint64_t* empty = bars + kTfMaxStages;      // [stages] MMA -> TMA
+  uint64_t* t_full = empty + kTfMaxStages;    // [2] accumulator ready
   uint64_t* t_empty = t_full + 2;             // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBlo);
-    for (int i = 0; i < kTfStages; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
+    for (int i = 0; i < kTfMaxStages; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, kTfEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
@@ -86,12 +89,13 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
   const uint32_t b_bytes = (uint32_t)a.bn * 128u;
   const uint32_t stage_tx = 2u * kTfABytes + 2u * b_bytes;
 
-  // unit u -> (m tile, n tile, k split); consecutive units share the n tile and split (B operand stays hot in L2)
+  // unit u -> (n tile, m tile, k split), n tile fastest: the CTAs working at the same time share the A tile (activations,
+  // streamed from HBM once) while the B tiles (weights) are small and stay in L2
   auto decode = [&](int u, int& mt, int& nt, int& sp) {
-    mt = u % a.n_mtiles;
-    const int r = u / a.n_mtiles;
-    nt = r % a.n_ntiles;
-    sp = r / a.n_ntiles;
+    nt = u % a.n_ntiles;
+    const int r = u / a.n_ntiles;
+    mt = r % a.n_mtiles;
+    sp = r / a.n_mtiles;
   };
 
   if (warp == 4) {
@@ -103,12 +107,15 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
         for (int c = c0; c < c1; c++) {
           mbar_wait(empty + st, ph ^ 1, a.err);
           mbar_expect_tx(full + st, stage_tx);
-          uint8_t* sb = smem + st * kTfStageBytes;
-          tma_load_2d(sb, &tmA, c * kTfKC, mt * kTfM, full + st);
-          tma_load_2d(sb + kTfABytes, &tmAlo, c * kTfKC, mt * kTfM, full + st);
-          tma_load_2d(sb + 2 * kTfABytes, &tmB, c * kTfKC, nt * a.bn, full + st);
-          tma_load_2d(sb + 2 * kTfABytes + kTfBBytesMax, &tmBlo, c * kTfKC, nt * a.bn, full + st);
-          if (++st == kTfStages) { st = 0; ph ^= 1; }
+          uint8_t* sb = smem + st * a.stage_bytes;
+          // row-major operands: tile = (columns of k-chunk c, rows of the tile); k-blocked panels: tile = rows of panel c
+          const int ax = a.a_rpc ? 0 : c * kTfKC, ay = a.a_rpc ? c * a.a_rpc + mt * kTfM : mt * kTfM;
+          const int bx = a.b_rpc ? 0 : c * kTfKC, by = a.b_rpc ? c * a.b_rpc + nt * a.bn : nt * a.bn;
+          tma_load_2d(sb, &tmA, ax, ay, full + st);
+          tma_load_2d(sb + kTfABytes, &tmAlo, ax, ay, full + st);
+          tma_load_2d(sb + 2 * kTfABytes, &tmB, bx, by, full + st);
+          tma_load_2d(sb + 2 * kTfABytes + b_bytes, &tmBlo, bx, by, full + st);
+          if (++st == a.n_stages) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -128,8 +135,8 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
           const uint32_t d = tmem_base + (uint32_t)(acc * 256);
           mbar_wait(full + st, ph, a.err);
           tc_fence_after();
-          const uint32_t sb = smem_u32(smem + st * kTfStageBytes);
-          const uint32_t ah = sb, al = sb + kTfABytes, bh = sb + 2 * kTfABytes, bl = bh + kTfBBytesMax;
+          const uint32_t sb = smem_u32(smem + st * a.stage_bytes);
+          const uint32_t ah = sb, al = sb + kTfABytes, bh = sb + 2 * kTfABytes, bl = bh + b_bytes;
 #pragma unroll
           for (int k4 = 0; k4 < 4; k4++) {          // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
             const uint32_t o = k4 * 32;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
             umma_tf32(d, make_sdesc(ah + o), make_sdesc(bh + o), idesc, 1u);
           }
           umma_commit(empty + st);
-          if (++st == kTfStages) { st = 0; ph ^= 1; }
+          if (++st == a.n_stages) { st = 0; ph ^= 1; }
           if (((c - c0) % a.drain_every) == a.drain_every - 1 || c == c1 - 1) {
             umma_commit(t_full + acc);              // partial sum complete: hand it to the epilogue warps
             if (++acc == 2) { acc = 0; tph ^= 1; }
@@ -149,9 +156,13 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
   } else {
     // ---- epilogue: thread = (TMEM lane quarter, lane) owns output row m = mt*128 + quarter*32 + lane; the two warps of
     // a quarter take alternating 32-column chunks ----
-    const int quarter = warp & 3, half = warp >= 6 ? 1 : 0;
+    // epilogue warps are 0-3 and 6-17: warp & 3 is the TMEM lane quarter a warp may touch, `sub` its turn among the
+    // four warps of the quarter (16-column chunk c belongs to the warp with c % 4 == sub)
+    const int quarter = warp & 3;
+    const int ew = warp < 4 ? warp : warp - 2;          // 0..15
+    const int sub = ew >> 2;
     int acc = 0; uint32_t tph = 0;
-    const int n_chunks = (a.bn + 31) / 32;
+    const int n_chunks = a.bn / 16;                     // 16-column chunks (bn is a multiple of 16)
     const int rep = a.hot.slot ? (int)(blockIdx.x % a.hot.n_rep) : 0;
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       int mt, nt, sp; decode(u, mt, nt, sp);
@@ -163,55 +174,60 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
       // partial sum of `drain_every` k-chunks; the partial sums are added here in registers with round-to-nearest.
       const int c1k = min(a.chunks_total, c0k + a.chunks_per_split);
       const int n_drains = has_work ? (c1k - c0k + a.drain_every - 1) / a.drain_every : 0;
-      float accr[4][32];
+      float accr[4][16];
       for (int dr = 0; dr < n_drains; dr++) {
         mbar_wait(t_full + acc, tph, a.err);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const int c = half + 2 * j;
+          const int c = sub + 4 * j;
           if (c < n_chunks) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c * 32, r);
-            tmem_ld_wait_for(r);
+            uint32_t r[16];
+            tmem_ld16(taddr + c * 16, r);
+            tmem_ld_wait_for16(r);
 #pragma unroll
-            for (int i = 0; i < 32; i++) accr[j][i] = (dr == 0) ? __uint_as_float(r[i]) : accr[j][i] + __uint_as_float(r[i]);
+            for (int i = 0; i < 16; i++) accr[j][i] = (dr == 0) ? __uint_as_float(r[i]) : accr[j][i] + __uint_as_float(r[i]);
           }
         }
         tc_fence_before();
         mbar_arrive(t_empty + acc);
         if (++acc == 2) { acc = 0; tph ^= 1; }
       }
+      if (a.epi == TF_EPI_SCATTER) {
+        // d(H_0)[m, n] belongs to embedding row idx[m, n / Kemb], element n % Kemb.  A 16-column chunk lies inside one
+        // field (Kemb % 16 == 0 is required by the host), so the id and hot-slot lookups of all four chunks are issued
+        // together before the reductions (they were a chain of 32 dependent global loads per unit).
+        float* dstp[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int n = nt * a.bn + (sub + 4 * j) * 16;
+          dstp[j] = nullptr;
+          if (sub + 4 * j < n_chunks && m < a.M && has_work && n < a.N) {
+            const int f = n / a.Kemb;
+            const int row = __ldg(a.idx + (int64_t)m * a.F + f);
+            const int hs = a.hot.slot ? __ldg(a.hot.slot + row) : -1;
+            dstp[j] = (hs >= 0 ? a.hot.ghot + ((size_t)rep * a.hot.n_hot + hs) * a.Kemb : a.C + (int64_t)row * a.Kemb) + (n - f * a.Kemb);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (dstp[j] == nullptr) continue;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) red_add_v4(dstp[j] + i, make_float4(accr[j][i], accr[j][i + 1], accr[j][i + 2], accr[j][i + 3]));
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int c = half + 2 * j;
+        const int c = sub + 4 * j;
         if (c >= n_chunks) continue;
-        const float (&r)[32] = accr[j];
-        const int nb = nt * a.bn + c * 32;
+        const float (&r)[16] = accr[j];
+        const int nb = nt * a.bn + c * 16;
         if (m >= a.M || !has_work) continue;
-        if (a.epi == TF_EPI_SCATTER) {
-          // d(H_0)[m, n] belongs to embedding row idx[m, n / Kemb], element n % Kemb (4 consecutive n share a row)
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int n = nb + i;
-            if (n < a.N && n < (nt + 1) * a.bn) {
-              const int f = n / a.Kemb;
-              const int row = __ldg(a.idx + (int64_t)m * a.F + f);
-              float* dst = a.C + (int64_t)row * a.Kemb;
-              if (a.hot.slot) {
-                const int s = __ldg(a.hot.slot + row);
-                if (s >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + s) * a.Kemb;
-              }
-              red_add_v4(dst + (n - f * a.Kemb), make_float4(r[i], r[i + 1],
-                                                            r[i + 2], r[i + 3]));
-            }
-          }
-          continue;
-        }
         float* crow = a.C + (int64_t)m * a.ldc;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 16; i += 4) {
           const int n = nb + i;
           if (n >= a.N || n >= (nt + 1) * a.bn) continue;
           float v[4] = {r[i], r[i + 1], r[i + 2], r[i + 3]};
@@ -219,15 +235,13 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
           if (a.epi == TF_EPI_BIAS_RELU) {
 #pragma unroll
             for (int q = 0; q < 4; q++) v[q] = (q < nv) ? fmaxf(v[q] + __ldg(a.bias + n + q), 0.f) : 0.f;
-          } else if (a.epi == TF_EPI_MASK) {
-            const float* mrow = a.mask + (int64_t)m * a.ldmask + n;
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = (q < nv && mrow[q] > 0.f) ? v[q] : 0.f;
           }
           if (a.epi == TF_EPI_ATOMIC) {
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-              if (q < nv) atomicAdd(crow + n + q, v[q]);
+            // split-K: this unit's partial tile goes to its own [128][bn] slot of the scratch buffer (plain stores);
+            // reduce_partials_kernel adds the splits into C.  (One atomic per element and split made every weight-gradient
+            // GEMM cost ~0.35 ms regardless of its size: millions of reductions on a few thousand addresses.)
+            float* slot = a.C + ((int64_t)u * kTfM + (quarter * 32 + lane)) * a.bn + (c * 16 + i);
+            *reinterpret_cast<float4*>(slot) = make_float4(v[0], v[1], v[2], v[3]);
           } else if (nv == 4) {
             *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
           } else {
@@ -244,11 +258,17 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
   if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// X [rows, ld] (cols valid) -> X_lo [rows, ld], XT [cols, ldt], XT_lo [cols, ldt]   (ldt >= rows).  32x32 tiles through
-// shared memory so both the row-major reads and the transposed writes are coalesced.  XT / XT_lo may be NULL.
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld,
-                                                              float* __restrict__ Xlo, float* __restrict__ XT,
-                                                              float* __restrict__ XTlo, int64_t ldt) {
+// X [rows, ld] (cols valid) -> X_lo [rows, ld] and the K-BLOCKED transposes XT / XT_lo: panel p = rows [32p, 32p+32) of X
+// stored as [cols][32] (element (r, c) at ((r/32)*cols + c)*32 + r%32), i.e. exactly the 128-byte-row tile a TMA box wants
+// for the weight-gradient GEMM (K = the sample index), contiguous per k-chunk.  A plain [cols, rows] transpose made that
+// GEMM fetch 128 bytes from each of ~600 rows half a megabyte apart per k-chunk (6x slower per chunk than the row-major
+// GEMMs).  Rows beyond `rows` inside the last panel are written as zeros.  32x32 tiles through shared memory so both the
+// reads and the writes are coalesced.  XT / XT_lo may be NULL.
+// With `mask` (the forward activation H of the same shape): v = X * (mask > 0), i.e. the relu backward, and the masked value is
+// also written to Xout (which may alias mask): the d-input GEMM stores the unmasked product and this pass finishes it
+// with coalesced reads (a mask lookup in the GEMM epilogue was a chain of dependent global loads per tile).
+__global__ void split_transpose_kernel(const float* X, const float* mask, float* Xout, int64_t rows, int cols, int64_t ld,
+                                       float* Xlo, float* __restrict__ XT, float* __restrict__ XTlo) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -260,6 +280,10 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
     float v = 0.f;
     if (r < rows && c < cols) {
       v = X[r * ld + c];
+      if (mask) {
+        v = mask[r * ld + c] > 0.f ? v : 0.f;
+        Xout[r * ld + c] = v;
+      }
       if (Xlo) Xlo[r * ld + c] = tf32_lo(v);
     }
     tile[ty + 8 * i][tx] = v;
@@ -269,11 +293,11 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __res
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int c = c0 + ty + 8 * i;
-    const int64_t r = r0 + tx;
-    if (c < cols && r < rows) {
-      const float v = tile[tx][ty + 8 * i];
-      XT[(int64_t)c * ldt + r] = v;
-      if (XTlo) XTlo[(int64_t)c * ldt + r] = tf32_lo(v);
+    if (c < cols) {
+      const float v = tile[tx][ty + 8 * i];                    // zero for rows >= `rows`
+      const int64_t o = ((int64_t)blockIdx.x * cols + c) * 32 + tx;
+      XT[o] = v;
+      if (XTlo) XTlo[o] = tf32_lo(v);
     }
   }
 }
@@ -325,6 +349,21 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
   }
 }
 
+// C[m, n] += sum over splits of the partial tiles written by the split-K epilogue (unit u = nt + n_ntiles*(mt + n_mtiles*sp))
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ scratch, int n_mtiles, int n_ntiles,
+                                                              int splits, int bn, int M, int N, float* __restrict__ C, int64_t ldc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  const int mt = m / kTfM, nt = n / bn;
+  float acc = 0.f;
+  for (int sp = 0; sp < splits; sp++) {
+    const int64_t u = nt + (int64_t)n_ntiles * (mt + (int64_t)n_mtiles * sp);
+    acc += scratch[(u * kTfM + (m - mt * kTfM)) * bn + (n - nt * bn)];
+  }
+  C[(int64_t)m * ldc + n] += acc;
+}
+
 static int make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) {
@@ -345,7 +384,10 @@ static int make_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64
   return HHFM_OK;
 }
 
+int64_t tf_splitk_scratch_floats() { return (int64_t)(sm_count() + 8) * kTfM * 256; }
+
 int tf_pick_bn(int N) {
+  // N-tile width: a multiple of 16, at most 256 (four 16-column chunks per epilogue thread), least padded work first
   if (N <= 256) return (N + 15) / 16 * 16;
   int best = 256, best_cost = 1 << 30;
   for (int bn = 256; bn >= 64; bn -= 16) {
@@ -357,7 +399,7 @@ int tf_pick_bn(int N) {
 
 int tf_gemm(const TfGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return HHFM_OK;
-  HHFM_REQUIRE((g.lda % 4) == 0 && (g.ldb % 4) == 0, "tf_gemm: operand leading dimensions must be multiples of 4 floats");
+  HHFM_REQUIRE(g.k_blocked || ((g.lda % 4) == 0 && (g.ldb % 4) == 0), "tf_gemm: operand leading dimensions must be multiples of 4 floats");
   HHFM_REQUIRE((((uintptr_t)g.A | (uintptr_t)g.A_lo | (uintptr_t)g.B | (uintptr_t)g.B_lo) & 15) == 0, "tf_gemm: operands must be 16-byte aligned");
   static bool attr_set = false;
   if (!attr_set) {
@@ -376,7 +418,7 @@ int tf_gemm(const TfGemm& g, cudaStream_t st) {
   a.splits = 1;
   if (g.epi == TF_EPI_ATOMIC) {
     const int tiles = a.n_mtiles * a.n_ntiles;
-    int splits = (3 * sm_count() + tiles - 1) / tiles;
+    int splits = sm_count() / tiles;                       // one wave: every split ends in tile-sized atomics, keep them few
     const int max_splits = (a.chunks_total + 15) / 16;     // at least 16 k-chunks (512 samples) per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -385,27 +427,61 @@ int tf_gemm(const TfGemm& g, cudaStream_t st) {
   a.chunks_per_split = (a.chunks_total + a.splits - 1) / a.splits;
   a.splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
   a.n_units = a.n_mtiles * a.n_ntiles * a.splits;
-  a.drain_every = 1;            // 32 k-elements (12 MMAs) per TMEM partial sum
+  {
+    // k-chunks (32 k-elements = 12 MMAs each) per TMEM partial sum: 1 gives < 4e-6 relative error; larger values trade
+    // accuracy (the truncation bias grows with the number of accumulation steps) for less epilogue work
+    const char* e = getenv("HHFM_TF_DRAIN");
+    a.drain_every = e ? atoi(e) : 1;
+    if (a.drain_every < 1) a.drain_every = 1;
+  }
+  a.stage_bytes = 2 * kTfABytes + 2 * a.bn * 128;
+  a.n_stages = kTfSmemBudget / a.stage_bytes;
+  if (a.n_stages > kTfMaxStages) a.n_stages = kTfMaxStages;
   a.epi = g.epi; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
+  if (g.epi == TF_EPI_ATOMIC) {
+    HHFM_REQUIRE(g.scratch && ((uintptr_t)g.scratch & 15) == 0, "tf_gemm: split-K needs a 16-byte aligned scratch buffer");
+    HHFM_REQUIRE((int64_t)a.n_units * kTfM * a.bn <= g.scratch_floats, "tf_gemm: split-K scratch too small");
+    a.C = g.scratch;
+  }
   a.idx = g.idx; a.F = g.F; a.Kemb = g.Kemb; a.hot = g.hot; a.err = nullptr;
+  HHFM_REQUIRE(g.epi != TF_EPI_MASK, "tf_gemm: the relu mask is applied by tf_split_transpose, not by the GEMM epilogue");
+  HHFM_REQUIRE(g.epi != TF_EPI_SCATTER || g.Kemb % 16 == 0, "tf_gemm: the scatter epilogue needs an embedding size that is a multiple of 16");
   HHFM_REQUIRE(g.epi == TF_EPI_SCATTER || g.epi == TF_EPI_ATOMIC || ((g.ldc % 4) == 0 && ((uintptr_t)g.C & 15) == 0),
                "tf_gemm: C must be 16-byte aligned with ldc %% 4 == 0");
   CUtensorMap tA, tAl, tB, tBl;
   int rc;
-  if ((rc = make_tmap_f32(&tA, g.A, g.M, g.K, g.lda, kTfM))) return rc;
-  if ((rc = make_tmap_f32(&tAl, g.A_lo, g.M, g.K, g.lda, kTfM))) return rc;
-  if ((rc = make_tmap_f32(&tB, g.B, g.N, g.K, g.ldb, a.bn))) return rc;
-  if ((rc = make_tmap_f32(&tBl, g.B_lo, g.N, g.K, g.ldb, a.bn))) return rc;
+  if (g.k_blocked) {
+    // operands are panels [ceil(K/32)][rows][32]: a 2-D tensor of 128-byte rows; a tile that runs past its panel reads the
+    // next panel's rows, which only feeds output rows / columns beyond M / N (discarded by the epilogue)
+    const int64_t panels = (g.K + kTfKC - 1) / kTfKC;
+    a.a_rpc = g.M; a.b_rpc = g.N;
+    if ((rc = make_tmap_f32(&tA, g.A, panels * g.M, kTfKC, kTfKC, kTfM))) return rc;
+    if ((rc = make_tmap_f32(&tAl, g.A_lo, panels * g.M, kTfKC, kTfKC, kTfM))) return rc;
+    if ((rc = make_tmap_f32(&tB, g.B, panels * g.N, kTfKC, kTfKC, a.bn))) return rc;
+    if ((rc = make_tmap_f32(&tBl, g.B_lo, panels * g.N, kTfKC, kTfKC, a.bn))) return rc;
+  } else {
+    if ((rc = make_tmap_f32(&tA, g.A, g.M, g.K, g.lda, kTfM))) return rc;
+    if ((rc = make_tmap_f32(&tAl, g.A_lo, g.M, g.K, g.lda, kTfM))) return rc;
+    if ((rc = make_tmap_f32(&tB, g.B, g.N, g.K, g.ldb, a.bn))) return rc;
+    if ((rc = make_tmap_f32(&tBl, g.B_lo, g.N, g.K, g.ldb, a.bn))) return rc;
+  }
   const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
   tf32x3_gemm_kernel<<<grid, kTfThreads, kTfSmemBytes, st>>>(tA, tAl, tB, tBl, a);
-  return check_launch("tf32x3_gemm_kernel");
+  if ((rc = check_launch("tf32x3_gemm_kernel"))) return rc;
+  if (g.epi == TF_EPI_ATOMIC) {
+    const int64_t n = (int64_t)g.M * g.N;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g.scratch, a.n_mtiles, a.n_ntiles, a.splits, a.bn, g.M, g.N,
+                                                                       g.C, g.ldc);
+    rc = check_launch("reduce_partials_kernel");
+  }
+  return rc;
 }
 
-int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, int64_t ldt,
-                       cudaStream_t st) {
+int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, cudaStream_t st,
+                       const float* mask, float* Xout) {
   if (rows <= 0 || cols <= 0) return HHFM_OK;
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-  split_transpose_kernel<<<grid, 256, 0, st>>>(X, rows, cols, ld, Xlo, XT, XTlo, ldt);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(X, mask, Xout, rows, cols, ld, Xlo, XT, XTlo);
   return check_launch("split_transpose_kernel");
 }
 
@@ -450,8 +526,8 @@ extern "C" int hhfm_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, 
   float* Alo = workspace;
   float* Blo = workspace + M * lda;
   int rc;
-  if ((rc = tf_split_transpose(A, M, (int)K, lda, Alo, nullptr, nullptr, 0, st))) return rc;
-  if ((rc = tf_split_transpose(B, N, (int)K, ldb, Blo, nullptr, nullptr, 0, st))) return rc;
+  if ((rc = tf_split_transpose(A, M, (int)K, lda, Alo, nullptr, nullptr, st))) return rc;
+  if ((rc = tf_split_transpose(B, N, (int)K, ldb, Blo, nullptr, nullptr, st))) return rc;
   TfGemm g{};
   g.A = A; g.A_lo = Alo; g.B = B; g.B_lo = Blo; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = lda; g.ldb = ldb;
   g.epi = TF_EPI_STORE; g.C = C; g.ldc = ldc;

@@ -14,6 +14,7 @@ struct TfGemm {
   const float* B_lo;
   int M, N, K;
   int64_t lda, ldb;
+  int k_blocked;         // 1: A and B are k-blocked panels [ceil(K/32)][M or N][32] (tf_split_transpose's XT layout)
   int epi;
   float* C;              // EPI_SCATTER: the embedding gradient table
   int64_t ldc;
@@ -23,11 +24,15 @@ struct TfGemm {
   const int32_t* idx;    // EPI_SCATTER: [M, F] ids; output column n belongs to row idx[m, n / Kemb], element n % Kemb
   int F, Kemb;
   HotPlan hot;           // EPI_SCATTER: optional hot-row replicas
+  float* scratch;        // EPI_ATOMIC (split-K): partial tiles, tf_splitk_scratch_floats() floats
+  int64_t scratch_floats;
 };
 
 int tf_gemm(const TfGemm& g, cudaStream_t st);
-int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, int64_t ldt,
-                       cudaStream_t st);
+int64_t tf_splitk_scratch_floats();
+// mask != NULL: v = X * (mask > 0) is what gets split / transposed, and it is also written to Xout (may alias mask)
+int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, cudaStream_t st,
+                       const float* mask = nullptr, float* Xout = nullptr);
 int tf_gather_x0(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, cudaStream_t st);
 int tf_colsum(const float* X, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st);
 int tf_prep_weight(const float* W, int rows, int cols, float* Wp, float* Wplo, int ldp, float* WT, float* WTlo, int ldtp,

@@ -837,9 +837,13 @@ class DeepFM(_Base):
             raise _lib.HhfmError("DeepFM: X has %d columns, field_size is %d" % (F, self.field_size))
         self._opt.begin_step()
         V, fb = self.weights["feature_embeddings"], self.weights["feature_bias"]
+        hot = self._hot_plan(idx, True)
         _lib.call("hhfm_dfm_fwd_bwd_sqloss", ptr(idx), B, F, ptr(V), ptr(fb), self._M, self._K, ptr(self._params),
                   len(self.deep_layers), self._sizes.ctypes.data, ptr(y), ptr(self._workspace(B)), None, ptr(self._gV),
-                  ptr(self._gb), ptr(self._gparams), ptr(self._loss_partials), cur_stream())
+                  ptr(self._gb), ptr(self._gparams), ptr(self._loss_partials), *(hot.args(True) if hot else NO_HOT_BIAS),
+                  cur_stream())
+        if hot:
+            hot.fold(self._gV, self._gb)
         if self._dp_group is not None:
             import torch.distributed as dist
             self._allreduce_grads()

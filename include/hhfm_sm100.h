@@ -162,7 +162,9 @@ int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
  *     [ layer_0 (F*K x d1) | ... | layer_{L-1} | concat_projection (F+K+d_L) | 0-3 zero pad | bias_0 (d1) | ... | bias_{L-1} | concat_bias ]
  *   (row-major matrices; hhfm_dfm_param_count() elements; the first hhfm_dfm_reg_count() carry DFM.py:145-150's l2).
  *   workspace: hhfm_workspace_bytes_dfm(B, ...) bytes, caller-owned (hidden activations, reused for their gradients).
- *   Layer 0 gathers its A operand straight from V; d(H_0) is scattered into gV by the GEMM epilogue.
+ *   The GEMMs run on the tensor cores as 3xTF32 splits with fp32 accumulation (dfm_tc.cu; HHFM_DFM_TC=0 selects the fp32
+ *   CUDA-core GEMMs, whose layer 0 gathers its A operand straight from V); d(H_0) is scattered into gV by the GEMM epilogue
+ *   (optionally through hot-row replicas, as in K1/K3).  workspace: 16-byte aligned.
  *   Gradients ACCUMULATE into gV [M,K], gbias [M], gparams (zero them first).
  * ------------------------------------------------------------------------------------------------ */
 int64_t hhfm_dfm_param_count(int64_t F, int64_t K, int32_t n_layers, const int32_t* layer_sizes);
@@ -174,7 +176,8 @@ int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const
 int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
                             int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
                             const float* labels, float* workspace, float* out, float* gV, float* gbias,
-                            float* gparams, float* loss_partials, hhfm_stream_t stream);
+                            float* gparams, float* loss_partials, const int32_t* hot_slot, float* ghot,
+                            float* ghot_bias, int32_t n_rep, int32_t n_hot, hhfm_stream_t stream);
 
 /* fp32-accurate GEMM on the tensor cores (the building block of the DeepFM tower, dfm_tc.cu): C[M,N] = A[M,K] . B[N,K]^T,
  * row-major operands with K contiguous, 3xTF32 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi) with fp32 accumulation in TMEM.

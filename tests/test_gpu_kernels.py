@@ -712,7 +712,7 @@ def test_dfm_fused_pass_matches_oracle(cuda, B, F, K, layers):
     gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gp = torch.zeros(flat.size, device=cuda)
     lp = torch.zeros(lib.partials_len(), device=cuda); lo = torch.zeros(1, device=cuda); o2 = torch.empty(B, device=cuda)
     lib.call("hhfm_dfm_fwd_bwd_sqloss", ptr(tX), B, F, ptr(tV), ptr(tb), M, K, ptr(tp), L, sizes.ctypes.data,
-             ptr(dev(Y.reshape(-1), cuda)), ptr(ws), ptr(o2), ptr(gV), ptr(gb), ptr(gp), ptr(lp), st())
+             ptr(dev(Y.reshape(-1), cuda)), ptr(ws), ptr(o2), ptr(gV), ptr(gb), ptr(gp), ptr(lp), None, None, None, 0, 0, st())
     lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(lo), st())
     assert_close(o2.cpu().numpy(), out, what="dfm out"); assert_close(lo.item(), loss, what="dfm loss")
     assert_close(gV.cpu().numpy(), g["feature_embeddings"], rtol=2e-5, what="dfm gV")
