@@ -522,9 +522,8 @@ static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float*
     if ((rc = tf_prep_weight(params + lo.w_off[i], lo.d[i], lo.d[i + 1], ws + t.w[i], ws + t.wlo[i], t.ldp[i], ws + t.wt[i],
                              ws + t.wtlo[i], t.ldt[i], st)))
       return rc;
-  if ((rc = tf_gather_x0(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], st))) return rc;
-  if ((rc = tf_split_transpose(ws + t.x[0], B, lo.d[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
-                               train ? ws + t.xtlo[0] : nullptr, st)))
+  if ((rc = tf_gather_split_transpose(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
+                                      train ? ws + t.xtlo[0] : nullptr, st)))
     return rc;
   for (int i = 0; i < lo.L; i++) {
     TfGemm g{};

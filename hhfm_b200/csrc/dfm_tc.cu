@@ -267,8 +267,11 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
 // With `mask` (the forward activation H of the same shape): v = X * (mask > 0), i.e. the relu backward, and the masked value is
 // also written to Xout (which may alias mask): the d-input GEMM stores the unmasked product and this pass finishes it
 // with coalesced reads (a mask lookup in the GEMM epilogue was a chain of dependent global loads per tile).
+// With `gidx` (ids [rows, gF]) X is the embedding table instead: v = X[gidx[r, c / gK], c % gK] (the flattened embeddings
+// of layer 0), written to Xout as the hi operand.
 __global__ void split_transpose_kernel(const float* X, const float* mask, float* Xout, int64_t rows, int cols, int64_t ld,
-                                       float* Xlo, float* __restrict__ XT, float* __restrict__ XTlo) {
+                                       float* Xlo, float* __restrict__ XT, float* __restrict__ XTlo,
+                                       const int32_t* __restrict__ gidx, int gF, int gK) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -279,7 +282,13 @@ __global__ void split_transpose_kernel(const float* X, const float* mask, float*
     const int c = c0 + tx;
     float v = 0.f;
     if (r < rows && c < cols) {
-      v = X[r * ld + c];
+      if (gidx) {
+        const int f = c / gK;
+        v = __ldg(X + (int64_t)__ldg(gidx + r * gF + f) * gK + (c - f * gK));
+        Xout[r * ld + c] = v;
+      } else {
+        v = X[r * ld + c];
+      }
       if (mask) {
         v = mask[r * ld + c] > 0.f ? v : 0.f;
         Xout[r * ld + c] = v;
@@ -481,8 +490,16 @@ int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float
                        const float* mask, float* Xout) {
   if (rows <= 0 || cols <= 0) return HHFM_OK;
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-  split_transpose_kernel<<<grid, 256, 0, st>>>(X, mask, Xout, rows, cols, ld, Xlo, XT, XTlo);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(X, mask, Xout, rows, cols, ld, Xlo, XT, XTlo, nullptr, 0, 0);
   return check_launch("split_transpose_kernel");
+}
+
+// X0 = flattened embeddings V[idx] [B, F*K] with its lo part and (optionally) the k-blocked transposes, in one pass
+int tf_gather_split_transpose(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, float* Xlo,
+                              float* XT, float* XTlo, cudaStream_t st) {
+  dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F * K + 31) / 32));
+  split_transpose_kernel<<<grid, 256, 0, st>>>(V, nullptr, X0, B, F * K, ld, Xlo, XT, XTlo, idx, F, K);
+  return check_launch("split_transpose_kernel(gather)");
 }
 
 int tf_gather_x0(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, cudaStream_t st) {

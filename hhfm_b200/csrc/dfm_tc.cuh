@@ -33,6 +33,8 @@ int64_t tf_splitk_scratch_floats();
 // mask != NULL: v = X * (mask > 0) is what gets split / transposed, and it is also written to Xout (may alias mask)
 int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, cudaStream_t st,
                        const float* mask = nullptr, float* Xout = nullptr);
+int tf_gather_split_transpose(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, float* Xlo,
+                              float* XT, float* XTlo, cudaStream_t st);
 int tf_gather_x0(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, cudaStream_t st);
 int tf_colsum(const float* X, int64_t rows, int cols, int64_t ld, float* out, cudaStream_t st);
 int tf_prep_weight(const float* W, int rows, int cols, float* Wp, float* Wplo, int ldp, float* WT, float* WTlo, int ldtp,
