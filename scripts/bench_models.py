@@ -172,7 +172,10 @@ def run_dfm(args, dev):
     return {"config": "DeepFM frappe-10 (640-150-200-150, K=64), B=2^17", "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
             "algorithmic_flops_per_sample": flops,
             "roofline": {"bound": "fp32-simt", "achieved_tflops": B * flops / ms / 1e9, "peak_tflops": FP32_SIMT_TFLOPS,
-                         "frac": B * flops / ms / 1e9 / FP32_SIMT_TFLOPS}}
+                         "frac": B * flops / ms / 1e9 / FP32_SIMT_TFLOPS,
+                         "note": "GEMMs run as 3xTF32 splits on tcgen05 (fp32-grade accuracy); frac is against the fp32 CUDA-core "
+                                 "peak that bounds an fp32 implementation; against the tensor ceiling of the scheme (measured bf16 "
+                                 "peak / 2 / 3 = 271 TFLOP/s fp32-equivalent) see profiles/r1_dfm_summary.md"}}
 
 
 RUNNERS = {"fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
