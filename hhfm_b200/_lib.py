@@ -31,6 +31,9 @@ SIGNATURES = {
     "hhfm_dfm_fwd_bwd_sqloss": [vp, i64, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32,
                                 vp],
     "hhfm_gemm_tn_tf32x3": [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp, vp],
+    "hhfm_afm_fwd_tc": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp],
+    "hhfm_afm_fwd_bwd_sqloss_tc": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
     "hhfm_pairrank_fwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_pairrank_fwd_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp,
                               vp, vp, vp, i32, i32, i32, vp],
@@ -68,6 +71,7 @@ INT64_FUNCS = {
     "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
+    "hhfm_workspace_bytes_afm": [i64, i64, i64, i64],
     "hhfm_dfm_param_count": [i64, i64, i32, vp],
     "hhfm_dfm_reg_count": [i64, i64, i32, vp],
     "hhfm_workspace_bytes_dfm": [i64, i64, i64, i32, vp],

@@ -56,6 +56,8 @@ __host__ __device__ inline size_t afm_smem_floats(int NW, int F, int K, int A, i
   return (size_t)K * (A + 1) + 2 * (size_t)A + K + (size_t)NW * afm_per_warp_floats(F, K, A, P) + 32;
 }
 
+constexpr int PB = 8;       // pairs per register-blocked sweep of the two matrix products
+
 template <int TK, int TA, int NW, bool TRAIN>
 __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -125,22 +127,22 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
       }
       __syncwarp();
       // ---- attention logits: Z_p = P_p W + b, s_p = relu(Z_p) . p   (4 pairs per sweep over k) ----
-      for (int p0 = 0; p0 < P; p0 += 4) {
-        float acc[4][TA];
+      for (int p0 = 0; p0 < P; p0 += PB) {
+        float acc[PB][TA];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < PB; q++)
 #pragma unroll
           for (int t = 0; t < TA; t++) acc[q][t] = (lane + 32 * t < A) ? sb[lane + 32 * t] : 0.f;
-        const float* ei[4]; const float* ej[4];
+        const float* ei[PB]; const float* ej[PB];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < PB; q++) {
           const int p = min(p0 + q, P - 1);
           ei[q] = sE + sPairI[p] * K; ej[q] = sE + sPairJ[p] * K;
         }
         for (int k = 0; k < K; k += 4) {
-          float pk[4][4];
+          float pk[PB][4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
+          for (int q = 0; q < PB; q++) {
             const float4 x = *reinterpret_cast<const float4*>(ei[q] + k);
             const float4 y = *reinterpret_cast<const float4*>(ej[q] + k);
             pk[q][0] = x.x * y.x; pk[q][1] = x.y * y.y; pk[q][2] = x.z * y.z; pk[q][3] = x.w * y.w;
@@ -152,12 +154,12 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
               const int aa = lane + 32 * t;
               const float w = (aa < A) ? sW[(k + kk) * AS + aa] : 0.f;
 #pragma unroll
-              for (int q = 0; q < 4; q++) acc[q][t] = fmaf(pk[q][kk], w, acc[q][t]);
+              for (int q = 0; q < PB; q++) acc[q][t] = fmaf(pk[q][kk], w, acc[q][t]);
             }
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < PB; q++) {
           const int p = p0 + q;
           if (p < P) {
             float part = 0.f;
@@ -252,18 +254,18 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
         // d P_p = a_p d afm + W d Z_p (lanes over k, 4 pairs per sweep over a) ; d E_i += dP*E_j ; d E_j += dP*E_i
         for (int i = lane; i < F * K; i += 32) sDE[i] = 0.f;
         __syncwarp();
-        for (int p0 = 0; p0 < P; p0 += 4) {
-          float dp[4][TK];
+        for (int p0 = 0; p0 < P; p0 += PB) {
+          float dp[PB][TK];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
+          for (int q = 0; q < PB; q++) {
             const float ap = (p0 + q < P) ? sS[p0 + q] : 0.f;
 #pragma unroll
             for (int t = 0; t < TK; t++) dp[q][t] = ap * dafm[t];
           }
           for (int a0 = 0; a0 < A; a0 += 4) {
-            float dz[4][4];
+            float dz[PB][4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < PB; q++) {
               const float4 v = *reinterpret_cast<const float4*>(sZ + min(p0 + q, P - 1) * A + a0);
               dz[q][0] = v.x; dz[q][1] = v.y; dz[q][2] = v.z; dz[q][3] = v.w;
             }
@@ -274,12 +276,12 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
                 const int k = lane + 32 * t;
                 const float w = (k < K) ? sW[k * AS + a0 + aa] : 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; q++) dp[q][t] = fmaf(w, dz[q][aa], dp[q][t]);
+                for (int q = 0; q < PB; q++) dp[q][t] = fmaf(w, dz[q][aa], dp[q][t]);
               }
             }
           }
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
+          for (int q = 0; q < PB; q++) {
             const int p = p0 + q;
             if (p < P) {
               const int fi = sPairI[p], fj = sPairJ[p];

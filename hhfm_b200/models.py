@@ -662,10 +662,31 @@ class AFM(FM):
     def score_device(self, idx):
         return self._predict_dev(idx)
 
+    def _tc_workspace(self, B, F):
+        """Workspace of the tensor-core path (csrc/afm_tc.cu) when it is selected with HHFM_AFM_TC=1, else None.  The
+        GEMM-ised path is correct (same parity tests) but its K = A = 64 products are too small to win once the pair tensors
+        travel through L2 (18 ms against 12 ms per 2^17 samples, profiles/r1_afm_summary.md): the fused CUDA-core kernel stays
+        the default until the products are fused into one tcgen05 kernel."""
+        import os
+        if os.environ.get("HHFM_AFM_TC", "0") != "1":
+            return None
+        need = int(_lib.load().hhfm_workspace_bytes_afm(B, F, self._K, self._A))
+        if need < 0:
+            return None
+        n = need // 4 + 4
+        if getattr(self, "_tc_ws", None) is None or self._tc_ws.numel() < n:
+            self._tc_ws = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self._tc_ws
+
     def _predict_dev(self, idx):
         B, F = idx.shape
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         W, batt, pv, wp = self._small()
+        ws = self._tc_workspace(B, F) if B > 0 else None
+        if ws is not None:
+            _lib.call("hhfm_afm_fwd_tc", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
+                      ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(out), ptr(ws), cur_stream())
+            return out
         _lib.call("hhfm_afm_fwd", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
                   ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(out), cur_stream())
         return out
@@ -684,10 +705,15 @@ class AFM(FM):
         ts, stamp, tr, tc = self._touch_args(extra=True)
         hot = self._hot_plan(idx, True)
         W, batt, pv, wp = self._small()
-        _lib.call("hhfm_afm_fwd_bwd_sqloss", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]),
-                  ptr(self.weights["feature_bias"]), ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(y), None,
-                  ptr(self._gV), ptr(self._gb), ptr(self._gb0), ptr(self._gW), ptr(self._gbatt), ptr(self._gp), ptr(self._gwp),
-                  ptr(self._loss_partials), ts, stamp, tr, tc, *(hot.args(True) if hot else NO_HOT_BIAS), cur_stream())
+        ws = self._tc_workspace(B, F)
+        common = (ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]), ptr(self._b0), W, batt,
+                  pv, wp, self._M, self._K, self._A, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0), ptr(self._gW),
+                  ptr(self._gbatt), ptr(self._gp), ptr(self._gwp), ptr(self._loss_partials), ts, stamp, tr, tc,
+                  *(hot.args(True) if hot else NO_HOT_BIAS))
+        if ws is not None:
+            _lib.call("hhfm_afm_fwd_bwd_sqloss_tc", *common, ptr(ws), cur_stream())
+        else:
+            _lib.call("hhfm_afm_fwd_bwd_sqloss", *common, cur_stream())
         if hot:
             hot.fold(self._gV, self._gb)
         if self._dp_group is not None:

@@ -154,6 +154,22 @@ int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
                             const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
                             hhfm_stream_t stream);
 
+/* K2 on the tensor cores (afm_tc.cu): the same forward / fused training pass with the three matrix products (P W, dZ W^T,
+ * P^T dZ) as 3xTF32 split GEMMs on tcgen05 and the rest as warp-per-sample kernels, chunked so that the pair tensors stay
+ * in L2.  Same arguments as hhfm_afm_fwd / hhfm_afm_fwd_bwd_sqloss plus a caller-owned, 16-byte aligned workspace of
+ * hhfm_workspace_bytes_afm(B, F, K, A) bytes. */
+int64_t hhfm_workspace_bytes_afm(int64_t B, int64_t F, int64_t K, int64_t A);
+int hhfm_afm_fwd_tc(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias, const float* b0,
+                    const float* W, const float* batt, const float* pvec, const float* wpred, int64_t M, int64_t K,
+                    int64_t A, float* out, float* workspace, hhfm_stream_t stream);
+int hhfm_afm_fwd_bwd_sqloss_tc(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias,
+                               const float* b0, const float* W, const float* batt, const float* pvec, const float* wpred,
+                               int64_t M, int64_t K, int64_t A, const float* labels, float* out, float* gV, float* gbias,
+                               float* gb0, float* gW, float* gbatt, float* gp, float* gwpred, float* loss_partials,
+                               int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
+                               const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
+                               float* workspace, hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K8  DeepFM (DFM.py:104-152): y1_f = feature_bias[x_f], y2 = 0.5((sum e)^2 - sum e^2), a relu MLP tower over the
  *     flattened embeddings, out = [y1 | y2 | H_L] . concat_projection + concat_bias;  loss = 0.5*sum(y-out)^2.

@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
     return
 
 
-def assert_close(a, b, rtol=1e-5, what=""):
+def assert_close(a, b, rtol=1e-5, what="", atol=0.0):
     """|a-b| <= rtol * max(|b|, rms(b)) element-wise: the 1e-5 relative fp32 tolerance of BASELINE.json with a
     floor at the RMS magnitude of the reference values (cancellation makes single elements arbitrarily small)."""
     a = np.asarray(a, dtype=np.float64)
@@ -27,7 +27,7 @@ def assert_close(a, b, rtol=1e-5, what=""):
     if b.size == 0:
         return
     rms = float(np.sqrt(np.mean(b * b)))
-    tol = rtol * np.maximum(np.abs(b), max(rms, 1e-30))
+    tol = rtol * np.maximum(np.abs(b), max(rms, 1e-30)) + atol
     err = np.abs(a - b)
     bad = err > tol
     assert not bad.any(), "%s: %d/%d elements off, worst err %.3e (tol %.3e) at %s" % (

@@ -923,3 +923,44 @@ def test_tf32x3_gemm_is_fp32_accurate(cuda, M, N, K):
     err = np.abs(got[:, :N] - ref).max() / scale
     assert err < 4e-6, "3xTF32 GEMM error %.3e (relative to sqrt(K)); plain tf32 would be ~5e-4" % err
     assert (got[:, N:] == 99.0).all()
+
+
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (5001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64)])
+def test_afm_tensor_core_pass_matches_oracle(cuda, B, F, K):
+    """K2 with the three matrix products as 3xTF32 GEMMs on tcgen05 (afm_tc.cu), chunked (B = 5001 spans three chunks)."""
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(B + F + K + 1)
+    M, A = 300, K
+    w = _afm_weights(rng, M, K, A)
+    X = rng.integers(0, M, (B, F)); X[:, 1] = rng.integers(0, 4, B)
+    if F > 3:
+        X[:, 3] = X[:, 2]
+    Y = rng.choice([1.0, -1.0], (B, 1)).astype(np.float32)
+    loss, out, g = O.afm_loss_grads(X, Y, w, 0.0)
+    tw = {k: dev(np.asarray(v, np.float32).reshape(-1) if k == "bias" else v, cuda) for k, v in w.items()}
+    P = lib.partials_len()
+    gV = torch.zeros(M, K, device=cuda); gb = torch.zeros(M, device=cuda); gb0 = torch.zeros(1, device=cuda)
+    gW = torch.zeros(K, A, device=cuda); gba = torch.zeros(A, device=cuda); gp = torch.zeros(A, device=cuda); gwp = torch.zeros(K, device=cuda)
+    lp = torch.zeros(P, device=cuda); o = torch.empty(B, device=cuda); lo = torch.zeros(1, device=cuda)
+    tX = dev(X, cuda, torch.int32)
+    ws = torch.empty(int(lib.load().hhfm_workspace_bytes_afm(B, F, K, A)) // 4 + 4, device=cuda)
+    args = (ptr(tX), B, F, ptr(tw["feature_embeddings"]), ptr(tw["feature_bias"]), ptr(tw["bias"]), ptr(tw["attention_W"]),
+            ptr(tw["attention_b"]), ptr(tw["attention_p"]), ptr(tw["prediction"]), M, K, A)
+    o2 = torch.empty(B, device=cuda)
+    lib.call("hhfm_afm_fwd_tc", *args, ptr(o2), ptr(ws), st())
+    assert_close(o2.cpu().numpy(), out, what="afm tc fwd out")
+    lib.call("hhfm_afm_fwd_bwd_sqloss_tc", *args, ptr(dev(Y.reshape(-1), cuda)), ptr(o), ptr(gV), ptr(gb), ptr(gb0), ptr(gW), ptr(gba),
+             ptr(gp), ptr(gwp), ptr(lp), None, 0, None, None, None, None, None, 0, 0, ptr(ws), st())
+    lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(lo), st())
+    assert_close(o.cpu().numpy(), out, what="afm tc out"); assert_close(lo.item(), loss, what="afm tc loss")
+    assert_close(gV.cpu().numpy(), g["feature_embeddings"], rtol=2e-5, what="afm tc gV")
+    assert_close(gb.cpu().numpy(), g["feature_bias"].reshape(-1), what="afm tc gbias")
+    assert_close(gb0.item(), g["bias"], what="afm tc gb0")
+    assert_close(gW.cpu().numpy(), g["attention_W"], rtol=2e-5, what="afm tc gW")
+    # d attention_b / d attention_p are sums over B*P terms that largely cancel (softmax gradients sum to zero over the pairs):
+    # their fp32 rounding noise grows with B in the oracle and on the device alike
+    noise = 2e-5 if B < 2000 else 1e-4
+    floor = 1e-5 * float(np.abs(g["attention_W"]).max())       # a tensor that is ALL cancellation noise has no scale of its own
+    assert_close(gba.cpu().numpy(), g["attention_b"].reshape(-1), rtol=noise, atol=floor, what="afm tc gb_att")
+    assert_close(gp.cpu().numpy(), g["attention_p"], rtol=noise, atol=floor, what="afm tc gp")
+    assert_close(gwp.cpu().numpy(), g["prediction"].reshape(-1), rtol=2e-5, what="afm tc gw_pred")
