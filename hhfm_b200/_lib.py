@@ -47,6 +47,8 @@ SIGNATURES = {
     "hhfm_opt_momentum_rows": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp],
     "hhfm_opt_sgd_rows": [vp, vp, vp, vp, i64, i64, f32, i32, vp],
     "hhfm_loss_finalize": [vp, vp, f32, vp, vp],
+    "hhfm_cars2_fwd": [vp, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, vp, vp, vp],
+    "hhfm_cars2_fwd_bwd": [vp, i64, i64, i32, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp],
     "hhfm_sample_negatives": [vp, i64, i32, i32, i32, vp, i64, i64, C.c_uint64, vp, i64, i64, vp],
     "hhfm_expand_rows": [vp, i64, i32, i64, vp, i32, vp, i32, vp],
     "hhfm_auc_count": [vp, vp, i64, i32, vp, vp],
@@ -72,6 +74,8 @@ INT64_FUNCS = {
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
     "hhfm_workspace_bytes_afm": [i64, i64, i64, i64],
+    "hhfm_cars2_param_count": [i64, i64, i64, i64, i64, i64],
+    "hhfm_workspace_bytes_cars2": [i64, i64, i64],
     "hhfm_dfm_param_count": [i64, i64, i32, vp],
     "hhfm_dfm_reg_count": [i64, i64, i32, vp],
     "hhfm_workspace_bytes_dfm": [i64, i64, i64, i32, vp],

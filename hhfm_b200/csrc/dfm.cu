@@ -472,6 +472,14 @@ static int dfm_forward(const int32_t* idx, int64_t B, int64_t F, const float* V,
   return HHFM_OK;
 }
 
+// C[M,N] += A[Kd,M]^T B[Kd,N] (split over Kd, atomics): the shared fp32 CUDA-core GEMM for the small products of other models
+int sgemm_tn_splitk(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int Kd, float* C, int64_t ldc,
+                    cudaStream_t st) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.Kd = Kd;
+  return launch_gemm<A_COL, B_ROW, EPI_ATOMIC>(g, st);
+}
+
 // ---- tensor-core path (dfm_tc.cu): every activation tensor X_l (l = 0: flattened embeddings, l >= 1: H_l, later dZ_l)
 // lives in four forms: X [B, ld_l], X_lo, and the k-blocked transposes X^T / X^T_lo ([B/32 panels][d_l][32]); every layer matrix in padded forms W [d_i, ldp_i] (+lo)
 // and W^T [d_{i+1}, ldt_i] (+lo).

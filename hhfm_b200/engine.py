@@ -436,6 +436,21 @@ class TopN:
             out_ids, out_sc = self._topk_exact(kind, Q, Fc, items, ibias, N, K, tp, item_lo)
         return (out_ids, out_sc) if return_scores else out_ids
 
+    def topk_from_query(self, Q, items, tp, method="auto", version=None):
+        """Top-tp items per row of a precomputed query matrix Q [C, K] under score = sum_k fl(q_k * v_nk) (the QUERY_USER
+        scorer); ids are item offsets."""
+        N, K = items.shape
+        lib = _lib.load()
+        supported = bool(lib.hhfm_topn_tc_supported(QUERY_USER, N, K, tp)) and N > 0
+        use_tc = supported and (method == "tc" or (method == "auto" and Q.shape[0] * N >= (1 << 22)))
+        self.last_method = "tc" if use_tc else "exact"
+        Q = Q.contiguous()
+        if use_tc:
+            ids, _ = self._topk_tc(QUERY_USER, Q, None, items, None, N, K, tp, 0, version)
+        else:
+            ids, _ = self._topk_exact(QUERY_USER, Q, None, items, None, N, K, tp, 0)
+        return ids
+
     def _topk_exact(self, kind, Q, Fc, items, ibias, N, K, tp, item_lo):
         C_rows = Q.shape[0]
         st = cur_stream()

@@ -908,3 +908,130 @@ class DeepFM(_Base):
         if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
             return self.partial_fit({"X": feed[self.feat_index], "Y": feed[self.label]}), None
         raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))
+
+
+# ====================================================================================================
+class CARS2:
+    """CARS2, Newcode/CARS2.py:45-187: the context-aware baseline of main.py:50-63.  One flat parameter block
+    [UI | Context | W | Z | A | B] (layout: include/hhfm_sm100.h, K10); `weights[...]` are views."""
+
+    def __init__(self, features_M, n_user, n_item, hidden_factor, learning_rate, lamda_bilinear, optimizer_type,
+                 random_seed=2016):
+        self.n_user = n_user
+        self.n_item = n_item
+        self.learning_rate = learning_rate
+        self.D = int(hidden_factor)
+        self.D_c = int(hidden_factor / 2.5)                  # CARS2.py:54-56
+        self.D_p = int(hidden_factor / 5)
+        self.D_q = int(hidden_factor / 2.5)
+        self.features_M = features_M
+        self.lamda_bilinear = lamda_bilinear
+        self.optimizer_type = optimizer_type
+        self.random_seed = random_seed
+        self._init_graph()
+
+    def _init_graph(self):
+        self.device = require_cuda()
+        if self.D > 128 or self.D_c < 1 or self.D_p < 1:
+            raise _lib.HhfmError("CARS2: hidden_factor must be in [5, 128] (D_c = D/2.5, D_p = D/5 >= 1)")
+        self.Pos, self.Fea, self.Neg = Handle("Pos"), Handle("Fea"), Handle("Neg")
+        self.PositiveFeadback = Handle("PositiveFeadback")
+        self.loss, self.optimizer = Handle("loss"), Handle("optimizer")
+        lib = _lib.load()
+        n_ui = self.n_user + self.n_item
+        D, Dc, Dp, Dq, M = self.D, self.D_c, self.D_p, self.D_q, int(self.features_M)
+        self._dims = (n_ui, M, D, Dp, Dq, Dc)
+        n = int(lib.hhfm_cars2_param_count(*self._dims))
+        self._params = torch.zeros(n + 4, dtype=torch.float32, device=self.device)[:n]
+        self._gparams = torch.zeros(n + 4, dtype=torch.float32, device=self.device)[:n]
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(self.random_seed))
+        self.weights = {}
+        off = 0
+        for name, shape, std in (("UI", (n_ui, D), 0.01), ("Context", (M, Dc), 0.01), ("W", (D, Dp, Dc), 0.01),
+                                 ("Z", (D, Dq, Dc), 0.01), ("A", (Dp,), 0.0), ("B", (Dq,), 0.0)):       # CARS2.py:155-167
+            cnt = int(np.prod(shape))
+            self.weights[name] = self._params[off:off + cnt].view(*shape)
+            if std > 0:
+                self.weights[name].copy_(torch.empty(*shape).normal_(0.0, std, generator=gen))
+            off += cnt
+        P = _lib.partials_len()
+        self._loss_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self._sq_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._opt = Optimizer(self.optimizer_type, self.learning_rate, initial_accumulator_value=0.1)
+        self._uploader = RecordUploader(self.device)
+        self._topn = TopN(self.device)
+        self._M = max(n_ui, M)                 # id limit of the packed records (users/items and context-tuple ids)
+        self._ws = None
+        self._version = 0
+        self.topn_method = "auto"
+        self.sess = Session(self)
+
+    def _workspace(self, B):
+        need = int(_lib.load().hhfm_workspace_bytes_cars2(B, self.D, self.D_c)) // 4 + 4
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def _forward(self, rec, mode):
+        B, stride = rec.shape
+        out = torch.empty(B if mode == 0 else (B, self.D), dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_cars2_fwd", ptr(rec), B, stride, ptr(self._params), *self._dims, mode, ptr(out),
+                  ptr(self._workspace(B)), cur_stream())
+        return out
+
+    def score_device(self, rec):
+        """PositiveFeadback [n] (device) for device records [n, >=3] = [user, item, context-tuple id]."""
+        return self._forward(rec, 0)
+
+    def positive_feedback(self, X, F1):
+        rec, _ = self._uploader.upload([np.asarray(X)[:, :2], np.asarray(F1).reshape(-1, 1)], self._M)
+        return self.score_device(rec).cpu().numpy().reshape(-1, 1)
+
+    def partial_fit(self, data):
+        """CARS2.py:168-171: data = {'X': [B,2], 'F1': [B] context-tuple ids, 'Y': [B,NG] negatives}; returns the loss."""
+        Y = np.asarray(data["Y"])
+        rec, _ = self._uploader.upload([np.asarray(data["X"])[:, :2], np.asarray(data["F1"]).reshape(-1, 1), Y], self._M)
+        self.fit_device(rec, Y.shape[1])
+        loss_host = self._loss_dev.cpu()
+        return float(loss_host[0])
+
+    def fit_device(self, rec, n_neg):
+        B, stride = rec.shape
+        self._opt.begin_step()
+        _lib.call("hhfm_cars2_fwd_bwd", ptr(rec), B, stride, n_neg, ptr(self._params), *self._dims, ptr(self._gparams),
+                  ptr(self._loss_partials), ptr(self._workspace(B)), cur_stream())
+        lam = float(self.lamda_bilinear)
+        self._opt.apply_dense("params", self._params, self._gparams, lam if lam > 0 else 0.0,
+                              self._sq_partials if lam > 0 else None)
+        self._version += 1
+        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), ptr(self._sq_partials) if lam > 0 else None, 0.5 * lam,
+                  ptr(self._loss_dev), cur_stream())
+
+    def topk(self, feed_dict, tp):
+        """CARS2.py:171-187: feed_dict = {'X': user ids [C], 'F1': context-tuple ids [C]}.  score(c, item) = item . (u + T c)
+        + a per-row constant, so the catalog is ranked by the dot product with that query vector (exact fp32 scorer or the
+        tcgen05 filter + exact rescoring, lowest index first on ties)."""
+        users = np.asarray(feed_dict["X"]).reshape(-1, 1)
+        fea = np.asarray(feed_dict["F1"]).reshape(-1, 1)
+        rec, _ = self._uploader.upload([users, np.zeros_like(users), fea], self._M)
+        Q = self._forward(rec, 2)
+        items = self.weights["UI"][self.n_user:self.n_user + self.n_item]
+        return self._topn.topk_from_query(Q, items, tp, method=self.topn_method, version=self._version).cpu().numpy()
+
+    def load_weights(self, weights):
+        for k, v in weights.items():
+            t = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(self.weights[k].shape)
+            self.weights[k].copy_(t.to(self.device))
+        self._version += 1
+
+    def get_weights(self):
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.weights.items()}
+
+    def _run(self, fetches, feed):
+        if fetches is self.PositiveFeadback:
+            return self.positive_feedback(feed[self.Pos], feed[self.Fea])
+        if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
+            return self.partial_fit({"X": feed[self.Pos], "F1": feed[self.Fea], "Y": feed[self.Neg]}), None
+        raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))

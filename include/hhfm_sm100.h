@@ -293,6 +293,23 @@ int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, co
                            float* loss_out, hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K10  CARS2 (CARS2.py:66-187), the context-aware baseline of main.py:50-63.
+ *   params / gparams: ONE flat block [ UI (n_ui x D) | Context (M x Dc) | W (D x Dp x Dc) | Z (D x Dq x Dc) | A (Dp) | B (Dq) ],
+ *   hhfm_cars2_param_count() floats, all of it L2-regularised (CARS2.py:116-123: apply hhfm_opt_*_dense_l2 to the block).
+ *   hhfm_cars2_fwd: mode 0 -> out[B] = PositiveFeadback of records [user, item, fea]; mode 2 -> out[B, D] = u + T c, the
+ *   query vector whose dot product with the item rows ranks the catalog (CARS2.topk, :171-187).
+ *   hhfm_cars2_fwd_bwd: records [user, item, fea, neg...]; loss partials of -sum log sigmoid(Pos - Neg); gradients ACCUMULATE.
+ *   workspace: hhfm_workspace_bytes_cars2(B, D, Dc) bytes.  D, Dc <= 128.
+ * ------------------------------------------------------------------------------------------------ */
+int64_t hhfm_cars2_param_count(int64_t n_ui, int64_t M, int64_t D, int64_t Dp, int64_t Dq, int64_t Dc);
+int64_t hhfm_workspace_bytes_cars2(int64_t B, int64_t D, int64_t Dc);
+int hhfm_cars2_fwd(const int32_t* rec, int64_t B, int64_t stride, const float* params, int64_t n_ui, int64_t M, int64_t D,
+                   int64_t Dp, int64_t Dq, int64_t Dc, int32_t mode, float* out, float* workspace, hhfm_stream_t stream);
+int hhfm_cars2_fwd_bwd(const int32_t* rec, int64_t B, int64_t stride, int32_t n_neg, const float* params, int64_t n_ui,
+                       int64_t M, int64_t D, int64_t Dp, int64_t Dq, int64_t Dc, float* gparams, float* loss_partials,
+                       float* workspace, hhfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K9  device negative sampler and evaluate_AUC (sampler.cu)
  * hhfm_sample_negatives: out[r, out_col0 + j] (row stride out_stride) = a uniform item id in [n_user, n_user+n_item),
  *   re-drawn while key_id[r]*span + item is in the sorted int64 list pf_codes (= `item in positive_feedback[key(row)]`,

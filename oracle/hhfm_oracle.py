@@ -508,6 +508,69 @@ def dfm_loss_grads(X, Y, w, l2_reg=0.0, n_layers=3):
 
 
 # ----------------------------------------------------------------------------------------------------
+# CARS2: CARS2.py:85-123 (restated op by op; the device kernels use the collapsed form T = sum_q B_q Z[:,q,:])
+# ----------------------------------------------------------------------------------------------------
+def cars2_feedback(Pos, Fea, w, items=None):
+    """PositiveFeadback (CARS2.py:104-106) for rows Pos [B,2] (user, item) and context ids Fea [B]."""
+    UI = _f32(w["UI"]); C = _f32(w["Context"])[np.asarray(Fea)]
+    u = UI[np.asarray(Pos)[:, 0]]
+    it = UI[np.asarray(Pos)[:, 1]] if items is None else items
+    pik = np.einsum("bd,dpc,bc->bp", u, _f32(w["W"]), C).astype(F32)                  # :92-93
+    qjk = np.einsum("bd,dqc,bc->bq", it, _f32(w["Z"]), C).astype(F32)                 # :95-96
+    return ((u * it).sum(axis=1, dtype=F32) + (pik * _f32(w["A"])).sum(axis=1, dtype=F32)
+            + (qjk * _f32(w["B"])).sum(axis=1, dtype=F32)).astype(F32)
+
+
+def cars2_loss_grads(Pos, Fea, Neg, w, lamda=0.0):
+    """loss = -sum log sigmoid(Pos - Neg) + lamda/2 * sum ||.||^2 over the six variables (CARS2.py:113-123) and all
+    gradients; Negitems is the SUM of the negative item rows (:90)."""
+    Pos = np.asarray(Pos); Neg = np.asarray(Neg); Fea = np.asarray(Fea)
+    UI = _f32(w["UI"]); Ctx = _f32(w["Context"]); W = _f32(w["W"]); Z = _f32(w["Z"]); A = _f32(w["A"]); Bv = _f32(w["B"])
+    u = UI[Pos[:, 0]]; ip = UI[Pos[:, 1]]; ineg = UI[Neg].sum(axis=1, dtype=F32); C = Ctx[Fea]
+    pos = cars2_feedback(Pos, Fea, w)
+    neg = cars2_feedback(Pos, Fea, w, items=ineg)
+    x = (pos - neg).astype(F32)
+    sg = _sigmoid(x)
+    loss = F32(-np.log(sg).astype(F32).sum(dtype=F32))
+    g = (sg - F32(1.0)).astype(F32)                                        # d loss / d x
+    d_pos, d_neg = g, -g
+    # d u: from u.ip, u.ineg and pik (pik.A appears in both scores: its contributions cancel)
+    pikA_u = np.einsum("dpc,p,bc->bd", W, A, C).astype(F32)
+    du = (d_pos[:, None] * (ip + pikA_u) + d_neg[:, None] * (ineg + pikA_u)).astype(F32)
+    ZB_c = np.einsum("dqc,q,bc->bd", Z, Bv, C).astype(F32)
+    dip = (d_pos[:, None] * (u + ZB_c)).astype(F32)
+    dineg = (d_neg[:, None] * (u + ZB_c)).astype(F32)
+    dC = (np.einsum("b,bd,dpc,p->bc", d_pos + d_neg, u, W, A) + np.einsum("b,bd,dqc,q->bc", d_pos, ip, Z, Bv)
+          + np.einsum("b,bd,dqc,q->bc", d_neg, ineg, Z, Bv)).astype(F32)
+    dW = np.einsum("b,bd,p,bc->dpc", d_pos + d_neg, u, A, C).astype(F32)
+    dA = np.einsum("b,bd,dpc,bc->p", d_pos + d_neg, u, W, C).astype(F32)
+    dZ = (np.einsum("b,bd,q,bc->dqc", d_pos, ip, Bv, C) + np.einsum("b,bd,q,bc->dqc", d_neg, ineg, Bv, C)).astype(F32)
+    dB = (np.einsum("b,bd,dqc,bc->q", d_pos, ip, Z, C) + np.einsum("b,bd,dqc,bc->q", d_neg, ineg, Z, C)).astype(F32)
+    dUI = np.zeros_like(UI); dCtx = np.zeros_like(Ctx)
+    np.add.at(dUI, Pos[:, 0], du); np.add.at(dUI, Pos[:, 1], dip)
+    for j in range(Neg.shape[1]):
+        np.add.at(dUI, Neg[:, j], dineg)
+    np.add.at(dCtx, Fea, dC)
+    grads = dict(UI=dUI, Context=dCtx, W=dW, Z=dZ, A=dA, B=dB)
+    if lamda > 0:
+        for k in grads:
+            wk = _f32(w[k])
+            loss = F32(loss + F32(lamda) * F32(0.5) * (wk * wk).astype(F32).sum(dtype=F32))
+            grads[k] = (grads[k] + F32(lamda) * wk).astype(F32)
+    return F32(loss), pos, grads
+
+
+def cars2_topk_scores(users, Fea, w, n_user, n_item):
+    """Feedback [C, N] of CARS2.topk (CARS2.py:171-187)."""
+    UI = _f32(w["UI"]); C = _f32(w["Context"])[np.asarray(Fea)]
+    u = UI[np.asarray(users)]; items = UI[n_user:n_user + n_item]
+    pik = np.einsum("bd,dpc,bc->bp", u, _f32(w["W"]), C).astype(F32)
+    qjk = np.einsum("nd,dqc,bc->bnq", items, _f32(w["Z"]), C).astype(F32)
+    return ((u @ items.T).astype(F32) + (pik * _f32(w["A"])).sum(axis=1, keepdims=True, dtype=F32)
+            + (qjk * _f32(w["B"])).sum(axis=2, dtype=F32)).astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------------
 # optimizers: TF1 semantics (FM.py:129-136, BPR.py:93, MF.py:104)
 # ----------------------------------------------------------------------------------------------------
 def adagrad_dense(w, acc, g, lr):

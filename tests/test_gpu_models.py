@@ -345,3 +345,56 @@ def test_dfm_steps_and_topk_match_oracle(cuda):
         tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
         for a_, b_ in zip(ids[r], want[r]):
             assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
+
+
+def _cars2_weights(rng, n_ui, M, D):
+    Dc, Dp, Dq = int(D / 2.5), int(D / 5), int(D / 2.5)
+    return dict(UI=rng.normal(0, 0.1, (n_ui, D)).astype(np.float32), Context=rng.normal(0, 0.1, (M, Dc)).astype(np.float32),
+                W=rng.normal(0, 0.1, (D, Dp, Dc)).astype(np.float32), Z=rng.normal(0, 0.1, (D, Dq, Dc)).astype(np.float32),
+                A=rng.normal(0, 0.3, Dp).astype(np.float32), B=rng.normal(0, 0.3, Dq).astype(np.float32))
+
+
+@pytest.mark.parametrize("D,NG", [(128, 1), (64, 3), (20, 2)])
+def test_cars2_steps_and_topk_match_oracle(cuda, D, NG):
+    """CARS2.partial_fit (CARS2.py:168-171) teacher-forced against the oracle + TF1 Adagrad, PositiveFeadback through the
+    sess shim and CARS2.topk (CARS2.py:171-187)."""
+    from conftest import assert_update_close
+    from hhfm_b200.models import CARS2
+    rng = np.random.default_rng(D + NG)
+    n_user, n_item, M, lr, lam = 40, 90, 25, 0.05, 0.001
+    model = CARS2(M, n_user, n_item, D, lr, lam, 'AdagradOptimizer')
+    model.load_weights(_cars2_weights(rng, n_user + n_item, M, D))
+    names = ["UI", "Context", "W", "Z", "A", "B"]
+    for step in range(3):
+        w = model.get_weights()
+        acc_flat = model._opt.state["params"][0].cpu().numpy().copy() if "params" in model._opt.state else None
+        B = 2000 if step < 2 else 317
+        Pos = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B)], axis=1)
+        Neg = n_user + rng.integers(0, n_item, (B, NG)); Fea = rng.integers(0, M, B)
+        loss_ref, pos_ref, g = O.cars2_loss_grads(Pos, Fea, Neg, w, lam)
+        fb = model.sess.run(model.PositiveFeadback, feed_dict={model.Pos: Pos, model.Fea: Fea})
+        assert_close(fb[:, 0], pos_ref, rtol=2e-5, what="cars2 PositiveFeadback step %d" % step)
+        loss = model.partial_fit({"X": Pos, "F1": Fea, "Y": Neg})
+        assert_close(loss, loss_ref, what="cars2 loss step %d" % step)
+        got = model.get_weights()
+        off = 0
+        for k in names:
+            wk = np.asarray(w[k], np.float32); gk = np.asarray(g[k], np.float32).reshape(wk.shape)
+            acc = np.full(wk.shape, 0.1, np.float32) if acc_flat is None else acc_flat[off:off + wk.size].reshape(wk.shape)
+            off += wk.size
+            w1, _ = O.adagrad_dense(wk, acc, gk, lr)
+            # d B_q contracts Z with dT = Delta^T C (two fp32 stages), the oracle's einsum contracts four factors at once:
+            # both are fp32, in a different association
+            assert_update_close(got[k], w1, wk, gk, acc, lr, rtol=1e-4 if k in ("A", "B") else 3e-5,
+                                atol=4 * 1.2e-7 * float(np.abs(wk).max()), what="cars2 %s step %d" % (k, step))
+    w = model.get_weights()
+    users = rng.integers(0, n_user, 50); fea = rng.integers(0, M, 50)
+    ids = model.topk({"X": users, "F1": fea}, 20)
+    ref = O.cars2_topk_scores(users, fea, w, n_user, n_item)
+    want = O.topk_lowest_index(ref, 20)
+    for r in range(len(users)):
+        if (ids[r] == want[r]).all():
+            continue
+        tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
+        for a_, b_ in zip(ids[r], want[r]):
+            assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])

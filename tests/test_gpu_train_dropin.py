@@ -25,7 +25,7 @@ def _write_dataset(root, name="frappe", rows=6000, n_user=60, n_item=120, seed=3
     return os.path.join(root, "")
 
 
-@pytest.mark.parametrize("which", ["FM", "AFM", "DFM", "M7", "BPR"])
+@pytest.mark.parametrize("which", ["FM", "AFM", "DFM", "M7", "BPR", "CARS2"])
 def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     path = _write_dataset(str(tmp_path))
     result = os.path.join(str(tmp_path), "result.txt")
@@ -43,6 +43,9 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
         argv += ["--verbose", "10", "--lr", "0.05"]
     elif which == "M7":
         from hhfm_b200.Newcode.OurModel7 import M7_main as main
+    elif which == "CARS2":
+        from hhfm_b200.Newcode.CARS2 import CARS2_main as main
+        argv += ["--lr", "0.1"]
     else:
         from hhfm_b200.Newcode.BPR import BPR_main as main
         argv += ["--Result", "0", "--lr", "0.1"]          # BPR.py:40 defaults to the early-stop mode (no periodic log)
@@ -61,7 +64,10 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
         assert auc_train > 0.6, text                                       # the cluster structure is learnable
     # the retrieval API: item offsets in [0, n_item), 20 per row, no duplicates
     rows = np.asarray(session.data.Test_data.values[:50, 1:], dtype=np.int64)
-    ids = session.model.topk(rows, 20)
+    if which == "CARS2":
+        ids = session.model.topk({"X": rows[:, 0], "F1": session.context_ids(rows)}, 20)
+    else:
+        ids = session.model.topk(rows, 20)
     assert ids.shape == (50, 20) and ids.min() >= 0 and ids.max() < session.n_item
     assert all(len(set(r.tolist())) == 20 for r in ids)
 
