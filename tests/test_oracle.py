@@ -100,3 +100,83 @@ def test_tf1_optimizer_restatements():
     assert_close(w1, [1.0 - 0.01 * np.sqrt(1 - 0.999) / (1 - 0.9) * 0.05 / (np.sqrt(0.00025) + 1e-8), -2.0])
     w1, a1 = O.momentum_dense(w, np.array([1.0, 1.0], np.float32), g, 0.1)
     assert_close(a1, [1.45, 0.95]); assert_close(w1, [1.0 - 0.145, -2.0 - 0.095])
+
+
+def test_dfm_gradients_agree_with_autograd():
+    """DeepFM restatement (DFM.py:104-152): every gradient against torch.autograd in float64."""
+    rng = np.random.default_rng(0)
+    M, K, F, B = 50, 8, 5, 40
+    dims = [F * K, 7, 9, 6]
+    w = {"feature_embeddings": rng.normal(0, .3, (M, K)).astype(np.float32), "feature_bias": rng.uniform(0, 1, (M, 1)).astype(np.float32),
+         "concat_projection": rng.normal(0, .3, (F + K + dims[-1], 1)).astype(np.float32), "concat_bias": np.float32(0.01)}
+    for i in range(3):
+        w["layer_%d" % i] = rng.normal(0, .3, (dims[i], dims[i + 1])).astype(np.float32)
+        w["bias_%d" % i] = rng.normal(0, .3, (1, dims[i + 1])).astype(np.float32)
+    X = rng.integers(0, M, (B, F)); Y = rng.choice([1., -1.], (B, 1)).astype(np.float32)
+    loss, out, g = O.dfm_loss_grads(X, Y, w, 0.01)
+    tw = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in w.items()}
+    E = tw["feature_embeddings"][torch.tensor(X)]
+    y1 = tw["feature_bias"].reshape(-1)[torch.tensor(X)]
+    S = E.sum(1); y2 = 0.5 * (S * S - (E * E).sum(1))
+    h = E.reshape(B, -1)
+    for i in range(3):
+        h = torch.relu(h @ tw["layer_%d" % i] + tw["bias_%d" % i])
+    o = (torch.cat([y1, y2, h], 1) @ tw["concat_projection"]).reshape(-1) + tw["concat_bias"]
+    L = 0.5 * ((torch.tensor(Y.reshape(-1), dtype=torch.float64) - o) ** 2).sum() + 0.005 * (
+        (tw["concat_projection"] ** 2).sum() + sum((tw["layer_%d" % i] ** 2).sum() for i in range(3)))
+    L.backward()
+    assert_close(loss, L.item(), what="dfm loss"); assert_close(out, o.detach().numpy(), what="dfm out")
+    for k in g:
+        assert_close(np.asarray(g[k], np.float64).reshape(-1), tw[k].grad.numpy().reshape(-1), rtol=2e-5, what="dfm grad " + k)
+
+
+def test_cars2_gradients_agree_with_autograd():
+    """CARS2 restatement (CARS2.py:85-123): every gradient against torch.autograd in float64."""
+    rng = np.random.default_rng(1)
+    nu, ni, M, D = 20, 30, 12, 10
+    Dc, Dp, Dq = 4, 2, 4
+    B, NG = 50, 2
+    w = dict(UI=rng.normal(0, .3, (nu + ni, D)).astype(np.float32), Context=rng.normal(0, .3, (M, Dc)).astype(np.float32),
+             W=rng.normal(0, .3, (D, Dp, Dc)).astype(np.float32), Z=rng.normal(0, .3, (D, Dq, Dc)).astype(np.float32),
+             A=rng.normal(0, .3, Dp).astype(np.float32), B=rng.normal(0, .3, Dq).astype(np.float32))
+    Pos = np.stack([rng.integers(0, nu, B), nu + rng.integers(0, ni, B)], 1)
+    Neg = nu + rng.integers(0, ni, (B, NG)); Fea = rng.integers(0, M, B)
+    loss, pos, g = O.cars2_loss_grads(Pos, Fea, Neg, w, 0.01)
+    tw = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in w.items()}
+
+    def fb(u, it, C):
+        pik = torch.einsum("bd,dpc,bc->bp", u, tw["W"], C); q = torch.einsum("bd,dqc,bc->bq", it, tw["Z"], C)
+        return (u * it).sum(1) + (pik * tw["A"]).sum(1) + (q * tw["B"]).sum(1)
+    u = tw["UI"][torch.tensor(Pos[:, 0])]; ip = tw["UI"][torch.tensor(Pos[:, 1])]
+    ineg = tw["UI"][torch.tensor(Neg)].sum(1); C = tw["Context"][torch.tensor(Fea)]
+    L = -torch.log(torch.sigmoid(fb(u, ip, C) - fb(u, ineg, C))).sum() + 0.005 * sum((v ** 2).sum() for v in tw.values())
+    L.backward()
+    assert_close(loss, L.item(), what="cars2 loss"); assert_close(pos, fb(u, ip, C).detach().numpy(), what="cars2 feedback")
+    for k in g:
+        assert_close(np.asarray(g[k], np.float64).reshape(-1), tw[k].grad.numpy().reshape(-1), rtol=2e-5, what="cars2 grad " + k)
+    # the ranking used by CARS2.topk is the dot product with u + T c up to a per-row constant
+    users = rng.integers(0, nu, 7); fea = rng.integers(0, M, 7)
+    ref = O.cars2_topk_scores(users, fea, w, nu, ni)
+    T_ = np.einsum("q,dqc->dc", w["B"], w["Z"])
+    q = w["UI"][users] + w["Context"][fea] @ T_.T
+    alt = q @ w["UI"][nu:nu + ni].T
+    d = ref - alt
+    assert np.abs(d - d[:, :1]).max() < 1e-5                  # differs by a constant per row only
+
+
+def test_hashed_negative_sampler_restatement():
+    """The counter-based sampler (device: csrc/sampler.cu): range, rejection, determinism, order independence."""
+    rng = np.random.default_rng(3)
+    n_user, n_item, span = 10, 25, 35
+    codes = np.unique(np.array([k * span + n_user + i for k in range(6) for i in rng.choice(n_item, 20, replace=False)], np.int64))
+    key_id = rng.integers(-1, 6, 400).astype(np.int64)
+    a = O.sample_negative_hashed(key_id, 5, n_user, n_item, codes, span, 1234)
+    b = O.sample_negative_hashed(key_id, 5, n_user, n_item, codes, span, 1234)
+    assert (a == b).all() and a.min() >= n_user and a.max() < n_user + n_item
+    cs = set(codes.tolist())
+    assert not any((int(k) * span + int(it)) in cs for k, row in zip(key_id, a) if k >= 0 for it in row)
+    c = O.sample_negative_hashed(key_id, 5, n_user, n_item, codes, span, 1235)
+    assert (a != c).mean() > 0.5                                # another seed, another sample
+    # a draw depends on (seed, cell, attempt) only: sampling a prefix of the rows gives the same cells
+    d = O.sample_negative_hashed(key_id[:100], 5, n_user, n_item, codes, span, 1234)
+    assert (d == a[:100]).all()
