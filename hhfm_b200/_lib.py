@@ -58,7 +58,7 @@ SIGNATURES = {
     "hhfm_p2p_free": [vp],
     "hhfm_p2p_barrier": [vp, i32, i32, i32, vp],
     "hhfm_opt_dense_l2_p2p": [i32, vp, vp, vp, vp, i32, vp, i64, f32, f32, f32, f32, f32, vp, vp],
-    "hhfm_loss_finalize_p2p": [vp, i32, vp, f32, vp, vp],
+    "hhfm_loss_finalize_p2p": [vp, i32, i32, vp, f32, vp, vp],
     "hhfm_hot_fold": [vp, vp, i32, i32, i64, vp, vp, vp, vp],
     "hhfm_topn_build_query": [i32, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],

@@ -56,8 +56,18 @@ __global__ void __launch_bounds__(256) opt_dense_p2p_kernel(float* __restrict__ 
   float4* a4 = reinterpret_cast<float4*>(s1);
   float4* b4 = reinterpret_cast<float4*>(s2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 gv = ld_peer4(reinterpret_cast<const float4*>(peers.g[0]) + i);
-    for (int r = 1; r < n_ranks; r++) gv = f4_add(gv, ld_peer4(reinterpret_cast<const float4*>(peers.g[r]) + i));
+    // the remote loads of four ranks are in flight together (one NVLink round trip per group); the sum is still formed in
+    // rank order, so every replica computes the same bits
+    float4 gv = f4_zero();
+    for (int r0 = 0; r0 < n_ranks; r0 += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        t[q] = (r0 + q < n_ranks) ? ld_peer4(reinterpret_cast<const float4*>(peers.g[r0 + q]) + i) : f4_zero();
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (r0 + q < n_ranks) gv = f4_add(gv, t[q]);
+    }
     float4 wv = w4[i];
     float4 av = (KIND != HHFM_OPT_SGD) ? a4[i] : f4_zero();
     float4 bv = (KIND == HHFM_OPT_ADAM) ? b4[i] : f4_zero();
@@ -118,11 +128,14 @@ __global__ void p2p_barrier_kernel(const FlagPtrs flags, int rank, int n_ranks, 
   __threadfence_system();
 }
 
-__global__ void loss_finalize_p2p_kernel(const PeerPtrs lp, int n_ranks, const float* __restrict__ sp, float half_lamda,
-                                         float* __restrict__ out) {
+// n_per_rank values are read from every rank.  The callers reduce their own loss partials locally first and publish ONE
+// float per rank: reading all 2048 partial slots of 8 ranks from a single warp was 512 dependent remote loads per lane
+// (~0.3 ms per step at 8 GPUs).
+__global__ void loss_finalize_p2p_kernel(const PeerPtrs lp, int n_ranks, int n_per_rank, const float* __restrict__ sp,
+                                         float half_lamda, float* __restrict__ out) {
   float a = 0.f, b = 0.f;
   for (int r = 0; r < n_ranks; r++)
-    for (int i = threadIdx.x; i < kPartials; i += 32) a += ld_peer(lp.g[r] + i);
+    for (int i = threadIdx.x; i < n_per_rank; i += 32) a += ld_peer(lp.g[r] + i);
   if (sp)
     for (int i = threadIdx.x; i < kPartials; i += 32) b += sp[i];
   a = warp_sum(a);
@@ -221,11 +234,12 @@ extern "C" int hhfm_opt_dense_l2_p2p(int32_t kind, float* w, float* s1, float* s
   return check_launch("opt_dense_p2p_kernel");
 }
 
-extern "C" int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, const float* sq_partials,
-                                      float half_lamda, float* loss_out, hhfm_stream_t stream) {
-  HHFM_REQUIRE(partial_ptrs_host && loss_out && n_ranks >= 1 && n_ranks <= kMaxPeers, "loss_finalize_p2p: bad arguments");
+extern "C" int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, int32_t n_per_rank,
+                                      const float* sq_partials, float half_lamda, float* loss_out, hhfm_stream_t stream) {
+  HHFM_REQUIRE(partial_ptrs_host && loss_out && n_ranks >= 1 && n_ranks <= kMaxPeers && n_per_rank >= 1 && n_per_rank <= kPartials,
+               "loss_finalize_p2p: bad arguments");
   PeerPtrs pp{};
   for (int r = 0; r < n_ranks; r++) pp.g[r] = reinterpret_cast<const float*>(partial_ptrs_host[r]);
-  loss_finalize_p2p_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n_ranks, sq_partials, half_lamda, loss_out);
+  loss_finalize_p2p_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, n_ranks, n_per_rank, sq_partials, half_lamda, loss_out);
   return check_launch("loss_finalize_p2p_kernel");
 }

@@ -91,6 +91,7 @@ class _Base:
         self._gV = arena[:n_v].view(self._M, self._K)
         self._gb = arena[n_v:n_v + n_b] if (n_b and self._with_bias_grad) else None
         self._gb0 = arena[n_v + n_b:n_v + n_b + 1]
+        self._loss_local = arena[n_v + n_b + 1:n_v + n_b + 2]        # this rank's reduced loss (peer exchange)
         self._loss_partials = arena[n_v + n_b + 4:n_v + n_b + 4 + P]
 
     def _hot_plan(self, idx_dev, with_bias):
@@ -119,6 +120,9 @@ class _Base:
             dist.broadcast(w, src=0, group=self._dp_group)
         self._peer = None
         ws = dist.get_world_size(self._dp_group)
+        import os
+        if os.environ.get("HHFM_DP_P2P") == "0":          # force the NCCL all-reduce exchange (A/B measurements)
+            p2p = False
         if p2p and ws > 1 and self.device.type == "cuda":
             peer, ok = None, 1
             try:
@@ -141,6 +145,9 @@ class _Base:
         if self._dp_group is None:
             return
         if self._peer is not None:
+            # publish this rank's loss as ONE float (arena slot after gb0) before the barrier: the peers then read
+            # n_ranks floats instead of n_ranks x 2048 partial slots
+            _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), None, 0.0, ptr(self._loss_local), cur_stream())
             self._peer.barrier()
         else:
             import torch.distributed as dist
@@ -218,8 +225,8 @@ class _Base:
                       cur_stream())
             return
         pr = self._peer
-        off = (self._loss_partials.data_ptr() - self._arena.data_ptr()) // 4
-        _lib.call("hhfm_loss_finalize_p2p", pr.table(pr.cur, off), pr.ws, sq, hl if with_reg else 0.0, ptr(self._loss_dev),
+        off = (self._loss_local.data_ptr() - self._arena.data_ptr()) // 4
+        _lib.call("hhfm_loss_finalize_p2p", pr.table(pr.cur, off), pr.ws, 1, sq, hl if with_reg else 0.0, ptr(self._loss_dev),
                   cur_stream())
         pr.cur ^= 1
         self._bind_arena(pr.bufs[pr.cur])

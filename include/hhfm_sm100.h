@@ -279,7 +279,8 @@ int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, flo
  * hhfm_opt_dense_l2_p2p: w/state update with g = sum over ranks (fixed rank order => bit-identical replicas) of
  *   grad_r[i] + lamda*w; g_zero (may be NULL) is a LOCAL buffer cleared on the way (the other half of a double-buffered
  *   gradient arena).  beta1 carries the momentum for HHFM_OPT_MOMENTUM, lr is lr_t for Adam.
- * hhfm_loss_finalize_p2p: loss = sum over ranks of the loss partials + half_lamda * sum(sq_partials).
+ * hhfm_loss_finalize_p2p: loss = sum over ranks of n_per_rank published values (the callers publish their locally reduced
+ *   loss, n_per_rank = 1) + half_lamda * sum(sq_partials).
  * ------------------------------------------------------------------------------------------------ */
 int hhfm_p2p_alloc(int64_t bytes, void** dev_ptr, void* handle64);
 int hhfm_p2p_open(const void* handle64, void** dev_ptr);
@@ -289,8 +290,8 @@ int hhfm_p2p_barrier(const int64_t* flag_ptrs_host, int32_t rank, int32_t n_rank
 int hhfm_opt_dense_l2_p2p(int32_t kind, float* w, float* s1, float* s2, const int64_t* grad_ptrs_host, int32_t n_ranks,
                           float* g_zero, int64_t n, float lr, float lamda, float beta1, float beta2, float eps,
                           float* sq_partials, hhfm_stream_t stream);
-int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, const float* sq_partials, float half_lamda,
-                           float* loss_out, hhfm_stream_t stream);
+int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, int32_t n_per_rank, const float* sq_partials,
+                           float half_lamda, float* loss_out, hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10  CARS2 (CARS2.py:66-187), the context-aware baseline of main.py:50-63.
