@@ -1,11 +1,11 @@
 // Data-parallel exchange over NVLink peer memory, fused into the optimizer.
 //
-// Every rank keeps its gradient arena in a cudaMalloc'd buffer that the other ranks of the box map through CUDA IPC.
-// A step is: local scatter kernels -> hhfm_p2p_barrier (flags written into every peer with system-scope release
-// stores, each rank spins on its own copy) -> hhfm_opt_*_dense_l2_p2p, which reads element i of the gradient from
-// EVERY rank's arena (fixed rank order, so all replicas compute bit-identical sums and stay bit-identical), applies the
-// TF1 optimizer update to the local replica and clears the slice of the OTHER arena buffer (arenas are double
-// buffered: a buffer is only re-zeroed after the barrier that proves every peer has finished reading it).
+// Every rank exports a copy of its gradient arena in a cudaMalloc'd buffer that the other ranks of the box map through
+// CUDA IPC (double buffered: a buffer is only rewritten after the barrier that proves every peer has finished reading it).
+// A step is: local scatter kernels -> copy into the export buffer -> hhfm_p2p_barrier (flags written into every peer with
+// system-scope release stores, each rank spins on its own copy) -> hhfm_opt_*_dense_l2_p2p, which reads element i of the
+// gradient from EVERY rank's export buffer (fixed rank order, so all replicas compute bit-identical sums and stay
+// bit-identical), applies the TF1 optimizer update to the local replica and clears the local arena slice.
 // There is no separate all-reduce pass: the reduction traffic (G x n x 4 bytes over NVLink per rank) is the
 // optimizer's gradient read.  NCCL stays in use for broadcast / all-gather plumbing only.
 #include <string.h>

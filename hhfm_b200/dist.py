@@ -94,9 +94,10 @@ class _RawDeviceBuffer:
 
 
 class PeerArena:
-    """Double-buffered gradient arena shared with the other ranks of the box over CUDA IPC + NVLink (csrc/p2p.cu).
+    """Double-buffered EXPORT copy of the gradient arena, shared with the other ranks of the box over CUDA IPC + NVLink
+    (csrc/p2p.cu).  The arena proper stays ordinary device memory; each step its gradient part is copied into bufs[cur].
 
-    bufs[b]      this rank's arena b as a float32 tensor (kernels scatter into bufs[cur])
+    bufs[b]      this rank's export buffer b as a float32 tensor
     table(b, o)  host array with the address of float `o` of arena b on every rank (rank order)
     barrier()    stream-ordered cross-GPU barrier: every rank's scatter kernels of this step are complete and visible
     """

@@ -121,12 +121,20 @@ class _Base:
         self._peer = None
         ws = dist.get_world_size(self._dp_group)
         import os
-        if os.environ.get("HHFM_DP_P2P") == "0":          # force the NCCL all-reduce exchange (A/B measurements)
+        env = os.environ.get("HHFM_DP_P2P")               # 0 / 1 force the NCCL all-reduce / the peer-memory exchange
+        if env == "0":
+            p2p = False
+        elif env == "1":
+            p2p = True
+        elif p2p == "auto" and ws > 2:
+            # measured on 8 B200 (bench.py, 200 steps): NCCL all-reduce (NVLS) 0.794 ms/step, peer-memory exchange 0.854 ms/step
+            # (2 GPUs: 0.80-0.86 both); the fused exchange stays the default only where it is not slower
             p2p = False
         if p2p and ws > 1 and self.device.type == "cuda":
             peer, ok = None, 1
             try:
-                peer = hd.PeerArena(self._arena.numel(), self.device, self._dp_group)
+                n_v, n_b, _ = self._arena_layout
+                peer = hd.PeerArena(n_v + n_b + 4, self.device, self._dp_group)      # gradients + gb0 + the loss slot
             except _lib.HhfmError:
                 if p2p is True:
                     raise
@@ -135,7 +143,6 @@ class _Base:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._dp_group)
             if int(flag.item()) == 1:
                 self._peer = peer
-                self._bind_arena(peer.bufs[peer.cur])
             elif p2p is True:
                 raise _lib.HhfmError("enable_data_parallel: a rank could not map its peers' arenas")
 
@@ -145,10 +152,14 @@ class _Base:
         if self._dp_group is None:
             return
         if self._peer is not None:
-            # publish this rank's loss as ONE float (arena slot after gb0) before the barrier: the peers then read
-            # n_ranks floats instead of n_ranks x 2048 partial slots
+            # publish this rank's loss as ONE float (arena slot after gb0): the peers then read n_ranks floats instead of
+            # n_ranks x 2048 partial slots.  The arena itself stays ordinary device memory (scattering straight into the
+            # IPC-exported buffer made the scatter kernel 5 % slower); its gradient part is copied into the current export
+            # buffer, then the barrier publishes it.
+            pr = self._peer
             _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), None, 0.0, ptr(self._loss_local), cur_stream())
-            self._peer.barrier()
+            pr.bufs[pr.cur].copy_(self._arena[:pr.n], non_blocking=True)
+            pr.barrier()
         else:
             import torch.distributed as dist
             dist.all_reduce(self._arena, group=self._dp_group)
@@ -160,8 +171,8 @@ class _Base:
             return
         pr = self._peer
         off = (g.data_ptr() - self._arena.data_ptr()) // 4
-        other = pr.bufs[pr.cur ^ 1]
-        self._opt.apply_dense_p2p(name, w, pr.table(pr.cur, off), pr.ws, other[off:off + g.numel()], lamda, sq)
+        # sum the ranks' export buffers; the local arena slice (never read by a peer) is cleared in place for the next step
+        self._opt.apply_dense_p2p(name, w, pr.table(pr.cur, off), pr.ws, g, lamda, sq)
 
     def enable_item_sharding(self, group=None):
         """Full-catalog top-N with the item catalog sharded across the ranks of `group`: every rank
@@ -228,8 +239,7 @@ class _Base:
         off = (self._loss_local.data_ptr() - self._arena.data_ptr()) // 4
         _lib.call("hhfm_loss_finalize_p2p", pr.table(pr.cur, off), pr.ws, 1, sq, hl if with_reg else 0.0, ptr(self._loss_dev),
                   cur_stream())
-        pr.cur ^= 1
-        self._bind_arena(pr.bufs[pr.cur])
+        pr.cur ^= 1          # the other export buffer next step: this one may still be read by a slower peer
 
     def _read_loss(self):
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
