@@ -142,10 +142,22 @@ __global__ void __launch_bounds__(256) hot_fold_kernel(float* __restrict__ ghot,
   if (i < total) {
     const int s = (int)(i / kv), c = (int)(i % kv);
     float4 acc = f4_zero();
-    for (int r = 0; r < n_rep; r++) {
-      float4* p = reinterpret_cast<float4*>(ghot + ((size_t)r * n_hot + s) * K) + c;
-      acc = f4_add(acc, *p);
-      *p = f4_zero();
+    // eight replica loads in flight per thread (the plain loop was a chain of n_rep dependent L2 round trips); the sum is
+    // still formed in replica order, so it is reproducible
+    for (int r0 = 0; r0 < n_rep; r0 += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        float4* p = reinterpret_cast<float4*>(ghot + ((size_t)(r0 + q) * n_hot + s) * K) + c;
+        t[q] = (r0 + q < n_rep) ? *p : f4_zero();
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (r0 + q < n_rep) {
+          acc = f4_add(acc, t[q]);
+          *(reinterpret_cast<float4*>(ghot + ((size_t)(r0 + q) * n_hot + s) * K) + c) = f4_zero();
+        }
+      }
     }
     float4* d = reinterpret_cast<float4*>(gV + (size_t)hot_rows[s] * K) + c;
     *d = f4_add(*d, acc);
