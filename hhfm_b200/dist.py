@@ -172,3 +172,25 @@ class PeerArena:
         for a in self._opened:
             self._lib.call("hhfm_p2p_close", a)
         self._opened = []
+
+
+def allreduce_metrics(codes, group=None):
+    """HR / NDCG / reciprocal-rank over context rows sharded across ranks: every rank walks its rows
+    (rank codes from `engine.metrics_walk`: -2 row dropped, -1 miss, n >= 0 hit at rank n), the three sums and the count
+    of contributing rows are all-reduced (the count varies per rank: FM.py:336-357 drops rows), then divided.
+    float64 sums: identical to np.average over the concatenated rows up to summation order."""
+    import numpy as np
+    c = np.asarray(codes).reshape(-1)
+    hit = c >= 0
+    n = c[hit].astype(np.float64)
+    local = torch.tensor([float(hit.sum()), float((np.log(2.0) / np.log(n + 2.0)).sum()), float((1.0 / (n + 1.0)).sum()),
+                          float((c != -2).sum())], dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        backend = dist.get_backend(group)
+        t = local.cuda() if backend == "nccl" else local
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        local = t.cpu()
+    cnt = float(local[3])
+    if cnt == 0:
+        return [float("nan")] * 3
+    return [float(local[0]) / cnt, float(local[1]) / cnt, float(local[2]) / cnt]

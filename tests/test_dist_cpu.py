@@ -87,3 +87,18 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _metric_shards(rank, world):
+    from hhfm_b200 import dist as hd
+    from hhfm_b200 import engine
+    rng = np.random.default_rng(5)
+    codes = rng.integers(-2, 10, 101).astype(np.int32)
+    lo, hi = hd.shard_range(len(codes), rank, world)
+    got = hd.allreduce_metrics(codes[lo:hi])
+    want = engine.metrics_from_codes(codes)
+    return bool(np.allclose(got, want, rtol=1e-12, atol=0))
+
+
+def test_sharded_metric_walk_allreduce_equals_the_single_process_average():
+    assert all(run2(_metric_shards))
