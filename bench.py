@@ -437,11 +437,11 @@ def run_ours(args):
             "gpu_launches": (4 if hot is not None else 3) * args.steps,
             "hot_rows": {"n_hot": hot.n_hot, "n_rep": hot.n_rep} if hot is not None else None,
             "roofline": {"bound": "hbm", "kernel": "pairrank_sum_train_kernel<16,8,10>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": 107.9e6, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": 103.3e6, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "kernel_ms": kern_ms,
                          "note": "frac > 1 is expected here: at frappe shape the 1.4 MB table and the hot-row replicas are "
                                  "L2-resident, so of the 8016 algorithmic B/sample only the 80 B record streams from HBM "
-                                 "(ncu: 108 MB DRAM traffic per launch, dram 2 %, l1tex 67 %, lts 56 % of peak); the kernel "
+                                 "(ncu: 103 MB DRAM traffic per launch -- profiles/r1_launches_bench.csv; dram 2 %, l1tex 67 %, lts 56 % of peak); the kernel "
                                  "is L1/L2-throughput bound, see profiles/r1_pairrank_summary.md"},
             "clocks": clocks, "final_loss": loss_value,
         }
