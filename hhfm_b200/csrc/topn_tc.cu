@@ -30,7 +30,8 @@ namespace hhfm {
 constexpr int kGroup = 32;          // items per group maximum (= one tcgen05.ld.32x32b.x32)
 constexpr int kBM = 128;            // contexts per CTA tile (UMMA M)
 constexpr int kKC = 64;             // bf16 elements per 128-byte swizzle row
-constexpr int kTcThreads = 320;     // warps 0-3 and 6-9: epilogue (two per TMEM lane quarter), warp 4: TMA, warp 5: MMA
+constexpr int kTcSubs = 4;           // epilogue warps per TMEM lane quarter (each owns BN/4 accumulator columns)
+constexpr int kTcThreads = (2 + 4 * kTcSubs) * 32;   // warps 0-3 and 6-17: epilogue, warp 4: TMA, warp 5: MMA
 
 // ---------------------------------------------------------------------------------------------------
 // operand preparation
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_co
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 256); }
+    for (int i = 0; i < 2; i++) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4 * kTcSubs * 32); }
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
@@ -214,28 +215,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_co
       }
     }
   } else {
-    // ================= epilogue: 8 warps.  A warp may only touch the TMEM lane quarter (warp % 4), so warps w and w+4
-    // (mod 4) share the 32 context rows of a quarter and split the BN accumulator columns in halves: thread
-    // (quarter, lane, half) owns context row quarter*32+lane for the item columns of its half.  With 4 epilogue warps the
-    // tensor pipe was 42 % (emission) / 69 % (max pass) busy, waiting for the epilogue to drain TMEM. =================
+    // ================= epilogue: 16 warps.  A warp may only touch the TMEM lane quarter (warp % 4), so the four warps of a
+    // quarter share its 32 context rows and split the BN accumulator columns in four: thread (quarter, lane, sub) owns
+    // context row quarter*32+lane for BN/4 item columns.  History: 4 warps -> tensor pipe 42 % (emission) / 69 % (max pass)
+    // busy waiting for the epilogue; 8 warps -> emission 1.21 -> 0.95 ms; 16 warps with 16-column TMEM loads (two register
+    // buffers of 16, no spills at 576 threads). =================
     int acc = 0; uint32_t tph = 0;
-    const int quarter = warp & 3, half = warp >= 6 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int sub = (warp < 4 ? warp : warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     constexpr int kChunksTile = BN / kGroup;
-    constexpr int kChunks = kChunksTile / 2;        // chunks per thread and tile
+    constexpr int kCols = BN / kTcSubs;              // columns per thread and tile (64 or 32)
+    constexpr int kChunks = kCols / kGroup;          // 32-item groups per thread and tile (2 or 1)
+    constexpr int kC16 = kCols / 16;                 // 16-column TMEM loads per thread and tile (4 or 2)
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
       const int rb = u / a.splits, sp = u % a.splits;
       const int t0 = sp * a.tiles_per_unit, t1 = min(a.n_tiles, t0 + a.tiles_per_unit);
       const int64_t row = (int64_t)rb * kBM + row_in_tile;
       const float thr = (EMIT && row < a.C) ? __ldg(a.thr_emit + row) : INFINITY;
-      int32_t* seg = EMIT ? a.seg_ids + (((int64_t)row * a.splits + sp) * 2 + half) * a.cap_u : nullptr;
+      int32_t* seg = EMIT ? a.seg_ids + (((int64_t)row * a.splits + sp) * kTcSubs + sub) * a.cap_u : nullptr;
       int n_emit = 0;
       for (int t = t0; t < t1; t++) {
         mbar_wait(t_full + acc, tph, a.err);
         tc_fence_after();
         float gm[kChunks];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-        const int64_t n_base = (int64_t)t * a.tile_stride * BN + half * (BN / 2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + sub * kCols);
+        const int64_t n_base = (int64_t)t * a.tile_stride * BN + sub * kCols;
         if (!EMIT) {
 #pragma unroll
           for (int c = 0; c < kChunks; c++) {
@@ -254,28 +259,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_co
             gm[c] = m;
           }
         } else {
-          // Survivor emission.  Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is
-          // scanned (with one buffer every chunk paid the full TMEM load latency: 1.7 ms against 1.0 ms for the max
-          // pass).  The scan is a max tree over four 8-item sub-groups; only a sub-group holding a survivor builds a
-          // bit mask.  The loop is unrolled by 2 only, so the epilogue stays inside the instruction cache (an unrolled
-          // 8 x 32 emission body is ~100 KB of SASS and ran 10x slower).
-          auto scan = [&](const uint32_t (&r)[32], int c) {
-            float mq[4];
+          // Survivor emission.  Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is scanned
+          // (with one buffer every chunk paid the full TMEM load latency).  The scan is a max tree over two 8-item
+          // sub-groups; only a sub-group holding a survivor builds a bit mask.  The loop is unrolled by 2 only, so the
+          // epilogue stays inside the instruction cache (an unrolled 8 x 32 emission body is ~100 KB of SASS and ran 10x
+          // slower).
+          auto scan = [&](const uint32_t (&r)[16], int c) {
+            float mq[2];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < 2; q++) {
               float m = __uint_as_float(r[8 * q]);
 #pragma unroll
               for (int i = 1; i < 8; i++) m = fmaxf(m, __uint_as_float(r[8 * q + i]));
               mq[q] = m;
             }
-            if (fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) >= thr) {   // rare: a few hundred survivors per row
+            if (fmaxf(mq[0], mq[1]) >= thr) {   // rare: a few hundred survivors per row
 #pragma unroll
-              for (int q = 0; q < 4; q++) {
+              for (int q = 0; q < 2; q++) {
                 if (mq[q] >= thr) {
                   unsigned mask = 0u;
 #pragma unroll
                   for (int i = 0; i < 8; i++) mask |= (__uint_as_float(r[8 * q + i]) >= thr ? 1u : 0u) << i;
-                  const int nb = (int)n_base + c * kGroup + 8 * q;
+                  const int nb = (int)n_base + c * 16 + 8 * q;
                   while (mask) {                // no atomics: the segment belongs to this thread
                     const int i = __ffs((int)mask) - 1;
                     mask &= mask - 1;
@@ -288,15 +293,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_co
               }
             }
           };
-          uint32_t ra[32], rb[32];
-          tmem_ld32(taddr, ra);
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr, ra);
 #pragma unroll 1
-          for (int c = 0; c < kChunks; c += 2) {
-            tmem_ld_wait_for(ra);
-            tmem_ld32(taddr + (c + 1) * kGroup, rb);
+          for (int c = 0; c < kC16; c += 2) {
+            tmem_ld_wait_for16(ra);
+            tmem_ld16(taddr + (c + 1) * 16, rb);
             scan(ra, c);
-            tmem_ld_wait_for(rb);
-            if (c + 2 < kChunks) tmem_ld32(taddr + (c + 2) * kGroup, ra);
+            tmem_ld_wait_for16(rb);
+            if (c + 2 < kC16) tmem_ld16(taddr + (c + 2) * 16, ra);
             scan(rb, c + 1);
           }
         }
@@ -304,25 +309,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_score_kernel(const __grid_co
         mbar_arrive(t_empty + acc);
         if (!EMIT && row < a.C) {
           if (a.fine) {
-            float* dst = a.gmax + row * a.gmax_stride + (int64_t)t * kChunksTile + half * kChunks;
-            if (kChunks % 4 == 0) {
-#pragma unroll
-              for (int c = 0; c + 3 < kChunks; c += 4)
-                reinterpret_cast<float4*>(dst)[c / 4] = make_float4(gm[c], gm[c + 1], gm[c + 2], gm[c + 3]);
-            } else {
-#pragma unroll
-              for (int c = 0; c + 1 < kChunks; c += 2) reinterpret_cast<float2*>(dst)[c / 2] = make_float2(gm[c], gm[c + 1]);
-            }
-          } else {                                   // one maximum per half tile
+            float* dst = a.gmax + row * a.gmax_stride + (int64_t)t * kChunksTile + sub * kChunks;
+            if (kChunks == 2) *reinterpret_cast<float2*>(dst) = make_float2(gm[0], gm[kChunks - 1]);
+            else dst[0] = gm[0];
+          } else {                                   // one maximum per quarter tile
             float m = gm[0];
 #pragma unroll
             for (int c = 1; c < kChunks; c++) m = fmaxf(m, gm[c]);
-            a.gmax[row * a.gmax_stride + 2 * t + half] = m;
+            a.gmax[row * a.gmax_stride + kTcSubs * t + sub] = m;
           }
         }
         if (++acc == 2) { acc = 0; tph ^= 1; }
       }
-      if (EMIT && row < a.C) a.seg_cnt[(row * a.splits + sp) * 2 + half] = n_emit;
+      if (EMIT && row < a.C) a.seg_cnt[(row * a.splits + sp) * kTcSubs + sub] = n_emit;
     }
   }
   tc_fence_before();
@@ -772,7 +771,7 @@ static void tc_decompose(int n_row_blocks, int n_tiles, int* splits_out, int* ti
   int lo = (4 * sms + n_row_blocks - 1) / n_row_blocks, hi = (12 * sms + n_row_blocks - 1) / n_row_blocks;
   if (lo < 1) lo = 1;
   if (hi > n_tiles) hi = n_tiles;
-  if (hi > 224) hi = 224;                 // tc_rescore_kernel keeps a prefix of the 2*splits segment counts in shared memory
+  if (hi > 112) hi = 112;                 // the candidate compaction handles at most 512 = kTcSubs * splits segments per row
   if (lo > hi) lo = hi;
   int64_t best = -1;
   int best_splits = lo, best_tpu = (n_tiles + lo - 1) / lo;
@@ -817,12 +816,12 @@ static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
     L.n_groups = s > 1 ? L.s_tiles * (bn / kGroup) : (int)((N + kGroup - 1) / kGroup);
     L.gmax_stride = (int64_t)L.s_tiles * (bn / kGroup);
   } else {
-    L.n_groups = 2 * (int)n_tiles;                    // one maximum per half tile
-    L.gmax_stride = (2 * n_tiles + 3) / 4 * 4;
+    L.n_groups = kTcSubs * (int)n_tiles;              // one maximum per quarter tile
+    L.gmax_stride = (int64_t)kTcSubs * n_tiles;
   }
   tc_decompose(L.n_row_blocks, L.s_tiles, &L.s_splits, &L.s_tiles_per_unit, &L.s_units);
   L.cap = (s > 1 ? 8 : 4) * tp + 256;                 // survivors per row (expected ~2 tp, ~3.5 tp when sampled)
-  L.cap_u = (4 * L.cap) / (2 * L.splits) + 32;        // per (row, split, column half) segment: 4x the even share + slack
+  L.cap_u = (4 * L.cap) / (kTcSubs * L.splits) + 32;  // per (row, split, column quarter) segment: 4x the even share + slack
   if (L.cap_u > L.cap) L.cap_u = L.cap;
   size_t o = 0;
   L.off_A = o; o = align(o + (size_t)C * Kp * 2);
@@ -831,8 +830,8 @@ static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
   L.off_tau = o; o = align(o + (size_t)C * L.rank_j * 4 * 2);      // select writes [C,rank_j] scores + ids
   L.off_thr = o; o = align(o + (size_t)C * 4);
   L.off_thrv = o; o = align(o + (size_t)C * 4);
-  L.off_seg = o; o = align(o + (size_t)C * 2 * L.splits * L.cap_u * 4);
-  L.off_segcnt = o; o = align(o + (size_t)C * 2 * L.splits * 4);
+  L.off_seg = o; o = align(o + (size_t)C * kTcSubs * L.splits * L.cap_u * 4);
+  L.off_segcnt = o; o = align(o + (size_t)C * kTcSubs * L.splits * 4);
   L.off_cs = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_ci = o; o = align(o + (size_t)C * L.cap * 4);
   L.off_cc = o; o = align(o + (size_t)C * 4);
@@ -977,14 +976,14 @@ extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float
   int32_t* ci = reinterpret_cast<int32_t*>(ws + L.off_ci);
   int32_t* cc = reinterpret_cast<int32_t*>(ws + L.off_cc);
   const int fm = kind == HHFM_QUERY_FM;
-  HHFM_REQUIRE(2 * L.splits <= 511, "topn_rescore_merge: too many item splits");
+  HHFM_REQUIRE(kTcSubs * L.splits <= 511, "topn_rescore_merge: too many item splits");
   int rc;
   const size_t stage_b = rescore_stage_bytes((int)K, fm);
   if (K % 4 == 0 && (((uintptr_t)items | (uintptr_t)Q | (uintptr_t)Fc) & 15) == 0 && 2 * stage_b + 128 <= (size_t)200 * 1024 &&
       L.cap <= 2048) {
     int32_t* n_work = reinterpret_cast<int32_t*>(ws + L.off_nwork);
     cudaMemsetAsync(n_work, 0, sizeof(int32_t), st);
-    tc_compact_kernel<<<(unsigned)C, 128, 0, st>>>(2 * L.splits, L.cap_u, L.cap, reinterpret_cast<const int32_t*>(ws + L.off_seg),
+    tc_compact_kernel<<<(unsigned)C, 128, 0, st>>>(kTcSubs * L.splits, L.cap_u, L.cap, reinterpret_cast<const int32_t*>(ws + L.off_seg),
                                                   reinterpret_cast<const int32_t*>(ws + L.off_segcnt), ci, cc, overflow,
                                                   reinterpret_cast<int32_t*>(ws + L.off_work), n_work);
     if ((rc = check_launch("tc_compact_kernel"))) return rc;
@@ -1001,7 +1000,7 @@ extern "C" int hhfm_topn_rescore_merge(int32_t kind, const float* Q, const float
     rc = check_launch("tc_rescore_staged_kernel");
   } else {
     const size_t smem = (size_t)K * (fm ? 2 : 1) * sizeof(float);
-    tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, 2 * L.splits, L.cap_u,
+    tc_rescore_kernel<<<(unsigned)C, 256, smem, st>>>(kind, Q, Fc, items, fm ? item_bias : nullptr, N, (int)K, kTcSubs * L.splits, L.cap_u,
                                                       reinterpret_cast<const int32_t*>(ws + L.off_seg),
                                                       reinterpret_cast<const int32_t*>(ws + L.off_segcnt), L.cap, cs, ci, cc,
                                                       overflow);
