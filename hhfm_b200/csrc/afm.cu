@@ -12,6 +12,8 @@
 // go through the same sort-free vector reductions (and hot-row replicas) as the FM / HHFM kernels.
 // This kernel is compute-bound (about 1.1 MFLOP per sample at F=10, K=A=64); a tcgen05 version with split-precision
 // operands is the planned next step.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hhfm {
@@ -370,6 +372,392 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second layout (K == A == KD in {16, 32, 64}): ONE LANE PER PAIR for the two row-times-matrix products.
+// In afm_kernel the lanes run over the attention columns, so every FMA group needs its own W loads (ncu: 3.3 instructions
+// per FMA, FMA pipe 29 %).  Here lane p owns pair p: its logit row Z_p[0..KD) lives in KD registers and the row of W for
+// the current k is a broadcast LDS.128 shared by all lanes: per 4 k, 2 + 16 LDS.128 and 4 FMUL feed 256 FMA.  The pair
+// products are formed on the fly from the sample's F embedding rows (row stride KD+4: conflict-free for LDS.128 with one
+// row per lane, and for scalar access with lanes over k).  dP_p = a_p d_afm + dZ_p W^T has the same shape (W^T is kept in
+// shared memory too) and is written in place over dZ_p.  A round whose tail has <= 16 pairs splits the columns between the
+// two half-warps instead of idling half the lanes (P = 45: 1.5 rounds, not 2).
+// Per tile of NW samples:  phase A (forward, dZ) | barrier | dW sweep over the tile (warp owns KD/NW columns, lanes over
+// k) | barrier | phase B (dP over dZ, dE, scatter).  Shared memory per warp is F + P rows, so 8 warps (2 per scheduler)
+// fit next to W and W^T.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int afm2_p4(int P) { return (P + 3) / 4 * 4; }
+__host__ __device__ inline size_t afm2_per_warp_floats(int F, int KD, int P) {
+  return (size_t)F * KD + KD + 2 * (size_t)afm2_p4(P) + (size_t)(F + P) * (KD + 4);   // every term a multiple of 4
+}
+__host__ __device__ inline size_t afm2_smem_floats(int NW, int F, int KD, int P) {
+  return 2 * (size_t)KD * KD + 3 * (size_t)KD + (size_t)NW * afm2_per_warp_floats(F, KD, P) + 32;
+}
+
+// acc[c] += sum_k x_k * Wc[k*KD + c], c in [0, NC), with x_k = u[k] * v[k] (PROD) or u[k]
+template <int KD, int NC, bool PROD>
+__device__ __forceinline__ void afm2_row_times_matrix(float (&acc)[NC], const float* __restrict__ u, const float* __restrict__ v,
+                                                      const float* __restrict__ Wc) {
+#pragma unroll 1
+  for (int k = 0; k < KD; k += 4) {
+    const float4 x4 = *reinterpret_cast<const float4*>(u + k);
+    float x[4] = {x4.x, x4.y, x4.z, x4.w};
+    if (PROD) {
+      const float4 y4 = *reinterpret_cast<const float4*>(v + k);
+      x[0] *= y4.x; x[1] *= y4.y; x[2] *= y4.z; x[3] *= y4.w;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const float4* w4 = reinterpret_cast<const float4*>(Wc + (k + kk) * KD);
+#pragma unroll
+      for (int c4 = 0; c4 < NC / 4; c4++) {
+        const float4 w = w4[c4];
+        acc[4 * c4] = fmaf(x[kk], w.x, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(x[kk], w.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(x[kk], w.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(x[kk], w.w, acc[4 * c4 + 3]);
+      }
+    }
+  }
+}
+
+// One round of logits: Z_p = P_p W + b into sZ, returns this lane's share of s_p = relu(Z_p) . p
+template <int KD, int NC>
+__device__ __forceinline__ float afm2_logits(const float* ei, const float* ej, const float* sW, const float* sb, const float* sp,
+                                             float* zrow, int c0, bool act) {
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) acc[c] = sb[c0 + c];
+  afm2_row_times_matrix<KD, NC, true>(acc, ei, ej, sW + c0);
+  float sc = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; c++) sc = fmaf(fmaxf(acc[c], 0.f), sp[c0 + c], sc);
+  if (act) {
+#pragma unroll
+    for (int c4 = 0; c4 < NC / 4; c4++)
+      reinterpret_cast<float4*>(zrow + c0)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+  }
+  return act ? sc : 0.f;
+}
+
+// One round of dP_p = a_p d_afm + dZ_p W^T, written over dZ_p (the row's readers finish before anyone writes)
+template <int KD, int NC>
+__device__ __forceinline__ void afm2_dpairs(float* zrow, const float* sWT, const float* sdafm, float ap, int c0, bool act) {
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) acc[c] = ap * sdafm[c0 + c];
+  afm2_row_times_matrix<KD, NC, false>(acc, zrow, nullptr, sWT + c0);
+  __syncwarp();
+  if (act) {
+#pragma unroll
+    for (int c4 = 0; c4 < NC / 4; c4++)
+      reinterpret_cast<float4*>(zrow + c0)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+  }
+}
+
+template <int KD, int NW, bool TRAIN>
+__global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float scratch[32];
+  __shared__ unsigned char sPairI[kAfmMaxP], sPairJ[kAfmMaxP];
+  constexpr int RS = KD + 4;                 // row stride of sE / sZ
+  constexpr int TD = (KD + 31) / 32;         // values per lane when the lanes run over k / a
+  constexpr int AS = KD / NW;                // columns of dW per warp
+  static_assert(AS % 4 == 0, "dW column slice is read with LDS.128");
+  const int F = a.F, P = a.P, P4 = afm2_p4(P);
+  float* sW = smem;                          // [KD][KD]   W[k][a]
+  float* sWT = sW + KD * KD;                 // [KD][KD]   W^T[a][k]
+  float* sp = sWT + KD * KD;                 // [KD]
+  float* sb = sp + KD;                       // [KD]
+  float* swp = sb + KD;                      // [KD]
+  float* warp_base = swp + KD;
+  const size_t per_warp = afm2_per_warp_floats(F, KD, P);
+  int* sValid = reinterpret_cast<int*>(warp_base + (size_t)NW * per_warp);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sDE = warp_base + warp * per_warp;  // [F][KD]
+  float* sdafm = sDE + (size_t)F * KD;       // [KD]
+  float* sS = sdafm + KD;                    // [P] s, later a
+  float* sD = sS + P4;                       // [P] d a, later d s
+  float* sE = sD + P4;                       // [F][RS]
+  float* sZ = sE + (size_t)F * RS;           // [P][RS]  Z, then dZ, then dP
+  const size_t offE = (size_t)F * KD + KD + 2 * (size_t)P4;
+
+  for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) {
+    const float w = __ldg(a.W + i);
+    sW[i] = w;
+    sWT[(i % KD) * KD + (i / KD)] = w;
+  }
+  for (int i = threadIdx.x; i < KD; i += blockDim.x) { sp[i] = __ldg(a.pvec + i); sb[i] = __ldg(a.batt + i); swp[i] = __ldg(a.wpred + i); }
+  if (threadIdx.x == 0) {
+    int p = 0;
+    for (int i = 0; i < F; i++)
+      for (int j = i + 1; j < F; j++) { sPairI[p] = (unsigned char)i; sPairJ[p] = (unsigned char)j; p++; }
+  }
+  __syncthreads();
+
+  const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
+  const int rep = a.hot.slot ? (int)(((int64_t)blockIdx.x * NW + warp) % a.hot.n_rep) : 0;
+  float dWacc[TRAIN ? TD : 1][AS];
+  float gbatt_acc[TD], gp_acc[TD], gwp_acc[TD];
+  float loss_acc = 0.f, g0_acc = 0.f;
+  if (TRAIN) {
+#pragma unroll
+    for (int t = 0; t < TD; t++)
+#pragma unroll
+      for (int r = 0; r < AS; r++) dWacc[t][r] = 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < TD; t++) { gbatt_acc[t] = 0.f; gp_acc[t] = 0.f; gwp_acc[t] = 0.f; }
+
+  for (int64_t s0 = (int64_t)blockIdx.x * NW; s0 < a.B; s0 += (int64_t)gridDim.x * NW) {
+    const int64_t s = s0 + warp;
+    const bool valid = s < a.B;
+    float g = 0.f;
+    if (lane == 0) sValid[warp] = valid ? 1 : 0;
+    if (valid) {
+      const int32_t* rec = a.idx + s * F;
+      // ---- gather E and the bias sum ----
+      float bsum = 0.f;
+      for (int f = 0; f < F; f++) {
+        const int id = __ldg(rec + f);
+        for (int k = lane; k < KD; k += 32) sE[f * RS + k] = __ldg(a.V + (size_t)id * KD + k);
+        if (a.bias) bsum += __ldg(a.bias + id);
+      }
+      __syncwarp();
+      // ---- logits: lane = pair ----
+      for (int p0 = 0; p0 < P; p0 += 32) {
+        if (P - p0 > 16) {
+          const int p = p0 + lane;
+          const bool act = p < P;
+          const int q = act ? p : 0;
+          const float sc = afm2_logits<KD, KD>(sE + sPairI[q] * RS, sE + sPairJ[q] * RS, sW, sb, sp, sZ + q * RS, 0, act);
+          if (act) sS[p] = sc;
+        } else {
+          const int p = p0 + (lane & 15);
+          const bool act = p < P;
+          const int q = act ? p : 0;
+          float sc = afm2_logits<KD, KD / 2>(sE + sPairI[q] * RS, sE + sPairJ[q] * RS, sW, sb, sp, sZ + q * RS, (lane >> 4) * (KD / 2), act);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 16);
+          if (act && lane < 16) sS[p] = sc;
+        }
+      }
+      __syncwarp();
+      // ---- softmax over pairs (AFM.py:125) ----
+      float mx = -INFINITY;
+      for (int p = lane; p < P; p += 32) mx = fmaxf(mx, sS[p]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float den = 0.f;
+      for (int p = lane; p < P; p += 32) { const float e = expf(sS[p] - mx); sS[p] = e; den += e; }
+      den = warp_sum(den);
+      __syncwarp();
+      for (int p = lane; p < P; p += 32) sS[p] = sS[p] / den;
+      __syncwarp();
+      // ---- afm = sum_p a_p E_i E_j (lanes over k), out ----
+      float afm[TD];
+#pragma unroll
+      for (int t = 0; t < TD; t++) afm[t] = 0.f;
+      {
+        int p = 0;
+        for (int i = 0; i < F; i++) {
+          float ei[TD], in[TD];
+#pragma unroll
+          for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; ei[t] = (k < KD) ? sE[i * RS + k] : 0.f; in[t] = 0.f; }
+          for (int j = i + 1; j < F; j++, p++) {
+            const float ap = sS[p];
+#pragma unroll
+            for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; if (k < KD) in[t] = fmaf(ap, sE[j * RS + k], in[t]); }
+          }
+#pragma unroll
+          for (int t = 0; t < TD; t++) afm[t] = fmaf(ei[t], in[t], afm[t]);
+        }
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; if (k < KD) part = fmaf(afm[t], swp[k], part); }
+      const float bil = warp_sum(part);
+      const float out = (bil + bsum) + b0;                       // AFM.py:142 add_n
+      if (a.out && lane == 0) a.out[s] = out;
+
+      if (TRAIN) {
+        const float y = __ldg(a.labels + s);
+        const float diff = y - out;
+        g = -diff;
+        if (lane == 0) { loss_acc += 0.5f * diff * diff; g0_acc += g; }
+#pragma unroll
+        for (int t = 0; t < TD; t++) {
+          const int k = lane + 32 * t;
+          if (k < KD) { sdafm[k] = g * swp[k]; gwp_acc[t] = fmaf(g, afm[t], gwp_acc[t]); }
+        }
+        __syncwarp();
+        // ---- d a_p = (E_i E_j) . d afm (lane = pair), softmax backward ----
+        float dotp = 0.f;
+        for (int p = lane; p < P; p += 32) {
+          const float* ei = sE + sPairI[p] * RS; const float* ej = sE + sPairJ[p] * RS;
+          float v = 0.f;
+#pragma unroll 4
+          for (int k = 0; k < KD; k += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(ei + k), y4 = *reinterpret_cast<const float4*>(ej + k);
+            const float4 d = *reinterpret_cast<const float4*>(sdafm + k);
+            v = fmaf(x.x * y4.x, d.x, v); v = fmaf(x.y * y4.y, d.y, v); v = fmaf(x.z * y4.z, d.z, v); v = fmaf(x.w * y4.w, d.w, v);
+          }
+          sD[p] = v;
+          dotp = fmaf(sS[p], v, dotp);
+        }
+        const float dot = warp_sum(dotp);
+        __syncwarp();
+        for (int p = lane; p < P; p += 32) sD[p] = sS[p] * (sD[p] - dot);       // d s_p
+        __syncwarp();
+        // ---- d Z_p = d s_p p (Z_p > 0) (over Z) ; d p += d s_p relu(Z_p) ; d b += d Z_p  (lanes over a) ----
+        for (int p = 0; p < P; p++) {
+          const float ds = sD[p];
+#pragma unroll
+          for (int t = 0; t < TD; t++) {
+            const int aa = lane + 32 * t;
+            if (aa < KD) {
+              const float z = sZ[p * RS + aa];
+              const float dz = (z > 0.f) ? ds * sp[aa] : 0.f;
+              gp_acc[t] = fmaf(ds, fmaxf(z, 0.f), gp_acc[t]);
+              gbatt_acc[t] += dz;
+              sZ[p * RS + aa] = dz;
+            }
+          }
+        }
+      }
+    }
+    if (TRAIN) {
+      __syncthreads();
+      // ---- d W[k][a] += (E_i E_j)[k] dZ_p[a]: lanes over k, warp w owns a in [w*AS, (w+1)*AS), every sample of the tile ----
+      for (int ws = 0; ws < NW; ws++) {
+        if (!sValid[ws]) continue;
+        const float* oE = warp_base + ws * per_warp + offE;
+        const float* oZ = oE + (size_t)F * RS + warp * AS;
+        int p = 0;
+        for (int i = 0; i < F; i++) {
+          float ei[TD];
+#pragma unroll
+          for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; ei[t] = (k < KD) ? oE[i * RS + k] : 0.f; }
+          for (int j = i + 1; j < F; j++, p++) {
+            float pk[TD];
+#pragma unroll
+            for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; pk[t] = (k < KD) ? ei[t] * oE[j * RS + k] : 0.f; }
+#pragma unroll
+            for (int r4 = 0; r4 < AS / 4; r4++) {
+              const float4 dz = *reinterpret_cast<const float4*>(oZ + p * RS + 4 * r4);
+#pragma unroll
+              for (int t = 0; t < TD; t++) {
+                dWacc[t][4 * r4] = fmaf(pk[t], dz.x, dWacc[t][4 * r4]);
+                dWacc[t][4 * r4 + 1] = fmaf(pk[t], dz.y, dWacc[t][4 * r4 + 1]);
+                dWacc[t][4 * r4 + 2] = fmaf(pk[t], dz.z, dWacc[t][4 * r4 + 2]);
+                dWacc[t][4 * r4 + 3] = fmaf(pk[t], dz.w, dWacc[t][4 * r4 + 3]);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (valid) {
+        const int32_t* rec = a.idx + s * F;
+        // ---- d P_p = a_p d afm + d Z_p W^T (lane = pair), in place ----
+        for (int p0 = 0; p0 < P; p0 += 32) {
+          if (P - p0 > 16) {
+            const int p = p0 + lane;
+            const bool act = p < P;
+            afm2_dpairs<KD, KD>(sZ + (act ? p : 0) * RS, sWT, sdafm, act ? sS[p] : 0.f, 0, act);
+          } else {
+            const int p = p0 + (lane & 15);
+            const bool act = p < P;
+            afm2_dpairs<KD, KD / 2>(sZ + (act ? p : 0) * RS, sWT, sdafm, act ? sS[p] : 0.f, (lane >> 4) * (KD / 2), act);
+          }
+        }
+        __syncwarp();
+        // ---- d E_f = sum_{g != f} dP_{fg} * E_g  (lanes over k, registers; no read-modify-write through shared memory) ----
+        for (int f = 0; f < F; f++) {
+          float de[TD];
+#pragma unroll
+          for (int t = 0; t < TD; t++) de[t] = 0.f;
+          for (int o = 0; o < F; o++) {
+            if (o == f) continue;
+            const int i = f < o ? f : o, j = f < o ? o : f;
+            const int p = i * F - ((i * (i + 1)) >> 1) + (j - i - 1);
+#pragma unroll
+            for (int t = 0; t < TD; t++) {
+              const int k = lane + 32 * t;
+              if (k < KD) de[t] = fmaf(sZ[p * RS + k], sE[o * RS + k], de[t]);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TD; t++) { const int k = lane + 32 * t; if (k < KD) sDE[f * KD + k] = de[t]; }
+        }
+        __syncwarp();
+        for (int f = 0; f < F; f++) {
+          const int id = __ldg(rec + f);
+          float* dst = a.gV + (size_t)id * KD;
+          if (a.hot.slot != nullptr) {
+            const int hs = __ldg(a.hot.slot + id);
+            if (hs >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + hs) * KD;
+          }
+          for (int c = lane; c < (KD >> 2); c += 32) red_add_v4(dst + 4 * c, reinterpret_cast<const float4*>(sDE + f * KD)[c]);
+          if (lane == 0) {
+            if (a.gbias) scatter_bias(a.gbias, a.hot, rep, id, g);
+            touch_row(a.touch_stamp, a.stamp, a.touched_rows, a.touched_count, id);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  if (TRAIN) {
+#pragma unroll
+    for (int t = 0; t < TD; t++) {
+      const int k = lane + 32 * t;
+      if (k < KD) {
+#pragma unroll
+        for (int r = 0; r < AS; r++)
+          if (dWacc[t][r] != 0.f) atomicAdd(a.gW + (size_t)k * KD + warp * AS + r, dWacc[t][r]);
+        atomicAdd(a.gbatt + k, gbatt_acc[t]); atomicAdd(a.gp + k, gp_acc[t]); atomicAdd(a.gwpred + k, gwp_acc[t]);
+      }
+    }
+    const float bl = block_sum(loss_acc, scratch);
+    write_partial(a.loss_partials, bl);
+    const float bg = block_sum(g0_acc, scratch);
+    if (threadIdx.x == 0 && a.gb0 && bg != 0.f) atomicAdd(a.gb0, bg);
+  }
+}
+
+template <int KD, int NW, bool TRAIN>
+static int launch_afm2(const AfmArgs& a, cudaStream_t st) {
+  const size_t smem = afm2_smem_floats(NW, a.F, KD, a.P) * sizeof(float);
+  if (smem > 220 * 1024) return 1;
+  auto kern = afm2_kernel<KD, NW, TRAIN>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("afm2_kernel: cannot reserve %zu bytes of shared memory", smem);
+    return HHFM_ERR_LAUNCH;
+  }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem);
+  if (occ < 1) occ = 1;
+  int64_t need = (a.B + NW - 1) / NW;
+  int64_t cap = (int64_t)sm_count() * occ;
+  if (cap > kPartials) cap = kPartials;
+  const int grid = (int)(need < cap ? need : cap);
+  kern<<<grid, NW * 32, smem, st>>>(a);
+  return check_launch("afm2_kernel");
+}
+
+// returns 1 when the shape is not covered (the caller then uses afm_kernel)
+template <bool TRAIN>
+static int dispatch_afm2(const AfmArgs& a, cudaStream_t st) {
+  const char* e = getenv("HHFM_AFM_V1");           // 1 = force the first layout (A/B measurements, tests of both kernels)
+  if (e && e[0] == '1') return 1;
+  if (a.K != a.A) return 1;
+  int rc = 1;
+  if (a.K == 64) { rc = launch_afm2<64, 8, TRAIN>(a, st); if (rc == 1) rc = launch_afm2<64, 4, TRAIN>(a, st); }
+  else if (a.K == 32) { rc = launch_afm2<32, 8, TRAIN>(a, st); if (rc == 1) rc = launch_afm2<32, 4, TRAIN>(a, st); }
+  else if (a.K == 16) rc = launch_afm2<16, 4, TRAIN>(a, st);
+  return rc;
+}
+
 template <int TK, int TA, int NW, bool TRAIN>
 static int launch_afm(const AfmArgs& a, cudaStream_t st) {
   const size_t smem = afm_smem_floats(NW, a.F, a.K, a.A, a.P) * sizeof(float);
@@ -392,6 +780,10 @@ static int launch_afm(const AfmArgs& a, cudaStream_t st) {
 
 template <bool TRAIN>
 static int dispatch_afm(const AfmArgs& a, cudaStream_t st) {
+  {
+    const int rc2 = dispatch_afm2<TRAIN>(a, st);
+    if (rc2 != 1) return rc2;
+  }
   // largest warp count whose shared-memory footprint fits; K % NW == 0 and K/NW % 4 == 0 are needed by the dW sweep
   const int tk = (a.K + 31) / 32, ta = (a.A + 31) / 32;
   int rc = 1;

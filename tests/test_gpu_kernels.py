@@ -620,8 +620,11 @@ def _afm_weights(rng, M, K, A):
                 prediction=rng.normal(1, 0.1, (K, 1)).astype(np.float32))
 
 
-@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64)])
-def test_afm_fused_pass_matches_oracle(cuda, B, F, K):
+@pytest.mark.parametrize("layout", ["pair-per-lane", "column-per-lane"])
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64), (45, 9, 32), (40, 11, 32)])
+def test_afm_fused_pass_matches_oracle(cuda, B, F, K, layout, monkeypatch):
+    """Both layouts of the fused kernel (afm.cu: afm2_kernel covers K == A in {16, 32, 64}; afm_kernel everything else)."""
+    monkeypatch.setenv("HHFM_AFM_V1", "1" if layout == "column-per-lane" else "0")
     lib, ptr, st = _lib_ptr()
     rng = np.random.default_rng(B + F + K)
     M, A = 300, K
