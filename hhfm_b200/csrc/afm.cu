@@ -393,17 +393,22 @@ __host__ __device__ inline size_t afm2_smem_floats(int NW, int F, int KD, int P)
   return 2 * (size_t)KD * KD + 3 * (size_t)KD + (size_t)NW * afm2_per_warp_floats(F, KD, P) + 32;
 }
 
-// acc[c] += sum_k x_k * Wc[k*KD + c], c in [0, NC), with x_k = u[k] * v[k] (PROD) or u[k]
-template <int KD, int NC, bool PROD>
-__device__ __forceinline__ void afm2_row_times_matrix(float (&acc)[NC], const float* __restrict__ u, const float* __restrict__ v,
-                                                      const float* __restrict__ Wc) {
+// acc[r][c] += sum_k x_rk * Wc[k*KD + c], c in [0, NC), r in [0, NR), with x_rk = u_r[k] * v_r[k] (PROD) or u_r[k].
+// One broadcast LDS.128 of W (2 shared-memory wavefronts for 16 bytes - the cost that bounds this kernel) feeds 4*NR FMAs.
+template <int KD, int NC, int NR, bool PROD>
+__device__ __forceinline__ void afm2_rows_times_matrix(float (&acc)[NR][NC], const float* const (&u)[NR], const float* const (&v)[NR],
+                                                       const float* __restrict__ Wc) {
 #pragma unroll 1
   for (int k = 0; k < KD; k += 4) {
-    const float4 x4 = *reinterpret_cast<const float4*>(u + k);
-    float x[4] = {x4.x, x4.y, x4.z, x4.w};
-    if (PROD) {
-      const float4 y4 = *reinterpret_cast<const float4*>(v + k);
-      x[0] *= y4.x; x[1] *= y4.y; x[2] *= y4.z; x[3] *= y4.w;
+    float x[NR][4];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const float4 x4 = *reinterpret_cast<const float4*>(u[r] + k);
+      x[r][0] = x4.x; x[r][1] = x4.y; x[r][2] = x4.z; x[r][3] = x4.w;
+      if (PROD) {
+        const float4 y4 = *reinterpret_cast<const float4*>(v[r] + k);
+        x[r][0] *= y4.x; x[r][1] *= y4.y; x[r][2] *= y4.z; x[r][3] *= y4.w;
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
@@ -411,50 +416,80 @@ __device__ __forceinline__ void afm2_row_times_matrix(float (&acc)[NC], const fl
 #pragma unroll
       for (int c4 = 0; c4 < NC / 4; c4++) {
         const float4 w = w4[c4];
-        acc[4 * c4] = fmaf(x[kk], w.x, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(x[kk], w.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(x[kk], w.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(x[kk], w.w, acc[4 * c4 + 3]);
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          acc[r][4 * c4] = fmaf(x[r][kk], w.x, acc[r][4 * c4]);
+          acc[r][4 * c4 + 1] = fmaf(x[r][kk], w.y, acc[r][4 * c4 + 1]);
+          acc[r][4 * c4 + 2] = fmaf(x[r][kk], w.z, acc[r][4 * c4 + 2]);
+          acc[r][4 * c4 + 3] = fmaf(x[r][kk], w.w, acc[r][4 * c4 + 3]);
+        }
       }
     }
   }
 }
 
-// One round of logits: Z_p = P_p W + b into sZ, returns this lane's share of s_p = relu(Z_p) . p
-template <int KD, int NC>
-__device__ __forceinline__ float afm2_logits(const float* ei, const float* ej, const float* sW, const float* sb, const float* sp,
-                                             float* zrow, int c0, bool act) {
-  float acc[NC];
+// Lane (h, l) = (lane >> 4, lane & 15) owns pairs l, l + 16, ... (NR of them) and the column half [h*KD/2, (h+1)*KD/2).
+// Logits: Z_p = P_p W + b into sZ, s_p = relu(Z_p) . p into sS.
+template <int KD, int NR>
+__device__ __forceinline__ void afm2_logits(const float* sE, const unsigned char* sPairI, const unsigned char* sPairJ, const float* sW,
+                                            const float* sb, const float* sp, float* sZ, float* sS, int P, int lane) {
+  constexpr int NC = KD / 2, RS = KD + 4;
+  const int c0 = (lane >> 4) * NC, l = lane & 15;
+  float acc[NR][NC];
+  const float* u[NR]; const float* v[NR];
 #pragma unroll
-  for (int c = 0; c < NC; c++) acc[c] = sb[c0 + c];
-  afm2_row_times_matrix<KD, NC, true>(acc, ei, ej, sW + c0);
-  float sc = 0.f;
+  for (int r = 0; r < NR; r++) {
+    const int p = l + 16 * r, q = p < P ? p : 0;
+    u[r] = sE + sPairI[q] * RS; v[r] = sE + sPairJ[q] * RS;
 #pragma unroll
-  for (int c = 0; c < NC; c++) sc = fmaf(fmaxf(acc[c], 0.f), sp[c0 + c], sc);
-  if (act) {
-#pragma unroll
-    for (int c4 = 0; c4 < NC / 4; c4++)
-      reinterpret_cast<float4*>(zrow + c0)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+    for (int c = 0; c < NC; c++) acc[r][c] = sb[c0 + c];
   }
-  return act ? sc : 0.f;
+  afm2_rows_times_matrix<KD, NC, NR, true>(acc, u, v, sW + c0);
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    const int p = l + 16 * r;
+    float sc = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; c++) sc = fmaf(fmaxf(acc[r][c], 0.f), sp[c0 + c], sc);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 16);
+    if (p < P) {
+#pragma unroll
+      for (int c4 = 0; c4 < NC / 4; c4++)
+        reinterpret_cast<float4*>(sZ + p * RS + c0)[c4] = make_float4(acc[r][4 * c4], acc[r][4 * c4 + 1], acc[r][4 * c4 + 2], acc[r][4 * c4 + 3]);
+      if (lane < 16) sS[p] = sc;
+    }
+  }
 }
 
-// One round of dP_p = a_p d_afm + dZ_p W^T, written over dZ_p (the row's readers finish before anyone writes)
-template <int KD, int NC>
-__device__ __forceinline__ void afm2_dpairs(float* zrow, const float* sWT, const float* sdafm, float ap, int c0, bool act) {
-  float acc[NC];
+// dP_p = a_p d_afm + dZ_p W^T, written over dZ_p (both lanes of a row finish reading it before either writes)
+template <int KD, int NR>
+__device__ __forceinline__ void afm2_dpairs(float* sZ, const float* sWT, const float* sdafm, const float* sS, int P, int lane) {
+  constexpr int NC = KD / 2, RS = KD + 4;
+  const int c0 = (lane >> 4) * NC, l = lane & 15;
+  float acc[NR][NC];
+  const float* u[NR];
 #pragma unroll
-  for (int c = 0; c < NC; c++) acc[c] = ap * sdafm[c0 + c];
-  afm2_row_times_matrix<KD, NC, false>(acc, zrow, nullptr, sWT + c0);
+  for (int r = 0; r < NR; r++) {
+    const int p = l + 16 * r;
+    const float ap = p < P ? sS[p] : 0.f;
+    u[r] = sZ + (p < P ? p : 0) * RS;
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[r][c] = ap * sdafm[c0 + c];
+  }
+  afm2_rows_times_matrix<KD, NC, NR, false>(acc, u, u, sWT + c0);
   __syncwarp();
-  if (act) {
 #pragma unroll
-    for (int c4 = 0; c4 < NC / 4; c4++)
-      reinterpret_cast<float4*>(zrow + c0)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+  for (int r = 0; r < NR; r++) {
+    const int p = l + 16 * r;
+    if (p < P) {
+#pragma unroll
+      for (int c4 = 0; c4 < NC / 4; c4++)
+        reinterpret_cast<float4*>(sZ + p * RS + c0)[c4] = make_float4(acc[r][4 * c4], acc[r][4 * c4 + 1], acc[r][4 * c4 + 2], acc[r][4 * c4 + 3]);
+    }
   }
 }
 
-template <int KD, int NW, bool TRAIN>
+template <int KD, int NW, int NR, bool TRAIN>
 __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float scratch[32];
@@ -523,23 +558,8 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
         if (a.bias) bsum += __ldg(a.bias + id);
       }
       __syncwarp();
-      // ---- logits: lane = pair ----
-      for (int p0 = 0; p0 < P; p0 += 32) {
-        if (P - p0 > 16) {
-          const int p = p0 + lane;
-          const bool act = p < P;
-          const int q = act ? p : 0;
-          const float sc = afm2_logits<KD, KD>(sE + sPairI[q] * RS, sE + sPairJ[q] * RS, sW, sb, sp, sZ + q * RS, 0, act);
-          if (act) sS[p] = sc;
-        } else {
-          const int p = p0 + (lane & 15);
-          const bool act = p < P;
-          const int q = act ? p : 0;
-          float sc = afm2_logits<KD, KD / 2>(sE + sPairI[q] * RS, sE + sPairJ[q] * RS, sW, sb, sp, sZ + q * RS, (lane >> 4) * (KD / 2), act);
-          sc += __shfl_xor_sync(0xffffffffu, sc, 16);
-          if (act && lane < 16) sS[p] = sc;
-        }
-      }
+      // ---- logits: lane = (column half, pair mod 16) ----
+      afm2_logits<KD, NR>(sE, sPairI, sPairJ, sW, sb, sp, sZ, sS, P, lane);
       __syncwarp();
       // ---- softmax over pairs (AFM.py:125) ----
       float mx = -INFINITY;
@@ -657,18 +677,8 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
       __syncthreads();
       if (valid) {
         const int32_t* rec = a.idx + s * F;
-        // ---- d P_p = a_p d afm + d Z_p W^T (lane = pair), in place ----
-        for (int p0 = 0; p0 < P; p0 += 32) {
-          if (P - p0 > 16) {
-            const int p = p0 + lane;
-            const bool act = p < P;
-            afm2_dpairs<KD, KD>(sZ + (act ? p : 0) * RS, sWT, sdafm, act ? sS[p] : 0.f, 0, act);
-          } else {
-            const int p = p0 + (lane & 15);
-            const bool act = p < P;
-            afm2_dpairs<KD, KD / 2>(sZ + (act ? p : 0) * RS, sWT, sdafm, act ? sS[p] : 0.f, (lane >> 4) * (KD / 2), act);
-          }
-        }
+        // ---- d P_p = a_p d afm + d Z_p W^T, in place ----
+        afm2_dpairs<KD, NR>(sZ, sWT, sdafm, sS, P, lane);
         __syncwarp();
         // ---- d E_f = sum_{g != f} dP_{fg} * E_g  (lanes over k, registers; no read-modify-write through shared memory) ----
         for (int f = 0; f < F; f++) {
@@ -725,11 +735,11 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
   }
 }
 
-template <int KD, int NW, bool TRAIN>
+template <int KD, int NW, int NR, bool TRAIN>
 static int launch_afm2(const AfmArgs& a, cudaStream_t st) {
   const size_t smem = afm2_smem_floats(NW, a.F, KD, a.P) * sizeof(float);
   if (smem > 220 * 1024) return 1;
-  auto kern = afm2_kernel<KD, NW, TRAIN>;
+  auto kern = afm2_kernel<KD, NW, NR, TRAIN>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     set_error("afm2_kernel: cannot reserve %zu bytes of shared memory", smem);
     return HHFM_ERR_LAUNCH;
@@ -745,17 +755,34 @@ static int launch_afm2(const AfmArgs& a, cudaStream_t st) {
   return check_launch("afm2_kernel");
 }
 
+template <int KD, int NR, bool TRAIN>
+static int launch_afm2_warps(const AfmArgs& a, cudaStream_t st) {
+  if constexpr (KD >= 32) {
+    const int rc = launch_afm2<KD, 8, NR, TRAIN>(a, st);
+    if (rc != 1) return rc;
+  }
+  return launch_afm2<KD, 4, NR, TRAIN>(a, st);
+}
+
 // returns 1 when the shape is not covered (the caller then uses afm_kernel)
 template <bool TRAIN>
 static int dispatch_afm2(const AfmArgs& a, cudaStream_t st) {
   const char* e = getenv("HHFM_AFM_V1");           // 1 = force the first layout (A/B measurements, tests of both kernels)
   if (e && e[0] == '1') return 1;
   if (a.K != a.A) return 1;
-  int rc = 1;
-  if (a.K == 64) { rc = launch_afm2<64, 8, TRAIN>(a, st); if (rc == 1) rc = launch_afm2<64, 4, TRAIN>(a, st); }
-  else if (a.K == 32) { rc = launch_afm2<32, 8, TRAIN>(a, st); if (rc == 1) rc = launch_afm2<32, 4, TRAIN>(a, st); }
-  else if (a.K == 16) rc = launch_afm2<16, 4, TRAIN>(a, st);
-  return rc;
+  const int nr = (a.P + 15) / 16;                   // pairs per lane
+  if (nr > 3) return 1;
+#define HHFM_AFM2_CASE(KD_)                                                       \
+  if (a.K == KD_) {                                                               \
+    if (nr == 1) return launch_afm2_warps<KD_, 1, TRAIN>(a, st);                  \
+    if (nr == 2) return launch_afm2_warps<KD_, 2, TRAIN>(a, st);                  \
+    return launch_afm2_warps<KD_, 3, TRAIN>(a, st);                               \
+  }
+  HHFM_AFM2_CASE(64)
+  HHFM_AFM2_CASE(32)
+  HHFM_AFM2_CASE(16)
+#undef HHFM_AFM2_CASE
+  return 1;
 }
 
 template <int TK, int TA, int NW, bool TRAIN>

@@ -621,7 +621,7 @@ def _afm_weights(rng, M, K, A):
 
 
 @pytest.mark.parametrize("layout", ["pair-per-lane", "column-per-lane"])
-@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64), (45, 9, 32), (40, 11, 32)])
+@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64), (45, 9, 32), (40, 11, 32), (70, 8, 64), (37, 7, 16)])
 def test_afm_fused_pass_matches_oracle(cuda, B, F, K, layout, monkeypatch):
     """Both layouts of the fused kernel (afm.cu: afm2_kernel covers K == A in {16, 32, 64}; afm_kernel everything else)."""
     monkeypatch.setenv("HHFM_AFM_V1", "1" if layout == "column-per-lane" else "0")
@@ -653,8 +653,11 @@ def test_afm_fused_pass_matches_oracle(cuda, B, F, K, layout, monkeypatch):
     assert_close(gb.cpu().numpy(), g["feature_bias"].reshape(-1), what="afm gbias")
     assert_close(gb0.item(), g["bias"], what="afm gb0")
     assert_close(gW.cpu().numpy(), g["attention_W"], rtol=2e-5, what="afm gW")
-    assert_close(gba.cpu().numpy(), g["attention_b"].reshape(-1), rtol=2e-5, what="afm gb_att")
-    assert_close(gp.cpu().numpy(), g["attention_p"], rtol=2e-5, what="afm gp")
+    # d attention_b sums d s_p over the pairs, and the softmax makes those sum to zero per sample: what is left is
+    # cancellation noise with no scale of its own, so it is held to 1e-5 of the attention_W gradient's scale
+    floor = 1e-5 * float(np.abs(g["attention_W"]).max())
+    assert_close(gba.cpu().numpy(), g["attention_b"].reshape(-1), rtol=2e-5, atol=floor, what="afm gb_att")
+    assert_close(gp.cpu().numpy(), g["attention_p"], rtol=2e-5, atol=floor, what="afm gp")
     assert_close(gwp.cpu().numpy(), g["prediction"].reshape(-1), rtol=2e-5, what="afm gw_pred")
 
 
