@@ -11,6 +11,8 @@ reference (`_init_graph`) is replaced by device tensors and C-ABI kernel launche
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -750,13 +752,30 @@ class AFM(FM):
 
     def topk(self, A, tp):
         """AFM.topk (AFM.py:209-246) scores every item for each context row.  The reference restates `out` with an
-        un-normalised exp attention and drops the per-row constants, which is rank-equivalent to scoring the full model:
-        here every (row, item) pair goes through the forward kernel and the exact selector (lowest-index ties)."""
+        un-normalised exp attention and drops the per-row constants, which is rank-equivalent to scoring the full model.
+        Covered shapes (K == A in {16, 32, 64}) go through the item-separable scorer (csrc/afm_topn.cu: the context-only
+        pairs once per row, the F-1 item pairs per (row, item)); other shapes send every (row, item) pair through the
+        forward kernel.  Either way the exact selector (lowest-index ties) makes the lists."""
         A = np.asarray(A)
         A_dev, stride = self._topn.upload_rows(A, self._M)
         C_rows, F = A.shape
         N = self.n_item
+        K, Adim = int(self.hidden_factor[1]), int(self._A)
         out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        separable = bool(_lib.load().hhfm_afm_topn_supported(F, K, Adim)) and os.environ.get("HHFM_AFM_TOPN_SEPARABLE", "1") != "0"
+        w = self.weights
+        if separable:
+            chunk = max(1, min(65535, (1 << 26) // max(N, 1)))
+            stats = torch.empty(min(chunk, C_rows), 4, dtype=torch.float32, device=self.device)
+            for c0 in range(0, C_rows, chunk):
+                c1 = min(C_rows, c0 + chunk)
+                sc = torch.empty(c1 - c0, N, dtype=torch.float32, device=self.device)
+                _lib.call("hhfm_afm_topn_scores", ptr(A_dev[c0:c1]), stride, c1 - c0, F, 1, ptr(w["feature_embeddings"]),
+                          ptr(w["feature_bias"]), ptr(w["bias"]), ptr(w["attention_W"]), ptr(w["attention_b"]),
+                          ptr(w["attention_p"]), ptr(w["prediction"]), self._M, K, Adim, self.n_user, N, ptr(stats), ptr(sc),
+                          cur_stream())
+                _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
+            return out_ids.cpu().numpy()
         items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
         chunk = max(1, (1 << 22) // max(N, 1))
         for c0 in range(0, C_rows, chunk):

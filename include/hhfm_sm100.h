@@ -170,6 +170,18 @@ int hhfm_afm_fwd_bwd_sqloss_tc(const int32_t* idx, int64_t B, int64_t F, const f
                                const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
                                float* workspace, hhfm_stream_t stream);
 
+/* K2 full-catalog scorer (AFM.py:209-246; afm_topn.cu): scores [C, N] = the AFM forward of every context row with field
+ * `item_col` replaced by item n (table row item_base + n), n < N.  Only the F-1 pairs that contain the item are evaluated
+ * per (context, item); the context-only pairs are reduced once per context into stats [C, 4] (caller-owned scratch).
+ * rows [C, row_stride] int32 (C <= 65535 per call); the entry of column item_col is ignored.  Covered shapes:
+ * hhfm_afm_topn_supported(F, K, A) == 1 (K == A in {16, 32, 64}, 2 <= F <= 16); other shapes are scored through
+ * hhfm_afm_fwd on expanded rows.  Feed `scores` to hhfm_topn_select for the lists (lowest index first on ties). */
+int hhfm_afm_topn_supported(int64_t F, int64_t K, int64_t A);
+int hhfm_afm_topn_scores(const int32_t* rows, int64_t row_stride, int64_t C, int64_t F, int32_t item_col, const float* V,
+                         const float* bias, const float* b0, const float* W, const float* batt, const float* pvec,
+                         const float* wpred, int64_t M, int64_t K, int64_t A, int64_t item_base, int64_t N, float* stats,
+                         float* scores, hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K8  DeepFM (DFM.py:104-152): y1_f = feature_bias[x_f], y2 = 0.5((sum e)^2 - sum e^2), a relu MLP tower over the
  *     flattened embeddings, out = [y1 | y2 | H_L] . concat_projection + concat_bias;  loss = 0.5*sum(y-out)^2.

@@ -620,6 +620,29 @@ def _afm_weights(rng, M, K, A):
                 prediction=rng.normal(1, 0.1, (K, 1)).astype(np.float32))
 
 
+@pytest.mark.parametrize("C,N,F,K", [(7, 700, 10, 64), (3, 37, 6, 32), (5, 1100, 3, 16), (4, 513, 2, 64), (2, 90, 12, 32)])
+def test_afm_item_separable_scorer_matches_forward(cuda, C, N, F, K):
+    """hhfm_afm_topn_scores (afm_topn.cu): context-only pairs once per row + the F-1 item pairs per (row, item) must equal the
+    op-by-op AFM forward (AFM.py:103-148) of every expanded row."""
+    lib, ptr, st = _lib_ptr()
+    rng = np.random.default_rng(C * 1000 + N + F + K)
+    n_user = 23
+    M = n_user + N + 40
+    w = _afm_weights(rng, M, K, K)
+    rows = rng.integers(n_user + N, M, (C, F)); rows[:, 0] = rng.integers(0, n_user, C); rows[:, 1] = -7      # column 1 is ignored
+    X = np.repeat(rows[:, None, :], N, axis=1); X[:, :, 1] = n_user + np.arange(N)[None, :]
+    ref = O.afm_forward(X.reshape(-1, F), w)[0].reshape(C, N)
+    assert lib.load().hhfm_afm_topn_supported(F, K, K) == 1
+    stats = torch.empty(C, 4, device=cuda); sc = torch.full((C, N), float("nan"), device=cuda)
+    stride = F + 2
+    rows_dev = torch.full((C, stride), -1, dtype=torch.int32, device=cuda); rows_dev[:, :F] = torch.from_numpy(rows.astype(np.int32)).to(cuda)
+    lib.call("hhfm_afm_topn_scores", ptr(rows_dev), stride, C, F, 1, ptr(dev(w["feature_embeddings"], cuda)), ptr(dev(w["feature_bias"].reshape(-1), cuda)),
+             ptr(dev(np.array([w["bias"]], np.float32), cuda)), ptr(dev(w["attention_W"], cuda)), ptr(dev(w["attention_b"].reshape(-1), cuda)),
+             ptr(dev(w["attention_p"], cuda)), ptr(dev(w["prediction"].reshape(-1), cuda)), M, K, K, n_user, N, ptr(stats), ptr(sc), st())
+    assert_close(sc.cpu().numpy(), ref, what="afm separable scores")
+    assert lib.load().hhfm_afm_topn_supported(F, 128, 128) == 0 and lib.load().hhfm_afm_topn_supported(F, 64, 32) == 0
+
+
 @pytest.mark.parametrize("layout", ["pair-per-lane", "column-per-lane"])
 @pytest.mark.parametrize("B,F,K", [(64, 10, 64), (1001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64), (45, 9, 32), (40, 11, 32), (70, 8, 64), (37, 7, 16)])
 def test_afm_fused_pass_matches_oracle(cuda, B, F, K, layout, monkeypatch):

@@ -231,7 +231,7 @@ def test_autograd_functions_match_torch_reference(cuda):
     assert_close(c.grad.item(), cr.grad.item(), what="autograd gb0")
 
 
-def test_afm_steps_and_topk_match_oracle(cuda):
+def test_afm_steps_and_topk_match_oracle(cuda, monkeypatch):
     """AFM.partial_fit (AFM.py:205-208) teacher-forced against the oracle + TF1 Adagrad; AFM.topk rank-equivalence."""
     from conftest import assert_update_close
     from hhfm_b200.models import AFM
@@ -272,7 +272,11 @@ def test_afm_steps_and_topk_match_oracle(cuda):
                                                model.dropout_keep: [1.0, 1.0], model.train_phase: False})
     assert_close(out[:, 0], O.afm_forward(X[:300], w)[0], what="afm predict")
     A = X[:40]
-    ids = model.topk(A, 20)
+    ids = model.topk(A, 20)                                   # item-separable scorer (csrc/afm_topn.cu)
+    monkeypatch.setenv("HHFM_AFM_TOPN_SEPARABLE", "0")
+    ids_full = model.topk(A, 20)                              # every (row, item) pair through the forward kernel
+    monkeypatch.delenv("HHFM_AFM_TOPN_SEPARABLE")
+    assert (ids == ids_full).mean() > 0.99
     ref = O.afm_topk_scores(A, w, n_user, n_item)
     want = O.topk_lowest_index(ref, 20)
     for r in range(len(A)):
