@@ -30,6 +30,7 @@ SIGNATURES = {
     "hhfm_dfm_fwd": [vp, i64, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp],
     "hhfm_dfm_fwd_bwd_sqloss": [vp, i64, i64, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32,
                                 vp],
+    "hhfm_dfm_topn_scores": [vp, i64, i64, i64, i32, vp, vp, i64, i64, vp, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_gemm_tn_tf32x3": [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp, vp],
     "hhfm_afm_topn_supported": [i64, i64, i64],
     "hhfm_afm_topn_scores": [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp],
@@ -76,6 +77,7 @@ INT64_FUNCS = {
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
     "hhfm_workspace_bytes_afm": [i64, i64, i64, i64],
+    "hhfm_workspace_bytes_dfm_topn": [i64, i64, i64, i64, i32, vp],
     "hhfm_cars2_param_count": [i64, i64, i64, i64, i64, i64],
     "hhfm_workspace_bytes_cars2": [i64, i64, i64],
     "hhfm_dfm_param_count": [i64, i64, i32, vp],

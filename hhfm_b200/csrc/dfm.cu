@@ -19,6 +19,8 @@
 //     bias_0 (d1) | ... | bias_{L-1} (d_L) | concat_bias (1) ]
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "dfm_tc.cuh"
 
@@ -451,9 +453,10 @@ static int dfm_layout(int64_t B, int64_t F, int64_t K, int32_t L, const int32_t*
   return HHFM_OK;
 }
 
+// first > 0: H_first is already in the workspace (item-separable evaluator)
 static int dfm_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
-                       const DfmLayout& lo, float* ws, cudaStream_t st) {
-  for (int i = 0; i < lo.L; i++) {
+                       const DfmLayout& lo, float* ws, cudaStream_t st, int first = 0) {
+  for (int i = first; i < lo.L; i++) {
     GemmArgs g{};
     g.M = (int)B; g.N = lo.d[i + 1]; g.Kd = lo.d[i];
     g.B = params + lo.w_off[i]; g.ldb = lo.d[i + 1];
@@ -499,16 +502,19 @@ static bool dfm_use_tc(int64_t K) {
   return K % 16 == 0;                          // the scatter epilogue maps 16-column chunks to one embedding row
 }
 
-static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t) {
+// forward_from > 0: inference that enters at layer `forward_from` (the item-separable evaluator): no input forms below it
+// and no transposed forms at all
+static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t, int forward_from = 0) {
   auto r4 = [](int64_t x) { return (x + 3) / 4 * 4; };
   t.ldB = (B + 31) / 32 * 32;          // the transposed forms are k-blocked panels of 32 samples
   int64_t o = 0;
   for (int l = 0; l <= lo.L; l++) {
     t.ldx[l] = r4(lo.d[l]);
-    t.x[l] = o; o += B * t.ldx[l];
-    t.xlo[l] = o; o += B * t.ldx[l];
-    t.xt[l] = o; o += (int64_t)lo.d[l] * t.ldB;
-    t.xtlo[l] = o; o += (int64_t)lo.d[l] * t.ldB;
+    const bool have = l >= forward_from;
+    t.x[l] = o; o += have ? B * t.ldx[l] : 0;
+    t.xlo[l] = o; o += have ? B * t.ldx[l] : 0;
+    t.xt[l] = o; o += forward_from ? 0 : (int64_t)lo.d[l] * t.ldB;
+    t.xtlo[l] = o; o += forward_from ? 0 : (int64_t)lo.d[l] * t.ldB;
   }
   for (int i = 0; i < lo.L; i++) {
     t.ldp[i] = (int)r4(lo.d[i + 1]);
@@ -523,17 +529,22 @@ static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t) {
   t.total = t.scratch + t.scratch_floats;
 }
 
+// first > 0 (inference only): X_first is already in the workspace (item-separable evaluator); its lo half is made here
 static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
-                          const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st) {
+                          const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st, int first = 0) {
   int rc;
-  for (int i = 0; i < lo.L; i++)
+  for (int i = first; i < lo.L; i++)
     if ((rc = tf_prep_weight(params + lo.w_off[i], lo.d[i], lo.d[i + 1], ws + t.w[i], ws + t.wlo[i], t.ldp[i], ws + t.wt[i],
                              ws + t.wtlo[i], t.ldt[i], st)))
       return rc;
-  if ((rc = tf_gather_split_transpose(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
-                                      train ? ws + t.xtlo[0] : nullptr, st)))
-    return rc;
-  for (int i = 0; i < lo.L; i++) {
+  if (first == 0) {
+    if ((rc = tf_gather_split_transpose(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
+                                        train ? ws + t.xtlo[0] : nullptr, st)))
+      return rc;
+  } else if (first < lo.L) {
+    if ((rc = tf_split_transpose(ws + t.x[first], B, lo.d[first], t.ldx[first], ws + t.xlo[first], nullptr, nullptr, st))) return rc;
+  }
+  for (int i = first; i < lo.L; i++) {
     TfGemm g{};
     g.A = ws + t.x[i]; g.A_lo = ws + t.xlo[i]; g.lda = t.ldx[i];
     g.B = ws + t.wt[i]; g.B_lo = ws + t.wtlo[i]; g.ldb = t.ldt[i];
@@ -548,6 +559,130 @@ static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float*
     }
   }
   return HHFM_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Item-separable full-catalog evaluator (DFM.py:219-231).  A context row with field item_col replaced by item n:
+//   first hidden layer   Z1[c, n] = (b1 + sum_{f != item} E_cf W1_f) + E_n W1_item = U[c] + T[n]   (W1_f = rows f*K..(f+1)*K of W1)
+//   first order          sum_{f != item} w[x_cf] proj[f]  +  w[n] proj[item_col]
+//   second order         0.5 ((S_c + v_n)^2 - (Q_c + v_n^2)) . proj2,  S_c / Q_c = sums of E_cf / E_cf^2 over the context fields
+// so the [F*K x d1] product (61 % of the tower's flops at 640-150-200-150), the 2.5 KB row gather and its tf32 split are
+// paid once per context and once per item instead of once per (context, item).  Rows are ordered s = c * N + n.
+// --------------------------------------------------------------------------------------------------------------
+struct DfmTopnArgs {
+  const int32_t* rows;
+  int64_t row_stride;
+  int C, F, K, item_col, d1;
+  int64_t ld1;
+  const float *V, *fbias, *W1, *b1, *proj;
+  int64_t item_base, N;
+  float *U, *T, *SQ, *fo;      // [C, ld1], [N, ld1], [C, 2K], [C]
+};
+
+__global__ void __launch_bounds__(256) dfm_topn_ctx_kernel(const DfmTopnArgs a) {
+  extern __shared__ float sE[];            // [F][K], the item field zeroed
+  __shared__ float scratch[32];
+  const int c = blockIdx.x, F = a.F, K = a.K;
+  const int32_t* rec = a.rows + (int64_t)c * a.row_stride;
+  for (int i = threadIdx.x; i < F * K; i += blockDim.x) {
+    const int f = i / K, k = i % K;
+    sE[i] = (f == a.item_col) ? 0.f : __ldg(a.V + (size_t)__ldg(rec + f) * K + k);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float S = 0.f, Q = 0.f;
+    for (int f = 0; f < F; f++) { const float e = sE[f * K + k]; S += e; Q = fmaf(e, e, Q); }
+    a.SQ[(int64_t)c * 2 * K + k] = S;
+    a.SQ[(int64_t)c * 2 * K + K + k] = Q;
+  }
+  float fo = 0.f;
+  if ((int)threadIdx.x < F && (int)threadIdx.x != a.item_col) fo = __ldg(a.fbias + __ldg(rec + threadIdx.x)) * __ldg(a.proj + threadIdx.x);
+  fo = block_sum(fo, scratch);
+  if (threadIdx.x == 0) a.fo[c] = fo;
+  for (int j = threadIdx.x; j < a.ld1; j += blockDim.x) {
+    float acc = 0.f;
+    if (j < a.d1) {
+      for (int f = 0; f < F; f++) {
+        if (f == a.item_col) continue;
+        const float* w = a.W1 + (size_t)f * K * a.d1 + j;
+        for (int k = 0; k < K; k++) acc = fmaf(sE[f * K + k], __ldg(w + (size_t)k * a.d1), acc);
+      }
+      acc += __ldg(a.b1 + j);
+    }
+    a.U[(int64_t)c * a.ld1 + j] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) dfm_topn_item_kernel(const DfmTopnArgs a) {
+  extern __shared__ float sV[];            // [8][K]
+  const int K = a.K;
+  const int64_t n0 = (int64_t)blockIdx.x * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    const int64_t n = n0 + i / K;
+    sV[i] = (n < a.N) ? __ldg(a.V + (size_t)(a.item_base + n) * K + i % K) : 0.f;
+  }
+  __syncthreads();
+  const float* W = a.W1 + (size_t)a.item_col * K * a.d1;
+  for (int j = threadIdx.x; j < a.ld1; j += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (j < a.d1)
+      for (int k = 0; k < K; k++) {
+        const float w = __ldg(W + (size_t)k * a.d1 + j);
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = fmaf(sV[r * K + k], w, acc[r]);
+      }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (n0 + r < a.N) a.T[(n0 + r) * a.ld1 + j] = acc[r];
+  }
+}
+
+// X1[c*N + n, :] = relu(U[c] + T[n]) (padding columns stay 0: U and T are 0 there)
+__global__ void __launch_bounds__(256) dfm_topn_h1_kernel(const float* __restrict__ U, const float* __restrict__ T, int64_t C, int64_t N,
+                                                          int64_t ld1, float* __restrict__ X1, int64_t ldx) {
+  const int64_t v4 = ld1 >> 2;
+  const int64_t total = C * N * v4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / v4, j = i % v4;
+    const int64_t c = s / N, n = s % N;
+    const float4 u = __ldg(reinterpret_cast<const float4*>(U + c * ld1) + j);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(T + n * ld1) + j);
+    reinterpret_cast<float4*>(X1 + s * ldx)[j] =
+        make_float4(fmaxf(u.x + t.x, 0.f), fmaxf(u.y + t.y, 0.f), fmaxf(u.z + t.z, 0.f), fmaxf(u.w + t.w, 0.f));
+  }
+}
+
+// one warp per (context, item): first order + second order + last hidden layer, through concat_projection (DFM.py:138-143)
+__global__ void __launch_bounds__(256) dfm_topn_head_kernel(const DfmTopnArgs a, const float* __restrict__ H, int64_t ldh, int D,
+                                                            const float* __restrict__ cbias, float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31, K = a.K;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t total = (int64_t)a.C * a.N;
+  const float cb = __ldg(cbias);
+  const float pitem = __ldg(a.proj + a.item_col);
+  const float* p2 = a.proj + a.F;
+  const float* p3 = a.proj + a.F + K;
+  for (int64_t s = warp_g; s < total; s += n_warps) {
+    const int64_t c = s / a.N, n = s % a.N;
+    const float* v = a.V + (size_t)(a.item_base + n) * K;
+    const float* S = a.SQ + c * 2 * K;
+    float part = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float e = __ldg(v + k);
+      const float sv = __ldg(S + k) + e, q = fmaf(e, e, __ldg(S + K + k));
+      part = fmaf(0.5f * (sv * sv - q), __ldg(p2 + k), part);
+    }
+    const float* hrow = H + s * ldh;
+    for (int j = lane; j < D; j += 32) part = fmaf(hrow[j], __ldg(p3 + j), part);
+    if (lane == 0) part += __ldg(a.fo + c) + __ldg(a.fbias + a.item_base + n) * pitem;
+    const float out = warp_sum(part) + cb;
+    if (lane == 0) scores[s] = out;
+  }
+}
+
+static int64_t dfm_topn_side_floats(int64_t C, int64_t N, int64_t K, int64_t ld1) {
+  return C * ld1 + N * ld1 + C * 2 * K + (C + 3) / 4 * 4;
 }
 
 }  // namespace hhfm
@@ -706,4 +841,72 @@ extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
     if (rc != HHFM_OK) return rc;
   }
   return HHFM_OK;
+}
+
+extern "C" int64_t hhfm_workspace_bytes_dfm_topn(int64_t C, int64_t N, int64_t F, int64_t K, int32_t n_layers,
+                                                 const int32_t* layer_sizes) {
+  DfmLayout lo;
+  if (C < 0 || N < 1 || dfm_layout(C * N, F, K, n_layers, layer_sizes, lo) != HHFM_OK) return -1;
+  const int64_t side = dfm_topn_side_floats(C, N, K, lo.ld[1]);
+  if (dfm_use_tc(K)) {
+    DfmTcLayout t;
+    dfm_tc_layout(C * N, lo, t, 1);
+    return (side + t.total) * (int64_t)sizeof(float);
+  }
+  return (side + lo.ws_floats) * (int64_t)sizeof(float);
+}
+
+extern "C" int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int64_t C, int64_t F, int32_t item_col,
+                                    const float* V, const float* feature_bias, int64_t M, int64_t K, const float* params,
+                                    int32_t n_layers, const int32_t* layer_sizes, int64_t item_base, int64_t N,
+                                    float* workspace, float* scores, hhfm_stream_t stream) {
+  HHFM_REQUIRE(rows && V && feature_bias && params && workspace && scores, "dfm_topn_scores: NULL argument");
+  HHFM_REQUIRE(C >= 0 && N >= 1 && C * N < (1ll << 31) && item_base >= 0 && item_base + N <= M, "dfm_topn_scores: bad C / N / item_base");
+  HHFM_REQUIRE(item_col >= 0 && item_col < F && row_stride >= F, "dfm_topn_scores: bad item_col / row_stride");
+  HHFM_REQUIRE(((uintptr_t)workspace & 15) == 0, "dfm_topn_scores: workspace must be 16-byte aligned");
+  if (C == 0) return HHFM_OK;
+  const int64_t B = C * N;
+  DfmLayout lo;
+  int rc = dfm_layout(B, F, K, n_layers, layer_sizes, lo);
+  if (rc != HHFM_OK) return rc;
+  HHFM_REQUIRE(F * K * sizeof(float) <= 200 * 1024, "dfm_topn_scores: F*K too large for the context kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ld1 = lo.ld[1];
+  DfmTopnArgs a{};
+  a.rows = rows; a.row_stride = row_stride; a.C = (int)C; a.F = (int)F; a.K = (int)K; a.item_col = item_col; a.d1 = lo.d[1]; a.ld1 = ld1;
+  a.V = V; a.fbias = feature_bias; a.W1 = params + lo.w_off[0]; a.b1 = params + lo.b_off[0]; a.proj = params + lo.proj_off;
+  a.item_base = item_base; a.N = N;
+  a.U = workspace; a.T = a.U + C * ld1; a.SQ = a.T + N * ld1; a.fo = a.SQ + C * 2 * K;
+  float* main_ws = workspace + dfm_topn_side_floats(C, N, K, ld1);
+  {
+    const size_t smem = (size_t)F * K * sizeof(float);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(dfm_topn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_error("dfm_topn_ctx_kernel: cannot reserve %zu bytes of shared memory", smem);
+      return HHFM_ERR_LAUNCH;
+    }
+    dfm_topn_ctx_kernel<<<(unsigned)C, 256, smem, st>>>(a);
+    if ((rc = check_launch("dfm_topn_ctx_kernel"))) return rc;
+    dfm_topn_item_kernel<<<(unsigned)((N + 7) / 8), 256, 8 * K * sizeof(float), st>>>(a);
+    if ((rc = check_launch("dfm_topn_item_kernel"))) return rc;
+  }
+  const float* H;
+  int64_t ldh;
+  const int h1_grid = (int)std::min<int64_t>((B * (ld1 >> 2) + 255) / 256, (int64_t)sm_count() * 16);
+  if (dfm_use_tc(K)) {
+    DfmTcLayout t;
+    dfm_tc_layout(B, lo, t, 1);
+    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + t.x[1], t.ldx[1]);
+    if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
+    if ((rc = dfm_tc_forward(nullptr, B, F, V, K, params, lo, t, main_ws, false, st, 1))) return rc;
+    H = main_ws + t.x[lo.L]; ldh = t.ldx[lo.L];
+  } else {
+    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + lo.h_off[1], lo.ld[1]);
+    if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
+    if ((rc = dfm_forward(nullptr, B, F, V, K, params, lo, main_ws, st, 1))) return rc;
+    H = main_ws + lo.h_off[lo.L]; ldh = lo.ld[lo.L];
+  }
+  const int head_grid = (int)std::min<int64_t>((B + 7) / 8, (int64_t)sm_count() * 8);
+  dfm_topn_head_kernel<<<head_grid, 256, 0, st>>>(a, H, ldh, lo.d[lo.L], params + lo.cbias_off, scores);
+  return check_launch("dfm_topn_head_kernel");
 }

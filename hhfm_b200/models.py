@@ -922,14 +922,31 @@ class DeepFM(_Base):
         self._enqueue_loss(lam > 0, 0.5 * lam)
 
     def topk(self, A, tp):
-        """DFM.py:220-231: every (row, item) pair through the forward graph, then top_k (lowest index first on ties)."""
+        """DFM.py:220-231: every (row, item) pair scored by the forward graph, then top_k (lowest index first on ties).  The
+        item-separable evaluator (hhfm_dfm_topn_scores) pays the first hidden layer once per row and once per item;
+        HHFM_DFM_TOPN_SEPARABLE=0 sends every expanded row through hhfm_dfm_fwd instead (A/B runs, tests)."""
         A = np.asarray(A)
         A_dev, stride = self._topn.upload_rows(A, self._M)
         C_rows, F = A.shape
         N = self.n_item
         out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
-        items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
         chunk = max(1, (1 << 21) // max(N, 1))
+        if os.environ.get("HHFM_DFM_TOPN_SEPARABLE", "1") != "0":
+            L = len(self.deep_layers)
+            need = int(_lib.load().hhfm_workspace_bytes_dfm_topn(min(chunk, C_rows), N, F, self._K, L, self._sizes.ctypes.data)) // 4
+            if need < 0:
+                raise _lib.HhfmError("hhfm_workspace_bytes_dfm_topn: bad shape")
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(max(need, 1), dtype=torch.float32, device=self.device)
+            for c0 in range(0, C_rows, chunk):
+                c1 = min(C_rows, c0 + chunk)
+                sc = torch.empty(c1 - c0, N, dtype=torch.float32, device=self.device)
+                _lib.call("hhfm_dfm_topn_scores", ptr(A_dev[c0:c1]), stride, c1 - c0, F, 1, ptr(self.weights["feature_embeddings"]),
+                          ptr(self.weights["feature_bias"]), self._M, self._K, ptr(self._params), L, self._sizes.ctypes.data,
+                          self.n_user, N, ptr(self._ws), ptr(sc), cur_stream())
+                _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
+            return out_ids.cpu().numpy()
+        items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
         for c0 in range(0, C_rows, chunk):
             c1 = min(C_rows, c0 + chunk)
             rows = A_dev[c0:c1, :F].unsqueeze(1).repeat(1, N, 1)

@@ -207,6 +207,19 @@ int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
                             float* gparams, float* loss_partials, const int32_t* hot_slot, float* ghot,
                             float* ghot_bias, int32_t n_rep, int32_t n_hot, hhfm_stream_t stream);
 
+/* K8 full-catalog scorer (DFM.py:219-231): scores [C, N] = the DeepFM forward of every context row with field item_col
+ * replaced by item n (table row item_base + n).  The first hidden layer is item-separable, relu((b1 + sum_{f != item}
+ * E_f W1_f) + E_n W1_item): its context part is computed once per row and its item part once per item; the remaining layers
+ * and the projection run per (row, item) pair (rows s = c*N + n) through the same GEMMs as hhfm_dfm_fwd.  rows [C, row_stride]
+ * int32 (column item_col ignored); C*N < 2^31; workspace: hhfm_workspace_bytes_dfm_topn(C, N, ...) bytes, 16-byte aligned.
+ * Feed `scores` to hhfm_topn_select for the lists. */
+int64_t hhfm_workspace_bytes_dfm_topn(int64_t C, int64_t N, int64_t F, int64_t K, int32_t n_layers,
+                                      const int32_t* layer_sizes);
+int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int64_t C, int64_t F, int32_t item_col, const float* V,
+                         const float* feature_bias, int64_t M, int64_t K, const float* params, int32_t n_layers,
+                         const int32_t* layer_sizes, int64_t item_base, int64_t N, float* workspace, float* scores,
+                         hhfm_stream_t stream);
+
 /* fp32-accurate GEMM on the tensor cores (the building block of the DeepFM tower, dfm_tc.cu): C[M,N] = A[M,K] . B[N,K]^T,
  * row-major operands with K contiguous, 3xTF32 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi) with fp32 accumulation in TMEM.
  * lda / ldb / ldc are multiples of 4 floats, pointers 16-byte aligned; workspace: (M*lda + N*ldb) floats. */

@@ -289,7 +289,7 @@ def test_afm_steps_and_topk_match_oracle(cuda, monkeypatch):
             assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
 
 
-def test_dfm_steps_and_topk_match_oracle(cuda):
+def test_dfm_steps_and_topk_match_oracle(cuda, monkeypatch):
     """DeepFM.partial_fit (DFM.py:216-219) teacher-forced against the oracle + TF1 Adagrad; DeepFM.topk (DFM.py:220-231)."""
     from conftest import assert_update_close
     from hhfm_b200.models import DeepFM
@@ -339,16 +339,32 @@ def test_dfm_steps_and_topk_match_oracle(cuda):
     out = model.sess.run(model.out, feed_dict={model.feat_index: X[:300], model.label: [[1]] * 300})
     assert_close(out[:, 0], O.dfm_forward(X[:300], w)[0], what="dfm predict")
     A = X[:40]
-    ids = model.topk(A, 20)
     rows = np.repeat(A[:, None, :], n_item, axis=1); rows[:, :, 1] = n_user + np.arange(n_item)[None, :]
     ref = O.dfm_forward(rows.reshape(-1, F), w)[0].reshape(len(A), n_item)
     want = O.topk_lowest_index(ref, 20)
-    for r in range(len(A)):
-        if (ids[r] == want[r]).all():
-            continue
-        tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
-        for a_, b_ in zip(ids[r], want[r]):
-            assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
+    # the item-separable evaluator's scores against the op-by-op forward of every expanded row, on both GEMM paths
+    import torch
+    from hhfm_b200 import _lib
+    from hhfm_b200.engine import cur_stream, ptr
+    for tc in ("1", "0"):
+        monkeypatch.setenv("HHFM_DFM_TC", tc)
+        A_dev, stride = model._topn.upload_rows(A, model._M)
+        need = int(_lib.load().hhfm_workspace_bytes_dfm_topn(len(A), n_item, F, K, len(layers), model._sizes.ctypes.data)) // 4
+        ws = torch.empty(need, device=cuda); sc = torch.full((len(A), n_item), float("nan"), device=cuda)
+        _lib.call("hhfm_dfm_topn_scores", ptr(A_dev), stride, len(A), F, 1, ptr(model.weights["feature_embeddings"]),
+                  ptr(model.weights["feature_bias"]), model._M, K, ptr(model._params), len(layers), model._sizes.ctypes.data,
+                  n_user, n_item, ptr(ws), ptr(sc), cur_stream())
+        assert_close(sc.cpu().numpy(), ref, rtol=2e-5, what="dfm separable scores (HHFM_DFM_TC=%s)" % tc)
+    monkeypatch.delenv("HHFM_DFM_TC")
+    for sep in ("1", "0"):          # separable evaluator / every expanded row through hhfm_dfm_fwd
+        monkeypatch.setenv("HHFM_DFM_TOPN_SEPARABLE", sep)
+        ids = model.topk(A, 20)
+        for r in range(len(A)):
+            if (ids[r] == want[r]).all():
+                continue
+            tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
+            for a_, b_ in zip(ids[r], want[r]):
+                assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
 
 
 def _cars2_weights(rng, n_ui, M, D):
