@@ -2,13 +2,16 @@
 // Packers replace the numpy slicing that builds `feed_dict` batches (FM.py:251-256, OurModel7.py:373-385):
 // id columns are narrowed to int32 and laid out as 16-byte aligned per-sample records in (pinned) host
 // memory, ready for one cudaMemcpyAsync.  Plain std::thread fan-out; no device work here.
+#include <immintrin.h>
 #include <pthread.h>
 
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -174,32 +177,89 @@ __global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t* __restri
 }
 
 template <typename D>
-static inline void pack_row_block(const hhfm_pack_part* parts, int n_parts, int64_t r0, int64_t r1, D* dst, int64_t stride,
-                                  int64_t width, int64_t id_limit, std::atomic<int64_t>& bad) {
+static inline void pack_row_block_scalar(const hhfm_pack_part* parts, int n_parts, int64_t r0, int64_t r1, D* dst, int64_t stride,
+                                         int64_t width, int64_t id_limit, std::atomic<int64_t>& bad) {
   const D pad = (D)-1;          // int32: -1, uint16: 0xFFFF
+  const uint64_t lim = (uint64_t)id_limit;
   for (int64_t r = r0; r < r1; r++) {
     D* d = dst + r * stride;
+    uint64_t viol = 0;          // branch-free range check: a negative id is a huge unsigned value
     for (int p = 0; p < n_parts; p++) {
       const hhfm_pack_part& pt = parts[p];
       if (pt.elem_bytes == 8) {
         const int64_t* s = reinterpret_cast<const int64_t*>(pt.data) + r * pt.row_stride;
         for (int64_t c = 0; c < pt.cols; c++) {
-          const int64_t v = s[c];
-          if (v < 0 || v >= id_limit) bad.store(r);
+          const uint64_t v = (uint64_t)s[c];
+          viol |= (uint64_t)(v >= lim);
           d[c] = (D)v;
         }
       } else {
         const int32_t* s = reinterpret_cast<const int32_t*>(pt.data) + r * pt.row_stride;
         for (int64_t c = 0; c < pt.cols; c++) {
-          const int64_t v = s[c];
-          if (v < 0 || v >= id_limit) bad.store(r);
+          const uint64_t v = (uint64_t)(int64_t)s[c];
+          viol |= (uint64_t)(v >= lim);
           d[c] = (D)v;
         }
       }
       d += pt.cols;
     }
+    if (viol) bad.store(r);
     for (int64_t c = width; c < stride; c++) dst[r * stride + c] = pad;
   }
+}
+
+// int64 ids -> 16-bit wire records, 8 ids per instruction (vpmovqw) with masked tails.  Alone, 16 threads on the B200 box pack
+// 168 MB of ids in 1.6 ms (scalar 2.1 ms, a read-only sweep 1.5 ms); inside partial_fit, where the H2D DMA shares the host
+// memory, both versions end at the same 3.5 ms per 2^20-positive step (profiles/r1_epoch_timing.md): the step is bound by
+// host memory traffic (int64 ids in, wire records out, DMA read), not by the packing arithmetic.
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+static void pack_row_block_u16_avx512(const hhfm_pack_part* parts, int n_parts, int64_t r0, int64_t r1, uint16_t* dst,
+                                      int64_t stride, int64_t width, int64_t id_limit, std::atomic<int64_t>& bad) {
+  const __m512i lim = _mm512_set1_epi64(id_limit);
+  for (int64_t r = r0; r < r1; r++) {
+    uint16_t* d = dst + r * stride;
+    __mmask8 viol = 0;
+    for (int p = 0; p < n_parts; p++) {
+      const hhfm_pack_part& pt = parts[p];
+      const int64_t* s = reinterpret_cast<const int64_t*>(pt.data) + r * pt.row_stride;
+      int64_t c = 0;
+      for (; c + 8 <= pt.cols; c += 8) {
+        const __m512i v = _mm512_loadu_si512(s + c);
+        viol |= _mm512_cmpge_epu64_mask(v, lim);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(d + c), _mm512_cvtepi64_epi16(v));
+      }
+      if (c < pt.cols) {
+        const __mmask8 m = (__mmask8)((1u << (pt.cols - c)) - 1);
+        const __m512i v = _mm512_maskz_loadu_epi64(m, s + c);
+        viol |= _mm512_cmpge_epu64_mask(v, lim);           // masked-off lanes are 0: in range
+        _mm512_mask_cvtepi64_storeu_epi16(d + c, m, v);
+      }
+      d += pt.cols;
+    }
+    if (viol) bad.store(r);
+    for (int64_t c = width; c < stride; c++) dst[r * stride + c] = 0xFFFF;
+  }
+}
+
+static bool cpu_has_avx512() {
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+  if (!ok) return false;
+  const char* e = getenv("HHFM_PACK_SIMD");          // 0 = scalar packer (A/B measurements)
+  return !(e && e[0] == '0');
+}
+
+template <typename D>
+static inline void pack_row_block(const hhfm_pack_part* parts, int n_parts, int64_t r0, int64_t r1, D* dst, int64_t stride,
+                                  int64_t width, int64_t id_limit, std::atomic<int64_t>& bad) {
+  if (sizeof(D) == 2 && cpu_has_avx512()) {
+    bool all64 = true;
+    for (int p = 0; p < n_parts; p++) all64 = all64 && parts[p].elem_bytes == 8;
+    if (all64) {
+      pack_row_block_u16_avx512(parts, n_parts, r0, r1, reinterpret_cast<uint16_t*>(dst), stride, width, id_limit, bad);
+      return;
+    }
+  }
+  pack_row_block_scalar<D>(parts, n_parts, r0, r1, dst, stride, width, id_limit, bad);
 }
 
 }  // namespace hhfm
@@ -278,23 +338,37 @@ extern "C" int hhfm_pack_upload_records(const hhfm_pack_part* parts, int32_t n_p
   const int64_t chunk = (rows + n_chunks - 1) / n_chunks;
   std::atomic<int64_t> bad{-1};
   const size_t esz = narrow ? 2 : 4;
-  for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
-    const int64_t c1 = std::min(rows, c0 + chunk);
-    const int64_t per = (c1 - c0 + nt - 1) / nt;
-    const std::function<void(int)> job = [&](int w) {
+  n_chunks = (rows + chunk - 1) / chunk;
+  // ONE parallel region for the whole batch: every worker packs its slice of chunk 0, 1, ... without a barrier in between,
+  // and whichever worker completes a chunk queues that chunk's H2D copy (waking the pool once per chunk cost as much as
+  // packing the chunk).  The copies all go to `stream`; their order among themselves does not matter.
+  int device = 0;
+  cudaGetDevice(&device);
+  std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_chunks]);
+  for (int64_t i = 0; i < n_chunks; i++) done[i].store(0);
+  std::atomic<int> copy_failed{0};
+  const std::function<void(int)> job = [&](int w) {
+    bool device_set = false;
+    for (int64_t ci = 0; ci < n_chunks; ci++) {
+      const int64_t c0 = ci * chunk, c1 = std::min(rows, c0 + chunk);
+      const int64_t per = (c1 - c0 + nt - 1) / nt;
       const int64_t a = c0 + (int64_t)w * per, b = std::min(c1, a + per);
-      if (a >= b) return;
-      if (narrow) pack_row_block<uint16_t>(parts, n_parts, a, b, reinterpret_cast<uint16_t*>(host_staging), stride, width, id_limit, bad);
-      else pack_row_block<int32_t>(parts, n_parts, a, b, reinterpret_cast<int32_t*>(host_staging), stride, width, id_limit, bad);
-    };
-    pool->run(job);
-    if (bad.load() >= 0) break;
-    const size_t off = (size_t)c0 * stride * esz, bytes = (size_t)(c1 - c0) * stride * esz;
-    void* dst = narrow ? (void*)((char*)dev_staging + off) : (void*)((char*)dev_records + off);
-    if (cudaMemcpyAsync(dst, (const char*)host_staging + off, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-      set_error("pack_upload_records: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return HHFM_ERR_LAUNCH;
+      if (a < b) {
+        if (narrow) pack_row_block<uint16_t>(parts, n_parts, a, b, reinterpret_cast<uint16_t*>(host_staging), stride, width, id_limit, bad);
+        else pack_row_block<int32_t>(parts, n_parts, a, b, reinterpret_cast<int32_t*>(host_staging), stride, width, id_limit, bad);
+      }
+      if (done[ci].fetch_add(1, std::memory_order_acq_rel) + 1 != nt) continue;
+      if (bad.load() >= 0 || copy_failed.load()) continue;
+      if (!device_set) { cudaSetDevice(device); device_set = true; }
+      const size_t off = (size_t)c0 * stride * esz, bytes = (size_t)(c1 - c0) * stride * esz;
+      void* dst = narrow ? (void*)((char*)dev_staging + off) : (void*)((char*)dev_records + off);
+      if (cudaMemcpyAsync(dst, (const char*)host_staging + off, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) copy_failed.store(1);
     }
+  };
+  pool->run(job);
+  if (copy_failed.load()) {
+    set_error("pack_upload_records: cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return HHFM_ERR_LAUNCH;
   }
   if (bad.load() >= 0) {
     set_error("pack_ids: id out of range [0,%lld) in row %lld", (long long)id_limit, (long long)bad.load());

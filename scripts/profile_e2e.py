@@ -32,3 +32,7 @@ print("h2d ms", t(lambda: stg.upload(host.numel())), "MB", host.numel() * 4 / 1e
 idx = stg.upload(host.numel()).view(n, stride)
 print("fit_device+loss ms", t(lambda: (m.fit_device(idx, 8, 0, 10), m._read_loss())))
 print("partial_fit ms", t(lambda: m.partial_fit(hb)))
+up = m._uploader if hasattr(m, "_uploader") else None
+for simd in ("0", "1", "0", "1"):
+    os.environ["HHFM_PACK_SIMD"] = simd
+    print("HHFM_PACK_SIMD=%s partial_fit ms" % simd, t(lambda: m.partial_fit(hb), reps=20))

@@ -878,6 +878,15 @@ def test_pack_upload_records_matches_the_host_packer(cuda, id_limit, rows):
         Xbad = X.copy(); Xbad[rows // 2, 0] = id_limit
         with pytest.raises(_lib.HhfmError, match="out of range"):
             up.upload([Xbad, F1, Y], id_limit)
+        # int64-only parts: the 16-bit wire format takes the vectorised packer (8 ids per instruction + masked tails)
+        Z = rng.integers(0, id_limit, (rows, 17)).astype(np.int64)
+        recs4, stride4 = up.upload([X, Y, Z], id_limit)
+        host4, _ = pack_records([X, Y, Z], id_limit, Staging(torch.int32))
+        assert (recs4.cpu().numpy() == host4.numpy().reshape(rows, stride4)).all()
+        for badval in (id_limit, -1, -(1 << 40), 1 << 40):
+            Zbad = Z.copy(); Zbad[rows - 1, 16] = badval
+            with pytest.raises(_lib.HhfmError, match="out of range"):
+                up.upload([X, Y, Zbad], id_limit)
 
 
 # ----------------------------------------------------------------------------------------------------
