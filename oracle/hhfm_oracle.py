@@ -638,7 +638,16 @@ def fm_topk_scores(A, V, b, n_user, n_item):
 def dot_topk_scores(Q, V, n_user, n_item):
     """BPR.topk / MF.topk / OUR.topk (BPR.py:132-135, MF.py:145-148, OurModel7.py:294): score = q_c . v_n."""
     items = _f32(V)[n_user:n_user + n_item]
-    return seq_dot(_f32(Q)[:, None, :], items[None, :, :])
+    Q = _f32(Q)
+    if Q.shape[0] * items.shape[0] < (1 << 22):
+        return seq_dot(Q[:, None, :], items[None, :, :])
+    # the same arithmetic as seq_dot (k ascending, multiply and add rounded separately) streamed over a K-major copy of the
+    # catalog: 10x faster for the million-item checks of tests/test_gpu_fullsize.py
+    items_t = np.ascontiguousarray(items.T)
+    acc = (Q[:, 0, None] * items_t[0][None, :]).astype(F32)
+    for k in range(1, items_t.shape[0]):
+        acc = (acc + (Q[:, k, None] * items_t[k][None, :]).astype(F32)).astype(F32)
+    return acc
 
 
 def afm_topk_scores(A, w, n_user, n_item):
