@@ -251,6 +251,12 @@ struct HeadArgs {
   float* gblast;           // [D]  bias gradient of the last hidden layer = column sums of dZ_L
   float* loss_partials;
   HotPlan hot;             // optional hot-row replicas for the FM-part scatter
+  // Wide&Deep mode (WDMF.py:51-126): no FM terms, out = H_L . proj3 + cbias + extra[s] is a logit, loss = mean sigmoid
+  // cross-entropy over the batch, d loss / d out is also written per sample for the wide part's scatter
+  int wd;
+  const float* extra;      // [B] additive logit (the wide part) or NULL
+  float* gsample;          // [B] d loss / d out (TRAIN) or NULL
+  float inv_b;             // 1 / B
 };
 
 constexpr int kHeadT = 8;    // D <= 32 * kHeadT
@@ -291,12 +297,12 @@ __global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
   for (int t = 0; t < kHeadT; t++) { g3[t] = 0.f; gbl[t] = 0.f; }
 
   for (int64_t s = warp_g; s < a.B; s += n_warps) {
-    const int my_id = (lane < F) ? __ldg(a.idx + s * F + lane) : 0;
-    const float y1 = (lane < F) ? __ldg(a.fbias + my_id) : 0.f;
+    const int my_id = (lane < F && !a.wd) ? __ldg(a.idx + s * F + lane) : 0;
+    const float y1 = (lane < F && !a.wd) ? __ldg(a.fbias + my_id) : 0.f;
     float4 S[VPL], Q[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; i++) { S[i] = f4_zero(); Q[i] = f4_zero(); }
-    for (int f = 0; f < F; f++) {
+    for (int f = 0; f < (a.wd ? 0 : F); f++) {
       const int id = __shfl_sync(0xffffffffu, my_id, f);
       const float4* row = reinterpret_cast<const float4*>(a.V) + (size_t)id * kv;
 #pragma unroll
@@ -324,12 +330,23 @@ __global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
       h[t] = (j < D) ? hrow[j] : 0.f;
       part = fmaf(h[t], p3[t], part);
     }
-    const float out = warp_sum(part) + cb;
+    float out = warp_sum(part) + cb;
+    if (a.wd && a.extra) out += __ldg(a.extra + s);
     if (lane == 0 && a.out) a.out[s] = out;
     if (!TRAIN) continue;
 
-    const float g = out - __ldg(a.labels + s);        // d loss / d out, loss = 0.5 (y - out)^2
-    loss_acc += (lane == 0) ? 0.5f * g * g : 0.f;
+    float g;
+    if (a.wd) {
+      // mean sigmoid cross-entropy, labels in {0, 1}: loss = (max(z,0) - z y + log(1 + exp(-|z|))) / B, d/dz = (sigmoid(z) - y) / B
+      const float y = __ldg(a.labels + s);
+      const float pr = 1.f / (1.f + expf(-out));
+      g = (pr - y) * a.inv_b;
+      loss_acc += (lane == 0) ? (fmaxf(out, 0.f) - out * y + log1pf(expf(-fabsf(out)))) * a.inv_b : 0.f;
+      if (lane == 0 && a.gsample) a.gsample[s] = g;
+    } else {
+      g = out - __ldg(a.labels + s);                  // d loss / d out, loss = 0.5 (y - out)^2
+      loss_acc += (lane == 0) ? 0.5f * g * g : 0.f;
+    }
     gcb += (lane == 0) ? g : 0.f;
     g1 = fmaf(g, y1, g1);
 #pragma unroll
@@ -342,6 +359,7 @@ __global__ void __launch_bounds__(256) dfm_head_kernel(const HeadArgs a) {
       gbl[t] += dz;
       if (j < D) hrow[j] = dz;
     }
+    if (a.wd) continue;
     // FM part of the embedding gradient: dV[x_f] += g * proj2 * (S - e_f);  d feature_bias[x_f] += g * proj1[f]
     const int my_slot = (a.hot.slot && lane < F) ? __ldg(a.hot.slot + my_id) : -1;
     if (lane < F) {
@@ -713,10 +731,10 @@ extern "C" int64_t hhfm_workspace_bytes_dfm(int64_t B, int64_t F, int64_t K, int
   return lo.ws_floats * (int64_t)sizeof(float);
 }
 
-extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
-                            int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
-                            float* workspace, float* out, hhfm_stream_t stream) {
-  HHFM_REQUIRE(idx && V && feature_bias && params && workspace && out, "dfm_fwd: NULL argument");
+static int dfm_fwd_impl(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
+                        int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
+                        float* workspace, float* out, hhfm_stream_t stream, int wd, const float* extra) {
+  HHFM_REQUIRE(idx && V && (feature_bias || wd) && params && workspace && out, "dfm_fwd: NULL argument");
   HHFM_REQUIRE(B >= 0 && B < (1ll << 31) && M > 0, "dfm_fwd: bad sizes");
   if (B == 0) return HHFM_OK;
   DfmLayout lo;
@@ -726,6 +744,7 @@ extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const floa
   HeadArgs h{};
   h.idx = idx; h.B = B; h.F = (int)F; h.K = (int)K; h.D = lo.d[lo.L];
   h.V = V; h.fbias = feature_bias; h.proj = params + lo.proj_off; h.cbias = params + lo.cbias_off; h.out = out;
+  h.wd = wd; h.extra = extra;
   if (dfm_use_tc(K)) {
     DfmTcLayout t;
     dfm_tc_layout(B, lo, t);
@@ -741,13 +760,13 @@ extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const floa
   return launch_head<false>(h, st);
 }
 
-extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V,
-                                       const float* feature_bias, int64_t M, int64_t K, const float* params,
-                                       int32_t n_layers, const int32_t* layer_sizes, const float* labels,
-                                       float* workspace, float* out, float* gV, float* gbias, float* gparams,
-                                       float* loss_partials, const int32_t* hot_slot, float* ghot, float* ghot_bias,
-                                       int32_t n_rep, int32_t n_hot, hhfm_stream_t stream) {
-  HHFM_REQUIRE(idx && V && feature_bias && params && workspace && labels && gV && gbias && gparams && loss_partials,
+static int dfm_fwd_bwd_impl(const int32_t* idx, int64_t B, int64_t F, const float* V,
+                            const float* feature_bias, int64_t M, int64_t K, const float* params,
+                            int32_t n_layers, const int32_t* layer_sizes, const float* labels,
+                            float* workspace, float* out, float* gV, float* gbias, float* gparams,
+                            float* loss_partials, const int32_t* hot_slot, float* ghot, float* ghot_bias,
+                            int32_t n_rep, int32_t n_hot, hhfm_stream_t stream, int wd, const float* extra, float* gsample) {
+  HHFM_REQUIRE(idx && V && (feature_bias || wd) && params && workspace && labels && gV && (gbias || wd) && gparams && loss_partials,
                "dfm_fwd_bwd_sqloss: NULL argument");
   HHFM_REQUIRE(B > 0 && B < (1ll << 31) && M > 0, "dfm_fwd_bwd_sqloss: bad sizes");
   DfmLayout lo;
@@ -763,6 +782,7 @@ extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
   h.labels = labels; h.out = out;
   h.gV = gV; h.gfbias = gbias; h.gproj = gparams + lo.proj_off; h.gcbias = gparams + lo.cbias_off;
   h.gblast = gparams + lo.b_off[L - 1]; h.loss_partials = loss_partials; h.hot = hot;
+  h.wd = wd; h.extra = extra; h.gsample = gsample; h.inv_b = 1.0f / (float)B;
   if (dfm_use_tc(K)) {
     DfmTcLayout t;
     dfm_tc_layout(B, lo, t);
@@ -841,6 +861,41 @@ extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
     if (rc != HHFM_OK) return rc;
   }
   return HHFM_OK;
+}
+
+extern "C" int hhfm_dfm_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* feature_bias,
+                            int64_t M, int64_t K, const float* params, int32_t n_layers, const int32_t* layer_sizes,
+                            float* workspace, float* out, hhfm_stream_t stream) {
+  return dfm_fwd_impl(idx, B, F, V, feature_bias, M, K, params, n_layers, layer_sizes, workspace, out, stream, 0, nullptr);
+}
+
+extern "C" int hhfm_dfm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const float* V,
+                                       const float* feature_bias, int64_t M, int64_t K, const float* params,
+                                       int32_t n_layers, const int32_t* layer_sizes, const float* labels,
+                                       float* workspace, float* out, float* gV, float* gbias, float* gparams,
+                                       float* loss_partials, const int32_t* hot_slot, float* ghot, float* ghot_bias,
+                                       int32_t n_rep, int32_t n_hot, hhfm_stream_t stream) {
+  return dfm_fwd_bwd_impl(idx, B, F, V, feature_bias, M, K, params, n_layers, layer_sizes, labels, workspace, out, gV, gbias,
+                          gparams, loss_partials, hot_slot, ghot, ghot_bias, n_rep, n_hot, stream, 0, nullptr, nullptr);
+}
+
+// Wide&Deep deep part (WDMF.py:57-73): the DeepFM tower with its FM terms off; `extra` [B] is the wide logit, `out` the summed
+// logit, `gsample` [B] receives d(mean log-loss)/d logit for the wide part's backward.  Parameter block: the DeepFM layout
+// (the first F + K entries of the projection block are unused and stay zero).
+extern "C" int hhfm_wd_deep_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t M, int64_t K,
+                                const float* params, int32_t n_layers, const int32_t* layer_sizes, const float* extra,
+                                float* workspace, float* out, hhfm_stream_t stream) {
+  return dfm_fwd_impl(idx, B, F, V, nullptr, M, K, params, n_layers, layer_sizes, workspace, out, stream, 1, extra);
+}
+
+extern "C" int hhfm_wd_deep_fwd_bwd_logloss(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t M, int64_t K,
+                                            const float* params, int32_t n_layers, const int32_t* layer_sizes,
+                                            const float* labels, const float* extra, float* workspace, float* out,
+                                            float* gV, float* gparams, float* gsample, float* loss_partials,
+                                            const int32_t* hot_slot, float* ghot, int32_t n_rep, int32_t n_hot,
+                                            hhfm_stream_t stream) {
+  return dfm_fwd_bwd_impl(idx, B, F, V, nullptr, M, K, params, n_layers, layer_sizes, labels, workspace, out, gV, nullptr, gparams,
+                          loss_partials, hot_slot, ghot, nullptr, n_rep, n_hot, stream, 1, extra, gsample);
 }
 
 extern "C" int64_t hhfm_workspace_bytes_dfm_topn(int64_t C, int64_t N, int64_t F, int64_t K, int32_t n_layers,

@@ -8,6 +8,7 @@ reference (`_init_graph`) is replaced by device tensors and C-ABI kernel launche
   FM    Newcode/FM.py:59-198          MF   Newcode/MF.py:43-149
   OUR   Newcode/OurModel7.py:50-307   BPR  Newcode/BPR.py:45-136
   AFM   Newcode/AFM.py:63-246          DeepFM  Newcode/DFM.py:50-232
+  CARS2 Newcode/CARS2.py:45-187        WD   Newcode/WDMF.py:51-126 (TF canned estimator restated; parity unpinned)
 """
 from __future__ import annotations
 
@@ -961,6 +962,170 @@ class DeepFM(_Base):
         if isinstance(fetches, (tuple, list)) and len(fetches) == 2 and fetches[0] is self.loss:
             return self.partial_fit({"X": feed[self.feat_index], "Y": feed[self.label]}), None
         raise NotImplementedError("sess.run: unsupported fetch %r" % (fetches,))
+
+
+# ====================================================================================================
+class WD(_Base):
+    """Wide&Deep, Newcode/WDMF.py:51-126: `WD(feature_num, n_user, n_item)` wraps tf.contrib.learn's
+    DNNLinearCombinedClassifier (hashed columns + all pairwise crossed columns -> linear model trained with FTRL; 128-d
+    embedding columns -> DNN [1024, 512, 256] trained with Adagrad; sigmoid cross-entropy head).  Everything numeric in the
+    reference happens inside TensorFlow, so this class follows TF's documented defaults with its own bucket functions
+    (include/hhfm_sm100.h K11, oracle wd_*): PARITY UNPINNED against the reference, pinned against the oracle restatement.
+
+      * single hashed columns: the loader's global feature id is its own bucket (ids must be < features_M, default 10^5 =
+        the reference's hash_bucket_size); crossed columns: splitmix64 of the id pair mod 10^4;
+      * linear half: FTRL, learning rate min(0.2, 1/sqrt(#linear columns)), accumulators 0.1, l1 = l2 = 0, weights start at 0;
+      * DNN half: Adagrad lr 0.05 (accumulators 0.1), Glorot-uniform kernels, zero biases, embeddings N(0, 1/sqrt(dim))
+        truncated at 2 sigma, field order = column order;
+      * `partial_fit(X, Y)` = `fit(steps=500)`: 500 full-batch steps; `predict(X)` = predict_proba rows [1-p, p]."""
+
+    def __init__(self, feature_num, n_user, n_item, features_M=100000, hidden_units=(1024, 512, 256), embedding_dim=128,
+                 cross_buckets=10000, steps=500, random_seed=2016):
+        self.feature_num = int(feature_num)
+        self.n_user = n_user
+        self.n_item = n_item
+        self.keys = ["Feature" + str(i) for i in range(self.feature_num)]
+        self.hidden_units = [int(h) for h in hidden_units]
+        self.steps = int(steps)
+        self.cross_buckets = int(cross_buckets)
+        self.random_seed = random_seed
+        F, K, L = self.feature_num, int(embedding_dim), len(self.hidden_units)
+        self.dnn_learning_rate = 0.05
+        n_pairs = F * (F - 1) // 2
+        self.linear_learning_rate = min(0.2, 1.0 / np.sqrt(F + n_pairs))
+        self._setup(features_M, K, random_seed, False, "AdagradOptimizer", self.dnn_learning_rate, 0.1, 0.0)
+        dev = self.device
+        rs = np.random.RandomState(self.random_seed)
+        emb = rs.normal(0, 1.0, (self._M, K))
+        bad = np.abs(emb) > 2.0
+        while bad.any():                                   # truncated normal: redraw beyond two sigma
+            emb[bad] = rs.normal(0, 1.0, int(bad.sum()))
+            bad = np.abs(emb) > 2.0
+        self.weights["feature_embeddings"].copy_(torch.tensor(emb / np.sqrt(K), dtype=torch.float32))
+        self._sizes = np.asarray(self.hidden_units, dtype=np.int32)
+        lib = _lib.load()
+        sp = self._sizes.ctypes.data
+        n_par = int(lib.hhfm_dfm_param_count(F, K, L, sp))
+        self._n_reg = int(lib.hhfm_dfm_reg_count(F, K, L, sp))
+        if n_par < 0:
+            raise _lib.HhfmError("WD: %s" % lib.hhfm_last_error().decode())
+        self._params = torch.zeros(n_par, dtype=torch.float32, device=dev)
+        self._gparams = torch.zeros(n_par, dtype=torch.float32, device=dev)
+        dims = [F * K] + self.hidden_units
+        off = 0
+        for i in range(L):
+            lim = np.sqrt(6.0 / (dims[i] + dims[i + 1]))                                      # Glorot uniform
+            n = dims[i] * dims[i + 1]
+            self.weights["layer_%d" % i] = self._params[off:off + n].view(dims[i], dims[i + 1])
+            self.weights["layer_%d" % i].copy_(torch.tensor(rs.uniform(-lim, lim, (dims[i], dims[i + 1])), dtype=torch.float32))
+            off += n
+        off += F + K                                       # the FM slots of the DeepFM projection block: unused, zero
+        lim = np.sqrt(6.0 / (dims[-1] + 1))
+        self.weights["logits_w"] = self._params[off:off + dims[-1]].view(dims[-1], 1)
+        self.weights["logits_w"].copy_(torch.tensor(rs.uniform(-lim, lim, (dims[-1], 1)), dtype=torch.float32))
+        off = self._n_reg
+        for i in range(L):
+            self.weights["bias_%d" % i] = self._params[off:off + dims[i + 1]].view(1, dims[i + 1])
+            off += dims[i + 1]
+        self.weights["logits_b"] = self._params[off:off + 1].view(())
+        # wide half: [w_lin (M) | w_cross (P x buckets) | bias (1)] in one block with its FTRL slots
+        n_wide = self._M + n_pairs * self.cross_buckets + 1
+        self._wide = torch.zeros(n_wide, dtype=torch.float32, device=dev)
+        self._gwide = torch.zeros(n_wide, dtype=torch.float32, device=dev)
+        self._ftrl_accum = torch.full((n_wide,), 0.1, dtype=torch.float32, device=dev)
+        self._ftrl_linear = torch.zeros(n_wide, dtype=torch.float32, device=dev)
+        self.weights["wide_linear"] = self._wide[:self._M]
+        self.weights["wide_cross"] = self._wide[self._M:n_wide - 1].view(n_pairs, self.cross_buckets)
+        self.weights["wide_bias"] = self._wide[n_wide - 1:].view(())
+        self._n_pairs = n_pairs
+        self._ws = None
+        self._wide_logit = None
+        self._gsample = None
+
+    def _workspace(self, B):
+        need = int(_lib.load().hhfm_workspace_bytes_dfm(B, self.feature_num, self._K, len(self.hidden_units),
+                                                        self._sizes.ctypes.data)) // 4
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1), dtype=torch.float32, device=self.device)
+        if self._wide_logit is None or self._wide_logit.numel() < B:
+            self._wide_logit = torch.empty(B, dtype=torch.float32, device=self.device)
+            self._gsample = torch.empty(B, dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def _wide_fwd(self, idx):
+        B, F = idx.shape
+        _lib.call("hhfm_wd_wide_fwd", ptr(idx), B, F, ptr(self.weights["wide_linear"]), ptr(self.weights["wide_cross"]),
+                  ptr(self.weights["wide_bias"]), self._M, self.cross_buckets, ptr(self._wide_logit), cur_stream())
+
+    def score_device(self, idx):
+        """Logits [B] (device) for device rows [B,F]; monotone in the probability the reference ranks by."""
+        B, F = idx.shape
+        if F != self.feature_num:
+            raise _lib.HhfmError("WD: X has %d columns, feature_num is %d" % (F, self.feature_num))
+        ws = self._workspace(B)
+        self._wide_fwd(idx)
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_wd_deep_fwd", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), self._M, self._K,
+                  ptr(self._params), len(self.hidden_units), self._sizes.ctypes.data, ptr(self._wide_logit), ptr(ws), ptr(out),
+                  cur_stream())
+        return out
+
+    def predict(self, X):
+        """model.predict_proba (WDMF.py:108-111): rows [P(label 0), P(label 1)]."""
+        p = torch.sigmoid(self.score_device(self._upload_rows(np.asarray(X)))).cpu().numpy()
+        return np.stack([1.0 - p, p], axis=1)
+
+    def fit_device(self, idx, y):
+        """One full-batch step of the estimator on device rows / labels: FTRL on the wide half, Adagrad on the DNN half."""
+        B, F = idx.shape
+        if F != self.feature_num:
+            raise _lib.HhfmError("WD: X has %d columns, feature_num is %d" % (F, self.feature_num))
+        if self._dp_group is not None:
+            raise NotImplementedError("WD is single-process (the reference estimator is)")
+        self._opt.begin_step()
+        V = self.weights["feature_embeddings"]
+        ws = self._workspace(B)
+        hot = self._hot_plan(idx, False)
+        self._wide_fwd(idx)
+        _lib.call("hhfm_wd_deep_fwd_bwd_logloss", ptr(idx), B, F, ptr(V), self._M, self._K, ptr(self._params),
+                  len(self.hidden_units), self._sizes.ctypes.data, ptr(y), ptr(self._wide_logit), ptr(ws), None, ptr(self._gV),
+                  ptr(self._gparams), ptr(self._gsample), ptr(self._loss_partials), *(hot.args() if hot else NO_HOT), cur_stream())
+        if hot:
+            hot.fold(self._gV, None)
+        n_wide = self._wide.numel()
+        _lib.call("hhfm_wd_wide_bwd", ptr(idx), B, F, ptr(self._gsample), self._M, self.cross_buckets, ptr(self._gwide),
+                  ptr(self._gwide[self._M:]), ptr(self._gwide[n_wide - 1:]), cur_stream())
+        self._apply_arena_dense("feature_embeddings", V, self._gV, 0.0, None)      # rows with g = 0 do not move under Adagrad
+        self._opt.apply_dense("dnn", self._params, self._gparams, 0.0, None)
+        _lib.call("hhfm_opt_ftrl_dense", ptr(self._wide), ptr(self._ftrl_accum), ptr(self._ftrl_linear), ptr(self._gwide), n_wide,
+                  float(self.linear_learning_rate), 0.0, 0.0, 1, cur_stream())
+        self._enqueue_loss(False)
+
+    def partial_fit(self, X, Y, steps=None):
+        """WDMF.py:113-115 `model.fit(input_fn, steps=500)`: `steps` steps on the whole (X, Y); returns the last loss."""
+        idx = self._upload_rows(np.asarray(X)).clone()
+        y = self._upload_f32(np.asarray(Y, dtype=np.float32)).clone()
+        for _ in range(self.steps if steps is None else int(steps)):
+            self.fit_device(idx, y)
+        return self._read_loss()
+
+    def topk(self, feed_dict, tp):
+        """WDMF.py:116-126: every (row, item) pair through predict_proba, then top_k (lowest index first on ties).  The
+        ranking uses the logit (sigmoid is monotone; equal logits are equal probabilities)."""
+        A = np.array(feed_dict, dtype=np.int64)
+        A_dev, stride = self._topn.upload_rows(A, self._M)
+        C_rows, F = A.shape
+        N = self.n_item
+        out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
+        items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
+        chunk = max(1, (1 << 20) // max(N, 1))
+        for c0 in range(0, C_rows, chunk):
+            c1 = min(C_rows, c0 + chunk)
+            rows = A_dev[c0:c1, :F].unsqueeze(1).repeat(1, N, 1)
+            rows[:, :, 1] = items.unsqueeze(0)
+            sc = self.score_device(rows.reshape(-1, F).contiguous()).view(c1 - c0, N)
+            _lib.call("hhfm_topn_select", ptr(sc), None, None, c1 - c0, N, N, tp, 0, None, ptr(out_ids[c0:c1]), cur_stream())
+        return out_ids.cpu().numpy()
 
 
 # ====================================================================================================

@@ -220,6 +220,37 @@ int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int64_t C, int
                          const int32_t* layer_sizes, int64_t item_base, int64_t N, float* workspace, float* scores,
                          hhfm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K11  Wide&Deep (WDMF.py:51-126: tf.contrib.learn.DNNLinearCombinedClassifier over hashed columns, crossed columns and
+ *      128-d embedding columns, DNN [1024, 512, 256]).  The arithmetic of the reference lives inside TensorFlow; this is a
+ *      restatement with documented choices (oracle/hhfm_oracle.py wd_*; parity unpinned):
+ *   logit = wide(x) + deep(x);  loss = mean sigmoid cross-entropy, labels in {0,1};  probability = sigmoid(logit)
+ *   wide(x) = b_wide + sum_f w_lin[x_f] + sum_{i<j} w_cross[p(i,j)][splitmix64((x_i << 32) | x_j) mod n_cross_buckets]
+ *             (single columns: the global feature id is its own bucket; pairs p in lexicographic order)
+ *   deep(x) = relu MLP over the concatenated embeddings V[x_f] (field order), then a [D_L] -> 1 layer with bias:
+ *             the DeepFM tower (K8) with its FM terms off; parameter block = the K8 layout, whose first F + K projection
+ *             entries are unused.
+ *   hhfm_wd_wide_fwd      out[s] = wide(x_s)
+ *   hhfm_wd_deep_fwd      out[s] = extra[s] + deep(x_s)                       (extra = the wide logit, may be NULL)
+ *   hhfm_wd_deep_fwd_bwd_logloss   + gV / gparams (accumulated), gsample[s] = d loss / d logit_s, loss partials
+ *   hhfm_wd_wide_bwd      g_lin / g_cross / g_b += scatter of gsample
+ *   hhfm_opt_ftrl_dense   TF1 ApplyFtrl, learning_rate_power -0.5 (the estimator's optimizer for the wide half)
+ * ------------------------------------------------------------------------------------------------ */
+int hhfm_wd_wide_fwd(const int32_t* idx, int64_t B, int64_t F, const float* w_lin, const float* w_cross,
+                     const float* b_wide, int64_t M, int32_t n_cross_buckets, float* out, hhfm_stream_t stream);
+int hhfm_wd_wide_bwd(const int32_t* idx, int64_t B, int64_t F, const float* gsample, int64_t M, int32_t n_cross_buckets,
+                     float* g_lin, float* g_cross, float* g_b, hhfm_stream_t stream);
+int hhfm_wd_deep_fwd(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t M, int64_t K, const float* params,
+                     int32_t n_layers, const int32_t* layer_sizes, const float* extra, float* workspace, float* out,
+                     hhfm_stream_t stream);
+int hhfm_wd_deep_fwd_bwd_logloss(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t M, int64_t K,
+                                 const float* params, int32_t n_layers, const int32_t* layer_sizes, const float* labels,
+                                 const float* extra, float* workspace, float* out, float* gV, float* gparams,
+                                 float* gsample, float* loss_partials, const int32_t* hot_slot, float* ghot, int32_t n_rep,
+                                 int32_t n_hot, hhfm_stream_t stream);
+int hhfm_opt_ftrl_dense(float* w, float* accum, float* linear, float* g, int64_t n, float lr, float l1, float l2,
+                        int32_t zero_grad, hhfm_stream_t stream);
+
 /* fp32-accurate GEMM on the tensor cores (the building block of the DeepFM tower, dfm_tc.cu): C[M,N] = A[M,K] . B[N,K]^T,
  * row-major operands with K contiguous, 3xTF32 split (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi) with fp32 accumulation in TMEM.
  * lda / ldb / ldc are multiples of 4 floats, pointers 16-byte aligned; workspace: (M*lda + N*ldb) floats. */

@@ -508,6 +508,100 @@ def dfm_loss_grads(X, Y, w, l2_reg=0.0, n_layers=3):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Wide&Deep: WDMF.py:51-126 (tf.contrib.learn.DNNLinearCombinedClassifier).  The arithmetic of the reference lives inside
+# TensorFlow (hashed / crossed / embedding columns, FTRL for the linear half, Adagrad for the DNN); it is restated here from
+# TF's documented behaviour with our own bucket functions -- PARITY UNPINNED: nothing in the reference tree pins
+# TF's string fingerprints, its column order or its initialisers.
+# ----------------------------------------------------------------------------------------------------
+def _splitmix64_arr(x):
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def wd_cross_bucket(xi, xj, n_buckets):
+    """Bucket of the crossed column (x_i, x_j): splitmix64((x_i << 32) | x_j) mod n_buckets (crossed_column(..., 1e4),
+    WDMF.py:66; TF's own fingerprint is not restatable)."""
+    with np.errstate(over="ignore"):
+        key = (np.asarray(xi, dtype=np.uint64) << np.uint64(32)) | np.asarray(xj, dtype=np.uint64)
+        return (_splitmix64_arr(key) % np.uint64(n_buckets)).astype(np.int64)
+
+
+def wd_wide(X, w):
+    """b_wide + sum_f w_lin[x_f] + sum_{i<j} w_cross[p(i,j)][bucket(x_i, x_j)]  (linear_feature_columns, WDMF.py:57-66;
+    single columns: the loader's global id is its own bucket).  Returns the logit [B] and the cross buckets [B,P]."""
+    X = np.asarray(X)
+    wl = _f32(w["wide_linear"]).reshape(-1); wc = _f32(w["wide_cross"])
+    pi = pair_index(X.shape[1])
+    buckets = np.stack([wd_cross_bucket(X[:, i], X[:, j], wc.shape[1]) for i, j in pi], axis=1) if pi else np.zeros((len(X), 0), np.int64)
+    acc = np.zeros(len(X), F32)
+    for f in range(X.shape[1]):
+        acc = (acc + wl[X[:, f]]).astype(F32)
+    for p in range(len(pi)):
+        acc = (acc + wc[p, buckets[:, p]]).astype(F32)
+    return (acc + F32(np.asarray(w["wide_bias"]).reshape(()))).astype(F32), buckets
+
+
+def wd_forward(X, w, n_layers=3):
+    """logit = wide + deep; deep = relu MLP over the concatenated 128-d embeddings (dnn_feature_columns, hidden units
+    [1024, 512, 256], WDMF.py:67-73) and a [D_L,1] logits layer with bias."""
+    wide, buckets = wd_wide(X, w)
+    E = _f32(w["feature_embeddings"])[np.asarray(X)]
+    h = E.reshape(E.shape[0], -1)
+    acts = [h]
+    for i in range(n_layers):
+        h = np.maximum((h @ _f32(w["layer_%d" % i])).astype(F32) + _f32(w["bias_%d" % i]).reshape(1, -1), F32(0)).astype(F32)
+        acts.append(h)
+    deep = ((h @ _f32(w["logits_w"]).reshape(-1, 1)).astype(F32).reshape(-1) + F32(np.asarray(w["logits_b"]).reshape(()))).astype(F32)
+    return (deep + wide).astype(F32), dict(E=E, acts=acts, buckets=buckets)
+
+
+def wd_loss_grads(X, Y, w, n_layers=3):
+    """Mean sigmoid cross-entropy over the batch (labels in {0,1}; the estimator's head) and the gradient of every variable."""
+    X = np.asarray(X); Y = _f32(Y).reshape(-1)
+    z, c = wd_forward(X, w, n_layers)
+    B, F, K = c["E"].shape
+    inv = F32(1.0 / B)
+    per = (np.maximum(z, F32(0)) - z * Y + np.log1p(np.exp(-np.abs(z)))).astype(F32)
+    loss = F32((per * inv).astype(F32).sum(dtype=F32))
+    g = ((_sigmoid(z) - Y) * inv).astype(F32)                              # d loss / d logit
+    grads = {}
+    gl = np.zeros(_f32(w["wide_linear"]).reshape(-1).shape, F32)
+    np.add.at(gl, X.reshape(-1), np.repeat(g, F))
+    gc = np.zeros(_f32(w["wide_cross"]).shape, F32)
+    for p in range(c["buckets"].shape[1]):
+        np.add.at(gc[p], c["buckets"][:, p], g)
+    grads["wide_linear"] = gl; grads["wide_cross"] = gc; grads["wide_bias"] = g.sum(dtype=F32)
+    h_last = c["acts"][-1]
+    grads["logits_w"] = (h_last.T @ g).astype(F32).reshape(-1, 1)
+    grads["logits_b"] = g.sum(dtype=F32)
+    d_h = (g[:, None] * _f32(w["logits_w"]).reshape(1, -1)).astype(F32)
+    for i in reversed(range(n_layers)):
+        h_out, h_in = c["acts"][i + 1], c["acts"][i]
+        dZ = (d_h * (h_out > 0)).astype(F32)
+        grads["layer_%d" % i] = (h_in.T @ dZ).astype(F32)
+        grads["bias_%d" % i] = dZ.sum(axis=0, dtype=F32).reshape(1, -1)
+        d_h = (dZ @ _f32(w["layer_%d" % i]).T).astype(F32)
+    dV = np.zeros_like(_f32(w["feature_embeddings"]))
+    np.add.at(dV, X.reshape(-1), d_h.reshape(-1, K))
+    grads["feature_embeddings"] = dV
+    return loss, z, grads
+
+
+def ftrl_dense(w, accum, linear, g, lr, l1=0.0, l2=0.0):
+    """TF1 ApplyFtrl, learning_rate_power = -0.5 (tf.train.FtrlOptimizer defaults: the linear half of
+    DNNLinearCombinedClassifier): n' = n + g^2; z += g - (sqrt(n') - sqrt(n))/lr * w;
+    w = (sign(z) l1 - z) / (sqrt(n')/lr + 2 l2) if |z| > l1 else 0."""
+    w = _f32(w); accum = _f32(accum); linear = _f32(linear); g = _f32(g)
+    a1 = (accum + g * g).astype(F32)
+    z = (linear + g - ((np.sqrt(a1) - np.sqrt(accum)) / F32(lr) * w).astype(F32)).astype(F32)
+    quad = (np.sqrt(a1) / F32(lr) + F32(2.0 * l2)).astype(F32)
+    w1 = np.where(np.abs(z) > F32(l1), ((np.sign(z) * F32(l1) - z) / quad).astype(F32), F32(0)).astype(F32)
+    return w1, a1, z
+
+
+# ----------------------------------------------------------------------------------------------------
 # CARS2: CARS2.py:85-123 (restated op by op; the device kernels use the collapsed form T = sum_q B_q Z[:,q,:])
 # ----------------------------------------------------------------------------------------------------
 def cars2_feedback(Pos, Fea, w, items=None):

@@ -367,6 +367,70 @@ def test_dfm_steps_and_topk_match_oracle(cuda, monkeypatch):
                 assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
 
 
+def test_wd_steps_and_topk_match_oracle(cuda):
+    """Wide&Deep (WDMF.py:51-126 restated; parity unpinned against TF, pinned against the oracle): teacher-forced full-batch
+    steps -- mean log-loss, Adagrad on the DNN half / embeddings, FTRL on the wide half -- then predict_proba and topk."""
+    from conftest import assert_update_close
+    from hhfm_b200.models import WD
+    rng = np.random.default_rng(13)
+    n_user, n_item, F, K = 40, 120, 5, 16
+    M = 300
+    hidden = [48, 32, 16]
+    model = WD(F, n_user, n_item, features_M=M, hidden_units=hidden, embedding_dim=K, cross_buckets=97, steps=1)
+    # the estimator starts the wide half and the biases at zero; give them values so that every term of the graph is exercised
+    init = model.get_weights()
+    for k in ("wide_linear", "wide_cross", "wide_bias", "bias_0", "bias_1", "bias_2", "logits_b"):
+        init[k] = rng.normal(0, 0.1, np.asarray(init[k]).shape).astype(np.float32)
+    model.load_weights(init)
+    adagrad = ["feature_embeddings", "layer_0", "layer_1", "layer_2", "bias_0", "bias_1", "bias_2", "logits_w", "logits_b"]
+    ftrl = ["wide_linear", "wide_cross", "wide_bias"]
+    acc = {k: np.full(np.asarray(init[k]).shape, 0.1, np.float32) for k in adagrad + ftrl}
+    lin = {k: np.zeros(np.asarray(init[k]).shape, np.float32) for k in ftrl}
+    lr_w = min(0.2, 1.0 / np.sqrt(F + F * (F - 1) // 2))
+    assert abs(model.linear_learning_rate - lr_w) < 1e-12 and model.dnn_learning_rate == 0.05
+    for step in range(3):
+        B = 2500 if step < 2 else 333
+        X = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B), 160 + rng.integers(0, 7, B),
+                      170 + rng.integers(0, 2, B), 180 + rng.integers(0, 100, B)], axis=1)
+        Y = rng.choice([1.0, 0.0], B).astype(np.float32)
+        w = model.get_weights()
+        loss_ref, z_ref, g = O.wd_loss_grads(X, Y, w)
+        loss = model.partial_fit(X, Y)
+        assert_close(loss, loss_ref, what="wd loss step %d" % step)
+        got = model.get_weights()
+        for k in adagrad:
+            wk = np.asarray(w[k], np.float32); gk = np.asarray(g[k], np.float32).reshape(wk.shape)
+            w1, a1 = O.adagrad_dense(wk, acc[k], gk, 0.05)
+            assert_update_close(np.asarray(got[k]).reshape(wk.shape), w1, wk, gk, acc[k], 0.05, rtol=3e-5,
+                                atol=4 * 1.2e-7 * float(np.abs(wk).max()), what="wd %s step %d" % (k, step))
+            acc[k] = a1
+        for k in ftrl:
+            wk = np.asarray(w[k], np.float32); gk = np.asarray(g[k], np.float32).reshape(wk.shape)
+            w1, a1, z1 = O.ftrl_dense(wk, acc[k], lin[k], gk, lr_w)
+            d_ref = w1.astype(np.float64) - wk
+            d_got = np.asarray(got[k], np.float64).reshape(wk.shape) - wk
+            scale = max(float(np.abs(d_ref).max()), 1e-12)
+            assert np.abs(d_got - d_ref).max() <= 3e-5 * scale + 4 * 1.2e-7 * float(np.abs(wk).max()), (k, step, np.abs(d_got - d_ref).max(), scale)
+            acc[k] = a1; lin[k] = z1
+    w = model.get_weights()
+    z = O.wd_forward(X[:200], w)[0]
+    proba = model.predict(X[:200])
+    assert proba.shape == (200, 2)
+    assert_close(proba[:, 1], 1.0 / (1.0 + np.exp(-z.astype(np.float64))), what="wd predict_proba")
+    assert np.allclose(proba.sum(axis=1), 1.0, atol=1e-6)
+    A = X[:30]
+    ids = model.topk(A, 20)
+    rows = np.repeat(A[:, None, :], n_item, axis=1); rows[:, :, 1] = n_user + np.arange(n_item)[None, :]
+    ref = O.wd_forward(rows.reshape(-1, F), w)[0].reshape(len(A), n_item)
+    want = O.topk_lowest_index(ref, 20)
+    for r in range(len(A)):
+        if (ids[r] == want[r]).all():
+            continue
+        tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
+        for a_, b_ in zip(ids[r], want[r]):
+            assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
+
+
 def _cars2_weights(rng, n_ui, M, D):
     Dc, Dp, Dq = int(D / 2.5), int(D / 5), int(D / 2.5)
     return dict(UI=rng.normal(0, 0.1, (n_ui, D)).astype(np.float32), Context=rng.normal(0, 0.1, (M, Dc)).astype(np.float32),

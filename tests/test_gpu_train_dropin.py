@@ -25,7 +25,7 @@ def _write_dataset(root, name="frappe", rows=6000, n_user=60, n_item=120, seed=3
     return os.path.join(root, "")
 
 
-@pytest.mark.parametrize("which", ["FM", "AFM", "DFM", "M7", "BPR", "CARS2"])
+@pytest.mark.parametrize("which", ["FM", "AFM", "DFM", "M7", "BPR", "CARS2", "WD"])
 def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     path = _write_dataset(str(tmp_path))
     result = os.path.join(str(tmp_path), "result.txt")
@@ -46,6 +46,9 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     elif which == "CARS2":
         from hhfm_b200.Newcode.CARS2 import CARS2_main as main
         argv += ["--lr", "0.1"]
+    elif which == "WD":
+        from hhfm_b200.Newcode.WDMF import WDMF_main as main
+        argv += ["--wd_steps", "12", "--wd_hidden", "64,32,16", "--wd_dim", "16"]      # a small estimator, 10 outer epochs
     else:
         from hhfm_b200.Newcode.BPR import BPR_main as main
         argv += ["--Result", "0", "--lr", "0.1"]          # BPR.py:40 defaults to the early-stop mode (no periodic log)

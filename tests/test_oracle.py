@@ -180,3 +180,52 @@ def test_hashed_negative_sampler_restatement():
     # a draw depends on (seed, cell, attempt) only: sampling a prefix of the rows gives the same cells
     d = O.sample_negative_hashed(key_id[:100], 5, n_user, n_item, codes, span, 1234)
     assert (d == a[:100]).all()
+
+
+def test_wd_gradients_match_autograd_and_ftrl_reduces_to_adagrad():
+    """Wide&Deep restatement (WDMF.py:51-126; parity unpinned): analytic gradients against torch.autograd in float64, the
+    cross-bucket hash against a scalar splitmix64, and FTRL's first step from (n, z, w) = (0.1, 0, 0) against Adagrad."""
+    import torch
+    rng = np.random.default_rng(0)
+    M, K, F, B, NB = 60, 8, 4, 50, 97
+    layers = [12, 10, 6]
+    w = dict(feature_embeddings=rng.normal(0, 0.3, (M, K)).astype(np.float32), wide_linear=rng.normal(0, 0.3, (M,)).astype(np.float32),
+             wide_cross=rng.normal(0, 0.3, (6, NB)).astype(np.float32), wide_bias=np.float32(0.1),
+             logits_w=rng.normal(0, 0.3, (layers[-1], 1)).astype(np.float32), logits_b=np.float32(-0.2))
+    d = [F * K] + layers
+    for i in range(3):
+        w["layer_%d" % i] = rng.normal(0, 0.3, (d[i], d[i + 1])).astype(np.float32)
+        w["bias_%d" % i] = rng.normal(0, 0.1, (1, d[i + 1])).astype(np.float32)
+    X = rng.integers(0, M, (B, F)); Y = rng.choice([1.0, 0.0], B).astype(np.float32)
+    loss, z, g = O.wd_loss_grads(X, Y, w)
+    tw = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in w.items()}
+    _, c = O.wd_forward(X, w)
+    Xt = torch.tensor(X)
+    wide = tw["wide_bias"] + tw["wide_linear"][Xt].sum(1)
+    for p in range(6):
+        wide = wide + tw["wide_cross"][p][torch.tensor(c["buckets"][:, p])]
+    h = tw["feature_embeddings"][Xt].reshape(B, -1)
+    for i in range(3):
+        h = torch.relu(h @ tw["layer_%d" % i] + tw["bias_%d" % i])
+    zt = (h @ tw["logits_w"]).reshape(-1) + tw["logits_b"] + wide
+    lt = torch.nn.functional.binary_cross_entropy_with_logits(zt, torch.tensor(Y, dtype=torch.float64))
+    lt.backward()
+    assert abs(float(loss) - float(lt.detach())) < 1e-6
+    for k in g:
+        a = np.asarray(g[k], np.float64).reshape(-1); b = tw[k].grad.numpy().reshape(-1)
+        assert np.abs(a - b).max() <= 2e-6 * (np.abs(b).max() + 1e-30), k
+
+    def splitmix(x):
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return x ^ (x >> 31)
+    xi, xj = np.array([0, 5, 99999, 4081]), np.array([1, 7, 12, 99998])
+    assert O.wd_cross_bucket(xi, xj, 10000).tolist() == [splitmix((int(a) << 32) | int(b)) % 10000 for a, b in zip(xi, xj)]
+
+    gg = rng.normal(0, 1, 100).astype(np.float32)
+    w1, a1, z1 = O.ftrl_dense(np.zeros(100, np.float32), np.full(100, 0.1, np.float32), np.zeros(100, np.float32), gg, 0.135)
+    wa, aa = O.adagrad_dense(np.zeros(100, np.float32), np.full(100, 0.1, np.float32), gg, 0.135)
+    assert np.allclose(w1, wa, rtol=1e-6, atol=1e-9) and np.allclose(a1, aa)
+    w2, _, _ = O.ftrl_dense(w1, a1, z1, gg, 0.135, l1=10.0)
+    assert (w2 == 0).all()                                   # |z| <= l1 clips to exactly zero
