@@ -4,7 +4,8 @@
 // (10^4 buckets); the linear model is  wide(x) = b + sum_f w_lin[bucket_f(x_f)] + sum_{i<j} w_cross[(i,j)][bucket_ij(x_i, x_j)].
 // TensorFlow's bucket functions are fingerprints of the id STRINGS (not restatable from the reference tree), so
 // this restatement documents its own:
-//   * single columns: the loader's global feature id itself (ids are unique per (column, value): a collision-free hash);
+//   * single columns: one table keyed by the loader's global feature id (collision-free; a token shared by two columns
+//     shares its weight, where TF's per-column tables would not);
 //   * crosses: splitmix64((x_i << 32) | x_j) mod n_cross_buckets  (oracle: wd_cross_bucket, bit-exact).
 // The deep half is the DeepFM tower without the FM terms (dfm.cu: hhfm_wd_deep_*).
 #include <algorithm>

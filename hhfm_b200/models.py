@@ -972,8 +972,10 @@ class WD(_Base):
     reference happens inside TensorFlow, so this class follows TF's documented defaults with its own bucket functions
     (include/hhfm_sm100.h K11, oracle wd_*): PARITY UNPINNED against the reference, pinned against the oracle restatement.
 
-      * single hashed columns: the loader's global feature id is its own bucket (ids must be < features_M, default 10^5 =
-        the reference's hash_bucket_size); crossed columns: splitmix64 of the id pair mod 10^4;
+      * single hashed columns: ONE table keyed by the loader's global feature id (ids must be < features_M, default 10^5 =
+        the reference's hash_bucket_size).  A token that occurs in two columns shares its weight / embedding, as it shares its
+        id in every other model of the reference; TF's per-column tables would keep them apart.  Crossed columns: splitmix64
+        of the id pair mod 10^4, one table per column pair;
       * linear half: FTRL, learning rate min(0.2, 1/sqrt(#linear columns)), accumulators 0.1, l1 = l2 = 0, weights start at 0;
       * DNN half: Adagrad lr 0.05 (accumulators 0.1), Glorot-uniform kernels, zero biases, embeddings N(0, 1/sqrt(dim))
         truncated at 2 sigma, field order = column order;

@@ -226,7 +226,7 @@ int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int64_t C, int
  *      restatement with documented choices (oracle/hhfm_oracle.py wd_*; parity unpinned):
  *   logit = wide(x) + deep(x);  loss = mean sigmoid cross-entropy, labels in {0,1};  probability = sigmoid(logit)
  *   wide(x) = b_wide + sum_f w_lin[x_f] + sum_{i<j} w_cross[p(i,j)][splitmix64((x_i << 32) | x_j) mod n_cross_buckets]
- *             (single columns: the global feature id is its own bucket; pairs p in lexicographic order)
+ *             (single columns: one table keyed by the global feature id; pairs p in lexicographic order)
  *   deep(x) = relu MLP over the concatenated embeddings V[x_f] (field order), then a [D_L] -> 1 layer with bias:
  *             the DeepFM tower (K8) with its FM terms off; parameter block = the K8 layout, whose first F + K projection
  *             entries are unused.
