@@ -222,6 +222,33 @@ static int launch_rows(float* w, float* s1, float* g, const int32_t* rows, const
   return check_launch("opt_rows_kernel");
 }
 
+// ---- coalesced-sparse gradient exchange: pack the touched rows of a dense gradient, mark received rows ----
+__global__ void __launch_bounds__(256) gather_rows_kernel(float* __restrict__ table, const int32_t* __restrict__ ids, int64_t n, int K,
+                                                          float* __restrict__ out, int zero_src) {
+  if (K == 1) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = __ldg(ids + i);
+      out[i] = table[r];
+      if (zero_src) table[r] = 0.f;
+    }
+    return;
+  }
+  const int kv = K >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * kv; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / kv;
+    const int c = (int)(i % kv);
+    float4* src = reinterpret_cast<float4*>(table) + (size_t)__ldg(ids + row) * kv + c;
+    reinterpret_cast<float4*>(out)[i] = *src;
+    if (zero_src) *src = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) touch_rows_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t* stamp_arr, int32_t stamp,
+                                                         int32_t* rows, int32_t* count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    touch_row(stamp_arr, stamp, rows, count, __ldg(ids + i));
+}
+
 }  // namespace hhfm
 
 using namespace hhfm;
@@ -293,4 +320,24 @@ extern "C" int hhfm_loss_finalize(const float* loss_partials, const float* sq_pa
   HHFM_REQUIRE(loss_partials && loss_out, "loss_finalize: NULL argument");
   loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, sq_partials, half_lamda, loss_out);
   return check_launch("loss_finalize_kernel");
+}
+
+extern "C" int hhfm_gather_rows(float* table, const int32_t* ids, int64_t n, int64_t K, int64_t M, float* out, int32_t zero_src,
+                                hhfm_stream_t stream) {
+  HHFM_REQUIRE(table && ids && out && M > 0 && n >= 0, "gather_rows: bad argument");
+  HHFM_REQUIRE(K == 1 || (K > 0 && K % 4 == 0), "gather_rows: K must be 1 or a multiple of 4");
+  if (n == 0) return HHFM_OK;
+  const int64_t work = K == 1 ? n : n * (K >> 2);
+  const int64_t need = (work + 255) / 256, cap = (int64_t)sm_count() * 8;
+  gather_rows_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(table, ids, n, (int)K, out, zero_src);
+  return check_launch("gather_rows_kernel");
+}
+
+extern "C" int hhfm_touch_rows(const int32_t* ids, int64_t n, int32_t* stamp_arr, int32_t stamp, int32_t* rows, int32_t* count,
+                               hhfm_stream_t stream) {
+  HHFM_REQUIRE(ids && stamp_arr && rows && count && n >= 0, "touch_rows: bad argument");
+  if (n == 0) return HHFM_OK;
+  const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  touch_rows_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(ids, n, stamp_arr, stamp, rows, count);
+  return check_launch("touch_rows_kernel");
 }

@@ -194,3 +194,31 @@ def allreduce_metrics(codes, group=None):
     if cnt == 0:
         return [float("nan")] * 3
     return [float(local[0]) / cnt, float(local[1]) / cnt, float(local[2]) / cnt]
+
+
+def allgather_rows(ids, cols, group=None):
+    """Coalesced-sparse exchange: every rank contributes `ids` [n] (int32, unique) and per-row payloads
+    `cols` = list of tensors with leading dimension n; returns, for every rank r in rank order, (ids_r, [payload_r, ...]).
+    The counts differ between ranks, so the lists travel padded to the longest one (one host sync to learn the counts).
+    Pure torch.distributed plumbing: works on gloo (CPU tests) and NCCL alike."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    n = int(ids.shape[0])
+    cnt = torch.tensor([n], dtype=torch.int64, device=ids.device)
+    counts = [torch.zeros_like(cnt) for _ in range(ws)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    maxc = max(counts)
+    if maxc == 0:
+        return [(ids[:0], [c[:0] for c in cols]) for _ in range(ws)]
+
+    def gather(t, fill):
+        pad = torch.full((maxc,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+        pad[:n] = t
+        outs = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(outs, pad, group=group)
+        return outs
+
+    g_ids = gather(ids, -1)
+    g_cols = [gather(c, 0) for c in cols]
+    return [(g_ids[r][:counts[r]], [g[r][:counts[r]] for g in g_cols]) for r in range(ws)]

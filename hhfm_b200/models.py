@@ -48,6 +48,8 @@ class Session:
 class _Base:
     """Shared device state: embedding table, gradient arena, loss partial buffers, staging, optimizer."""
 
+    _supports_sparse_dp = False     # True where fit_device ends in _apply_table(sparse_ok=True) with touched-row tracking
+
     def _setup(self, features_M, K, seed, with_bias, optimizer_type, learning_rate, acc0, lamda):
         self.device = require_cuda()
         if K % 4 != 0 or K > 512:
@@ -79,6 +81,7 @@ class _Base:
         self._f32_stage = Staging(torch.float32, self.device)
         self._topn = TopN(self.device)
         self._dp_group = None
+        self._dp_sparse = False
         self._version = 0           # bumped whenever the weights change (invalidates cached top-N item operands)
         self.topn_method = "auto"   # "auto" | "exact" | "tc"
         self.deterministic = False
@@ -110,10 +113,15 @@ class _Base:
         return self._hot
 
     # ---- data parallel: batch rows sharded across ranks, one all-reduce of the arena ----
-    def enable_data_parallel(self, group=None, p2p="auto"):
+    def enable_data_parallel(self, group=None, p2p="auto", sparse="auto"):
         """Batch rows sharded across the ranks of `group`, weights replicated.  On CUDA the gradient
         exchange is fused into the optimizer over NVLink peer memory (dist.PeerArena, csrc/p2p.cu); `p2p=False`, or a box
-        where CUDA IPC is unavailable, falls back to one NCCL all-reduce of the arena per step."""
+        where CUDA IPC is unavailable, falls back to one NCCL all-reduce of the arena per step.
+
+        `sparse`: exchange the COALESCED touched rows (row id + gradient row, all-gather) instead of the dense [M, K]
+        gradient, then add the ranks' lists in rank order and run the touched-row optimizer on the union.  Only for
+        lamda == 0 (IndexedSlices semantics; a dense L2 term touches every row anyway).  "auto": tables above 64 MB
+        (SURVEY 8e); `HHFM_DP_SPARSE=0/1` forces either."""
         import torch.distributed as dist
         from . import dist as hd
         if not dist.is_initialized():
@@ -124,6 +132,16 @@ class _Base:
         self._peer = None
         ws = dist.get_world_size(self._dp_group)
         import os
+        env_s = os.environ.get("HHFM_DP_SPARSE")
+        if env_s in ("0", "1"):
+            sparse = env_s == "1"
+        elif sparse == "auto":
+            sparse = self._M * self._K * 4 > (64 << 20)
+        self._dp_sparse = bool(sparse) and self._lamda <= 0 and ws > 1 and self._supports_sparse_dp
+        if self._dp_sparse:
+            if self._opt.kind == "momentum":
+                raise NotImplementedError("sparse Momentum under data parallelism is not implemented")
+            return
         env = os.environ.get("HHFM_DP_P2P")               # 0 / 1 force the NCCL all-reduce / the peer-memory exchange
         if env == "0":
             p2p = False
@@ -154,6 +172,9 @@ class _Base:
         arenas itself, otherwise an all-reduce of the arena."""
         if self._dp_group is None:
             return
+        if self._dp_sparse:
+            self._exchange_sparse_rows()
+            return
         if self._peer is not None:
             # publish this rank's loss as ONE float (arena slot after gb0): the peers then read n_ranks floats instead of
             # n_ranks x 2048 partial slots.  The arena itself stays ordinary device memory (scattering straight into the
@@ -166,6 +187,36 @@ class _Base:
         else:
             import torch.distributed as dist
             dist.all_reduce(self._arena, group=self._dp_group)
+
+    def _exchange_sparse_rows(self):
+        """SURVEY 8e, tables too large for a dense all-reduce: all-gather the coalesced (row id, gradient row) lists, clear
+        the local rows, add every rank's list (own one included) in rank order -- each row then holds the same fp32 sum on
+        every rank, so the replicas stay bit-identical -- and extend the touched-row list to the union for the optimizer.
+        The small dense tail of the arena (scalar bias gradient, loss partials) is all-reduced."""
+        import torch.distributed as dist
+        from . import dist as hd
+        t = self._touch
+        n = int(t.count.item())
+        ids = t.rows[:n]
+        st = cur_stream()
+        rows = torch.empty(n, self._K, dtype=torch.float32, device=self.device)
+        _lib.call("hhfm_gather_rows", ptr(self._gV), ptr(ids), n, self._K, self._M, ptr(rows), 1, st)
+        cols = [rows]
+        if self._with_bias_grad:
+            gb = torch.empty(n, dtype=torch.float32, device=self.device)
+            _lib.call("hhfm_gather_rows", ptr(self._gb), ptr(ids), n, 1, self._M, ptr(gb), 1, st)
+            cols.append(gb)
+        for ids_r, cols_r in hd.allgather_rows(ids, cols, self._dp_group):
+            m = int(ids_r.shape[0])
+            if m == 0:
+                continue
+            ids_r = ids_r.contiguous()
+            _lib.call("hhfm_scatter_add_rows", ptr(ids_r), ptr(cols_r[0].contiguous()), m, self._K, ptr(self._gV), self._M, st)
+            if self._with_bias_grad:
+                _lib.call("hhfm_scatter_add_rows", ptr(ids_r), ptr(cols_r[1].contiguous()), m, 1, ptr(self._gb), self._M, st)
+            _lib.call("hhfm_touch_rows", ptr(ids_r), m, ptr(t.stamp_arr), t.stamp, ptr(t.rows), ptr(t.count), st)
+        n_v, n_b, _ = self._arena_layout
+        dist.all_reduce(self._arena[n_v + n_b:], group=self._dp_group)
 
     def _apply_arena_dense(self, name, w, g, lamda, sq):
         """Dense optimizer step for a tensor whose gradient `g` is a slice of the arena."""
@@ -205,7 +256,7 @@ class _Base:
 
     def _touch_args(self, extra=False):
         """Touched-row tracking is only paid for when a *_rows optimizer will consume the list."""
-        need = self._dp_group is None and (self._lamda <= 0 or extra)
+        need = (self._dp_group is None or self._dp_sparse) and (self._lamda <= 0 or extra)
         if not need:
             return (None, 0, None, None)
         self._touch.begin_step()
@@ -217,7 +268,7 @@ class _Base:
         lamda == 0: IndexedSlices semantics; Adagrad/SGD/Adam dense kernels are exactly equivalent on untouched
         rows (g = 0), Momentum needs the touched-row list."""
         V = self.weights["feature_embeddings"]
-        use_rows = sparse_ok and self._lamda <= 0 and self._dp_group is None
+        use_rows = sparse_ok and self._lamda <= 0 and (self._dp_group is None or self._dp_sparse)
         if use_rows:
             self._opt.apply_rows("feature_embeddings", V, self._gV, self._touch.rows, self._touch.count, self._K)
             return False
@@ -278,6 +329,8 @@ class _Base:
 # ====================================================================================================
 class FM(_Base):
     """Factorization machine, Newcode/FM.py:59-198."""
+
+    _supports_sparse_dp = True
 
     interaction = 0
 
@@ -459,6 +512,8 @@ class MF(FM):
 class _PairRank(_Base):
     """Shared HHFM / BPR machinery: record packing, fused forward+backward kernel, scoring, top-N."""
 
+    _supports_sparse_dp = True
+
     def _groups(self):
         raise NotImplementedError
 
@@ -620,6 +675,8 @@ class BPR(_PairRank):
 # ====================================================================================================
 class AFM(FM):
     """Attentional FM, Newcode/AFM.py:63-246.  hidden_factor = [attention size A, embedding size K] (AFM.py:39)."""
+
+    _supports_sparse_dp = False
 
     def __init__(self, n_user, n_item, features_M, attention, hidden_factor, activation_function, learning_rate,
                  lamda_attention, keep, optimizer_type, decay, valid_dimension, random_seed=2016):

@@ -288,6 +288,15 @@ int hhfm_pairrank_bwd(const int32_t* idx, int64_t B, int64_t stride, int32_t n_c
 int hhfm_scatter_add_rows(const int32_t* rows, const float* src, int64_t n, int64_t K, float* dst, int64_t M,
                           hhfm_stream_t stream);
 
+/* Coalesced-sparse gradient exchange (data-parallel training of tables too large for a dense all-reduce):
+ *   hhfm_gather_rows  out[i, :] = table[ids[i], :] (K == 1 or K % 4 == 0); zero_src != 0 clears the source rows, so that the
+ *                     ranks' row lists (own one included) can be added back in rank order -> bit-identical replicas;
+ *   hhfm_touch_rows   appends ids not yet stamped in this step to the touched-row list the *_rows optimizers consume. */
+int hhfm_gather_rows(float* table, const int32_t* ids, int64_t n, int64_t K, int64_t M, float* out, int32_t zero_src,
+                     hhfm_stream_t stream);
+int hhfm_touch_rows(const int32_t* ids, int64_t n, int32_t* stamp_arr, int32_t stamp, int32_t* rows, int32_t* count,
+                    hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  optimizers with TF-1.x semantics (FM.py:129-136; BPR.py:93 / MF.py:104 use acc0 = 1e-8)
  *   adagrad : acc += g^2; w -= lr*g/sqrt(acc)                (no epsilon)

@@ -102,3 +102,33 @@ def _metric_shards(rank, world):
 
 def test_sharded_metric_walk_allreduce_equals_the_single_process_average():
     assert all(run2(_metric_shards))
+
+
+def _sparse_rows(rank, world):
+    """Coalesced-sparse exchange: each rank holds the touched rows of its shard's gradient; after the all-gather
+    of the padded (id, row, bias) lists, adding them in rank order reproduces the dense gradient of the full batch on every
+    rank -- including a rank whose list is empty."""
+    from hhfm_b200 import dist as hd
+    rng = np.random.default_rng(3)
+    M, K = 50, 4
+    counts = [7, 0] if world == 2 else [5] * world
+    full = np.zeros((M, K), np.float32); fullb = np.zeros(M, np.float32)
+    lists = []
+    for r in range(world):
+        ids = rng.choice(M, counts[r], replace=False).astype(np.int32)
+        rows = rng.normal(0, 1, (counts[r], K)).astype(np.float32); b = rng.normal(0, 1, counts[r]).astype(np.float32)
+        lists.append((ids, rows, b))
+    acc = np.zeros((M, K), np.float32); accb = np.zeros(M, np.float32)
+    ids, rows, b = lists[rank]
+    got = hd.allgather_rows(torch.from_numpy(ids), [torch.from_numpy(rows), torch.from_numpy(b)])
+    ok = len(got) == world
+    for r, (ids_r, cols_r) in enumerate(got):
+        ok = ok and ids_r.numpy().tolist() == lists[r][0].tolist()
+        np.add.at(acc, ids_r.numpy(), cols_r[0].numpy()); np.add.at(accb, ids_r.numpy(), cols_r[1].numpy())
+    for ids_r, rows_r, b_r in lists:
+        np.add.at(full, ids_r, rows_r); np.add.at(fullb, ids_r, b_r)
+    return bool(ok and (acc == full).all() and (accb == fullb).all())
+
+
+def test_coalesced_sparse_row_exchange_rebuilds_the_full_gradient():
+    assert all(run2(_sparse_rows))

@@ -72,3 +72,84 @@ def test_data_parallel_step_and_sharded_topk(cuda):
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
         assert ret[r] == ((True, True, True, True), (True, True, True, True), True), (r, ret[r])
+
+
+def _sparse_worker(rank, world, port, ret):
+    """Coalesced-sparse gradient exchange: lamda = 0 models, rows sharded, every rank ends on the weights of the
+    single-process step on the full batch; replicas bit-identical; rows nobody touched do not move."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hhfm_b200 import dist as hd
+        from hhfm_b200.models import FM, OUR
+        from oracle import hhfm_oracle as O
+        rng = np.random.default_rng(5)
+        n_user, n_item, M, K, B = 300, 700, 1200, 64, 4096
+        out = []
+        # ---- HHFM (pair ranking, no bias), lamda = 0 ----
+        fc = 4
+        X = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B)], axis=1)
+        F1 = rng.integers(n_user + n_item, M - 100, (B, fc))
+        Y = n_user + rng.integers(0, n_item, (B, 10))
+        lo, hi = hd.shard_range(B, rank, world)
+        model = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.0, 'AdagradOptimizer', True, False)
+        model.enable_data_parallel(sparse=True)
+        assert model._dp_sparse == (world > 1)
+        V = model.get_weights()["feature_embeddings"].copy()
+        loss = model.partial_fit({"X": X[lo:hi], "F1": F1[lo:hi], "Y": Y[lo:hi]})
+        loss_ref, _, _, dV = O.pairrank_loss_grads(V, X, Y, F1, None, (0, 0, 0), 0.0)
+        V1, _ = O.adagrad_dense(V, np.full_like(V, 0.1), dV, 0.1)
+        got = model.get_weights()["feature_embeddings"]
+        upd = V1 - V
+        ok = abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
+        ok = ok and bool(np.all(np.abs(got - V1) <= 1e-4 * np.maximum(np.abs(upd), np.sqrt(np.mean(upd ** 2)))))
+        ok = ok and bool((got[M - 100:] == V[M - 100:]).all())                          # untouched rows
+        for step in range(3):
+            r2 = np.random.default_rng(200 + step)
+            Xs = np.stack([r2.integers(0, n_user, B), n_user + r2.integers(0, n_item, B)], axis=1)
+            Ys = n_user + r2.integers(0, n_item, (B, 10)); Fs = r2.integers(n_user + n_item, M - 100, (B, fc))
+            model.partial_fit({"X": Xs[lo:hi], "F1": Fs[lo:hi], "Y": Ys[lo:hi]})
+        w = model.weights["feature_embeddings"]
+        gathered = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(gathered, w)
+        out.append((bool(ok), all(bool(torch.equal(gathered[0], g)) for g in gathered)))
+        # ---- FM (pointwise, feature bias + scalar bias) ----
+        F = 6
+        Xf = np.concatenate([X, rng.integers(n_user + n_item, M - 100, (B, F - 2))], axis=1)
+        Yf = rng.choice([1.0, 0.0], (B, 1)).astype(np.float32)
+        fm = FM(F, M, n_user, n_item, K, 0.1, 0.0, 1, 'AdagradOptimizer', 0, 0)
+        fm.enable_data_parallel(sparse=True)
+        w0 = fm.get_weights()
+        loss = fm.partial_fit({"X": Xf[lo:hi], "Y": Yf[lo:hi]})
+        loss_ref, _, dV, db, db0, _ = O.fm_loss_grads(Xf, Yf, w0["feature_embeddings"], w0["feature_bias"], w0["bias"], 0.0)
+        V1, _ = O.adagrad_dense(w0["feature_embeddings"], np.full_like(w0["feature_embeddings"], 0.1), dV, 0.1)
+        b1, _ = O.adagrad_dense(w0["feature_bias"], np.full_like(w0["feature_bias"], 0.1), np.asarray(db).reshape(-1, 1), 0.1)
+        got = fm.get_weights()
+        upd = V1 - w0["feature_embeddings"]; updb = b1 - w0["feature_bias"]
+        ok = abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
+        ok = ok and bool(np.all(np.abs(got["feature_embeddings"] - V1) <= 1e-4 * np.maximum(np.abs(upd), np.sqrt(np.mean(upd ** 2)))))
+        ok = ok and bool(np.all(np.abs(got["feature_bias"] - b1) <= 1e-4 * np.maximum(np.abs(updb), np.sqrt(np.mean(updb ** 2)))))
+        ok = ok and bool((got["feature_embeddings"][M - 100:] == w0["feature_embeddings"][M - 100:]).all())
+        for step in range(2):
+            fm.partial_fit({"X": Xf[lo:hi][::-1].copy(), "Y": Yf[lo:hi][::-1].copy()})
+        same = True
+        for k in ("feature_embeddings", "feature_bias"):
+            w = fm.weights[k]
+            gathered = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(gathered, w)
+            same = same and all(bool(torch.equal(gathered[0], g)) for g in gathered)
+        out.append((bool(ok), same))
+        ret[rank] = tuple(out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_coalesced_sparse_exchange(cuda):
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 2)
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_sparse_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] == ((True, True), (True, True)), (r, ret[r])
