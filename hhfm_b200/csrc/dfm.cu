@@ -549,7 +549,8 @@ static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t, int fo
 
 // first > 0 (inference only): X_first is already in the workspace (item-separable evaluator); its lo half is made here
 static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
-                          const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st, int first = 0) {
+                          const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st, int first = 0,
+                          bool first_has_lo = false) {
   int rc;
   for (int i = first; i < lo.L; i++)
     if ((rc = tf_prep_weight(params + lo.w_off[i], lo.d[i], lo.d[i + 1], ws + t.w[i], ws + t.wlo[i], t.ldp[i], ws + t.wt[i],
@@ -559,7 +560,7 @@ static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float*
     if ((rc = tf_gather_split_transpose(idx, B, (int)F, (int)K, V, ws + t.x[0], t.ldx[0], ws + t.xlo[0], train ? ws + t.xt[0] : nullptr,
                                         train ? ws + t.xtlo[0] : nullptr, st)))
       return rc;
-  } else if (first < lo.L) {
+  } else if (first < lo.L && !first_has_lo) {
     if ((rc = tf_split_transpose(ws + t.x[first], B, lo.d[first], t.ldx[first], ws + t.xlo[first], nullptr, nullptr, st))) return rc;
   }
   for (int i = first; i < lo.L; i++) {
@@ -655,9 +656,14 @@ __global__ void __launch_bounds__(256) dfm_topn_item_kernel(const DfmTopnArgs a)
   }
 }
 
-// X1[c*N + n, :] = relu(U[c] + T[n]) (padding columns stay 0: U and T are 0 there)
+// X1[c*N + n, :] = relu(U[c] + T[n]) (padding columns stay 0: U and T are 0 there); X1lo (tensor-core path) = its tf32 lo part
+__device__ __forceinline__ float dfm_tf32_lo(float x) {      // = tf32_lo of dfm_tc.cu
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+
 __global__ void __launch_bounds__(256) dfm_topn_h1_kernel(const float* __restrict__ U, const float* __restrict__ T, int64_t C, int64_t N,
-                                                          int64_t ld1, float* __restrict__ X1, int64_t ldx) {
+                                                          int64_t ld1, float* __restrict__ X1, float* __restrict__ X1lo, int64_t ldx) {
   const int64_t v4 = ld1 >> 2;
   const int64_t total = C * N * v4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -665,8 +671,9 @@ __global__ void __launch_bounds__(256) dfm_topn_h1_kernel(const float* __restric
     const int64_t c = s / N, n = s % N;
     const float4 u = __ldg(reinterpret_cast<const float4*>(U + c * ld1) + j);
     const float4 t = __ldg(reinterpret_cast<const float4*>(T + n * ld1) + j);
-    reinterpret_cast<float4*>(X1 + s * ldx)[j] =
-        make_float4(fmaxf(u.x + t.x, 0.f), fmaxf(u.y + t.y, 0.f), fmaxf(u.z + t.z, 0.f), fmaxf(u.w + t.w, 0.f));
+    const float4 h = make_float4(fmaxf(u.x + t.x, 0.f), fmaxf(u.y + t.y, 0.f), fmaxf(u.z + t.z, 0.f), fmaxf(u.w + t.w, 0.f));
+    reinterpret_cast<float4*>(X1 + s * ldx)[j] = h;
+    if (X1lo) reinterpret_cast<float4*>(X1lo + s * ldx)[j] = make_float4(dfm_tf32_lo(h.x), dfm_tf32_lo(h.y), dfm_tf32_lo(h.z), dfm_tf32_lo(h.w));
   }
 }
 
@@ -951,12 +958,12 @@ extern "C" int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int
   if (dfm_use_tc(K)) {
     DfmTcLayout t;
     dfm_tc_layout(B, lo, t, 1);
-    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + t.x[1], t.ldx[1]);
+    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + t.x[1], main_ws + t.xlo[1], t.ldx[1]);
     if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
-    if ((rc = dfm_tc_forward(nullptr, B, F, V, K, params, lo, t, main_ws, false, st, 1))) return rc;
+    if ((rc = dfm_tc_forward(nullptr, B, F, V, K, params, lo, t, main_ws, false, st, 1, true))) return rc;
     H = main_ws + t.x[lo.L]; ldh = t.ldx[lo.L];
   } else {
-    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + lo.h_off[1], lo.ld[1]);
+    dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + lo.h_off[1], nullptr, lo.ld[1]);
     if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
     if ((rc = dfm_forward(nullptr, B, F, V, K, params, lo, main_ws, st, 1))) return rc;
     H = main_ws + lo.h_off[lo.L]; ldh = lo.ld[lo.L];
