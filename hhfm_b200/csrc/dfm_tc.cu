@@ -311,6 +311,67 @@ __global__ void split_transpose_kernel(const float* X, const float* mask, float*
   }
 }
 
+// The same pass with 16-byte accesses: a CTA owns 32 rows x 128 columns; thread (row = t / 8, g = t % 8) reads the float4s
+// g, g + 8, g + 16, g + 24 of its row (8 threads = 128 contiguous bytes), writes Xout / Xlo the same way, parks the values in a
+// padded shared tile, and thread (column = t / 8 + 32 j, q = t % 8) then writes samples 4q .. 4q+3 of that column as one float4
+// of the k-blocked transposed panels.  Requires ld % 4 == 0, 16-byte aligned blocks and (gather form) gK % 4 == 0.
+__global__ void __launch_bounds__(256) split_transpose_vec_kernel(const float* X, const float* mask, float* Xout, int64_t rows, int cols,
+                                                                  int64_t ld, float* Xlo, float* __restrict__ XT,
+                                                                  float* __restrict__ XTlo, const int32_t* __restrict__ gidx, int gF,
+                                                                  int gK) {
+  __shared__ float tile[32][129];
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 128;
+  {
+    const int rl = t >> 3, g = t & 7;
+    const int64_t r = r0 + rl;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int cl = (g + 8 * j) * 4;
+      const int c = c0 + cl;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows && c < cols) {            // cols <= ld and ld % 4 == 0: the float4 stays inside the row's padded block
+        if (gidx) {
+          const int f = c / gK;
+          v = __ldg(reinterpret_cast<const float4*>(X + (int64_t)__ldg(gidx + r * gF + f) * gK + (c - f * gK)));
+          *reinterpret_cast<float4*>(Xout + r * ld + c) = v;
+        } else {
+          v = *reinterpret_cast<const float4*>(X + r * ld + c);
+        }
+        if (mask) {
+          const float4 m = *reinterpret_cast<const float4*>(mask + r * ld + c);
+          v = make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+          *reinterpret_cast<float4*>(Xout + r * ld + c) = v;
+        }
+        if (Xlo) *reinterpret_cast<float4*>(Xlo + r * ld + c) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
+      tile[rl][cl] = v.x; tile[rl][cl + 1] = v.y; tile[rl][cl + 2] = v.z; tile[rl][cl + 3] = v.w;
+    }
+  }
+  if (XT == nullptr) return;
+  __syncthreads();
+  const int q = t & 7;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int cl = (t >> 3) + 32 * j;
+    const int c = c0 + cl;
+    if (c < cols) {
+      const float4 v = make_float4(tile[4 * q][cl], tile[4 * q + 1][cl], tile[4 * q + 2][cl], tile[4 * q + 3][cl]);   // zero for rows >= `rows`
+      const int64_t o = ((int64_t)blockIdx.x * cols + c) * 32 + 4 * q;
+      *reinterpret_cast<float4*>(XT + o) = v;
+      if (XTlo) *reinterpret_cast<float4*>(XTlo + o) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+    }
+  }
+}
+
+static bool split_vec_ok(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f, int64_t ld) {
+  const char* env = getenv("HHFM_DFM_SPLIT_VEC");           // 0 = the 32 x 32 scalar tiles (A/B measurements)
+  if (env && env[0] == '0') return false;
+  const uintptr_t all = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)f;
+  return (ld & 3) == 0 && (all & 15) == 0;
+}
+
 // X0[b, f*K + k] = V[idx[b, f], k]: the flattened embeddings as a dense [B, F*K] matrix (the TMA operand of layer 0)
 __global__ void __launch_bounds__(256) gather_x0_kernel(const int32_t* __restrict__ idx, int64_t B, int F, int K,
                                                         const float* __restrict__ V, float* __restrict__ X0, int64_t ld) {
@@ -506,6 +567,11 @@ int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float
                                                                             reinterpret_cast<float4*>(Xlo), n4);
     return check_launch("split_lo_vec_kernel");
   }
+  if (split_vec_ok(X, mask, Xout, Xlo, XT, XTlo, ld)) {
+    dim3 gridv((unsigned)((rows + 31) / 32), (unsigned)((cols + 127) / 128));
+    split_transpose_vec_kernel<<<gridv, 256, 0, st>>>(X, mask, Xout, rows, cols, ld, Xlo, XT, XTlo, nullptr, 0, 0);
+    return check_launch("split_transpose_vec_kernel");
+  }
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
   split_transpose_kernel<<<grid, 256, 0, st>>>(X, mask, Xout, rows, cols, ld, Xlo, XT, XTlo, nullptr, 0, 0);
   return check_launch("split_transpose_kernel");
@@ -514,6 +580,11 @@ int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float
 // X0 = flattened embeddings V[idx] [B, F*K] with its lo part and (optionally) the k-blocked transposes, in one pass
 int tf_gather_split_transpose(const int32_t* idx, int64_t B, int F, int K, const float* V, float* X0, int64_t ld, float* Xlo,
                               float* XT, float* XTlo, cudaStream_t st) {
+  if ((K & 3) == 0 && split_vec_ok(V, nullptr, X0, Xlo, XT, XTlo, ld)) {
+    dim3 gridv((unsigned)((B + 31) / 32), (unsigned)((F * K + 127) / 128));
+    split_transpose_vec_kernel<<<gridv, 256, 0, st>>>(V, nullptr, X0, B, F * K, ld, Xlo, XT, XTlo, idx, F, K);
+    return check_launch("split_transpose_vec_kernel(gather)");
+  }
   dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F * K + 31) / 32));
   split_transpose_kernel<<<grid, 256, 0, st>>>(V, nullptr, X0, B, F * K, ld, Xlo, XT, XTlo, idx, F, K);
   return check_launch("split_transpose_kernel(gather)");
