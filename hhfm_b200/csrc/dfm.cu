@@ -550,7 +550,7 @@ static void dfm_tc_layout(int64_t B, const DfmLayout& lo, DfmTcLayout& t, int fo
 // first > 0 (inference only): X_first is already in the workspace (item-separable evaluator); its lo half is made here
 static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float* V, int64_t K, const float* params,
                           const DfmLayout& lo, const DfmTcLayout& t, float* ws, bool train, cudaStream_t st, int first = 0,
-                          bool first_has_lo = false) {
+                          bool first_has_lo = false, const float* proj_last = nullptr) {
   int rc;
   for (int i = first; i < lo.L; i++)
     if ((rc = tf_prep_weight(params + lo.w_off[i], lo.d[i], lo.d[i + 1], ws + t.w[i], ws + t.wlo[i], t.ldp[i], ws + t.wt[i],
@@ -569,6 +569,11 @@ static int dfm_tc_forward(const int32_t* idx, int64_t B, int64_t F, const float*
     g.B = ws + t.wt[i]; g.B_lo = ws + t.wtlo[i]; g.ldb = t.ldt[i];
     g.M = (int)B; g.N = lo.d[i + 1]; g.K = lo.d[i];
     g.epi = TF_EPI_BIAS_RELU; g.C = ws + t.x[i + 1]; g.ldc = t.ldx[i + 1]; g.bias = params + lo.b_off[i];
+    if (proj_last != nullptr && i == lo.L - 1) {
+      // evaluator: the last hidden layer is only ever multiplied by the projection -- keep relu(H W + b) . proj as
+      // tf_proj_partials() partial sums per row in the H_L block instead of writing and re-reading H_L
+      g.epi = TF_EPI_BIAS_RELU_PROJ; g.proj = proj_last;
+    }
     if ((rc = tf_gemm(g, st))) return rc;
     if (i + 1 < lo.L) {   // H_L is consumed by the head kernel as is (and replaced by dZ_L, split afterwards)
       const bool need_t = train;
@@ -678,8 +683,9 @@ __global__ void __launch_bounds__(256) dfm_topn_h1_kernel(const float* __restric
 }
 
 // one warp per (context, item): first order + second order + last hidden layer, through concat_projection (DFM.py:138-143)
+// n_part > 0: H holds n_part partial sums of H_L . proj3 per row (TF_EPI_BIAS_RELU_PROJ) instead of H_L itself
 __global__ void __launch_bounds__(256) dfm_topn_head_kernel(const DfmTopnArgs a, const float* __restrict__ H, int64_t ldh, int D,
-                                                            const float* __restrict__ cbias, float* __restrict__ scores) {
+                                                            int n_part, const float* __restrict__ cbias, float* __restrict__ scores) {
   const int lane = threadIdx.x & 31, K = a.K;
   const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -699,7 +705,15 @@ __global__ void __launch_bounds__(256) dfm_topn_head_kernel(const DfmTopnArgs a,
       part = fmaf(0.5f * (sv * sv - q), __ldg(p2 + k), part);
     }
     const float* hrow = H + s * ldh;
-    for (int j = lane; j < D; j += 32) part = fmaf(hrow[j], __ldg(p3 + j), part);
+    if (n_part > 0) {
+      if (lane == 0) {
+        float d = 0.f;
+        for (int q = 0; q < n_part; q++) d += hrow[q];
+        part += d;
+      }
+    } else {
+      for (int j = lane; j < D; j += 32) part = fmaf(hrow[j], __ldg(p3 + j), part);
+    }
     if (lane == 0) part += __ldg(a.fo + c) + __ldg(a.fbias + a.item_base + n) * pitem;
     const float out = warp_sum(part) + cb;
     if (lane == 0) scores[s] = out;
@@ -954,14 +968,19 @@ extern "C" int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int
   }
   const float* H;
   int64_t ldh;
+  int n_part = 0;
   const int h1_grid = (int)std::min<int64_t>((B * (ld1 >> 2) + 255) / 256, (int64_t)sm_count() * 16);
   if (dfm_use_tc(K)) {
     DfmTcLayout t;
     dfm_tc_layout(B, lo, t, 1);
     dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + t.x[1], main_ws + t.xlo[1], t.ldx[1]);
     if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
-    if ((rc = dfm_tc_forward(nullptr, B, F, V, K, params, lo, t, main_ws, false, st, 1, true))) return rc;
+    const bool fuse_proj = lo.L >= 2 && tf_proj_partials(lo.d[lo.L]) <= t.ldx[lo.L];
+    if ((rc = dfm_tc_forward(nullptr, B, F, V, K, params, lo, t, main_ws, false, st, 1, true,
+                             fuse_proj ? params + lo.proj_off + F + K : nullptr)))
+      return rc;
     H = main_ws + t.x[lo.L]; ldh = t.ldx[lo.L];
+    n_part = fuse_proj ? tf_proj_partials(lo.d[lo.L]) : 0;
   } else {
     dfm_topn_h1_kernel<<<h1_grid, 256, 0, st>>>(a.U, a.T, C, N, ld1, main_ws + lo.h_off[1], nullptr, lo.ld[1]);
     if ((rc = check_launch("dfm_topn_h1_kernel"))) return rc;
@@ -969,6 +988,6 @@ extern "C" int hhfm_dfm_topn_scores(const int32_t* rows, int64_t row_stride, int
     H = main_ws + lo.h_off[lo.L]; ldh = lo.ld[lo.L];
   }
   const int head_grid = (int)std::min<int64_t>((B + 7) / 8, (int64_t)sm_count() * 8);
-  dfm_topn_head_kernel<<<head_grid, 256, 0, st>>>(a, H, ldh, lo.d[lo.L], params + lo.cbias_off, scores);
+  dfm_topn_head_kernel<<<head_grid, 256, 0, st>>>(a, H, ldh, lo.d[lo.L], n_part, params + lo.cbias_off, scores);
   return check_launch("dfm_topn_head_kernel");
 }

@@ -51,6 +51,7 @@ struct TfKernelArgs {
   float* C;
   int64_t ldc;
   const float* bias;
+  const float* proj;
   const float* mask;
   int64_t ldmask;
   const int32_t* idx;
@@ -216,6 +217,22 @@ __global__ void __launch_bounds__(kTfThreads, 1) tf32x3_gemm_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 16; i += 4) red_add_v4(dstp[j] + i, make_float4(accr[j][i], accr[j][i + 1], accr[j][i + 2], accr[j][i + 3]));
         }
+        continue;
+      }
+      if (a.epi == TF_EPI_BIAS_RELU_PROJ) {
+        // this thread's share of relu(row + bias) . proj over its 16-column chunks; one plain store per (row, n-tile, group)
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = sub + 4 * j;
+          if (c >= n_chunks) continue;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int n = nt * a.bn + c * 16 + i;
+            if (n < a.N) p = fmaf(fmaxf(accr[j][i] + __ldg(a.bias + n), 0.f), __ldg(a.proj + n), p);
+          }
+        }
+        if (m < a.M && has_work) a.C[(int64_t)m * a.ldc + nt * 4 + sub] = p;
         continue;
       }
 #pragma unroll
@@ -467,6 +484,8 @@ int tf_pick_bn(int N) {
   return best;
 }
 
+int tf_proj_partials(int N) { return 4 * ((N + tf_pick_bn(N) - 1) / tf_pick_bn(N)); }
+
 int tf_gemm(const TfGemm& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return HHFM_OK;
   HHFM_REQUIRE(g.k_blocked || ((g.lda % 4) == 0 && (g.ldb % 4) == 0), "tf_gemm: operand leading dimensions must be multiples of 4 floats");
@@ -507,7 +526,9 @@ int tf_gemm(const TfGemm& g, cudaStream_t st) {
   a.stage_bytes = 2 * kTfABytes + 2 * a.bn * 128;
   a.n_stages = kTfSmemBudget / a.stage_bytes;
   if (a.n_stages > kTfMaxStages) a.n_stages = kTfMaxStages;
-  a.epi = g.epi; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.mask = g.mask; a.ldmask = g.ldmask;
+  a.epi = g.epi; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.proj = g.proj; a.mask = g.mask; a.ldmask = g.ldmask;
+  HHFM_REQUIRE(g.epi != TF_EPI_BIAS_RELU_PROJ || (g.proj && g.bias && g.ldc >= 4 * a.n_ntiles),
+               "tf_gemm: the projection epilogue needs bias, proj and ldc >= 4 * n-tiles");
   if (g.epi == TF_EPI_ATOMIC) {
     HHFM_REQUIRE(g.scratch && ((uintptr_t)g.scratch & 15) == 0, "tf_gemm: split-K needs a 16-byte aligned scratch buffer");
     HHFM_REQUIRE((int64_t)a.n_units * kTfM * a.bn <= g.scratch_floats, "tf_gemm: split-K scratch too small");
@@ -516,7 +537,8 @@ int tf_gemm(const TfGemm& g, cudaStream_t st) {
   a.idx = g.idx; a.F = g.F; a.Kemb = g.Kemb; a.hot = g.hot; a.err = nullptr;
   HHFM_REQUIRE(g.epi != TF_EPI_MASK, "tf_gemm: the relu mask is applied by tf_split_transpose, not by the GEMM epilogue");
   HHFM_REQUIRE(g.epi != TF_EPI_SCATTER || g.Kemb % 16 == 0, "tf_gemm: the scatter epilogue needs an embedding size that is a multiple of 16");
-  HHFM_REQUIRE(g.epi == TF_EPI_SCATTER || g.epi == TF_EPI_ATOMIC || ((g.ldc % 4) == 0 && ((uintptr_t)g.C & 15) == 0),
+  HHFM_REQUIRE(g.epi == TF_EPI_SCATTER || g.epi == TF_EPI_ATOMIC || g.epi == TF_EPI_BIAS_RELU_PROJ ||
+                   ((g.ldc % 4) == 0 && ((uintptr_t)g.C & 15) == 0),
                "tf_gemm: C must be 16-byte aligned with ldc %% 4 == 0");
   CUtensorMap tA, tAl, tB, tBl;
   int rc;

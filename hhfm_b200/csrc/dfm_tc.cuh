@@ -4,7 +4,7 @@
 
 namespace hhfm {
 
-enum { TF_EPI_STORE = 0, TF_EPI_BIAS_RELU = 1, TF_EPI_MASK = 2, TF_EPI_ATOMIC = 3, TF_EPI_SCATTER = 4 };
+enum { TF_EPI_STORE = 0, TF_EPI_BIAS_RELU = 1, TF_EPI_MASK = 2, TF_EPI_ATOMIC = 3, TF_EPI_SCATTER = 4, TF_EPI_BIAS_RELU_PROJ = 5 };
 
 // C[M,N] (epilogue) = A[M,K] . B[N,K]^T, all row-major with the K index contiguous; *_lo = x - tf32(x) of the same shape.
 struct TfGemm {
@@ -18,7 +18,10 @@ struct TfGemm {
   int epi;
   float* C;              // EPI_SCATTER: the embedding gradient table
   int64_t ldc;
-  const float* bias;     // EPI_BIAS_RELU
+  const float* bias;     // EPI_BIAS_RELU, EPI_BIAS_RELU_PROJ
+  const float* proj;     // EPI_BIAS_RELU_PROJ [N]: instead of relu(A.B^T + bias) itself, each thread stores its share of
+                         // relu(...) . proj: C[m, nt*4 + g] for n-tile nt and column group g (ldc >= tf_proj_partials(N));
+                         // the consumer adds the partials in index order (deterministic, no atomics)
   const float* mask;     // EPI_MASK (may alias C)
   int64_t ldmask;
   const int32_t* idx;    // EPI_SCATTER: [M, F] ids; output column n belongs to row idx[m, n / Kemb], element n % Kemb
@@ -30,6 +33,7 @@ struct TfGemm {
 
 int tf_gemm(const TfGemm& g, cudaStream_t st);
 int64_t tf_splitk_scratch_floats();
+int tf_proj_partials(int N);      // partial sums per output row written by EPI_BIAS_RELU_PROJ
 // mask != NULL: v = X * (mask > 0) is what gets split / transposed, and it is also written to Xout (may alias mask)
 int tf_split_transpose(const float* X, int64_t rows, int cols, int64_t ld, float* Xlo, float* XT, float* XTlo, cudaStream_t st,
                        const float* mask = nullptr, float* Xout = nullptr);
