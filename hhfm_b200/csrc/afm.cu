@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(NW * 32) afm_kernel(const AfmArgs a) {
 // row per lane, and for scalar access with lanes over k).  dP_p = a_p d_afm + dZ_p W^T has the same shape (W^T is kept in
 // shared memory too) and is written in place over dZ_p.  A round whose tail has <= 16 pairs splits the columns between the
 // two half-warps instead of idling half the lanes (P = 45: 1.5 rounds, not 2).
-// Per tile of NW samples:  phase A (forward, dZ) | barrier | dW sweep over the tile (warp owns KD/NW columns, lanes over
-// k) | barrier | phase B (dP over dZ, dE, scatter).  Shared memory per warp is F + P rows, so 8 warps (2 per scheduler)
+// Per tile of NW samples:  phase A (forward, dZ) | barrier | dW sweep over the tile (warp owns 2 KD/NW columns of half the
+// tile's samples, lanes over k) | barrier | phase B (dP over dZ, dE, scatter).  Shared memory per warp is F + P rows, so 8 warps (2 per scheduler)
 // fit next to W and W^T.
 // ---------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline int afm2_p4(int P) { return (P + 3) / 4 * 4; }
@@ -496,7 +496,8 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
   __shared__ unsigned char sPairI[kAfmMaxP], sPairJ[kAfmMaxP];
   constexpr int RS = KD + 4;                 // row stride of sE / sZ
   constexpr int TD = (KD + 31) / 32;         // values per lane when the lanes run over k / a
-  constexpr int AS = KD / NW;                // columns of dW per warp
+  constexpr int SG = (NW >= 8 && KD >= 32) ? 2 : 1;   // the tile's samples are split over SG groups of warps for the dW sweep
+  constexpr int AS = KD * SG / NW;           // columns of dW per warp (more columns per warp = more FMAs per loaded operand)
   static_assert(AS % 4 == 0, "dW column slice is read with LDS.128");
   const int F = a.F, P = a.P, P4 = afm2_p4(P);
   float* sW = smem;                          // [KD][KD]   W[k][a]
@@ -646,11 +647,12 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
     }
     if (TRAIN) {
       __syncthreads();
-      // ---- d W[k][a] += (E_i E_j)[k] dZ_p[a]: lanes over k, warp w owns a in [w*AS, (w+1)*AS), every sample of the tile ----
-      for (int ws = 0; ws < NW; ws++) {
+      // ---- d W[k][a] += (E_i E_j)[k] dZ_p[a]: lanes over k; the warps form SG groups, group g sweeps the samples of its
+      // share of the tile and warp w of a group owns AS columns (32 FMAs per pair of operand loads instead of 16) ----
+      for (int ws = (warp * SG / NW) * (NW / SG); ws < (warp * SG / NW + 1) * (NW / SG); ws++) {
         if (!sValid[ws]) continue;
         const float* oE = warp_base + ws * per_warp + offE;
-        const float* oZ = oE + (size_t)F * RS + warp * AS;
+        const float* oZ = oE + (size_t)F * RS + (warp % (NW / SG)) * AS;
         int p = 0;
         for (int i = 0; i < F; i++) {
           float ei[TD];
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(NW * 32, 1) afm2_kernel(const AfmArgs a) {
       if (k < KD) {
 #pragma unroll
         for (int r = 0; r < AS; r++)
-          if (dWacc[t][r] != 0.f) atomicAdd(a.gW + (size_t)k * KD + warp * AS + r, dWacc[t][r]);
+          if (dWacc[t][r] != 0.f) atomicAdd(a.gW + (size_t)k * KD + (warp % (NW / SG)) * AS + r, dWacc[t][r]);
         atomicAdd(a.gbatt + k, gbatt_acc[t]); atomicAdd(a.gp + k, gp_acc[t]); atomicAdd(a.gwpred + k, gwp_acc[t]);
       }
     }
