@@ -8,7 +8,8 @@
 //   * item pairs (item, f): P = E_n * E_f, so Z = P W + b = E_n (diag(E_f) W) + b: for a fixed (context, field) the N item
 //     rows multiply ONE K x A matrix W_f = diag(E_f) W.  afm_topn_score_kernel builds W_f in shared memory, keeps 4 item
 //     rows x A/2 logit columns per lane in registers (lane = (column half, item mod 16), the layout of afm2_kernel in
-//     afm.cu) and folds each item pair into a running (max, numerator, denominator) per item.
+//     afm.cu), reads the tile's 512 item rows from a shared-memory copy staged once per CTA, and folds each item pair into a
+//     running (max, numerator, denominator) per item.
 //   out[c, n] = (T' + sum_f e_f t_f) / (D' + sum_f e_f) + sum of biases + b0,  e_f = exp(s_f - max), primes rescaled to the
 //   common max: the softmax-weighted sum of AFM.py:125-139 with the terms grouped differently (fp32 rounding differs from
 //   the op-by-op order at the 1e-7 level; the parity tests hold it to 1e-5).
@@ -103,15 +104,24 @@ __global__ void __launch_bounds__(256, 1) afm_topn_score_kernel(const AfmTopnArg
   for (int i = threadIdx.x; i < KD; i += blockDim.x) { sb[i] = __ldg(a.batt + i); sp[i] = __ldg(a.pvec + i); }
   if (threadIdx.x < a.F) sbias[threadIdx.x] = (a.bias && (int)threadIdx.x != a.item_col) ? __ldg(a.bias + __ldg(rec + threadIdx.x)) : 0.f;
 
+  // the tile's item rows, staged once for all F-1 fields (row stride KD+4: conflict-free LDS.128 with one row per lane)
+  extern __shared__ __align__(16) float sX[];
+  constexpr int XS = KD + 4;
+  for (int i = threadIdx.x; i < TI * (KD / 4); i += blockDim.x) {
+    const int item = i / (KD / 4), c4 = i % (KD / 4);
+    int64_t q = (int64_t)blockIdx.x * TI + item;
+    q = q < a.N ? q : a.N - 1;
+    *reinterpret_cast<float4*>(sX + item * XS + 4 * c4) = __ldg(reinterpret_cast<const float4*>(a.V + (size_t)(a.item_base + q) * KD) + c4);
+  }
   int64_t n[NR];
   const float* xrow[NR];
   float m[NR], num[NR], den[NR];
   const float m0 = __ldg(a.stats + 4 * c), d0 = __ldg(a.stats + 4 * c + 1), t0 = __ldg(a.stats + 4 * c + 2);
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    n[r] = (int64_t)blockIdx.x * TI + warp * (16 * NR) + l + 16 * r;
-    const int64_t q = n[r] < a.N ? n[r] : a.N - 1;
-    xrow[r] = a.V + (size_t)(a.item_base + q) * KD;
+    const int item = warp * (16 * NR) + l + 16 * r;
+    n[r] = (int64_t)blockIdx.x * TI + item;
+    xrow[r] = sX + item * XS;
     m[r] = m0; num[r] = t0; den[r] = d0;
   }
   __syncthreads();
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) afm_topn_score_kernel(const AfmTopnArg
       const float4 tv = *reinterpret_cast<const float4*>(tf + k);
 #pragma unroll
       for (int r = 0; r < NR; r++) {
-        const float4 x4 = __ldg(reinterpret_cast<const float4*>(xrow[r] + k));
+        const float4 x4 = *reinterpret_cast<const float4*>(xrow[r] + k);
         x[r][0] = x4.x; x[r][1] = x4.y; x[r][2] = x4.z; x[r][3] = x4.w;
         t[r] = fmaf(x4.x, tv.x, t[r]); t[r] = fmaf(x4.y, tv.y, t[r]); t[r] = fmaf(x4.z, tv.z, t[r]); t[r] = fmaf(x4.w, tv.w, t[r]);
       }
@@ -206,7 +216,13 @@ static int launch_afm_topn(const AfmTopnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   constexpr int TI = 512;
   dim3 grid((unsigned)((a.N + TI - 1) / TI), (unsigned)a.C);
-  afm_topn_score_kernel<KD><<<grid, 256, 0, st>>>(a);
+  const size_t xs = (size_t)TI * (KD + 4) * sizeof(float);
+  auto score = afm_topn_score_kernel<KD>;
+  if (cudaFuncSetAttribute(score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs) != cudaSuccess) {
+    set_error("afm_topn_score_kernel: cannot reserve %zu bytes of shared memory", xs);
+    return HHFM_ERR_LAUNCH;
+  }
+  score<<<grid, 256, xs, st>>>(a);
   return check_launch("afm_topn_score_kernel");
 }
 
