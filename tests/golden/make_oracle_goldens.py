@@ -47,6 +47,52 @@ def cases():
     for k, v in g.items():
         out["afm_g_" + k] = np.asarray(v)
     out["afm_top20"] = O.topk_lowest_index(O.afm_topk_scores(X[:8], w, n_user, n_item), 20)
+    # ---- appended later (new random draws only AFTER the ones above, so the earlier vectors stay what they were) ----
+    # DeepFM (DFM.py:104-152): tower F*K -> 12 -> 10 -> 6
+    layers = [12, 10, 6]
+    dw = dict(feature_embeddings=V, feature_bias=rng.uniform(0, 1, (M, 1)).astype(np.float32))
+    d = [F * K] + layers
+    for i in range(3):
+        dw["layer_%d" % i] = rng.normal(0, 0.3, (d[i], d[i + 1])).astype(np.float32)
+        dw["bias_%d" % i] = rng.normal(0, 0.1, (1, d[i + 1])).astype(np.float32)
+    dw["concat_projection"] = rng.normal(0, 0.3, (F + K + layers[-1], 1)).astype(np.float32)
+    dw["concat_bias"] = np.float32(0.01)
+    loss, o, g = O.dfm_loss_grads(X, Y * 2 - 1, dw, 0.01)
+    for k, v in dw.items():
+        if k != "feature_embeddings":
+            out["dfm_w_" + k] = np.asarray(v)
+    out.update(dfm_loss=loss, dfm_out=o)
+    for k, v in g.items():
+        out["dfm_g_" + k] = np.asarray(v)
+    # Wide&Deep (WDMF.py:51-126 restated): same tower shape, 97 cross buckets
+    n_pairs = F * (F - 1) // 2
+    ww = dict(feature_embeddings=V, wide_linear=rng.normal(0, 0.1, (M,)).astype(np.float32),
+              wide_cross=rng.normal(0, 0.1, (n_pairs, 97)).astype(np.float32), wide_bias=np.float32(0.03),
+              logits_w=rng.normal(0, 0.3, (layers[-1], 1)).astype(np.float32), logits_b=np.float32(-0.02))
+    for i in range(3):
+        ww["layer_%d" % i] = dw["layer_%d" % i]; ww["bias_%d" % i] = dw["bias_%d" % i]
+    loss, z, g = O.wd_loss_grads(X, Y, ww)
+    out.update(wd_wide_linear=ww["wide_linear"], wd_wide_cross=ww["wide_cross"], wd_logits_w=ww["logits_w"], wd_loss=loss, wd_logit=z,
+               wd_buckets=O.wd_wide(X, ww)[1])
+    for k, v in g.items():
+        out["wd_g_" + k] = np.asarray(v)
+    w1, a1, z1 = O.ftrl_dense(ww["wide_linear"], np.full(M, 0.1, np.float32), np.zeros(M, np.float32), g["wide_linear"], 0.135)
+    out.update(wd_ftrl_w=w1, wd_ftrl_accum=a1, wd_ftrl_linear=z1)
+    # CARS2 (CARS2.py:85-123): D = 20 -> D_c 8, D_p 4, D_q 8
+    D = 20
+    Dc, Dp, Dq = int(D / 2.5), int(D / 5), int(D / 2.5)
+    cw = dict(UI=rng.normal(0, 0.1, (n_user + n_item, D)).astype(np.float32), Context=rng.normal(0, 0.1, (30, Dc)).astype(np.float32),
+              W=rng.normal(0, 0.1, (D, Dp, Dc)).astype(np.float32), Z=rng.normal(0, 0.1, (D, Dq, Dc)).astype(np.float32),
+              A=rng.normal(0, 0.3, Dp).astype(np.float32), B=rng.normal(0, 0.3, Dq).astype(np.float32))
+    Fea = rng.integers(0, 30, B)
+    loss, pos, gr = O.cars2_loss_grads(X[:, :2], Fea, Neg[:, :3], cw, 0.001)
+    out["cars2_Fea"] = Fea
+    for k, v in cw.items():
+        out["cars2_w_" + k] = v
+    out.update(cars2_loss=np.asarray(loss), cars2_pos=np.asarray(pos))
+    for k, v in gr.items():
+        out["cars2_g_" + k] = np.asarray(v)
+    out["cars2_feedback"] = O.cars2_feedback(X[:, :2], Fea, cw)
     return out
 
 

@@ -482,3 +482,34 @@ def test_cars2_steps_and_topk_match_oracle(cuda, D, NG):
         tol = 2e-5 * max(abs(ref[r, want[r, -1]]), float(np.sqrt(np.mean(ref[r] ** 2))))
         for a_, b_ in zip(ids[r], want[r]):
             assert abs(ref[r, a_] - ref[r, b_]) <= tol, (r, a_, b_, ref[r, a_], ref[r, b_])
+
+
+def test_models_match_committed_golden_vectors(cuda):
+    """DeepFM / Wide&Deep / CARS2 forward passes on the committed fixtures of tests/golden/oracle_vectors.npz (weights and
+    inputs injected, outputs frozen when the oracle was pinned)."""
+    import os
+    from hhfm_b200.models import CARS2, DeepFM, WD
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.npz"))
+    n_user, n_item, M, K, B, F, NG = [int(x) for x in g["dims"]]
+    X, V = g["X"], g["V"]
+    layers = [12, 10, 6]
+    dfm = DeepFM(n_user, n_item, M, F, K, layers, 'relu', 0.01, 0, 0.01)
+    w = {"feature_embeddings": V}
+    for k in dfm.weights:
+        if k != "feature_embeddings":
+            w[k] = g["dfm_w_" + k]
+    dfm.load_weights(w)
+    assert_close(dfm.predict(X)[:, 0], g["dfm_out"], rtol=2e-5, what="golden dfm out")
+    wd = WD(F, n_user, n_item, features_M=M, hidden_units=layers, embedding_dim=K, cross_buckets=97, steps=1)
+    w = {"feature_embeddings": V, "wide_linear": g["wd_wide_linear"], "wide_cross": g["wd_wide_cross"], "wide_bias": np.float32(0.03),
+         "logits_w": g["wd_logits_w"], "logits_b": np.float32(-0.02)}
+    for i in range(3):
+        w["layer_%d" % i] = g["dfm_w_layer_%d" % i]; w["bias_%d" % i] = g["dfm_w_bias_%d" % i]
+    wd.load_weights(w)
+    assert_close(wd.score_device(wd._upload_rows(X)).cpu().numpy(), g["wd_logit"], rtol=2e-5, what="golden wd logit")
+    assert_close(wd.predict(X)[:, 1], 1.0 / (1.0 + np.exp(-g["wd_logit"].astype(np.float64))), rtol=2e-5, what="golden wd proba")
+    D = g["cars2_w_UI"].shape[1]
+    c2 = CARS2(g["cars2_w_Context"].shape[0], n_user, n_item, D, 0.05, 0.001, 'AdagradOptimizer')
+    c2.load_weights({k: g["cars2_w_" + k] for k in ("UI", "Context", "W", "Z", "A", "B")})
+    fb = c2.sess.run(c2.PositiveFeadback, feed_dict={c2.Pos: X[:, :2], c2.Fea: g["cars2_Fea"]})
+    assert_close(fb[:, 0], g["cars2_feedback"], rtol=2e-5, what="golden cars2 PositiveFeadback")
