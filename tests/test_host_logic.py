@@ -140,3 +140,32 @@ def test_hhfm_epoch_batches_match_reference_run(gold, data_root):
     assert [len(b["X"]) for b in t.model.batches] == gold["m7_epoch_sizes"].tolist()
     for k in ("X", "F1", "F2", "Y"):
         assert (np.concatenate([b[k] for b in t.model.batches]) == gold["m7_epoch_" + k]).all(), k
+
+
+def test_dropin_parse_args_keep_the_reference_defaults():
+    """The `parse_args(dataname, factor, Topk)` of every drop-in module keeps the reference's flags and defaults (FM.py:19-55,
+    AFM.py:22-62, DFM.py:19-47, OurModel7.py:21-48, BPR.py:18-43, CARS2.py:18-43, WDMF.py:18-49); the values below were read
+    off the reference sources when the drop-ins were written."""
+    import importlib
+    want = {
+        "FM": dict(path='../data/positive/', epoch=60, batch_size=5000, lamda=0.1, keep=1, lr=0.1, optimizer='AdagradOptimizer',
+                   verbose=10, batch_norm=0, Result=0),
+        "AFM": dict(path='../data/positive/', epoch=60, batch_size=5000, attention=1, lamda_attention=100.0, lr=0.1,
+                    optimizer='AdagradOptimizer', verbose=10, batch_norm=0, decay=0.999, activation='relu', Result=0),
+        "DFM": dict(path='../data/positive/', epoch=60, batch_size=5000, lamda=0.01, keep=1, lr=0.01, optimizer='AdagradOptimizer',
+                    verbose=10, batch_norm=0, Result=0),
+        "OurModel7": dict(path='../data/positive/', epoch=60, batch_size=5000, lamda=0.01, keep=1, lr=0.1,
+                          optimizer='AdagradOptimizer', batch_norm=0, Result=0),
+        "BPR": dict(path='../data/positive/', epoch=1110, batch_size=5000, lamda=0.1, keep=1, lr=0.01, optimizer='AdagradOptimizer',
+                    batch_norm=0, Result=1),
+        "CARS2": dict(path='../data/positive/', epoch=60, batch_size=5000, lamda=0.001, keep=1, lr=0.01,
+                      optimizer='AdagradOptimizer', batch_norm=0, Result=0),
+        "WDMF": dict(process='train', mla=0, path='../data/positive/', epoch=110, batch_size=4096, lamda=0.1, keep=1, lr=0.01,
+                     optimizer='AdagradOptimizer', verbose=10, batch_norm=0),
+    }
+    for name, defaults in want.items():
+        mod = importlib.import_module("hhfm_b200.Newcode." + name)
+        a = mod.parse_args("frappe", 64, 5, argv=[])
+        assert a.dataset == "frappe" and int(a.TopK) == 5, name
+        for k, v in defaults.items():
+            assert getattr(a, k) == v, (name, k, getattr(a, k), v)
