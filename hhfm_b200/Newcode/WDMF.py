@@ -3,7 +3,6 @@
 The reference's `WD` is tf.contrib.learn's canned DNNLinearCombinedClassifier; `hhfm_b200.models.WD` restates it on the
 sm_100a kernels (parity unpinned: see the class docstring)."""
 import argparse
-import copy
 from time import time
 
 import numpy as np
@@ -42,7 +41,7 @@ def parse_args(dataname, factor, Topk, argv=None):
 
 class Train(BaseTrain):
     """WDMF.py:132-257: ten outer epochs of (one negative per positive, shuffle, `partial_fit` = 500 full-batch steps), each
-    followed by AUC on 10 sampled negatives per row and the `item in prediction` form of the top-K walk."""
+    followed by AUC on 10 sampled negatives per row and the `item in prediction` form of the top-K walk (vectorised here)."""
     method = method
 
     def __init__(self, args):
@@ -68,65 +67,71 @@ class Train(BaseTrain):
     def score_rows(self, rows):
         return self.model.predict(rows)[:, 1].reshape(-1, 1)
 
+    OUTER_NEGATIVES = 1        # WDMF.py:169  NG = 1
+    AUC_NEGATIVES = 10         # WDMF.py:191,213  sample_negative(..., num=10)
+    AUC_CHUNK = 3000           # WDMF.py:209
+    TOPK_ROUNDS, TOPK_ROWS = 20, 50   # WDMF.py:227,234: int(500/25) rounds of 50 rows
+
+    def _epoch_batch(self):
+        """Positives plus one sampled-item copy each (label 0), shuffled: the (X, Y) of WDMF.py:168-184."""
+        pos = np.asarray(self.data.Train_data.values)
+        neg = np.repeat(pos, self.OUTER_NEGATIVES, axis=0)
+        neg[:, 2] = self.sample_negative(pos[:, 1:], self.OUTER_NEGATIVES).ravel()
+        neg[:, 0] = 0
+        rows = np.concatenate([pos, neg], axis=0)
+        np.random.shuffle(rows)
+        return rows[:, 1:].astype(np.int64), rows[:, 0]
+
     def train(self):
-        t2 = time()
-        # WDMF.py:155-165: the initial evaluation is commented out; the line is logged with zeros
+        t0 = time()
+        # the reference logs an all-zero "Init" line (its initial evaluation is commented out, WDMF.py:155-165)
         self._log("Dataset=%s %s Init: \t train=AUC:%.4f;test=AUC:%.4f,HR:%.4f,NDCG:%.4f,PRE:%.4f;[%.1f s]"
-                  % (self.args.dataset, method, 0, 0, 0, 0, 0, time() - t2))
+                  % (self.args.dataset, method, 0, 0, 0, 0, 0, time() - t0))
         self.loss_epoch = []
-        for epoch in range(1, int(self.args.wd_outer) + 1):
-            t1 = time()
-            NG = 1
-            pos = np.array(self.data.Train_data.values)
-            neg = np.tile(np.expand_dims(copy.deepcopy(pos), axis=1), [1, NG, 1]).reshape(-1, pos.shape[1])
-            neg[:, 2] = self.sample_negative(pos[:, 1:], NG).reshape(-1)
-            neg[:, 0] = 0
-            dat = np.append(pos, neg, axis=0)
-            np.random.shuffle(dat)
-            X = np.array(dat[:, 1:], dtype=np.int64)
-            Y = dat[:, 0]
+        for outer in range(1, int(self.args.wd_outer) + 1):
+            t_fit = time()
+            X, Y = self._epoch_batch()
             self.loss_epoch.append(self.model.partial_fit(X, Y))
-            t2 = time()
-            a_tr = self.evaluate_AUC(self.data.Train_data)
-            a_te = self.evaluate_AUC(self.data.Test_data)
-            tk = self.evaluate_TopK(self.data.Test_data)
+            t_eval = time()
+            auc_train = self.evaluate_AUC(self.data.Train_data)
+            auc_test = self.evaluate_AUC(self.data.Test_data)
+            hr, ndcg, pre = self.evaluate_TopK(self.data.Test_data)
             self._log("%s Epoch %d [%.1f s]\ttrain=AUC:%.4f;test=AUC:%.4f,HR:%.4f,NDCG:%.4f,PRE:%.4f;[%.1f s]"
-                      % (method, epoch * 10, t2 - t1, a_tr, a_te, tk[0], tk[1], tk[2], time() - t2))
+                      % (method, outer * 10, t_eval - t_fit, auc_train, auc_test, hr, ndcg, pre, time() - t_eval))
 
     def evaluate_AUC(self, data1):
-        """WDMF.py:202-225: chunks of 3000 positives, 10 sampled negatives each, mean over the chunks of mean(pos > neg)."""
-        dat = np.asarray(data1.values if hasattr(data1, "values") else data1)
-        dat = dat[dat[:, 0] > 0]
-        X = np.array(dat[:, 1:], dtype=np.int64)
-        score = []
-        for c0 in range(0, len(X), 3000):
-            pos = X[c0:c0 + 3000]
-            negs = self.sample_negative(pos)
-            neg = np.tile(np.expand_dims(copy.deepcopy(pos), axis=1), [1, 10, 1]).reshape(-1, pos.shape[1])
-            neg[:, 1] = negs.reshape(-1)
-            neg_score = self.score_rows(neg)
-            pos_score = np.reshape(np.tile(np.expand_dims(self.score_rows(pos), axis=1), [1, 10, 1]), [-1, 1])
-            score.append(np.mean(pos_score > neg_score))
-        return np.mean(score)
+        """WDMF.py:202-225.  Quirk kept: `predict_proba(...)[:, 1]` is 1-D there, so `pos_score > neg_score` broadcasts a
+        [10n, 1] column against a [10n] row -- every positive of a 3000-row chunk is compared with EVERY sampled negative of
+        the chunk (10 per positive), not only with its own.  The mean of that [10n, 10n] matrix is computed here from the
+        sorted negatives (same value, no 900 MB boolean matrix); the chunk means are averaged."""
+        table = np.asarray(data1.values if hasattr(data1, "values") else data1)
+        X = table[table[:, 0] > 0][:, 1:].astype(np.int64)
+        shares = []
+        for start in range(0, len(X), self.AUC_CHUNK):
+            pos = X[start:start + self.AUC_CHUNK]
+            neg = np.repeat(pos, self.AUC_NEGATIVES, axis=0)
+            neg[:, 1] = self.sample_negative(pos).ravel()
+            p_neg = np.sort(self.score_rows(neg).ravel())
+            p_pos = self.score_rows(pos).ravel()
+            below = np.searchsorted(p_neg, p_pos, side="left")          # negatives strictly below each positive
+            shares.append(float(below.sum()) / (len(p_pos) * len(p_neg)))
+        return np.mean(shares)
 
     def evaluate_TopK(self, data1):
-        """WDMF.py:226-249: 20 rounds of 50 rows drawn with replacement; hit = the row's item is in its top-K list."""
-        size = 500
-        res_map, res_ndcg, res_pre = [], [], []
-        dat = np.asarray(data1.values if hasattr(data1, "values") else data1)
-        for _ in range(int(size / 25)):
-            feed = np.array(dat[:, 1:][np.random.randint(0, len(dat), 50)], dtype=np.int64)
+        """WDMF.py:226-249: 20 rounds of 50 rows drawn with replacement; a row scores when its own item is in its top-K list
+        (hit, log 2 / log(rank + 2), 1 / (rank + 1) with rank = position of the first match)."""
+        table = np.asarray(data1.values if hasattr(data1, "values") else data1)
+        hits, gains, recip = [], [], []
+        for _ in range(self.TOPK_ROUNDS):
+            feed = table[np.random.randint(0, len(table), self.TOPK_ROWS)][:, 1:].astype(np.int64)
             self.score = self.model.topk(feed, self.TopK)
-            prediction = self.score + self.n_user
-            for i, item in enumerate(feed[:, 1]):
-                if item in prediction[i]:
-                    index1 = prediction[i].tolist().index(item)
-                    res_map.append(1)
-                    res_ndcg.append(np.log(2) / np.log(index1 + 2))
-                    res_pre.append(1 / (index1 + 1))
-                else:
-                    res_map.append(0); res_ndcg.append(0); res_pre.append(0)
-        return [np.average(res_map), np.average(res_ndcg), np.average(res_pre)]
+            match = (self.score + self.n_user) == feed[:, 1:2]
+            found = match.any(axis=1)
+            rank = match.argmax(axis=1)
+            hits.append(found.astype(np.float64))
+            gains.append(np.where(found, np.log(2) / np.log(rank + 2.0), 0.0))
+            recip.append(np.where(found, 1.0 / (rank + 1.0), 0.0))
+        return [np.average(np.concatenate(hits)), np.average(np.concatenate(gains)), np.average(np.concatenate(recip))]
 
 
 def WDMF_main(dataname, factor, Topk, argv=None):
