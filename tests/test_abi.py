@@ -33,6 +33,16 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert not missing, "declared in the header but not exported: %s" % missing
 
 
+def test_library_exports_nothing_the_header_does_not_declare(lib_path):
+    """Every `hhfm_*` symbol in the dynamic symbol table is part of the documented C ABI (no private entry points)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if re.search(r"\s[TW]\shhfm_[a-z0-9_]+$", ln)})
+    assert exported, "nm found no hhfm_* exports"
+    extra = sorted(set(exported) - set(declared_symbols()))
+    assert not extra, "exported but not declared in include/hhfm_sm100.h: %s" % extra
+
+
 def test_python_binding_covers_the_header(lib_path):
     from hhfm_b200 import _lib
     _lib.load()
@@ -52,6 +62,19 @@ def test_bad_arguments_fail_loudly_without_a_gpu(lib_path):
     with pytest.raises(_lib.HhfmError, match="n_neg"):
         _lib.call("hhfm_pairrank_fwd", ctypes.c_void_p(16), 4, 72, 2, 0, 65, 0, 0, 0, ctypes.c_void_p(16), 10, 8,
                   ctypes.c_void_p(16), None, None)
+    p16 = ctypes.c_void_p(16)
+    # evaluators / Wide&Deep / sparse-exchange helpers: shape checks run before any launch
+    assert lib.hhfm_afm_topn_supported(10, 64, 64) == 1 and lib.hhfm_afm_topn_supported(10, 128, 128) == 0
+    with pytest.raises(_lib.HhfmError, match="not covered"):
+        _lib.call("hhfm_afm_topn_scores", p16, 12, 4, 10, 1, p16, None, None, p16, p16, p16, p16, 100, 128, 128, 10, 50, p16, p16, None)
+    with pytest.raises(_lib.HhfmError, match="item_col"):
+        _lib.call("hhfm_afm_topn_scores", p16, 12, 4, 10, 10, p16, None, None, p16, p16, p16, p16, 100, 64, 64, 10, 50, p16, p16, None)
+    with pytest.raises(_lib.HhfmError, match="bad sizes"):
+        _lib.call("hhfm_wd_wide_fwd", p16, 4, 33, p16, p16, p16, 100, 97, p16, None)
+    with pytest.raises(_lib.HhfmError, match="bad argument"):
+        _lib.call("hhfm_opt_ftrl_dense", p16, p16, p16, p16, 8, 0.0, 0.0, 0.0, 1, None)
+    with pytest.raises(_lib.HhfmError, match="multiple of 4"):
+        _lib.call("hhfm_gather_rows", p16, p16, 4, 6, 100, p16, 0, None)
 
 
 def test_host_packer_narrows_and_validates(lib_path):
