@@ -1,7 +1,8 @@
 """CPU oracle for the HHFM factorization-machine hot path  --  TEST INFRASTRUCTURE ONLY.
 
 This file is a NumPy fp32 restatement of the TensorFlow-1.x graphs the reference builds in
-`Newcode/{FM,MF,AFM,DFM,OurModel7,BPR}.py` plus the host logic of `Newcode/NewLoadData.py` and the
+`Newcode/{FM,MF,AFM,DFM,OurModel7,BPR,CARS2}.py`, of the Wide&Deep estimator `Newcode/WDMF.py` wraps (TF's
+documented defaults with this repo's own bucket functions), plus the host logic of `Newcode/NewLoadData.py` and the
 `Train.evaluate_TopK / sample_negative` loops.  Every function cites the reference file:line it follows.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import
