@@ -1177,7 +1177,7 @@ class WD(_Base):
         N = self.n_item
         out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=self.device)
         items = torch.arange(self.n_user, self.n_user + N, dtype=torch.int32, device=self.device)
-        chunk = max(1, (1 << 20) // max(N, 1))
+        chunk = max(1, (1 << 18) // max(N, 1))      # <= 2^18 expanded rows per pass: the tower's workspace is ~50 KB per row
         for c0 in range(0, C_rows, chunk):
             c1 = min(C_rows, c0 + chunk)
             rows = A_dev[c0:c1, :F].unsqueeze(1).repeat(1, N, 1)
