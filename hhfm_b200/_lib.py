@@ -62,14 +62,10 @@ SIGNATURES = {
     "hhfm_sample_negatives": [vp, i64, i32, i32, i32, vp, i64, i64, C.c_uint64, vp, i64, i64, vp],
     "hhfm_expand_rows": [vp, i64, i32, i64, vp, i32, vp, i32, vp],
     "hhfm_auc_count": [vp, vp, i64, i32, vp, vp],
-    "hhfm_p2p_alloc": [i64, vp, vp],
-    "hhfm_p2p_open": [vp, vp],
-    "hhfm_p2p_close": [vp],
-    "hhfm_p2p_free": [vp],
-    "hhfm_p2p_barrier": [vp, i32, i32, i32, vp],
-    "hhfm_opt_dense_l2_p2p": [i32, vp, vp, vp, vp, i32, vp, i64, f32, f32, f32, f32, f32, vp, vp],
-    "hhfm_loss_finalize_p2p": [vp, i32, i32, vp, f32, vp, vp],
+    "hhfm_dp_step": [i32, vp, i32, vp, i64, vp, vp, i32, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, vp, f32, f32, f32,
+                     f32, vp, vp, C.c_double, vp],
     "hhfm_hot_fold": [vp, vp, i32, i32, i64, vp, vp, vp, vp],
+    "hhfm_l2_read_sweep": [vp, i64, i32, vp, vp],
     "hhfm_topn_build_query": [i32, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_topn_score_exact": [i32, vp, vp, i64, vp, vp, i64, i64, vp, i64, vp],
     "hhfm_topn_select": [vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp],
@@ -84,6 +80,7 @@ INT64_FUNCS = {
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
     "hhfm_workspace_bytes_afm": [i64, i64, i64, i64],
+    "hhfm_dp_exchange_floats": [i64],
     "hhfm_workspace_bytes_dfm_topn": [i64, i64, i64, i64, i32, vp],
     "hhfm_cars2_param_count": [i64, i64, i64, i64, i64, i64],
     "hhfm_workspace_bytes_cars2": [i64, i64, i64],
@@ -138,10 +135,14 @@ def declare(name, argtypes):
         fn.argtypes = argtypes
 
 
+CALLS = {}      # entry point -> number of successful calls (bench.py derives its kernel-launch count from the deltas)
+
+
 def call(name, *args):
     """Invoke an entry point and raise HhfmError with the library's message on failure."""
     lib = load()
     rc = getattr(lib, name)(*args)
+    CALLS[name] = CALLS.get(name, 0) + 1
     if rc != 0:
         raise HhfmError("%s failed (%d): %s" % (name, rc, lib.hhfm_last_error().decode("utf-8", "replace")))
 

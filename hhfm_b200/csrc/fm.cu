@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "staged.cuh"
 
 namespace hhfm {
 
@@ -335,42 +336,6 @@ static int dispatch_fm_fixed(const FmArgs& a, cudaStream_t st) {
 // so NS*F rows (NS*F*K*4 bytes, 20 KB at F=10, K=128) are in flight per warp with no register cost, and no load of
 // the consumer step (C) goes to global memory.  Touched rows are marked with a plain store into the stamp array and
 // compacted into the list afterwards (touched_compact_kernel) instead of one returning atomic per row.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldgsts4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void ldgsts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_row(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
-__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_addr(bar);
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s
-  }
-}
-
 constexpr int kStagedWarps = 10;
 constexpr int kStagedMaxF = 16;
 
@@ -525,6 +490,14 @@ __global__ void __launch_bounds__(256) touched_compact_kernel(const int32_t* __r
   }
 }
 
+int launch_touched_compact(const int32_t* stamp_arr, int32_t stamp, int64_t M, int32_t* list, int32_t* count, cudaStream_t st) {
+  int64_t blocks = (M + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  touched_compact_kernel<<<(int)blocks, 256, 0, st>>>(stamp_arr, stamp, M, list, count);
+  return check_launch("touched_compact_kernel");
+}
+
 // HHFM_ERR_UNSUPPORTED when the shape is not covered or the table is small enough to live in L2 (the register kernel wins
 // there); `M` is needed for the stamp compaction.
 static int dispatch_fm_staged(const FmArgs& a, int64_t M, cudaStream_t st) {
@@ -557,13 +530,7 @@ static int dispatch_fm_staged(const FmArgs& a, int64_t M, cudaStream_t st) {
   }
   int rc = check_launch("fm_train_staged_kernel");
   if (rc != HHFM_OK) return rc;
-  if (a.touch_stamp != nullptr) {
-    int64_t blocks = (M + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    touched_compact_kernel<<<(int)blocks, 256, 0, st>>>(a.touch_stamp, a.stamp, M, a.touched_rows, a.touched_count);
-    rc = check_launch("touched_compact_kernel");
-  }
+  if (a.touch_stamp != nullptr) rc = launch_touched_compact(a.touch_stamp, a.stamp, M, a.touched_rows, a.touched_count, st);
   return rc;
 }
 

@@ -249,9 +249,31 @@ __global__ void __launch_bounds__(256) touch_rows_kernel(const int32_t* __restri
     touch_row(stamp_arr, stamp, rows, count, __ldg(ids + i));
 }
 
+// Measurement aid (bench.py `roofline.peak` of the L2-bound kernels): every thread streams the whole buffer `iters` times
+// with 16-byte loads that bypass L1 (ld.global.cg), so a buffer that fits the 126 MB L2 is served by L2 only.
+__global__ void __launch_bounds__(256) l2_read_sweep_kernel(const float4* __restrict__ buf, int64_t n4, int iters, float* sink) {
+  float4 acc = f4_zero();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; it++) {
+    int64_t i = tid;
+    for (; i + 3 * nth < n4; i += 4 * nth) {
+      const float4 a = __ldcg(buf + i), b = __ldcg(buf + i + nth), c = __ldcg(buf + i + 2 * nth), d = __ldcg(buf + i + 3 * nth);
+      acc = f4_add(acc, f4_add(f4_add(a, b), f4_add(c, d)));
+    }
+    for (; i < n4; i += nth) acc = f4_add(acc, __ldcg(buf + i));
+  }
+  if (f4_hsum(acc) == 123.456f) *sink = 1.f;      // keeps the loads alive without a store on the hot path
+}
+
 }  // namespace hhfm
 
 using namespace hhfm;
+
+extern "C" int hhfm_l2_read_sweep(const float* buf, int64_t n_floats, int32_t iters, float* sink, hhfm_stream_t stream) {
+  HHFM_REQUIRE(buf && sink && n_floats >= 4 && iters >= 1 && ((uintptr_t)buf & 15) == 0, "l2_read_sweep: bad arguments");
+  l2_read_sweep_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(buf), n_floats >> 2, iters, sink);
+  return check_launch("l2_read_sweep_kernel");
+}
 
 extern "C" int hhfm_opt_adagrad_dense_l2(float* w, float* acc, float* g, int64_t n, float lr, float lamda,
                                          int32_t zero_grad, float* sq_partials, hhfm_stream_t stream) {

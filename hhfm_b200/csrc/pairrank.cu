@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "staged.cuh"
 
 namespace hhfm {
 
@@ -422,6 +423,207 @@ static int dispatch_pr_fast(const PrArgs& a, cudaStream_t st, int* rc) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Staged variant of the sum-pooling training pass for tables that do not fit in L2 (scaled config: M = 10^7, K = 128,
+// 5 GB of rows; every gathered row comes from HBM).  Same per-warp pipeline as fm_train_staged_kernel (fm.cu): iteration t
+//   (A) LDGSTS the W = 2 + NP + NNEG ids of sample t                                  -> id ring
+//   (B) sample t-PD: one bulk copy (cp.async.bulk, UBLKCP) per row, lane w copies row w -> row stage, completion on the
+//       stage's mbarrier; LDGSTS of hot_slot[id]                                         -> per-stage side buffer
+//   (C) sample t-PD-NS+1: wait on its mbarrier, forward + loss + backward from shared memory, REDs from registers
+// so NS*W rows (20 KB at W = 20, K = 128, NS = 2) are in flight per warp at no register cost.  One sample per warp
+// iteration; lane l owns the float4 columns l, l+32, ...  Arithmetic order as in pairrank_sum_train_kernel (the idle upper
+// lanes of K < 128 add exact zeros to the butterfly sums).  Touched rows are marked with a plain store into the stamp array
+// and compacted afterwards (launch_touched_compact) instead of one returning atomic per row.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPrStagedWarps = 10;
+constexpr int kPrMaxW = 32;
+
+__host__ __device__ inline size_t pr_staged_warp_bytes(int NS, int W, int K) {
+  const int PD = NS - 1;
+  const size_t b = (size_t)NS * W * K * 4 + (size_t)((NS + PD) + NS) * kPrMaxW * 4 + (size_t)NS * 8;
+  return (b + 127) / 128 * 128;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kPrStagedWarps * 32, 1) pairrank_sum_train_staged_kernel(const PrArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float scratch[32];
+  constexpr int PD = NS - 1;
+  constexpr int RI = NS + PD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NP = a.n_ctx + a.n_time, NNEG = a.n_neg;
+  const int W = 2 + NP + NNEG;
+  const int K = a.K, kv = K >> 2;
+  const uint32_t row_bytes = (uint32_t)K * 4u;
+  unsigned char* base = smem_raw + (size_t)warp * pr_staged_warp_bytes(NS, W, K);
+  float* rows = reinterpret_cast<float*>(base);                                   // [NS][W][K]
+  int* idring = reinterpret_cast<int*>(base + (size_t)NS * W * K * 4);             // [RI][32]
+  int* slotbuf = idring + RI * kPrMaxW;                                            // [NS][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slotbuf + NS * kPrMaxW);            // [NS]
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) mbar_init1(bars + i);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int64_t n_warps = (int64_t)gridDim.x * kPrStagedWarps;
+  const int64_t warp_g = (int64_t)blockIdx.x * kPrStagedWarps + warp;
+  const int64_t per = (a.B + n_warps - 1) / n_warps;
+  const int64_t s_beg = warp_g * per;
+  const int64_t s_end = (s_beg + per < a.B) ? s_beg + per : a.B;
+  const int64_t n = s_end > s_beg ? s_end - s_beg : 0;
+  const int rep = a.hot.slot ? (int)(warp_g % a.hot.n_rep) : 0;
+  float loss_acc = 0.f;
+
+  for (int64_t t = 0; t < n + PD + NS - 1; t++) {
+    if (t < n && lane < W) ldgsts4(idring + (t % RI) * kPrMaxW + lane, a.idx + (s_beg + t) * a.stride + lane);
+    ldgsts_wait<(PD > 0 ? PD - 1 : 0)>();      // groups <= t-PD complete: ids of sample t-PD, hot slots of the consumed sample
+    __syncwarp();
+    const int64_t j = t - PD;
+    if (j >= 0 && j < n) {
+      const int st = (int)(j % NS);
+      if (lane == 0) mbar_expect(bars + st, row_bytes * (uint32_t)W);
+      __syncwarp();
+      if (lane < W) {
+        const int id = idring[(j % RI) * kPrMaxW + lane];
+        bulk_row(rows + ((size_t)st * W + lane) * K, a.V + (size_t)id * K, row_bytes, bars + st);
+        if (a.hot.slot) ldgsts4(slotbuf + st * kPrMaxW + lane, a.hot.slot + id);
+      }
+    }
+    ldgsts_commit();
+    const int64_t c = t - PD - NS + 1;
+    if (c >= 0 && c < n) {
+      const int st = (int)(c % NS);
+      mbar_wait_parity(bars + st, (uint32_t)((c / NS) & 1));
+      const float4* r4 = reinterpret_cast<const float4*>(rows + (size_t)st * W * K);
+      const int* ids = idring + (c % RI) * kPrMaxW;
+      const int* slots = slotbuf + st * kPrMaxW;
+      float4 hyb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int cc = lane + 32 * i;
+        hyb[i] = f4_zero();
+        if (cc < kv) {
+          hyb[i] = r4[cc];                                       // user, then ctx.., time.. in record order
+          for (int q = 0; q < NP; q++) hyb[i] = f4_add(hyb[i], r4[(2 + q) * kv + cc]);
+        }
+      }
+      auto dot_row = [&](int w) {
+        float p = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) p += f4_dot(hyb[i], r4[w * kv + cc]);
+        }
+        return warp_sum(p);
+      };
+      const float pos = dot_row(1);
+      float m = -INFINITY;
+      unsigned tie = 0u;
+      for (int jn = 0; jn < NNEG; jn++) {
+        const float p = dot_row(2 + NP + jn);
+        if (p > m) { m = p; tie = 1u << jn; }
+        else if (p == m) tie |= 1u << jn;
+      }
+      const float x = pos - m;
+      const float sg = 1.f / (1.f + expf(-x));
+      if (lane == 0) loss_acc += -logf(sg);
+      const float gp = sg - 1.f;
+      const float gn = -gp / (float)__popc(tie);
+      auto dst_of = [&](int w) {
+        const int slot = a.hot.slot ? slots[w] : -1;
+        return (slot >= 0) ? a.hot.ghot + ((size_t)rep * a.hot.n_hot + slot) * K : a.gV + (size_t)ids[w] * K;
+      };
+      float4 dh[4];
+      {
+        float* d = dst_of(1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) {
+            dh[i] = f4_scale(r4[kv + cc], gp);
+            red_add_v4(d + 4 * cc, f4_scale(hyb[i], gp));
+          }
+        }
+      }
+      unsigned wl = tie;
+      while (wl) {
+        const int jn = __ffs((int)wl) - 1;
+        wl &= wl - 1;
+        const int w = 2 + NP + jn;
+        float* d = dst_of(w);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) {
+            dh[i] = f4_fma(r4[w * kv + cc], gn, dh[i]);
+            red_add_v4(d + 4 * cc, f4_scale(hyb[i], gn));
+          }
+        }
+      }
+      for (int w = 0; w < 2 + NP; w++) {
+        if (w == 1) continue;
+        float* d = dst_of(w);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cc = lane + 32 * i;
+          if (cc < kv) red_add_v4(d + 4 * cc, dh[i]);
+        }
+      }
+      if (a.touch_stamp && lane < W) {
+        const bool touched = (lane < 2 + NP) || ((tie >> (lane - 2 - NP)) & 1u);
+        if (touched) a.touch_stamp[ids[lane]] = a.stamp;       // compacted into the list afterwards
+      }
+      __syncwarp();     // every lane is done with this stage before the next iteration re-arms it
+    }
+  }
+  ldgsts_wait<0>();
+  const float bl = block_sum(loss_acc, scratch);
+  write_partial(a.loss_partials, bl);
+}
+
+// HHFM_ERR_UNSUPPORTED when the configuration is not covered or the table is small enough to live in L2 (the register
+// kernel wins there).  HHFM_PR_STAGED=0/1 forces the choice.
+static int dispatch_pr_staged(const PrArgs& a, int64_t M, cudaStream_t st) {
+  const bool all_sum = (a.n_ctx == 0 || a.pc == HHFM_POOL_SUM) && (a.n_time == 0 || a.pt == HHFM_POOL_SUM) &&
+                       ((a.n_ctx == 0 && a.n_time == 0) || a.pf == HHFM_POOL_SUM);
+  if (!all_sum || a.pos_out || a.neg_out) return HHFM_ERR_UNSUPPORTED;
+  const int W = 2 + a.n_ctx + a.n_time + a.n_neg;
+  if (W > kPrMaxW || a.n_neg < 1 || a.n_neg > 31 || a.K < 64 || a.K > 512 || W > a.stride) return HHFM_ERR_UNSUPPORTED;
+  const char* env = getenv("HHFM_PR_STAGED");
+  const int force = env ? (env[0] == '1' ? 1 : 0) : 2;
+  if (force == 0) return HHFM_ERR_UNSUPPORTED;
+  if (force == 2 && (size_t)M * a.K * 4 < ((size_t)96 << 20)) return HHFM_ERR_UNSUPPORTED;
+  const size_t cap = (size_t)224 * 1024;
+  int ns = 4;
+  while (ns > 2 && pr_staged_warp_bytes(ns, W, a.K) * kPrStagedWarps > cap) ns--;
+  const size_t smem = pr_staged_warp_bytes(ns, W, a.K) * kPrStagedWarps;
+  if (smem > cap) return HHFM_ERR_UNSUPPORTED;
+  const int grid = sm_count();
+  if (grid > kPartials) return HHFM_ERR_UNSUPPORTED;
+  cudaError_t e = cudaSuccess;
+  if (ns == 4) {
+    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<4><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
+  } else if (ns == 3) {
+    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<3><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<2><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
+  }
+  if (e != cudaSuccess) {
+    set_error("pairrank_sum_train_staged_kernel: %s", cudaGetErrorString(e));
+    return HHFM_ERR_LAUNCH;
+  }
+  int rc = check_launch("pairrank_sum_train_staged_kernel");
+  if (rc != HHFM_OK) return rc;
+  if (a.touch_stamp != nullptr) rc = launch_touched_compact(a.touch_stamp, a.stamp, M, a.touched_rows, a.touched_count, st);
+  return rc;
+}
+
 template <int LPS, int VPL, int MODE, bool ANYMAX>
 static int launch_pr(const PrArgs& a, int deterministic, cudaStream_t st) {
   static int occ = 0;
@@ -518,7 +720,8 @@ extern "C" int hhfm_pairrank_fwd_bwd(const int32_t* idx, int64_t B, int64_t stri
   a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows; a.touched_count = touched_count;
   a.hot = HotPlan{hot_slot, ghot, nullptr, n_rep, n_hot};
   if (!deterministic && hhfm_fast_path_enabled()) {
-    int frc = 0;
+    int frc = dispatch_pr_staged(a, M, (cudaStream_t)stream);
+    if (frc != HHFM_ERR_UNSUPPORTED) return frc;
     if (dispatch_pr_fast(a, (cudaStream_t)stream, &frc) == 0) return frc;
   }
   return dispatch_pr<PR_TRAIN>(a, deterministic, (cudaStream_t)stream);

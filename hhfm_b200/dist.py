@@ -6,11 +6,14 @@
              local top-tp with GLOBAL ids, all-gather of [C, tp] (score, id), and a merge under the comparator
              (score desc, id asc) -- the lists are bit-identical to a single-GPU run.
 
-`PeerArena` is the training exchange on one NVLink box: the gradient arenas are cudaMalloc'd, mapped into every peer
-through CUDA IPC, and the optimizer kernel reads all ranks' arenas directly (csrc/p2p.cu) after a flag barrier -- no
-all-reduce pass.  `allreduce_arena` (NCCL / gloo) remains the fallback and what the CPU tests exercise.
+`SymmExchange` is the training exchange on one NVLink box: every rank's exchange buffer lives in symmetric memory (mapped
+into every peer, multicast-bound on NVSwitch) and ONE kernel per step folds, all-reduces (multimem.ld_reduce / multimem.st)
+and applies the optimizer (csrc/p2p.cu).  `allreduce_arena` (NCCL / gloo) remains the fallback and what the CPU tests
+exercise.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -35,38 +38,71 @@ def allreduce_arena(arena, group=None):
     return arena
 
 
-def merge_topk(local_scores, local_ids, tp, group=None):
-    """All-gather the per-shard candidate lists and keep the tp best per row under (score desc, id asc).
-    local_scores f32 [C, tp_local], local_ids int [C, tp_local] (global ids; -1 = padding)."""
+def gather_candidates(local_scores, local_ids, group=None):
+    """All-gather of the per-shard candidate lists: [C, tl] per rank -> [C, ws*tl] (rank order).  torch.distributed
+    plumbing only (NCCL on the GPUs, gloo in the CPU tests)."""
     rank, ws = world(group)
-    if ws > 1:
-        sc = [torch.empty_like(local_scores) for _ in range(ws)]
-        ids = [torch.empty_like(local_ids) for _ in range(ws)]
-        dist.all_gather(sc, local_scores.contiguous(), group=group)
-        dist.all_gather(ids, local_ids.contiguous(), group=group)
-        scores, idx = torch.cat(sc, dim=1), torch.cat(ids, dim=1)
-    else:
-        scores, idx = local_scores, local_ids
-    if scores.is_cuda:
-        from . import _lib
-        from .engine import cur_stream, ptr
-        C, n = scores.shape
-        out_ids = torch.empty(C, tp, dtype=torch.int32, device=scores.device)
-        out_sc = torch.empty(C, tp, dtype=torch.float32, device=scores.device)
-        scores = scores.contiguous().float(); idx = idx.contiguous().to(torch.int32)
-        # padding entries carry id -1: give them the lowest possible score so they sort last
-        scores = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
-        idx = torch.where(idx < 0, torch.full_like(idx, 2 ** 31 - 1), idx)
-        _lib.call("hhfm_topn_select", ptr(scores), ptr(idx), None, C, n, n, tp, 0, ptr(out_sc), ptr(out_ids), cur_stream())
-        out_ids = torch.where(out_ids == 2 ** 31 - 1, torch.full_like(out_ids, -1), out_ids)
-        return out_ids, out_sc
-    # host tensors (gloo tests / tiny merges): stable sort by id, then stable sort by descending score
+    if ws == 1:
+        return local_scores, local_ids
+    sc = [torch.empty_like(local_scores) for _ in range(ws)]
+    ids = [torch.empty_like(local_ids) for _ in range(ws)]
+    dist.all_gather(sc, local_scores.contiguous(), group=group)
+    dist.all_gather(ids, local_ids.contiguous(), group=group)
+    return torch.cat(sc, dim=1), torch.cat(ids, dim=1)
+
+
+def exchange_candidates_sharded(local_scores, local_ids, group=None):
+    """All-to-all of the candidate lists with the CONTEXT rows sharded for the merge: rank r receives every rank's candidates
+    for context rows [r*C/ws, (r+1)*C/ws) -> [C/ws, ws*tl].  Each rank receives C*tl candidates instead of the ws*C*tl of
+    the all-gather.  C must be a multiple of the world size."""
+    rank, ws = world(group)
+    if ws == 1:
+        return local_scores, local_ids
+    C_rows, tl = local_scores.shape
+    if C_rows % ws != 0:
+        raise ValueError("exchange_candidates_sharded: %d context rows are not a multiple of the world size %d" % (C_rows, ws))
+    per = C_rows // ws
+    sc_in, id_in = local_scores.contiguous(), local_ids.contiguous()
+    sc_out, id_out = torch.empty_like(sc_in), torch.empty_like(id_in)
+    dist.all_to_all_single(sc_out, sc_in, group=group)          # block r of the output = rank r's candidates for my rows
+    dist.all_to_all_single(id_out, id_in, group=group)
+    return (sc_out.view(ws, per, tl).transpose(0, 1).reshape(per, ws * tl),
+            id_out.view(ws, per, tl).transpose(0, 1).reshape(per, ws * tl))
+
+
+def merge_topk(local_scores, local_ids, tp, group=None):
+    """All-gather the per-shard candidate lists and keep the tp best per row under (score desc, id asc) with the device
+    selector.  local_scores f32 [C, tp_local], local_ids int [C, tp_local] (global ids; -1 = padding), CUDA tensors."""
+    if not local_scores.is_cuda:
+        raise RuntimeError("merge_topk: candidates must be CUDA tensors (the selector is a device kernel; there is no CPU path)")
+    scores, idx = gather_candidates(local_scores, local_ids, group)
+    return _select_merged(scores, idx, tp)
+
+
+def merge_topk_sharded(local_scores, local_ids, tp, group=None):
+    """Item-sharded top-N merge that leaves the result sharded by context rows: one all-to-all
+    (`exchange_candidates_sharded`), then rank r re-selects tp of the ws*tp candidates of ITS rows [r*C/ws, (r+1)*C/ws) --
+    the HR / NDCG walk shards by context rows anyway (`allreduce_metrics`).  Same lists, bit for bit, as
+    `merge_topk` restricted to the slice."""
+    if not local_scores.is_cuda:
+        raise RuntimeError("merge_topk_sharded: candidates must be CUDA tensors")
+    scores, idx = exchange_candidates_sharded(local_scores.float(), local_ids.to(torch.int32), group)
+    return _select_merged(scores, idx, tp)
+
+
+def _select_merged(scores, idx, tp):
+    from . import _lib
+    from .engine import cur_stream, ptr
+    C_rows, n = scores.shape
+    out_ids = torch.empty(C_rows, tp, dtype=torch.int32, device=scores.device)
+    out_sc = torch.empty(C_rows, tp, dtype=torch.float32, device=scores.device)
+    scores = scores.contiguous().float(); idx = idx.contiguous().to(torch.int32)
+    # padding entries carry id -1: give them the lowest possible score so they sort last
     scores = torch.where(idx < 0, torch.full_like(scores, float("-inf")), scores)
-    o1 = torch.argsort(idx, dim=1, stable=True)
-    s1, i1 = torch.gather(scores, 1, o1), torch.gather(idx, 1, o1)
-    s1 = s1 + 0.0                                                 # -0.0 -> +0.0 (top_k compares values)
-    o2 = torch.argsort(s1, dim=1, descending=True, stable=True)
-    return torch.gather(i1, 1, o2)[:, :tp], torch.gather(s1, 1, o2)[:, :tp]
+    idx = torch.where(idx < 0, torch.full_like(idx, 2 ** 31 - 1), idx)
+    _lib.call("hhfm_topn_select", ptr(scores), ptr(idx), None, C_rows, n, n, tp, 0, ptr(out_sc), ptr(out_ids), cur_stream())
+    out_ids = torch.where(out_ids == 2 ** 31 - 1, torch.full_like(out_ids, -1), out_ids)
+    return out_ids, out_sc
 
 
 def gather_rows(t, group=None):
@@ -86,92 +122,60 @@ def gather_rows(t, group=None):
     return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
 
 
-class _RawDeviceBuffer:
-    """Zero-copy view of library-owned device memory for torch.as_tensor (__cuda_array_interface__)."""
+class DpSegment(C.Structure):
+    """hhfm_dp_segment (include/hhfm_sm100.h, K12)."""
+    _fields_ = [("w", C.c_void_p), ("s1", C.c_void_p), ("s2", C.c_void_p), ("offset", C.c_int64), ("n", C.c_int64),
+                ("lamda", C.c_float), ("reserved", C.c_int32)]
 
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
+class SymmExchange:
+    """The exchange buffer of the fused data-parallel step (csrc/p2p.cu): `n_floats` fp32 + a flag array per rank in
+    SYMMETRIC memory -- same size on every rank, mapped into every peer of the box and, where the NVSwitch offers it,
+    bound to one multicast object.  Allocation, handle exchange and mapping are torch.distributed plumbing
+    (`torch.distributed._symmetric_memory`); what moves through the buffers is the kernel's business.
 
-class PeerArena:
-    """Double-buffered EXPORT copy of the gradient arena, shared with the other ranks of the box over CUDA IPC + NVLink
-    (csrc/p2p.cu).  The arena proper stays ordinary device memory; each step its gradient part is copied into bufs[cur].
-
-    bufs[b]      this rank's export buffer b as a float32 tensor
-    table(b, o)  host array with the address of float `o` of arena b on every rank (rank order)
-    barrier()    stream-ordered cross-GPU barrier: every rank's scatter kernels of this step are complete and visible
+    x            this rank's buffer (float32 tensor, n_floats)
+    x_table      host int64[ws]: address of every rank's buffer in this process (rank order, own one included)
+    flag_table   host int64[ws]: address of every rank's flag array (FLAG_INTS int32, zero-initialised)
+    multicast    address of the multicast alias of `x`, or 0
     """
 
     FLAG_INTS = 64
+    MAX_RANKS = 16
 
     def __init__(self, n_floats, device, group=None):
-        import ctypes as C
-        from . import _lib
-        self._lib = _lib
+        import torch.distributed._symmetric_memory as symm
         self.rank, self.ws = world(group)
-        if self.ws > 16:
-            raise _lib.HhfmError("PeerArena: at most 16 ranks")
-        self.device = device
+        if self.ws > self.MAX_RANKS:
+            raise RuntimeError("SymmExchange: at most %d ranks" % self.MAX_RANKS)
         self.n = int(n_floats)
-        nbytes = (self.n * 4 + 255) // 256 * 256
-        self._own = []
-        handles = []
-        for _ in range(2):
-            p = C.c_void_p()
-            h = (C.c_ubyte * 64)()
-            _lib.call("hhfm_p2p_alloc", nbytes, C.byref(p), C.cast(h, C.c_void_p))
-            self._own.append(int(p.value))
-            handles.append(bytes(h))
-        p = C.c_void_p()
-        h = (C.c_ubyte * 64)()
-        _lib.call("hhfm_p2p_alloc", self.FLAG_INTS * 4, C.byref(p), C.cast(h, C.c_void_p))
-        self._own_flags = int(p.value)
-        handles.append(bytes(h))
+        flag_off = (self.n + 63) // 64 * 64                     # flags start on a 256-byte boundary behind the floats
+        total = flag_off + self.FLAG_INTS
+        grp = group if group is not None else dist.group.WORLD
+        self._buf = symm.empty(total, dtype=torch.float32, device=device)
+        self._buf.zero_()
         torch.cuda.synchronize(device)
-        everyone = [None] * self.ws
-        dist.all_gather_object(everyone, handles, group=group)
-        self._opened = []
-        self.base = [[0] * self.ws for _ in range(2)]
-        self.flag_base = [0] * self.ws
-        for r in range(self.ws):
-            for k in range(3):
-                if r == self.rank:
-                    addr = (self._own + [self._own_flags])[k]
-                else:
-                    q = C.c_void_p()
-                    hb = (C.c_ubyte * 64).from_buffer_copy(everyone[r][k])
-                    _lib.call("hhfm_p2p_open", C.cast(hb, C.c_void_p), C.byref(q))
-                    addr = int(q.value)
-                    self._opened.append(addr)
-                if k < 2:
-                    self.base[k][r] = addr
-                else:
-                    self.flag_base[r] = addr
-        self.bufs = [torch.as_tensor(_RawDeviceBuffer(self._own[b], (self.n,), "<f4"), device=device) for b in range(2)]
-        self._flag_table = (C.c_int64 * self.ws)(*self.flag_base)
-        self._tables = {}
-        self.epoch = 0
-        self.cur = 0
-        dist.barrier(group=group)
-
-    def table(self, b, offset_floats):
-        import ctypes as C
-        key = (b, int(offset_floats))
-        t = self._tables.get(key)
-        if t is None:
-            t = (C.c_int64 * self.ws)(*[self.base[b][r] + 4 * int(offset_floats) for r in range(self.ws)])
-            self._tables[key] = t
-        return t
-
-    def barrier(self):
-        from .engine import cur_stream
-        self.epoch += 1
-        self._lib.call("hhfm_p2p_barrier", self._flag_table, self.rank, self.ws, self.epoch, cur_stream())
+        self._hdl = symm.rendezvous(self._buf, grp.group_name)
+        base = [int(p) for p in self._hdl.buffer_ptrs]
+        off = int(self._buf.data_ptr()) - base[self.rank]        # the tensor's offset inside its allocation block
+        if off < 0:
+            raise RuntimeError("SymmExchange: tensor lies outside its symmetric block")
+        self.x = self._buf[:self.n]
+        self.x_table = (C.c_int64 * self.ws)(*[b + off for b in base])
+        self.flag_table = (C.c_int64 * self.ws)(*[b + off + 4 * flag_off for b in base])
+        mc = 0
+        try:
+            if bool(getattr(self._hdl, "has_multicast_support", False)):
+                mc = int(self._hdl.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.multicast = (mc + off) if mc else 0
+        dist.barrier(group=group)                                # every rank has zeroed its buffer before anyone signals
 
     def close(self):
-        for a in self._opened:
-            self._lib.call("hhfm_p2p_close", a)
-        self._opened = []
+        self._hdl = None
+        self._buf = None
+        self.x = None
 
 
 def allreduce_metrics(codes, group=None):

@@ -277,14 +277,6 @@ class Optimizer:
 
     KIND_ID = {"adagrad": 0, "adam": 1, "momentum": 2, "sgd": 3}
 
-    def apply_dense_p2p(self, name, w, grad_table, n_ranks, g_zero, lamda=0.0, sq_partials=None):
-        """Dense update with the gradient summed over the ranks' arenas inside the kernel (csrc/p2p.cu)."""
-        s1, s2 = self.slots(name, w)
-        lr = self._lr_t() if self.kind == "adam" else self.lr
-        b1 = self.momentum if self.kind == "momentum" else self.beta1
-        _lib.call("hhfm_opt_dense_l2_p2p", self.KIND_ID[self.kind], ptr(w), ptr(s1), ptr(s2), grad_table, n_ranks, ptr(g_zero),
-                  w.numel(), lr, lamda, b1, self.beta2, self.eps, ptr(sq_partials), cur_stream())
-
     def apply_rows(self, name, w, g, rows, n_rows_dev, K, zero_grad=True):
         """Sparse (IndexedSlices) update: only the touched rows move.  TF1's sparse Adam moves every row, so it
         maps to the dense kernel."""

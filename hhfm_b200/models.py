@@ -68,7 +68,13 @@ class _Base:
         n_b = self._M if with_bias else 0
         self._arena_layout = (n_v, n_b, P)
         self._with_bias_grad = with_bias
-        self._peer = None
+        self._dpx = None            # dist.SymmExchange once enable_data_parallel() mapped the peers
+        self._fused = os.environ.get("HHFM_FUSED_STEP", "1") != "0"      # fold + exchange + optimizer + loss in one kernel
+        self._dp_state = torch.zeros(4, dtype=torch.int32, device=self.device)      # [step counter, sticky error, -, -]
+        self._dp_state_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+        self._reg_ws = torch.zeros(256, dtype=torch.float32, device=self.device)
+        self._x_local = None
+        self._segs = None
         self._bind_arena(torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device))
         self._sq_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
         self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -113,10 +119,13 @@ class _Base:
         return self._hot
 
     # ---- data parallel: batch rows sharded across ranks, one all-reduce of the arena ----
-    def enable_data_parallel(self, group=None, p2p="auto", sparse="auto"):
-        """Batch rows sharded across the ranks of `group`, weights replicated.  On CUDA the gradient
-        exchange is fused into the optimizer over NVLink peer memory (dist.PeerArena, csrc/p2p.cu); `p2p=False`, or a box
-        where CUDA IPC is unavailable, falls back to one NCCL all-reduce of the arena per step.
+    def enable_data_parallel(self, group=None, fused="auto", sparse="auto", p2p=None):
+        """Batch rows sharded across the ranks of `group`, weights replicated.  On one NVLink box the gradient
+        exchange is fused with the hot-replica fold, the optimizer and the loss reduction into ONE kernel over symmetric
+        memory (dist.SymmExchange, csrc/p2p.cu: multimem.ld_reduce / multimem.st through the NVSwitch, peer loads / stores
+        without multicast); `fused=False`, `HHFM_DP_FUSED=0`, a model with further dense variables (AFM, DeepFM) or a box
+        where symmetric memory cannot be mapped use one NCCL all-reduce of the arena per step.  `p2p` is the old name of
+        `fused`.
 
         `sparse`: exchange the COALESCED touched rows (row id + gradient row, all-gather) instead of the dense [M, K]
         gradient, then add the ranks' lists in rank order and run the touched-row optimizer on the union.  Only for
@@ -126,12 +135,15 @@ class _Base:
         from . import dist as hd
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
+        if p2p is not None:
+            fused = p2p
         self._dp_group = group if group is not None else dist.group.WORLD
         for w in self.weights.values():
             dist.broadcast(w, src=0, group=self._dp_group)
-        self._peer = None
+        self._version += 1           # the broadcast changed the weights: cached top-N item operands are stale
+        self._dpx = None
+        self._segs = None
         ws = dist.get_world_size(self._dp_group)
-        import os
         env_s = os.environ.get("HHFM_DP_SPARSE")
         if env_s in ("0", "1"):
             sparse = env_s == "1"
@@ -142,51 +154,119 @@ class _Base:
             if self._opt.kind == "momentum":
                 raise NotImplementedError("sparse Momentum under data parallelism is not implemented")
             return
-        env = os.environ.get("HHFM_DP_P2P")               # 0 / 1 force the NCCL all-reduce / the peer-memory exchange
+        env = os.environ.get("HHFM_DP_FUSED", os.environ.get("HHFM_DP_P2P"))      # 0 / 1 force NCCL / the fused exchange
         if env == "0":
-            p2p = False
+            fused = False
         elif env == "1":
-            p2p = True
-        elif p2p == "auto" and ws > 2:
-            # measured on 8 B200 (bench.py, 200 steps): NCCL all-reduce (NVLS) 0.794 ms/step, peer-memory exchange 0.854 ms/step
-            # (2 GPUs: 0.80-0.86 both); the fused exchange stays the default only where it is not slower
-            p2p = False
-        if p2p and ws > 1 and self.device.type == "cuda":
-            peer, ok = None, 1
+            fused = True
+        want = bool(fused) and ws > 1 and self.device.type == "cuda" and self._fused_segments() is not None \
+            and self._opt.kind != "momentum"
+        if not want:
+            if fused is True and ws > 1:
+                raise _lib.HhfmError("enable_data_parallel: the fused exchange does not cover this model / optimizer")
+            return
+        # every phase that can fail on one rank only is followed by ONE all-reduce that agrees on the outcome, so the
+        # ranks never sit in different collectives
+        def agree(ok):
+            flag = torch.tensor([1 if ok else 0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._dp_group)
+            return int(flag.item()) == 1
+
+        dpx, err = None, None
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401  (phase 1: is the facility there at all)
+        except Exception as e:                           # pragma: no cover
+            err = e
+        if agree(err is None):
             try:
                 n_v, n_b, _ = self._arena_layout
-                peer = hd.PeerArena(n_v + n_b + 4, self.device, self._dp_group)      # gradients + gb0 + the loss slot
-            except _lib.HhfmError:
-                if p2p is True:
-                    raise
-                ok = 0
-            flag = torch.tensor([ok], device=self.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._dp_group)
-            if int(flag.item()) == 1:
-                self._peer = peer
-            elif p2p is True:
-                raise _lib.HhfmError("enable_data_parallel: a rank could not map its peers' arenas")
+                n_x = int(_lib.load().hhfm_dp_exchange_floats(n_v + n_b + 1))
+                dpx = hd.SymmExchange(n_x, self.device, self._dp_group)      # collective (phase 2)
+            except Exception as e:
+                err = e
+            if not agree(dpx is not None):
+                if dpx is not None:
+                    dpx.close()
+                dpx = None
+        if dpx is None:
+            if fused is True:
+                raise _lib.HhfmError("enable_data_parallel: symmetric memory is unavailable on this box (%r)" % (err,))
+            return
+        self._dpx = dpx
+        self._dp_state.zero_()
+
+    def _fused_segments(self):
+        """[(name, weight, gradient offset in the arena, n, lamda)] of the variables the fused tail updates, or None when
+        the model has dense variables outside the arena (AFM, DeepFM, WD)."""
+        return None
+
+    def _use_fused_tail(self):
+        """The one-kernel tail (csrc/p2p.cu) replaces hot_fold + [all-reduce] + dense optimizer + loss_finalize whenever the
+        dense optimizer kernels would run; the touched-row (IndexedSlices) path and Momentum keep their own kernels."""
+        if not self._fused or self._fused_segments() is None or self._opt.kind == "momentum":
+            return False
+        if self._dp_group is not None:
+            return self._dpx is not None
+        return self._lamda > 0
+
+    def _fused_tail(self, hot, with_hot_bias):
+        from . import dist as hd
+        import ctypes as C
+        if self._segs is None:
+            segs = self._fused_segments()
+            arr = (hd.DpSegment * len(segs))()
+            keep = []
+            for i, (name, w, off, n, lam) in enumerate(segs):
+                s1, s2 = self._opt.slots(name, w)
+                arr[i].w, arr[i].s1, arr[i].s2 = w.data_ptr(), (s1.data_ptr() if s1 is not None else None), \
+                    (s2.data_ptr() if s2 is not None else None)
+                arr[i].offset, arr[i].n, arr[i].lamda = int(off), int(n), float(lam)
+                keep.append((w, s1, s2))
+            self._segs = (arr, len(segs), keep)
+        arr, n_seg, _ = self._segs
+        n_v, n_b, _ = self._arena_layout
+        n_g = n_v + n_b + 1
+        o = self._opt
+        lr = o._lr_t() if o.kind == "adam" else o.lr
+        dpx = self._dpx
+        if dpx is None:
+            if self._x_local is None:
+                self._x_local = torch.zeros(int(_lib.load().hhfm_dp_exchange_floats(n_g)), dtype=torch.float32, device=self.device)
+            x, mc, xt, ft, rank, ws = self._x_local, None, None, None, 0, 1
+        else:
+            x, mc, xt, ft, rank, ws = dpx.x, (C.c_void_p(dpx.multicast) if dpx.multicast else None), dpx.x_table, dpx.flag_table, \
+                dpx.rank, dpx.ws
+        if hot is not None:
+            hargs = (ptr(hot.ghot), ptr(hot.ghot_bias) if with_hot_bias else None, hot.n_rep, hot.n_hot, self._K, ptr(hot.rows), n_v)
+        else:
+            hargs = (None, None, 0, 0, self._K, None, n_v)
+        _lib.call("hhfm_dp_step", o.KIND_ID[o.kind], C.cast(arr, C.c_void_p), n_seg, ptr(self._arena), n_g, *hargs,
+                  ptr(self._loss_partials), ptr(x), mc, xt, ft, rank, ws, ptr(self._dp_state), lr, o.beta1, o.beta2, o.eps,
+                  ptr(self._reg_ws), ptr(self._loss_dev), float(os.environ.get("HHFM_DP_TIMEOUT_S", "120")), cur_stream())
+        self._version += 1
+
+    def _finish_step(self, hot, with_hot_bias, bias_step=None):
+        """Everything after the scatter kernels of a step: fold, exchange, optimizer, loss."""
+        if self._use_fused_tail():
+            self._fused_tail(hot, with_hot_bias)
+            return
+        if hot:
+            hot.fold(self._gV, self._gb if with_hot_bias else None)
+        self._allreduce_grads()
+        with_reg = self._apply_table(sparse_ok=True)
+        if bias_step is not None:
+            bias_step()
+        self._enqueue_loss(with_reg)
 
     def _allreduce_grads(self):
-        """Make every rank's gradients of this step available: a cross-GPU barrier when the optimizer sums the peers'
-        arenas itself, otherwise an all-reduce of the arena."""
+        """NCCL path: one all-reduce of the arena (dense) or the coalesced-sparse row exchange."""
         if self._dp_group is None:
             return
         if self._dp_sparse:
             self._exchange_sparse_rows()
             return
-        if self._peer is not None:
-            # publish this rank's loss as ONE float (arena slot after gb0): the peers then read n_ranks floats instead of
-            # n_ranks x 2048 partial slots.  The arena itself stays ordinary device memory (scattering straight into the
-            # IPC-exported buffer made the scatter kernel 5 % slower); its gradient part is copied into the current export
-            # buffer, then the barrier publishes it.
-            pr = self._peer
-            _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), None, 0.0, ptr(self._loss_local), cur_stream())
-            pr.bufs[pr.cur].copy_(self._arena[:pr.n], non_blocking=True)
-            pr.barrier()
-        else:
-            import torch.distributed as dist
-            dist.all_reduce(self._arena, group=self._dp_group)
+        import torch.distributed as dist
+        dist.all_reduce(self._arena, group=self._dp_group)
 
     def _exchange_sparse_rows(self):
         """SURVEY 8e, tables too large for a dense all-reduce: all-gather the coalesced (row id, gradient row) lists, clear
@@ -220,13 +300,7 @@ class _Base:
 
     def _apply_arena_dense(self, name, w, g, lamda, sq):
         """Dense optimizer step for a tensor whose gradient `g` is a slice of the arena."""
-        if self._peer is None:
-            self._opt.apply_dense(name, w, g, lamda, sq)
-            return
-        pr = self._peer
-        off = (g.data_ptr() - self._arena.data_ptr()) // 4
-        # sum the ranks' export buffers; the local arena slice (never read by a peer) is cleared in place for the next step
-        self._opt.apply_dense_p2p(name, w, pr.table(pr.cur, off), pr.ws, g, lamda, sq)
+        self._opt.apply_dense(name, w, g, lamda, sq)
 
     def enable_item_sharding(self, group=None):
         """Full-catalog top-N with the item catalog sharded across the ranks of `group`: every rank
@@ -280,24 +354,22 @@ class _Base:
 
     def _enqueue_loss(self, with_reg, half_lamda=None):
         """Deterministic reduction of the per-CTA loss partials (+ regulariser) into `_loss_dev`; no host sync.  Under data
-        parallelism the loss is the sum over all ranks (the reference loss is a sum over the batch, FM.py:124).  This is
-        the last call of a step: the peer arena flips to its other buffer here."""
+        parallelism the partials were all-reduced with the arena, so the loss is the sum over all ranks (the reference loss
+        is a sum over the batch, FM.py:124)."""
         self._version += 1
         hl = (0.5 * self._lamda) if half_lamda is None else half_lamda
         sq = ptr(self._sq_partials) if with_reg else None
-        if self._peer is None:
-            _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), sq, hl if with_reg else 0.0, ptr(self._loss_dev),
-                      cur_stream())
-            return
-        pr = self._peer
-        off = (self._loss_local.data_ptr() - self._arena.data_ptr()) // 4
-        _lib.call("hhfm_loss_finalize_p2p", pr.table(pr.cur, off), pr.ws, 1, sq, hl if with_reg else 0.0, ptr(self._loss_dev),
+        _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), sq, hl if with_reg else 0.0, ptr(self._loss_dev),
                   cur_stream())
-        pr.cur ^= 1          # the other export buffer next step: this one may still be read by a slower peer
 
     def _read_loss(self):
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
+        if self._dpx is not None:
+            self._dp_state_host.copy_(self._dp_state, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if self._dpx is not None and int(self._dp_state_host[1]) != 0:
+            raise _lib.HhfmError("data-parallel step: a peer did not reach the cross-GPU barrier within HHFM_DP_TIMEOUT_S; "
+                                 "the replicas are no longer in step (the CUDA context is intact)")
         return float(self._loss_host[0])
 
     def _upload_rows(self, X):
@@ -401,18 +473,25 @@ class FM(_Base):
                   self._K, self.interaction, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0),
                   ptr(self._loss_partials), ts, stamp, tr, tc, *(hot.args(True) if hot else NO_HOT_BIAS),
                   1 if self.deterministic else 0, cur_stream())
-        if hot:
-            hot.fold(self._gV, self._gb)
-        self._allreduce_grads()
-        with_reg = self._apply_table(sparse_ok=True)
-        if bias is not None:
-            self._apply_bias()
-        self._enqueue_loss(with_reg)
+        self._finish_step(hot, True, self._apply_bias if bias is not None else None)
+
+    def _fused_segments(self):
+        n_v, n_b, _ = self._arena_layout
+        segs = [("feature_embeddings", self.weights["feature_embeddings"], 0, n_v, self._lamda if self._lamda > 0 else 0.0)]
+        if self._with_bias_grad and n_b:
+            # feature_bias receives IndexedSlices; for Adagrad / SGD rows with g = 0 do not move and TF1's sparse Adam
+            # moves every row, so the dense update is exact for the optimizers the fused tail covers
+            segs.append(("feature_bias", self.weights["feature_bias"], n_v, n_b, 0.0))
+        if getattr(self, "_b0", None) is not None:
+            segs.append(("bias", self._b0, n_v + n_b, 1, 0.0))
+        return segs
 
     def _apply_bias(self):
         # feature_bias receives IndexedSlices (only touched rows move); the scalar bias is dense.
         bias = self.weights["feature_bias"]
-        if self._opt.kind == "momentum" and self._dp_group is None:
+        if self._opt.kind == "momentum":
+            if self._dp_group is not None:
+                raise NotImplementedError("sparse Momentum under data parallelism is not implemented")
             self._opt.apply_rows("feature_bias", bias, self._gb, self._touch.rows, self._touch.count, 1)
         else:
             self._apply_arena_dense("feature_bias", bias, self._gb, 0.0, None)
@@ -498,11 +577,11 @@ class MF(FM):
         _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, 2, ptr(V), None, None, self._M, self._K, 1, ptr(y),
                   None, ptr(self._gV), None, None, ptr(self._loss_partials), ts, stamp, tr, tc,
                   *(hot.args(True) if hot else NO_HOT_BIAS), 1 if self.deterministic else 0, cur_stream())
-        if hot:
-            hot.fold(self._gV, None)
-        self._allreduce_grads()
-        with_reg = self._apply_table(sparse_ok=True)
-        self._enqueue_loss(with_reg)
+        self._finish_step(hot, False)
+
+    def _fused_segments(self):
+        n_v = self._arena_layout[0]
+        return [("feature_embeddings", self.weights["feature_embeddings"], 0, n_v, self._lamda if self._lamda > 0 else 0.0)]
 
     def topk(self, A, tp=100):
         return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, tp)
@@ -533,11 +612,11 @@ class _PairRank(_Base):
         _lib.call("hhfm_pairrank_fwd_bwd", ptr(idx), B, stride, n_ctx, n_time, n_neg, pc, pt, pf, ptr(V), self._M,
                   self._K, None, None, ptr(self._gV), ptr(self._loss_partials), ts, stamp, tr, tc,
                   *(hot.args() if hot else NO_HOT), 1 if self.deterministic else 0, cur_stream())
-        if hot:
-            hot.fold(self._gV, None)
-        self._allreduce_grads()
-        with_reg = self._apply_table(sparse_ok=True)
-        self._enqueue_loss(with_reg)
+        self._finish_step(hot, False)
+
+    def _fused_segments(self):
+        n_v = self._arena_layout[0]
+        return [("feature_embeddings", self.weights["feature_embeddings"], 0, n_v, self._lamda if self._lamda > 0 else 0.0)]
 
     def _positive_feedback(self, parts, n_ctx, n_time):
         idx, stride = self._upload_ids(parts)
@@ -726,6 +805,9 @@ class AFM(FM):
         self._gbatt = torch.zeros(A, dtype=torch.float32, device=dev)
         self._gp = torch.zeros(A, dtype=torch.float32, device=dev)
         self._gwp = torch.zeros(K, dtype=torch.float32, device=dev)
+
+    def _fused_segments(self):
+        return None            # attention_W / b / p and the projection are dense variables outside the arena
 
     def _small(self):
         w = self.weights

@@ -334,29 +334,46 @@ int hhfm_hot_fold(float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot, i
 int hhfm_loss_finalize(const float* loss_partials, const float* sq_partials, float half_lamda, float* loss_out,
                        hhfm_stream_t stream);
 
+/* Measurement aid: stream `n_floats` floats `iters` times with L1-bypassing 16-byte loads (an L2-resident buffer gives the
+ * L2 -> SM read bandwidth that bench.py quotes as the peak of the L2-bound gather kernels). */
+int hhfm_l2_read_sweep(const float* buf, int64_t n_floats, int32_t iters, float* sink, hhfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
- * Data-parallel exchange over NVLink peer memory, fused into the optimizer (p2p.cu).
- * hhfm_p2p_alloc: cudaMalloc'd, zeroed buffer + its 64-byte CUDA IPC handle; hhfm_p2p_open maps a peer's handle
- * (one process per GPU on one box).  *_ptrs_host arguments are HOST arrays of n_ranks device addresses (rank order),
- * this rank's own buffer included.
- * hhfm_p2p_barrier: stream-ordered cross-GPU barrier (system-scope release/acquire flags; flags buffers hold >= n_ranks
- *   int32 per rank, zero-initialised; `epoch` must increase by one per call).
- * hhfm_opt_dense_l2_p2p: w/state update with g = sum over ranks (fixed rank order => bit-identical replicas) of
- *   grad_r[i] + lamda*w; g_zero (may be NULL) is a LOCAL buffer cleared on the way (the other half of a double-buffered
- *   gradient arena).  beta1 carries the momentum for HHFM_OPT_MOMENTUM, lr is lr_t for Adam.
- * hhfm_loss_finalize_p2p: loss = sum over ranks of n_per_rank published values (the callers publish their locally reduced
- *   loss, n_per_rank = 1) + half_lamda * sum(sq_partials).
+ * K12  data-parallel training step (p2p.cu): hot-replica fold + cross-GPU all-reduce of the gradient arena
+ *   + TF1 optimizer + loss reduction in ONE persistent cooperative kernel.  The reference has no distributed code; this
+ *   replaces what `optimizer.minimize` (FM.py:129-136, OurModel7.py:185-189) does after the gradients exist, for a batch
+ *   whose rows are sharded across the GPUs of one box.
+ *
+ *   arena        rank-private gradient buffer; floats [0, n_grad) are consumed (and cleared); gV occupies [0, M*K).
+ *   segs         up to 4 variables whose gradients are arena[offset, offset+n): w / s1 / s2 as in K5, lamda per segment
+ *                (g_eff = g + lamda*w; the loss gets 0.5*lamda*sum(w^2) of the weights BEFORE the update).
+ *   ghot...      the two-level scatter plan of K1/K3 (NULL / 0 = none); bias_off = offset of the feature_bias gradient.
+ *   x_local      this rank's exchange buffer, hhfm_dp_exchange_floats(n_grad) floats.  For n_ranks > 1 it must be symmetric
+ *                memory: x_peers_host[r] = address of rank r's buffer in THIS process (own one included), x_multicast =
+ *                the multicast alias of the same buffers (multimem.ld_reduce / multimem.st) or NULL (peer loads / stores).
+ *   flag_peers_host[r]  address of rank r's flag array (>= 16 int32, zero-initialised, symmetric memory).
+ *   state        device int32[4]: [0] step counter (starts 0, owned by the kernel), [1] sticky error flag -- set when a
+ *                cross-GPU barrier waited longer than timeout_s (<= 0: 120 s); later steps return at once, the host
+ *                reads it back with the loss.  No trap: the CUDA context stays usable.
+ *   reg_workspace  >= 256 floats.   loss_out[0] = sum over ranks of sum(loss_partials) + regulariser.
+ *   Adam: `lr` is lr_t (K5); Momentum: beta1 carries the momentum.  All replicas consume the same reduced bits, so they
+ *   stay bit-identical.  n_ranks == 1: fold + optimizer + loss of a single-GPU step in one launch.
  * ------------------------------------------------------------------------------------------------ */
-int hhfm_p2p_alloc(int64_t bytes, void** dev_ptr, void* handle64);
-int hhfm_p2p_open(const void* handle64, void** dev_ptr);
-int hhfm_p2p_close(void* dev_ptr);
-int hhfm_p2p_free(void* dev_ptr);
-int hhfm_p2p_barrier(const int64_t* flag_ptrs_host, int32_t rank, int32_t n_ranks, int32_t epoch, hhfm_stream_t stream);
-int hhfm_opt_dense_l2_p2p(int32_t kind, float* w, float* s1, float* s2, const int64_t* grad_ptrs_host, int32_t n_ranks,
-                          float* g_zero, int64_t n, float lr, float lamda, float beta1, float beta2, float eps,
-                          float* sq_partials, hhfm_stream_t stream);
-int hhfm_loss_finalize_p2p(const int64_t* partial_ptrs_host, int32_t n_ranks, int32_t n_per_rank, const float* sq_partials,
-                           float half_lamda, float* loss_out, hhfm_stream_t stream);
+typedef struct {
+  float* w;
+  float* s1;
+  float* s2;
+  int64_t offset;
+  int64_t n;
+  float lamda;
+  int32_t reserved;
+} hhfm_dp_segment;
+int64_t hhfm_dp_exchange_floats(int64_t n_grad);
+int hhfm_dp_step(int32_t kind, const hhfm_dp_segment* segs, int32_t n_segs, float* arena, int64_t n_grad, float* ghot,
+                 float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K, const int32_t* hot_rows, int64_t bias_off,
+                 const float* loss_partials, float* x_local, float* x_multicast, const int64_t* x_peers_host,
+                 const int64_t* flag_peers_host, int32_t rank, int32_t n_ranks, int32_t* state, float lr, float beta1,
+                 float beta2, float eps, float* reg_workspace, float* loss_out, double timeout_s, hhfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10  CARS2 (CARS2.py:66-187), the context-aware baseline of main.py:50-63.

@@ -111,6 +111,50 @@ def run_fm_c5(args, dev):
                          "frac": B * algo / ms / 1e6 / peaks()}}
 
 
+def run_hhfm_c5(args, dev):
+    """OurModel7 (HHFM) at the scaled c5 shape: M = 10^7 ids (4 M users, 1 M items, 8 context columns of
+    625 000 values), K = 128, NG = 10, B = 2^20 positives, sparse (lamda = 0) Adagrad rows.  The 5.1 GB table lives in HBM,
+    so this is the configuration where the headline model is HBM-bound.  Algorithmic bytes per positive: ids 80 + gather
+    (F+NG) = 20 rows x 512 B + scatter 11 rows x 512 B (user, item+, 8 context rows, the arg-max negative) + optimizer
+    20*K B per unique touched row."""
+    import torch
+    from hhfm_b200.models import OUR
+    from hhfm_b200.engine import Staging, pack_records
+    rng = np.random.default_rng(55)
+    B, K, NG = 1 << 20, 128, 10
+    n_user, n_item, n_ctx_ids = 4_000_000, 1_000_000, 5_000_000
+    M = n_user + n_item + n_ctx_ids
+    per_ctx = n_ctx_ids // 8
+    recs, uniq = [], 0
+    for b in range(3):
+        X = np.stack([zipf_ids(rng, n_user, B), n_user + zipf_ids(rng, n_item, B)], 1).astype(np.int64)
+        base = n_user + n_item
+        cols = []
+        for c in range(8):
+            cols.append(base + rng.integers(0, per_ctx, B))
+            base += per_ctx
+        F1 = np.stack(cols, 1).astype(np.int64)
+        Y = (n_user + rng.integers(0, n_item, (B, NG))).astype(np.int64)
+        stg = Staging(torch.int32, dev)
+        host, stride = pack_records([X, F1, Y], M, stg)
+        recs.append(stg.upload(host.numel()).view(B, stride).clone())
+        del stg
+    m = OUR(8, 0, M, n_user, n_item, K, 0.1, 0.0, "AdagradOptimizer", True, False)     # lamda = 0: IndexedSlices rows
+    ev = []
+
+    def step(i):
+        m.fit_device(recs[i % 3], 8, 0, NG)
+    ms = timed(step, args.steps, 3)
+    uniq = int(m._touch.count.item())                 # rows touched by the last step
+    algo = 80 + 20 * 4 * K + 11 * 4 * K + 20 * K * uniq / B
+    del ev
+    return {"config": "c5-shaped HHFM (F=10, NG=10, M=10^7, K=128, sparse Adagrad rows), B=2^20, %d touched rows/step" % uniq,
+            "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
+            "roofline": {"bound": "hbm", "kernel": "pairrank_sum_train_staged_kernel + opt_rows_kernel (whole step)",
+                         "achieved": B * algo / ms / 1e6, "peak": peaks(), "unit": "GB/s", "frac": B * algo / ms / 1e6 / peaks(),
+                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)"}}
+
+
 def run_bpr_c4(args, dev):
     import torch
     from hhfm_b200.models import BPR
@@ -178,7 +222,7 @@ def run_dfm(args, dev):
                                  "peak / 2 / 3 = 271 TFLOP/s fp32-equivalent) see profiles/r1_dfm_summary.md"}}
 
 
-RUNNERS = {"fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
+RUNNERS = {"hhfm_c5": run_hhfm_c5, "fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
 
 
 def main():

@@ -68,8 +68,23 @@ def _eval_shards(rank, world):
     local = O.topk_lowest_index(score[:, lo:hi], tp)
     ls = torch.from_numpy(np.take_along_axis(score[:, lo:hi], local, axis=1))
     li = torch.from_numpy(local + lo)
-    ids, sc = hd.merge_topk(ls, li, tp)
+    # the exchange is torch.distributed plumbing (gloo here); the product selects with a device kernel, this test with a
+    # stable sort by id followed by a stable sort by descending score
+    def select(scores, idx):
+        o1 = torch.argsort(idx, dim=1, stable=True)
+        s1, i1 = torch.gather(scores, 1, o1) + 0.0, torch.gather(idx, 1, o1)
+        o2 = torch.argsort(s1, dim=1, descending=True, stable=True)
+        return torch.gather(i1, 1, o2)[:, :tp], torch.gather(s1, 1, o2)[:, :tp]
+    ids, sc = select(*hd.gather_candidates(ls, li))
     want = O.topk_lowest_index(score, tp)
+    # context-sharded variant (all-to-all): pad the 9 rows to a multiple of the world size
+    pad = (-C) % world
+    ls_p = torch.cat([ls, torch.zeros(pad, tp)]); li_p = torch.cat([li, torch.zeros(pad, tp, dtype=li.dtype)])
+    ids_s, _ = select(*hd.exchange_candidates_sharded(ls_p, li_p))
+    per = (C + pad) // world
+    rows = slice(rank * per, min(C, (rank + 1) * per))
+    if not (ids_s.numpy()[:rows.stop - rows.start] == want[rows]).all():
+        return (False, False, False)
     codes = torch.arange(lo, hi, dtype=torch.int32)
     allc = hd.gather_rows(codes)
     return ((ids.numpy() == want).all(), (sc.numpy() == np.take_along_axis(score, want, axis=1)).all(), allc.tolist() == list(range(N)))

@@ -31,11 +31,11 @@ def _worker(rank, world, port, ret):
         lo, hi = hd.shard_range(B, rank, world)
         finals = {}
         results = []
-        for mode in ("auto", False):           # NVLink peer-arena exchange fused into the optimizer / NCCL all-reduce
+        for mode in ("auto", False):           # fused fold + multimem all-reduce + optimizer kernel / NCCL all-reduce
             model = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, 'AdagradOptimizer', True, False)
             model.enable_data_parallel(p2p=mode); model.enable_item_sharding()
             if world > 1 and mode == "auto":
-                assert model._peer is not None, "CUDA IPC peer mapping should be available on one box"
+                assert model._dpx is not None, "symmetric memory should be available on one NVLink box"
             V = model.get_weights()["feature_embeddings"].copy()
             loss = model.partial_fit({"X": X[lo:hi], "F1": F1[lo:hi], "Y": Y[lo:hi]})
             loss_ref, _, _, dV = O.pairrank_loss_grads(V, X, Y, F1, None, (0, 0, 0), 0.01)

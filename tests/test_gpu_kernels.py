@@ -805,6 +805,49 @@ def test_fm_staged_pipeline_with_hot_rows(cuda, monkeypatch):
     assert_close(gV.cpu().numpy(), dV, what="fm gV hot staged"); assert_close(gb.cpu().numpy(), db, what="fm gb hot staged")
 
 
+@pytest.mark.parametrize("K,fc,ft,NG,B", [(128, 8, 0, 10, 5000), (64, 8, 0, 10, 3001), (128, 5, 5, 10, 999), (256, 3, 0, 4, 777),
+                                          (128, 0, 0, 10, 2049), (512, 2, 1, 1, 65), (64, 10, 10, 10, 1500)])
+@pytest.mark.parametrize("use_hot", [False, True])
+def test_pairrank_staged_pipeline_matches_oracle(cuda, K, fc, ft, NG, B, use_hot, monkeypatch):
+    """pairrank_sum_train_staged_kernel (cp.async.bulk row staging + mbarriers; chosen automatically when the table exceeds
+    L2, the scaled c5 shape) forced on small inputs: loss / gradient / touched-row set against the oracle, and against the
+    register kernel."""
+    lib, ptr, st = _lib_ptr()
+    from hhfm_b200.engine import NO_HOT, HotRows
+    rng = np.random.default_rng(K + fc + ft + NG)
+    M = 700
+    V = make_table(rng, M, K)
+    Pos = np.stack([rng.integers(0, 6, B), rng.integers(100, 400, B)], axis=1)
+    Fea = np.stack([600 + 3 * c + rng.integers(0, 3, B) for c in range(fc)], axis=1) if fc else None
+    Tim = rng.integers(100, 400, (B, ft)) if ft else None
+    Neg = rng.integers(100, 400, (B, NG)); Neg[::9] = Neg[::9, :1]
+    if NG > 5:
+        Neg[:, 5] = Neg[:, 4]
+    loss, pos, neg, dV = O.pairrank_loss_grads(V, Pos, Neg, Fea, Tim, (0, 0, 0), 0.0)
+    rec, stride = _records(Pos, Fea, Tim, Neg)
+    P = lib.partials_len()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HHFM_PR_STAGED", mode)
+        hot = HotRows(np.concatenate([np.arange(6), np.arange(600, 600 + 3 * fc)]), M, K, cuda, n_rep=8) if use_hot else None
+        gV = torch.zeros(M, K, device=cuda); lp = torch.zeros(P, device=cuda); out = torch.zeros(1, device=cuda)
+        stamp = torch.zeros(M, dtype=torch.int32, device=cuda); rows = torch.zeros(M, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+        lib.call("hhfm_pairrank_fwd_bwd", ptr(dev(rec, cuda)), B, stride, fc, ft, NG, 0, 0, 0, ptr(dev(V, cuda)), M, K, None, None,
+                 ptr(gV), ptr(lp), ptr(stamp), 5, ptr(rows), ptr(cnt), *(hot.args() if hot else NO_HOT), 0, st())
+        if hot:
+            hot.fold(gV, None)
+        lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(out), st())
+        n = int(cnt.item())
+        res[mode] = (gV.cpu().numpy(), float(out.item()), np.sort(rows[:n].cpu().numpy()))
+    for mode, (gV, l, touched) in res.items():
+        assert_close(l, loss, what="staged=%s loss" % mode); assert_close(gV, dV, what="staged=%s gV" % mode)
+        assert len(set(touched.tolist())) == len(touched)
+        nz = np.flatnonzero(np.abs(dV).sum(1) > 0)
+        assert set(nz.tolist()) <= set(touched.tolist())
+    assert (res["1"][2] == res["0"][2]).all(), "the staged and the register kernel disagree on the touched rows"
+
+
 # ----------------------------------------------------------------------------------------------------
 # K6 tensor-core path, sampled cut (large catalogs): the cut is a rank statistic of every 8th item tile, proven per row
 # after rescoring; rows that cannot be proven are redone exactly.  Lists must stay bit-identical.
