@@ -65,7 +65,7 @@ class Train(PairwiseTrain):
         return np.clip(pos, 0, len(self._ctx_keys) - 1)
 
     def run_epoch(self):
-        pos = np.array(self.data.Train_data.values[:, 1:])
+        pos = self._train_values()[:, 1:]                    # persistent view: the in-place shuffle composes across epochs
         np.random.shuffle(pos)                               # CARS2.py:247
         neg = self.sample_negative(pos, self.NG)
         fea = self.context_ids(pos)

@@ -23,6 +23,8 @@ SIGNATURES = {
     "hhfm_fm_fwd": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp],
     "hhfm_fm_fwd_bwd_sqloss": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp,
                                vp, vp, vp, vp, i32, i32, i32, vp],
+    "hhfm_fm_fwd_bwd_sqloss_dropout": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp,
+                                       vp, vp, vp, vp, i32, i32, i32, f32, C.c_uint64, vp],
     "hhfm_fm_bwd": [vp, vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, i32, vp],
     "hhfm_afm_fwd": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp],
     "hhfm_afm_fwd_bwd_sqloss": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
@@ -39,9 +41,6 @@ SIGNATURES = {
     "hhfm_gemm_tn_tf32x3": [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp, vp],
     "hhfm_afm_topn_supported": [i64, i64, i64],
     "hhfm_afm_topn_scores": [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp],
-    "hhfm_afm_fwd_tc": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp],
-    "hhfm_afm_fwd_bwd_sqloss_tc": [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                   vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
     "hhfm_pairrank_fwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp],
     "hhfm_pairrank_fwd_bwd": [vp, i64, i64, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, vp, i32, vp,
                               vp, vp, vp, i32, i32, i32, vp],
@@ -79,7 +78,6 @@ INT64_FUNCS = {
     "hhfm_topn_tc_item_operand_bytes": [i32, i64, i64],
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
-    "hhfm_workspace_bytes_afm": [i64, i64, i64, i64],
     "hhfm_dp_exchange_floats": [i64],
     "hhfm_workspace_bytes_dfm_topn": [i64, i64, i64, i64, i32, vp],
     "hhfm_cars2_param_count": [i64, i64, i64, i64, i64, i64],

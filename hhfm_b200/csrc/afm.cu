@@ -10,44 +10,14 @@
 // The weight gradient dW = sum P_p^T dZ_p is accumulated in REGISTERS: warp w owns the k-slice [w K/NW, (w+1) K/NW)
 // and, after a CTA barrier, sweeps the (E, dZ) of all NW samples of the tile from shared memory.  Embedding gradients
 // go through the same sort-free vector reductions (and hot-row replicas) as the FM / HHFM kernels.
-// This kernel is compute-bound (about 1.1 MFLOP per sample at F=10, K=A=64); a tcgen05 version with split-precision
-// operands is the planned next step.
+// These kernels are compute-bound (about 1.1 MFLOP per sample at F=10, K=A=64) and serve every shape; the training pass of the
+// reference's default shape family (K = A = 64, F <= 11) runs on the tensor cores instead (afm_fused_tc.cu).
 #include <stdlib.h>
 
+#include "afm.cuh"
 #include "common.cuh"
 
 namespace hhfm {
-
-constexpr int kAfmMaxF = 16;
-constexpr int kAfmMaxP = kAfmMaxF * (kAfmMaxF - 1) / 2;
-
-struct AfmArgs {
-  const int32_t* idx;     // [B, F]
-  int64_t B;
-  int F, K, A, P;
-  const float* V;
-  const float* bias;
-  const float* b0;
-  const float* W;         // [K, A]
-  const float* batt;      // [A]
-  const float* pvec;      // [A]
-  const float* wpred;     // [K]
-  const float* labels;
-  float* out;
-  float* gV;
-  float* gbias;
-  float* gb0;
-  float* gW;
-  float* gbatt;
-  float* gp;
-  float* gwpred;
-  float* loss_partials;
-  int32_t* touch_stamp;
-  int32_t stamp;
-  int32_t* touched_rows;
-  int32_t* touched_count;
-  HotPlan hot;
-};
 
 __host__ __device__ inline size_t afm_per_warp_floats(int F, int K, int A, int P) {
   return 2 * (size_t)F * K + (size_t)P * A + (size_t)((2 * P + 3) / 4 * 4);
@@ -880,5 +850,9 @@ extern "C" int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F,
   a.gwpred = gwpred; a.loss_partials = loss_partials; a.touch_stamp = touch_stamp; a.stamp = stamp;
   a.touched_rows = touched_rows; a.touched_count = touched_count;
   a.hot = HotPlan{hot_slot, ghot, ghot_bias, n_rep, n_hot};
+  {
+    const int frc = dispatch_afm_fused_tc(a, M, (cudaStream_t)stream);      // K = A = 64, F <= 11: one tcgen05 kernel
+    if (frc != 1) return frc;
+  }
   return dispatch_afm<true>(a, (cudaStream_t)stream);
 }

@@ -91,6 +91,22 @@ __device__ __forceinline__ void touch_row(int32_t* stamp_arr, int32_t stamp, int
   }
 }
 
+// Counter-based generator shared by the device sampler (sampler.cu) and the dropout masks (fm.cu): every draw is a pure
+// function of (seed, counter), restated bit-exactly by the oracle.
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// tf.nn.dropout(x, keep) = x / keep * floor(keep + u), u uniform in [0,1): element (sample s, column k) is kept iff
+// u24(seed, s, k) * 2^-24 < keep.  Returns the 0/1 mask value.
+__device__ __forceinline__ float dropout_keep01(uint64_t seed, int64_t s, int k, float keep) {
+  const uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)s * 0x100000001B3ull + (uint64_t)k));
+  return ((float)(h >> 40) * (1.0f / 16777216.0f) < keep) ? 1.f : 0.f;
+}
+
 // Embedding row fragment held by one lane: VPL float4 chunks, chunk c = lg + i*LPS of the K/4 in a row.
 template <int LPS, int VPL>
 struct Frag {

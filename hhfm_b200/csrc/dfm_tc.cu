@@ -33,14 +33,6 @@ constexpr int kTfABytes = kTfM * 128;            // one A tile (hi or lo)
 constexpr int kTfSmemBudget = 216 * 1024;        // operand stages (the rest of the 227 KB: barriers + alignment slack)
 constexpr int kTfSmemBytes = kTfSmemBudget + 1024 + 256;
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-// lo part: x - hi is exact in fp32 but has up to 13 significant bits; it is stored already ROUNDED to the nearest tf32 so
-// that the hardware's truncation of the operand loses nothing more (unbiased, half the error of letting it truncate)
-__device__ __forceinline__ float tf32_lo(float x) {
-  const float lo = x - tf32_hi(x);
-  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
-}
-
 struct TfKernelArgs {
   int M, N, K;
   int n_mtiles, n_ntiles, bn, splits, chunks_total, chunks_per_split, n_units;

@@ -36,11 +36,16 @@ struct FmArgs {
   int32_t* touched_count;
   int groups_active;
   HotPlan hot;
+  float keep;            // dropout keep probability of the interaction layer (FM.py:114, MF.py:87); 1 = off
+  uint64_t drop_seed;
 };
 
 enum { FM_FWD = 0, FM_TRAIN = 1, FM_BWD = 2 };
 
-template <int LPS, int VPL, int MODE>
+// DROP: tf.nn.dropout on the [B, K] interaction vector before the sum over k (training launches only; the reference
+// evaluates with dropout_keep = 1).  m_k / keep multiplies element k of the vector and of every gradient that flows
+// through it.
+template <int LPS, int VPL, int MODE, bool DROP = false>
 __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
   __shared__ float scratch[32];
   using F4 = Frag<LPS, VPL>;
@@ -66,12 +71,21 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
         end = beg + a.F;
       }
     }
-    F4 S, Q, e0, e1;
+    F4 S, Q, e0, e1, dm;
     frag_zero(S);
     frag_zero(Q);
     frag_zero(e0);
     frag_zero(e1);
     float bsum = 0.f, part = 0.f;
+    if (DROP) {
+      const int64_t sm = valid ? s : 0;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const int k0 = 4 * (lg + i * LPS);
+        dm.v[i] = make_float4(dropout_keep01(a.drop_seed, sm, k0, a.keep), dropout_keep01(a.drop_seed, sm, k0 + 1, a.keep),
+                              dropout_keep01(a.drop_seed, sm, k0 + 2, a.keep), dropout_keep01(a.drop_seed, sm, k0 + 3, a.keep));
+      }
+    }
 
     if (a.interaction == 0) {
       // ---- FM.py:99-109: S = sum_f e_f, Q = sum_f e_f^2 (fields in order, 4 gathers in flight) ----
@@ -105,7 +119,13 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
 #pragma unroll
       for (int i = 0; i < VPL; i++) {
         float4 t = f4_sub(f4_mul(S.v[i], S.v[i]), Q.v[i]);
-        part += 0.5f * f4_hsum(t);
+        if (DROP) {
+          t = f4_scale(t, 0.5f);                                   // FM.py:109 `0.5 * subtract`, then :114 dropout
+          t = f4_mul(make_float4(t.x / a.keep, t.y / a.keep, t.z / a.keep, t.w / a.keep), dm.v[i]);
+          part += f4_hsum(t);
+        } else {
+          part += 0.5f * f4_hsum(t);
+        }
       }
     } else {
       // ---- MF.py:81-92: out = sum_k V[x0]*V[x1]; the bias term is not added (:92) ----
@@ -113,7 +133,15 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
         frag_load(e0, a.V, __ldg(a.col + beg), K, lg);
         frag_load(e1, a.V, __ldg(a.col + beg + 1), K, lg);
       }
-      part = frag_dot(e0, e1);
+      if (DROP) {
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+          const float4 t = f4_mul(e0.v[i], e1.v[i]);
+          part += f4_hsum(f4_mul(make_float4(t.x / a.keep, t.y / a.keep, t.z / a.keep, t.w / a.keep), dm.v[i]));
+        }
+      } else {
+        part = frag_dot(e0, e1);
+      }
     }
     const float bil = group_sum<LPS>(part);
     const float out = (bil + bsum) + b0;   // FM.py:120 add_n([Bilinear, Feature_bias, Bias])
@@ -163,6 +191,7 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
             for (int i = 0; i < VPL; i++) {
               float4 x = a.val ? f4_scale(e[u].v[i], vv[u]) : e[u].v[i];
               d.v[i] = f4_scale(f4_sub(S.v[i], x), gv);
+              if (DROP) d.v[i] = f4_mul(d.v[i], make_float4(dm.v[i].x / a.keep, dm.v[i].y / a.keep, dm.v[i].z / a.keep, dm.v[i].w / a.keep));
             }
             scatter_row<LPS, VPL>(a.gV, a.hot, rep, id[u], K, lg, d);
             if (lg == 0) {
@@ -179,6 +208,11 @@ __global__ void __launch_bounds__(kBlock) fm_kernel(const FmArgs a) {
       for (int i = 0; i < VPL; i++) {
         d0.v[i] = f4_scale(e1.v[i], g);
         d1.v[i] = f4_scale(e0.v[i], g);
+        if (DROP) {
+          const float4 mk = make_float4(dm.v[i].x / a.keep, dm.v[i].y / a.keep, dm.v[i].z / a.keep, dm.v[i].w / a.keep);
+          d0.v[i] = f4_mul(d0.v[i], mk);
+          d1.v[i] = f4_mul(d1.v[i], mk);
+        }
       }
       scatter_row<LPS, VPL>(a.gV, a.hot, rep, x0, K, lg, d0);
       scatter_row<LPS, VPL>(a.gV, a.hot, rep, x1, K, lg, d1);
@@ -534,22 +568,22 @@ static int dispatch_fm_staged(const FmArgs& a, int64_t M, cudaStream_t st) {
   return rc;
 }
 
-template <int LPS, int VPL, int MODE>
+template <int LPS, int VPL, int MODE, bool DROP = false>
 static int launch_fm(const FmArgs& a, int deterministic, cudaStream_t st) {
   static int occ = 0;
   if (occ == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm_kernel<LPS, VPL, MODE>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm_kernel<LPS, VPL, MODE, DROP>, kBlock, 0);
     if (occ < 1) occ = 1;
   }
   FmArgs b = a;
   constexpr int G = 32 / LPS;
   if (deterministic) {
     b.groups_active = 1;
-    fm_kernel<LPS, VPL, MODE><<<1, 32, 0, st>>>(b);
+    fm_kernel<LPS, VPL, MODE, DROP><<<1, 32, 0, st>>>(b);
   } else {
     b.groups_active = G;
     const int grid = grid_for(a.B, (kBlock / 32) * G, occ);
-    fm_kernel<LPS, VPL, MODE><<<grid, kBlock, 0, st>>>(b);
+    fm_kernel<LPS, VPL, MODE, DROP><<<grid, kBlock, 0, st>>>(b);
   }
   return check_launch("fm_kernel");
 }
@@ -557,6 +591,13 @@ static int launch_fm(const FmArgs& a, int deterministic, cudaStream_t st) {
 template <int MODE>
 static int dispatch_fm(const FmArgs& a, int deterministic, cudaStream_t st) {
 #define CALL(L, V) return launch_fm<L, V, MODE>(a, deterministic, st)
+  HHFM_DISPATCH_K(a.K, CALL);
+#undef CALL
+  return HHFM_ERR_UNSUPPORTED;
+}
+
+static int dispatch_fm_train_dropout(const FmArgs& a, int deterministic, cudaStream_t st) {
+#define CALL(L, V) return launch_fm<L, V, FM_TRAIN, true>(a, deterministic, st)
   HHFM_DISPATCH_K(a.K, CALL);
 #undef CALL
   return HHFM_ERR_UNSUPPORTED;
@@ -591,13 +632,13 @@ extern "C" int hhfm_fm_fwd(const int32_t* row_ptr, const int32_t* col, const flo
   return dispatch_fm<FM_FWD>(a, 0, (cudaStream_t)stream);
 }
 
-extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B,
+extern "C" int hhfm_fm_fwd_bwd_sqloss_dropout(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B,
                                       int64_t F, const float* V, const float* bias, const float* b0, int64_t M,
                                       int64_t K, int32_t interaction, const float* labels, float* out, float* gV,
                                       float* gbias, float* gb0, float* loss_partials, int32_t* touch_stamp,
                                       int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
                                       const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep,
-                                      int32_t n_hot, int32_t deterministic, hhfm_stream_t stream) {
+                                      int32_t n_hot, int32_t deterministic, float keep, uint64_t drop_seed, hhfm_stream_t stream) {
   int rc = check_common(B, F, col, V, M, K, interaction, row_ptr);
   if (rc) return rc;
   HHFM_REQUIRE(!hot_slot || (ghot && n_rep >= 1 && n_hot >= 1), "fm_fwd_bwd_sqloss: hot_slot needs ghot, n_rep, n_hot");
@@ -611,6 +652,10 @@ extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col
   a.loss_partials = loss_partials; a.touch_stamp = touch_stamp; a.stamp = stamp; a.touched_rows = touched_rows;
   a.touched_count = touched_count;
   a.hot = HotPlan{hot_slot, ghot, ghot_bias, n_rep, n_hot};
+  HHFM_REQUIRE(keep > 0.f && keep <= 1.f, "fm_fwd_bwd_sqloss: dropout keep must be in (0, 1]");
+  a.keep = keep;
+  a.drop_seed = drop_seed;
+  if (keep < 1.f) return dispatch_fm_train_dropout(a, deterministic, (cudaStream_t)stream);
   if (!deterministic) {
     rc = dispatch_fm_staged(a, M, (cudaStream_t)stream);
     if (rc != HHFM_ERR_UNSUPPORTED) return rc;
@@ -618,6 +663,18 @@ extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col
     if (rc != HHFM_ERR_UNSUPPORTED) return rc;
   }
   return dispatch_fm<FM_TRAIN>(a, deterministic, (cudaStream_t)stream);
+}
+
+extern "C" int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B,
+                                      int64_t F, const float* V, const float* bias, const float* b0, int64_t M,
+                                      int64_t K, int32_t interaction, const float* labels, float* out, float* gV,
+                                      float* gbias, float* gb0, float* loss_partials, int32_t* touch_stamp,
+                                      int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
+                                      const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep,
+                                      int32_t n_hot, int32_t deterministic, hhfm_stream_t stream) {
+  return hhfm_fm_fwd_bwd_sqloss_dropout(row_ptr, col, val, B, F, V, bias, b0, M, K, interaction, labels, out, gV, gbias, gb0,
+                                        loss_partials, touch_stamp, stamp, touched_rows, touched_count, hot_slot, ghot,
+                                        ghot_bias, n_rep, n_hot, deterministic, 1.0f, 0ull, stream);
 }
 
 extern "C" int hhfm_fm_bwd(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,

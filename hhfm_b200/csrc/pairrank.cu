@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(kBlock) pairrank_kernel(const PrArgs a) {
 // hybrid feature and all receive d_hyb), K == 4*LPS, and the group widths are compile-time constants:
 // NP = n_ctx + n_time pooled rows, NNEG negatives.  Everything is unrolled: the record is read with int4 loads,
 // all NP + NNEG + 2 row gathers are independent LDG.128s, no bound or mode tests remain in the loop.
-// Same arithmetic order as the generic kernel.  (~3x fewer instructions per sample; see profiles/.)
+// The hybrid feature is summed in record order, ((u + c0) + c1) + ..., where the generic kernel pools the group first,
+// u + (c0 + c1 + ...): the two differ in the last bit, both are within the 1e-5 parity bar.
+// (~3x fewer instructions per sample; see profiles/.)
 // ---------------------------------------------------------------------------------------------------
 template <int LPS, int NP, int NNEG>
 __global__ void __launch_bounds__(kBlock, 2) pairrank_sum_train_kernel(const PrArgs a) {

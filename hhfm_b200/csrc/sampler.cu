@@ -11,13 +11,6 @@
 
 namespace hhfm {
 
-__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-
 // item = n_user + floor(u32 * n_item / 2^32), u32 = top half of the hash of (seed, cell, attempt)
 __device__ __forceinline__ int draw_item(uint64_t seed, uint64_t cell, uint32_t attempt, int n_user, int n_item) {
   const uint64_t h = splitmix64(seed ^ splitmix64(cell * 0x100000001B3ull + attempt));

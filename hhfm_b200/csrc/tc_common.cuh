@@ -155,6 +155,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// fp32 -> (hi, lo) tf32 operand split of the 3xTF32 products (dfm_tc.cu, afm_fused_tc.cu)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// lo part: x - hi is exact in fp32 but has up to 13 significant bits; it is stored already ROUNDED to the nearest tf32 so
+// that the hardware's truncation of the operand loses nothing more (unbiased, half the error of letting it truncate)
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float lo = x - tf32_hi(x);
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+
 // The driver entry point is resolved at run time so the library does not link against libcuda (it must load on a
 // box without a GPU driver: the CPU test tier imports it to check the exported symbols).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -134,7 +134,8 @@ class RecordUploader:
 
     def upload(self, parts, id_limit, align=4, extra_cols=0):
         """`extra_cols` reserves columns after the packed ones (filled with the padding code -1 here, e.g. negatives that
-        the device sampler writes afterwards)."""
+        the device sampler writes afterwards).  The returned tensor is a VIEW of this uploader's device buffer: the next
+        `upload` overwrites it (clone it to keep it)."""
         parts = [_as_2d_ids(p) for p in parts if p is not None]
         B = parts[0].shape[0]
         for p in parts:
@@ -144,6 +145,9 @@ class RecordUploader:
         stride = _round_up(max(width + int(extra_cols), 1), align)
         lib = _lib.load()
         nbytes = int(lib.hhfm_pack_upload_staging_bytes(B, stride, id_limit))
+        if self._busy is not None and (self.host is None or self.host.numel() < nbytes or self.dev is None
+                                       or self.dev.numel() < B * stride):
+            self._busy.synchronize()        # the previous upload's copies (issued by library threads) still use the old buffers
         if self.host is None or self.host.numel() < nbytes:
             cap = max(nbytes, 4096)
             self.host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)

@@ -106,6 +106,17 @@ class _Base:
         self._loss_local = arena[n_v + n_b + 1:n_v + n_b + 2]        # this rank's reduced loss (peer exchange)
         self._loss_partials = arena[n_v + n_b + 4:n_v + n_b + 4 + P]
 
+    def _drop_args(self):
+        """(keep, seed) of this step's dropout mask (FM.py:114 / MF.py:87; training only -- the reference evaluates with
+        dropout_keep = 1).  Counter-based masks: the seed is a pure function of (random_seed, step), so a run is reproducible
+        and the oracle can restate the mask; it is statistically TF's dropout, not its random stream."""
+        keep = float(getattr(self, "keep", 1.0))
+        if keep >= 1.0:
+            return 1.0, 0
+        seed = (int(getattr(self, "random_seed", 2016)) * 0x9E3779B97F4A7C15 + self._opt.t) & 0xFFFFFFFFFFFFFFFF
+        self._last_drop_seed = seed
+        return keep, seed
+
     def _hot_plan(self, idx_dev, with_bias):
         """Hot-row plan for the two-level scatter (engine.HotRows), built once from the first batch."""
         if not self._hot_planned:
@@ -397,6 +408,10 @@ class _Base:
     def get_weights(self):
         return {k: v.detach().cpu().numpy().copy() for k, v in self.weights.items()}
 
+    def invalidate(self):
+        """Call after editing `model.weights[...]` in place: cached top-N item operands are keyed on the weight version."""
+        self._version += 1
+
 
 # ====================================================================================================
 class FM(_Base):
@@ -426,8 +441,8 @@ class FM(_Base):
     def _init_graph(self):
         if self.batch_norm:
             raise NotImplementedError("batch_norm=1 (FM.py:111-112) is not on the accelerated path; default is 0")
-        if float(self.keep) != 1.0:
-            raise NotImplementedError("dropout keep<1 (FM.py:114) is not on the accelerated path; default is 1")
+        if not (0.0 < float(self.keep) <= 1.0):
+            raise ValueError("keep must be in (0, 1]")
         self.train_features = Handle("train_features_fm")    # FM.py:89-92
         self.train_labels = Handle("train_labels_fm")
         self.dropout_keep = Handle("dropout_keep_fm")
@@ -469,10 +484,11 @@ class FM(_Base):
         bias = self.weights.get("feature_bias")
         ts, stamp, tr, tc = self._touch_args(extra=self._opt.kind == "momentum")
         hot = self._hot_plan(idx, True)
-        _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, F, ptr(V), ptr(bias), ptr(self._b0), self._M,
+        keep, dseed = self._drop_args()
+        _lib.call("hhfm_fm_fwd_bwd_sqloss_dropout", None, ptr(idx), None, B, F, ptr(V), ptr(bias), ptr(self._b0), self._M,
                   self._K, self.interaction, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0),
                   ptr(self._loss_partials), ts, stamp, tr, tc, *(hot.args(True) if hot else NO_HOT_BIAS),
-                  1 if self.deterministic else 0, cur_stream())
+                  1 if self.deterministic else 0, keep, dseed, cur_stream())
         self._finish_step(hot, True, self._apply_bias if bias is not None else None)
 
     def _fused_segments(self):
@@ -537,9 +553,8 @@ class MF(FM):
     def _init_graph(self):
         if self.batch_norm:
             raise NotImplementedError("batch_norm=1 is not on the accelerated path")
-        if float(self.keep) != 1.0:
-            raise NotImplementedError("MF dropout keep<1 (MF.py:87, default 0.7) needs TF's RNG stream and is not on "
-                                      "the accelerated path; pass keep=1")
+        if not (0.0 < float(self.keep) <= 1.0):
+            raise ValueError("keep must be in (0, 1]")
         self.train_features = Handle("train_features_fm")
         self.train_labels = Handle("train_labels_fm")
         self.dropout_keep = Handle("dropout_keep_fm")
@@ -574,9 +589,10 @@ class MF(FM):
         V = self.weights["feature_embeddings"]
         ts, stamp, tr, tc = self._touch_args()
         hot = self._hot_plan(idx, False)
-        _lib.call("hhfm_fm_fwd_bwd_sqloss", None, ptr(idx), None, B, 2, ptr(V), None, None, self._M, self._K, 1, ptr(y),
+        keep, dseed = self._drop_args()
+        _lib.call("hhfm_fm_fwd_bwd_sqloss_dropout", None, ptr(idx), None, B, 2, ptr(V), None, None, self._M, self._K, 1, ptr(y),
                   None, ptr(self._gV), None, None, ptr(self._loss_partials), ts, stamp, tr, tc,
-                  *(hot.args(True) if hot else NO_HOT_BIAS), 1 if self.deterministic else 0, cur_stream())
+                  *(hot.args(True) if hot else NO_HOT_BIAS), 1 if self.deterministic else 0, keep, dseed, cur_stream())
         self._finish_step(hot, False)
 
     def _fused_segments(self):
@@ -821,31 +837,10 @@ class AFM(FM):
     def score_device(self, idx):
         return self._predict_dev(idx)
 
-    def _tc_workspace(self, B, F):
-        """Workspace of the tensor-core path (csrc/afm_tc.cu) when it is selected with HHFM_AFM_TC=1, else None.  The
-        GEMM-ised path is correct (same parity tests) but its K = A = 64 products are too small to win once the pair tensors
-        travel through L2 (18 ms against 12 ms per 2^17 samples, profiles/r1_afm_summary.md): the fused CUDA-core kernel stays
-        the default until the products are fused into one tcgen05 kernel."""
-        import os
-        if os.environ.get("HHFM_AFM_TC", "0") != "1":
-            return None
-        need = int(_lib.load().hhfm_workspace_bytes_afm(B, F, self._K, self._A))
-        if need < 0:
-            return None
-        n = need // 4 + 4
-        if getattr(self, "_tc_ws", None) is None or self._tc_ws.numel() < n:
-            self._tc_ws = torch.empty(n, dtype=torch.float32, device=self.device)
-        return self._tc_ws
-
     def _predict_dev(self, idx):
         B, F = idx.shape
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         W, batt, pv, wp = self._small()
-        ws = self._tc_workspace(B, F) if B > 0 else None
-        if ws is not None:
-            _lib.call("hhfm_afm_fwd_tc", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
-                      ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(out), ptr(ws), cur_stream())
-            return out
         _lib.call("hhfm_afm_fwd", ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]),
                   ptr(self._b0), W, batt, pv, wp, self._M, self._K, self._A, ptr(out), cur_stream())
         return out
@@ -864,15 +859,12 @@ class AFM(FM):
         ts, stamp, tr, tc = self._touch_args(extra=True)
         hot = self._hot_plan(idx, True)
         W, batt, pv, wp = self._small()
-        ws = self._tc_workspace(B, F)
         common = (ptr(idx), B, F, ptr(self.weights["feature_embeddings"]), ptr(self.weights["feature_bias"]), ptr(self._b0), W, batt,
                   pv, wp, self._M, self._K, self._A, ptr(y), None, ptr(self._gV), ptr(self._gb), ptr(self._gb0), ptr(self._gW),
                   ptr(self._gbatt), ptr(self._gp), ptr(self._gwp), ptr(self._loss_partials), ts, stamp, tr, tc,
                   *(hot.args(True) if hot else NO_HOT_BIAS))
-        if ws is not None:
-            _lib.call("hhfm_afm_fwd_bwd_sqloss_tc", *common, ptr(ws), cur_stream())
-        else:
-            _lib.call("hhfm_afm_fwd_bwd_sqloss", *common, cur_stream())
+        # K == A == 64, F <= 11: one fused tcgen05 kernel (csrc/afm_fused_tc.cu); other shapes: fp32 CUDA-core kernels
+        _lib.call("hhfm_afm_fwd_bwd_sqloss", *common, cur_stream())
         if hot:
             hot.fold(self._gV, self._gb)
         if self._dp_group is not None:
@@ -1362,6 +1354,11 @@ class CARS2:
         _lib.call("hhfm_cars2_fwd_bwd", ptr(rec), B, stride, n_neg, ptr(self._params), *self._dims, ptr(self._gparams),
                   ptr(self._loss_partials), ptr(self._workspace(B)), cur_stream())
         lam = float(self.lamda_bilinear)
+        if lam <= 0 and self._opt.kind == "momentum":
+            # without the L2 term TF hands UI / Context IndexedSlices to SparseApplyMomentum (only touched rows move); the
+            # dense kernel would keep moving untouched rows (accum *= mu; w -= lr * accum)
+            raise NotImplementedError("CARS2: MomentumOptimizer with lamda == 0 needs the touched-row update, which is not "
+                                      "implemented for the CARS2 parameter block; use lamda > 0 (reference default 0.001)")
         self._opt.apply_dense("params", self._params, self._gparams, lam if lam > 0 else 0.0,
                               self._sq_partials if lam > 0 else None)
         self._version += 1

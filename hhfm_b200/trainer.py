@@ -5,7 +5,8 @@ assembly, evaluate_AUC / evaluate_TopK and the result.txt log format of the refe
 What changed versus the reference: the pure-Python double loops (sample_negative FM.py:284-294, the per-row
 metric walk FM.py:336-357) are vectorised / moved to the device, and `toolz.partition_all` + fancy indexing
 became plain slicing.  What did not change: the order and kind of `np.random` draws (so a seeded run consumes
-the same random stream as the reference), batch contents, labels, chunk sizes and the log text.
+the same random stream as the reference), batch contents (the pairwise trainers shuffle ONE persistent copy of the train
+rows in place, as the reference shuffles its `.values` view), labels, chunk sizes and the log text.
 """
 from __future__ import annotations
 
@@ -91,8 +92,20 @@ class BaseTrain(object):
             engine.auc_wins(model.score_device(idx), model.score_device(neg_rows), 50, wins)
         return float(wins.item()) / (50.0 * len(X))
 
+    def _train_values(self):
+        """The train table as ONE persistent ndarray.  The reference takes `Train_data.values[:, 1:]` and shuffles it in place
+        every epoch (OurModel7.py:369-370): with the pandas of its time that is a view, so the permutation persists, composes
+        across epochs, and `evaluate_AUC(Train_data)` (first 600 rows only, :461) sees the shuffled rows.  pandas 3 hands out
+        read-only copies, so the drop-in keeps the array itself."""
+        tv = getattr(self, "_train_tv", None)
+        if tv is None:
+            tv = self._train_tv = np.array(self.data.Train_data.values)
+        return tv
+
     def evaluate_AUC(self, data1):
         """FM.py:296-324: 50 sampled negatives per positive, fraction with pos > neg, chunks of 600 rows."""
+        if data1 is self.data.Train_data and getattr(self, "_train_tv", None) is not None:
+            data1 = self._train_tv
         dat = np.asarray(data1.values if hasattr(data1, "values") else data1)
         dat = dat[dat[:, 0] > 0]
         X = np.array(dat[:, 1:], dtype=np.int64)
@@ -155,7 +168,7 @@ class BaseTrain(object):
         if args.Result == 0:
             self._log(self._eval_line("Dataset=%s %s" % (args.dataset, self.method), None, t2))
         self.loss_epoch = []
-        every = getattr(self, "verbose", 10) or 10
+        every = getattr(self, "verbose", 10)      # FM.py:273 `self.verbose > 0 and epoch % self.verbose == 0`; OurModel7.py:403 `% 10`
         for epoch in range(1, self.epoch):
             t1 = time()
             loss = self.run_epoch()
@@ -244,7 +257,7 @@ class PairwiseTrain(BaseTrain):
         """Shuffled positives are uploaded once per epoch as records with NG empty negative slots, the device sampler
         fills the slots, and the batches are row ranges of that buffer."""
         model, smp = self.model, self._sampler()
-        pos = np.array(self.data.Train_data.values[:, 1:])
+        pos = self._train_values()[:, 1:]                    # persistent view: the shuffle composes across epochs
         np.random.shuffle(pos)                               # OurModel7.py:370
         d = self.split(pos)
         parts = [d['X']] + ([d['F1']] if 'F1' in d else []) + ([d['F2']] if 'F2' in d else [])
@@ -262,7 +275,7 @@ class PairwiseTrain(BaseTrain):
     def run_epoch(self):
         if self.device_sampler:
             return self.run_epoch_device()
-        pos = np.array(self.data.Train_data.values[:, 1:])   # pandas-3 `.values` is a read-only view: copy
+        pos = self._train_values()[:, 1:]                    # persistent view (see _train_values)
         np.random.shuffle(pos)                               # OurModel7.py:370
         neg = self.sample_negative(pos, self.NG)
         loss = 0

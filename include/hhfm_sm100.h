@@ -128,6 +128,16 @@ int hhfm_fm_fwd_bwd_sqloss(const int32_t* row_ptr, const int32_t* col, const flo
                            float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
                            int32_t* touched_count, const int32_t* hot_slot, float* ghot, float* ghot_bias,
                            int32_t n_rep, int32_t n_hot, int32_t deterministic, hhfm_stream_t stream);
+/* The same step with tf.nn.dropout on the [B, K] interaction vector before the sum over k (FM.py:114, MF.py:87; the
+ * reference's MF default is keep = 0.7): element (s, k) is kept iff u24(splitmix64(seed ^ splitmix64(s*0x100000001B3 + k)))
+ * * 2^-24 < keep, kept elements are divided by keep.  keep = 1 is the call above.  Counter-based masks: statistically
+ * TF's dropout, not its random stream; restated bit-exactly by the oracle (dropout_mask_hashed). */
+int hhfm_fm_fwd_bwd_sqloss_dropout(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
+                           const float* V, const float* bias, const float* b0, int64_t M, int64_t K,
+                           int32_t interaction, const float* labels, float* out, float* gV, float* gbias, float* gb0,
+                           float* loss_partials, int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows,
+                           int32_t* touched_count, const int32_t* hot_slot, float* ghot, float* ghot_bias,
+                           int32_t n_rep, int32_t n_hot, int32_t deterministic, float keep, uint64_t drop_seed, hhfm_stream_t stream);
 
 /* Backward only, for torch.autograd: g = gout[s] given by the caller. */
 int hhfm_fm_bwd(const int32_t* row_ptr, const int32_t* col, const float* val, int64_t B, int64_t F,
@@ -154,22 +164,9 @@ int hhfm_afm_fwd_bwd_sqloss(const int32_t* idx, int64_t B, int64_t F, const floa
                             const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
                             hhfm_stream_t stream);
 
-/* K2 on the tensor cores (afm_tc.cu): the same forward / fused training pass with the three matrix products (P W, dZ W^T,
- * P^T dZ) as 3xTF32 split GEMMs on tcgen05 and the rest as warp-per-sample kernels, chunked so that the pair tensors stay
- * in L2.  Same arguments as hhfm_afm_fwd / hhfm_afm_fwd_bwd_sqloss plus a caller-owned, 16-byte aligned workspace of
- * hhfm_workspace_bytes_afm(B, F, K, A) bytes. */
-int64_t hhfm_workspace_bytes_afm(int64_t B, int64_t F, int64_t K, int64_t A);
-int hhfm_afm_fwd_tc(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias, const float* b0,
-                    const float* W, const float* batt, const float* pvec, const float* wpred, int64_t M, int64_t K,
-                    int64_t A, float* out, float* workspace, hhfm_stream_t stream);
-int hhfm_afm_fwd_bwd_sqloss_tc(const int32_t* idx, int64_t B, int64_t F, const float* V, const float* bias,
-                               const float* b0, const float* W, const float* batt, const float* pvec, const float* wpred,
-                               int64_t M, int64_t K, int64_t A, const float* labels, float* out, float* gV, float* gbias,
-                               float* gb0, float* gW, float* gbatt, float* gp, float* gwpred, float* loss_partials,
-                               int32_t* touch_stamp, int32_t stamp, int32_t* touched_rows, int32_t* touched_count,
-                               const int32_t* hot_slot, float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot,
-                               float* workspace, hhfm_stream_t stream);
-
+/* The training pass of K == A == 64, F <= 11 runs as ONE tcgen05 kernel (afm_fused_tc.cu: the three matrix products P W,
+ * dZ W^T, P^T dZ as 3xTF32 split products with the operands built in shared memory and the logits / dP in TMEM);
+ * hhfm_afm_fwd_bwd_sqloss selects it by shape, HHFM_AFM_TC=0 forces the fp32 CUDA-core kernels. */
 /* K2 full-catalog scorer (AFM.py:209-246; afm_topn.cu): scores [C, N] = the AFM forward of every context row with field
  * `item_col` replaced by item n (table row item_base + n), n < N.  Only the F-1 pairs that contain the item are evaluated
  * per (context, item); the context-only pairs are reduced once per context into stats [C, 4] (caller-owned scratch).

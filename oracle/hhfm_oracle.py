@@ -295,6 +295,66 @@ def mf_loss_grads(X, Y, V, lamda=0.0):
 
 
 # ----------------------------------------------------------------------------------------------------
+# dropout on the interaction layer (FM.py:114, MF.py:87): tf.nn.dropout(x, keep) = x / keep * floor(keep + u)
+# ----------------------------------------------------------------------------------------------------
+def dropout_mask_hashed(seed, B, K, keep):
+    """Restatement of the DEVICE dropout mask (csrc/common.cuh dropout_keep01): element (s, k) is kept iff
+    (splitmix64(seed ^ splitmix64(s * 0x100000001B3 + k)) >> 40) * 2^-24 < keep.  Returns the 0/1 mask float32 [B, K].
+    TF draws its mask from its own stream; this is statistically the same dropout, bit-exact against the kernel."""
+    with np.errstate(over="ignore"):
+        s = np.arange(B, dtype=np.uint64)[:, None]
+        k = np.arange(K, dtype=np.uint64)[None, :]
+        h = _splitmix64(np.uint64(seed) ^ _splitmix64(s * np.uint64(0x100000001B3) + k))
+    u = (h >> np.uint64(40)).astype(np.float32) * F32(1.0 / 16777216.0)
+    return (u < F32(keep)).astype(F32)
+
+
+def fm_dropout_loss_grads(X, Y, V, b, b0, keep, seed, lamda=0.0):
+    """FM.py:99-126 with dropout_keep < 1 (:114): FM = 0.5*(S^2 - sum e^2); FM = FM / keep * mask; out = sum_k FM + ..."""
+    V = _f32(V); Y = _f32(Y).reshape(-1)
+    E = V[X]
+    S = E.sum(axis=1, dtype=F32)
+    fm = (F32(0.5) * ((S * S).astype(F32) - (E * E).astype(F32).sum(axis=1, dtype=F32))).astype(F32)
+    mk = (dropout_mask_hashed(seed, X.shape[0], V.shape[1], keep) / F32(keep)).astype(F32)
+    fm = ((fm / F32(keep)).astype(F32) * dropout_mask_hashed(seed, X.shape[0], V.shape[1], keep)).astype(F32)
+    out = fm.sum(axis=1, dtype=F32)
+    if b is not None:
+        out = (out + _f32(b).reshape(-1)[X].sum(axis=1, dtype=F32)).astype(F32)
+    out = (out + F32(b0 if b0 is not None else 0.0)).astype(F32)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)
+    dE = ((g[:, None, None] * (S[:, None, :] - E)).astype(F32) * mk[:, None, :]).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, X.reshape(-1), dE.reshape(-1, V.shape[1]))
+    db = np.zeros(V.shape[0], F32)
+    np.add.at(db, X.reshape(-1), np.broadcast_to(g[:, None], X.shape).reshape(-1))
+    if lamda > 0:
+        loss = F32(loss + F32(lamda) * F32(0.5) * (V * V).astype(F32).sum(dtype=F32))
+        dV = (dV + F32(lamda) * V).astype(F32)
+    return F32(loss), out, dV, db, F32(g.sum(dtype=F32))
+
+
+def mf_dropout_loss_grads(X, Y, V, keep, seed, lamda=0.0):
+    """MF.py:81-98 with the reference default dropout_keep = 0.7 (:31,87)."""
+    V = _f32(V); Y = _f32(Y).reshape(-1)
+    u = V[X[:, 0]]; it = V[X[:, 1]]
+    m01 = dropout_mask_hashed(seed, X.shape[0], V.shape[1], keep)
+    mk = (m01 / F32(keep)).astype(F32)
+    out = (((u * it).astype(F32) / F32(keep)).astype(F32) * m01).astype(F32).sum(axis=1, dtype=F32)
+    diff = (Y - out).astype(F32)
+    loss = F32(0.5) * (diff * diff).astype(F32).sum(dtype=F32)
+    g = (-diff).astype(F32)
+    dV = np.zeros_like(V)
+    np.add.at(dV, X[:, 0], ((g[:, None] * it).astype(F32) * mk).astype(F32))
+    np.add.at(dV, X[:, 1], ((g[:, None] * u).astype(F32) * mk).astype(F32))
+    if lamda > 0:
+        loss = F32(loss + F32(lamda) * F32(0.5) * (V * V).astype(F32).sum(dtype=F32))
+        dV = (dV + F32(lamda) * V).astype(F32)
+    return F32(loss), out, dV
+
+
+# ----------------------------------------------------------------------------------------------------
 # HHFM (OurModel7.py:105-184) and BPR (BPR.py:76-88): pairwise ranking with max-negative
 # ----------------------------------------------------------------------------------------------------
 def _pool(E, mode):

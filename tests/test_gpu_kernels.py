@@ -648,6 +648,7 @@ def test_afm_item_separable_scorer_matches_forward(cuda, C, N, F, K):
 def test_afm_fused_pass_matches_oracle(cuda, B, F, K, layout, monkeypatch):
     """Both layouts of the fused kernel (afm.cu: afm2_kernel covers K == A in {16, 32, 64}; afm_kernel everything else)."""
     monkeypatch.setenv("HHFM_AFM_V1", "1" if layout == "column-per-lane" else "0")
+    monkeypatch.setenv("HHFM_AFM_TC", "0")          # the fp32 CUDA-core kernels (K = A = 64 would take the tcgen05 kernel)
     lib, ptr, st = _lib_ptr()
     rng = np.random.default_rng(B + F + K)
     M, A = 300, K
@@ -1006,12 +1007,17 @@ def test_tf32x3_gemm_is_fp32_accurate(cuda, M, N, K):
     assert (got[:, N:] == 99.0).all()
 
 
-@pytest.mark.parametrize("B,F,K", [(64, 10, 64), (5001, 10, 64), (130, 6, 32), (77, 12, 128), (50, 3, 16), (33, 2, 64)])
-def test_afm_tensor_core_pass_matches_oracle(cuda, B, F, K):
-    """K2 with the three matrix products as 3xTF32 GEMMs on tcgen05 (afm_tc.cu), chunked (B = 5001 spans three chunks)."""
+@pytest.mark.parametrize("B,F", [(64, 10), (5001, 10), (1, 10), (2, 10), (333, 11), (130, 6), (77, 3), (33, 2), (1000, 7)])
+@pytest.mark.parametrize("extras", [False, True])
+def test_afm_fused_tensor_core_pass_matches_oracle(cuda, B, F, extras, monkeypatch):
+    """K2 as ONE tcgen05 kernel (afm_fused_tc.cu, K = A = 64, F <= 11): P W, dZ W^T and P^T dZ as 3xTF32 products with the
+    operands built in shared memory; selected by hhfm_afm_fwd_bwd_sqloss from the shape.  `extras`: hot-row replicas and
+    touched-row tracking.  Odd B exercises the half-empty last tile."""
+    monkeypatch.delenv("HHFM_AFM_TC", raising=False)
     lib, ptr, st = _lib_ptr()
-    rng = np.random.default_rng(B + F + K + 1)
-    M, A = 300, K
+    from hhfm_b200.engine import HotRows
+    rng = np.random.default_rng(B + F + 64 + 1)
+    M, K, A = 300, 64, 64
     w = _afm_weights(rng, M, K, A)
     X = rng.integers(0, M, (B, F)); X[:, 1] = rng.integers(0, 4, B)
     if F > 3:
@@ -1024,14 +1030,21 @@ def test_afm_tensor_core_pass_matches_oracle(cuda, B, F, K):
     gW = torch.zeros(K, A, device=cuda); gba = torch.zeros(A, device=cuda); gp = torch.zeros(A, device=cuda); gwp = torch.zeros(K, device=cuda)
     lp = torch.zeros(P, device=cuda); o = torch.empty(B, device=cuda); lo = torch.zeros(1, device=cuda)
     tX = dev(X, cuda, torch.int32)
-    ws = torch.empty(int(lib.load().hhfm_workspace_bytes_afm(B, F, K, A)) // 4 + 4, device=cuda)
     args = (ptr(tX), B, F, ptr(tw["feature_embeddings"]), ptr(tw["feature_bias"]), ptr(tw["bias"]), ptr(tw["attention_W"]),
             ptr(tw["attention_b"]), ptr(tw["attention_p"]), ptr(tw["prediction"]), M, K, A)
-    o2 = torch.empty(B, device=cuda)
-    lib.call("hhfm_afm_fwd_tc", *args, ptr(o2), ptr(ws), st())
-    assert_close(o2.cpu().numpy(), out, what="afm tc fwd out")
-    lib.call("hhfm_afm_fwd_bwd_sqloss_tc", *args, ptr(dev(Y.reshape(-1), cuda)), ptr(o), ptr(gV), ptr(gb), ptr(gb0), ptr(gW), ptr(gba),
-             ptr(gp), ptr(gwp), ptr(lp), None, 0, None, None, None, None, None, 0, 0, ptr(ws), st())
+    if extras:
+        hot = HotRows(np.arange(0, 8), M, K, cuda, with_bias=True, n_rep=4)
+        stamp = torch.zeros(M, dtype=torch.int32, device=cuda); rows = torch.zeros(M, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+        tail = (ptr(stamp), 3, ptr(rows), ptr(cnt), *hot.args(True))
+    else:
+        tail = (None, 0, None, None, None, None, None, 0, 0)
+    lib.call("hhfm_afm_fwd_bwd_sqloss", *args, ptr(dev(Y.reshape(-1), cuda)), ptr(o), ptr(gV), ptr(gb), ptr(gb0), ptr(gW), ptr(gba),
+             ptr(gp), ptr(gwp), ptr(lp), *tail, st())
+    if extras:
+        hot.fold(gV, gb)
+        n = int(cnt.item())
+        assert sorted(rows[:n].cpu().numpy().tolist()) == sorted(np.unique(X).tolist())
     lib.call("hhfm_loss_finalize", ptr(lp), None, 0.0, ptr(lo), st())
     assert_close(o.cpu().numpy(), out, what="afm tc out"); assert_close(lo.item(), loss, what="afm tc loss")
     assert_close(gV.cpu().numpy(), g["feature_embeddings"], rtol=2e-5, what="afm tc gV")
