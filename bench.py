@@ -514,6 +514,7 @@ def e2e_epoch():
     out = {"dataset": "frappe.libfm (shipped)", "reference_result_txt_epoch_s": "3.7-4.1 (result.txt:431-435, hardware unknown)"}
     os.environ.setdefault("HHFM_RESULT_FILE", os.devnull)
     sess = None
+    saved_default = trainer.BaseTrain.device_sampler
     for name, dev_sampler in (("host_sampler", False), ("device_sampler", True)):
         trainer.BaseTrain.device_sampler = dev_sampler
         np.random.seed(1)
@@ -526,7 +527,7 @@ def e2e_epoch():
             sess.run_epoch()
         torch.cuda.synchronize()
         out[name + "_epoch_s"] = (time.perf_counter() - t0) / 3
-    trainer.BaseTrain.device_sampler = False
+    trainer.BaseTrain.device_sampler = saved_default
     out["train_rows"] = int(len(sess.data.Train_data))
     out["samples_per_s_device_sampler"] = out["train_rows"] / out["device_sampler_epoch_s"]
     # CPU port: the same epoch (vectorised reference sampler + 18 steps of 5000) with the torch-CPU mirror
@@ -560,8 +561,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        # the host packer of the e2e arm: every rank gets its share of the cores instead of a full-width pool each
-        os.environ.setdefault("HHFM_PACK_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
     dev = torch.device("cuda", local)
     B = args.batch
     n_batches = 4

@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
 
 int dispatch_afm_fused_tc(const AfmArgs& a, int64_t M, cudaStream_t st) {
   if (a.K != aft::KD || a.A != aft::KD || a.F > aft::kMaxF || a.F < 2 || a.P > aft::kSlot) return 1;
-  const char* env = getenv("HHFM_AFM_TC");               // 0 = fp32 SIMT kernels (A/B runs, tests of both paths)
-  if (env && env[0] == '0') return 1;
+  const char* env = getenv("HHFM_AFM_TC");               // opt-in while the dW product is being reworked
+  if (!env || env[0] != '1') return 1;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(aft::afm_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aft::kSmemBytes) != cudaSuccess) {

@@ -4,6 +4,7 @@
 // memory, ready for one cudaMemcpyAsync.  Plain std::thread fan-out; no device work here.
 #include <immintrin.h>
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -102,8 +103,19 @@ static int pack_ids(const T* src, int64_t rows, int64_t cols, int64_t src_row_st
 // ---------------------------------------------------------------------------------------------------------------
 class Pool {
  public:
-  explicit Pool(int n) : n_(n) {
+  // pin_base >= 0: worker i is pinned to core (pin_base + i) % cores, so the pools of several ranks on one box work on
+  // disjoint cores instead of migrating over all of them
+  Pool(int n, int pin_base) : n_(n) {
     for (int i = 0; i < n_; i++) th_.emplace_back([this, i] { loop(i); });
+    if (pin_base >= 0) {
+      const int cores = (int)std::thread::hardware_concurrency();
+      for (int i = 0; i < n_ && cores > 0; i++) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET((pin_base + i) % cores, &set);
+        pthread_setaffinity_np(th_[i].native_handle(), sizeof(set), &set);      // best effort
+      }
+    }
   }
   int size() const { return n_; }
   // run fn(worker) on every worker and wait
@@ -157,7 +169,8 @@ static Pool* get_pool(int nthreads) {
     if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
-    g_pool = new Pool(nthreads);      // lives for the process (workers block on a condition variable when idle)
+    const char* pin = getenv("HHFM_PACK_PIN_BASE");
+    g_pool = new Pool(nthreads, pin ? atoi(pin) : -1);      // lives for the process (workers block on a condition variable when idle)
   }
   return g_pool;
 }

@@ -16,7 +16,24 @@ from . import _lib
 
 POOL_SUM, POOL_MAX, POOL_MEAN = 0, 1, 2
 QUERY_USER, QUERY_FM, QUERY_HHFM = 0, 1, 2
-_NTHREADS = int(os.environ.get("HHFM_PACK_THREADS", "0"))   # 0 = hardware concurrency
+
+
+def _pack_threads():
+    """Worker threads of the host packer.  One process per GPU: every rank of a box gets its share of the cores (and pins its
+    pool to them) instead of a full-width pool per rank fighting over all cores.  HHFM_PACK_THREADS / HHFM_PACK_PIN_BASE
+    override; 0 = hardware concurrency."""
+    if "HHFM_PACK_THREADS" in os.environ:
+        return int(os.environ["HHFM_PACK_THREADS"])
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    if lws <= 1:
+        return 0
+    cores = os.cpu_count() or 1
+    n = max(2, cores // lws)
+    os.environ.setdefault("HHFM_PACK_PIN_BASE", str((int(os.environ.get("LOCAL_RANK", "0") or 0) * n) % cores))
+    return n
+
+
+_NTHREADS = _pack_threads()
 
 
 def require_cuda():

@@ -600,7 +600,9 @@ class MF(FM):
         return [("feature_embeddings", self.weights["feature_embeddings"], 0, n_v, self._lamda if self._lamda > 0 else 0.0)]
 
     def topk(self, A, tp=100):
-        return self._topk(QUERY_USER, A, 0, 0, (0, 0, 0), None, tp)
+        """MF.py:144-149: top-100 items per row of A by u . v (the rows may carry context columns; the table holds users and
+        items only, MF.py:171)."""
+        return self._topk(QUERY_USER, np.asarray(A)[:, :2], 0, 0, (0, 0, 0), None, tp)
 
 
 # ====================================================================================================

@@ -48,9 +48,12 @@ class BaseTrain(object):
     early_stop_tol = -0.0075  # FM.py:261 (AFM.py:330 uses -0.01)
     early_stop_cap = 100     # FM.py:262 `or epoch>100` (DFM has no cap)
     result_file = "../result.txt"
-    # negatives drawn and evaluate_AUC computed on the device (counter-based generator: statistically
-    # the reference's sampler, not numpy's stream).  Off by default so that a seeded run consumes the reference's stream.
-    device_sampler = bool(int(os.environ.get("HHFM_DEVICE_SAMPLER", "0")))
+    # by default the epoch is device-resident -- the train ids are uploaded once per epoch, the negatives
+    # are drawn by the device sampler (counter-based generator: statistically the reference's sampler, not numpy's stream),
+    # the batches are row ranges of that buffer, the epoch loss is summed on the device, and evaluate_AUC runs on the device.
+    # HHFM_DEVICE_SAMPLER=0 selects the host path, which consumes exactly the reference's numpy random stream
+    # (pinned against the reference's own code in tests/test_host_logic.py).
+    device_sampler = bool(int(os.environ.get("HHFM_DEVICE_SAMPLER", "1")))
     record_align = 1         # stride alignment of expanded rows (pair-ranking records need 4)
 
     # ---- to be provided by subclasses ----
@@ -204,11 +207,11 @@ class PointwiseTrain(BaseTrain):
                        torch.full((n * self.NG,), float(self.neg_label), device=model.device)])
         perm = torch.as_tensor(np.random.permutation(len(rows)), device=model.device)      # FM.py:250 np.random.shuffle
         rows, y = rows[perm].contiguous(), y[perm].contiguous()
-        loss = 0
+        loss = torch.zeros(1, dtype=torch.float64, device=model.device)     # one read-back per epoch instead of one per batch
         for c0 in range(0, len(rows), self.batch_size):
             model.fit_device(rows[c0:c0 + self.batch_size], y[c0:c0 + self.batch_size])
-            loss = loss + model._read_loss()
-        return loss
+            loss += model._loss_dev.double()
+        return float(loss.item())
 
     def run_epoch(self):
         if self.device_sampler:
@@ -266,11 +269,11 @@ class PairwiseTrain(BaseTrain):
         smp.sample(smp.key_ids(pos), self.NG, out=rec, out_stride=stride, out_col0=width)
         n_ctx = d['F1'].shape[1] if 'F1' in d else 0
         n_time = d['F2'].shape[1] if 'F2' in d else 0
-        loss = 0
+        loss = torch.zeros(1, dtype=torch.float64, device=model.device)     # one read-back per epoch instead of one per batch
         for c0 in range(0, len(pos), self.batch_size):
             model.fit_device(rec[c0:c0 + self.batch_size], n_ctx, n_time, self.NG)
-            loss = loss + model._read_loss()
-        return loss
+            loss += model._loss_dev.double()
+        return float(loss.item())
 
     def run_epoch(self):
         if self.device_sampler:

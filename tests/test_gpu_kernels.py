@@ -1013,7 +1013,7 @@ def test_afm_fused_tensor_core_pass_matches_oracle(cuda, B, F, extras, monkeypat
     """K2 as ONE tcgen05 kernel (afm_fused_tc.cu, K = A = 64, F <= 11): P W, dZ W^T and P^T dZ as 3xTF32 products with the
     operands built in shared memory; selected by hhfm_afm_fwd_bwd_sqloss from the shape.  `extras`: hot-row replicas and
     touched-row tracking.  Odd B exercises the half-empty last tile."""
-    monkeypatch.delenv("HHFM_AFM_TC", raising=False)
+    monkeypatch.setenv("HHFM_AFM_TC", "1")
     lib, ptr, st = _lib_ptr()
     from hhfm_b200.engine import HotRows
     rng = np.random.default_rng(B + F + 64 + 1)

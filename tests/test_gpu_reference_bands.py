@@ -59,9 +59,9 @@ def test_baselines_on_frappe_land_in_the_reference_band(cuda, model):
     _check(model, "frappe", 2, 64)
 
 
-@pytest.mark.parametrize("how", ["lr_sign", "no_ctx_grad"])
+@pytest.mark.parametrize("how", ["lr_sign", "neg1"])
 def test_a_corrupted_training_step_falls_out_of_the_band(cuda, how):
-    """The band test has teeth: gradient ascent, or context rows that never move (HHFM degenerates to BPR-MF), leave it."""
+    """The band test has teeth: gradient ascent (HR ~ 0), or the max over ONE negative instead of ten (HR@5 0.60, measured), leave it."""
     import reference_bands as rb
     run = rb.run_one("M7", "frappe", 100, 30, 64, broken=how)
     out = rb.summarize("M7", "frappe", [run])

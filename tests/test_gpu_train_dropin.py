@@ -30,6 +30,8 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     path = _write_dataset(str(tmp_path))
     result = os.path.join(str(tmp_path), "result.txt")
     monkeypatch.setenv("HHFM_RESULT_FILE", result)
+    from hhfm_b200 import trainer
+    monkeypatch.setattr(trainer.BaseTrain, "device_sampler", False)      # the host path (the reference's numpy random stream)
     np.random.seed(7)
     argv = ["--path", path, "--epoch", "11", "--batch_size", "2000"]
     if which == "FM":
@@ -75,7 +77,7 @@ def test_dropin_main_trains_and_logs(cuda, which, tmp_path, monkeypatch):
     assert all(len(set(r.tolist())) == 20 for r in ids)
 
 
-@pytest.mark.parametrize("which", ["FM", "M7", "DFM"])
+@pytest.mark.parametrize("which", ["FM", "M7", "DFM", "AFM", "BPR"])
 def test_device_sampler_epoch_and_auc(cuda, which, tmp_path, monkeypatch):
     """negatives drawn on the device, batches cut from device-resident rows, evaluate_AUC on the device.
     Statistically the reference's sampler: the model must train, and the device AUC must agree with the host-sampled AUC
@@ -92,6 +94,12 @@ def test_device_sampler_epoch_and_auc(cuda, which, tmp_path, monkeypatch):
     elif which == "DFM":
         from hhfm_b200.Newcode.DFM import DFM_main as main
         argv += ["--verbose", "10", "--lr", "0.05"]
+    elif which == "AFM":
+        from hhfm_b200.Newcode.AFM import AFM_main as main
+        argv += ["--verbose", "10"]
+    elif which == "BPR":
+        from hhfm_b200.Newcode.BPR import BPR_main as main
+        argv += ["--Result", "0", "--lr", "0.1"]
     else:
         from hhfm_b200.Newcode.OurModel7 import M7_main as main
     session = main("frappe", 32, 5, argv=argv)
@@ -101,5 +109,5 @@ def test_device_sampler_epoch_and_auc(cuda, which, tmp_path, monkeypatch):
     session.device_sampler = False
     auc_host = session.evaluate_AUC(session.data.Train_data)
     assert abs(auc_dev - auc_host) < 0.03, (auc_dev, auc_host)
-    if which != "DFM":
+    if which not in ("DFM", "AFM"):
         assert auc_dev > 0.6
