@@ -61,7 +61,7 @@ SIGNATURES = {
     "hhfm_sample_negatives": [vp, i64, i32, i32, i32, vp, i64, i64, C.c_uint64, vp, i64, i64, vp],
     "hhfm_expand_rows": [vp, i64, i32, i64, vp, i32, vp, i32, vp],
     "hhfm_auc_count": [vp, vp, i64, i32, vp, vp],
-    "hhfm_dp_step": [i32, vp, i32, vp, i64, vp, vp, i32, i32, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, vp, f32, f32, f32,
+    "hhfm_dp_step": [i32, vp, i32, vp, i64, vp, vp, i32, i32, i64, i64, vp, i64, vp, vp, vp, vp, vp, i32, i32, vp, f32, f32, f32,
                      f32, vp, vp, C.c_double, vp],
     "hhfm_hot_fold": [vp, vp, i32, i32, i64, vp, vp, vp, vp],
     "hhfm_l2_read_sweep": [vp, i64, i32, vp, vp],
@@ -79,6 +79,7 @@ INT64_FUNCS = {
     "hhfm_workspace_bytes_topn": [i32, i64, i64, i64, i32],
     "hhfm_pack_upload_staging_bytes": [i64, i64, i64],
     "hhfm_dp_exchange_floats": [i64],
+    "hhfm_dp_flag_ints": [],
     "hhfm_workspace_bytes_dfm_topn": [i64, i64, i64, i64, i32, vp],
     "hhfm_cars2_param_count": [i64, i64, i64, i64, i64, i64],
     "hhfm_workspace_bytes_cars2": [i64, i64, i64],

@@ -5,20 +5,24 @@
 // relu, softmax over the pairs, the weighted sum, the chain rule, the embedding scatter) runs in the same CTA between
 // the MMA phases, so the [pairs, K] tensors never leave shared memory / TMEM.
 //
-// Tile = 2 samples = 128 operand rows: sample slot ss owns rows [64 ss, 64 ss + P), the rows P..63 of a slot stay zero.
-//   P operand   [128 rows][K = 64]   written by the threads as (x, lo(x)) in the 128-byte-swizzled K-major tile layout
-//                                    (two 32-column tiles per part); the SAME buffer is the MN-major operand of dW.
-//   GEMM 1      Z[128, 64]   = P . W          A = P (K-major),  B = W^T tiles (K-major)        -> TMEM columns [0, 64)
-//   epilogue 1  thread = (row, column half): Z row from TMEM, relu, logits, softmax over the slot's pairs, afm, out,
-//               loss, d a, d s, dZ = ds * p * relu'  -> dZ operand tiles (x, lo) ; column sums -> d p, d b
-//   GEMM 2      dP[128, 64]  = dZ . W^T       A = dZ (K-major), B = W tiles (K-major)          -> TMEM columns [64, 128)
-//   GEMM 3      D[128, 64]  += [P ; P_lo]^T . (dZ + dZ_lo)   both operands MN-major views of the tiles above, reduction over
-//               the 128 tile rows; rows 0..63 of D hold P^T dZ, rows 64..127 hold P_lo^T dZ      -> TMEM columns [128, 192)
+// Tile = 2 samples = 128 operand rows: sample slot ss owns rows [64 ss, 64 ss + P), the rows P..63 of a slot are zero.
+// Thread = (row r, column half): warp & 3 is the TMEM lane quarter (rows), warp >> 2 the 32-column half.
+//   P rows      the thread builds its half row of pair products in registers and writes it (x and lo(x)) with tcgen05.st
+//               into TMEM -- the A operand of GEMM 1 -- and, transposed, into the K-major tiles PT[k][r] (A operand of GEMM 3)
+//   GEMM 1      Z[128, 64]   = P . W          A = P from TMEM,   B = W^T tiles (K-major smem)   -> TMEM columns [0, 64)
+//   epilogue 1  Z row from TMEM, relu, logits, softmax over the slot's pairs (warp reductions), afm, out, loss, d a, d s,
+//               dZ = ds * p * relu' -> TMEM (A operand of GEMM 2) and, transposed, the K-major tiles dZT[a][r]; column sums
+//               over the tile rows -> d p, d b
+//   GEMM 2      dP[128, 64]  = dZ . W^T       A = dZ from TMEM,  B = W tiles (K-major smem)     -> TMEM columns [64, 128)
+//   GEMM 3      D[128, 64]  += [PT ; PT_lo] . (dZT + dZT_lo)^T   K-major operands, reduction over the 128 tile rows; rows
+//               0..63 of D hold P^T dZ, rows 64..127 hold P_lo^T dZ                              -> TMEM columns [128, 192)
 //   epilogue 2  dP row from TMEM (+ a_p * d afm) -> shared memory; thread = (slot, field, float4): dE_f = sum_j dP_(f,j) * E_j,
 //               one vector reduction per 16 bytes into the gradient table (hot-row replicas as in K1 / K3)
-// dW stays in TMEM for kDrain tiles, then the partial sum is added into a shared-memory accumulator (two-level
-// accumulation: the tensor core adds into its accumulator with truncation, see dfm_tc.cu); the CTA adds its accumulator
-// into the global gradient once at the end.
+// (tf32 operands can only be MN-major in the SWIZZLE_128B_BASE32B layout, which the K-major products cannot share, so the
+// transposed operands of dW are separate tiles written by the same threads -- lane = row makes those stores contiguous.)
+// dW is read back from TMEM after every tile and added into registers (two-level accumulation: the tensor core adds into
+// its accumulator with truncation, see dfm_tc.cu); the threads add their registers into the global gradient once at the end.
+// The embedding rows of tile t+1 are fetched with cp.async into a second staging buffer while tile t is processed.
 //
 // Shapes covered: K == A == 64, F <= 11 (P <= 55 pairs).  Everything else stays on the fp32 SIMT kernels (afm.cu).
 #include <stdlib.h>
@@ -36,21 +40,21 @@ constexpr int kRows = 128;             // operand rows per tile (2 sample slots 
 constexpr int kSlot = 64;              // rows per sample slot
 constexpr int kThreads = 256;          // 8 warps: warp & 3 = TMEM lane quarter (rows), warp >> 2 = column half
 constexpr int kMaxF = 11;
-constexpr int kDrain = 2;              // tiles between two drains of the dW accumulator
 constexpr int kEP = KD + 4;            // padded row of the staged embeddings (floats)
 constexpr uint32_t kTile = kRows * 128;          // bytes of one [128 rows][32 fp32] operand tile
 constexpr uint32_t kWTile = KD * 128;            // bytes of one [64 rows][32 fp32] weight tile
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;
+// TMEM columns: Z | dP | dW | P x | P lo | dZ x | dZ lo
+constexpr uint32_t cZ = 0, cDP = 64, cDW = 128, cPX = 192, cPL = 256, cZX = 320, cZL = 384;
 
 // shared-memory map (bytes); operand tiles are 1024-byte aligned
-constexpr uint32_t oP = 0;                              // [x kb0][x kb1][lo kb0][lo kb1]
-constexpr uint32_t oZ = oP + 4 * kTile;                 // dZ tiles, same order; reused for the dP rows after GEMM 2/3
+constexpr uint32_t oP = 0;                              // PT tiles [M = 64 x rows + 64 lo rows][32 r] for r blocks 0..3
+constexpr uint32_t oZ = oP + 4 * kTile;                 // dZT tiles: x [64 a rows][32 r] for r blocks 0..3, then lo; reused for the dP rows
 constexpr uint32_t oWt = oZ + 4 * kTile;                // W^T tiles (rows = a, contiguous k): [x kb0][x kb1][lo kb0][lo kb1]
 constexpr uint32_t oWn = oWt + 4 * kWTile;              // W tiles (rows = k, contiguous a)
-constexpr int kDWP = KD + 1;           // padded row of the dW accumulator (bank spread for the row-per-lane atomics)
-constexpr uint32_t oDW = oWn + 4 * kWTile;              // float dW accumulator [64][kDWP]
-constexpr uint32_t oE = oDW + KD * kDWP * 4;             // float E[2][kMaxF][kEP]
-constexpr uint32_t oMisc = oE + 2 * kMaxF * kEP * 4;
+constexpr uint32_t kEBytes = 2 * kMaxF * kEP * 4;       // staged embedding rows of one tile: float E[2][kMaxF][kEP]
+constexpr uint32_t oE = oWn + 4 * kWTile;               // two tiles (the rows of tile t+1 land while tile t is processed)
+constexpr uint32_t oMisc = oE + 2 * kEBytes;
 constexpr uint32_t kSmemBytes = oMisc + 8192 + 1024;    // + alignment slack
 
 struct Misc {
@@ -62,8 +66,11 @@ struct Misc {
   float ds[kRows];
   float afm[2][KD], dafm[2][KD];
   float red[2][4];             // per-slot partial sums of out
+  float wred[8];               // per-warp partial of a slot-wide reduction (max, sum)
+  float afm_part[8][32];       // per-warp column sums of a_p * P_p
   float g[2], bsum[2];
-  int ids[2][kMaxF + 1];
+  float biasv[2][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
+  int ids[2][2][kMaxF + 1];       // [buffer][slot][field]
   unsigned char pi[kSlot], pj[kSlot];
   unsigned char pidx[kMaxF][kMaxF + 1];
   uint64_t bar;
@@ -74,19 +81,31 @@ static_assert(sizeof(Misc) <= 8192, "Misc does not fit its shared-memory slot");
 // byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 
-// MN-major operand descriptor (SWIZZLE_128B): 32 fp32 of the M/N index are contiguous (one tile row), the next block of
-// 32 starts LBO bytes further (the next tile), 8 reduction rows form one 1024-byte atom, the next 8 start SBO bytes further.
-__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// byte offset of fp32 element e (0..31) of row r inside a 128-byte-swizzled tile
+__device__ __forceinline__ uint32_t swz_e(int r, int e) { return swz(r, e >> 2) + (uint32_t)(e & 3) * 4u; }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
 }
-// kind::tf32 instruction descriptor with both operands MN-major (transpose bits 15 / 16)
-__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) { return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand is [M lanes][K columns] of fp32 words in tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
 
@@ -110,8 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   __shared__ float scratch[32];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   Misc& mi = *reinterpret_cast<Misc*>(smem + oMisc);
-  float* dWs = reinterpret_cast<float*>(smem + oDW);
-  float* Es = reinterpret_cast<float*>(smem + oE);
+  float* EsBuf = reinterpret_cast<float*>(smem + oE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = a.F, P = a.P;
   const int quarter = warp & 3, half = warp >> 2;
@@ -119,9 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   const int ss = row >> 6, pp = row & 63;       // sample slot, pair index
   const bool prow = pp < P;
 
-  // ---- one-time setup: zero the operand tiles (pad rows stay zero), W tiles, small vectors, pair tables, TMEM ----
-  for (uint32_t i = tid; i < (8 * kTile) / 16; i += kThreads) reinterpret_cast<float4*>(smem + oP)[i] = f4_zero();
-  for (int i = tid; i < KD * kDWP; i += kThreads) dWs[i] = 0.f;
+  // ---- one-time setup: W tiles, small vectors, pair tables, TMEM ----
   for (int i = tid; i < KD * (KD / 4); i += kThreads) {
     const int k = i / (KD / 4), c = i % (KD / 4);           // W row k, float4 chunk c of the A columns
     const float4 w = __ldg(reinterpret_cast<const float4*>(a.W) + i);
@@ -165,49 +181,97 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   const int rep = a.hot.slot ? (int)(blockIdx.x % a.hot.n_rep) : 0;
   uint32_t bar_ph = 0;
   float loss_acc = 0.f, gb0_acc = 0.f, gwp_acc = 0.f;
-  int since_drain = 0;
-
-  // add the TMEM dW partial sum into the shared accumulator: dW[k][a] = D[k][a] + D[64 + k][a]
-  auto drain_dw = [&]() {
-    uint32_t r[32];
-    tmem_ld32(t_lane + 128 + half * 32, r);
-    tmem_ld_wait_for(r);
-    float* dst = dWs + (row & 63) * kDWP + half * 32;
+  float dwacc[32];                  // this thread's share of dW: TMEM lane `row` (k = row & 63, x or lo part), its 32 columns
 #pragma unroll
-    for (int i = 0; i < 32; i++) atomicAdd(dst + i, __uint_as_float(r[i]));
+  for (int i = 0; i < 32; i++) dwacc[i] = 0.f;
+
+  // ---- staging pipeline: ids two tiles ahead, embedding rows + bias values one tile ahead (cp.async) ----
+  auto load_id = [&](int64_t t) {
+    if (tid >= 2 * F || t >= n_tiles) return -1;
+    const int64_t s = 2 * t + tid / F;
+    return (s < a.B) ? __ldg(a.idx + s * F + tid % F) : -1;
+  };
+  auto stage_rows = [&](int buf) {          // rows of the tile whose ids are in mi.ids[buf] -> EsBuf[buf], biasv[buf]
+    float* Es = EsBuf + buf * (kEBytes / 4);
+    for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
+      const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
+      const int id = mi.ids[buf][s2][f];
+      float* dst = Es + (s2 * kMaxF + f) * kEP + 4 * c;
+      if (id >= 0) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(a.V + (size_t)id * KD + 4 * c) : "memory");
+        if (c == 0 && a.bias) ldgsts4(&mi.biasv[buf][s2][f], a.bias + id);
+      } else {
+        *reinterpret_cast<float4*>(dst) = f4_zero();
+        if (c == 0) mi.biasv[buf][s2][f] = 0.f;
+      }
+    }
+    ldgsts_commit();
+  };
+  int cur = 0;
+  {
+    const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + gridDim.x);
+    if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
+    if (tid < 2 * (kMaxF + 1)) { mi.biasv[0][tid / (kMaxF + 1)][tid % (kMaxF + 1)] = 0.f; mi.biasv[1][tid / (kMaxF + 1)][tid % (kMaxF + 1)] = 0.f; }
+    __syncthreads();
+    stage_rows(0);
+  }
+
+  // slot-wide reduction over the 64 rows of a sample: the two warps that hold them (same column half) are warp and warp ^ 1
+  auto slot_max = [&](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) mi.wred[warp] = v;
+    __syncthreads();
+    const float r = fmaxf(mi.wred[warp], mi.wred[warp ^ 1]);
+    __syncthreads();
+    return r;
+  };
+  auto slot_sum = [&](float v) {
+    v = warp_sum(v);
+    if (lane == 0) mi.wred[warp] = v;
+    __syncthreads();
+    const float r = mi.wred[warp & ~1] + mi.wred[warp | 1];       // fixed order: both warps get the same bits
+    __syncthreads();
+    return r;
   };
 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    // ---- phase 0: ids, bias, embedding rows of the two samples ----
-    if (tid < 2 * F) {
-      const int s2 = tid / F, f = tid % F;
-      const int64_t s = 2 * t + s2;
-      mi.ids[s2][f] = (s < a.B) ? __ldg(a.idx + s * F + f) : -1;
-    }
+    // ---- phase 0: the staged rows of this tile have landed; start the next tile's rows, fetch the ids after that ----
+    float* Es = EsBuf + cur * (kEBytes / 4);
+    ldgsts_wait<0>();
     __syncthreads();
-    for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
-      const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
-      const int id = mi.ids[s2][f];
-      const float4 v = id >= 0 ? __ldg(reinterpret_cast<const float4*>(a.V + (size_t)id * KD) + c) : f4_zero();
-      *reinterpret_cast<float4*>(Es + (s2 * kMaxF + f) * kEP + 4 * c) = v;
-    }
+    if (t + gridDim.x < n_tiles) stage_rows(cur ^ 1);
+    const int id_next2 = load_id(t + 2 * (int64_t)gridDim.x);       // stored into mi.ids[cur] when this tile is done with it
     if (tid < 2) {
       float bs = 0.f;
-      if (a.bias)
-        for (int f = 0; f < F; f++) { const int id = mi.ids[tid][f]; if (id >= 0) bs += __ldg(a.bias + id); }
+      for (int f = 0; f < F; f++) bs += mi.biasv[cur][tid][f];
       mi.bsum[tid] = bs;
     }
-    __syncthreads();
 
-    // ---- phase 1: pair products -> P operand tiles (x and lo(x)) ----
-    for (int i = tid; i < 2 * P * (KD / 4); i += kThreads) {
-      const int s2 = i / (P * (KD / 4)), rem = i % (P * (KD / 4)), p = rem / (KD / 4), c = rem % (KD / 4);
-      const float4 ei = *reinterpret_cast<const float4*>(Es + (s2 * kMaxF + mi.pi[p]) * kEP + 4 * c);
-      const float4 ej = *reinterpret_cast<const float4*>(Es + (s2 * kMaxF + mi.pj[p]) * kEP + 4 * c);
-      const float4 v = f4_mul(ei, ej);
-      const uint32_t off = (uint32_t)(c >> 3) * kTile + swz(s2 * kSlot + p, c & 7);
-      *reinterpret_cast<float4*>(smem + oP + off) = v;
-      *reinterpret_cast<float4*>(smem + oP + 2 * kTile + off) = lo4(v);
+    // ---- phase 1: this thread's half row of pair products -> registers, TMEM (A of GEMM 1), PT tiles (A of GEMM 3) ----
+    float pr[32];
+    {
+      const float* ei = Es + (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + half * 32;
+      const float* ej = Es + (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + half * 32;
+      uint32_t rx[32], rl[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
+        pr[i] = prow ? x.x * y.x : 0.f; pr[i + 1] = prow ? x.y * y.y : 0.f;
+        pr[i + 2] = prow ? x.z * y.z : 0.f; pr[i + 3] = prow ? x.w * y.w : 0.f;
+      }
+      uint8_t* pt = smem + oP + (uint32_t)quarter * kTile;             // r block = quarter, column of the tile row = lane
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float lo = tf32_lo(pr[i]);
+        rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo);
+        const int k = half * 32 + i;
+        *reinterpret_cast<float*>(pt + swz_e(k, lane)) = pr[i];
+        *reinterpret_cast<float*>(pt + swz_e(KD + k, lane)) = lo;
+      }
+      tmem_st32(t_lane + cPX + half * 32, rx);
+      tmem_st32(t_lane + cPL + half * 32, rl);
+      tmem_st_wait();
     }
     fence_proxy_async();
     tc_fence_before();
@@ -219,12 +283,11 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
       for (int kb = 0; kb < 2; kb++)
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++) {
-          const uint32_t o = k4 * 32;
-          const uint32_t ax = sP + kb * kTile + o, al = sP + (2 + kb) * kTile + o;
+          const uint32_t o = k4 * 32, kc = kb * 32 + k4 * 8;          // byte offset inside the B tile row / A column offset
           const uint32_t bx = sWt + kb * kWTile + o, bl = sWt + (2 + kb) * kWTile + o;
-          umma_tf32(tmem, make_sdesc(al), make_sdesc(bx), idesc, (kb | k4) ? 1u : 0u);
-          umma_tf32(tmem, make_sdesc(ax), make_sdesc(bl), idesc, 1u);
-          umma_tf32(tmem, make_sdesc(ax), make_sdesc(bx), idesc, 1u);
+          umma_tf32_ts(tmem + cZ, tmem + cPL + kc, make_sdesc(bx), idesc, (kb | k4) ? 1u : 0u);
+          umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bl), idesc, 1u);
+          umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bx), idesc, 1u);
         }
       umma_commit(&mi.bar);
     }
@@ -233,37 +296,36 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
     tc_fence_after();
 
     // ---- epilogue 1: logits, softmax, afm, out, loss ----
-    float z[32];
     {
       uint32_t r[32];
-      tmem_ld32(t_lane + half * 32, r);
+      tmem_ld32(t_lane + cZ + half * 32, r);
       tmem_ld_wait_for(r);
       float sp = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        z[i] = __uint_as_float(r[i]) + mi.batt[half * 32 + i];                   // AFM.py:117-123
-        sp = fmaf(fmaxf(z[i], 0.f), mi.pvec[half * 32 + i], sp);
+        const float zi = __uint_as_float(r[i]) + mi.batt[half * 32 + i];         // AFM.py:117-123
+        sp = fmaf(fmaxf(zi, 0.f), mi.pvec[half * 32 + i], sp);
       }
       mi.s_part[half][row] = sp;
     }
     __syncthreads();
-    float att = 0.f;
+    const float s_r = mi.s_part[0][row] + mi.s_part[1][row];
+    const float mx = slot_max(prow ? s_r : -INFINITY);
+    const float e_r = prow ? expf(s_r - mx) : 0.f;                               // AFM.py:125 softmax over the pairs
+    const float den = slot_sum(e_r);
+    const float att = e_r / den;
     {
-      const float* s0 = mi.s_part[0] + ss * kSlot;
-      const float* s1 = mi.s_part[1] + ss * kSlot;
-      float mx = -INFINITY;
-      for (int p = 0; p < P; p++) mx = fmaxf(mx, s0[p] + s1[p]);
-      float den = 0.f;
-      for (int p = 0; p < P; p++) den += expf((s0[p] + s1[p]) - mx);            // AFM.py:125 softmax over the pairs
-      if (prow) att = expf((s0[pp] + s1[pp]) - mx) / den;
-      if (half == 0) mi.att[row] = att;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = att * pr[i];                           // AFM.py:130
+      const float cs = warp_colsum32(v, lane);
+      mi.afm_part[warp][lane] = cs;
     }
     __syncthreads();
     if (tid < 2 * KD) {
       const int s2 = tid >> 6, k = tid & 63;
-      const float* e = Es + s2 * kMaxF * kEP + k;
-      float acc = 0.f;
-      for (int p = 0; p < P; p++) acc = fmaf(mi.att[s2 * kSlot + p], e[mi.pi[p] * kEP] * e[mi.pj[p] * kEP], acc);   // AFM.py:130
+      const int w0 = (k >> 5) * 4 + 2 * s2;
+      const float acc = mi.afm_part[w0][k & 31] + mi.afm_part[w0 + 1][k & 31];
       mi.afm[s2][k] = acc;
       const float part = warp_sum(acc * mi.wpred[k]);                            // AFM.py:138-139
       if (lane == 0) mi.red[s2][warp & 1] = part;
@@ -292,41 +354,38 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
     __syncthreads();
     {
       // d a_p = d afm . P_p over this thread's 32 columns
-      const float* ei = Es + (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + half * 32;
-      const float* ej = Es + (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + half * 32;
       const float* df = mi.dafm[ss] + half * 32;
       float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
-        const float4 d = *reinterpret_cast<const float4*>(df + i);
-        acc = fmaf(d.x, x.x * y.x, acc); acc = fmaf(d.y, x.y * y.y, acc); acc = fmaf(d.z, x.z * y.z, acc); acc = fmaf(d.w, x.w * y.w, acc);
-      }
-      mi.da_part[half][row] = prow ? acc : 0.f;
+      for (int i = 0; i < 32; i++) acc = fmaf(df[i], pr[i], acc);
+      mi.da_part[half][row] = acc;
     }
     __syncthreads();
     {
-      const float* d0 = mi.da_part[0] + ss * kSlot;
-      const float* d1 = mi.da_part[1] + ss * kSlot;
-      const float* at = mi.att + ss * kSlot;
-      float sd = 0.f;
-      for (int p = 0; p < P; p++) sd = fmaf(at[p], d0[p] + d1[p], sd);
-      const float ds = att * ((d0[pp] + d1[pp]) - sd);                           // softmax backward
+      const float da = mi.da_part[0][row] + mi.da_part[1][row];
+      const float sd = slot_sum(att * da);
+      const float ds = att * (da - sd);                                          // softmax backward
       // dZ = ds * p * relu'(Z + b); d p += ds * relu(Z + b); d b += dZ (column sums over the tile rows)
       float dz[32], hp[32];
+      uint32_t rx[32], rl[32];
+      uint8_t* zt = smem + oZ + (uint32_t)quarter * kWTile;             // dZT x tiles: r block = quarter, column = lane
+      tmem_ld32(t_lane + cZ + half * 32, rx);                           // the logits again (cheaper than 32 live registers)
+      tmem_ld_wait_for(rx);
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        const bool on = z[i] > 0.f;
+        const float zi = __uint_as_float(rx[i]) + mi.batt[half * 32 + i];
+        const bool on = zi > 0.f;
         dz[i] = on ? ds * mi.pvec[half * 32 + i] : 0.f;
-        hp[i] = on ? ds * z[i] : 0.f;
+        hp[i] = on ? ds * zi : 0.f;
+        const float lo = tf32_lo(dz[i]);
+        rx[i] = __float_as_uint(dz[i]); rl[i] = __float_as_uint(lo);
+        const int an = half * 32 + i;
+        *reinterpret_cast<float*>(zt + swz_e(an, lane)) = dz[i];
+        *reinterpret_cast<float*>(zt + 4 * kWTile + swz_e(an, lane)) = lo;
       }
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const float4 v = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
-        const uint32_t off = (uint32_t)half * kTile + swz(row, c);
-        *reinterpret_cast<float4*>(smem + oZ + off) = v;
-        *reinterpret_cast<float4*>(smem + oZ + 2 * kTile + off) = lo4(v);
-      }
+      tmem_st32(t_lane + cZX + half * 32, rx);
+      tmem_st32(t_lane + cZL + half * 32, rl);
+      tmem_st_wait();
       const float cb = warp_colsum32(dz, lane);
       const float cp = warp_colsum32(hp, lane);
       atomicAdd(&mi.gbatt[half * 32 + lane], cb);
@@ -342,32 +401,32 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
       for (int ab = 0; ab < 2; ab++)
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++) {
-          const uint32_t o = k4 * 32;
-          const uint32_t ax = sZ + ab * kTile + o, al = sZ + (2 + ab) * kTile + o;
+          const uint32_t o = k4 * 32, kc = ab * 32 + k4 * 8;
           const uint32_t bx = sWn + ab * kWTile + o, bl = sWn + (2 + ab) * kWTile + o;
-          umma_tf32(tmem + 64, make_sdesc(al), make_sdesc(bx), idesc, (ab | k4) ? 1u : 0u);
-          umma_tf32(tmem + 64, make_sdesc(ax), make_sdesc(bl), idesc, 1u);
-          umma_tf32(tmem + 64, make_sdesc(ax), make_sdesc(bx), idesc, 1u);
+          umma_tf32_ts(tmem + cDP, tmem + cZL + kc, make_sdesc(bx), idesc, (ab | k4) ? 1u : 0u);
+          umma_tf32_ts(tmem + cDP, tmem + cZX + kc, make_sdesc(bl), idesc, 1u);
+          umma_tf32_ts(tmem + cDP, tmem + cZX + kc, make_sdesc(bx), idesc, 1u);
         }
-      const uint32_t idesc_mn = make_idesc_tf32_mn(kRows, KD);
+      // dW: reduction over the 128 tile rows = 4 r blocks x 4 k-steps of 8; A = [PT x ; PT lo] (M = 128), B = dZT x, dZT lo
 #pragma unroll
-      for (int ks = 0; ks < kRows / 8; ks++) {               // 8 tile rows (one swizzle atom) per MMA
-        const uint32_t o = ks * 1024;
-        const uint64_t ad = make_sdesc_mn(sP + o, kTile);     // M blocks: x kb0, x kb1, lo kb0, lo kb1
-        umma_tf32(tmem + 128, ad, make_sdesc_mn(sZ + o, kTile), idesc_mn, (since_drain | ks) ? 1u : 0u);
-        umma_tf32(tmem + 128, ad, make_sdesc_mn(sZ + 2 * kTile + o, kTile), idesc_mn, 1u);
-      }
+      for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+          const uint32_t o = k4 * 32;
+          const uint64_t ad = make_sdesc(sP + rb * kTile + o);
+          umma_tf32(tmem + cDW, ad, make_sdesc(sZ + rb * kWTile + o), idesc, (rb | k4) ? 1u : 0u);
+          umma_tf32(tmem + cDW, ad, make_sdesc(sZ + (4 + rb) * kWTile + o), idesc, 1u);
+        }
       umma_commit(&mi.bar);
     }
     mbar_wait(&mi.bar, bar_ph, nullptr);
     bar_ph ^= 1;
     tc_fence_after();
-    since_drain++;
 
-    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm) -> shared memory (the dZ tiles are free now) ----
+    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm) -> shared memory (the dZT tiles are free now) ----
     {
       uint32_t r[32];
-      tmem_ld32(t_lane + 64 + half * 32, r);
+      tmem_ld32(t_lane + cDP + half * 32, r);
       tmem_ld_wait_for(r);
       const float* df = mi.dafm[ss] + half * 32;
       float* dst = reinterpret_cast<float*>(smem + oZ) + row * KD;
@@ -377,15 +436,17 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
                                      fmaf(att, df[4 * c + 2], __uint_as_float(r[4 * c + 2])), fmaf(att, df[4 * c + 3], __uint_as_float(r[4 * c + 3])));
         *reinterpret_cast<float4*>(dst + 4 * ((half * 8 + c) ^ (row & 15))) = v;
       }
-      if (since_drain == kDrain) drain_dw();
+      tmem_ld32(t_lane + cDW + half * 32, r);                 // this tile's dW partial sum -> registers (two-level accumulation)
+      tmem_ld_wait_for(r);
+#pragma unroll
+      for (int i = 0; i < 32; i++) dwacc[i] += __uint_as_float(r[i]);
     }
-    if (since_drain == kDrain) since_drain = 0;
     tc_fence_before();
     __syncthreads();
     // dE_f = sum_{j != f} dP_(f,j) * E_j ; one vector reduction per 16 bytes of the gradient row
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
-      const int id = mi.ids[s2][f];
+      const int id = mi.ids[cur][s2][f];
       if (id < 0) continue;
       float4 acc = f4_zero();
       for (int j = 0; j < F; j++) {
@@ -410,22 +471,20 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
         if (a.touch_stamp) a.touch_stamp[id] = a.stamp;      // compacted into the touched-row list afterwards
       }
     }
-    __syncthreads();        // Es / ids / the dP rows are free for the next tile; the P tiles were released by the commit wait
-    // the dZ tile region was used as plain storage: its pad rows must read as zero again for the next GEMM 2 / 3
-    for (int i = tid; i < 2 * (kSlot - P) * 8; i += kThreads) {
-      const int s2 = i / ((kSlot - P) * 8), rem = i % ((kSlot - P) * 8), r2 = s2 * kSlot + P + rem / 8, c = rem % 8;
-      *reinterpret_cast<float4*>(smem + oZ + swz(r2, c)) = f4_zero();
-      *reinterpret_cast<float4*>(smem + oZ + kTile + swz(r2, c)) = f4_zero();
-    }
+    __syncthreads();        // Es / ids / the dP rows are free for the next tile (every thread rewrites its PT / dZT column)
+    if (tid < 2 * F) mi.ids[cur][tid / F][tid % F] = id_next2;
+    cur ^= 1;
   }
 
-  if (since_drain != 0) drain_dw();
+  ldgsts_wait<0>();
   tc_fence_before();
   __syncthreads();
-  // ---- flush the CTA's accumulators ----
-  for (int i = tid; i < KD * KD; i += kThreads) {
-    const float v = dWs[(i >> 6) * kDWP + (i & 63)];
-    if (v != 0.f) atomicAdd(a.gW + i, v);
+  // ---- flush the accumulators: dW[k][a] = D[k][a] + D[64 + k][a] (x and lo rows land on the same element) ----
+  {
+    float* dst = a.gW + (size_t)(row & 63) * KD + half * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (dwacc[i] != 0.f) atomicAdd(dst + i, dwacc[i]);
   }
   if (tid < KD) {
     atomicAdd(a.gbatt + tid, mi.gbatt[tid]);
@@ -446,8 +505,8 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
 
 int dispatch_afm_fused_tc(const AfmArgs& a, int64_t M, cudaStream_t st) {
   if (a.K != aft::KD || a.A != aft::KD || a.F > aft::kMaxF || a.F < 2 || a.P > aft::kSlot) return 1;
-  const char* env = getenv("HHFM_AFM_TC");               // opt-in while the dW product is being reworked
-  if (!env || env[0] != '1') return 1;
+  const char* env = getenv("HHFM_AFM_TC");               // 0 = fp32 CUDA-core kernels (A/B runs, tests of both paths)
+  if (env && env[0] == '0') return 1;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(aft::afm_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aft::kSmemBytes) != cudaSuccess) {

@@ -14,17 +14,17 @@ struct OptP {
 template <int KIND>
 __device__ __forceinline__ void opt_elem(float& w, float& s1, float& s2, float g, const OptP& p) {
   if (KIND == HHFM_OPT_ADAGRAD) {
-    s1 = s1 + g * g;
+    s1 = fmaf(g, g, s1);                                // explicit contractions: the same bits as p2p.cu::opt_elem2
     w = w - p.lr * g / sqrtf(s1);
   } else if (KIND == HHFM_OPT_ADAM) {
-    s1 = p.p1 * s1 + (1.f - p.p1) * g;
-    s2 = p.p2 * s2 + (1.f - p.p2) * (g * g);
+    s1 = fmaf(p.p1, s1, (1.f - p.p1) * g);
+    s2 = fmaf(p.p2, s2, (1.f - p.p2) * (g * g));
     w = w - p.lr * s1 / (sqrtf(s2) + p.p3);
   } else if (KIND == HHFM_OPT_MOMENTUM) {
-    s1 = s1 * p.p1 + g;
-    w = w - p.lr * s1;
+    s1 = fmaf(s1, p.p1, g);
+    w = fmaf(-p.lr, s1, w);
   } else {
-    w = w - p.lr * g;
+    w = fmaf(-p.lr, g, w);
   }
 }
 

@@ -136,11 +136,10 @@ class SymmExchange:
 
     x            this rank's buffer (float32 tensor, n_floats)
     x_table      host int64[ws]: address of every rank's buffer in this process (rank order, own one included)
-    flag_table   host int64[ws]: address of every rank's flag array (FLAG_INTS int32, zero-initialised)
+    flag_table   host int64[ws]: address of every rank's flag array (hhfm_dp_flag_ints() int32, zero-initialised)
     multicast    address of the multicast alias of `x`, or 0
     """
 
-    FLAG_INTS = 64
     MAX_RANKS = 16
 
     def __init__(self, n_floats, device, group=None):
@@ -149,6 +148,8 @@ class SymmExchange:
         if self.ws > self.MAX_RANKS:
             raise RuntimeError("SymmExchange: at most %d ranks" % self.MAX_RANKS)
         self.n = int(n_floats)
+        from . import _lib
+        self.FLAG_INTS = int(_lib.load().hhfm_dp_flag_ints())   # two phases x CTAs x ranks
         flag_off = (self.n + 63) // 64 * 64                     # flags start on a 256-byte boundary behind the floats
         total = flag_off + self.FLAG_INTS
         grp = group if group is not None else dist.group.WORLD

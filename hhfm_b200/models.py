@@ -72,7 +72,7 @@ class _Base:
         self._fused = os.environ.get("HHFM_FUSED_STEP", "1") != "0"      # fold + exchange + optimizer + loss in one kernel
         self._dp_state = torch.zeros(4, dtype=torch.int32, device=self.device)      # [step counter, sticky error, -, -]
         self._dp_state_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
-        self._reg_ws = torch.zeros(256, dtype=torch.float32, device=self.device)
+        self._reg_ws = torch.zeros(512, dtype=torch.float32, device=self.device)
         self._x_local = None
         self._segs = None
         self._bind_arena(torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device))
@@ -248,9 +248,10 @@ class _Base:
             x, mc, xt, ft, rank, ws = dpx.x, (C.c_void_p(dpx.multicast) if dpx.multicast else None), dpx.x_table, dpx.flag_table, \
                 dpx.rank, dpx.ws
         if hot is not None:
-            hargs = (ptr(hot.ghot), ptr(hot.ghot_bias) if with_hot_bias else None, hot.n_rep, hot.n_hot, self._K, ptr(hot.rows), n_v)
+            hargs = (ptr(hot.ghot), ptr(hot.ghot_bias) if with_hot_bias else None, hot.n_rep, hot.n_hot, self._K, self._M,
+                     ptr(hot.slot), n_v)
         else:
-            hargs = (None, None, 0, 0, self._K, None, n_v)
+            hargs = (None, None, 0, 0, self._K, self._M, None, n_v)
         _lib.call("hhfm_dp_step", o.KIND_ID[o.kind], C.cast(arr, C.c_void_p), n_seg, ptr(self._arena), n_g, *hargs,
                   ptr(self._loss_partials), ptr(x), mc, xt, ft, rank, ws, ptr(self._dp_state), lr, o.beta1, o.beta2, o.eps,
                   ptr(self._reg_ws), ptr(self._loss_dev), float(os.environ.get("HHFM_DP_TIMEOUT_S", "120")), cur_stream())

@@ -341,18 +341,20 @@ int hhfm_l2_read_sweep(const float* buf, int64_t n_floats, int32_t iters, float*
  *   replaces what `optimizer.minimize` (FM.py:129-136, OurModel7.py:185-189) does after the gradients exist, for a batch
  *   whose rows are sharded across the GPUs of one box.
  *
- *   arena        rank-private gradient buffer; floats [0, n_grad) are consumed (and cleared); gV occupies [0, M*K).
+ *   arena        rank-private gradient buffer; floats [0, n_grad) are consumed (and cleared); the table gradient [M, K]
+ *                occupies [0, M*K).
  *   segs         up to 4 variables whose gradients are arena[offset, offset+n): w / s1 / s2 as in K5, lamda per segment
  *                (g_eff = g + lamda*w; the loss gets 0.5*lamda*sum(w^2) of the weights BEFORE the update).
- *   ghot...      the two-level scatter plan of K1/K3 (NULL / 0 = none); bias_off = offset of the feature_bias gradient.
+ *   ghot...      the two-level scatter plan of K1/K3 (NULL / 0 = none): hot_slot [M] as given to the scatter kernels,
+ *                bias_off = offset of the feature_bias gradient (with ghot_bias).
  *   x_local      this rank's exchange buffer, hhfm_dp_exchange_floats(n_grad) floats.  For n_ranks > 1 it must be symmetric
  *                memory: x_peers_host[r] = address of rank r's buffer in THIS process (own one included), x_multicast =
  *                the multicast alias of the same buffers (multimem.ld_reduce / multimem.st) or NULL (peer loads / stores).
- *   flag_peers_host[r]  address of rank r's flag array (>= 16 int32, zero-initialised, symmetric memory).
- *   state        device int32[4]: [0] step counter (starts 0, owned by the kernel), [1] sticky error flag -- set when a
- *                cross-GPU barrier waited longer than timeout_s (<= 0: 120 s); later steps return at once, the host
- *                reads it back with the loss.  No trap: the CUDA context stays usable.
- *   reg_workspace  >= 256 floats.   loss_out[0] = sum over ranks of sum(loss_partials) + regulariser.
+ *   flag_peers_host[r]  address of rank r's flag array (hhfm_dp_flag_ints() int32, zero-initialised, symmetric memory).
+ *   state        device int32[4], zero-initialised: [0] step counter, [2] ticket (both owned by the kernel), [1] sticky
+ *                error flag -- set when a cross-GPU flag wait took longer than timeout_s (<= 0: 120 s); later steps return
+ *                at once, the host reads it back with the loss.  No trap: the CUDA context stays usable.
+ *   reg_workspace  >= 257 floats.   loss_out[0] = sum over ranks of sum(loss_partials) + regulariser.
  *   Adam: `lr` is lr_t (K5); Momentum: beta1 carries the momentum.  All replicas consume the same reduced bits, so they
  *   stay bit-identical.  n_ranks == 1: fold + optimizer + loss of a single-GPU step in one launch.
  * ------------------------------------------------------------------------------------------------ */
@@ -366,8 +368,9 @@ typedef struct {
   int32_t reserved;
 } hhfm_dp_segment;
 int64_t hhfm_dp_exchange_floats(int64_t n_grad);
+int64_t hhfm_dp_flag_ints(void);
 int hhfm_dp_step(int32_t kind, const hhfm_dp_segment* segs, int32_t n_segs, float* arena, int64_t n_grad, float* ghot,
-                 float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K, const int32_t* hot_rows, int64_t bias_off,
+                 float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K, int64_t M, const int32_t* hot_slot, int64_t bias_off,
                  const float* loss_partials, float* x_local, float* x_multicast, const int64_t* x_peers_host,
                  const int64_t* flag_peers_host, int32_t rank, int32_t n_ranks, int32_t* state, float lr, float beta1,
                  float beta2, float eps, float* reg_workspace, float* loss_out, double timeout_s, hhfm_stream_t stream);
