@@ -669,7 +669,7 @@ def run_ours(args):
         import bench_models as bm
         margs = argparse.Namespace(steps=10)
         models = {}
-        for name in ("hhfm_c5", "fm_c1", "fm_c5", "bpr_c4", "afm_c3", "dfm"):
+        for name in ("hhfm_c5", "fm_c1", "fm_c5", "fm_c5_l2", "bpr_c4", "afm_c3", "dfm"):
             try:
                 models[name] = bm.RUNNERS[name](margs, dev)
             except Exception as e:                      # a secondary line must not take the headline line down

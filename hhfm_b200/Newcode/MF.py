@@ -39,6 +39,7 @@ class Train(PointwiseTrain):
     method = method
     NG = 2
     neg_label = -1           # MF.py:190
+    n_model_cols = 2         # the table holds users and items only (MF.py:171)
 
     def __init__(self, args):
         self.args = args

@@ -48,6 +48,9 @@ SIGNATURES = {
     "hhfm_scatter_add_rows": [vp, vp, i64, i64, vp, i64, vp],
     "hhfm_gather_rows": [vp, vp, i64, i64, i64, vp, i32, vp],
     "hhfm_touch_rows": [vp, i64, vp, i32, vp, vp, vp],
+    "hhfm_mark_rows": [vp, i64, vp, i32, i64, vp, vp, vp],
+    "hhfm_opt_adagrad_l2_replay": [vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, i32, vp],
+    "hhfm_opt_adagrad_rows_l2": [vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, vp, i32, vp],
     "hhfm_opt_adagrad_dense_l2": [vp, vp, vp, i64, f32, f32, i32, vp, vp],
     "hhfm_opt_adam_dense_l2": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp],
     "hhfm_opt_momentum_dense_l2": [vp, vp, vp, i64, f32, f32, f32, i32, vp, vp],

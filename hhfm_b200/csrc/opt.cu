@@ -4,6 +4,7 @@
 // ApplyAdam with lr_t folded by the caller, ApplyMomentum `accum = accum*mu + g; var -= lr*accum`.
 // All kernels are pure streaming float4 passes (HBM-bound): read g,w,state -> write w,state,(g=0).
 #include "common.cuh"
+#include "staged.cuh"
 
 namespace hhfm {
 
@@ -249,6 +250,78 @@ __global__ void __launch_bounds__(256) touch_rows_kernel(const int32_t* __restri
     touch_row(stamp_arr, stamp, rows, count, __ldg(ids + i));
 }
 
+// plain stamp stores (padding ids < 0 skipped); the list is produced by launch_touched_compact afterwards
+__global__ void __launch_bounds__(256) mark_rows_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ stamp_arr,
+                                                        int32_t stamp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int id = __ldg(ids + i);
+    if (id >= 0) stamp_arr[id] = stamp;
+  }
+}
+
+// Lazy-exact dense L2 (hard part 2-ii).  The reference's l2_regularizer on the table (FM.py:124,
+// OurModel7.py:181-182) makes every row move every step: g = lamda*w; acc += g^2; w -= lr*g/sqrt(acc).  For a row that no
+// sample touches those steps depend on nothing but the row itself, so they can be replayed later, element by element, with
+// the same fp32 operations in the same order: bit-identical to the dense kernel.  `last_step[row]` = the last optimizer step
+// the row reflects; this kernel replays steps last+1 .. upto for the listed rows (rows == NULL: all M rows).
+__global__ void __launch_bounds__(256) adagrad_l2_replay_kernel(float* __restrict__ w, float* __restrict__ acc,
+                                                                int32_t* __restrict__ last_step, const int32_t* __restrict__ rows,
+                                                                const int32_t* __restrict__ n_rows_dev, int64_t M, int K, OptP p,
+                                                                int32_t upto) {
+  const int kv = K >> 2;
+  const int64_t n_rows = rows ? (int64_t)*n_rows_dev : M;
+  const int64_t total = n_rows * kv;
+  float dummy = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t li = i / kv;
+    const int r = rows ? rows[li] : (int)li;
+    const int n = upto - last_step[r];
+    if (n > 0) {
+      const int64_t off = (int64_t)r * kv + (i % kv);
+      float4 wv = reinterpret_cast<float4*>(w)[off], av = reinterpret_cast<float4*>(acc)[off];
+      for (int s = 0; s < n; s++) {
+        opt_elem<HHFM_OPT_ADAGRAD>(wv.x, av.x, dummy, fmaf(wv.x, p.lamda, 0.f), p);
+        opt_elem<HHFM_OPT_ADAGRAD>(wv.y, av.y, dummy, fmaf(wv.y, p.lamda, 0.f), p);
+        opt_elem<HHFM_OPT_ADAGRAD>(wv.z, av.z, dummy, fmaf(wv.z, p.lamda, 0.f), p);
+        opt_elem<HHFM_OPT_ADAGRAD>(wv.w, av.w, dummy, fmaf(wv.w, p.lamda, 0.f), p);
+      }
+      reinterpret_cast<float4*>(w)[off] = wv;
+      reinterpret_cast<float4*>(acc)[off] = av;
+    }
+  }
+}
+
+// every chunk of a row reads last_step before any chunk of that row may overwrite it: the stamps are written by a second
+// launch
+__global__ void __launch_bounds__(256) set_last_step_kernel(int32_t* __restrict__ last_step, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ n_rows_dev, int64_t M, int32_t value) {
+  const int64_t n_rows = rows ? (int64_t)*n_rows_dev : M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
+    last_step[rows ? rows[i] : i] = value;
+}
+
+// SparseApplyAdagrad on the listed rows with the dense L2 term of this step: g_eff = g + lamda*w (same expression as
+// opt_dense_kernel); the caller stamps last_step = t afterwards.
+__global__ void __launch_bounds__(256) adagrad_rows_l2_kernel(float* __restrict__ w, float* __restrict__ acc, float* __restrict__ g,
+                                                              const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows_dev,
+                                                              int K, OptP p, int zero_grad) {
+  const int n_rows = *n_rows_dev;
+  const int kv = K >> 2;
+  const int64_t total = (int64_t)n_rows * kv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = rows[i / kv];
+    const int64_t off = (int64_t)r * kv + (i % kv);
+    float4 wv = reinterpret_cast<float4*>(w)[off], gv = reinterpret_cast<float4*>(g)[off];
+    float4 av = reinterpret_cast<float4*>(acc)[off];
+    float4 bv = f4_zero();
+    gv = f4_fma(wv, p.lamda, gv);
+    opt_vec4<HHFM_OPT_ADAGRAD>(wv, av, bv, gv, p);
+    reinterpret_cast<float4*>(w)[off] = wv;
+    reinterpret_cast<float4*>(acc)[off] = av;
+    if (zero_grad) reinterpret_cast<float4*>(g)[off] = f4_zero();
+  }
+}
+
 // Measurement aid (bench.py `roofline.peak` of the L2-bound kernels): every thread streams the whole buffer `iters` times
 // with 16-byte loads that bypass L1 (ld.global.cg), so a buffer that fits the 126 MB L2 is served by L2 only.
 __global__ void __launch_bounds__(256) l2_read_sweep_kernel(const float4* __restrict__ buf, int64_t n4, int iters, float* sink) {
@@ -353,6 +426,50 @@ extern "C" int hhfm_gather_rows(float* table, const int32_t* ids, int64_t n, int
   const int64_t need = (work + 255) / 256, cap = (int64_t)sm_count() * 8;
   gather_rows_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(table, ids, n, (int)K, out, zero_src);
   return check_launch("gather_rows_kernel");
+}
+
+extern "C" int hhfm_mark_rows(const int32_t* ids, int64_t n, int32_t* stamp_arr, int32_t stamp, int64_t M, int32_t* rows,
+                              int32_t* count, hhfm_stream_t stream) {
+  HHFM_REQUIRE(ids && stamp_arr && rows && count && n >= 0 && M > 0, "mark_rows: bad argument");
+  if (n == 0) return HHFM_OK;
+  const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  mark_rows_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(ids, n, stamp_arr, stamp);
+  int rc = check_launch("mark_rows_kernel");
+  if (rc != HHFM_OK) return rc;
+  return launch_touched_compact(stamp_arr, stamp, M, rows, count, (cudaStream_t)stream);
+}
+
+extern "C" int hhfm_opt_adagrad_l2_replay(float* w, float* acc, int32_t* last_step, const int32_t* rows, const int32_t* n_rows_dev,
+                                          int64_t max_rows, int64_t M, int64_t K, float lr, float lamda, int32_t upto,
+                                          hhfm_stream_t stream) {
+  HHFM_REQUIRE(w && acc && last_step && M > 0 && K > 0 && K % 4 == 0, "opt_adagrad_l2_replay: bad argument");
+  HHFM_REQUIRE(!rows || (n_rows_dev && max_rows > 0), "opt_adagrad_l2_replay: rows needs n_rows_dev and max_rows");
+  OptP p{lr, lamda, 0.f, 0.f, 0.f};
+  const int64_t n = rows ? max_rows : M;
+  const int64_t need = (n * (K >> 2) + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  adagrad_l2_replay_kernel<<<grid, 256, 0, st>>>(w, acc, last_step, rows, n_rows_dev, M, (int)K, p, upto);
+  int rc = check_launch("adagrad_l2_replay_kernel");
+  if (rc != HHFM_OK) return rc;
+  set_last_step_kernel<<<grid, 256, 0, st>>>(last_step, rows, n_rows_dev, M, upto);
+  return check_launch("set_last_step_kernel");
+}
+
+extern "C" int hhfm_opt_adagrad_rows_l2(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev,
+                                        int64_t max_rows, int64_t K, float lr, float lamda, int32_t zero_grad,
+                                        int32_t* last_step, int32_t step, hhfm_stream_t stream) {
+  HHFM_REQUIRE(w && acc && g && rows && n_rows_dev && last_step && max_rows > 0 && K > 0 && K % 4 == 0,
+               "opt_adagrad_rows_l2: bad argument");
+  OptP p{lr, lamda, 0.f, 0.f, 0.f};
+  const int64_t need = (max_rows * (K >> 2) + 255) / 256, cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  adagrad_rows_l2_kernel<<<grid, 256, 0, st>>>(w, acc, g, rows, n_rows_dev, (int)K, p, zero_grad);
+  int rc = check_launch("adagrad_rows_l2_kernel");
+  if (rc != HHFM_OK) return rc;
+  set_last_step_kernel<<<grid, 256, 0, st>>>(last_step, rows, n_rows_dev, 0, step);
+  return check_launch("set_last_step_kernel");
 }
 
 extern "C" int hhfm_touch_rows(const int32_t* ids, int64_t n, int32_t* stamp_arr, int32_t stamp, int32_t* rows, int32_t* count,

@@ -22,6 +22,7 @@
 // immediately -- the CUDA context stays usable (no __trap).  The launch is cooperative only for its guarantee that all
 // CTAs are resident (a CTA waits for its peers on other GPUs, never for a CTA of its own grid).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -152,11 +153,12 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const DpArgs a) {
   float4* x4 = reinterpret_cast<float4*>(a.x);
 
   // this rank's data loss (sum of the per-CTA partials of the scatter kernel), by the CTA that owns the loss slot
-  if (owns_loss && threadIdx.x < 32) {
+  if (owns_loss) {                                   // CTA-uniform; all threads: four independent loads each, not 64 in a chain
     float l = 0.f;
-    for (int i = lane; i < kPartials; i += 32) l += a.loss_partials[i];
-    l = warp_sum(l);
-    if (lane == 0) s_loss = l;
+#pragma unroll
+    for (int i = 0; i < kPartials / kDpThreads; i++) l += __ldcv(a.loss_partials + threadIdx.x + i * kDpThreads);
+    l = block_sum(l, scratch);
+    if (threadIdx.x == 0) s_loss = l;
   }
   __syncthreads();
 
@@ -358,9 +360,13 @@ static int launch_dp(const DpArgs& a, cudaStream_t st) {
     }
     grid_cached = sm_count();      // one CTA per SM: every CTA is resident, grid.sync() is legal
   }
+  // One CTA per SM and at least one resident CTA per SM (checked above): the whole grid is resident as soon as the previous
+  // kernel of the stream has drained, which is all the cross-GPU flag waits need (a CTA never waits for a CTA of its own
+  // grid).  A cooperative launch would guarantee it formally but costs tens of microseconds per step; HHFM_DP_COOP=1 selects it.
+  static const bool coop = [] { const char* e = getenv("HHFM_DP_COOP"); return e && e[0] == '1'; }();
   cudaError_t e = cudaSuccess;
-  if (a.n_ranks == 1) {
-    dp_step_kernel<KIND><<<grid_cached, kDpThreads, 0, st>>>(a);          // no peer waits: residency does not matter
+  if (a.n_ranks == 1 || !coop) {
+    dp_step_kernel<KIND><<<grid_cached, kDpThreads, 0, st>>>(a);
   } else {
     void* params[] = {(void*)&a};
     e = cudaLaunchCooperativeKernel((const void*)dp_step_kernel<KIND>, dim3(grid_cached), dim3(kDpThreads), params, 0, st);

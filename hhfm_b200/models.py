@@ -75,6 +75,10 @@ class _Base:
         self._reg_ws = torch.zeros(512, dtype=torch.float32, device=self.device)
         self._x_local = None
         self._segs = None
+        # lazy-exact dense L2: "auto" = tables of 96 MB and more with lamda > 0 on one GPU; True / False force it
+        self.lazy_l2 = {"0": False, "1": True}.get(os.environ.get("HHFM_LAZY_L2", ""), "auto")
+        self._last_step = None
+        self._lazy_reg = None
         self._bind_arena(torch.zeros(n_v + n_b + 4 + P, dtype=torch.float32, device=self.device))
         self._sq_partials = torch.zeros(P, dtype=torch.float32, device=self.device)
         self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -116,6 +120,51 @@ class _Base:
         seed = (int(getattr(self, "random_seed", 2016)) * 0x9E3779B97F4A7C15 + self._opt.t) & 0xFFFFFFFFFFFFFFFF
         self._last_drop_seed = seed
         return keep, seed
+
+    # ---- lazy-exact dense L2 -----------------------------------------------------------------------------------------
+    def _lazy(self):
+        """True when the dense L2 update of the table runs lazily: only the rows a batch gathers are brought up to date
+        (replay of their missed `g = lamda*w` steps, bit-identical to the dense kernel) and updated; everything else waits
+        for `flush()`.  Adagrad (the reference default), one GPU, lamda > 0."""
+        if self._lamda <= 0 or self._opt.kind != "adagrad" or self._dp_group is not None:
+            return False
+        if self.lazy_l2 == "auto":
+            return self._M * self._K * 4 >= (96 << 20)
+        return bool(self.lazy_l2)
+
+    def _lazy_prepare(self, ids_dev):
+        """Before the forward of step t: the distinct rows of the batch -> touched list, replayed up to step t-1."""
+        if self._last_step is None:
+            self._last_step = torch.zeros(self._M, dtype=torch.int32, device=self.device)
+        t = self._touch
+        t.begin_step()
+        flat = ids_dev.reshape(-1)
+        st = cur_stream()
+        _lib.call("hhfm_mark_rows", ptr(flat), flat.numel(), ptr(t.stamp_arr), t.stamp, self._M, ptr(t.rows), ptr(t.count), st)
+        V = self.weights["feature_embeddings"]
+        acc, _ = self._opt.slots("feature_embeddings", V)
+        _lib.call("hhfm_opt_adagrad_l2_replay", ptr(V), ptr(acc), ptr(self._last_step), ptr(t.rows), ptr(t.count), self._M, self._M,
+                  self._K, self._opt.lr, self._lamda, self._opt.t - 1, st)
+
+    def _lazy_apply(self):
+        """Step t on the gathered rows (g + lamda*w), stamped with t.  The regulariser term of the reported loss is the one of
+        the last flush (the untouched rows are not materialised between flushes)."""
+        t = self._touch
+        V = self.weights["feature_embeddings"]
+        acc, _ = self._opt.slots("feature_embeddings", V)
+        _lib.call("hhfm_opt_adagrad_rows_l2", ptr(V), ptr(acc), ptr(self._gV), ptr(t.rows), ptr(t.count), self._M, self._K,
+                  self._opt.lr, self._lamda, 1, ptr(self._last_step), self._opt.t, cur_stream())
+
+    def flush(self):
+        """Bring every row of the table to the current optimizer step (no-op outside the lazy mode).  Called by everything
+        that reads the table: topk, predict / score_device, get_weights."""
+        if self._last_step is None:
+            return
+        V = self.weights["feature_embeddings"]
+        acc, _ = self._opt.slots("feature_embeddings", V)
+        _lib.call("hhfm_opt_adagrad_l2_replay", ptr(V), ptr(acc), ptr(self._last_step), None, None, 0, self._M, self._K,
+                  self._opt.lr, self._lamda, self._opt.t, cur_stream())
+        self._lazy_reg = (0.5 * self._lamda) * V.square().sum(dtype=torch.float32)
 
     def _hot_plan(self, idx_dev, with_bias):
         """Hot-row plan for the two-level scatter (engine.HotRows), built once from the first batch."""
@@ -218,7 +267,7 @@ class _Base:
             return False
         if self._dp_group is not None:
             return self._dpx is not None
-        return self._lamda > 0
+        return self._lamda > 0 and not self._lazy()
 
     def _fused_tail(self, hot, with_hot_bias):
         from . import dist as hd
@@ -259,6 +308,16 @@ class _Base:
 
     def _finish_step(self, hot, with_hot_bias, bias_step=None):
         """Everything after the scatter kernels of a step: fold, exchange, optimizer, loss."""
+        if self._lazy():
+            if hot:
+                hot.fold(self._gV, self._gb if with_hot_bias else None)
+            self._lazy_apply()
+            if bias_step is not None:
+                bias_step()
+            self._enqueue_loss(False)
+            if self._lazy_reg is not None:
+                self._loss_dev += self._lazy_reg
+            return
         if self._use_fused_tail():
             self._fused_tail(hot, with_hot_bias)
             return
@@ -325,6 +384,7 @@ class _Base:
     def _topk(self, kind, A, n_ctx, n_time, pools, bias, tp):
         from . import dist as hd
         A = np.asarray(A)
+        self.flush()
         A_dev, stride = self._topn.upload_rows(A, self._M)
         V = self.weights["feature_embeddings"]
         grp = getattr(self, "_eval_group", None)
@@ -343,7 +403,7 @@ class _Base:
     def _touch_args(self, extra=False):
         """Touched-row tracking is only paid for when a *_rows optimizer will consume the list."""
         need = (self._dp_group is None or self._dp_sparse) and (self._lamda <= 0 or extra)
-        if not need:
+        if not need or self._lazy():            # lazy mode: the list was built from the ids before the forward
             return (None, 0, None, None)
         self._touch.begin_step()
         return (ptr(self._touch.stamp_arr), self._touch.stamp, ptr(self._touch.rows), ptr(self._touch.count))
@@ -405,8 +465,11 @@ class _Base:
             t = torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(self.weights[k].shape)
             self.weights[k].copy_(t.to(self.device))
         self._version += 1
+        if self._last_step is not None:
+            self._last_step.fill_(self._opt.t)       # injected weights are current as of this step
 
     def get_weights(self):
+        self.flush()
         return {k: v.detach().cpu().numpy().copy() for k, v in self.weights.items()}
 
     def invalidate(self):
@@ -459,6 +522,7 @@ class FM(_Base):
     # -- forward only: `sess.run(model.out, ...)` of evaluate_AUC (FM.py:313-319) --
     def score_device(self, idx):
         """Scores [n] (device) for device-resident id rows idx int32 [n, F]."""
+        self.flush()
         B, F = idx.shape
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         _lib.call("hhfm_fm_fwd", None, ptr(idx), None, B, F, ptr(self.weights["feature_embeddings"]),
@@ -483,6 +547,8 @@ class FM(_Base):
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
         bias = self.weights.get("feature_bias")
+        if self._lazy():
+            self._lazy_prepare(idx)
         ts, stamp, tr, tc = self._touch_args(extra=self._opt.kind == "momentum")
         hot = self._hot_plan(idx, True)
         keep, dseed = self._drop_args()
@@ -568,6 +634,7 @@ class MF(FM):
         self._b0 = None
 
     def score_device(self, idx):
+        self.flush()
         B = idx.shape[0]
         idx2 = idx[:, :2].contiguous() if idx.shape[1] != 2 else idx
         out = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -588,6 +655,8 @@ class MF(FM):
         B = idx.shape[0]
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
+        if self._lazy():
+            self._lazy_prepare(idx)
         ts, stamp, tr, tc = self._touch_args()
         hot = self._hot_plan(idx, False)
         keep, dseed = self._drop_args()
@@ -626,6 +695,8 @@ class _PairRank(_Base):
         self._opt.begin_step()
         V = self.weights["feature_embeddings"]
         pc, pt, pf = self.pools
+        if self._lazy():
+            self._lazy_prepare(idx)                  # padding ids (-1) are skipped
         ts, stamp, tr, tc = self._touch_args()
         hot = self._hot_plan(idx, False)
         _lib.call("hhfm_pairrank_fwd_bwd", ptr(idx), B, stride, n_ctx, n_time, n_neg, pc, pt, pf, ptr(V), self._M,
@@ -642,6 +713,7 @@ class _PairRank(_Base):
         return self._positive_feedback_dev(idx, n_ctx, n_time).cpu().numpy().reshape(-1, 1)
 
     def _positive_feedback_dev(self, idx, n_ctx, n_time):
+        self.flush()
         B, stride = idx.shape
         pos = torch.empty(B, dtype=torch.float32, device=self.device)
         pc, pt, pf = self.pools

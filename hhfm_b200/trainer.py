@@ -193,14 +193,16 @@ class PointwiseTrain(BaseTrain):
 
     NG = 2
     neg_label = 0            # FM.py:248 `-0`; AFM.py:317 / DFM.py:286 use -1
+    n_model_cols = None      # id columns the model reads (None = all; MF reads user and item only, MF.py:81-82)
 
     def run_epoch_device(self):
         """The same epoch with the negatives drawn on the device and the shuffled batches cut from device-resident rows:
         one id upload per epoch instead of one per batch."""
         model, smp = self.model, self._sampler()
         pos = np.array(self.data.Train_data.values)
-        n, F = pos.shape[0], pos.shape[1] - 1
-        idx, _ = model._uploader.upload([pos[:, 1:]], model._M, align=1)
+        n = pos.shape[0]
+        F = pos.shape[1] - 1 if self.n_model_cols is None else int(self.n_model_cols)
+        idx, _ = model._uploader.upload([pos[:, 1:1 + F]], model._M, align=1)
         negs = smp.sample(smp.key_ids(pos[:, 1:]), self.NG)
         rows = torch.cat([idx, engine.expand_rows(idx, F, negs)], dim=0)
         y = torch.cat([torch.as_tensor(pos[:, 0].astype(np.float32), device=model.device),

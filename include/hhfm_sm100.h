@@ -323,6 +323,22 @@ int hhfm_opt_momentum_rows(float* w, float* acc, float* g, const int32_t* rows, 
 int hhfm_opt_sgd_rows(float* w, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
                       int64_t K, float lr, int32_t zero_grad, hhfm_stream_t stream);
 
+/* Lazy-exact dense L2 (hard part 2-ii): the reference's l2_regularizer on the table (FM.py:124,
+ * OurModel7.py:181-182) moves every row every step (g = lamda*w for an untouched row).  Those steps depend on the row alone,
+ * so they are replayed -- same fp32 operations, same order, bit-identical to hhfm_opt_adagrad_dense_l2 -- when the row is next
+ * gathered and at flush.  last_step [M] int32 = the optimizer step each row reflects.
+ *   hhfm_mark_rows: rows [*count] = the distinct ids >= 0 among ids[0, n) (stamp stores + compaction; stamp as in K1).
+ *   hhfm_opt_adagrad_l2_replay: replays steps last_step[row]+1 .. upto for the listed rows (rows == NULL: all M rows) and
+ *     sets last_step = upto.
+ *   hhfm_opt_adagrad_rows_l2: step `step` on the listed rows with g_eff = g + lamda*w; sets last_step = step. */
+int hhfm_mark_rows(const int32_t* ids, int64_t n, int32_t* stamp_arr, int32_t stamp, int64_t M, int32_t* rows, int32_t* count,
+                   hhfm_stream_t stream);
+int hhfm_opt_adagrad_l2_replay(float* w, float* acc, int32_t* last_step, const int32_t* rows, const int32_t* n_rows_dev,
+                               int64_t max_rows, int64_t M, int64_t K, float lr, float lamda, int32_t upto, hhfm_stream_t stream);
+int hhfm_opt_adagrad_rows_l2(float* w, float* acc, float* g, const int32_t* rows, const int32_t* n_rows_dev, int64_t max_rows,
+                             int64_t K, float lr, float lamda, int32_t zero_grad, int32_t* last_step, int32_t step,
+                             hhfm_stream_t stream);
+
 /* gV[hot_rows[s], :] += sum_r ghot[r, s, :] (and gbias likewise), replicas cleared; fixed summation order. */
 int hhfm_hot_fold(float* ghot, float* ghot_bias, int32_t n_rep, int32_t n_hot, int64_t K, const int32_t* hot_rows,
                   float* gV, float* gbias, hhfm_stream_t stream);

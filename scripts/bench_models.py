@@ -155,6 +155,47 @@ def run_hhfm_c5(args, dev):
                          "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)"}}
 
 
+def run_fm_c5_l2(args, dev):
+    """c5 scaled FM with the reference's regulariser (lamda = 0.1, FM.py:40,124): the dense L2 term moves all 10^7 rows every
+    step in the reference; here it runs lazily (rows replay their missed `g = lamda*w` steps when they are next gathered,
+    bit-identical to the dense update -- tests/test_gpu_fused_step.py).  Two roofline views: the bytes the lazy algorithm
+    has to move, and the bytes of the reference's dense update it replaces (+ 20*M*K B per step)."""
+    import torch
+    from hhfm_b200.models import FM
+    rng = np.random.default_rng(5)
+    B, K = 1 << 20, 128
+    n_user, n_item, n_ctx_ids = 4_000_000, 1_000_000, 5_000_000
+    M = n_user + n_item + n_ctx_ids
+    per_ctx = n_ctx_ids // 8
+    batches = []
+    for _ in range(3):
+        cols = [zipf_ids(rng, n_user, B), n_user + zipf_ids(rng, n_item, B)]
+        base = n_user + n_item
+        for c in range(8):
+            cols.append(base + rng.integers(0, per_ctx, B))
+            base += per_ctx
+        X = np.stack(cols, 1).astype(np.int32)
+        batches.append((torch.from_numpy(X).to(dev), torch.from_numpy(rng.choice([1.0, 0.0], B).astype(np.float32)).to(dev)))
+    m = FM(10, M, n_user, n_item, K, 0.1, 0.1, 1, "AdagradOptimizer", 0, 0)
+    assert m._lazy()
+    ms = timed(lambda i: m.fit_device(*batches[i % 3]), args.steps, 3)
+    uniq = int(m._touch.count.item())
+    F = 10
+    kern = (4 * F + 4 * F * K + 4 * F + 4 + 4) + (4 * F * K + 4 * F)
+    lazy = kern + (16 * K + 20 * K + 20) * uniq / B          # replay r/w (w, acc) + step r g, r/w w, r/w acc, w g=0 (+ bias)
+    dense = kern + 20.0 * M * (K + 1) / B                     # what the reference's dense Adagrad moves per step
+    t0 = __import__("time").perf_counter()
+    m.flush(); torch.cuda.synchronize()
+    flush_ms = (__import__("time").perf_counter() - t0) * 1e3
+    return {"config": "c5 scaled FM with lamda = 0.1 (lazy-exact dense L2), B=2^20, %d gathered rows/step" % uniq,
+            "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "flush_ms": flush_ms,
+            "algorithmic_bytes_per_sample": lazy, "reference_dense_bytes_per_sample": dense,
+            "roofline": {"bound": "hbm", "achieved_gbs": B * lazy / ms / 1e6, "peak_gbs": peaks(), "frac": B * lazy / ms / 1e6 / peaks(),
+                         "frac_vs_reference_dense_update": B * dense / ms / 1e6 / peaks(),
+                         "note": "frac counts the bytes of the lazy algorithm; the reference's dense update of all 10^7 rows would "
+                                 "need %.1f ms per step at the HBM peak on its own" % (20.0 * M * (K + 1) / peaks() / 1e6)}}
+
+
 def run_bpr_c4(args, dev):
     import torch
     from hhfm_b200.models import BPR
@@ -222,7 +263,7 @@ def run_dfm(args, dev):
                                  "peak / 2 / 3 = 271 TFLOP/s fp32-equivalent) see profiles/r1_dfm_summary.md"}}
 
 
-RUNNERS = {"hhfm_c5": run_hhfm_c5, "fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
+RUNNERS = {"hhfm_c5": run_hhfm_c5, "fm_c1": run_fm_c1, "fm_c5": run_fm_c5, "fm_c5_l2": run_fm_c5_l2, "bpr_c4": run_bpr_c4, "afm_c3": run_afm_c3, "dfm": run_dfm}
 
 
 def main():

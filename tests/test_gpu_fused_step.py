@@ -178,3 +178,47 @@ def test_fused_tail_folds_bias_replicas(cuda):
     assert_update_close(got["feature_embeddings"], V1, w0["feature_embeddings"], dV, np.full_like(V1, 0.1), 0.1, what="V")
     assert_update_close(got["feature_bias"], b1, w0["feature_bias"], np.asarray(db).reshape(-1, 1), np.full_like(b1, 0.1), 0.1, what="bias")
     assert float(m._hot.ghot.abs().max()) == 0.0 and float(m._hot.ghot_bias.abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------------
+# lazy-exact dense L2 (hard part 2-ii): untouched rows replay their `g = lamda * w` steps when they are next
+# gathered / at flush -- bit-identical to the dense update of every row every step
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["OUR", "FM", "BPR"])
+def test_lazy_l2_replay_is_bit_identical_to_the_dense_update(cuda, which):
+    from hhfm_b200.models import BPR, FM, OUR
+    rng = np.random.default_rng(17)
+    n_user, n_item, M, K, fc, B, steps = 300, 900, 1400, 64, 4, 96, 50
+    res = {}
+    for lazy in (True, False):
+        if which == "OUR":
+            m = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, 'AdagradOptimizer', True, False)
+        elif which == "BPR":
+            m = BPR(M, n_user, n_item, K, 0.05, 0.1, 'AdagradOptimizer')
+        else:
+            m = FM(2 + fc, M, n_user, n_item, K, 0.1, 0.1, 1, 'AdagradOptimizer', 0, 0)
+        m.lazy_l2 = lazy
+        m.deterministic = True             # program-order scatter: the data gradient is bit-reproducible
+        assert m._lazy() == lazy
+        r2 = np.random.default_rng(5)
+        mid = None
+        for step in range(steps):
+            X = np.stack([r2.integers(0, n_user, B), n_user + r2.integers(0, n_item, B)], axis=1)
+            F1 = r2.integers(n_user + n_item, M - 50, (B, fc))          # the last 50 rows are never gathered
+            if which == "FM":
+                m.partial_fit({"X": np.concatenate([X, F1], axis=1), "Y": r2.choice([1.0, 0.0], (B, 1)).astype(np.float32)})
+            elif which == "BPR":
+                m.partial_fit({"X": X, "Y": n_user + r2.integers(0, n_item, (B, 10))})
+            else:
+                m.partial_fit({"X": X, "F1": F1, "Y": n_user + r2.integers(0, n_item, (B, 10))})
+            if step == 20:                  # a read in the middle of training flushes: the lists must agree as well
+                A = np.concatenate([X[:32], F1[:32]], axis=1) if which != "BPR" else X[:32]
+                mid = m.topk(A, 20)
+        w = m.get_weights()["feature_embeddings"]                        # flushes
+        acc = m._opt.state["feature_embeddings"][0].cpu().numpy()
+        res[lazy] = (w, acc, mid)
+    assert np.array_equal(res[True][0], res[False][0]), "weights differ between the lazy replay and the dense update"
+    assert np.array_equal(res[True][1], res[False][1]), "Adagrad accumulators differ"
+    assert np.array_equal(res[True][2], res[False][2]), "top-N lists after the mid-training flush differ"
+    w0 = np.asarray(res[True][0])
+    assert not np.array_equal(w0[-50:], np.zeros_like(w0[-50:]))
