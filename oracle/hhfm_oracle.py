@@ -21,6 +21,11 @@ PARITY STATUS
       update with zero rows; reduce_max splits its gradient equally among ties; top_k sorts descending with
       the lower index first among equals; softmax subtracts the row max.
     Analytic gradients here are cross-checked against torch.autograd (tests/test_oracle.py).
+    What the reference DOES hold for this arithmetic is statistical: its shipped datasets and the HR / NDCG / AUC lines
+    of its run log (result.txt).  The CUDA path that this oracle checks is run on those datasets with the reference
+    defaults and must land inside bands derived from that log (scripts/reference_bands.py,
+    tests/test_gpu_reference_bands.py: HHFM frappe HR@5 0.67-0.69 against the reference's 0.674-0.698) -- a pin of the
+    training outcome, not of single operations.
 
 All arithmetic is float32 (np.float32 arrays; each NumPy ufunc rounds to fp32 like a non-fused GPU op).
 Canonical score order for the top-N evaluators: products and sums are taken for k = 0..K-1 in ascending
