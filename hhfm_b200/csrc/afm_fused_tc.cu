@@ -6,13 +6,14 @@
 // the MMA phases, so the [pairs, K] tensors never leave shared memory / TMEM.
 //
 // Tile = 2 samples = 128 operand rows: sample slot ss owns rows [64 ss, 64 ss + P), the rows P..63 of a slot are zero.
-// Thread = (row r, column half): warp & 3 is the TMEM lane quarter (rows), warp >> 2 the 32-column half.
-//   P rows      the thread builds its half row of pair products in registers and writes it (x and lo(x)) with tcgen05.st
+// Thread = (row r, column group): warp & 3 is the TMEM lane quarter (rows), warp >> 2 the group of 16 columns (16 warps).
+//   P rows      the thread builds its 16 pair products in registers and writes them (x and lo(x)) with tcgen05.st
 //               into TMEM -- the A operand of GEMM 1 -- and, transposed, into the K-major tiles PT[k][r] (A operand of GEMM 3)
 //   GEMM 1      Z[128, 64]   = P . W          A = P from TMEM,   B = W^T tiles (K-major smem)   -> TMEM columns [0, 64)
-//   epilogue 1  Z row from TMEM, relu, logits, softmax over the slot's pairs (warp reductions), afm, out, loss, d a, d s,
-//               dZ = ds * p * relu' -> TMEM (A operand of GEMM 2) and, transposed, the K-major tiles dZT[a][r]; column sums
-//               over the tile rows -> d p, d b
+//   epilogue 1  Z row from TMEM, relu, logits; every warp then works out the softmax of its sample slot by itself (lane l
+//               looks at pairs l and l + 32, warp shuffles only): with u_p = prediction_W . P_p the output is sum_p a_p u_p,
+//               d a_p = g u_p and ds_p = g a_p (u_p - sum_q a_q u_q) -- no afm vector, no CTA-wide reductions.
+//               dZ = ds * p * relu' -> TMEM (A operand of GEMM 2) and, transposed, the K-major tiles dZT[a][r]
 //   GEMM 2      dP[128, 64]  = dZ . W^T       A = dZ from TMEM,  B = W tiles (K-major smem)     -> TMEM columns [64, 128)
 //   GEMM 3      D[128, 64]  += [PT ; PT_lo] . (dZT + dZT_lo)^T   K-major operands, reduction over the 128 tile rows; rows
 //               0..63 of D hold P^T dZ, rows 64..127 hold P_lo^T dZ                              -> TMEM columns [128, 192)
@@ -22,7 +23,10 @@
 // transposed operands of dW are separate tiles written by the same threads -- lane = row makes those stores contiguous.)
 // dW is read back from TMEM after every tile and added into registers (two-level accumulation: the tensor core adds into
 // its accumulator with truncation, see dfm_tc.cu); the threads add their registers into the global gradient once at the end.
-// The embedding rows of tile t+1 are fetched with cp.async into a second staging buffer while tile t is processed.
+// The column sums over the tile rows (d attention_b, d attention_p, d prediction_W) are deferred: one butterfly step per
+// tile into 8 registers, issued behind GEMM 2 / 3, finished once at the end of the kernel.
+// The embedding rows (+ bias values, hot-row slots) of tile t+1 are fetched with cp.async into a second staging buffer
+// behind GEMM 1 of tile t; ids and labels are loaded two / one tile ahead.  Five CTA-wide barriers per tile.
 //
 // Shapes covered: K == A == 64, F <= 11 (P <= 55 pairs).  Everything else stays on the fp32 SIMT kernels (afm.cu).
 #include <stdlib.h>
@@ -38,7 +42,6 @@ namespace aft {
 constexpr int KD = 64;                 // K == A
 constexpr int kRows = 128;             // operand rows per tile (2 sample slots x 64)
 constexpr int kSlot = 64;              // rows per sample slot
-constexpr int kThreads = 256;          // 8 warps: warp & 3 = TMEM lane quarter (rows), warp >> 2 = column half
 constexpr int kMaxF = 11;
 constexpr int kEP = KD + 4;            // padded row of the staged embeddings (floats)
 constexpr uint32_t kTile = kRows * 128;          // bytes of one [128 rows][32 fp32] operand tile
@@ -55,28 +58,24 @@ constexpr uint32_t oWn = oWt + 4 * kWTile;              // W tiles (rows = k, co
 constexpr uint32_t kEBytes = 2 * kMaxF * kEP * 4;       // staged embedding rows of one tile: float E[2][kMaxF][kEP]
 constexpr uint32_t oE = oWn + 4 * kWTile;               // two tiles (the rows of tile t+1 land while tile t is processed)
 constexpr uint32_t oMisc = oE + 2 * kEBytes;
-constexpr uint32_t kSmemBytes = oMisc + 8192 + 1024;    // + alignment slack
+constexpr uint32_t kMiscBytes = 8192;
+constexpr uint32_t kSmemBytes = oMisc + kMiscBytes + 1024;    // + alignment slack
 
 struct Misc {
   float batt[KD], pvec[KD], wpred[KD];
-  float gbatt[KD], gp[KD];
-  float s_part[2][kRows];      // logits by column half
-  float att[kRows];            // softmax weights a_p
-  float da_part[2][kRows];
-  float ds[kRows];
-  float afm[2][KD], dafm[2][KD];
-  float red[2][4];             // per-slot partial sums of out
-  float wred[8];               // per-warp partial of a slot-wide reduction (max, sum)
-  float afm_part[8][32];       // per-warp column sums of a_p * P_p
+  float gbatt[KD], gp[KD], gwp[KD];
+  float s_part[4][kRows];      // logits by column group
+  float u_part[4][kRows];      // prediction_W . P_p by column group
   float g[2], bsum[2];
   float biasv[2][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
+  int hslot[2][2][kMaxF + 1];     // [buffer][slot][field] hot-row slot of the staged rows (-1: none)
   int ids[2][2][kMaxF + 1];       // [buffer][slot][field]
   unsigned char pi[kSlot], pj[kSlot];
   unsigned char pidx[kMaxF][kMaxF + 1];
   uint64_t bar;
   uint32_t tmem;
 };
-static_assert(sizeof(Misc) <= 8192, "Misc does not fit its shared-memory slot");
+static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
@@ -84,7 +83,7 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)r * 128
 // byte offset of fp32 element e (0..31) of row r inside a 128-byte-swizzled tile
 __device__ __forceinline__ uint32_t swz_e(int r, int e) { return swz(r, e >> 2) + (uint32_t)(e & 3) * 4u; }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -95,7 +94,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); tmem_ld_wait_for(r); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); tmem_ld_wait_for16(r); }
 
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand is [M lanes][K columns] of fp32 words in tensor memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -109,22 +118,59 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
 
-// lane l ends with the sum over the warp's lanes of v[l] (reduce-scatter butterfly, 31 shuffles)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+// Column sums over the rows of the tile are deferred: every tile adds a partially reduced copy of the thread's CW values
+// into 8 registers (reduce-scatter butterfly over lane bits 16 [, 8]); finish8() completes the butterfly once, at the end
+// of the kernel.  acc[i] of lane l belongs to column  (CW == 16 ? 8 * bit4(l) : 16 * bit4(l) + 8 * bit3(l)) + i.
+template <int CW>
+__device__ __forceinline__ void fold8(const float (&v)[CW], float (&acc)[8], int lane) {
+  const bool up = (lane & 16) != 0;
+  if (CW == 16) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
+    for (int i = 0; i < 8; i++) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      acc[i] += keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  } else {
+    float t[16];
 #pragma unroll
-    for (int i = 0; i < off; i++) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    for (int i = 0; i < 16; i++) {
+      const float send = up ? v[i] : v[i + 16];
+      const float keep = up ? v[i + 16] : v[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const bool up8 = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float send = up8 ? t[i] : t[i + 8];
+      const float keep = up8 ? t[i + 8] : t[i];
+      acc[i] += keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
   }
-  return v[0];
+}
+// -> the warp's column sum; CW == 32: lane l holds column l, CW == 16: lanes 2c and 2c + 1 hold column c
+template <int CW>
+__device__ __forceinline__ float finish8(float (&acc)[8], int lane) {
+  int off = (CW == 16) ? 8 : 4;
+#pragma unroll
+  for (int h = 4; h >= 1; h >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; i++) {
+      const float send = up ? acc[i] : acc[i + h];
+      const float keep = up ? acc[i + h] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (CW == 16) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+  return acc[0];
 }
 
-__global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs a, const int64_t n_tiles) {
+// NQ column groups: thread = (operand row, group of CW = 64 / NQ columns); 128 * NQ threads
+template <int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs a, const int64_t n_tiles) {
+  constexpr int CW = KD / NQ;
+  constexpr int kThreads = 128 * NQ;
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -132,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   float* EsBuf = reinterpret_cast<float*>(smem + oE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = a.F, P = a.P;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, cg = warp >> 2, c0 = cg * CW;
   const int row = quarter * 32 + lane;          // operand row / TMEM lane of this thread
   const int ss = row >> 6, pp = row & 63;       // sample slot, pair index
   const bool prow = pp < P;
@@ -156,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   }
   if (tid < KD) {
     mi.batt[tid] = __ldg(a.batt + tid); mi.pvec[tid] = __ldg(a.pvec + tid); mi.wpred[tid] = __ldg(a.wpred + tid);
-    mi.gbatt[tid] = 0.f; mi.gp[tid] = 0.f;
+    mi.gbatt[tid] = 0.f; mi.gp[tid] = 0.f; mi.gwp[tid] = 0.f;
   }
   if (tid == 0) {
     int p = 0;
@@ -179,19 +225,23 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   const uint32_t sP = smem_u32(smem + oP), sZ = smem_u32(smem + oZ), sWt = smem_u32(smem + oWt), sWn = smem_u32(smem + oWn);
   const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
   const int rep = a.hot.slot ? (int)(blockIdx.x % a.hot.n_rep) : 0;
+  const bool has_hot = a.hot.slot != nullptr;
   uint32_t bar_ph = 0;
-  float loss_acc = 0.f, gb0_acc = 0.f, gwp_acc = 0.f;
-  float dwacc[32];                  // this thread's share of dW: TMEM lane `row` (k = row & 63, x or lo part), its 32 columns
+  float loss_acc = 0.f, gb0_acc = 0.f;
+  float dwacc[CW];                  // this thread's share of dW: TMEM lane `row` (k = row & 63, x or lo part), its CW columns
+  float gb8[8], gp8[8], gw8[8];     // deferred column sums: d attention_b, d attention_p, d prediction_W (fold8)
 #pragma unroll
-  for (int i = 0; i < 32; i++) dwacc[i] = 0.f;
+  for (int i = 0; i < CW; i++) dwacc[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { gb8[i] = 0.f; gp8[i] = 0.f; gw8[i] = 0.f; }
 
-  // ---- staging pipeline: ids two tiles ahead, embedding rows + bias values one tile ahead (cp.async) ----
+  // ---- staging pipeline: ids two tiles ahead, embedding rows + bias values + hot slots one tile ahead (cp.async) ----
   auto load_id = [&](int64_t t) {
     if (tid >= 2 * F || t >= n_tiles) return -1;
     const int64_t s = 2 * t + tid / F;
     return (s < a.B) ? __ldg(a.idx + s * F + tid % F) : -1;
   };
-  auto stage_rows = [&](int buf) {          // rows of the tile whose ids are in mi.ids[buf] -> EsBuf[buf], biasv[buf]
+  auto stage_rows = [&](int buf) {          // rows of the tile whose ids are in mi.ids[buf] -> EsBuf[buf], biasv[buf], hslot[buf]
     float* Es = EsBuf + buf * (kEBytes / 4);
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
@@ -200,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
       if (id >= 0) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(a.V + (size_t)id * KD + 4 * c) : "memory");
         if (c == 0 && a.bias) ldgsts4(&mi.biasv[buf][s2][f], a.bias + id);
+        if (c == 1 && has_hot) ldgsts4(&mi.hslot[buf][s2][f], a.hot.slot + id);
       } else {
         *reinterpret_cast<float4*>(dst) = f4_zero();
         if (c == 0) mi.biasv[buf][s2][f] = 0.f;
@@ -211,66 +262,58 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   {
     const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + gridDim.x);
     if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
-    if (tid < 2 * (kMaxF + 1)) { mi.biasv[0][tid / (kMaxF + 1)][tid % (kMaxF + 1)] = 0.f; mi.biasv[1][tid / (kMaxF + 1)][tid % (kMaxF + 1)] = 0.f; }
+    if (tid < 2 * (kMaxF + 1)) {
+      const int s2 = tid / (kMaxF + 1), f = tid % (kMaxF + 1);
+      mi.biasv[0][s2][f] = 0.f; mi.biasv[1][s2][f] = 0.f;
+      mi.hslot[0][s2][f] = -1; mi.hslot[1][s2][f] = -1;
+    }
     __syncthreads();
     stage_rows(0);
   }
-
-  // slot-wide reduction over the 64 rows of a sample: the two warps that hold them (same column half) are warp and warp ^ 1
-  auto slot_max = [&](float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) mi.wred[warp] = v;
-    __syncthreads();
-    const float r = fmaxf(mi.wred[warp], mi.wred[warp ^ 1]);
-    __syncthreads();
-    return r;
-  };
-  auto slot_sum = [&](float v) {
-    v = warp_sum(v);
-    if (lane == 0) mi.wred[warp] = v;
-    __syncthreads();
-    const float r = mi.wred[warp & ~1] + mi.wred[warp | 1];       // fixed order: both warps get the same bits
-    __syncthreads();
-    return r;
-  };
+  int id_pending = -1;              // id of tile t + grid * 1 ... stored into mi.ids once the buffer's previous tile is done with it
+  bool have_pending = false;
 
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    // ---- phase 0: the staged rows of this tile have landed; start the next tile's rows, fetch the ids after that ----
+    // ---- phase 0: the staged rows of this tile have landed (and the previous tile is done with its buffers) ----
     float* Es = EsBuf + cur * (kEBytes / 4);
     ldgsts_wait<0>();
     __syncthreads();
-    if (t + gridDim.x < n_tiles) stage_rows(cur ^ 1);
-    const int id_next2 = load_id(t + 2 * (int64_t)gridDim.x);       // stored into mi.ids[cur] when this tile is done with it
+    if (have_pending && tid < 2 * F) mi.ids[cur ^ 1][tid / F][tid % F] = id_pending;     // ids of tile t + 1 (stage_rows below)
+    const int id_next2 = load_id(t + 2 * (int64_t)gridDim.x);
+    const int64_t smp = 2 * t + ss;
+    const float label = (smp < a.B) ? __ldg(a.labels + smp) : 0.f;
     if (tid < 2) {
       float bs = 0.f;
       for (int f = 0; f < F; f++) bs += mi.biasv[cur][tid][f];
       mi.bsum[tid] = bs;
     }
 
-    // ---- phase 1: this thread's half row of pair products -> registers, TMEM (A of GEMM 1), PT tiles (A of GEMM 3) ----
-    float pr[32];
+    // ---- phase 1: this thread's CW pair products -> registers, TMEM (A of GEMM 1), PT tiles (A of GEMM 3) ----
+    const float* ei = Es + (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + c0;
+    const float* ej = Es + (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + c0;
     {
-      const float* ei = Es + (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + half * 32;
-      const float* ej = Es + (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + half * 32;
-      uint32_t rx[32], rl[32];
+      float pr[CW];
+      uint32_t rx[CW], rl[CW];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < CW; i += 4) {
         const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
         pr[i] = prow ? x.x * y.x : 0.f; pr[i + 1] = prow ? x.y * y.y : 0.f;
         pr[i + 2] = prow ? x.z * y.z : 0.f; pr[i + 3] = prow ? x.w * y.w : 0.f;
       }
       uint8_t* pt = smem + oP + (uint32_t)quarter * kTile;             // r block = quarter, column of the tile row = lane
+      float up = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
+      for (int i = 0; i < CW; i++) {
         const float lo = tf32_lo(pr[i]);
         rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo);
-        const int k = half * 32 + i;
+        const int k = c0 + i;
         *reinterpret_cast<float*>(pt + swz_e(k, lane)) = pr[i];
         *reinterpret_cast<float*>(pt + swz_e(KD + k, lane)) = lo;
+        up = fmaf(mi.wpred[k], pr[i], up);                              // AFM.py:138-139, per pair
       }
-      tmem_st32(t_lane + cPX + half * 32, rx);
-      tmem_st32(t_lane + cPL + half * 32, rl);
+      mi.u_part[cg][row] = up;
+      tmem_st(t_lane + cPX + c0, rx);
+      tmem_st(t_lane + cPL + c0, rl);
       tmem_st_wait();
     }
     fence_proxy_async();
@@ -291,105 +334,86 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
         }
       umma_commit(&mi.bar);
     }
+    // behind GEMM 1: the next tile's rows (its ids were stored after the barrier at the top of this tile)
+    if (t + gridDim.x < n_tiles) stage_rows(cur ^ 1);
     mbar_wait(&mi.bar, bar_ph, nullptr);
     bar_ph ^= 1;
     tc_fence_after();
 
-    // ---- epilogue 1: logits, softmax, afm, out, loss ----
+    // ---- epilogue 1: logits ----
     {
-      uint32_t r[32];
-      tmem_ld32(t_lane + cZ + half * 32, r);
-      tmem_ld_wait_for(r);
+      uint32_t r[CW];
+      tmem_ld(t_lane + cZ + c0, r);
       float sp = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const float zi = __uint_as_float(r[i]) + mi.batt[half * 32 + i];         // AFM.py:117-123
-        sp = fmaf(fmaxf(zi, 0.f), mi.pvec[half * 32 + i], sp);
+      for (int i = 0; i < CW; i++) {
+        const float zi = __uint_as_float(r[i]) + mi.batt[c0 + i];                // AFM.py:117-123
+        sp = fmaf(fmaxf(zi, 0.f), mi.pvec[c0 + i], sp);
       }
-      mi.s_part[half][row] = sp;
+      mi.s_part[cg][row] = sp;
     }
     __syncthreads();
-    const float s_r = mi.s_part[0][row] + mi.s_part[1][row];
-    const float mx = slot_max(prow ? s_r : -INFINITY);
-    const float e_r = prow ? expf(s_r - mx) : 0.f;                               // AFM.py:125 softmax over the pairs
-    const float den = slot_sum(e_r);
-    const float att = e_r / den;
+    // Every warp works out the softmax of its sample slot by itself: lane l looks at the slot's pairs l and l + 32.
+    float att, c_r, ds;
     {
-      float v[32];
+      const int rlo = ss * kSlot + lane, rhi = rlo + 32;
+      float s_lo = mi.s_part[0][rlo], s_hi = mi.s_part[0][rhi], u_lo = mi.u_part[0][rlo], u_hi = mi.u_part[0][rhi];
 #pragma unroll
-      for (int i = 0; i < 32; i++) v[i] = att * pr[i];                           // AFM.py:130
-      const float cs = warp_colsum32(v, lane);
-      mi.afm_part[warp][lane] = cs;
-    }
-    __syncthreads();
-    if (tid < 2 * KD) {
-      const int s2 = tid >> 6, k = tid & 63;
-      const int w0 = (k >> 5) * 4 + 2 * s2;
-      const float acc = mi.afm_part[w0][k & 31] + mi.afm_part[w0 + 1][k & 31];
-      mi.afm[s2][k] = acc;
-      const float part = warp_sum(acc * mi.wpred[k]);                            // AFM.py:138-139
-      if (lane == 0) mi.red[s2][warp & 1] = part;
-    }
-    __syncthreads();
-    if (tid < 2) {
-      const int64_t s = 2 * t + tid;
+      for (int q = 1; q < NQ; q++) {
+        s_lo += mi.s_part[q][rlo]; s_hi += mi.s_part[q][rhi];
+        u_lo += mi.u_part[q][rlo]; u_hi += mi.u_part[q][rhi];
+      }
+      const bool v_lo = lane < P, v_hi = lane + 32 < P;
+      float mx = fmaxf(v_lo ? s_lo : -INFINITY, v_hi ? s_hi : -INFINITY);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e_lo = v_lo ? expf(s_lo - mx) : 0.f, e_hi = v_hi ? expf(s_hi - mx) : 0.f;   // AFM.py:125 softmax over the pairs
+      float d0 = e_lo, d1 = e_hi, n0 = e_lo * u_lo, n1 = e_hi * u_hi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        n0 += __shfl_xor_sync(0xffffffffu, n0, o); n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+      }
+      const float den = d0 + d1;
+      const float od = (n0 + n1) / den;                       // sum_p a_p (prediction_W . P_p) = prediction_W . afm, AFM.py:130-139
+      att = ((pp < 32) ? e_lo : e_hi) / den;
+      const float u_r = (pp < 32) ? u_lo : u_hi;
       float g = 0.f;
-      if (s < a.B) {
-        const float out = ((mi.red[tid][0] + mi.red[tid][1]) + mi.bsum[tid]) + b0;   // AFM.py:142
-        const float diff = __ldg(a.labels + s) - out;
+      if (smp < a.B) {
+        const float out = (od + mi.bsum[ss]) + b0;            // AFM.py:142
+        const float diff = label - out;
         g = -diff;
-        loss_acc += 0.5f * diff * diff;                                          // AFM.py:146 tf.nn.l2_loss
-        gb0_acc += g;
-        if (a.out) a.out[s] = out;
+        if (pp == 0 && cg == 0) {
+          loss_acc += 0.5f * diff * diff;                     // AFM.py:146 tf.nn.l2_loss
+          gb0_acc += g;
+          if (a.out) a.out[smp] = out;
+        }
       }
-      mi.g[tid] = g;
+      if (pp == 0 && cg == 0) mi.g[ss] = g;
+      c_r = g * att;                                          // d afm . P_p = g * u_p; softmax backward: ds = a (da - sum a da)
+      ds = c_r * (u_r - od);
     }
-    __syncthreads();
-    if (tid < 2 * KD) {
-      const int s2 = tid >> 6, k = tid & 63;
-      const float g = mi.g[s2];
-      mi.dafm[s2][k] = g * mi.wpred[k];
-      gwp_acc = fmaf(g, mi.afm[s2][k], gwp_acc);
-    }
-    __syncthreads();
+    // dZ = ds * p * relu'(Z + b) -> TMEM (A of GEMM 2) and the K-major dZT tiles (B of GEMM 3)
+    float dz[CW], hp[CW];
     {
-      // d a_p = d afm . P_p over this thread's 32 columns
-      const float* df = mi.dafm[ss] + half * 32;
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; i++) acc = fmaf(df[i], pr[i], acc);
-      mi.da_part[half][row] = acc;
-    }
-    __syncthreads();
-    {
-      const float da = mi.da_part[0][row] + mi.da_part[1][row];
-      const float sd = slot_sum(att * da);
-      const float ds = att * (da - sd);                                          // softmax backward
-      // dZ = ds * p * relu'(Z + b); d p += ds * relu(Z + b); d b += dZ (column sums over the tile rows)
-      float dz[32], hp[32];
-      uint32_t rx[32], rl[32];
+      uint32_t rx[CW], rl[CW];
       uint8_t* zt = smem + oZ + (uint32_t)quarter * kWTile;             // dZT x tiles: r block = quarter, column = lane
-      tmem_ld32(t_lane + cZ + half * 32, rx);                           // the logits again (cheaper than 32 live registers)
-      tmem_ld_wait_for(rx);
+      tmem_ld(t_lane + cZ + c0, rx);                                    // the logits again (cheaper than CW live registers)
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const float zi = __uint_as_float(rx[i]) + mi.batt[half * 32 + i];
+      for (int i = 0; i < CW; i++) {
+        const float zi = __uint_as_float(rx[i]) + mi.batt[c0 + i];
         const bool on = zi > 0.f;
-        dz[i] = on ? ds * mi.pvec[half * 32 + i] : 0.f;
-        hp[i] = on ? ds * zi : 0.f;
+        dz[i] = on ? ds * mi.pvec[c0 + i] : 0.f;
+        hp[i] = on ? ds * zi : 0.f;                                     // d p += ds * relu(Z + b)
         const float lo = tf32_lo(dz[i]);
         rx[i] = __float_as_uint(dz[i]); rl[i] = __float_as_uint(lo);
-        const int an = half * 32 + i;
+        const int an = c0 + i;
         *reinterpret_cast<float*>(zt + swz_e(an, lane)) = dz[i];
         *reinterpret_cast<float*>(zt + 4 * kWTile + swz_e(an, lane)) = lo;
       }
-      tmem_st32(t_lane + cZX + half * 32, rx);
-      tmem_st32(t_lane + cZL + half * 32, rl);
+      tmem_st(t_lane + cZX + c0, rx);
+      tmem_st(t_lane + cZL + c0, rl);
       tmem_st_wait();
-      const float cb = warp_colsum32(dz, lane);
-      const float cp = warp_colsum32(hp, lane);
-      atomicAdd(&mi.gbatt[half * 32 + lane], cb);
-      atomicAdd(&mi.gp[half * 32 + lane], cp);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -419,27 +443,37 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
         }
       umma_commit(&mi.bar);
     }
+    // behind GEMM 2 / 3: the column sums over the tile rows (d b = sum dZ, d p, d prediction_W = sum g a_p P_p), deferred
+    fold8<CW>(dz, gb8, lane);
+    fold8<CW>(hp, gp8, lane);
+    {
+      const float cm = prow ? c_r : 0.f;                     // the pair products again from the staged rows (fewer live registers)
+#pragma unroll
+      for (int i = 0; i < CW; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
+        dz[i] = cm * (x.x * y.x); dz[i + 1] = cm * (x.y * y.y); dz[i + 2] = cm * (x.z * y.z); dz[i + 3] = cm * (x.w * y.w);
+      }
+    }
+    fold8<CW>(dz, gw8, lane);
     mbar_wait(&mi.bar, bar_ph, nullptr);
     bar_ph ^= 1;
     tc_fence_after();
 
-    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm) -> shared memory (the dZT tiles are free now) ----
+    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm = g a_p prediction_W) -> shared memory (the dZT tiles are free now) ----
     {
-      uint32_t r[32];
-      tmem_ld32(t_lane + cDP + half * 32, r);
-      tmem_ld_wait_for(r);
-      const float* df = mi.dafm[ss] + half * 32;
+      uint32_t r[CW];
+      tmem_ld(t_lane + cDP + c0, r);
       float* dst = reinterpret_cast<float*>(smem + oZ) + row * KD;
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const float4 v = make_float4(fmaf(att, df[4 * c], __uint_as_float(r[4 * c])), fmaf(att, df[4 * c + 1], __uint_as_float(r[4 * c + 1])),
-                                     fmaf(att, df[4 * c + 2], __uint_as_float(r[4 * c + 2])), fmaf(att, df[4 * c + 3], __uint_as_float(r[4 * c + 3])));
-        *reinterpret_cast<float4*>(dst + 4 * ((half * 8 + c) ^ (row & 15))) = v;
+      for (int c = 0; c < CW / 4; c++) {
+        const float* wp = mi.wpred + c0 + 4 * c;
+        const float4 v = make_float4(fmaf(c_r, wp[0], __uint_as_float(r[4 * c])), fmaf(c_r, wp[1], __uint_as_float(r[4 * c + 1])),
+                                     fmaf(c_r, wp[2], __uint_as_float(r[4 * c + 2])), fmaf(c_r, wp[3], __uint_as_float(r[4 * c + 3])));
+        *reinterpret_cast<float4*>(dst + 4 * ((cg * (CW / 4) + c) ^ (row & 15))) = v;
       }
-      tmem_ld32(t_lane + cDW + half * 32, r);                 // this tile's dW partial sum -> registers (two-level accumulation)
-      tmem_ld_wait_for(r);
+      tmem_ld(t_lane + cDW + c0, r);                          // this tile's dW partial sum -> registers (two-level accumulation)
 #pragma unroll
-      for (int i = 0; i < 32; i++) dwacc[i] += __uint_as_float(r[i]);
+      for (int i = 0; i < CW; i++) dwacc[i] += __uint_as_float(r[i]);
     }
     tc_fence_before();
     __syncthreads();
@@ -457,11 +491,8 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
         acc.x = fmaf(dp.x, e.x, acc.x); acc.y = fmaf(dp.y, e.y, acc.y); acc.z = fmaf(dp.z, e.z, acc.z); acc.w = fmaf(dp.w, e.w, acc.w);
       }
       float* dst = a.gV + (size_t)id * KD;
-      int hs = -1;
-      if (a.hot.slot != nullptr) {
-        hs = __ldg(a.hot.slot + id);
-        if (hs >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + hs) * KD;
-      }
+      const int hs = has_hot ? mi.hslot[cur][s2][f] : -1;
+      if (hs >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + hs) * KD;
       red_add_v4(dst + 4 * c, acc);
       if (c == 0) {
         if (a.gbias) {
@@ -471,8 +502,8 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
         if (a.touch_stamp) a.touch_stamp[id] = a.stamp;      // compacted into the touched-row list afterwards
       }
     }
-    __syncthreads();        // Es / ids / the dP rows are free for the next tile (every thread rewrites its PT / dZT column)
-    if (tid < 2 * F) mi.ids[cur][tid / F][tid % F] = id_next2;
+    // no barrier here: the one at the top of the next tile separates these reads from every later write
+    id_pending = id_next2; have_pending = true;              // -> mi.ids[cur] after that barrier
     cur ^= 1;
   }
 
@@ -481,16 +512,24 @@ __global__ void __launch_bounds__(kThreads, 1) afm_fused_tc_kernel(const AfmArgs
   __syncthreads();
   // ---- flush the accumulators: dW[k][a] = D[k][a] + D[64 + k][a] (x and lo rows land on the same element) ----
   {
-    float* dst = a.gW + (size_t)(row & 63) * KD + half * 32;
+    float* dst = a.gW + (size_t)(row & 63) * KD + c0;
 #pragma unroll
-    for (int i = 0; i < 32; i++)
+    for (int i = 0; i < CW; i++)
       if (dwacc[i] != 0.f) atomicAdd(dst + i, dwacc[i]);
   }
+  {
+    const float cb = finish8<CW>(gb8, lane), cp = finish8<CW>(gp8, lane), cw = finish8<CW>(gw8, lane);
+    const int col = c0 + ((CW == 16) ? (lane >> 1) : lane);
+    if (CW == 32 || (lane & 1) == 0) {
+      atomicAdd(&mi.gbatt[col], cb); atomicAdd(&mi.gp[col], cp); atomicAdd(&mi.gwp[col], cw);
+    }
+  }
+  __syncthreads();
   if (tid < KD) {
     atomicAdd(a.gbatt + tid, mi.gbatt[tid]);
     atomicAdd(a.gp + tid, mi.gp[tid]);
+    atomicAdd(a.gwpred + tid, mi.gwp[tid]);
   }
-  if (tid < 2 * KD) atomicAdd(a.gwpred + (tid & 63), gwp_acc);
   {
     const float bl = block_sum(loss_acc, scratch);
     write_partial(a.loss_partials, bl);
@@ -509,17 +548,20 @@ int dispatch_afm_fused_tc(const AfmArgs& a, int64_t M, cudaStream_t st) {
   if (env && env[0] == '0') return 1;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(aft::afm_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aft::kSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(aft::afm_fused_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aft::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(aft::afm_fused_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aft::kSmemBytes) != cudaSuccess) {
       cudaGetLastError();
       return 1;
     }
     configured = true;
   }
+  const int groups = (env && env[0] == '2') ? 2 : 4;      // column groups per row: 4 = 16 warps (default), HHFM_AFM_TC=2: 8 warps
   const int64_t n_tiles = (a.B + 1) / 2;
   int grid = sm_count();
   if (grid > kPartials) grid = kPartials;
   if ((int64_t)grid > n_tiles) grid = (int)n_tiles;
-  aft::afm_fused_tc_kernel<<<grid, aft::kThreads, aft::kSmemBytes, st>>>(a, n_tiles);
+  if (groups == 4) aft::afm_fused_tc_kernel<4><<<grid, 512, aft::kSmemBytes, st>>>(a, n_tiles);
+  else aft::afm_fused_tc_kernel<2><<<grid, 256, aft::kSmemBytes, st>>>(a, n_tiles);
   int rc = check_launch("afm_fused_tc_kernel");
   if (rc != HHFM_OK) return rc;
   if (a.touch_stamp != nullptr) rc = launch_touched_compact(a.touch_stamp, a.stamp, M, a.touched_rows, a.touched_count, st);

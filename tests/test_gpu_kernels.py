@@ -1009,11 +1009,16 @@ def test_tf32x3_gemm_is_fp32_accurate(cuda, M, N, K):
 
 @pytest.mark.parametrize("B,F", [(64, 10), (5001, 10), (1, 10), (2, 10), (333, 11), (130, 6), (77, 3), (33, 2), (1000, 7)])
 @pytest.mark.parametrize("extras", [False, True])
-def test_afm_fused_tensor_core_pass_matches_oracle(cuda, B, F, extras, monkeypatch):
+@pytest.mark.parametrize("groups", [4, 2])
+def test_afm_fused_tensor_core_pass_matches_oracle(cuda, B, F, extras, groups, monkeypatch):
     """K2 as ONE tcgen05 kernel (afm_fused_tc.cu, K = A = 64, F <= 11): P W, dZ W^T and P^T dZ as 3xTF32 products with the
     operands built in shared memory; selected by hhfm_afm_fwd_bwd_sqloss from the shape.  `extras`: hot-row replicas and
-    touched-row tracking.  Odd B exercises the half-empty last tile."""
-    monkeypatch.delenv("HHFM_AFM_TC", raising=False)
+    touched-row tracking.  Odd B exercises the half-empty last tile.  `groups`: 16 columns per thread / 16 warps (the default)
+    or 32 columns per thread / 8 warps (HHFM_AFM_TC=2)."""
+    if groups == 4:
+        monkeypatch.delenv("HHFM_AFM_TC", raising=False)
+    else:
+        monkeypatch.setenv("HHFM_AFM_TC", "2")
     lib, ptr, st = _lib_ptr()
     from hhfm_b200.engine import HotRows
     rng = np.random.default_rng(B + F + 64 + 1)
