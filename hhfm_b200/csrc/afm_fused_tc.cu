@@ -56,8 +56,8 @@ constexpr uint32_t oZ = oP + 4 * kTile;                 // dZT tiles: x [64 a ro
 constexpr uint32_t oWt = oZ + 4 * kTile;                // W^T tiles (rows = a, contiguous k): [x kb0][x kb1][lo kb0][lo kb1]
 constexpr uint32_t oWn = oWt + 4 * kWTile;              // W tiles (rows = k, contiguous a)
 constexpr uint32_t kEBytes = 2 * kMaxF * kEP * 4;       // staged embedding rows of one tile: float E[2][kMaxF][kEP]
-constexpr uint32_t oE = oWn + 4 * kWTile;               // two tiles (the rows of tile t+1 land while tile t is processed)
-constexpr uint32_t oMisc = oE + 2 * kEBytes;
+constexpr uint32_t oE = oWn + 4 * kWTile;               // three tiles in flight: scattered, processed, landing
+constexpr uint32_t oMisc = oE + 3 * kEBytes;
 constexpr uint32_t kMiscBytes = 8192;
 constexpr uint32_t kSmemBytes = oMisc + kMiscBytes + 1024;    // + alignment slack
 
@@ -67,12 +67,12 @@ struct Misc {
   float s_part[4][kRows];      // logits by column group
   float u_part[4][kRows];      // prediction_W . P_p by column group
   float g[2], bsum[2];
-  float biasv[2][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
-  int hslot[2][2][kMaxF + 1];     // [buffer][slot][field] hot-row slot of the staged rows (-1: none)
-  int ids[2][2][kMaxF + 1];       // [buffer][slot][field]
+  float biasv[3][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
+  int hslot[3][2][kMaxF + 1];     // [buffer][slot][field] hot-row slot of the staged rows (-1: none)
+  int ids[3][2][kMaxF + 1];       // [buffer][slot][field]
   unsigned char pi[kSlot], pj[kSlot];
   unsigned char pidx[kMaxF][kMaxF + 1];
-  uint64_t bar;
+  uint64_t bar1, bar2;          // GEMM 1 | GEMM 2 + 3 complete
   uint32_t tmem;
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
@@ -115,6 +115,10 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+
+// The part of x that tf32 truncation drops, itself left unrounded: the tensor core truncates it again (error 2^-21 |x|, below
+// the lo * lo term that a 3xTF32 product leaves out anyway).
+__device__ __forceinline__ float lo_part(float x) { return x - tf32_hi(x); }
 
 __device__ __forceinline__ float4 lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
 
@@ -212,7 +216,8 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
         mi.pidx[i][j] = (unsigned char)p; mi.pidx[j][i] = (unsigned char)p;
         p++;
       }
-    mbar_init(&mi.bar, 1);
+    mbar_init(&mi.bar1, 1);
+    mbar_init(&mi.bar2, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&mi.tmem, kTmemCols);
@@ -226,7 +231,6 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
   const float b0 = a.b0 ? __ldg(a.b0) : 0.f;
   const int rep = a.hot.slot ? (int)(blockIdx.x % a.hot.n_rep) : 0;
   const bool has_hot = a.hot.slot != nullptr;
-  uint32_t bar_ph = 0;
   float loss_acc = 0.f, gb0_acc = 0.f;
   float dwacc[CW];                  // this thread's share of dW: TMEM lane `row` (k = row & 63, x or lo part), its CW columns
   float gb8[8], gp8[8], gw8[8];     // deferred column sums: d attention_b, d attention_p, d prediction_W (fold8)
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
 #pragma unroll
   for (int i = 0; i < 8; i++) { gb8[i] = 0.f; gp8[i] = 0.f; gw8[i] = 0.f; }
 
-  // ---- staging pipeline: ids two tiles ahead, embedding rows + bias values + hot slots one tile ahead (cp.async) ----
+  // ---- staging pipeline (three buffers): ids three tiles ahead, embedding rows + bias values + hot slots two tiles ahead ----
   auto load_id = [&](int64_t t) {
     if (tid >= 2 * F || t >= n_tiles) return -1;
     const int64_t s = 2 * t + tid / F;
@@ -258,86 +262,99 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
     ldgsts_commit();
   };
-  int cur = 0;
+  // this thread's CW pair products of the tile staged in Es (zero for the padding rows of a slot)
+  const int off_i = (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + c0, off_j = (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + c0;
+  auto pair_products = [&](const float* Es, float (&pr)[CW], float scale) {
+    const float* ei = Es + off_i;
+    const float* ej = Es + off_j;
+    const float m = prow ? scale : 0.f;
+#pragma unroll
+    for (int i = 0; i < CW; i += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
+      pr[i] = m * (x.x * y.x); pr[i + 1] = m * (x.y * y.y); pr[i + 2] = m * (x.z * y.z); pr[i + 3] = m * (x.w * y.w);
+    }
+  };
+  // P rows of a tile -> TMEM (x and lo): the A operand of GEMM 1
+  auto build_p_tmem = [&](const float* Es) {
+    float pr[CW];
+    uint32_t rx[CW], rl[CW];
+    pair_products(Es, pr, 1.f);
+#pragma unroll
+    for (int i = 0; i < CW; i++) { rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo_part(pr[i])); }
+    tmem_st(t_lane + cPX + c0, rx);
+    tmem_st(t_lane + cPL + c0, rl);
+    tmem_st_wait();
+  };
+  auto issue_gemm1 = [&]() {                // Z = P . W (3xTF32): A = P from TMEM, B = W^T tiles
+    const uint32_t idesc = make_idesc_tf32(kRows, KD);
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++) {
+        const uint32_t o = k4 * 32, kc = kb * 32 + k4 * 8;          // byte offset inside the B tile row / A column offset
+        const uint32_t bx = sWt + kb * kWTile + o, bl = sWt + (2 + kb) * kWTile + o;
+        umma_tf32_ts(tmem + cZ, tmem + cPL + kc, make_sdesc(bx), idesc, (kb | k4) ? 1u : 0u);
+        umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bl), idesc, 1u);
+        umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bx), idesc, 1u);
+      }
+    umma_commit(&mi.bar1);
+  };
+  const int64_t g_tiles = gridDim.x;
+  int buf = 0;
   {
-    const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + gridDim.x);
+    const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + g_tiles);
     if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
     if (tid < 2 * (kMaxF + 1)) {
       const int s2 = tid / (kMaxF + 1), f = tid % (kMaxF + 1);
-      mi.biasv[0][s2][f] = 0.f; mi.biasv[1][s2][f] = 0.f;
-      mi.hslot[0][s2][f] = -1; mi.hslot[1][s2][f] = -1;
+#pragma unroll
+      for (int q = 0; q < 3; q++) { mi.biasv[q][s2][f] = 0.f; mi.hslot[q][s2][f] = -1; }
     }
     __syncthreads();
     stage_rows(0);
-  }
-  int id_pending = -1;              // id of tile t + grid * 1 ... stored into mi.ids once the buffer's previous tile is done with it
-  bool have_pending = false;
-
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    // ---- phase 0: the staged rows of this tile have landed (and the previous tile is done with its buffers) ----
-    float* Es = EsBuf + cur * (kEBytes / 4);
-    ldgsts_wait<0>();
+    stage_rows(1);
+    ldgsts_wait<1>();                       // the first tile's rows
     __syncthreads();
-    if (have_pending && tid < 2 * F) mi.ids[cur ^ 1][tid / F][tid % F] = id_pending;     // ids of tile t + 1 (stage_rows below)
-    const int id_next2 = load_id(t + 2 * (int64_t)gridDim.x);
+    build_p_tmem(EsBuf);
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) { tc_fence_after(); issue_gemm1(); }
+  }
+  int id_reg = load_id((int64_t)blockIdx.x + 2 * g_tiles);      // ids of the tile after next, stored at the top of the next tile
+  uint32_t ph1 = 0, ph2 = 0;
+
+  // Software pipeline: GEMM 1 of tile t+1 is issued before the embedding scatter of tile t and completes behind it; its
+  // operand (the P rows of tile t+1 in TMEM) is built behind GEMM 2 / 3 of tile t.
+  for (int64_t t = blockIdx.x; t < n_tiles; t += g_tiles) {
+    const int nb = (buf == 2) ? 0 : buf + 1, nnb = (nb == 2) ? 0 : nb + 1;
+    const float* Es = EsBuf + buf * (kEBytes / 4);
+    const bool has_next = t + g_tiles < n_tiles;
+    __syncthreads();            // T: the previous tile's scatter is done with its rows, ids and dP rows
+    if (tid < 2 * F) mi.ids[nnb][tid / F][tid % F] = id_reg;
+    id_reg = load_id(t + 3 * g_tiles);
     const int64_t smp = 2 * t + ss;
     const float label = (smp < a.B) ? __ldg(a.labels + smp) : 0.f;
     if (tid < 2) {
       float bs = 0.f;
-      for (int f = 0; f < F; f++) bs += mi.biasv[cur][tid][f];
+      for (int f = 0; f < F; f++) bs += mi.biasv[buf][tid][f];
       mi.bsum[tid] = bs;
     }
-
-    // ---- phase 1: this thread's CW pair products -> registers, TMEM (A of GEMM 1), PT tiles (A of GEMM 3) ----
-    const float* ei = Es + (ss * kMaxF + mi.pi[prow ? pp : 0]) * kEP + c0;
-    const float* ej = Es + (ss * kMaxF + mi.pj[prow ? pp : 0]) * kEP + c0;
+    // ---- phase 1: the K-major PT tiles (A of GEMM 3; GEMM 3 of the previous tile is complete) and u_p = prediction_W . P_p ----
     {
       float pr[CW];
-      uint32_t rx[CW], rl[CW];
-#pragma unroll
-      for (int i = 0; i < CW; i += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
-        pr[i] = prow ? x.x * y.x : 0.f; pr[i + 1] = prow ? x.y * y.y : 0.f;
-        pr[i + 2] = prow ? x.z * y.z : 0.f; pr[i + 3] = prow ? x.w * y.w : 0.f;
-      }
+      pair_products(Es, pr, 1.f);
       uint8_t* pt = smem + oP + (uint32_t)quarter * kTile;             // r block = quarter, column of the tile row = lane
       float up = 0.f;
 #pragma unroll
       for (int i = 0; i < CW; i++) {
-        const float lo = tf32_lo(pr[i]);
-        rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo);
         const int k = c0 + i;
         *reinterpret_cast<float*>(pt + swz_e(k, lane)) = pr[i];
-        *reinterpret_cast<float*>(pt + swz_e(KD + k, lane)) = lo;
+        *reinterpret_cast<float*>(pt + swz_e(KD + k, lane)) = lo_part(pr[i]);
         up = fmaf(mi.wpred[k], pr[i], up);                              // AFM.py:138-139, per pair
       }
       mi.u_part[cg][row] = up;
-      tmem_st(t_lane + cPX + c0, rx);
-      tmem_st(t_lane + cPL + c0, rl);
-      tmem_st_wait();
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_tf32(kRows, KD);
-#pragma unroll
-      for (int kb = 0; kb < 2; kb++)
-#pragma unroll
-        for (int k4 = 0; k4 < 4; k4++) {
-          const uint32_t o = k4 * 32, kc = kb * 32 + k4 * 8;          // byte offset inside the B tile row / A column offset
-          const uint32_t bx = sWt + kb * kWTile + o, bl = sWt + (2 + kb) * kWTile + o;
-          umma_tf32_ts(tmem + cZ, tmem + cPL + kc, make_sdesc(bx), idesc, (kb | k4) ? 1u : 0u);
-          umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bl), idesc, 1u);
-          umma_tf32_ts(tmem + cZ, tmem + cPX + kc, make_sdesc(bx), idesc, 1u);
-        }
-      umma_commit(&mi.bar);
-    }
-    // behind GEMM 1: the next tile's rows (its ids were stored after the barrier at the top of this tile)
-    if (t + gridDim.x < n_tiles) stage_rows(cur ^ 1);
-    mbar_wait(&mi.bar, bar_ph, nullptr);
-    bar_ph ^= 1;
+    mbar_wait(&mi.bar1, ph1, nullptr);      // GEMM 1 of this tile (issued one tile ago)
+    ph1 ^= 1;
     tc_fence_after();
 
     // ---- epilogue 1: logits ----
@@ -352,9 +369,11 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       }
       mi.s_part[cg][row] = sp;
     }
+    ldgsts_wait<0>();           // the next tile's rows (staged one tile ago)
     __syncthreads();
+    if (t + 2 * g_tiles < n_tiles) stage_rows(nnb);
     // Every warp works out the softmax of its sample slot by itself: lane l looks at the slot's pairs l and l + 32.
-    float att, c_r, ds;
+    float c_r, ds;
     {
       const int rlo = ss * kSlot + lane, rhi = rlo + 32;
       float s_lo = mi.s_part[0][rlo], s_hi = mi.s_part[0][rhi], u_lo = mi.u_part[0][rlo], u_hi = mi.u_part[0][rhi];
@@ -376,7 +395,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       }
       const float den = d0 + d1;
       const float od = (n0 + n1) / den;                       // sum_p a_p (prediction_W . P_p) = prediction_W . afm, AFM.py:130-139
-      att = ((pp < 32) ? e_lo : e_hi) / den;
+      const float att = ((pp < 32) ? e_lo : e_hi) / den;
       const float u_r = (pp < 32) ? u_lo : u_hi;
       float g = 0.f;
       if (smp < a.B) {
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
         const bool on = zi > 0.f;
         dz[i] = on ? ds * mi.pvec[c0 + i] : 0.f;
         hp[i] = on ? ds * zi : 0.f;                                     // d p += ds * relu(Z + b)
-        const float lo = tf32_lo(dz[i]);
+        const float lo = lo_part(dz[i]);
         rx[i] = __float_as_uint(dz[i]); rl[i] = __float_as_uint(lo);
         const int an = c0 + i;
         *reinterpret_cast<float*>(zt + swz_e(an, lane)) = dz[i];
@@ -441,22 +460,17 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
           umma_tf32(tmem + cDW, ad, make_sdesc(sZ + rb * kWTile + o), idesc, (rb | k4) ? 1u : 0u);
           umma_tf32(tmem + cDW, ad, make_sdesc(sZ + (4 + rb) * kWTile + o), idesc, 1u);
         }
-      umma_commit(&mi.bar);
+      umma_commit(&mi.bar2);
     }
-    // behind GEMM 2 / 3: the column sums over the tile rows (d b = sum dZ, d p, d prediction_W = sum g a_p P_p), deferred
+    // behind GEMM 2 / 3: the column sums over the tile rows (d b = sum dZ, d p, d prediction_W = sum g a_p P_p), deferred,
+    // and the P rows of the next tile -> TMEM
     fold8<CW>(dz, gb8, lane);
     fold8<CW>(hp, gp8, lane);
-    {
-      const float cm = prow ? c_r : 0.f;                     // the pair products again from the staged rows (fewer live registers)
-#pragma unroll
-      for (int i = 0; i < CW; i += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(ei + i), y = *reinterpret_cast<const float4*>(ej + i);
-        dz[i] = cm * (x.x * y.x); dz[i + 1] = cm * (x.y * y.y); dz[i + 2] = cm * (x.z * y.z); dz[i + 3] = cm * (x.w * y.w);
-      }
-    }
+    pair_products(Es, dz, c_r);
     fold8<CW>(dz, gw8, lane);
-    mbar_wait(&mi.bar, bar_ph, nullptr);
-    bar_ph ^= 1;
+    if (has_next) build_p_tmem(EsBuf + nb * (kEBytes / 4));
+    mbar_wait(&mi.bar2, ph2, nullptr);
+    ph2 ^= 1;
     tc_fence_after();
 
     // ---- epilogue 2: dP rows (+ the direct path a_p * d afm = g a_p prediction_W) -> shared memory (the dZT tiles are free now) ----
@@ -477,10 +491,11 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0 && has_next) { tc_fence_after(); issue_gemm1(); }      // GEMM 1 of the next tile runs behind the scatter below
     // dE_f = sum_{j != f} dP_(f,j) * E_j ; one vector reduction per 16 bytes of the gradient row
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
-      const int id = mi.ids[cur][s2][f];
+      const int id = mi.ids[buf][s2][f];
       if (id < 0) continue;
       float4 acc = f4_zero();
       for (int j = 0; j < F; j++) {
@@ -491,7 +506,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
         acc.x = fmaf(dp.x, e.x, acc.x); acc.y = fmaf(dp.y, e.y, acc.y); acc.z = fmaf(dp.z, e.z, acc.z); acc.w = fmaf(dp.w, e.w, acc.w);
       }
       float* dst = a.gV + (size_t)id * KD;
-      const int hs = has_hot ? mi.hslot[cur][s2][f] : -1;
+      const int hs = has_hot ? mi.hslot[buf][s2][f] : -1;
       if (hs >= 0) dst = a.hot.ghot + ((size_t)rep * a.hot.n_hot + hs) * KD;
       red_add_v4(dst + 4 * c, acc);
       if (c == 0) {
@@ -502,9 +517,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
         if (a.touch_stamp) a.touch_stamp[id] = a.stamp;      // compacted into the touched-row list afterwards
       }
     }
-    // no barrier here: the one at the top of the next tile separates these reads from every later write
-    id_pending = id_next2; have_pending = true;              // -> mi.ids[cur] after that barrier
-    cur ^= 1;
+    buf = nb;
   }
 
   ldgsts_wait<0>();
