@@ -58,21 +58,21 @@ constexpr uint32_t oWn = oWt + 4 * kWTile;              // W tiles (rows = k, co
 constexpr uint32_t kEBytes = 2 * kMaxF * kEP * 4;       // staged embedding rows of one tile: float E[2][kMaxF][kEP]
 constexpr uint32_t oE = oWn + 4 * kWTile;               // three tiles in flight: scattered, processed, landing
 constexpr uint32_t oMisc = oE + 3 * kEBytes;
-constexpr uint32_t kMiscBytes = 8192;
+constexpr uint32_t kMiscBytes = 10240;
 constexpr uint32_t kSmemBytes = oMisc + kMiscBytes + 1024;    // + alignment slack
 
 struct Misc {
   float batt[KD], pvec[KD], wpred[KD];
   float gbatt[KD], gp[KD], gwp[KD];
   float s_part[4][kRows];      // logits by column group
-  float u_part[4][kRows];      // prediction_W . P_p by column group
+  float u_part[2][4][kRows];   // [tile parity] prediction_W . P_p by column group (built one tile ahead)
   float g[2], bsum[2];
   float biasv[3][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
   int hslot[3][2][kMaxF + 1];     // [buffer][slot][field] hot-row slot of the staged rows (-1: none)
   int ids[3][2][kMaxF + 1];       // [buffer][slot][field]
   unsigned char pi[kSlot], pj[kSlot];
   unsigned char pidx[kMaxF][kMaxF + 1];
-  uint64_t bar1, bar2;          // GEMM 1 | GEMM 2 + 3 complete
+  uint64_t bar1, bar2, bar3;    // GEMM 1 | GEMM 2 | GEMM 3 complete
   uint32_t tmem;
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       }
     mbar_init(&mi.bar1, 1);
     mbar_init(&mi.bar2, 1);
+    mbar_init(&mi.bar3, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&mi.tmem, kTmemCols);
@@ -275,12 +276,17 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
   };
   // P rows of a tile -> TMEM (x and lo): the A operand of GEMM 1
-  auto build_p_tmem = [&](const float* Es) {
+  auto build_p_tmem = [&](const float* Es, int par) {
     float pr[CW];
     uint32_t rx[CW], rl[CW];
     pair_products(Es, pr, 1.f);
+    float up = 0.f;
 #pragma unroll
-    for (int i = 0; i < CW; i++) { rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo_part(pr[i])); }
+    for (int i = 0; i < CW; i++) {
+      rx[i] = __float_as_uint(pr[i]); rl[i] = __float_as_uint(lo_part(pr[i]));
+      up = fmaf(mi.wpred[c0 + i], pr[i], up);                           // u_p = prediction_W . P_p (AFM.py:138-139, per pair)
+    }
+    mi.u_part[par][cg][row] = up;
     tmem_st(t_lane + cPX + c0, rx);
     tmem_st(t_lane + cPL + c0, rl);
     tmem_st_wait();
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     umma_commit(&mi.bar1);
   };
   const int64_t g_tiles = gridDim.x;
-  int buf = 0;
+  int buf = 0, par = 0;
   {
     const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + g_tiles);
     if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     stage_rows(1);
     ldgsts_wait<1>();                       // the first tile's rows
     __syncthreads();
-    build_p_tmem(EsBuf);
+    build_p_tmem(EsBuf, 0);
     tc_fence_before();
     __syncthreads();
     if (tid == 0) { tc_fence_after(); issue_gemm1(); }
@@ -338,20 +344,17 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       for (int f = 0; f < F; f++) bs += mi.biasv[buf][tid][f];
       mi.bsum[tid] = bs;
     }
-    // ---- phase 1: the K-major PT tiles (A of GEMM 3; GEMM 3 of the previous tile is complete) and u_p = prediction_W . P_p ----
+    // ---- phase 1: the K-major PT tiles (A of GEMM 3; GEMM 3 of the previous tile is complete) ----
     {
       float pr[CW];
       pair_products(Es, pr, 1.f);
       uint8_t* pt = smem + oP + (uint32_t)quarter * kTile;             // r block = quarter, column of the tile row = lane
-      float up = 0.f;
 #pragma unroll
       for (int i = 0; i < CW; i++) {
         const int k = c0 + i;
         *reinterpret_cast<float*>(pt + swz_e(k, lane)) = pr[i];
         *reinterpret_cast<float*>(pt + swz_e(KD + k, lane)) = lo_part(pr[i]);
-        up = fmaf(mi.wpred[k], pr[i], up);                              // AFM.py:138-139, per pair
       }
-      mi.u_part[cg][row] = up;
     }
     mbar_wait(&mi.bar1, ph1, nullptr);      // GEMM 1 of this tile (issued one tile ago)
     ph1 ^= 1;
@@ -376,11 +379,11 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     float c_r, ds;
     {
       const int rlo = ss * kSlot + lane, rhi = rlo + 32;
-      float s_lo = mi.s_part[0][rlo], s_hi = mi.s_part[0][rhi], u_lo = mi.u_part[0][rlo], u_hi = mi.u_part[0][rhi];
+      float s_lo = mi.s_part[0][rlo], s_hi = mi.s_part[0][rhi], u_lo = mi.u_part[par][0][rlo], u_hi = mi.u_part[par][0][rhi];
 #pragma unroll
       for (int q = 1; q < NQ; q++) {
         s_lo += mi.s_part[q][rlo]; s_hi += mi.s_part[q][rhi];
-        u_lo += mi.u_part[q][rlo]; u_hi += mi.u_part[q][rhi];
+        u_lo += mi.u_part[par][q][rlo]; u_hi += mi.u_part[par][q][rhi];
       }
       const bool v_lo = lane < P, v_hi = lane + 32 < P;
       float mx = fmaxf(v_lo ? s_lo : -INFINITY, v_hi ? s_hi : -INFINITY);
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
           umma_tf32_ts(tmem + cDP, tmem + cZX + kc, make_sdesc(bl), idesc, 1u);
           umma_tf32_ts(tmem + cDP, tmem + cZX + kc, make_sdesc(bx), idesc, 1u);
         }
+      umma_commit(&mi.bar2);
       // dW: reduction over the 128 tile rows = 4 r blocks x 4 k-steps of 8; A = [PT x ; PT lo] (M = 128), B = dZT x, dZT lo
 #pragma unroll
       for (int rb = 0; rb < 4; rb++)
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
           umma_tf32(tmem + cDW, ad, make_sdesc(sZ + rb * kWTile + o), idesc, (rb | k4) ? 1u : 0u);
           umma_tf32(tmem + cDW, ad, make_sdesc(sZ + (4 + rb) * kWTile + o), idesc, 1u);
         }
-      umma_commit(&mi.bar2);
+      umma_commit(&mi.bar3);
     }
     // behind GEMM 2 / 3: the column sums over the tile rows (d b = sum dZ, d p, d prediction_W = sum g a_p P_p), deferred,
     // and the P rows of the next tile -> TMEM
@@ -468,23 +472,25 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     fold8<CW>(hp, gp8, lane);
     pair_products(Es, dz, c_r);
     fold8<CW>(dz, gw8, lane);
-    if (has_next) build_p_tmem(EsBuf + nb * (kEBytes / 4));
-    mbar_wait(&mi.bar2, ph2, nullptr);
-    ph2 ^= 1;
+    if (has_next) build_p_tmem(EsBuf + nb * (kEBytes / 4), par ^ 1);
+    mbar_wait(&mi.bar2, ph2, nullptr);      // GEMM 2
     tc_fence_after();
 
-    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm = g a_p prediction_W) -> shared memory (the dZT tiles are free now) ----
+    // ---- epilogue 2: dP rows (+ the direct path a_p * d afm = g a_p prediction_W) -> shared memory, once GEMM 3 is done with
+    //      the dZT tiles ----
     {
       uint32_t r[CW];
       tmem_ld(t_lane + cDP + c0, r);
+#pragma unroll
+      for (int i = 0; i < CW; i++) r[i] = __float_as_uint(fmaf(c_r, mi.wpred[c0 + i], __uint_as_float(r[i])));
+      mbar_wait(&mi.bar3, ph2, nullptr);    // GEMM 3
+      ph2 ^= 1;
+      tc_fence_after();
       float* dst = reinterpret_cast<float*>(smem + oZ) + row * KD;
 #pragma unroll
-      for (int c = 0; c < CW / 4; c++) {
-        const float* wp = mi.wpred + c0 + 4 * c;
-        const float4 v = make_float4(fmaf(c_r, wp[0], __uint_as_float(r[4 * c])), fmaf(c_r, wp[1], __uint_as_float(r[4 * c + 1])),
-                                     fmaf(c_r, wp[2], __uint_as_float(r[4 * c + 2])), fmaf(c_r, wp[3], __uint_as_float(r[4 * c + 3])));
-        *reinterpret_cast<float4*>(dst + 4 * ((cg * (CW / 4) + c) ^ (row & 15))) = v;
-      }
+      for (int c = 0; c < CW / 4; c++)
+        *reinterpret_cast<float4*>(dst + 4 * ((cg * (CW / 4) + c) ^ (row & 15))) =
+            make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
       tmem_ld(t_lane + cDW + c0, r);                          // this tile's dW partial sum -> registers (two-level accumulation)
 #pragma unroll
       for (int i = 0; i < CW; i++) dwacc[i] += __uint_as_float(r[i]);
@@ -498,8 +504,9 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       const int id = mi.ids[buf][s2][f];
       if (id < 0) continue;
       float4 acc = f4_zero();
-      for (int j = 0; j < F; j++) {
-        if (j == f) continue;
+#pragma unroll
+      for (int j = 0; j < kMaxF; j++) {                       // unrolled: the loads of all terms are in flight together
+        if (j >= F || j == f) continue;
         const int r2 = s2 * kSlot + mi.pidx[f][j];
         const float4 dp = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + oZ) + r2 * KD + 4 * (c ^ (r2 & 15)));
         const float4 e = *reinterpret_cast<const float4*>(Es + (s2 * kMaxF + j) * kEP + 4 * c);
@@ -518,6 +525,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       }
     }
     buf = nb;
+    par ^= 1;
   }
 
   ldgsts_wait<0>();
