@@ -402,6 +402,64 @@ def run_topn_c5(world, rank, dev):
                          "note": "per GPU, algorithmic 2*K flop per pair over the whole pipeline incl. exchange + merge; burst bf16 peak"}}
 
 
+def run_topn_c5_ctx(world, rank, dev):
+    """The same evaluation (10^6-item catalog, K = 128, 65 536 context rows, tp = 100) with the CONTEXT rows sharded: every
+    rank holds the whole table (it does under data-parallel training: 0.5 GB + 0.26 GB of bf16 operand) and scores its
+    65 536/N rows against all 10^6 items; the [C/N, tp] lists are all-gathered inside the timed region.  No candidate exchange,
+    no merge, and the per-row stages shard with the rows (`models.enable_context_sharding`)."""
+    import torch
+    import torch.distributed as dist
+    from hhfm_b200 import dist as hd
+    from hhfm_b200.engine import TopN
+    C, N, K, tp, n_user = 65536, 1000000, 128, 100, 4096
+    g = torch.Generator(device="cpu").manual_seed(777)
+    V = torch.empty(n_user + N, K).normal_(0, 0.01, generator=g).to(dev)
+    A = torch.stack([torch.randint(0, n_user, (C,), generator=g), torch.full((C,), n_user, dtype=torch.int64)], 1).to(torch.int32)
+    lo, hi = hd.shard_range(C, rank, world)
+    t = TopN(dev, max_workspace_bytes=6 << 30)
+    A_dev, stride = t.upload_rows(A[lo:hi].numpy(), n_user + N)
+    chunk = 16384
+
+    def once():
+        outs = []
+        for c0 in range(0, hi - lo, chunk):
+            outs.append(t.topk(0, A_dev[c0:c0 + chunk], stride, 0, 0, (0, 0, 0), V, None, n_user, N, tp, method="tc", version=1))
+        ids = torch.cat(outs) if len(outs) > 1 else outs[0]
+        return hd.gather_rows(ids) if world > 1 else ids
+
+    for _ in range(2):
+        once()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = once()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    pairs = float(C) * N
+    burst, sustained = _tensor_peaks()
+    ach_tf = 2.0 * K * pairs / world / (ms * 1e-3) / 1e12
+    return {"metric": "topn_scored_pairs_per_s", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_query_batch": ms,
+            "scaling": "strong", "lists_gathered": [int(out.shape[0]), int(out.shape[1])],
+            "config": {"workload": "BASELINE configs[4]: 10^6-item catalog, K=128, top-100, CONTEXT rows sharded (table replicated), "
+                                   "lists all-gathered inside the timed region", "contexts": C, "contexts_per_gpu": hi - lo,
+                       "items_total": N, "K": K, "tp": tp},
+            "overflow_rows": t.last_overflow_rows,
+            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": burst, "unit": "TFLOP/s", "frac": ach_tf / burst,
+                         "frac_of_sustained": ach_tf / sustained,
+                         "note": "per GPU, algorithmic 2*K flop per pair over the whole pipeline incl. the all-gather of the lists; burst bf16 peak"}}
+
+
 def workload_config(batch, n_gpus):
     return {"workload": "OurModel7 (HHFM) train step, frappe-10 shape: 10 fields, features_M=%d, K=%d, NG=%d, "
                         "Adagrad lr=0.1, lamda=0.01 (dense L2 update)" % (FEATURES_M, K_FACTOR, NG),
@@ -661,6 +719,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     topn = None if args.no_topn else run_topn(world, rank, dev, args.quick)
     topn_c5 = None if (args.no_topn or args.quick) else run_topn_c5(world, rank, dev)
+    topn_c5_ctx = None if (args.no_topn or args.quick or world == 1) else run_topn_c5_ctx(world, rank, dev)
     models = None
     l2_peak = bands = epoch = None
     if world == 1 and not args.quick and not args.no_models:
@@ -729,6 +788,8 @@ def run_ours(args):
             line["topn"] = topn
         if topn_c5 is not None:
             line["topn_c5"] = topn_c5
+        if topn_c5_ctx is not None:
+            line["topn_c5_context_sharded"] = topn_c5_ctx
         if models is not None:
             line["models"] = models
         if bands is not None:

@@ -381,10 +381,35 @@ class _Base:
             raise RuntimeError("enable_item_sharding: torch.distributed is not initialised")
         self._eval_group = group if group is not None else dist.group.WORLD
 
+    def enable_context_sharding(self, group=None):
+        """Full-catalog top-N with the CONTEXT rows sharded across the ranks of `group`: rank r scores rows
+        shard_range(C, r, ws) against the WHOLE catalog and the lists are concatenated in rank order.  This is the
+        evaluator's decomposition whenever the table is replicated (it is under data-parallel training): no candidate
+        exchange, no merge, and the per-row work (rescoring, selection) shards with the rows -- strong scaling is the row
+        split.  Item sharding (`enable_item_sharding`) is for catalogs that do not fit one GPU.  Lists are bit-identical."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("enable_context_sharding: torch.distributed is not initialised")
+        if getattr(self, "_eval_group", None) is not None:
+            raise RuntimeError("enable_context_sharding: item sharding is already enabled on this model")
+        self._eval_ctx_group = group if group is not None else dist.group.WORLD
+
     def _topk(self, kind, A, n_ctx, n_time, pools, bias, tp):
         from . import dist as hd
         A = np.asarray(A)
         self.flush()
+        cgrp = getattr(self, "_eval_ctx_group", None)
+        if cgrp is not None:
+            rank, ws = hd.world(cgrp)
+            lo, hi = hd.shard_range(A.shape[0], rank, ws)
+            V = self.weights["feature_embeddings"]
+            if hi > lo:
+                A_dev, stride = self._topn.upload_rows(A[lo:hi], self._M)
+                ids = self._topn.topk(kind, A_dev, stride, n_ctx, n_time, pools, V, bias, self.n_user, self.n_item, tp,
+                                      method=self.topn_method, version=self._version)
+            else:
+                ids = torch.empty(0, tp, dtype=torch.int32, device=V.device)
+            return hd.gather_rows(ids, cgrp).cpu().numpy()
         A_dev, stride = self._topn.upload_rows(A, self._M)
         V = self.weights["feature_embeddings"]
         grp = getattr(self, "_eval_group", None)

@@ -46,6 +46,12 @@ def _worker(rank, world, port, ret):
             A = np.concatenate([X[:200], F1[:200]], axis=1)
             ids = model.topk(A, 20)
             want = O.topk_lowest_index(O.hhfm_topk_scores(A, got, n_user, n_item, fc, 0), 20)
+            # the other decomposition of the evaluator: context rows sharded, whole catalog per rank, lists concatenated
+            eg, model._eval_group = model._eval_group, None
+            model.enable_context_sharding()
+            ids_ctx = model.topk(A[:197], 20)                    # 197 rows: uneven shards
+            model._eval_ctx_group, model._eval_group = None, eg
+            ok_ctx = ids_ctx.shape == (197, 20) and bool((ids_ctx == want[:197]).all())
             # three more steps (both arena buffers get reused), then the replicas must still be identical on every rank
             for step in range(3):
                 r2 = np.random.default_rng(100 + step)
@@ -57,7 +63,7 @@ def _worker(rank, world, port, ret):
             dist.all_gather(gathered, w)
             same = all(bool(torch.equal(gathered[0], g)) for g in gathered)
             finals[mode] = w.cpu().numpy().copy()
-            results.append((ok_loss, ok_w, bool((ids == want).all()), same))
+            results.append((ok_loss, ok_w, bool((ids == want).all()) and ok_ctx, same))
         d = np.abs(finals["auto"] - finals[False])
         close = bool(np.all(d <= 1e-4 * np.maximum(np.abs(finals[False]), np.sqrt(np.mean(finals[False] ** 2)))))
         ret[rank] = tuple(results) + (close,)
