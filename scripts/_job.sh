@@ -1,13 +1,4 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -8 > gpurun_out/r2_gputest_q.log
-cat gpurun_out/r2_gputest_q.log
-P=$((29500 + RANDOM % 400))
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $P bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_bench_n2_ctx.json 2> gpurun_out/r2_bench_n2_ctx.err
-tail -3 gpurun_out/r2_bench_n2_ctx.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_n2_ctx.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'])
-for k in ('topn','topn_c5','topn_c5_context_sharded'):
-    print(k, d.get(k,{}).get('ms_per_query_batch'), d.get(k,{}).get('value'))
-PY
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/c5_st_launches.csv python scripts/bench_models.py --only fm_c5,hhfm_c5 --steps 2 > gpurun_out/c5_st_ncu.log 2>&1
+HHFM_SINGLE_TOUCH=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/c5_nost_launches.csv python scripts/bench_models.py --only fm_c5,hhfm_c5 --steps 2 > gpurun_out/c5_nost_ncu.log 2>&1
+tail -2 gpurun_out/c5_st_ncu.log

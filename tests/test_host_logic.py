@@ -122,6 +122,7 @@ def test_fm_epoch_batches_match_reference_run(gold, data_root):
     t = PointwiseTrain.__new__(PointwiseTrain)
     t.data, t.n_user, t.n_item, t.batch_size, t.model = ld, ld.n_user, ld.n_item, 1000, _Capture()
     t.NG, t.neg_label = 2, 0
+    t.device_sampler = False          # the host path: the one that consumes the reference's numpy random stream
     np.random.seed(33)
     t.run_epoch()
     assert [len(b["X"]) for b in t.model.batches] == gold["fm_epoch_sizes"].tolist()
@@ -135,6 +136,7 @@ def test_hhfm_epoch_batches_match_reference_run(gold, data_root):
     t = PairwiseTrain.__new__(PairwiseTrain)
     t.data, t.n_user, t.n_item, t.batch_size, t.model = ld, ld.n_user, ld.n_item, 500, _Capture()
     t.NG, t.context, t.time, t.time_dimension = 10, True, True, 5
+    t.device_sampler = False
     np.random.seed(44)
     t.run_epoch()
     assert [len(b["X"]) for b in t.model.batches] == gold["m7_epoch_sizes"].tolist()
