@@ -50,7 +50,7 @@ def test_fm_single_touch_rows_are_bit_identical_to_the_arena_path(cuda, opt, mon
     res = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("HHFM_SINGLE_TOUCH", mode)
-        m = FM(F, M, 100, 100, K, 0.05, 0.0, 1, opt, 0, 0)
+        m = FM(F, M, 100, 100, K, 0.05 if opt == "AdagradOptimizer" else 0.002, 0.0, 1, opt, 0, 0)
         m.hot_rows = None
         snaps, touched = [], []
         for X, y in batches:
