@@ -23,6 +23,21 @@ from .engine import (NO_HOT, NO_HOT_BIAS, POOL_SUM, QUERY_FM, QUERY_HHFM, QUERY_
                      SingleTouchPlan, Staging, TopN, TouchTracker, cur_stream, pack_records, ptr, require_cuda)
 
 
+class PendingLoss:
+    """The loss of a step enqueued by `partial_fit_async`."""
+
+    def __init__(self, model, slot, event):
+        self._model, self._slot, self._event = model, slot, event
+
+    def result(self):
+        self._event.synchronize()
+        m = self._model
+        if m._dpx is not None and int(m._dp_state_host[1]) != 0:
+            raise _lib.HhfmError("data-parallel step: a peer did not reach the cross-GPU barrier within HHFM_DP_TIMEOUT_S; "
+                                 "the replicas are no longer in step (the CUDA context is intact)")
+        return float(m._loss_ring[self._slot])
+
+
 class Handle:
     """Stand-in for a tf.placeholder / graph tensor: only its identity matters (feed_dict key, fetch)."""
 
@@ -491,7 +506,30 @@ class _Base:
         _lib.call("hhfm_loss_finalize", ptr(self._loss_partials), sq, hl if with_reg else 0.0, ptr(self._loss_dev),
                   cur_stream())
 
+    def partial_fit_async(self, data):
+        """`partial_fit` without the wait: the step (host packing, H2D copy, kernels, D2H copy of the loss into a pinned slot)
+        is enqueued and a `PendingLoss` comes back; `.result()` waits for that step alone and returns the float that
+        `partial_fit` would have returned.  Keeping one step in flight lets the host pack batch i+1 while the GPU runs batch i
+        (the reference's loop only sums the losses of an epoch, FM.py:251-256).  At most 4 results may be outstanding."""
+        self._defer_loss = True
+        try:
+            return self.partial_fit(data)
+        finally:
+            self._defer_loss = False
+
     def _read_loss(self):
+        if getattr(self, "_defer_loss", False):
+            if getattr(self, "_loss_ring", None) is None:
+                self._loss_ring = torch.empty(4, dtype=torch.float32, pin_memory=True)
+                self._loss_ring_n = 0
+            slot = self._loss_ring_n % 4
+            self._loss_ring_n += 1
+            self._loss_ring[slot:slot + 1].copy_(self._loss_dev, non_blocking=True)
+            if self._dpx is not None:
+                self._dp_state_host.copy_(self._dp_state, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return PendingLoss(self, slot, ev)
         self._loss_host.copy_(self._loss_dev, non_blocking=True)
         if self._dpx is not None:
             self._dp_state_host.copy_(self._dp_state, non_blocking=True)

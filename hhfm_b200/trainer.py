@@ -224,12 +224,11 @@ class PointwiseTrain(BaseTrain):
         neg[:, 0] = self.neg_label
         dat = np.append(pos, neg, axis=0)
         np.random.shuffle(dat)
-        loss = 0
+        fit = _PipelinedFit(self.model)
         for c0 in range(0, len(dat), self.batch_size):
             chunk = dat[c0:c0 + self.batch_size]
-            loss = loss + self.model.partial_fit({'X': np.array(chunk[:, 1:], dtype=np.int64),
-                                                  'Y': np.expand_dims(chunk[:, 0], axis=1)})
-        return loss
+            fit({'X': np.array(chunk[:, 1:], dtype=np.int64), 'Y': np.expand_dims(chunk[:, 0], axis=1)})
+        return fit.total()
 
     def score_rows(self, rows):
         return self.model.predict(rows)
@@ -283,12 +282,40 @@ class PairwiseTrain(BaseTrain):
         pos = self._train_values()[:, 1:]                    # persistent view (see _train_values)
         np.random.shuffle(pos)                               # OurModel7.py:370
         neg = self.sample_negative(pos, self.NG)
-        loss = 0
+        fit = _PipelinedFit(self.model)
         for c0 in range(0, len(pos), self.batch_size):
             d = self.split(pos[c0:c0 + self.batch_size])
             d['Y'] = np.array(neg[c0:c0 + self.batch_size], dtype=np.int64)
-            loss = loss + self.model.partial_fit(d)
-        return loss
+            fit(d)
+        return fit.total()
+
+
+class _PipelinedFit:
+    """The epoch loop's `loss = loss + model.partial_fit(batch)` (FM.py:251-256) with one step in flight: the loss of batch i
+    is waited for after batch i+1 has been enqueued (`partial_fit_async`), so the host assembles and packs the next batch
+    while the GPU runs the current one.  The losses are added in batch order; a model without the async call (a test
+    double) is driven synchronously."""
+
+    def __init__(self, model):
+        self._async = getattr(model, "partial_fit_async", None)
+        self._sync = model.partial_fit
+        self._prev = None
+        self._loss = 0
+
+    def __call__(self, batch):
+        if self._async is None:
+            self._loss = self._loss + self._sync(batch)
+            return
+        h = self._async(batch)
+        if self._prev is not None:
+            self._loss = self._loss + self._prev.result()
+        self._prev = h
+
+    def total(self):
+        if self._prev is not None:
+            self._loss = self._loss + self._prev.result()
+            self._prev = None
+        return self._loss
 
 
 def default_result_file():

@@ -222,3 +222,36 @@ def test_lazy_l2_replay_is_bit_identical_to_the_dense_update(cuda, which):
     assert np.array_equal(res[True][2], res[False][2]), "top-N lists after the mid-training flush differ"
     w0 = np.asarray(res[True][0])
     assert not np.array_equal(w0[-50:], np.zeros_like(w0[-50:]))
+
+
+def test_partial_fit_async_returns_the_same_losses_with_one_step_in_flight(cuda):
+    """`partial_fit_async` + `PendingLoss.result()` (the trainers' pipelined epoch loop) against the blocking call: the same
+    floats in the same order, also when the four-slot result ring wraps."""
+    from hhfm_b200.models import OUR
+    from hhfm_b200.trainer import _PipelinedFit
+    rng = np.random.default_rng(21)
+    n_user, n_item, M, K, fc, B = 80, 150, 260, 64, 4, 1500
+    batches = [_hhfm_batch(rng, n_user, n_item, M, fc, B) for _ in range(7)]
+    out = {}
+    for mode in ("blocking", "async"):
+        m = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, "AdagradOptimizer", True, False)
+        m.deterministic = True
+        if mode == "blocking":
+            losses = [m.partial_fit(b) for b in batches]
+        else:
+            losses, prev = [], None
+            for b in batches:
+                h = m.partial_fit_async(b)
+                if prev is not None:
+                    losses.append(prev.result())
+                prev = h
+            losses.append(prev.result())
+        out[mode] = (losses, m.get_weights()["feature_embeddings"])
+    assert out["blocking"][0] == out["async"][0]
+    assert np.array_equal(out["blocking"][1], out["async"][1])
+    m = OUR(fc, 0, M, n_user, n_item, K, 0.1, 0.01, "AdagradOptimizer", True, False)
+    m.deterministic = True
+    fit = _PipelinedFit(m)
+    for b in batches:
+        fit(b)
+    assert abs(fit.total() - sum(out["blocking"][0])) <= 1e-6 * abs(sum(out["blocking"][0]))
