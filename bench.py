@@ -425,8 +425,9 @@ def run_topn_c5_ctx(world, rank, dev):
         for c0 in range(0, hi - lo, chunk):
             outs.append(t.topk(0, A_dev[c0:c0 + chunk], stride, 0, 0, (0, 0, 0), V, None, n_user, N, tp, method="tc", version=1))
         ids = torch.cat(outs) if len(outs) > 1 else outs[0]
-        return hd.gather_rows(ids) if world > 1 else ids
+        return hd.gather_rows(ids, None, sizes) if world > 1 else ids
 
+    sizes = [hd.shard_range(C, r, world)[1] - hd.shard_range(C, r, world)[0] for r in range(world)]
     for _ in range(2):
         once()
     if world > 1:

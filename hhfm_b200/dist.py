@@ -105,15 +105,26 @@ def _select_merged(scores, idx, tp):
     return out_ids, out_sc
 
 
-def gather_rows(t, group=None):
-    """Concatenate per-rank row blocks of possibly different length (rank order)."""
+def gather_rows(t, group=None, sizes=None):
+    """Concatenate per-rank row blocks of possibly different length (rank order).  `sizes`: the ranks' row counts when the
+    caller knows them (e.g. `shard_range` shards) -- saves the size exchange and its host synchronisation; equal blocks then
+    go through one all_gather_into_tensor straight into the result."""
     rank, ws = world(group)
     if ws == 1:
         return t
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(ws)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        got = [torch.zeros_like(n) for _ in range(ws)]
+        dist.all_gather(got, n, group=group)
+        sizes = [int(s.item()) for s in got]
+    else:
+        sizes = [int(x) for x in sizes]
+        if len(sizes) != ws or sizes[rank] != t.shape[0]:
+            raise ValueError("gather_rows: sizes %r do not describe this rank's block of %d rows" % (sizes, t.shape[0]))
+    if min(sizes) == max(sizes) and hasattr(dist, "all_gather_into_tensor"):
+        out = torch.empty((sizes[0] * ws,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
     mx = max(sizes)
     pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[:t.shape[0]] = t

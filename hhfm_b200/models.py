@@ -456,7 +456,8 @@ class _Base:
                                       method=self.topn_method, version=self._version)
             else:
                 ids = torch.empty(0, tp, dtype=torch.int32, device=V.device)
-            return hd.gather_rows(ids, cgrp).cpu().numpy()
+            sizes = [hd.shard_range(A.shape[0], r, ws)[1] - hd.shard_range(A.shape[0], r, ws)[0] for r in range(ws)]
+            return hd.gather_rows(ids, cgrp, sizes).cpu().numpy()
         A_dev, stride = self._topn.upload_rows(A, self._M)
         V = self.weights["feature_embeddings"]
         grp = getattr(self, "_eval_group", None)

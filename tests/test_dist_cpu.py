@@ -87,6 +87,12 @@ def _eval_shards(rank, world):
         return (False, False, False)
     codes = torch.arange(lo, hi, dtype=torch.int32)
     allc = hd.gather_rows(codes)
+    sizes = [hd.shard_range(N, r, world)[1] - hd.shard_range(N, r, world)[0] for r in range(world)]
+    if hd.gather_rows(codes, None, sizes).tolist() != list(range(N)):                 # known sizes: no size exchange (uneven: 51 + 50)
+        return (False, False, False)
+    even = torch.arange(rank * 8, rank * 8 + 8, dtype=torch.int32).view(4, 2)           # equal blocks: one all_gather_into_tensor
+    if hd.gather_rows(even, None, [4] * world).reshape(-1).tolist() != list(range(8 * world)):
+        return (False, False, False)
     return ((ids.numpy() == want).all(), (sc.numpy() == np.take_along_axis(score, want, axis=1)).all(), allc.tolist() == list(range(N)))
 
 
