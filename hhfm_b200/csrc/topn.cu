@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
   extern __shared__ unsigned long long s_keys[];     // tp_pow2 winners (+ the row's keys when staged)
   __shared__ unsigned s_hist[256];
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_krem, s_cnt;
+  __shared__ int s_krem, s_cnt, s_done;
   const int64_t c = blockIdx.x;
   const float* sc = scores + c * row_stride;
   const int32_t* idp = ids ? ids + c * row_stride : nullptr;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
 
   unsigned long long thresh = 0ull;
   if (n > tp) {
-    if (t == 0) { s_prefix = 0ull; s_krem = tp; }
+    if (t == 0) { s_prefix = 0ull; s_krem = tp; s_done = 0; }
     for (int pass = 0; pass < 8; pass++) {
       const int shift = 56 - 8 * pass;
       s_hist[t] = 0u;
@@ -195,11 +195,18 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ s
           }
           s_krem = (int)(krem - cum);
           s_prefix = (prefix << 8) | (unsigned long long)(t * 8 + bsel);
+          // every key of the chosen bin is among the winners: the lowest key this prefix can have is a valid threshold and
+          // the remaining digits need not be looked at (typical after 2-3 of the 8 passes on a few hundred candidates)
+          if (shift > 0 && h[bsel] == krem - cum) {
+            s_prefix <<= shift;
+            s_done = 1;
+          }
         }
       }
       __syncthreads();
+      if (s_done) break;
     }
-    thresh = s_prefix;                               // exact key of the tp-th best element
+    thresh = s_prefix;                               // the tp-th best key, or a lower bound that no losing key reaches
   }
   if (t == 0) s_cnt = 0;
   for (int i = t; i < tp_pow2; i += 256) s_keys[i] = 0ull;   // 0 sorts last

@@ -805,7 +805,11 @@ static TcLayout tc_layout(int64_t C, int64_t N, int Kp, int tp, int bn) {
   // 32-item group maximum of that sample, chosen so that ~3.5 tp items of the full catalog pass it (proven per row
   // afterwards, tc_verify_kernel).  Small catalogs: every tile, tau = tp-th largest group maximum (guaranteed cut).
   int s = tc_sample_stride_env();
-  int j = (int)((7 * (int64_t)tp + 2 * s - 1) / (2 * s)) + 4;
+  // expected survivors of the cut = x * tp, x = 3.5 (HHFM_TOPN_CUT_X10 = 10 x for A/B runs).  Measured at C = 16 384, N = 10^6,
+  // tp = 100: x = 3.5 -> no row fails its proof, 4.7 ms; x = 2.5 -> 4 rows fail (the proof needs tp candidates above the cut
+  // PLUS the bf16 error bound, which eats most of the margin) and their exact redo costs 2 ms; x = 2.0 -> 126 rows.
+  static const int x10 = [] { const char* e = getenv("HHFM_TOPN_CUT_X10"); const int v = e ? atoi(e) : 35; return v < 15 ? 15 : (v > 80 ? 80 : v); }();
+  int j = (int)((x10 * (int64_t)tp + 10 * s - 1) / (10 * s)) + 4;
   if (s > 1 && (n_tiles / s) * (bn / kGroup) < 8 * (int64_t)j) s = 1;
   if (j > 1024) s = 1;
   L.sample_stride = s;
