@@ -52,6 +52,15 @@ def _worker(rank, world, port, ret):
             ids_ctx = model.topk(A[:197], 20)                    # 197 rows: uneven shards
             model._eval_ctx_group, model._eval_group = None, eg
             ok_ctx = ids_ctx.shape == (197, 20) and bool((ids_ctx == want[:197]).all())
+            # the HR / NDCG walk sharded by context rows (device walk on this rank's rows + all-reduce of the sums over NCCL)
+            from hhfm_b200 import engine
+            tgt = rng.integers(0, n_item, 197).astype(np.int32); inpf = (rng.random(197) < 0.1).astype(np.uint8)
+            full = engine.metrics_walk(torch.from_numpy(want[:197].astype(np.int32)).cuda(), torch.from_numpy(tgt).cuda(),
+                                       torch.from_numpy(inpf).cuda(), 5).cpu().numpy()
+            r0, r1 = hd.shard_range(197, rank, world)
+            mine = engine.metrics_walk(torch.from_numpy(ids_ctx[r0:r1].astype(np.int32)).cuda(), torch.from_numpy(tgt[r0:r1]).cuda(),
+                                       torch.from_numpy(inpf[r0:r1]).cuda(), 5).cpu().numpy()
+            ok_ctx = ok_ctx and bool(np.allclose(hd.allreduce_metrics(mine), engine.metrics_from_codes(full), rtol=1e-12, atol=0))
             # three more steps (both arena buffers get reused), then the replicas must still be identical on every rank
             for step in range(3):
                 r2 = np.random.default_rng(100 + step)
