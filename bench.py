@@ -324,6 +324,9 @@ def run_topn(world, rank, dev, quick):
                                  "reported as item_operand_prep_ms, outside the timed region"}}
 
 
+_C5_LISTS = {}
+
+
 def run_topn_c5(world, rank, dev):
     """BASELINE.json configs[4] as written: ONE catalog of 10^6 items, K = 128, C = 65 536 context rows,
     tp = 100; at N GPUs every rank scores all contexts against its 10^6/N items (STRONG scaling).  Contexts run in chunks;
@@ -377,7 +380,7 @@ def run_topn_c5(world, rank, dev):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        once()
+        last = once()
     e1.record()
     if world > 1:
         dist.barrier()
@@ -387,6 +390,9 @@ def run_topn_c5(world, rank, dev):
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+        # kept for the cross-check against the context-sharded evaluator: chunk c leaves rank r with rows
+        # [c*per + r*per/world, c*per + (r+1)*per/world) of the merged lists
+        _C5_LISTS["item_sharded"] = [x.clone() for x in last]
     prep_ms = _time_prepare_items(t, V, n_user, 0, n_loc, K)
     pairs = float(C) * N
     burst, sustained = _tensor_peaks()
@@ -450,8 +456,21 @@ def run_topn_c5_ctx(world, rank, dev):
     pairs = float(C) * N
     burst, sustained = _tensor_peaks()
     ach_tf = 2.0 * K * pairs / world / (ms * 1e-3) / 1e12
+    # N > 1 evidence: the two decompositions of the same evaluation (same catalog, same context rows) must give the same lists
+    same = None
+    if world > 1 and "item_sharded" in _C5_LISTS:
+        chunks = _C5_LISTS.pop("item_sharded")
+        per = C // len(chunks)
+        ok = True
+        for c, lst in enumerate(chunks):
+            r0 = c * per + rank * (per // world)
+            ok = ok and bool(torch.equal(lst.to(torch.int32), out[r0:r0 + per // world].to(torch.int32)))
+        tt = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        same = bool(tt.item() == 1.0)
     return {"metric": "topn_scored_pairs_per_s", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_query_batch": ms,
             "scaling": "strong", "lists_gathered": [int(out.shape[0]), int(out.shape[1])],
+            "lists_identical_to_item_sharded": same,
             "config": {"workload": "BASELINE configs[4]: 10^6-item catalog, K=128, top-100, CONTEXT rows sharded (table replicated), "
                                    "lists all-gathered inside the timed region", "contexts": C, "contexts_per_gpu": hi - lo,
                        "items_total": N, "K": K, "tp": tp},
