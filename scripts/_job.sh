@@ -1,8 +1,5 @@
-set -x
-timeout 600 python -m pytest tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -4
-bash scripts/_job_scale.sh 2
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_final_n2.json').read().strip().splitlines()[-1])
-print('lists_identical', d['topn_c5_context_sharded'].get('lists_identical_to_item_sharded'))
-PY
+for cfg in "8 35" "16 35" "16 40" "16 45" "16 50" "32 50"; do
+  set -- $cfg
+  echo "sample=$1 x10=$2"
+  HHFM_TOPN_SAMPLE=$1 HHFM_TOPN_CUT_X10=$2 python scripts/topn_stage_times.py --contexts 65536 --items 1000000 --reps 4 2>/dev/null
+done
