@@ -71,8 +71,11 @@ class Staging:
         self.device = device
         self.host = None
         self.dev = None
+        self._busy = None          # recorded after the last upload: the pinned buffer may be rewritten once it has passed
 
     def ensure(self, numel):
+        if self._busy is not None:
+            self._busy.synchronize()    # a step may still be in flight (partial_fit_async): its copy must have read the buffer
         if self.host is None or self.host.numel() < numel:
             cap = max(numel, 1024)
             pin = torch.cuda.is_available()
@@ -84,6 +87,10 @@ class Staging:
     def upload(self, numel):
         """Asynchronous H2D of the first `numel` elements on the current stream."""
         self.dev[:numel].copy_(self.host[:numel], non_blocking=True)
+        if self.host.is_pinned():
+            if self._busy is None:
+                self._busy = torch.cuda.Event()
+            self._busy.record()
         return self.dev[:numel]
 
 
