@@ -1,3 +1,4 @@
+# One rank per GPU, the command the driver uses: bash scripts/run_scale.sh N  ->  gpurun_out/r2_final_nN.json (+ a short summary)
 set -x
 N=$1
 P=$((29500 + RANDOM % 400))
