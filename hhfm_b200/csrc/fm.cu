@@ -383,8 +383,8 @@ __host__ __device__ inline size_t staged_warp_bytes(int NS, int F, int K) {
   return (b + 127) / 128 * 128;
 }
 
-template <int NS>
-__global__ void __launch_bounds__(kStagedWarps * 32, 1) fm_train_staged_kernel(const FmArgs a) {
+template <int NS, int NW = kStagedWarps>
+__global__ void __launch_bounds__(NW * 32, 1) fm_train_staged_kernel(const FmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[32];
   constexpr int PD = NS - 1;          // id prefetch distance (iterations)
@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) fm_train_staged_kernel(c
   __syncwarp();
 
   // contiguous range of samples per warp: consecutive iterations read consecutive id records
-  const int64_t n_warps = (int64_t)gridDim.x * kStagedWarps;
-  const int64_t warp_g = (int64_t)blockIdx.x * kStagedWarps + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * NW;
+  const int64_t warp_g = (int64_t)blockIdx.x * NW + warp;
   const int64_t per = (a.B + n_warps - 1) / n_warps;
   const int64_t s_beg = warp_g * per;
   const int64_t s_end = (s_beg + per < a.B) ? s_beg + per : a.B;
@@ -677,25 +677,45 @@ static int dispatch_fm_staged(const FmArgs& a, int64_t M, cudaStream_t st) {
   FmArgs b = a;
   if (b.K > 128) b.st1 = SingleTouch{};                    // the deferred in-place step keeps one float4 chunk per lane
   const size_t cap = (size_t)224 * 1024;
-  int ns = 4;
+  // measured at the c5 shape (F = 10, K = 128): 10 warps x 4 stages 5.95 ms per step, 10 x 3 5.91, 11 x 3 5.64, 12 x 3 5.74,
+  // 13 x 3 5.81, 14 x 3 5.88, 16 x 2 5.92 -> eleven warps with three stages each when that fits
+  int ns = 4, nw = kStagedWarps;
+  if (staged_warp_bytes(3, a.F, a.K) * 11 <= cap && staged_warp_bytes(4, a.F, a.K) * kStagedWarps > (size_t)200 * 1024) { ns = 3; nw = 11; }
   const char* ens = getenv("HHFM_FM_STAGES");              // 2..4: pipeline depth (A/B runs)
   if (ens && ens[0] >= '2' && ens[0] <= '4') ns = ens[0] - '0';
-  while (ns > 2 && staged_warp_bytes(ns, a.F, a.K) * kStagedWarps > cap) ns--;
-  const size_t smem = staged_warp_bytes(ns, a.F, a.K) * kStagedWarps;
+  const char* enw = getenv("HHFM_FM_WARPS");               // 10 .. 14 / 16 warps per CTA (A/B runs)
+  if (enw) { const int v = atoi(enw); if ((v >= 10 && v <= 14) || v == 16) nw = v; }
+  while (ns > 2 && staged_warp_bytes(ns, a.F, a.K) * nw > cap) ns--;
+  const size_t smem = staged_warp_bytes(ns, a.F, a.K) * nw;
   if (smem > cap) return HHFM_ERR_UNSUPPORTED;
   const int grid = sm_count();
   if (grid > kPartials) return HHFM_ERR_UNSUPPORTED;
   cudaError_t e = cudaSuccess;
-  if (ns == 4) {
-    e = cudaFuncSetAttribute(fm_train_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) fm_train_staged_kernel<4><<<grid, kStagedWarps * 32, smem, st>>>(b);
-  } else if (ns == 3) {
-    e = cudaFuncSetAttribute(fm_train_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) fm_train_staged_kernel<3><<<grid, kStagedWarps * 32, smem, st>>>(b);
+#define HHFM_LAUNCH_STAGED(NS_, NW_)                                                                                              \
+  do {                                                                                                                            \
+    e = cudaFuncSetAttribute(fm_train_staged_kernel<NS_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess) fm_train_staged_kernel<NS_, NW_><<<grid, NW_ * 32, smem, st>>>(b);                                      \
+  } while (0)
+  if (nw == kStagedWarps) {
+    if (ns == 4) HHFM_LAUNCH_STAGED(4, kStagedWarps);
+    else if (ns == 3) HHFM_LAUNCH_STAGED(3, kStagedWarps);
+    else HHFM_LAUNCH_STAGED(2, kStagedWarps);
+  } else if (nw == 11) {
+    if (ns >= 3) HHFM_LAUNCH_STAGED(3, 11);
+    else HHFM_LAUNCH_STAGED(2, 11);
+  } else if (nw == 13) {
+    if (ns >= 3) HHFM_LAUNCH_STAGED(3, 13);
+    else HHFM_LAUNCH_STAGED(2, 13);
+  } else if (nw == 12) {
+    if (ns >= 3) HHFM_LAUNCH_STAGED(3, 12);
+    else HHFM_LAUNCH_STAGED(2, 12);
+  } else if (nw == 14) {
+    if (ns >= 3) HHFM_LAUNCH_STAGED(3, 14);
+    else HHFM_LAUNCH_STAGED(2, 14);
   } else {
-    e = cudaFuncSetAttribute(fm_train_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) fm_train_staged_kernel<2><<<grid, kStagedWarps * 32, smem, st>>>(b);
+    HHFM_LAUNCH_STAGED(2, 16);
   }
+#undef HHFM_LAUNCH_STAGED
   if (e != cudaSuccess) {
     set_error("fm_train_staged_kernel: %s", cudaGetErrorString(e));
     return HHFM_ERR_LAUNCH;

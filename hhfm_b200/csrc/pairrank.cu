@@ -448,8 +448,8 @@ __host__ __device__ inline size_t pr_staged_warp_bytes(int NS, int W, int K) {
   return (b + 127) / 128 * 128;
 }
 
-template <int NS>
-__global__ void __launch_bounds__(kPrStagedWarps * 32, 1) pairrank_sum_train_staged_kernel(const PrArgs a) {
+template <int NS, int NW = kPrStagedWarps>
+__global__ void __launch_bounds__(NW * 32, 1) pairrank_sum_train_staged_kernel(const PrArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float scratch[32];
   constexpr int PD = NS - 1;
@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(kPrStagedWarps * 32, 1) pairrank_sum_train_sta
   }
   __syncwarp();
 
-  const int64_t n_warps = (int64_t)gridDim.x * kPrStagedWarps;
-  const int64_t warp_g = (int64_t)blockIdx.x * kPrStagedWarps + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * NW;
+  const int64_t warp_g = (int64_t)blockIdx.x * NW + warp;
   const int64_t per = (a.B + n_warps - 1) / n_warps;
   const int64_t s_beg = warp_g * per;
   const int64_t s_end = (s_beg + per < a.B) ? s_beg + per : a.B;
@@ -644,23 +644,34 @@ static int dispatch_pr_staged(const PrArgs& a_in, int64_t M, cudaStream_t st) {
   if (force == 0) return HHFM_ERR_UNSUPPORTED;
   if (force == 2 && (size_t)M * a.K * 4 < ((size_t)96 << 20)) return HHFM_ERR_UNSUPPORTED;
   const size_t cap = (size_t)224 * 1024;
-  int ns = 4;
-  while (ns > 2 && pr_staged_warp_bytes(ns, W, a.K) * kPrStagedWarps > cap) ns--;
-  const size_t smem = pr_staged_warp_bytes(ns, W, a.K) * kPrStagedWarps;
+  int ns = 4, nw = kPrStagedWarps;
+  const char* enw = getenv("HHFM_PR_WARPS");               // 7 .. 10 warps per CTA (A/B runs)
+  if (enw) { const int v = atoi(enw); if (v >= 7 && v <= 10) nw = v; }
+  const char* ens = getenv("HHFM_PR_STAGES");
+  if (ens && ens[0] >= '2' && ens[0] <= '4') ns = ens[0] - '0';
+  while (ns > 2 && pr_staged_warp_bytes(ns, W, a.K) * nw > cap) ns--;
+  const size_t smem = pr_staged_warp_bytes(ns, W, a.K) * nw;
   if (smem > cap) return HHFM_ERR_UNSUPPORTED;
   const int grid = sm_count();
   if (grid > kPartials) return HHFM_ERR_UNSUPPORTED;
   cudaError_t e = cudaSuccess;
-  if (ns == 4) {
-    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<4><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
-  } else if (ns == 3) {
-    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<3><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<2><<<grid, kPrStagedWarps * 32, smem, st>>>(a);
-  }
+#define HHFM_LAUNCH_PR(NS_, NW_)                                                                                                  \
+  do {                                                                                                                            \
+    e = cudaFuncSetAttribute(pairrank_sum_train_staged_kernel<NS_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) pairrank_sum_train_staged_kernel<NS_, NW_><<<grid, NW_ * 32, smem, st>>>(a);                             \
+  } while (0)
+#define HHFM_LAUNCH_PR_NS(NW_)                                                                                                    \
+  do {                                                                                                                            \
+    if (ns == 4) HHFM_LAUNCH_PR(4, NW_);                                                                                          \
+    else if (ns == 3) HHFM_LAUNCH_PR(3, NW_);                                                                                     \
+    else HHFM_LAUNCH_PR(2, NW_);                                                                                                  \
+  } while (0)
+  if (nw == 7) HHFM_LAUNCH_PR_NS(7);
+  else if (nw == 8) HHFM_LAUNCH_PR_NS(8);
+  else if (nw == 9) HHFM_LAUNCH_PR_NS(9);
+  else HHFM_LAUNCH_PR_NS(10);
+#undef HHFM_LAUNCH_PR_NS
+#undef HHFM_LAUNCH_PR
   if (e != cudaSuccess) {
     set_error("pairrank_sum_train_staged_kernel: %s", cudaGetErrorString(e));
     return HHFM_ERR_LAUNCH;
