@@ -6,7 +6,7 @@ import torch
 
 from hhfm_b200 import engine
 from hhfm_b200.models import CARS2  # noqa: F401
-from hhfm_b200.trainer import PairwiseTrain, default_result_file
+from hhfm_b200.trainer import PairwiseTrain, default_result_file, shuffle_rows
 from hhfm_b200.Newcode import NewLoadData as DATA
 
 method = 'CARS2'
@@ -66,7 +66,7 @@ class Train(PairwiseTrain):
 
     def run_epoch(self):
         pos = self._train_values()[:, 1:]                    # persistent view: the in-place shuffle composes across epochs
-        np.random.shuffle(pos)                               # CARS2.py:247
+        shuffle_rows(pos)                                    # CARS2.py:247 np.random.shuffle
         neg = self.sample_negative(pos, self.NG)
         fea = self.context_ids(pos)
         loss = 0

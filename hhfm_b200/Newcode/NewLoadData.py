@@ -80,10 +80,37 @@ class LoadData(object):
         uk = self._key_lookup_keys
         if len(uk) == 0:
             return np.full(len(rows), -1, dtype=np.int64)
-        # lexicographic search through a structured view
+        # 64-bit hash of the key columns -> binary search among the sorted hashes of the known keys -> verify the columns.
+        # (A lexicographic searchsorted through a structured view gives the same ids but costs 50 ms per 10^5 rows: numpy
+        # compares structured elements field by field in Python-object speed.)  Rows whose hash matches a different key --
+        # a collision, or a run of equal hashes -- take the structured search.
+        if getattr(self, "_key_hash", None) is None:
+            h = self._hash_rows(np.ascontiguousarray(uk))
+            self._key_hash_order = np.argsort(h, kind="stable")
+            self._key_hash = h[self._key_hash_order]
+        hq = self._hash_rows(q)
+        p = np.clip(np.searchsorted(self._key_hash, hq), 0, len(uk) - 1)
+        cand = self._key_hash_order[p]
+        hit = (uk[cand] == q).all(axis=1)
+        out = np.where(hit, cand, -1).astype(np.int64)
+        redo = np.nonzero(~hit & (self._key_hash[p] == hq))[0]
+        if len(redo):
+            out[redo] = self._key_ids_lexicographic(q[redo])
+        return out
+
+    @staticmethod
+    def _hash_rows(K):
+        h = np.zeros(len(K), dtype=np.uint64)
+        for j in range(K.shape[1]):
+            h = (h ^ (K[:, j].astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))) * np.uint64(0xBF58476D1CE4E5B9)
+            h ^= h >> np.uint64(29)
+        return h
+
+    def _key_ids_lexicographic(self, q):
+        uk = self._key_lookup_keys
         dt = np.dtype([("f%d" % i, np.int64) for i in range(uk.shape[1])])
         ukv = np.ascontiguousarray(uk).view(dt).reshape(-1)
-        qv = q.view(dt).reshape(-1)
+        qv = np.ascontiguousarray(q).view(dt).reshape(-1)
         pos = np.searchsorted(ukv, qv)
         pos = np.clip(pos, 0, len(ukv) - 1)
         hit = ukv[pos] == qv

@@ -8,7 +8,7 @@ from time import time
 import numpy as np
 
 from hhfm_b200.models import WD  # noqa: F401
-from hhfm_b200.trainer import BaseTrain, default_result_file
+from hhfm_b200.trainer import BaseTrain, default_result_file, shuffle_rows
 from hhfm_b200.Newcode import NewLoadData as DATA
 
 method = 'WD'
@@ -79,7 +79,7 @@ class Train(BaseTrain):
         neg[:, 2] = self.sample_negative(pos[:, 1:], self.OUTER_NEGATIVES).ravel()
         neg[:, 0] = 0
         rows = np.concatenate([pos, neg], axis=0)
-        np.random.shuffle(rows)
+        shuffle_rows(rows)                                   # np.random.shuffle, same permutation and generator state
         return rows[:, 1:].astype(np.int64), rows[:, 0]
 
     def train(self):

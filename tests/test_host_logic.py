@@ -171,3 +171,26 @@ def test_dropin_parse_args_keep_the_reference_defaults():
         assert a.dataset == "frappe" and int(a.TopK) == 5, name
         for k, v in defaults.items():
             assert getattr(a, k) == v, (name, k, getattr(a, k), v)
+
+
+def test_shuffle_rows_is_numpy_shuffle_bit_for_bit():
+    """trainer.shuffle_rows replaces np.random.shuffle on the 2-D id tables (FM.py:250, OurModel7.py:370): same rows, same
+    generator state afterwards, also on a column view of a wider array."""
+    from hhfm_b200.trainer import shuffle_rows
+    a = np.arange(5000 * 7).reshape(5000, 7).astype(np.int64)
+    b = a.copy()
+    np.random.seed(123); np.random.shuffle(a[:, 1:]); sa = np.random.get_state()[1].copy(); ra = np.random.rand()
+    np.random.seed(123); perm = shuffle_rows(b[:, 1:]); sb = np.random.get_state()[1].copy(); rb = np.random.rand()
+    assert np.array_equal(a, b) and np.array_equal(sa, sb) and ra == rb
+    assert np.array_equal(np.arange(5000 * 7).reshape(5000, 7)[perm][:, 1:], b[:, 1:])
+
+
+def test_key_ids_hash_lookup_equals_the_lexicographic_search(data_root):
+    ld = load(data_root, "frappe")
+    rows = np.concatenate([np.array(ld.Train_data.values[:, 1:]), np.array(ld.Test_data.values[:, 1:])])
+    unknown = rows[:50].copy(); unknown[:, 0] = 10 ** 7          # a user that never trained
+    rows = np.concatenate([rows, unknown])
+    kc = [c - 1 for c in ld.key_cols]
+    want = ld._key_ids_lexicographic(np.ascontiguousarray(rows[:, kc]))
+    got = ld.key_ids(rows)
+    assert np.array_equal(got, want) and (got[-50:] == -1).all() and (got[:-50] >= 0).sum() > 0
