@@ -513,3 +513,37 @@ def test_models_match_committed_golden_vectors(cuda):
     c2.load_weights({k: g["cars2_w_" + k] for k in ("UI", "Context", "W", "Z", "A", "B")})
     fb = c2.sess.run(c2.PositiveFeadback, feed_dict={c2.Pos: X[:, :2], c2.Fea: g["cars2_Fea"]})
     assert_close(fb[:, 0], g["cars2_feedback"], rtol=2e-5, what="golden cars2 PositiveFeadback")
+
+
+def test_cars2_momentum_without_l2_raises_instead_of_moving_untouched_rows(cuda):
+    """CARS2.py with lamda == 0 gives UI / Context IndexedSlices gradients, i.e. TF's SparseApplyMomentum; the dense Momentum
+    kernel would keep moving untouched rows, so the combination must refuse to run."""
+    from hhfm_b200.models import CARS2
+    rng = np.random.default_rng(0)
+    n_user, n_item, M, D, B = 20, 30, 10, 20, 64
+    model = CARS2(M, n_user, n_item, D, 0.05, 0.0, 'MomentumOptimizer')
+    Pos = np.stack([rng.integers(0, n_user, B), n_user + rng.integers(0, n_item, B)], axis=1)
+    with pytest.raises(NotImplementedError):
+        model.partial_fit({"X": Pos, "F1": rng.integers(0, M, B), "Y": n_user + rng.integers(0, n_item, (B, 2))})
+
+
+def test_invalidate_drops_the_cached_item_operand_after_an_in_place_weight_edit(cuda):
+    """The tensor-core top-N caches the bf16 item operand per weight version; `invalidate()` is the hook for edits of
+    `model.weights[...]` that bypass the training step."""
+    import torch
+    from hhfm_b200.models import BPR
+    rng = np.random.default_rng(3)
+    n_user, n_item, K, C = 64, 4000, 64, 1100
+    m = BPR(n_user + n_item, n_user, n_item, K, 0.05, 0.0, 'AdagradOptimizer')
+    m.topn_method = "tc"
+    A = np.stack([rng.integers(0, n_user, C), n_user + rng.integers(0, n_item, C)], axis=1)
+    V = m.get_weights()["feature_embeddings"]
+    first = m.topk(A, 10)
+    assert (first == O.topk_lowest_index(V[A[:, 0]] @ V[n_user:].T, 10)).mean() > 0.99      # fp32 order of the dot products aside
+    with torch.no_grad():
+        m.weights["feature_embeddings"][n_user:] *= -1.0
+    m.invalidate()
+    second = m.topk(A, 10)
+    V2 = m.get_weights()["feature_embeddings"]
+    assert (second == O.topk_lowest_index(V2[A[:, 0]] @ V2[n_user:].T, 10)).mean() > 0.99
+    assert (first != second).mean() > 0.9
