@@ -36,6 +36,42 @@ def peaks():
     return 6650.0
 
 
+_L2_PEAK = {}
+
+
+def l2_peak(dev):
+    """L2 -> SM read bandwidth measured in this process (hhfm_l2_read_sweep over an L2-resident 48 MB buffer), GB/s: the
+    roofline denominator of the shapes whose table lives in L2 (an HBM fraction above 1 says nothing there)."""
+    if "v" not in _L2_PEAK:
+        import torch
+        from hhfm_b200 import _lib
+        from hhfm_b200.engine import cur_stream, ptr
+        n = (48 << 20) // 4
+        buf = torch.ones(n, dtype=torch.float32, device=dev)
+        sink = torch.zeros(1, dtype=torch.float32, device=dev)
+        _lib.call("hhfm_l2_read_sweep", ptr(buf), n, 4, ptr(sink), cur_stream())
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("hhfm_l2_read_sweep", ptr(buf), n, 20, ptr(sink), cur_stream())
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 4.0 * n * 20 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        _L2_PEAK["v"] = best
+    return _L2_PEAK["v"]
+
+
+def l2_roofline(B, algo, ms, dev):
+    ach = B * algo / ms / 1e6
+    pk = l2_peak(dev)
+    return {"bound": "l2", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk,
+            "peak_source": "hhfm_l2_read_sweep, measured in this run", "frac_of_hbm_peak_by_algorithmic_bytes": ach / peaks(),
+            "note": "the table and the hot-row replicas are L2 / L1 resident at this shape: only the id records stream from HBM, so "
+                    "the algorithmic bytes are compared with the measured L2 read bandwidth (a part of them is served by L1)"}
+
+
 def zipf_ids(rng, n, size, a=1.1):
     # inverse-CDF sampling of a truncated Zipf without materialising n probabilities for huge n
     if n <= 1 << 16:
@@ -86,8 +122,7 @@ def run_fm_c1(args, dev):
     algo = 2648 + 2600
     return {"config": "c1 FM frappe-10 (F=10, M=%d, K=64, dense-L2 Adagrad), B=2^20" % M, "ms_per_step": ms,
             "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
-            "roofline": {"bound": "hbm", "achieved_gbs": B * algo / ms / 1e6, "peak_gbs": peaks(),
-                         "frac": B * algo / ms / 1e6 / peaks(), "note": "table L2-resident at this shape"}}
+            "roofline": l2_roofline(B, algo, ms, dev)}
 
 
 def run_fm_c5(args, dev):
@@ -223,8 +258,7 @@ def run_bpr_c4(args, dev):
     algo = 12 * 4 * K + 48 + 3 * 4 * K
     return {"config": "c4 BPR restaurant shape (M=7730, N=580, K=128, NG=10, dense-L2 Adagrad), B=2^20",
             "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "algorithmic_bytes_per_sample": algo,
-            "roofline": {"bound": "hbm", "achieved_gbs": B * algo / ms / 1e6, "peak_gbs": peaks(),
-                         "frac": B * algo / ms / 1e6 / peaks(), "note": "table L2-resident at this shape"}}
+            "roofline": l2_roofline(B, algo, ms, dev)}
 
 
 def run_afm_c3(args, dev):
