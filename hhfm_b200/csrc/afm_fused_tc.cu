@@ -26,7 +26,8 @@
 // The column sums over the tile rows (d attention_b, d attention_p, d prediction_W) are deferred: one butterfly step per
 // tile into 8 registers, issued behind GEMM 2 / 3, finished once at the end of the kernel.
 // The embedding rows (+ bias values, hot-row slots) of tile t+1 are fetched with cp.async into a second staging buffer
-// behind GEMM 1 of tile t; ids and labels are loaded two / one tile ahead.  Five CTA-wide barriers per tile.
+// two tiles ahead (three buffers); ids three tiles ahead (ring of four).  Three CTA-wide barriers per tile; the scatter of
+// tile t and the PT build of tile t+1 are not separated by one.
 //
 // Shapes covered: K == A == 64, F <= 11 (P <= 55 pairs).  Everything else stays on the fp32 SIMT kernels (afm.cu).
 #include <stdlib.h>
@@ -69,7 +70,7 @@ struct Misc {
   float g[2], bsum[2];
   float biasv[3][2][kMaxF + 1];   // [buffer][slot][field] feature_bias values of the staged rows
   int hslot[3][2][kMaxF + 1];     // [buffer][slot][field] hot-row slot of the staged rows (-1: none)
-  int ids[3][2][kMaxF + 1];       // [buffer][slot][field]
+  int ids[4][2][kMaxF + 1];       // [ring slot][slot][field]: four deep, so the ids of tile t+2 never land on a slot a scatter still reads
   unsigned char pi[kSlot], pj[kSlot];
   unsigned char pidx[kMaxF][kMaxF + 1];
   uint64_t bar1, bar2, bar3;    // GEMM 1 | GEMM 2 | GEMM 3 complete
@@ -246,11 +247,11 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     const int64_t s = 2 * t + tid / F;
     return (s < a.B) ? __ldg(a.idx + s * F + tid % F) : -1;
   };
-  auto stage_rows = [&](int buf) {          // rows of the tile whose ids are in mi.ids[buf] -> EsBuf[buf], biasv[buf], hslot[buf]
+  auto stage_rows = [&](int buf, int islot) {   // rows of the tile whose ids are in mi.ids[islot] -> EsBuf[buf], biasv[buf], hslot[buf]
     float* Es = EsBuf + buf * (kEBytes / 4);
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
-      const int id = mi.ids[buf][s2][f];
+      const int id = mi.ids[islot][s2][f];
       float* dst = Es + (s2 * kMaxF + f) * kEP + 4 * c;
       if (id >= 0) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(a.V + (size_t)id * KD + 4 * c) : "memory");
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     umma_commit(&mi.bar1);
   };
   const int64_t g_tiles = gridDim.x;
-  int buf = 0, par = 0;
+  int buf = 0, par = 0, islot = 0;      // staging buffer (mod 3), u_part parity, ids ring slot (mod 4) of the current tile
   {
     const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + g_tiles);
     if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
       for (int q = 0; q < 3; q++) { mi.biasv[q][s2][f] = 0.f; mi.hslot[q][s2][f] = -1; }
     }
     __syncthreads();
-    stage_rows(0);
-    stage_rows(1);
+    stage_rows(0, 0);
+    stage_rows(1, 1);
     ldgsts_wait<1>();                       // the first tile's rows
     __syncthreads();
     build_p_tmem(EsBuf, 0);
@@ -334,8 +335,10 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     const int nb = (buf == 2) ? 0 : buf + 1, nnb = (nb == 2) ? 0 : nb + 1;
     const float* Es = EsBuf + buf * (kEBytes / 4);
     const bool has_next = t + g_tiles < n_tiles;
-    __syncthreads();            // T: the previous tile's scatter is done with its rows, ids and dP rows
-    if (tid < 2 * F) mi.ids[nnb][tid / F][tid % F] = id_reg;
+    // No barrier here: warps that are done with the previous tile's scatter start on this tile's PT tiles while the others
+    // finish.  Everything the scatter still reads (its staged rows, hot slots, ids, the dP rows, mi.g) is next written after
+    // barrier (3) below, except the ids -- hence the four-deep ring: slot + 2 was last read two tiles ago.
+    if (tid < 2 * F) mi.ids[(islot + 2) & 3][tid / F][tid % F] = id_reg;
     id_reg = load_id(t + 3 * g_tiles);
     const int64_t smp = 2 * t + ss;
     const float label = (smp < a.B) ? __ldg(a.labels + smp) : 0.f;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
     ldgsts_wait<0>();           // the next tile's rows (staged one tile ago)
     __syncthreads();
-    if (t + 2 * g_tiles < n_tiles) stage_rows(nnb);
+    if (t + 2 * g_tiles < n_tiles) stage_rows(nnb, (islot + 2) & 3);
     // Every warp works out the softmax of its sample slot by itself: lane l looks at the slot's pairs l and l + 32.
     float c_r, ds;
     {
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     // dE_f = sum_{j != f} dP_(f,j) * E_j ; one vector reduction per 16 bytes of the gradient row
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
-      const int id = mi.ids[buf][s2][f];
+      const int id = mi.ids[islot][s2][f];
       if (id < 0) continue;
       float4 acc = f4_zero();
 #pragma unroll
@@ -526,6 +529,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
     buf = nb;
     par ^= 1;
+    islot = (islot + 1) & 3;
   }
 
   ldgsts_wait<0>();
