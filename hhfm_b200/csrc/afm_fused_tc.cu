@@ -25,9 +25,10 @@
 // its accumulator with truncation, see dfm_tc.cu); the threads add their registers into the global gradient once at the end.
 // The column sums over the tile rows (d attention_b, d attention_p, d prediction_W) are deferred: one butterfly step per
 // tile into 8 registers, issued behind GEMM 2 / 3, finished once at the end of the kernel.
-// The embedding rows (+ bias values, hot-row slots) of tile t+1 are fetched with cp.async into a second staging buffer
-// two tiles ahead (three buffers); ids three tiles ahead (ring of four).  Three CTA-wide barriers per tile; the scatter of
-// tile t and the PT build of tile t+1 are not separated by one.
+// Pipeline: the embedding rows (+ bias values, hot-row slots) are fetched with cp.async two tiles ahead (three staging
+// buffers), the ids three tiles ahead (ring of four); GEMM 1 of tile t+1 is issued before the scatter of tile t, its A
+// operand (P of tile t+1 in TMEM) is built behind GEMM 2 / 3 of tile t; GEMM 2 and GEMM 3 complete on separate mbarriers.
+// Three CTA-wide barriers per tile; the scatter of tile t and the PT build of tile t+1 are not separated by one.
 //
 // Shapes covered: K == A == 64, F <= 11 (P <= 55 pairs).  Everything else stays on the fp32 SIMT kernels (afm.cu).
 #include <stdlib.h>
