@@ -176,15 +176,16 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const DpArgs a) {
         const int s = __ldg(a.hot_slot + i / kv);
         if (s >= 0) {
           const int c = (int)(i % kv);
-          for (int r0 = 0; r0 < a.n_rep; r0 += 8) {
-            float4 t[8];
+          constexpr int kFoldBatch = 16;            // replica loads in flight per thread (the fold is the long pole of phase A)
+          for (int r0 = 0; r0 < a.n_rep; r0 += kFoldBatch) {
+            float4 t[kFoldBatch];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < kFoldBatch; q++) {
               float4* p = reinterpret_cast<float4*>(a.ghot + ((size_t)(r0 + q) * a.n_hot + s) * a.K) + c;
               t[q] = (r0 + q < a.n_rep) ? *p : f4_zero();
             }
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < kFoldBatch; q++) {
               if (r0 + q < a.n_rep) {
                 v = f4_add(v, t[q]);
                 *(reinterpret_cast<float4*>(a.ghot + ((size_t)(r0 + q) * a.n_hot + s) * a.K) + c) = f4_zero();
