@@ -202,10 +202,17 @@ __global__ void __launch_bounds__(kDpThreads) dp_step_kernel(const DpArgs a) {
           const int s = __ldg(a.hot_slot + f);
           if (s < 0) continue;
           float acc = 0.f;
-          for (int r = 0; r < a.n_rep; r++) {
-            float* p = a.ghot_bias + (size_t)r * a.n_hot + s;
-            acc += *p;
-            *p = 0.f;
+          for (int r0 = 0; r0 < a.n_rep; r0 += 16) {        // 16 loads in flight, added in replica order
+            float t[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) t[q] = (r0 + q < a.n_rep) ? a.ghot_bias[(size_t)(r0 + q) * a.n_hot + s] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+              if (r0 + q < a.n_rep) {
+                acc += t[q];
+                a.ghot_bias[(size_t)(r0 + q) * a.n_hot + s] = 0.f;
+              }
+            }
           }
           vv[j] += acc;
         }
