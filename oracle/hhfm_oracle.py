@@ -747,6 +747,27 @@ def adagrad_rows(w, acc, g, rows, lr):
     return w, acc
 
 
+def adagrad_dense_l2(w, acc, g, lr, lamda):
+    """The reference's dense step on a regularised table (FM.py:124,132): g_eff = g + lamda * w, then ApplyAdagrad."""
+    ge = (_f32(g) + (F32(lamda) * _f32(w)).astype(F32)).astype(F32)
+    return adagrad_dense(w, acc, ge, lr)
+
+
+def adagrad_l2_lazy_replay(w, acc, last_step, rows, upto, lr, lamda):
+    """Lazy-exact dense L2 (hard part 2-ii; csrc/opt.cu adagrad_l2_replay_kernel): a row that no batch gathered at
+    steps last_step+1 .. upto saw g = 0 there, i.e. g_eff = lamda * w, a recurrence of the row alone.  Replays those steps for
+    `rows` (None = every row) and stamps them with `upto`; the result has the bits the dense schedule would have produced."""
+    w = _f32(w).copy(); acc = _f32(acc).copy(); last_step = np.asarray(last_step).copy()
+    rows = np.arange(len(w)) if rows is None else np.asarray(rows)
+    for r in rows:
+        for _ in range(int(upto) - int(last_step[r])):
+            ge = (F32(lamda) * w[r]).astype(F32)
+            acc[r] = (acc[r] + (ge * ge).astype(F32)).astype(F32)
+            w[r] = (w[r] - (F32(lr) * ge / np.sqrt(acc[r])).astype(F32)).astype(F32)
+        last_step[r] = upto
+    return w, acc, last_step
+
+
 def adam_dense(w, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
     """TF1 AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); var -= lr_t*m/(sqrt(v)+eps).  The sparse path
     (`_apply_sparse_shared`) decays m,v of every row and moves every row, i.e. equals this with zero rows."""

@@ -229,3 +229,29 @@ def test_wd_gradients_match_autograd_and_ftrl_reduces_to_adagrad():
     assert np.allclose(w1, wa, rtol=1e-6, atol=1e-9) and np.allclose(a1, aa)
     w2, _, _ = O.ftrl_dense(w1, a1, z1, gg, 0.135, l1=10.0)
     assert (w2 == 0).all()                                   # |z| <= l1 clips to exactly zero
+
+
+def test_lazy_dense_l2_schedule_is_bit_identical_to_the_dense_schedule():
+    """SURVEY.md 7 hard part 2-ii on the CPU: every step the dense schedule moves EVERY row with g + lamda*w (FM.py:124,132);
+    the lazy schedule replays a row's missed `g = lamda*w` steps when a batch gathers it (and at the final flush), then applies
+    the step with the batch gradient.  Same fp32 operations in the same order per row -> the same bits."""
+    rng = np.random.default_rng(17)
+    M, K, lr, lam, steps = 40, 8, np.float32(0.1), np.float32(0.05), 12
+    w0 = rng.normal(0, 0.3, (M, K)).astype(np.float32)
+    a0 = np.full((M, K), 0.1, np.float32)
+    touched = [np.unique(rng.integers(0, M, rng.integers(0, 9))) for _ in range(steps)]
+    grads = [rng.normal(0, 0.2, (len(t), K)).astype(np.float32) for t in touched]
+    # dense schedule
+    wd, ad = w0.copy(), a0.copy()
+    for t, g in zip(touched, grads):
+        G = np.zeros((M, K), np.float32); G[t] = g
+        wd, ad = O.adagrad_dense_l2(wd, ad, G, lr, lam)
+    # lazy schedule
+    wl, al, last = w0.copy(), a0.copy(), np.zeros(M, np.int64)
+    for step, (t, g) in enumerate(zip(touched, grads), start=1):
+        wl, al, last = O.adagrad_l2_lazy_replay(wl, al, last, t, step - 1, lr, lam)         # bring the gathered rows to step-1
+        if len(t):
+            wl[t], al[t] = O.adagrad_dense_l2(wl[t], al[t], g, lr, lam)
+            last[t] = step
+    wl, al, last = O.adagrad_l2_lazy_replay(wl, al, last, None, steps, lr, lam)              # flush
+    assert np.array_equal(wd, wl) and np.array_equal(ad, al) and (last == steps).all()
