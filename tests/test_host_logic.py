@@ -194,3 +194,47 @@ def test_key_ids_hash_lookup_equals_the_lexicographic_search(data_root):
     want = ld._key_ids_lexicographic(np.ascontiguousarray(rows[:, kc]))
     got = ld.key_ids(rows)
     assert np.array_equal(got, want) and (got[-50:] == -1).all() and (got[:-50] >= 0).sum() > 0
+
+
+def test_pipelined_fit_adds_the_losses_in_batch_order_with_and_without_the_async_call():
+    """trainer._PipelinedFit (the epoch loop `loss = loss + model.partial_fit(batch)`, FM.py:251-256, with one step in flight):
+    a model that only has the blocking call is driven synchronously; with `partial_fit_async` every result is collected exactly
+    once, in order, and at most one step is outstanding."""
+    from hhfm_b200.trainer import _PipelinedFit
+
+    class Blocking:
+        def __init__(self):
+            self.seen = []
+
+        def partial_fit(self, d):
+            self.seen.append(d)
+            return float(d)
+
+    class Pending:
+        def __init__(self, owner, v):
+            self.owner, self.v = owner, v
+
+        def result(self):
+            self.owner.collected.append(self.v)
+            self.owner.outstanding -= 1
+            return float(self.v)
+
+    class Async(Blocking):
+        def __init__(self):
+            super().__init__()
+            self.collected, self.outstanding, self.max_outstanding = [], 0, 0
+
+        def partial_fit_async(self, d):
+            self.seen.append(d)
+            self.outstanding += 1
+            self.max_outstanding = max(self.max_outstanding, self.outstanding)
+            return Pending(self, d)
+
+    batches = [3, 1, 4, 1, 5, 9, 2, 6]
+    for model in (Blocking(), Async()):
+        fit = _PipelinedFit(model)
+        for b in batches:
+            fit(b)
+        assert fit.total() == float(sum(batches)) and model.seen == batches
+        assert fit.total() == float(sum(batches))                  # idempotent: nothing left to collect
+    assert model.collected == batches and model.max_outstanding == 2 and model.outstanding == 0
