@@ -36,6 +36,15 @@ def peaks():
     return 6650.0
 
 
+def _traffic(kernel):
+    """DRAM bytes per launch of `kernel` and the ncu capture they come from (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel) or {}
+    return d.get("dram_bytes_per_launch"), d.get("capture")
+
+
 _L2_PEAK = {}
 
 
@@ -195,7 +204,11 @@ def run_hhfm_c5(args, dev):
             "roofline": {"bound": "hbm", "kernel": "pairrank_sum_train_staged_kernel + opt_rows_kernel (whole step)",
                          "achieved": B * algo / ms / 1e6, "peak": peaks(), "unit": "GB/s", "frac": B * algo / ms / 1e6 / peaks(),
                          "frac_of_nominal_8000_gbs": B * algo / ms / 1e6 / 8000.0,
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)"}}
+                         "traffic": _traffic("pairrank_sum_train_staged_kernel")[0],
+                         "traffic_capture": _traffic("pairrank_sum_train_staged_kernel")[1],
+                         "traffic_note": "DRAM bytes per launch of the scatter kernel alone (16.7 GB algorithmic): the vector "
+                                         "reductions into DRAM-resident gradient lines are read-modify-writes",
+                         "peak_source": "measured (MEASURED_PEAKS.json)"}}
 
 
 def run_fm_c5_l2(args, dev):
