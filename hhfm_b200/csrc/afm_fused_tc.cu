@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
   constexpr int kThreads = 128 * NQ;
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an offset from the __shared__ symbol (not an integer round trip of the pointer): the compiler keeps
+  // the address space and emits LDS / STS instead of generic LD / ST for every access below
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Misc& mi = *reinterpret_cast<Misc*>(smem + oMisc);
   float* EsBuf = reinterpret_cast<float*>(smem + oE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
