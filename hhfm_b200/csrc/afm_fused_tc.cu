@@ -177,6 +177,12 @@ template <int NQ>
 __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs a, const int64_t n_tiles) {
   constexpr int CW = KD / NQ;
   constexpr int kThreads = 128 * NQ;
+  // The three products are issued by lane 0 of three DIFFERENT warps, the last ones of the CTA: they have no share of the
+  // embedding scatter (its items go to threads 0..351) while warp 0 has that plus the id bookkeeping, and every product
+  // completes on its own mbarrier (a commit covers the issuing thread's MMAs), so nothing orders the issuers among themselves.
+  // Issued by thread 0 the ~400 issue instructions of a tile were serial on the slowest warp: 3.62 -> 3.42 ms for one issuer
+  // in the last warp.
+  constexpr int kIssuer2 = kThreads - 32, kIssuer3 = kThreads - 64, kIssuer1 = (NQ == 4) ? kThreads - 96 : kThreads - 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ float scratch[32];
   // 1024-byte alignment by an offset from the __shared__ symbol (not an integer round trip of the pointer): the compiler keeps
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     build_p_tmem(EsBuf, 0);
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) { tc_fence_after(); issue_gemm1(); }
+    if (tid == kIssuer1) { tc_fence_after(); issue_gemm1(); }
   }
   int id_reg = load_id((int64_t)blockIdx.x + 2 * g_tiles);      // ids of the tile after next, stored at the top of the next tile
   uint32_t ph1 = 0, ph2 = 0;
@@ -446,7 +452,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == kIssuer2) {
       tc_fence_after();
       const uint32_t idesc = make_idesc_tf32(kRows, KD);
 #pragma unroll
@@ -460,6 +466,10 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
           umma_tf32_ts(tmem + cDP, tmem + cZX + kc, make_sdesc(bx), idesc, 1u);
         }
       umma_commit(&mi.bar2);
+    }
+    if (tid == kIssuer3) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_tf32(kRows, KD);
       // dW: reduction over the 128 tile rows = 4 r blocks x 4 k-steps of 8; A = [PT x ; PT lo] (M = 128), B = dZT x, dZT lo
 #pragma unroll
       for (int rb = 0; rb < 4; rb++)
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     }
     tc_fence_before();
     __syncthreads();
-    if (tid == 0 && has_next) { tc_fence_after(); issue_gemm1(); }      // GEMM 1 of the next tile runs behind the scatter below
+    if (tid == kIssuer1 && has_next) { tc_fence_after(); issue_gemm1(); }      // GEMM 1 of the next tile runs behind the scatter below
     // dE_f = sum_{j != f} dP_(f,j) * E_j ; one vector reduction per 16 bytes of the gradient row
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
       const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
