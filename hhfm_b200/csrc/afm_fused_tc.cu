@@ -251,10 +251,14 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
   for (int i = 0; i < 8; i++) { gb8[i] = 0.f; gp8[i] = 0.f; gw8[i] = 0.f; }
 
   // ---- staging pipeline (three buffers): ids three tiles ahead, embedding rows + bias values + hot slots two tiles ahead ----
+  // id bookkeeping (load the ids of a tile three tiles ahead, store them, sum the bias values) by a warp that has neither
+  // scatter items nor an issuer role when there is one (16 warps: warp 12)
+  constexpr int kBook0 = (NQ == 4) ? kThreads - 128 : 0;
+  const int bt = tid - kBook0;                  // 0 .. 2F-1: (sample slot, field) of this thread's id
   auto load_id = [&](int64_t t) {
-    if (tid >= 2 * F || t >= n_tiles) return -1;
-    const int64_t s = 2 * t + tid / F;
-    return (s < a.B) ? __ldg(a.idx + s * F + tid % F) : -1;
+    if (bt < 0 || bt >= 2 * F || t >= n_tiles) return -1;
+    const int64_t s = 2 * t + bt / F;
+    return (s < a.B) ? __ldg(a.idx + s * F + bt % F) : -1;
   };
   auto stage_rows = [&](int buf, int islot) {   // rows of the tile whose ids are in mi.ids[islot] -> EsBuf[buf], biasv[buf], hslot[buf]
     float* Es = EsBuf + buf * (kEBytes / 4);
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
   int buf = 0, par = 0, islot = 0;      // staging buffer (mod 3), u_part parity, ids ring slot (mod 4) of the current tile
   {
     const int id0 = load_id(blockIdx.x), id1 = load_id((int64_t)blockIdx.x + g_tiles);
-    if (tid < 2 * F) { mi.ids[0][tid / F][tid % F] = id0; mi.ids[1][tid / F][tid % F] = id1; }
+    if (bt >= 0 && bt < 2 * F) { mi.ids[0][bt / F][bt % F] = id0; mi.ids[1][bt / F][bt % F] = id1; }
     if (tid < 2 * (kMaxF + 1)) {
       const int s2 = tid / (kMaxF + 1), f = tid % (kMaxF + 1);
 #pragma unroll
@@ -347,14 +351,14 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     // No barrier here: warps that are done with the previous tile's scatter start on this tile's PT tiles while the others
     // finish.  Everything the scatter still reads (its staged rows, hot slots, ids, the dP rows, mi.g) is next written after
     // barrier (3) below, except the ids -- hence the four-deep ring: slot + 2 was last read two tiles ago.
-    if (tid < 2 * F) mi.ids[(islot + 2) & 3][tid / F][tid % F] = id_reg;
+    if (bt >= 0 && bt < 2 * F) mi.ids[(islot + 2) & 3][bt / F][bt % F] = id_reg;
     id_reg = load_id(t + 3 * g_tiles);
     const int64_t smp = 2 * t + ss;
     const float label = (smp < a.B) ? __ldg(a.labels + smp) : 0.f;
-    if (tid < 2) {
+    if (bt == 30 || bt == 31) {                  // two more lanes of the bookkeeping warp (2 F <= 22)
       float bs = 0.f;
-      for (int f = 0; f < F; f++) bs += mi.biasv[buf][tid][f];
-      mi.bsum[tid] = bs;
+      for (int f = 0; f < F; f++) bs += mi.biasv[buf][bt - 30][f];
+      mi.bsum[bt - 30] = bs;
     }
     // ---- phase 1: the K-major PT tiles (A of GEMM 3; GEMM 3 of the previous tile is complete) ----
     {
