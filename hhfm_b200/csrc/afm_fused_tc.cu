@@ -250,6 +250,18 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
 #pragma unroll
   for (int i = 0; i < 8; i++) { gb8[i] = 0.f; gp8[i] = 0.f; gw8[i] = 0.f; }
 
+  // 16 warps: thread i < 2 F 16 owns the same (sample slot, field, 16-byte chunk) item of the staging and of the embedding
+  // scatter in every tile -- its decomposition (two integer divisions by the runtime F) and the tile rows of its F - 1 pairs
+  // are worked out once; rows are packed four per register
+  const bool it_on = NQ == 4 && tid < 2 * F * (KD / 4);
+  const int it_s2 = it_on ? tid / (F * (KD / 4)) : 0, it_rem = it_on ? tid % (F * (KD / 4)) : 0;
+  const int it_f = it_rem / (KD / 4), it_c = it_rem % (KD / 4);
+  uint32_t it_rows[3] = {0u, 0u, 0u};
+  if (it_on) {
+#pragma unroll
+    for (int j = 0; j < kMaxF; j++)
+      if (j < F && j != it_f) it_rows[j >> 2] |= (uint32_t)(it_s2 * kSlot + mi.pidx[it_f][j]) << (8 * (j & 3));
+  }
   // ---- staging pipeline (three buffers): ids three tiles ahead, embedding rows + bias values + hot slots two tiles ahead ----
   // id bookkeeping (load the ids of a tile three tiles ahead, store them, sum the bias values) by a warp that has neither
   // scatter items nor an issuer role when there is one (16 warps: warp 12)
@@ -263,7 +275,9 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
   auto stage_rows = [&](int buf, int islot) {   // rows of the tile whose ids are in mi.ids[islot] -> EsBuf[buf], biasv[buf], hslot[buf]
     float* Es = EsBuf + buf * (kEBytes / 4);
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
-      const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
+      int s2, f, c;
+      if (NQ == 4) { s2 = it_s2; f = it_f; c = it_c; }
+      else { s2 = i / (F * (KD / 4)); const int rem = i % (F * (KD / 4)); f = rem / (KD / 4); c = rem % (KD / 4); }
       const int id = mi.ids[islot][s2][f];
       float* dst = Es + (s2 * kMaxF + f) * kEP + 4 * c;
       if (id >= 0) {
@@ -520,14 +534,16 @@ __global__ void __launch_bounds__(128 * NQ, 1) afm_fused_tc_kernel(const AfmArgs
     if (tid == kIssuer1 && has_next) { tc_fence_after(); issue_gemm1(); }      // GEMM 1 of the next tile runs behind the scatter below
     // dE_f = sum_{j != f} dP_(f,j) * E_j ; one vector reduction per 16 bytes of the gradient row
     for (int i = tid; i < 2 * F * (KD / 4); i += kThreads) {
-      const int s2 = i / (F * (KD / 4)), rem = i % (F * (KD / 4)), f = rem / (KD / 4), c = rem % (KD / 4);
+      int s2, f, c;
+      if (NQ == 4) { s2 = it_s2; f = it_f; c = it_c; }
+      else { s2 = i / (F * (KD / 4)); const int rem = i % (F * (KD / 4)); f = rem / (KD / 4); c = rem % (KD / 4); }
       const int id = mi.ids[islot][s2][f];
       if (id < 0) continue;
       float4 acc = f4_zero();
 #pragma unroll
       for (int j = 0; j < kMaxF; j++) {                       // unrolled: the loads of all terms are in flight together
         if (j >= F || j == f) continue;
-        const int r2 = s2 * kSlot + mi.pidx[f][j];
+        const int r2 = (NQ == 4) ? (int)((it_rows[j >> 2] >> (8 * (j & 3))) & 0xFFu) : s2 * kSlot + mi.pidx[f][j];
         const float4 dp = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem + oZ) + r2 * KD + 4 * (c ^ (r2 & 15)));
         const float4 e = *reinterpret_cast<const float4*>(Es + (s2 * kMaxF + j) * kEP + 4 * c);
         acc.x = fmaf(dp.x, e.x, acc.x); acc.y = fmaf(dp.y, e.y, acc.y); acc.z = fmaf(dp.z, e.z, acc.z); acc.w = fmaf(dp.w, e.w, acc.w);
